@@ -1,0 +1,119 @@
+"""ctypes binding of librltime_b200.so (the C ABI declared in include/rltime_b200.h).
+
+The product path has no CPU fallback: if the CUDA library is missing or fails to load,
+importing a device-backed component raises immediately.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librltime_b200.so")
+
+RT_OK = 0
+RT_NEED_MORE_DATA = 1
+RT_MAX_FIELDS = 16
+RT_BATCH_SLOTS = 3
+RT_KIND_UNIFORM = 0
+RT_KIND_PRIORITIZED = 1
+
+
+class RtError(RuntimeError):
+    pass
+
+
+class ReplayConfig(C.Structure):
+    _fields_ = [
+        ("size", C.c_int64), ("kind", C.c_int32), ("nstep_train", C.c_int32),
+        ("prefix_steps", C.c_int32), ("nstep_target", C.c_int32), ("overlap", C.c_int32),
+        ("global_importance_scaling", C.c_int32), ("gamma", C.c_double),
+        ("alpha", C.c_double), ("eps", C.c_double), ("max_weight_factor", C.c_double),
+        ("max_envs", C.c_int32), ("device", C.c_int32),
+        ("num_state_fields", C.c_int32), ("state_field_bytes", C.c_int64 * RT_MAX_FIELDS),
+        ("num_po_fields", C.c_int32), ("po_field_bytes", C.c_int64 * RT_MAX_FIELDS),
+    ]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("S", C.c_int32), ("n", C.c_int32),
+        ("num_state_fields", C.c_int32), ("num_po_fields", C.c_int32),
+        ("all_states", C.c_void_p * RT_MAX_FIELDS),
+        ("policy_outputs", C.c_void_p * RT_MAX_FIELDS),
+        ("returns", C.c_void_p), ("nsteps", C.c_void_p), ("target_masks", C.c_void_p),
+        ("importance_weights", C.c_void_p), ("loss_indices", C.c_void_p),
+        ("idxes", C.c_void_p), ("slots", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); also the list the CPU test checks against the header
+_VP = C.c_void_p
+SIGNATURES = {
+    "rt_last_error": (C.c_char_p, []),
+    "rt_version": (C.c_int, []),
+    "rt_launch_count": (C.c_int64, []),
+    "rt_replay_create": (C.c_int, [C.POINTER(ReplayConfig), C.POINTER(_VP)]),
+    "rt_replay_destroy": (None, [_VP]),
+    "rt_replay_append": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
+    "rt_replay_len": (C.c_int64, [_VP]),
+    "rt_replay_active_sequences": (C.c_int64, [_VP]),
+    "rt_replay_uniform_available": (C.c_int64, [_VP]),
+    "rt_replay_sample_prioritized": (C.c_int, [_VP, C.c_int32, C.c_double, _VP, _VP]),
+    "rt_replay_sample_uniform": (C.c_int, [_VP, C.c_int32, _VP, _VP]),
+    "rt_replay_batch": (C.c_int, [_VP, C.POINTER(Batch)]),
+    "rt_replay_update_losses": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP]),
+    "rt_replay_update_losses_last": (C.c_int, [_VP, _VP, _VP]),
+    "rt_replay_tree_sum": (C.c_int, [_VP, C.POINTER(C.c_double), _VP]),
+    "rt_replay_tree_min": (C.c_int, [_VP, C.POINTER(C.c_double), _VP]),
+    "rt_replay_tree_leaf": (C.c_int, [_VP, C.c_int32, C.POINTER(C.c_double), _VP]),
+    "rt_tree_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(_VP)]),
+    "rt_tree_destroy": (None, [_VP]),
+    "rt_tree_set": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP]),
+    "rt_tree_sum": (C.c_int, [_VP, C.POINTER(C.c_double), _VP]),
+    "rt_tree_find": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RtError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    """Raises on a negative status; returns the (non-negative) status otherwise."""
+    if rc < 0:
+        raise RtError("rltime_b200: %s (status %d)" % (load().rt_last_error().decode(), rc))
+    return rc
+
+
+class DevPtr:
+    """Borrowed device memory exposed through __cuda_array_interface__ (zero-copy into torch)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(int(s) for s in shape), "typestr": typestr,
+            "data": (int(ptr), False), "version": 2, "strides": None,
+        }
+
+
+def as_tensor(ptr, shape, typestr, device):
+    import torch
+    if any(int(s) == 0 for s in shape):
+        import numpy as np
+        return torch.empty(tuple(shape), dtype=torch.from_numpy(np.empty(0, np.dtype(typestr))).dtype,
+                           device=device)
+    return torch.as_tensor(DevPtr(ptr, shape, typestr), device=device)

@@ -1,0 +1,16 @@
+"""Drop-in history buffers (mirror of rltime/history/__init__.py:1-11)."""
+from .device_history import (DevicePrioritizedReplayHistoryBuffer,
+                             DeviceReplayHistoryBuffer)
+
+# same class names as the reference so `@python('rltime_b200.history.X')` reads naturally
+ReplayHistoryBuffer = DeviceReplayHistoryBuffer
+PrioritizedReplayHistoryBuffer = DevicePrioritizedReplayHistoryBuffer
+
+
+def get_types():
+    """Registry entries for the `history` type group (rltime/history/__init__.py:6-11).
+    `online` has no device kernel and is not provided here."""
+    return {
+        "replay": DeviceReplayHistoryBuffer,
+        "prioritized_replay": DevicePrioritizedReplayHistoryBuffer,
+    }
