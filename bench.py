@@ -1,0 +1,375 @@
+"""Headline benchmark: learner updates/sec on a 1M-transition prioritized sequence replay.
+
+One "step" = one full learner update of BASELINE.json's metric:
+  stratified sum-tree draw of B=32 sequences -> n-step assembly + importance weights ->
+  gather of the (T+n) x B x (4,84,84) uint8 frame stack (+ LSTM states) ->
+  double-Q IQN targets (target + selection forward) -> training forward, quantile-Huber loss,
+  backward, grad-norm clip, Adam -> priority write-back.
+Workload (config.workload): BASELINE.json configs[2]/[4] shape — Atari IQN+LSTM, T=20, n=2,
+B=32, Nq=32, 1M-transition weighted PER (alpha .9, beta .6, overlap 10), synthetic transitions
+(SURVEY.md 8d), random-init nature-CNN -> LSTM512 -> FC512 dueling IQN.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+`value`  : updates/s with everything resident in HBM (device-timed, CUDA events).
+`e2e`    : the same update through the public Python API with HOST buffers: every step
+           ingests `train_frequency`-worth of new transitions from pinned host memory (H2D)
+           and reads the step's loss back (D2H).
+`--impl reference`: the CPU port of the reference path (oracle/, torch CPU + Python replay)
+           on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CFG = dict(size=1_000_000, envs=32, T=20, P=0, n=2, B=32, Nq=32, A=6, units=512, fc=512,
+           frame=(4, 84, 84), conv=[(32, 8, 4), (64, 4, 2), (64, 3, 1)], alpha=0.9, beta=0.6,
+           gamma=0.99, clip_grad=40.0, adam_eps=1e-5, train_frequency=4)
+FRAME_BYTES = 4 * 84 * 84
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._th = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.check_output(
+                    ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                     "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=5)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def build_device_workload(cfg, device, seed, rank):
+    from rltime_b200.history import DevicePrioritizedReplayHistoryBuffer
+    from rltime_b200.learner import DeviceLearner
+    from rltime_b200.init import init_params
+    hist = DevicePrioritizedReplayHistoryBuffer(
+        size=cfg["size"], train_frequency=None, alpha=cfg["alpha"], beta=cfg["beta"],
+        nstep_target=cfg["n"], nstep_train=cfg["T"], prefix_steps=cfg["P"], gamma=cfg["gamma"],
+        max_envs=cfg["envs"], device=device)
+    E, U, A = cfg["envs"], cfg["units"], cfg["A"]
+    g = torch.Generator(device=device).manual_seed(seed + rank)
+    pool = torch.randint(0, 255, (256,) + cfg["frame"], dtype=torch.uint8, device=device, generator=g)
+    hist.set_structure({"x": ("leaf", 0), "layer0_state": {},
+                        "layer1_state": {"hx": ("leaf", 1), "cx": ("leaf", 2), "initials": ("leaf", 3)},
+                        "layer2_state": {}},
+                       {"actions": ("leaf", 0), "qvalues": ("leaf", 1)})
+    steps_total = cfg["size"] // E
+    chunk_steps = 256
+    rs = np.random.RandomState(seed + rank)
+    t0 = time.time()
+    for s0 in range(0, steps_total, chunk_steps):
+        ns = min(chunk_steps, steps_total - s0)
+        m = ns * E
+        gidx = torch.arange(s0 * E, s0 * E + m, device=device)
+        frames = pool[gidx & 255]
+        hx = torch.randn(m, U, device=device, generator=g)
+        cx = torch.randn(m, U, device=device, generator=g)
+        step = (torch.arange(m, device=device) // E) + s0
+        env = torch.arange(m, device=device) % E
+        done = ((step + 1 + 37 * env) % 500) == 0
+        prev_done = ((step + 37 * env) % 500) == 0
+        initials = prev_done.float()
+        actions = torch.randint(0, A, (m,), device=device, generator=g)
+        qv = torch.randn(m, A, device=device, generator=g)
+        reward = np.sign(rs.randn(m))
+        hist.update_arrays(env.cpu().numpy(), reward, done.cpu().numpy(),
+                           [frames, hx, cx, initials], [actions, qv])
+    torch.cuda.synchronize(device)
+    fill_s = time.time() - t0
+    learner = DeviceLearner(cfg["frame"], cfg["conv"], U, cfg["fc"], A, cfg["Nq"], 64, True,
+                            mbatch=cfg["B"], nstep_train=cfg["T"], burn_in=cfg["P"],
+                            nstep_target=cfg["n"], gamma=cfg["gamma"], double_q=True,
+                            rnn_bootstrap=True, vf_scale_epsilon=None, clip_grad=cfg["clip_grad"],
+                            adam_epsilon=cfg["adam_eps"], lr=3e-4, seed=seed, device=device)
+    learner.load_state_dict(init_params(learner.param_info, U, seed=1), 0)
+    learner.load_state_dict(init_params(learner.param_info, U, seed=2), 1)
+    return hist, learner, fill_s
+
+
+def one_update(hist, learner, B):
+    td = hist.get_train_data(B, 0.0)
+    assert td is not None
+    learner.step(hist.last_batch)
+    hist.update_losses_device(learner.td_abs())
+
+
+def run_gpu(args):
+    from rltime_b200 import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    cfg = dict(CFG)
+    if args.size:
+        cfg["size"] = args.size
+    import random
+    random.seed(rank)
+    hist, learner, fill_s = build_device_workload(cfg, device, seed=0, rank=rank)
+    lib = _lib.load()
+    B = cfg["B"]
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(max(args.warmup, 3)):
+        one_update(hist, learner, B)
+    barrier()
+    launches0 = lib.rt_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            one_update(hist, learner, B)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.rt_launch_count() - launches0
+    stats = learner.stats()
+
+    # gather kernel alone (roofline): time draws without the learner
+    torch.cuda.synchronize(device)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 50
+    for _ in range(5):
+        hist.get_train_data(B, 0.0)
+    g0.record()
+    for _ in range(reps):
+        hist.get_train_data(B, 0.0)
+    g1.record()
+    torch.cuda.synchronize(device)
+    draw_ms = g0.elapsed_time(g1) / reps
+
+    # end to end through the public API with host buffers
+    E = cfg["envs"]
+    feed = (B * cfg["T"]) // cfg["train_frequency"]          # transitions ingested per update
+    feed = (feed // E) * E
+    rs = np.random.RandomState(7)
+    h_frames = torch.from_numpy(rs.randint(0, 255, (feed,) + cfg["frame"]).astype(np.uint8)).pin_memory()
+    h_hx = torch.randn(feed, cfg["units"]).pin_memory()
+    h_cx = torch.randn(feed, cfg["units"]).pin_memory()
+    h_init = torch.zeros(feed).pin_memory()
+    h_act = torch.randint(0, cfg["A"], (feed,)).pin_memory()
+    h_qv = torch.randn(feed, cfg["A"]).pin_memory()
+    env_ids = np.arange(feed) % E
+    reward = np.sign(rs.randn(feed))
+    done = np.zeros(feed, dtype=np.uint8)
+    h2d = sum(t.numel() * t.element_size() for t in (h_frames, h_hx, h_cx, h_init, h_act, h_qv)) + \
+        feed * (8 + 1 + 8 + 4) + B * 8
+    d2h = cfg["T"] * B * 4 + B * 4 + 16
+
+    def e2e_update():
+        hist.update_arrays(env_ids, reward, done,
+                           [h_frames.numpy(), h_hx.numpy(), h_cx.numpy(), h_init.numpy()],
+                           [h_act.numpy(), h_qv.numpy()])
+        one_update(hist, learner, B)
+        return learner.stats()["qloss"]
+    for _ in range(3):
+        e2e_update()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_update()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    vals = torch.tensor([ms, e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(vals[0]), float(vals[1])
+    if rank != 0:
+        return
+    hbm, which = peaks()
+    S, n = cfg["T"] + cfg["P"], cfg["n"]
+    state_bytes = FRAME_BYTES + 2 * cfg["units"] * 4 + 4
+    gather_bytes = 2 * (S + n) * B * state_bytes        # read once + write once
+    out = {
+        "metric": "learner updates/sec (32x20-step seq batches, 1M prioritized replay)",
+        "value": world * args.steps / (ms / 1e3), "unit": "updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "atari_iqn_lstm seq-PER: N=%d T=20 n=2 B=32 Nq=32 A=6 "
+                               "nature-CNN-LSTM512-FC512 dueling double-Q" % cfg["size"],
+                   "replay_per_gpu": cfg["size"], "l2": "inputs (28 GB frame store) exceed L2; "
+                   "every draw gathers different rows", "fill_s": round(fill_s, 1)},
+        "e2e": {"value": world * args.steps / e2e_s, "unit": "updates/s",
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": {"kernel": "k_gather (sample+assemble+gather timed together)", "bound": "hbm",
+                     "achieved": gather_bytes / (draw_ms * 1e-3) / 1e9, "peak": hbm,
+                     "peak_source": which, "unit": "GB/s",
+                     "frac": gather_bytes / (draw_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                     "draw_ms": draw_ms},
+        "last_stats": stats,
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = run_reference(args, quiet=True)["cpu_baseline"]
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------- reference arm
+def run_reference(args, quiet=False):
+    """CPU port of the reference path (oracle/): Python replay + torch fp32 learner on the host
+    cores.  Bounded sample: a 1M fill is the untimed setup, `steps` updates are timed."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    import random
+    from oracle import learner_oracle as lo
+    from oracle import replay_oracle as ro
+    from rltime_b200.synthetic import SyntheticStream
+    cfg = dict(CFG)
+    cfg["size"] = args.ref_size
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    random.seed(0)
+    np.random.seed(0)
+    stream = SyntheticStream(num_envs=cfg["envs"], frame_shape=cfg["frame"], num_actions=cfg["A"],
+                             lstm_units=cfg["units"], seed=1, clip_rewards=True)
+    g = cfg["gamma"]
+    hist = ro.PrioritizedReplayOracle(
+        size=cfg["size"], train_frequency=None, alpha=cfg["alpha"], beta=cfg["beta"],
+        nstep_target=cfg["n"], nstep_train=cfg["T"], prefix_steps=cfg["P"],
+        discount_function=lambda k, r, po: (g ** k) * r)
+    # pooled LSTM states keep the host footprint of the fill bounded
+    hpool = np.random.RandomState(3).randn(256, cfg["units"]).astype(np.float32)
+    t0 = time.time()
+    for s in range(cfg["size"] // cfg["envs"]):
+        a = stream.next_arrays()
+        a["hx"] = hpool[(a["frame_idx"]) & 255]
+        a["cx"] = hpool[(a["frame_idx"] + 7) & 255]
+        hist.update(stream.samples_from_arrays(a))
+    fill_s = time.time() - t0
+    spec = lo.ModelSpec(cfg["frame"], cfg["conv"], cfg["units"], cfg["fc"], cfg["A"], cfg["Nq"], 64, True)
+    p_on, p_tg = spec.init_params(1), spec.init_params(2)
+    opt = lo.Adam(p_on, lr=3e-4, eps=cfg["adam_eps"])
+    B, T, Nq = cfg["B"], cfg["T"], cfg["Nq"]
+    steps = max(1, min(args.steps, args.ref_steps))
+
+    def update():
+        td = hist.get_train_data(B, 0.0)
+        to_t = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+        batch = {
+            "states": {"x": to_t(td["states"]["x"]), "layer1_state": {
+                k: to_t(v) for k, v in td["states"]["layer1_state"].items()}},
+            "target_states": {"x": to_t(td["target_states"]["x"]), "layer1_state": {
+                k: to_t(v) for k, v in td["target_states"]["layer1_state"].items()}},
+            "returns": to_t(td["returns"]), "nsteps": to_t(td["nsteps"]),
+            "target_masks": to_t(np.asarray(td["target_masks"], dtype=np.float64)),
+            "actions": to_t(td["policy_outputs"]["actions"]),
+            "importance_weights": to_t(td["extra_data"]["importance_weights"]),
+        }
+        taus = {k: torch.rand(T * B * Nq) for k in ("target", "select", "train")}
+        res = lo.learner_update(spec, p_on, p_tg, opt, batch, taus, cfg["gamma"], double_q=True,
+                                rnn_bootstrap=True, clip_grad=cfg["clip_grad"])
+        li = td["extra_data"]["loss_indices"].reshape(-1, 2)
+        hist.update_losses(li, res["report"].numpy().astype(np.float64))
+    for _ in range(min(args.warmup, 1)):
+        update()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        update()
+    dt = time.perf_counter() - t0
+    val = steps / dt
+    cb = {"value": val, "unit": "updates/s", "cores": cores, "kind": "port",
+          "sample": "%d updates on a %d-transition replay (fill %.1fs untimed); torch CPU fp32, "
+                    "%d threads; Python replay oracle" % (steps, cfg["size"], fill_s, cores)}
+    line = {
+        "impl": "reference",
+        "metric": "learner updates/sec (32x20-step seq batches, 1M prioritized replay)",
+        "value": val, "unit": "updates/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "atari_iqn_lstm seq-PER: N=%d T=20 n=2 B=32 Nq=32 A=6 "
+                               "nature-CNN-LSTM512-FC512 dueling double-Q" % cfg["size"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    if not quiet:
+        print(json.dumps(line))
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=0, help="override replay capacity (debug)")
+    ap.add_argument("--ref-size", type=int, default=200_000,
+                    help="replay transitions filled for the CPU reference arm (bounded sample)")
+    ap.add_argument("--ref-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -138,6 +138,92 @@ int rt_tree_set(rt_tree* t, int32_t m, const int32_t* idx, const double* val, vo
 int rt_tree_sum(rt_tree* t, double* out, void* stream);
 int rt_tree_find(rt_tree* t, int32_t m, const double* mass, int32_t* out_idx, void* stream);
 
+
+/* ------------------------------------------------------------------------ learner */
+typedef struct rt_learner rt_learner;
+#define RT_MAX_CONV 8
+
+/* Topology family of the hot path: CNN -> [LSTM] -> FC -> IQN quantile layer (injected
+ * before the last layer, injection_layer=-1) -> out (+ dueling value branch).  Mirrors the
+ * json model description consumed by SequentialModel (rltime/models/torch/sequential.py:15-66,
+ * configs/models/nature_cnn_lstm512_fc512.json) and the IQNPolicy / DQNPolicy constructor
+ * arguments (rltime/policies/torch/iqn.py:12-13, dqn.py:15-16). */
+typedef struct rt_model_desc {
+  int32_t in_c, in_h, in_w;            /* observation (C, H, W), uint8, channel first */
+  int32_t num_conv;
+  int32_t conv_filters[RT_MAX_CONV], conv_kernel[RT_MAX_CONV], conv_stride[RT_MAX_CONV];
+  int32_t lstm_units;                  /* 0 = no recurrent layer */
+  int32_t fc_size;
+  int32_t num_actions;
+  int32_t num_quantiles;               /* num_sampling_quantiles */
+  int32_t embedding_dim;
+  int32_t dueling;
+} rt_model_desc;
+
+/* Training arguments: union of IQN/DQN._train, TorchTrainer._train and MultiStepTrainer._train
+ * (rltime/training/torch/dqn.py:15-17, torch_trainer.py:9-10, multi_step_trainer.py:152-156). */
+typedef struct rt_train_desc {
+  int32_t mbatch;         /* B */
+  int32_t nstep_train;    /* T */
+  int32_t burn_in;        /* burn_in_timesteps = prefix_steps P */
+  int32_t nstep_target;   /* n */
+  int32_t double_q;
+  int32_t rnn_bootstrap;
+  int32_t loss_sum;       /* loss_aggregation: 0 = mean, 1 = sum */
+  int32_t reserved;
+  double gamma;
+  double vf_scale_epsilon; /* <= 0: no value rescaling */
+  double huber_kappa;
+  double clip_grad;        /* <= 0: no clipping */
+  double adam_epsilon;
+  double lr;               /* NB the reference's train_init ignores lr (torch_trainer.py:80-83) */
+  uint64_t seed;           /* device RNG for the quantile fractions when none are injected */
+} rt_train_desc;
+
+/* Which leaves of the replay batch feed the learner. */
+typedef struct rt_learner_io {
+  int32_t field_x, field_hx, field_cx, field_initials; /* indices into rt_batch.all_states */
+  int32_t po_field_actions;                            /* index into rt_batch.policy_outputs (int64) */
+} rt_learner_io;
+
+#define RT_BUF_ONLINE 0
+#define RT_BUF_TARGET 1
+#define RT_BUF_GRAD 2
+#define RT_BUF_ADAM_M 3
+#define RT_BUF_ADAM_V 4
+
+/* PolicyTrainer.init_policies / IQN.create_policy + TorchTrainer.train_init
+ * (rltime/training/policy_trainer.py:39-66, torch/iqn.py:11-13, torch_trainer.py:80-83). */
+int rt_learner_create(const rt_model_desc* model, const rt_train_desc* train, int32_t device,
+                      rt_learner** out);
+void rt_learner_destroy(rt_learner* h);
+/* state_dict surface (TorchPolicy.get_state / load_state, torch_policy.py:97-101): tensors are
+ * enumerated in the reference's registration order with its parameter names and layouts. */
+int32_t rt_learner_num_params(const rt_learner* h);
+int64_t rt_learner_num_weights(const rt_learner* h);
+int rt_learner_param_info(const rt_learner* h, int32_t i, char* name, int32_t name_cap,
+                          int64_t* shape4, int32_t* ndim);
+int rt_learner_load_params(rt_learner* h, int32_t which, const float* const* tensors);
+int rt_learner_get_params(rt_learner* h, int32_t which, float* const* tensors);
+/* PolicyTrainer.sync_target -> TorchPolicy.copy_from (policy_trainer.py:68-70). */
+int rt_learner_sync_target(rt_learner* h, void* stream);
+/* TorchTrainer.set_lr (torch_trainer.py:149-151). */
+int rt_learner_set_lr(rt_learner* h, double lr);
+/* One learner update on a replay batch: burn-in (multi_step_trainer.py:90-131), bootstrap
+ * targets (torch/iqn.py:15-52, torch_trainer.py:101-147), training forward + quantile-Huber
+ * loss + backward (torch/iqn.py:54-129), grad-norm clip + Adam (torch_trainer.py:177-199).
+ * taus_host: NULL, or 3 host arrays of T*B*Nq fractions (target, action-selection, train
+ * forward) replacing the reference's torch.rand draws (policies/torch/iqn.py:88). */
+int rt_learner_step(rt_learner* h, const rt_batch* batch, const rt_learner_io* io,
+                    const float* const* taus_host, void* stream);
+/* Device pointer to the T*B reported |td| means (torch/iqn.py:112) of the last step. */
+int rt_learner_td_abs(rt_learner* h, float** out_device);
+/* qloss, td_mean, grad_norm of the last step (torch/iqn.py:127-129, torch_trainer.py:187-190);
+ * synchronises the stream. */
+int rt_learner_read_stats(rt_learner* h, float* loss, float* td_mean, float* grad_norm, void* stream);
+/* Test hook: named intermediate activations / gradients of the last step. */
+int rt_learner_debug_tensor(rt_learner* h, const char* name, void** dev_ptr, int64_t* count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,35 @@ class Batch(C.Structure):
     ]
 
 
+RT_MAX_CONV = 8
+RT_BUF_ONLINE, RT_BUF_TARGET, RT_BUF_GRAD, RT_BUF_ADAM_M, RT_BUF_ADAM_V = range(5)
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("in_c", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("num_conv", C.c_int32),
+        ("conv_filters", C.c_int32 * RT_MAX_CONV), ("conv_kernel", C.c_int32 * RT_MAX_CONV),
+        ("conv_stride", C.c_int32 * RT_MAX_CONV), ("lstm_units", C.c_int32),
+        ("fc_size", C.c_int32), ("num_actions", C.c_int32), ("num_quantiles", C.c_int32),
+        ("embedding_dim", C.c_int32), ("dueling", C.c_int32),
+    ]
+
+
+class TrainDesc(C.Structure):
+    _fields_ = [
+        ("mbatch", C.c_int32), ("nstep_train", C.c_int32), ("burn_in", C.c_int32),
+        ("nstep_target", C.c_int32), ("double_q", C.c_int32), ("rnn_bootstrap", C.c_int32),
+        ("loss_sum", C.c_int32), ("reserved", C.c_int32), ("gamma", C.c_double),
+        ("vf_scale_epsilon", C.c_double), ("huber_kappa", C.c_double), ("clip_grad", C.c_double),
+        ("adam_epsilon", C.c_double), ("lr", C.c_double), ("seed", C.c_uint64),
+    ]
+
+
+class LearnerIO(C.Structure):
+    _fields_ = [("field_x", C.c_int32), ("field_hx", C.c_int32), ("field_cx", C.c_int32),
+                ("field_initials", C.c_int32), ("po_field_actions", C.c_int32)]
+
+
 # name -> (restype, argtypes); also the list the CPU test checks against the header
 _VP = C.c_void_p
 SIGNATURES = {
@@ -70,6 +99,22 @@ SIGNATURES = {
     "rt_tree_set": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP]),
     "rt_tree_sum": (C.c_int, [_VP, C.POINTER(C.c_double), _VP]),
     "rt_tree_find": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP]),
+    "rt_learner_create": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(TrainDesc), C.c_int32,
+                                    C.POINTER(_VP)]),
+    "rt_learner_destroy": (None, [_VP]),
+    "rt_learner_num_params": (C.c_int32, [_VP]),
+    "rt_learner_num_weights": (C.c_int64, [_VP]),
+    "rt_learner_param_info": (C.c_int, [_VP, C.c_int32, C.c_char_p, C.c_int32,
+                                        C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "rt_learner_load_params": (C.c_int, [_VP, C.c_int32, _VP]),
+    "rt_learner_get_params": (C.c_int, [_VP, C.c_int32, _VP]),
+    "rt_learner_sync_target": (C.c_int, [_VP, _VP]),
+    "rt_learner_set_lr": (C.c_int, [_VP, C.c_double]),
+    "rt_learner_step": (C.c_int, [_VP, C.POINTER(Batch), C.POINTER(LearnerIO), _VP, _VP]),
+    "rt_learner_td_abs": (C.c_int, [_VP, C.POINTER(_VP)]),
+    "rt_learner_read_stats": (C.c_int, [_VP, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                        C.POINTER(C.c_float), _VP]),
+    "rt_learner_debug_tensor": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP), C.POINTER(C.c_int64)]),
 }
 
 _lib = None

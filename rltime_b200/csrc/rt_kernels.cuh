@@ -1,0 +1,520 @@
+// Learner kernels for sm_100a: fp32 GEMM (SIMT path), im2col / col2im, LSTM cell, IQN
+// quantile embedding, dueling heads, double-Q target + value rescaling, fused quantile-Huber
+// loss forward+backward, column reductions, fused grad-norm + clip + Adam.
+//
+// Activations are NHWC ((row, pixel), channel) so every convolution / linear layer is a
+// GEMM C[M,N] = A[M,K] . W[N,K]^T on K-major operands — the layout the tcgen05 path in
+// rt_gemm_tc.cuh consumes directly.  Reference call sites are cited per kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtk {
+
+// ------------------------------------------------------------------------------- GEMM
+// C[M,N] = epi( alpha * sum_k Aop[m,k] * Bop[k,n] )
+//   Aop[m,k] = transA ? A[k*lda+m] : A[m*lda+k]
+//   Bop[k,n] = transB ? B[n*ldb+k] : B[k*ldb+n]      (transB=1: nn.Linear weight [N,K])
+// epi(v)[m,n] = (accumulate ? C_old : 0) + mask( relu( v + bias[n] + bias2[n] ) )
+//   mask: multiplies by (mask[m*ldmask+n] > 0), i.e. the ReLU derivative of a saved output.
+struct GemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  int M, N, K;
+  int lda, ldb, ldc;
+  int transA, transB;
+  float alpha;
+  const float* bias;
+  const float* bias2;
+  int relu;
+  const float* mask;
+  int ldmask;
+  int accumulate;
+  float* ws;      // split-K workspace [splits][M][N] (raw partial sums)
+  int kchunk;     // K range per z-slice
+};
+
+__device__ __forceinline__ float gemm_epilogue(const GemmArgs& g, int m, int n, float acc) {
+  float v = acc * g.alpha;
+  if (g.bias) v += g.bias[n];
+  if (g.bias2) v += g.bias2[n];
+  if (g.relu) v = fmaxf(v, 0.f);
+  if (g.mask) v = (g.mask[(size_t)m * g.ldmask + n] > 0.f) ? v : 0.f;
+  if (g.accumulate) v += g.C[(size_t)m * g.ldc + n];
+  return v;
+}
+
+template <int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) k_sgemm(const __grid_constant__ GemmArgs g) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * g.kchunk;
+  const int kend = min(g.K, kbeg + g.kchunk);
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < (BM * BK) / NT; ++i) {
+      int e = tid + i * NT;
+      int kk, mm;
+      if (!g.transA) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
+      int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < g.M && gk < kend)
+        v = g.transA ? g.A[(size_t)gk * g.lda + gm] : g.A[(size_t)gm * g.lda + gk];
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < (BN * BK) / NT; ++i) {
+      int e = tid + i * NT;
+      int kk, nn;
+      if (g.transB) { kk = e % BK; nn = e / BK; } else { nn = e % BN; kk = e / BN; }
+      int gn = n0 + nn, gk = k0 + kk;
+      float v = 0.f;
+      if (gn < g.N && gk < kend)
+        v = g.transB ? g.B[(size_t)gn * g.ldb + gk] : g.B[(size_t)gk * g.ldb + gn];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + ty * TM + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + tx * TN + j;
+      if (n >= g.N) continue;
+      if (gridDim.z > 1)
+        g.ws[((size_t)blockIdx.z * g.M + m) * g.N + n] = acc[i][j];
+      else
+        g.C[(size_t)m * g.ldc + n] = gemm_epilogue(g, m, n, acc[i][j]);
+    }
+  }
+}
+
+// Deterministic split-K reduction + epilogue.
+__global__ void k_splitk_reduce(const __grid_constant__ GemmArgs g, int splits) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)g.M * g.N;
+  if (idx >= total) return;
+  int m = (int)(idx / g.N), n = (int)(idx - (size_t)m * g.N);
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc += g.ws[(size_t)s * total + idx];
+  g.C[(size_t)m * g.ldc + n] = gemm_epilogue(g, m, n, acc);
+}
+
+// ------------------------------------------------------------------------------ im2col
+// conv input NCHW uint8 frames (the replay batch), fused x.float() * (1/255)
+// (rltime/models/torch/modules/cnn.py:44-45).  col[(m,oh,ow), (c,kh,kw)].
+__global__ void k_im2col_u8_nchw(const uint8_t* __restrict__ x, float* __restrict__ col, int rows,
+                                 int C, int H, int W, int KH, int S, int OH, int OW, float scale) {
+  const int K = C * KH * KH;
+  size_t total = (size_t)rows * OH * OW * K;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    int k = (int)(idx % K);
+    size_t r = idx / K;
+    int ow = (int)(r % OW);
+    int oh = (int)((r / OW) % OH);
+    size_t m = r / ((size_t)OW * OH);
+    int kw = k % KH, kh = (k / KH) % KH, c = k / (KH * KH);
+    uint8_t v = x[((m * C + c) * H + (oh * S + kh)) * W + (ow * S + kw)];
+    col[idx] = __fmul_rn((float)v, scale);
+  }
+}
+
+// conv input NHWC float.  col[(m,oh,ow), (kh,kw,c)].
+__global__ void k_im2col_f32_nhwc(const float* __restrict__ x, float* __restrict__ col, int rows,
+                                  int C, int H, int W, int KH, int S, int OH, int OW) {
+  const int K = C * KH * KH;
+  size_t total = (size_t)rows * OH * OW * K;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    int k = (int)(idx % K);
+    size_t r = idx / K;
+    int ow = (int)(r % OW);
+    int oh = (int)((r / OW) % OH);
+    size_t m = r / ((size_t)OW * OH);
+    int c = k % C, kw = (k / C) % KH, kh = k / (C * KH);
+    col[idx] = x[((m * H + (oh * S + kh)) * W + (ow * S + kw)) * C + c];
+  }
+}
+
+// Transposed convolution data-gradient, gather form (deterministic, no atomics):
+// dx[m,ih,iw,c] = sum over (kh,kw) with oh*S+kh == ih, ow*S+kw == iw of dcol[(m,oh,ow),(kh,kw,c)].
+__global__ void k_col2im_nhwc(const float* __restrict__ dcol, float* __restrict__ dx, int rows, int C,
+                              int H, int W, int KH, int S, int OH, int OW) {
+  const int K = C * KH * KH;
+  size_t total = (size_t)rows * H * W * C;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(idx % C);
+    size_t r = idx / C;
+    int iw = (int)(r % W);
+    int ih = (int)((r / W) % H);
+    size_t m = r / ((size_t)W * H);
+    float acc = 0.f;
+    for (int kh = 0; kh < KH; ++kh) {
+      int t = ih - kh;
+      if (t < 0 || t % S) continue;
+      int oh = t / S;
+      if (oh >= OH) continue;
+      for (int kw = 0; kw < KH; ++kw) {
+        int u = iw - kw;
+        if (u < 0 || u % S) continue;
+        int ow = u / S;
+        if (ow >= OW) continue;
+        acc += dcol[((m * OH + oh) * OW + ow) * K + (kh * KH + kw) * C + c];
+      }
+    }
+    dx[idx] = acc;
+  }
+}
+
+// y *= (ref > 0)   (ReLU derivative through a saved post-activation output)
+__global__ void k_relu_bwd_inplace(float* __restrict__ dy, const float* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    if (!(y[i] > 0.f)) dy[i] = 0.f;
+}
+
+// ------------------------------------------------------------------------------- LSTM
+// rltime/models/torch/modules/lstm.py:84-116 (single-sample case), time-major rows t*B+b.
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// t = 0: hprev/cprev[0] = stored state * (1 - initials[0])   (lstm.py:67-70, 95-98)
+__global__ void k_lstm_init(const float* __restrict__ hx, const float* __restrict__ cx,
+                            const float* __restrict__ initials, float* __restrict__ hprev,
+                            float* __restrict__ cprev, int B, int U) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * U) return;
+  int b = i / U;
+  float keep = 1.f - initials[b];
+  hprev[i] = hx[i] * keep;
+  cprev[i] = cx[i] * keep;
+}
+
+// gates = xg[t] (x W_ih^T + b_ih + b_hh) + hg (h W_hh^T); PyTorch gate order i, f, g, o.
+// Writes activated gates (for BPTT), c, h, and the masked carry-in of step t+1.
+__global__ void k_lstm_cell(const float* __restrict__ xg, const float* __restrict__ hg,
+                            const float* __restrict__ cprev, float* __restrict__ gates,
+                            float* __restrict__ c_out, float* __restrict__ h_out,
+                            const float* __restrict__ next_initials, float* __restrict__ hprev_next,
+                            float* __restrict__ cprev_next, int B, int U) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * U) return;
+  int b = i / U, u = i - b * U;
+  size_t g0 = (size_t)b * 4 * U + u;
+  float gi = sigmoidf_(xg[g0] + hg[g0]);
+  float gf = sigmoidf_(xg[g0 + U] + hg[g0 + U]);
+  float gg = tanhf(xg[g0 + 2 * U] + hg[g0 + 2 * U]);
+  float go = sigmoidf_(xg[g0 + 3 * U] + hg[g0 + 3 * U]);
+  float c = gf * cprev[i] + gi * gg;
+  float h = go * tanhf(c);
+  gates[g0] = gi; gates[g0 + U] = gf; gates[g0 + 2 * U] = gg; gates[g0 + 3 * U] = go;
+  c_out[i] = c;
+  h_out[i] = h;
+  if (hprev_next) {
+    float keep = 1.f - next_initials[b];
+    hprev_next[i] = h * keep;
+    cprev_next[i] = c * keep;
+  }
+}
+
+// BPTT cell: dh = dout[t] + dh_carry; produces pre-activation gate grads and the carries.
+__global__ void k_lstm_cell_bwd(const float* __restrict__ dout, const float* __restrict__ dh_carry,
+                                float* __restrict__ dc_carry, const float* __restrict__ gates,
+                                const float* __restrict__ c, const float* __restrict__ cprev,
+                                const float* __restrict__ initials, float* __restrict__ dgates,
+                                int B, int U) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * U) return;
+  int b = i / U, u = i - b * U;
+  size_t g0 = (size_t)b * 4 * U + u;
+  float gi = gates[g0], gf = gates[g0 + U], gg = gates[g0 + 2 * U], go = gates[g0 + 3 * U];
+  float dh = dout[i] + (dh_carry ? dh_carry[i] : 0.f);
+  float tc = tanhf(c[i]);
+  float dc = dc_carry[i] + dh * go * (1.f - tc * tc);
+  dgates[g0] = dc * gg * gi * (1.f - gi);
+  dgates[g0 + U] = dc * cprev[i] * gf * (1.f - gf);
+  dgates[g0 + 2 * U] = dc * gi * (1.f - gg * gg);
+  dgates[g0 + 3 * U] = dh * tc * go * (1.f - go);
+  // carry into step t-1 passes through this step's episode-reset mask
+  dc_carry[i] = dc * gf * (1.f - initials[b]);
+}
+
+// dh_carry = (dgates[t] . W_hh) * (1 - initials[t])
+__global__ void k_mask_rows(float* __restrict__ x, const float* __restrict__ initials, int B, int U) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * U) return;
+  x[i] *= (1.f - initials[i / U]);
+}
+
+// ------------------------------------------------------------------------------- IQN
+// cos(pi * i * tau), i = 1..E   (rltime/policies/torch/iqn.py:91-93)
+__global__ void k_cos_features(const float* __restrict__ tau, float* __restrict__ cf, int rows, int E) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)rows * E) return;
+  int i = (int)(idx % E);
+  float t = tau[idx / E];
+  cf[idx] = cosf(__fmul_rn(__fmul_rn((float)(i + 1), 3.14159274101257324f), t));
+}
+
+// xq[r,d] = x[r / Nq, d] * phi[r,d]      (iqn.py:84, 99-100)
+__global__ void k_quantile_mul(const float* __restrict__ x, const float* __restrict__ phi,
+                               float* __restrict__ xq, size_t rowsq, int D, int Nq) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rowsq * D) return;
+  size_t r = idx / D;
+  int d = (int)(idx - r * D);
+  xq[idx] = x[(r / Nq) * D + d] * phi[idx];
+}
+
+// dphi_pre[r,d] = dxq[r,d] * x[m,d] * (phi > 0);  dx[m,d] = sum_q dxq[m*Nq+q, d] * phi[m*Nq+q, d]
+__global__ void k_quantile_mul_bwd(const float* __restrict__ dxq, const float* __restrict__ x,
+                                   const float* __restrict__ phi, float* __restrict__ dphi,
+                                   float* __restrict__ dx, int M, int D, int Nq) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)M * D) return;
+  int m = (int)(idx / D), d = (int)(idx - (size_t)m * D);
+  float xv = x[idx], acc = 0.f;
+  for (int q = 0; q < Nq; ++q) {
+    size_t r = ((size_t)m * Nq + q) * D + d;
+    float p = phi[r], g = dxq[r];
+    acc += g * p;
+    dphi[r] = (p > 0.f) ? g * xv : 0.f;
+  }
+  dx[idx] = acc;
+}
+
+// q[r,a] = v[r] + adv[r,a] - mean_a adv[r,:]     (rltime/policies/torch/dqn.py:86-87)
+__global__ void k_dueling(const float* __restrict__ adv, const float* __restrict__ v,
+                          float* __restrict__ q, size_t rows, int A) {
+  size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int a = 0; a < A; ++a) s += adv[r * A + a];
+  float mean = s / (float)A;
+  float vv = v ? v[r] : 0.f;
+  for (int a = 0; a < A; ++a) q[r * A + a] = v ? (vv + adv[r * A + a] - mean) : adv[r * A + a];
+}
+
+// dq (nonzero only at the acted action) -> dadv, dv
+__global__ void k_dueling_bwd(const float* __restrict__ dtheta, const long long* __restrict__ actions,
+                              float* __restrict__ dadv, float* __restrict__ dv, size_t rows, int A,
+                              int Nq, int dueling) {
+  size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  int act = (int)actions[r / Nq];
+  float g = dtheta[r];
+  for (int a = 0; a < A; ++a) {
+    float d = (a == act) ? g : 0.f;
+    dadv[r * A + a] = dueling ? d - g / (float)A : d;
+  }
+  if (dv) dv[r] = g;
+}
+
+// ------------------------------------------------------------------------------ target
+// IQN._get_bootstrap_target_value (rltime/training/torch/iqn.py:37-52) +
+// TorchTrainer.calc_target_values / _vf_unscale / _vf_scale (torch_trainer.py:46-78,144-147).
+__global__ void k_iqn_target(const float* __restrict__ tq, const float* __restrict__ sq,
+                             const double* __restrict__ returns, const double* __restrict__ masks,
+                             const long long* __restrict__ nsteps, float* __restrict__ targets, int M,
+                             int Nq, int A, float gamma, double vf_eps) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  int best = 0;
+  float best_v = -INFINITY;
+  for (int a = 0; a < A; ++a) {
+    float s = 0.f;
+    for (int q = 0; q < Nq; ++q) s += sq[((size_t)m * Nq + q) * A + a];
+    s /= (float)Nq;
+    if (s > best_v) { best_v = s; best = a; }
+  }
+  float ret = (float)returns[m], mask = (float)masks[m];
+  float disc = powf(gamma, (float)nsteps[m]);
+  for (int q = 0; q < Nq; ++q) {
+    float boot = tq[((size_t)m * Nq + q) * A + best];
+    if (vf_eps > 0.0) {
+      double sx = (double)boot, a = fabs(sx), e = vf_eps;
+      double x = a / e - ((1.0 / (2.0 * (e * e))) * sqrt(4.0 * e * a + (2.0 * e + 1.0) * (2.0 * e + 1.0))) +
+                 (2.0 * e + 1.0) / (2.0 * (e * e));
+      x *= (sx > 0.0) - (sx < 0.0);
+      boot = (float)x;
+    }
+    float y = ret + disc * boot * mask;
+    if (vf_eps > 0.0) {
+      float sg = (float)((y > 0.f) - (y < 0.f));
+      y = sg * (sqrtf(fabsf(y) + 1.f) - 1.f) + (float)vf_eps * y;
+    }
+    targets[(size_t)m * Nq + q] = y;
+  }
+}
+
+// -------------------------------------------------------------------------------- loss
+// IQN._compute_grads (rltime/training/torch/iqn.py:72-125) forward AND backward, one CTA per
+// row m.  theta_j = q[m,j,a_m]; delta_ij = y_i - theta_j; rho_ij = |tau_j - 1[delta<0]|
+// row_loss = (1/Nq') sum_ij rho*huber/kappa ; report = mean_ij |delta|
+// dtheta_j = -(w_m * scale) * (1/Nq') sum_i rho * huber'(delta) / kappa
+__global__ void k_iqn_loss(const float* __restrict__ q, const float* __restrict__ targets,
+                           const float* __restrict__ tau, const long long* __restrict__ actions,
+                           const double* __restrict__ weights, float* __restrict__ dtheta,
+                           float* __restrict__ row_loss, float* __restrict__ report, int Nq, int A,
+                           float kappa, float grad_scale) {
+  extern __shared__ float sm[];
+  float* s_y = sm;            // Nq
+  float* s_th = sm + Nq;      // Nq
+  float* s_tau = sm + 2 * Nq; // Nq
+  float* s_red = sm + 3 * Nq; // 2 * blockDim
+  int m = blockIdx.x;
+  int act = (int)actions[m];
+  for (int j = threadIdx.x; j < Nq; j += blockDim.x) {
+    s_y[j] = targets[(size_t)m * Nq + j];
+    s_th[j] = q[((size_t)m * Nq + j) * A + act];
+    s_tau[j] = tau[(size_t)m * Nq + j];
+  }
+  __syncthreads();
+  float w = weights ? (float)weights[m] : 1.f;
+  float lsum = 0.f, asum = 0.f;
+  // thread j owns online quantile j (column), loops over target samples i
+  for (int j = threadIdx.x; j < Nq; j += blockDim.x) {
+    float th = s_th[j], tj = s_tau[j], g = 0.f;
+    for (int i = 0; i < Nq; ++i) {
+      float d = s_y[i] - th;
+      float a = fabsf(d);
+      float hub = (a <= kappa) ? 0.5f * d * d : kappa * (a - 0.5f * kappa);
+      float dh = (a <= kappa) ? d : (d > 0.f ? kappa : -kappa);
+      float rho = fabsf(tj - (d < 0.f ? 1.f : 0.f));
+      lsum += rho * hub / kappa;
+      asum += a;
+      g += rho * dh / kappa;
+    }
+    dtheta[(size_t)m * Nq + j] = -(w * grad_scale) * g / (float)Nq;
+  }
+  s_red[threadIdx.x] = lsum;
+  s_red[blockDim.x + threadIdx.x] = asum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float l = 0.f, a = 0.f;
+    for (int t = 0; t < blockDim.x; ++t) { l += s_red[t]; a += s_red[blockDim.x + t]; }
+    row_loss[m] = (l / (float)Nq) * w;            // weighted per-row loss (dqn.py:83-95)
+    report[m] = a / (float)(Nq * Nq);             // iqn.py:112
+  }
+}
+
+// stats[0] = aggregate(row_loss), stats[1] = mean(report) = td_mean (iqn.py:127-129)
+__global__ void k_loss_stats(const float* __restrict__ row_loss, const float* __restrict__ report,
+                             float* __restrict__ stats, int M, int mean_agg) {
+  __shared__ double s[2][256];
+  double l = 0.0, r = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) { l += row_loss[i]; r += report[i]; }
+  s[0][threadIdx.x] = l; s[1][threadIdx.x] = r;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double L = 0, R = 0;
+    for (int t = 0; t < blockDim.x; ++t) { L += s[0][t]; R += s[1][t]; }
+    stats[0] = (float)(mean_agg ? L / M : L);
+    stats[1] = (float)(R / M);
+  }
+}
+
+// -------------------------------------------------------------------- column reductions
+// out[n] = sum_m x[m, n]; two deterministic stages.
+__global__ void k_colsum_partial(const float* __restrict__ x, float* __restrict__ part, size_t rows,
+                                 int N, int rows_per_block) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  size_t r0 = (size_t)blockIdx.y * rows_per_block;
+  size_t r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc = 0.f;
+  for (size_t r = r0; r < r1; ++r) acc += x[r * N + n];
+  part[(size_t)blockIdx.y * N + n] = acc;
+}
+__global__ void k_colsum_final(const float* __restrict__ part, float* __restrict__ out, int parts,
+                               int N, int accumulate) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int p = 0; p < parts; ++p) acc += part[(size_t)p * N + n];
+  out[n] = accumulate ? out[n] + acc : acc;
+}
+
+// --------------------------------------------------------------------------- optimiser
+// stage 1: per-block sum of squares of the flat gradient (deterministic)
+__global__ void k_sumsq_partial(const float* __restrict__ g, double* __restrict__ part, size_t n) {
+  __shared__ double s[256];
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    double v = g[i];
+    acc += v * v;
+  }
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = s[0];
+}
+// stage 2: norm, clip coefficient (torch.nn.utils.clip_grad_norm_: coef = min(1, c/(norm+1e-6)))
+// stats[2] = grad_norm, stats[3] = clip coefficient applied
+__global__ void k_gradnorm_final(const double* __restrict__ part, int parts, float* __restrict__ stats,
+                                 float clip) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < parts; ++i) t += part[i];
+    float norm = (float)sqrt(t);
+    stats[2] = norm;
+    float coef = 1.f;
+    if (clip > 0.f) {
+      coef = clip / (norm + 1e-6f);
+      if (coef > 1.f) coef = 1.f;
+    }
+    stats[3] = coef;
+  }
+}
+// torch.optim.Adam single-tensor math (torch_trainer.py:82-83,199): one pass over the flat
+// parameter / gradient / moment buffers: 16 B read + 12 B written per parameter.
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, size_t n, const float* __restrict__ stats, float lr,
+                       float b1, float b2, float eps, float bc1, float bc2_sqrt) {
+  float coef = stats[3];
+  float step_size = lr / bc1;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * coef;
+    float mi = m[i] + (gi - m[i]) * (1.f - b1);       // exp_avg.lerp_(grad, 1 - beta1)
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+}  // namespace rtk

@@ -1,0 +1,858 @@
+// IQN / R2D2-style learner for B200 (sm_100a): nature-CNN -> [LSTM] -> FC -> IQN quantile +
+// dueling heads, double-Q n-step targets with value rescaling, quantile-Huber loss, global
+// grad-norm clip and Adam — every op a hand-written kernel (rt_kernels.cuh), no cuDNN/cuBLAS.
+//
+// Replaces, behind the C ABI of include/rltime_b200.h:
+//   rltime/models/torch/{sequential,modules/cnn,modules/lstm,modules/fc}.py   (forward)
+//   rltime/policies/torch/{dqn,iqn}.py                                        (heads)
+//   rltime/training/torch/{torch_trainer,dqn,iqn}.py                          (target, loss, step)
+//   rltime/training/multi_step_trainer.py:90-131                              (burn-in)
+//
+// Parameters live in one flat fp32 buffer per network (online / target) with matching flat
+// gradient and Adam-moment buffers, so clip + Adam + target sync are single passes.  Internal
+// weight layouts are permuted once at load time (conv filters to (f,kh,kw,c), CNN-feature
+// columns to (h,w,c)) so that activations can stay NHWC and every layer is a K-major GEMM.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "rt_common.h"
+#include "rt_kernels.cuh"
+
+namespace {
+
+struct ConvL {
+  int cin, hin, win, f, k, s, hout, wout, K;
+  size_t w, b;  // offsets in the flat parameter buffer
+};
+
+enum PermKind { PERM_NONE = 0, PERM_CONV = 1, PERM_FEAT_COLS = 2, PERM_FEAT_ROWS = 3 };
+
+struct PInfo {
+  std::string name;
+  std::vector<int> shape;
+  size_t off, count;
+  int perm;
+  int conv_c = 0, conv_k = 0;  // PERM_CONV geometry
+};
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+struct rt_learner {
+  rt_model_desc md;
+  rt_train_desc td;
+  int device = 0;
+  std::vector<ConvL> conv;
+  int featC = 0, featHW = 0, feat = 0;  // last conv output
+  int U = 0, D = 0, F = 0, A = 0, Nq = 0, E = 0;
+  bool dueling = false;
+  std::vector<PInfo> pinfo;
+  size_t nparams = 0;
+  // parameter offsets
+  size_t o_wih = 0, o_whh = 0, o_bih = 0, o_bhh = 0, o_fcw = 0, o_fcb = 0, o_outw = 0, o_outb = 0,
+         o_vhw = 0, o_vhb = 0, o_vw = 0, o_vb = 0, o_qw = 0, o_qb = 0;
+  float* p[2] = {nullptr, nullptr};  // 0 online, 1 target
+  float* grad = nullptr;
+  float* adam_m = nullptr;
+  float* adam_v = nullptr;
+  long long adam_t = 0;
+  float lr = 1e-3f;
+
+  // geometry
+  int B = 0, T = 0, P = 0, n = 0, S = 0;
+  int max_rows = 0;   // trunk rows per pass
+  int M = 0, MQ = 0;  // head rows (T*B) and quantile-expanded rows
+  int chunk_rows = 128;
+
+  // activations (one set; passes are sequential)
+  std::vector<float*> c_out;   // conv outputs
+  std::vector<float*> d_c;     // conv output grads
+  float *col = nullptr, *dcol = nullptr;
+  float *xg = nullptr, *hg = nullptr, *hprev = nullptr, *cprev = nullptr, *gates = nullptr,
+        *c_all = nullptr, *h_all = nullptr;
+  float *tau = nullptr, *cf = nullptr, *phi = nullptr, *xq = nullptr, *h1 = nullptr, *v1 = nullptr,
+        *adv = nullptr, *v = nullptr, *q = nullptr;
+  float *tq = nullptr, *sq = nullptr, *targets = nullptr;
+  float *dtheta = nullptr, *row_loss = nullptr, *report = nullptr, *stats = nullptr;
+  float *dadv = nullptr, *dv = nullptr, *dh1 = nullptr, *dv1 = nullptr, *dxq = nullptr, *dphi = nullptr,
+        *dfeatq = nullptr, *dgates = nullptr, *dh_carry = nullptr, *dc_carry = nullptr, *dfeat = nullptr;
+  float* ws = nullptr;
+  size_t ws_floats = 0;
+  float* colsum_part = nullptr;
+  double* sumsq_part = nullptr;
+  float* tau_stage = nullptr;  // device staging for injected taus (5 segments)
+  unsigned long long rng_counter = 0;
+  std::map<std::string, std::pair<void*, long long>> debug;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename T>
+int dalloc(rt_learner* h, T** p, size_t count, const char* name = nullptr) {
+  RT_CUDA(cudaMalloc(reinterpret_cast<void**>(p), (count ? count : 1) * sizeof(T)));
+  RT_CUDA(cudaMemset(*p, 0, (count ? count : 1) * sizeof(T)));
+  h->allocs.push_back(*p);
+  if (name) h->debug[name] = std::make_pair((void*)*p, (long long)count);
+  return RT_OK;
+}
+
+size_t add_param(rt_learner* h, const std::string& name, std::vector<int> shape, int perm,
+                 int conv_c = 0, int conv_k = 0) {
+  PInfo pi;
+  pi.name = name;
+  pi.shape = shape;
+  pi.count = 1;
+  for (int d : shape) pi.count *= (size_t)d;
+  pi.off = (h->nparams + 63) / 64 * 64;  // 256-byte aligned tensors
+  pi.perm = perm;
+  pi.conv_c = conv_c;
+  pi.conv_k = conv_k;
+  h->nparams = pi.off + pi.count;
+  h->pinfo.push_back(pi);
+  return pi.off;
+}
+
+// reference flat index -> internal flat index for one tensor
+size_t perm_index(const rt_learner* h, const PInfo& pi, size_t j) {
+  switch (pi.perm) {
+    case PERM_CONV: {  // [f][c][kh][kw] -> [f][kh][kw][c]
+      int C = pi.conv_c, K = pi.conv_k;
+      size_t per_f = (size_t)C * K * K;
+      size_t f = j / per_f, r = j % per_f;
+      int c = (int)(r / (K * K)), kh = (int)((r / K) % K), kw = (int)(r % K);
+      return f * per_f + ((size_t)kh * K + kw) * C + c;
+    }
+    case PERM_FEAT_COLS: {  // [rows][c*HW + hw] -> [rows][hw*C + c]
+      size_t cols = (size_t)h->feat;
+      size_t row = j / cols, col = j % cols;
+      int c = (int)(col / h->featHW), hw = (int)(col % h->featHW);
+      return row * cols + (size_t)hw * h->featC + c;
+    }
+    case PERM_FEAT_ROWS: {  // [c*HW + hw][inner] -> [hw*C + c][inner]
+      size_t inner = pi.count / (size_t)h->feat;
+      size_t row = j / inner, in = j % inner;
+      int c = (int)(row / h->featHW), hw = (int)(row % h->featHW);
+      return ((size_t)hw * h->featC + c) * inner + in;
+    }
+    default:
+      return j;
+  }
+}
+
+int gemm(rt_learner* h, cudaStream_t st, rtk::GemmArgs g) {
+  if (g.M <= 0 || g.N <= 0) return RT_OK;
+  constexpr int BM = 128, BN = 64, BK = 16;
+  int tm = cdiv(g.M, BM), tn = cdiv(g.N, BN);
+  long long tiles = (long long)tm * tn;
+  int splits = 1;
+  if (tiles < 148 && g.K >= 2048) {
+    splits = (int)((296 + tiles - 1) / tiles);
+    int maxs = g.K / 512;
+    if (splits > maxs) splits = maxs;
+    size_t per = (size_t)g.M * g.N;
+    if ((size_t)splits * per > h->ws_floats) splits = (int)(h->ws_floats / per);
+    if (splits < 1) splits = 1;
+  }
+  int kchunk = cdiv(g.K, splits);
+  kchunk = cdiv(kchunk, BK) * BK;
+  splits = cdiv(g.K, kchunk);
+  g.kchunk = kchunk;
+  g.ws = h->ws;
+  dim3 grid(tn, tm, splits);
+  rtk::k_sgemm<BM, BN, BK, 8, 4><<<grid, 256, 0, st>>>(g);
+  RT_LAUNCH_CHECK();
+  if (splits > 1) {
+    size_t total = (size_t)g.M * g.N;
+    rtk::k_splitk_reduce<<<cdiv(total, 256), 256, 0, st>>>(g, splits);
+    RT_LAUNCH_CHECK();
+  }
+  return RT_OK;
+}
+
+rtk::GemmArgs mk(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C,
+                 int ldc, int M, int N, int K) {
+  rtk::GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K;
+  g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.transA = transA; g.transB = transB;
+  g.alpha = 1.f;
+  return g;
+}
+
+int colsum(rt_learner* h, cudaStream_t st, const float* x, size_t rows, int N, float* out,
+           int accumulate) {
+  int rpb = 1024;
+  int parts = cdiv(rows, rpb);
+  if (parts > 2048) {
+    rpb = cdiv(rows, 2048);
+    parts = cdiv(rows, rpb);
+  }
+  dim3 grid(cdiv(N, 128), parts);
+  rtk::k_colsum_partial<<<grid, 128, 0, st>>>(x, h->colsum_part, rows, N, rpb);
+  RT_LAUNCH_CHECK();
+  rtk::k_colsum_final<<<cdiv(N, 128), 128, 0, st>>>(h->colsum_part, out, parts, N, accumulate);
+  RT_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+#define RT_TRY(x)            \
+  do {                       \
+    int rc__ = (x);          \
+    if (rc__ != RT_OK) return rc__; \
+  } while (0)
+
+int grid1d(size_t n, int threads = 256) {
+  size_t b = (n + threads - 1) / threads;
+  if (b > 148 * 32) b = 148 * 32;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// CNN forward for `rows` frames, chunked so the im2col buffers stay L2-resident.
+int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows) {
+  const float scale = (float)(1.0 / 255.0);
+  for (int r0 = 0; r0 < rows; r0 += h->chunk_rows) {
+    int rc = rows - r0 < h->chunk_rows ? rows - r0 : h->chunk_rows;
+    for (size_t i = 0; i < h->conv.size(); ++i) {
+      const ConvL& L = h->conv[i];
+      size_t opix = (size_t)L.hout * L.wout;
+      size_t n_col = (size_t)rc * opix * L.K;
+      if (i == 0) {
+        const uint8_t* xin = x + (size_t)r0 * L.cin * L.hin * L.win;
+        rtk::k_im2col_u8_nchw<<<grid1d(n_col), 256, 0, st>>>(xin, h->col, rc, L.cin, L.hin, L.win,
+                                                            L.k, L.s, L.hout, L.wout, scale);
+      } else {
+        const ConvL& Lp = h->conv[i - 1];
+        const float* xin = h->c_out[i - 1] + (size_t)r0 * Lp.hout * Lp.wout * Lp.f;
+        rtk::k_im2col_f32_nhwc<<<grid1d(n_col), 256, 0, st>>>(xin, h->col, rc, L.cin, L.hin, L.win,
+                                                             L.k, L.s, L.hout, L.wout);
+      }
+      RT_LAUNCH_CHECK();
+      float* out = h->c_out[i] + (size_t)r0 * opix * L.f;
+      rtk::GemmArgs g = mk(h->col, L.K, 0, net + L.w, L.K, 1, out, L.f, (int)(rc * opix), L.f, L.K);
+      g.bias = net + L.b;
+      g.relu = 1;
+      RT_TRY(gemm(h, st, g));
+    }
+  }
+  return RT_OK;
+}
+
+// LSTM forward over `rows` = timesteps * Beff time-major rows (lstm.py:50-122).
+int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int rows,
+                 int timesteps, const float* hx, const float* cx, const float* initials) {
+  int U = h->U, Beff = rows / timesteps;
+  rtk::GemmArgs g = mk(feat, h->feat, 0, net + h->o_wih, h->feat, 1, h->xg, 4 * U, rows, 4 * U, h->feat);
+  g.bias = net + h->o_bih;
+  g.bias2 = net + h->o_bhh;
+  RT_TRY(gemm(h, st, g));
+  int nb = cdiv((size_t)Beff * U, 256);
+  rtk::k_lstm_init<<<nb, 256, 0, st>>>(hx, cx, initials, h->hprev, h->cprev, Beff, U);
+  RT_LAUNCH_CHECK();
+  for (int t = 0; t < timesteps; ++t) {
+    size_t ro = (size_t)t * Beff;
+    rtk::GemmArgs gh = mk(h->hprev + ro * U, U, 0, net + h->o_whh, U, 1, h->hg, 4 * U, Beff, 4 * U, U);
+    RT_TRY(gemm(h, st, gh));
+    bool last = t == timesteps - 1;
+    rtk::k_lstm_cell<<<nb, 256, 0, st>>>(
+        h->xg + ro * 4 * U, h->hg, h->cprev + ro * U, h->gates + ro * 4 * U, h->c_all + ro * U,
+        h->h_all + ro * U, last ? nullptr : initials + ro + Beff,
+        last ? nullptr : h->hprev + (ro + Beff) * U, last ? nullptr : h->cprev + (ro + Beff) * U, Beff, U);
+    RT_LAUNCH_CHECK();
+  }
+  return RT_OK;
+}
+
+struct StateView {  // device pointers to the (rows, ...) leaves of a batch slice
+  const uint8_t* x;
+  float* hx;
+  float* cx;
+  const float* initials;
+};
+
+// CNN (+LSTM); returns the feature pointer [rows, D-or-feat] that feeds the heads.
+int trunk_forward(rt_learner* h, cudaStream_t st, const float* net, const StateView& sv, int rows,
+                  int timesteps, const float** feat_out) {
+  RT_TRY(cnn_forward(h, st, net, sv.x, rows));
+  const float* feat = h->c_out.back();
+  if (h->U) {
+    RT_TRY(lstm_forward(h, st, net, feat, rows, timesteps, sv.hx, sv.cx, sv.initials));
+    feat = h->h_all;
+  }
+  *feat_out = feat;
+  return RT_OK;
+}
+
+// IQN quantile layer + FC + out (+ dueling) on M rows (iqn.py:67-122, dqn.py:74-112).
+int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int M,
+                  const float* tau) {
+  int Nq = h->Nq, D = h->D, F = h->F, A = h->A, E = h->E;
+  size_t MQ = (size_t)M * Nq;
+  rtk::k_cos_features<<<cdiv(MQ * E, 256), 256, 0, st>>>(tau, h->cf, (int)MQ, E);
+  RT_LAUNCH_CHECK();
+  rtk::GemmArgs g = mk(h->cf, E, 0, net + h->o_qw, E, 1, h->phi, D, (int)MQ, D, E);
+  g.bias = net + h->o_qb;
+  g.relu = 1;
+  RT_TRY(gemm(h, st, g));
+  rtk::k_quantile_mul<<<cdiv(MQ * D, 256), 256, 0, st>>>(feat, h->phi, h->xq, MQ, D, Nq);
+  RT_LAUNCH_CHECK();
+  g = mk(h->xq, D, 0, net + h->o_fcw, D, 1, h->h1, F, (int)MQ, F, D);
+  g.bias = net + h->o_fcb;
+  g.relu = 1;
+  RT_TRY(gemm(h, st, g));
+  g = mk(h->h1, F, 0, net + h->o_outw, F, 1, h->adv, A, (int)MQ, A, F);
+  g.bias = net + h->o_outb;
+  RT_TRY(gemm(h, st, g));
+  if (h->dueling) {
+    g = mk(h->xq, D, 0, net + h->o_vhw, D, 1, h->v1, F, (int)MQ, F, D);
+    g.bias = net + h->o_vhb;
+    g.relu = 1;
+    RT_TRY(gemm(h, st, g));
+    g = mk(h->v1, F, 0, net + h->o_vw, F, 1, h->v, 1, (int)MQ, 1, F);
+    g.bias = net + h->o_vb;
+    RT_TRY(gemm(h, st, g));
+  }
+  rtk::k_dueling<<<cdiv(MQ, 256), 256, 0, st>>>(h->adv, h->dueling ? h->v : nullptr, h->q, MQ, A);
+  RT_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int M,
+                   const long long* actions) {
+  int Nq = h->Nq, D = h->D, F = h->F, A = h->A, E = h->E;
+  size_t MQ = (size_t)M * Nq;
+  float* G = h->grad;
+  rtk::k_dueling_bwd<<<cdiv(MQ, 256), 256, 0, st>>>(h->dtheta, actions, h->dadv,
+                                                   h->dueling ? h->dv : nullptr, MQ, A, Nq,
+                                                   h->dueling ? 1 : 0);
+  RT_LAUNCH_CHECK();
+  // out layer
+  RT_TRY(gemm(h, st, mk(h->dadv, A, 1, h->h1, F, 0, G + h->o_outw, F, A, F, (int)MQ)));
+  RT_TRY(colsum(h, st, h->dadv, MQ, A, G + h->o_outb, 0));
+  rtk::GemmArgs g = mk(h->dadv, A, 0, net + h->o_outw, F, 0, h->dh1, F, (int)MQ, F, A);
+  g.mask = h->h1;
+  g.ldmask = F;
+  RT_TRY(gemm(h, st, g));
+  // FC
+  RT_TRY(gemm(h, st, mk(h->dh1, F, 1, h->xq, D, 0, G + h->o_fcw, D, F, D, (int)MQ)));
+  RT_TRY(colsum(h, st, h->dh1, MQ, F, G + h->o_fcb, 0));
+  RT_TRY(gemm(h, st, mk(h->dh1, F, 0, net + h->o_fcw, D, 0, h->dxq, D, (int)MQ, D, F)));
+  if (h->dueling) {
+    RT_TRY(gemm(h, st, mk(h->dv, 1, 1, h->v1, F, 0, G + h->o_vw, F, 1, F, (int)MQ)));
+    RT_TRY(colsum(h, st, h->dv, MQ, 1, G + h->o_vb, 0));
+    g = mk(h->dv, 1, 0, net + h->o_vw, F, 0, h->dv1, F, (int)MQ, F, 1);
+    g.mask = h->v1;
+    g.ldmask = F;
+    RT_TRY(gemm(h, st, g));
+    RT_TRY(gemm(h, st, mk(h->dv1, F, 1, h->xq, D, 0, G + h->o_vhw, D, F, D, (int)MQ)));
+    RT_TRY(colsum(h, st, h->dv1, MQ, F, G + h->o_vhb, 0));
+    g = mk(h->dv1, F, 0, net + h->o_vhw, D, 0, h->dxq, D, (int)MQ, D, F);
+    g.accumulate = 1;
+    RT_TRY(gemm(h, st, g));
+  }
+  rtk::k_quantile_mul_bwd<<<cdiv((size_t)M * D, 256), 256, 0, st>>>(h->dxq, feat, h->phi, h->dphi,
+                                                                   h->dfeatq, M, D, Nq);
+  RT_LAUNCH_CHECK();
+  RT_TRY(gemm(h, st, mk(h->dphi, D, 1, h->cf, E, 0, G + h->o_qw, E, D, E, (int)MQ)));
+  RT_TRY(colsum(h, st, h->dphi, MQ, D, G + h->o_qb, 0));
+  return RT_OK;
+}
+
+// BPTT through the LSTM given dfeatq = d(loss)/d(h_all); produces dfeat (CNN features).
+int lstm_backward(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int rows,
+                  int timesteps, const float* initials) {
+  int U = h->U, Beff = rows / timesteps;
+  float* G = h->grad;
+  int nb = cdiv((size_t)Beff * U, 256);
+  RT_CUDA(cudaMemsetAsync(h->dc_carry, 0, (size_t)Beff * U * sizeof(float), st));
+  for (int t = timesteps - 1; t >= 0; --t) {
+    size_t ro = (size_t)t * Beff;
+    rtk::k_lstm_cell_bwd<<<nb, 256, 0, st>>>(
+        h->dfeatq + ro * U, t == timesteps - 1 ? nullptr : h->dh_carry, h->dc_carry,
+        h->gates + ro * 4 * U, h->c_all + ro * U, h->cprev + ro * U, initials + ro,
+        h->dgates + ro * 4 * U, Beff, U);
+    RT_LAUNCH_CHECK();
+    if (t > 0) {
+      RT_TRY(gemm(h, st, mk(h->dgates + ro * 4 * U, 4 * U, 0, net + h->o_whh, U, 0, h->dh_carry, U,
+                            Beff, U, 4 * U)));
+      rtk::k_mask_rows<<<nb, 256, 0, st>>>(h->dh_carry, initials + ro, Beff, U);
+      RT_LAUNCH_CHECK();
+    }
+  }
+  RT_TRY(gemm(h, st, mk(h->dgates, 4 * U, 1, h->hprev, U, 0, G + h->o_whh, U, 4 * U, U, rows)));
+  RT_TRY(gemm(h, st, mk(h->dgates, 4 * U, 1, feat, h->feat, 0, G + h->o_wih, h->feat, 4 * U, h->feat, rows)));
+  RT_TRY(colsum(h, st, h->dgates, rows, 4 * U, G + h->o_bih, 0));
+  RT_CUDA(cudaMemcpyAsync(G + h->o_bhh, G + h->o_bih, (size_t)4 * U * sizeof(float),
+                          cudaMemcpyDeviceToDevice, st));
+  RT_TRY(gemm(h, st, mk(h->dgates, 4 * U, 0, net + h->o_wih, h->feat, 0, h->dfeat, h->feat, rows,
+                        h->feat, 4 * U)));
+  return RT_OK;
+}
+
+// Conv stack backward; `dlast` = gradient w.r.t. the (post-ReLU) last conv output.
+int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows,
+                 float* dlast) {
+  const float scale = (float)(1.0 / 255.0);
+  float* G = h->grad;
+  int nl = (int)h->conv.size();
+  {
+    const ConvL& L = h->conv[nl - 1];
+    size_t n = (size_t)rows * L.hout * L.wout * L.f;
+    rtk::k_relu_bwd_inplace<<<grid1d(n), 256, 0, st>>>(dlast, h->c_out[nl - 1], n);
+    RT_LAUNCH_CHECK();
+  }
+  for (int r0 = 0; r0 < rows; r0 += h->chunk_rows) {
+    int rc = rows - r0 < h->chunk_rows ? rows - r0 : h->chunk_rows;
+    int first = r0 == 0;
+    for (int i = nl - 1; i >= 0; --i) {
+      const ConvL& L = h->conv[i];
+      size_t opix = (size_t)L.hout * L.wout;
+      size_t n_col = (size_t)rc * opix * L.K;
+      float* dy = (i == nl - 1 ? dlast : h->d_c[i]) + (size_t)r0 * opix * L.f;
+      // recompute this layer's im2col input
+      if (i == 0) {
+        const uint8_t* xin = x + (size_t)r0 * L.cin * L.hin * L.win;
+        rtk::k_im2col_u8_nchw<<<grid1d(n_col), 256, 0, st>>>(xin, h->col, rc, L.cin, L.hin, L.win,
+                                                            L.k, L.s, L.hout, L.wout, scale);
+      } else {
+        const ConvL& Lp = h->conv[i - 1];
+        const float* xin = h->c_out[i - 1] + (size_t)r0 * Lp.hout * Lp.wout * Lp.f;
+        rtk::k_im2col_f32_nhwc<<<grid1d(n_col), 256, 0, st>>>(xin, h->col, rc, L.cin, L.hin, L.win,
+                                                             L.k, L.s, L.hout, L.wout);
+      }
+      RT_LAUNCH_CHECK();
+      rtk::GemmArgs g = mk(dy, L.f, 1, h->col, L.K, 0, G + L.w, L.K, L.f, L.K, (int)(rc * opix));
+      g.accumulate = first ? 0 : 1;
+      RT_TRY(gemm(h, st, g));
+      RT_TRY(colsum(h, st, dy, (size_t)rc * opix, L.f, G + L.b, first ? 0 : 1));
+      if (i > 0) {
+        const ConvL& Lp = h->conv[i - 1];
+        RT_TRY(gemm(h, st, mk(dy, L.f, 0, net + L.w, L.K, 0, h->dcol, L.K, (int)(rc * opix), L.K, L.f)));
+        float* dxp = h->d_c[i - 1] + (size_t)r0 * Lp.hout * Lp.wout * Lp.f;
+        size_t n_in = (size_t)rc * L.hin * L.win * L.cin;
+        rtk::k_col2im_nhwc<<<grid1d(n_in), 256, 0, st>>>(h->dcol, dxp, rc, L.cin, L.hin, L.win, L.k,
+                                                        L.s, L.hout, L.wout);
+        RT_LAUNCH_CHECK();
+        rtk::k_relu_bwd_inplace<<<grid1d(n_in), 256, 0, st>>>(
+            dxp, h->c_out[i - 1] + (size_t)r0 * Lp.hout * Lp.wout * Lp.f, n_in);
+        RT_LAUNCH_CHECK();
+      }
+    }
+  }
+  return RT_OK;
+}
+
+__global__ void k_uniform(float* out, size_t n, unsigned long long seed, unsigned long long ctr) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (ctr + i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  out[i] = (float)(z >> 40) * (1.0f / 16777216.0f);  // 24-bit mantissa, [0, 1)
+}
+
+// masked write-back of the burned-in LSTM state into the batch (multi_step_trainer.py:117-126
+// + LSTM.get_state, lstm.py:150-152)
+__global__ void k_store_state(const float* __restrict__ h_last, const float* __restrict__ c_last,
+                              const float* __restrict__ initials, float* __restrict__ hx,
+                              float* __restrict__ cx, int B, int U) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * U) return;
+  float keep = 1.f - initials[i / U];
+  hx[i] = h_last[i] * keep;
+  cx[i] = c_last[i] * keep;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t device,
+                      rt_learner** out) {
+  RT_REQUIRE(md && td && out, "null argument");
+  RT_REQUIRE(md->num_conv >= 1 && md->num_conv <= RT_MAX_CONV, "num_conv out of range");
+  RT_REQUIRE(md->num_quantiles >= 1 && md->num_quantiles <= 256, "num_quantiles out of range");
+  RT_REQUIRE(md->num_actions >= 1 && md->num_actions <= 64, "num_actions out of range");
+  RT_REQUIRE(td->mbatch >= 1 && td->nstep_train >= 1 && td->burn_in >= 0 && td->nstep_target >= 1,
+             "bad batch geometry");
+  RT_CUDA(cudaSetDevice(device));
+  rt_learner* h = new rt_learner();
+  h->md = *md;
+  h->td = *td;
+  h->device = device;
+  h->U = md->lstm_units; h->F = md->fc_size; h->A = md->num_actions; h->Nq = md->num_quantiles;
+  h->E = md->embedding_dim; h->dueling = md->dueling != 0;
+  h->B = td->mbatch; h->T = td->nstep_train; h->P = td->burn_in; h->n = td->nstep_target;
+  h->S = h->T + h->P;
+  h->lr = (float)td->lr;
+  RT_REQUIRE(!(h->P > 0 && h->U == 0), "burn-in only makes sense for recurrent models");
+
+  int c = md->in_c, hh = md->in_h, ww = md->in_w;
+  for (int i = 0; i < md->num_conv; ++i) {
+    ConvL L;
+    L.cin = c; L.hin = hh; L.win = ww; L.f = md->conv_filters[i]; L.k = md->conv_kernel[i];
+    L.s = md->conv_stride[i];
+    RT_REQUIRE(L.f > 0 && L.k > 0 && L.s > 0 && L.k <= hh && L.k <= ww, "bad conv layer %d", i);
+    L.hout = (hh - L.k) / L.s + 1;
+    L.wout = (ww - L.k) / L.s + 1;
+    L.K = c * L.k * L.k;
+    char nm[96];
+    snprintf(nm, sizeof(nm), "model.layers.0.layers.%d.weight", i);
+    L.w = add_param(h, nm, {L.f, c, L.k, L.k}, i == 0 ? PERM_NONE : PERM_CONV, c, L.k);
+    snprintf(nm, sizeof(nm), "model.layers.0.layers.%d.bias", i);
+    L.b = add_param(h, nm, {L.f}, PERM_NONE);
+    h->conv.push_back(L);
+    c = L.f; hh = L.hout; ww = L.wout;
+  }
+  h->featC = c; h->featHW = hh * ww; h->feat = c * hh * ww;
+  int fc_layer = h->U ? 2 : 1;
+  if (h->U) {
+    int U = h->U;
+    h->o_wih = add_param(h, "model.layers.1.lstm_cell.weight_ih", {4 * U, h->feat}, PERM_FEAT_COLS);
+    h->o_whh = add_param(h, "model.layers.1.lstm_cell.weight_hh", {4 * U, U}, PERM_NONE);
+    h->o_bih = add_param(h, "model.layers.1.lstm_cell.bias_ih", {4 * U}, PERM_NONE);
+    h->o_bhh = add_param(h, "model.layers.1.lstm_cell.bias_hh", {4 * U}, PERM_NONE);
+    h->D = U;
+  } else {
+    h->D = h->feat;
+  }
+  int featperm_cols = h->U ? PERM_NONE : PERM_FEAT_COLS;
+  int featperm_rows = h->U ? PERM_NONE : PERM_FEAT_ROWS;
+  {
+    char nm[96];
+    snprintf(nm, sizeof(nm), "model.layers.%d.layers.0.0.weight", fc_layer);
+    h->o_fcw = add_param(h, nm, {h->F, h->D}, featperm_cols);
+    snprintf(nm, sizeof(nm), "model.layers.%d.layers.0.0.bias", fc_layer);
+    h->o_fcb = add_param(h, nm, {h->F}, PERM_NONE);
+  }
+  h->o_outw = add_param(h, "out_layer.weight", {h->A, h->F}, PERM_NONE);
+  h->o_outb = add_param(h, "out_layer.bias", {h->A}, PERM_NONE);
+  if (h->dueling) {
+    h->o_vhw = add_param(h, "value_hidden_layer.weight", {h->F, h->D}, featperm_cols);
+    h->o_vhb = add_param(h, "value_hidden_layer.bias", {h->F}, PERM_NONE);
+    h->o_vw = add_param(h, "value_layer.weight", {1, h->F}, PERM_NONE);
+    h->o_vb = add_param(h, "value_layer.bias", {1}, PERM_NONE);
+  }
+  h->o_qw = add_param(h, "quantile_layer.weight", {h->D, h->E}, featperm_rows);
+  h->o_qb = add_param(h, "quantile_layer.bias", {h->D}, featperm_rows);
+  h->nparams = (h->nparams + 63) / 64 * 64;
+
+  RT_TRY(dalloc(h, &h->p[0], h->nparams, "params_online"));
+  RT_TRY(dalloc(h, &h->p[1], h->nparams, "params_target"));
+  RT_TRY(dalloc(h, &h->grad, h->nparams, "grad"));
+  RT_TRY(dalloc(h, &h->adam_m, h->nparams, "adam_m"));
+  RT_TRY(dalloc(h, &h->adam_v, h->nparams, "adam_v"));
+
+  h->M = h->T * h->B;
+  h->MQ = h->M * h->Nq;
+  int burn_rows = h->P * h->B;
+  h->max_rows = h->M > burn_rows ? h->M : burn_rows;
+  size_t rows = (size_t)h->max_rows;
+  size_t maxcol = 0;
+  for (size_t i = 0; i < h->conv.size(); ++i) {
+    const ConvL& L = h->conv[i];
+    size_t opix = (size_t)L.hout * L.wout;
+    float *co = nullptr, *dco = nullptr;
+    char nm[32];
+    snprintf(nm, sizeof(nm), "c%d", (int)i);
+    RT_TRY(dalloc(h, &co, rows * opix * L.f, nm));
+    snprintf(nm, sizeof(nm), "dc%d", (int)i);
+    RT_TRY(dalloc(h, &dco, (size_t)h->M * opix * L.f, nm));
+    h->c_out.push_back(co);
+    h->d_c.push_back(dco);
+    size_t cc = (size_t)h->chunk_rows * opix * L.K;
+    if (cc > maxcol) maxcol = cc;
+  }
+  RT_TRY(dalloc(h, &h->col, maxcol));
+  RT_TRY(dalloc(h, &h->dcol, maxcol));
+  if (h->U) {
+    size_t U = h->U;
+    RT_TRY(dalloc(h, &h->xg, rows * 4 * U, "xg"));
+    RT_TRY(dalloc(h, &h->hg, rows * 4 * U, "hg"));
+    RT_TRY(dalloc(h, &h->hprev, rows * U, "hprev"));
+    RT_TRY(dalloc(h, &h->cprev, rows * U, "cprev"));
+    RT_TRY(dalloc(h, &h->gates, rows * 4 * U, "gates"));
+    RT_TRY(dalloc(h, &h->c_all, rows * U, "c_all"));
+    RT_TRY(dalloc(h, &h->h_all, rows * U, "h_all"));
+    RT_TRY(dalloc(h, &h->dgates, (size_t)h->M * 4 * U, "dgates"));
+    RT_TRY(dalloc(h, &h->dh_carry, (size_t)h->M * U));
+    RT_TRY(dalloc(h, &h->dc_carry, (size_t)h->M * U));
+    RT_TRY(dalloc(h, &h->dfeat, (size_t)h->M * h->feat, "dfeat"));
+  }
+  size_t MQ = h->MQ, D = h->D, F = h->F, A = h->A;
+  RT_TRY(dalloc(h, &h->tau, MQ, "tau"));
+  RT_TRY(dalloc(h, &h->tau_stage, MQ * 3));
+  RT_TRY(dalloc(h, &h->cf, MQ * h->E, "cf"));
+  RT_TRY(dalloc(h, &h->phi, MQ * D, "phi"));
+  RT_TRY(dalloc(h, &h->xq, MQ * D, "xq"));
+  RT_TRY(dalloc(h, &h->h1, MQ * F, "h1"));
+  RT_TRY(dalloc(h, &h->v1, MQ * F, "v1"));
+  RT_TRY(dalloc(h, &h->adv, MQ * A, "adv"));
+  RT_TRY(dalloc(h, &h->v, MQ, "v"));
+  RT_TRY(dalloc(h, &h->q, MQ * A, "q"));
+  RT_TRY(dalloc(h, &h->tq, MQ * A, "tq"));
+  RT_TRY(dalloc(h, &h->sq, MQ * A, "sq"));
+  RT_TRY(dalloc(h, &h->targets, MQ, "targets"));
+  RT_TRY(dalloc(h, &h->dtheta, MQ, "dtheta"));
+  RT_TRY(dalloc(h, &h->row_loss, (size_t)h->M, "row_loss"));
+  RT_TRY(dalloc(h, &h->report, (size_t)h->M, "report"));
+  RT_TRY(dalloc(h, &h->stats, 8, "stats"));
+  RT_TRY(dalloc(h, &h->dadv, MQ * A, "dadv"));
+  RT_TRY(dalloc(h, &h->dv, MQ, "dv"));
+  RT_TRY(dalloc(h, &h->dh1, MQ * F, "dh1"));
+  RT_TRY(dalloc(h, &h->dv1, MQ * F, "dv1"));
+  RT_TRY(dalloc(h, &h->dxq, MQ * D, "dxq"));
+  RT_TRY(dalloc(h, &h->dphi, MQ * D, "dphi"));
+  RT_TRY(dalloc(h, &h->dfeatq, (size_t)h->M * D, "dfeatq"));
+  h->ws_floats = (size_t)64 << 20;  // 256 MiB split-K workspace
+  RT_TRY(dalloc(h, &h->ws, h->ws_floats));
+  size_t maxN = 4 * (size_t)(h->U ? h->U : 1);
+  if (D > maxN) maxN = D;
+  if (F > maxN) maxN = F;
+  if (A > maxN) maxN = A;
+  for (auto& L : h->conv)
+    if ((size_t)L.f > maxN) maxN = L.f;
+  RT_TRY(dalloc(h, &h->colsum_part, 2048 * maxN));
+  RT_TRY(dalloc(h, &h->sumsq_part, 1024));
+  *out = h;
+  return RT_OK;
+}
+
+void rt_learner_destroy(rt_learner* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+int32_t rt_learner_num_params(const rt_learner* h) { return h ? (int32_t)h->pinfo.size() : 0; }
+int64_t rt_learner_num_weights(const rt_learner* h) {
+  int64_t n = 0;
+  if (h)
+    for (auto& pi : h->pinfo) n += (int64_t)pi.count;
+  return n;
+}
+
+int rt_learner_param_info(const rt_learner* h, int32_t i, char* name, int32_t name_cap,
+                          int64_t* shape4, int32_t* ndim) {
+  RT_REQUIRE(h && i >= 0 && i < (int)h->pinfo.size() && name && shape4 && ndim, "bad argument");
+  const PInfo& pi = h->pinfo[i];
+  snprintf(name, name_cap, "%s", pi.name.c_str());
+  *ndim = (int)pi.shape.size();
+  for (int d = 0; d < 4; ++d) shape4[d] = d < (int)pi.shape.size() ? pi.shape[d] : 1;
+  return RT_OK;
+}
+
+static float* which_buffer(rt_learner* h, int which) {
+  switch (which) {
+    case RT_BUF_ONLINE: return h->p[0];
+    case RT_BUF_TARGET: return h->p[1];
+    case RT_BUF_GRAD: return h->grad;
+    case RT_BUF_ADAM_M: return h->adam_m;
+    case RT_BUF_ADAM_V: return h->adam_v;
+  }
+  return nullptr;
+}
+
+int rt_learner_load_params(rt_learner* h, int32_t which, const float* const* tensors) {
+  RT_REQUIRE(h && tensors, "null argument");
+  float* dst = which_buffer(h, which);
+  RT_REQUIRE(dst, "bad buffer selector");
+  RT_CUDA(cudaSetDevice(h->device));
+  std::vector<float> flat(h->nparams, 0.f);
+  for (size_t i = 0; i < h->pinfo.size(); ++i) {
+    const PInfo& pi = h->pinfo[i];
+    for (size_t j = 0; j < pi.count; ++j) flat[pi.off + perm_index(h, pi, j)] = tensors[i][j];
+  }
+  RT_CUDA(cudaMemcpy(dst, flat.data(), h->nparams * sizeof(float), cudaMemcpyHostToDevice));
+  return RT_OK;
+}
+
+int rt_learner_get_params(rt_learner* h, int32_t which, float* const* tensors) {
+  RT_REQUIRE(h && tensors, "null argument");
+  float* src = which_buffer(h, which);
+  RT_REQUIRE(src, "bad buffer selector");
+  RT_CUDA(cudaSetDevice(h->device));
+  RT_CUDA(cudaDeviceSynchronize());
+  std::vector<float> flat(h->nparams);
+  RT_CUDA(cudaMemcpy(flat.data(), src, h->nparams * sizeof(float), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < h->pinfo.size(); ++i) {
+    const PInfo& pi = h->pinfo[i];
+    for (size_t j = 0; j < pi.count; ++j) tensors[i][j] = flat[pi.off + perm_index(h, pi, j)];
+  }
+  return RT_OK;
+}
+
+int rt_learner_sync_target(rt_learner* h, void* stream) {
+  RT_REQUIRE(h, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  // TorchPolicy.copy_from with factor 1.0 (torch_policy.py:61-68): one flat copy
+  RT_CUDA(cudaMemcpyAsync(h->p[1], h->p[0], h->nparams * sizeof(float), cudaMemcpyDeviceToDevice,
+                          (cudaStream_t)stream));
+  return RT_OK;
+}
+
+int rt_learner_set_lr(rt_learner* h, double lr) {
+  RT_REQUIRE(h, "null argument");
+  h->lr = (float)lr;
+  return RT_OK;
+}
+
+int rt_learner_step(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
+                    const float* const* taus_host, void* stream) {
+  RT_REQUIRE(h && b && io, "null argument");
+  RT_REQUIRE(b->B == h->B && b->S == h->S && b->n == h->n,
+             "batch geometry (B=%d,S=%d,n=%d) does not match the learner (B=%d,S=%d,n=%d)", b->B,
+             b->S, b->n, h->B, h->S, h->n);
+  RT_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = h->B, T = h->T, P = h->P, n = h->n, U = h->U, M = h->M, Nq = h->Nq;
+  const size_t frame = (size_t)h->md.in_c * h->md.in_h * h->md.in_w;
+  const uint8_t* all_x = (const uint8_t*)b->all_states[io->field_x];
+  float* all_hx = U ? (float*)b->all_states[io->field_hx] : nullptr;
+  float* all_cx = U ? (float*)b->all_states[io->field_cx] : nullptr;
+  const float* all_init = U ? (const float*)b->all_states[io->field_initials] : nullptr;
+  auto view = [&](int row0) {
+    StateView sv;
+    sv.x = all_x + (size_t)row0 * B * frame;
+    sv.hx = U ? all_hx + (size_t)row0 * B * U : nullptr;
+    sv.cx = U ? all_cx + (size_t)row0 * B * U : nullptr;
+    sv.initials = U ? all_init + (size_t)row0 * B : nullptr;
+    return sv;
+  };
+  const float* feat = nullptr;
+  const int rnn_boot = h->td.rnn_bootstrap ? 1 : 0;
+
+  // ---- burn-in (multi_step_trainer.py:90-131): only the recurrent state is needed, so the
+  // heads the reference also evaluates are skipped.  states / target_states alias one stack,
+  // and the write-back order (online first) is the reference's.
+  if (P > 0) {
+    for (int pass = 0; pass < 1 + rnn_boot; ++pass) {
+      int row0 = pass == 0 ? 0 : n;
+      StateView sv = view(row0);
+      RT_TRY(trunk_forward(h, st, h->p[pass], sv, P * B, P, &feat));
+      StateView dst = view(row0 + P);
+      size_t last = (size_t)(P - 1) * B * U;
+      k_store_state<<<cdiv((size_t)B * U, 256), 256, 0, st>>>(h->h_all + last, h->c_all + last,
+                                                             dst.initials, dst.hx, dst.cx, B, U);
+      RT_LAUNCH_CHECK();
+    }
+  }
+
+  // ---- quantile fractions: injected (parity) or drawn on the device
+  const float* tau_seg[3];
+  for (int s = 0; s < 3; ++s) {
+    float* dst = h->tau_stage + (size_t)s * h->MQ;
+    if (taus_host && taus_host[s]) {
+      RT_CUDA(cudaMemcpyAsync(dst, taus_host[s], (size_t)h->MQ * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+      k_uniform<<<cdiv(h->MQ, 256), 256, 0, st>>>(dst, (size_t)h->MQ, h->td.seed, h->rng_counter);
+      RT_LAUNCH_CHECK();
+      h->rng_counter += (unsigned long long)h->MQ;
+    }
+    tau_seg[s] = dst;
+  }
+
+  // ---- bootstrap target (iqn.py:15-52): target net, then the action-selection net
+  {
+    StateView sv = view(P + n);
+    int ts = rnn_boot ? T : 1;
+    RT_TRY(trunk_forward(h, st, h->p[1], sv, M, ts, &feat));
+    RT_TRY(heads_forward(h, st, h->p[1], feat, M, tau_seg[0]));
+    RT_CUDA(cudaMemcpyAsync(h->tq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const float* sel = h->td.double_q ? h->p[0] : h->p[1];
+    RT_TRY(trunk_forward(h, st, sel, sv, M, ts, &feat));
+    RT_TRY(heads_forward(h, st, sel, feat, M, tau_seg[1]));
+    RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    size_t off = (size_t)P * B;
+    rtk::k_iqn_target<<<cdiv(M, 128), 128, 0, st>>>(
+        h->tq, h->sq, b->returns + off, b->target_masks + off, (const long long*)b->nsteps + off,
+        h->targets, M, Nq, h->A, (float)h->td.gamma, h->td.vf_scale_epsilon);
+    RT_LAUNCH_CHECK();
+  }
+
+  // ---- training forward + loss (iqn.py:54-129)
+  StateView svt = view(P);
+  RT_TRY(trunk_forward(h, st, h->p[0], svt, M, T, &feat));
+  RT_TRY(heads_forward(h, st, h->p[0], feat, M, tau_seg[2]));
+  RT_CUDA(cudaMemcpyAsync(h->tau, tau_seg[2], (size_t)h->MQ * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const long long* actions = (const long long*)b->policy_outputs[io->po_field_actions] + (size_t)P * B;
+  const double* weights = b->importance_weights ? b->importance_weights + (size_t)P * B : nullptr;
+  {
+    int threads = ((Nq + 31) / 32) * 32;
+    size_t smem = (3 * (size_t)Nq + 2 * threads) * sizeof(float);
+    float gscale = h->td.loss_sum ? 1.f : 1.f / (float)M;
+    rtk::k_iqn_loss<<<M, threads, smem, st>>>(h->q, h->targets, h->tau, actions, weights, h->dtheta,
+                                             h->row_loss, h->report, Nq, h->A,
+                                             (float)h->td.huber_kappa, gscale);
+    RT_LAUNCH_CHECK();
+    rtk::k_loss_stats<<<1, 256, 0, st>>>(h->row_loss, h->report, h->stats, M, h->td.loss_sum ? 0 : 1);
+    RT_LAUNCH_CHECK();
+  }
+
+  // ---- backward
+  RT_CUDA(cudaMemsetAsync(h->grad, 0, h->nparams * sizeof(float), st));
+  RT_TRY(heads_backward(h, st, h->p[0], feat, M, actions));
+  float* dlast = h->dfeatq;
+  if (U) {
+    RT_TRY(lstm_backward(h, st, h->p[0], h->c_out.back(), M, T, svt.initials));
+    dlast = h->dfeat;
+  }
+  RT_TRY(cnn_backward(h, st, h->p[0], svt.x, M, dlast));
+
+  // ---- grad-norm, clip, Adam (torch_trainer.py:177-199)
+  {
+    int parts = 512;
+    rtk::k_sumsq_partial<<<parts, 256, 0, st>>>(h->grad, h->sumsq_part, h->nparams);
+    RT_LAUNCH_CHECK();
+    rtk::k_gradnorm_final<<<1, 32, 0, st>>>(h->sumsq_part, parts, h->stats,
+                                           h->td.clip_grad > 0 ? (float)h->td.clip_grad : 0.f);
+    RT_LAUNCH_CHECK();
+    h->adam_t++;
+    double b1 = 0.9, b2 = 0.999;
+    float bc1 = (float)(1.0 - std::pow(b1, (double)h->adam_t));
+    float bc2s = (float)std::sqrt(1.0 - std::pow(b2, (double)h->adam_t));
+    rtk::k_adam<<<grid1d(h->nparams), 256, 0, st>>>(h->p[0], h->grad, h->adam_m, h->adam_v, h->nparams,
+                                                   h->stats, h->lr, (float)b1, (float)b2,
+                                                   (float)h->td.adam_epsilon, bc1, bc2s);
+    RT_LAUNCH_CHECK();
+  }
+  return RT_OK;
+}
+
+int rt_learner_td_abs(rt_learner* h, float** out_device) {
+  RT_REQUIRE(h && out_device, "null argument");
+  *out_device = h->report;
+  return RT_OK;
+}
+
+int rt_learner_read_stats(rt_learner* h, float* loss, float* td_mean, float* grad_norm, void* stream) {
+  RT_REQUIRE(h, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  float s[4];
+  RT_CUDA(cudaMemcpyAsync(s, h->stats, sizeof(s), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  RT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (loss) *loss = s[0];
+  if (td_mean) *td_mean = s[1];
+  if (grad_norm) *grad_norm = s[2];
+  return RT_OK;
+}
+
+int rt_learner_debug_tensor(rt_learner* h, const char* name, void** dev_ptr, int64_t* count) {
+  RT_REQUIRE(h && name && dev_ptr && count, "null argument");
+  auto it = h->debug.find(name);
+  RT_REQUIRE(it != h->debug.end(), "no debug tensor named '%s'", name);
+  *dev_ptr = it->second.first;
+  *count = it->second.second;
+  return RT_OK;
+}
+
+}  // extern "C"

@@ -138,6 +138,7 @@ class DeviceReplayHistoryBuffer:
         self._state_skel = None
         self._po_skel = None
         self.last_sampled_idxes = None
+        self.last_batch = None
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -321,6 +322,7 @@ class DeviceReplayHistoryBuffer:
     def _wrap_batch(self):
         b = _lib.Batch()
         _lib.check(self._lib.rt_replay_batch(self._h, C.byref(b)))
+        self.last_batch = b      # raw device view of the draw (input of DeviceLearner.step)
         B, S, n = b.B, b.S, b.n
         dev = self.device
         states, targets = [], []

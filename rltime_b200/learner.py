@@ -1,0 +1,189 @@
+"""Host-side handle of the CUDA learner (rt_learner_* in include/rltime_b200.h).
+
+Mirrors the parts of the reference a trainer touches on the learner side:
+  IQNPolicy / DQNPolicy state (state_dict names, get_state / load_state,
+      rltime/policies/torch/torch_policy.py:97-101),
+  TorchTrainer.train_batch / calc_target_values / set_lr (training/torch/torch_trainer.py),
+  PolicyTrainer.sync_target (training/policy_trainer.py:68-70).
+No CPU fallback: construction fails without the built library and a CUDA device.
+"""
+import ctypes as C
+import io
+
+import numpy as np
+
+from . import _lib
+
+
+class DeviceLearner:
+    def __init__(self, in_shape, conv, lstm_units, fc_size, num_actions, num_quantiles=32,
+                 embedding_dim=64, dueling=True, *, mbatch, nstep_train, burn_in=0,
+                 nstep_target=1, gamma=0.99, double_q=False, rnn_bootstrap=False,
+                 vf_scale_epsilon=None, huber_kappa=1.0, clip_grad=None, adam_epsilon=1e-8,
+                 lr=1e-3, loss_aggregation="mean", seed=0, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.RtError("rltime_b200 learner needs a CUDA device (no CPU fallback)")
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        md = _lib.ModelDesc()
+        md.in_c, md.in_h, md.in_w = in_shape
+        md.num_conv = len(conv)
+        for i, (f, k, s) in enumerate(conv):
+            md.conv_filters[i], md.conv_kernel[i], md.conv_stride[i] = f, k, s
+        md.lstm_units = lstm_units
+        md.fc_size = fc_size
+        md.num_actions = num_actions
+        md.num_quantiles = num_quantiles
+        md.embedding_dim = embedding_dim
+        md.dueling = 1 if dueling else 0
+        td = _lib.TrainDesc()
+        td.mbatch, td.nstep_train, td.burn_in, td.nstep_target = mbatch, nstep_train, burn_in, nstep_target
+        td.double_q = 1 if double_q else 0
+        td.rnn_bootstrap = 1 if rnn_bootstrap else 0
+        assert loss_aggregation in ("mean", "sum")
+        td.loss_sum = 1 if loss_aggregation == "sum" else 0
+        td.gamma = gamma
+        td.vf_scale_epsilon = vf_scale_epsilon or 0.0
+        td.huber_kappa = huber_kappa
+        td.clip_grad = clip_grad or 0.0
+        td.adam_epsilon = adam_epsilon
+        td.lr = lr
+        td.seed = seed
+        self.B, self.T, self.P, self.n = mbatch, nstep_train, burn_in, nstep_target
+        self.Nq, self.A, self.U = num_quantiles, num_actions, lstm_units
+        h = C.c_void_p()
+        _lib.check(self._lib.rt_learner_create(C.byref(md), C.byref(td), self.device.index or 0,
+                                               C.byref(h)))
+        self._h = h
+        self.param_info = []
+        for i in range(self._lib.rt_learner_num_params(self._h)):
+            name = C.create_string_buffer(128)
+            shape = (C.c_int64 * 4)()
+            nd = C.c_int32()
+            _lib.check(self._lib.rt_learner_param_info(self._h, i, name, 128, shape, C.byref(nd)))
+            self.param_info.append((name.value.decode(), tuple(shape[:nd.value])))
+        self.io = _lib.LearnerIO(0, 1, 2, 3, 0)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._lib.rt_learner_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- parameters ---------------------------------------------------------------
+    def load_state_dict(self, sd, which=_lib.RT_BUF_ONLINE):
+        arrs = []
+        for name, shape in self.param_info:
+            a = sd[name]
+            a = a.detach().cpu().numpy() if hasattr(a, "detach") else np.asarray(a)
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            assert a.shape == shape, (name, a.shape, shape)
+            arrs.append(a)
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        _lib.check(self._lib.rt_learner_load_params(self._h, which, C.cast(ptrs, C.c_void_p)))
+
+    def state_dict(self, which=_lib.RT_BUF_ONLINE):
+        import torch
+        arrs = [np.empty(shape, dtype=np.float32) for _, shape in self.param_info]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        _lib.check(self._lib.rt_learner_get_params(self._h, which, C.cast(ptrs, C.c_void_p)))
+        return {name: torch.from_numpy(a) for (name, _), a in zip(self.param_info, arrs)}
+
+    def get_state(self):
+        """Same bytes contract as TorchPolicy.get_state (torch_policy.py:97-98): a torch-saved
+        state_dict with the reference's parameter names (+ the embedding_range buffer)."""
+        import torch
+        sd = self.state_dict()
+        sd["embedding_range"] = torch.arange(
+            1, self.param_info[-2][1][1] + 1, dtype=torch.float32)
+        f = io.BytesIO()
+        torch.save(sd, f)
+        return f.getvalue()
+
+    def load_state(self, state):
+        import torch
+        sd = torch.load(io.BytesIO(state), map_location="cpu")
+        self.load_state_dict(sd)
+
+    def sync_target(self):
+        _lib.check(self._lib.rt_learner_sync_target(self._h, self._stream()))
+
+    def set_lr(self, lr):
+        _lib.check(self._lib.rt_learner_set_lr(self._h, float(lr)))
+
+    # ---- update -------------------------------------------------------------------
+    def step(self, batch, taus=None, io=None):
+        """batch: ctypes _lib.Batch (from a device history buffer or hand-built)."""
+        tp = None
+        keep = []
+        if taus is not None:
+            arr = (C.c_void_p * 3)()
+            for i, t in enumerate(taus):
+                a = np.ascontiguousarray(t.detach().cpu().numpy() if hasattr(t, "detach") else t,
+                                         dtype=np.float32)
+                assert a.size == self.T * self.B * self.Nq
+                keep.append(a)
+                arr[i] = a.ctypes.data
+            tp = C.cast(arr, C.c_void_p)
+        _lib.check(self._lib.rt_learner_step(self._h, C.byref(batch), C.byref(io or self.io), tp,
+                                             self._stream()))
+
+    def td_abs(self):
+        p = C.c_void_p()
+        _lib.check(self._lib.rt_learner_td_abs(self._h, C.byref(p)))
+        return _lib.as_tensor(p.value, (self.T * self.B,), "<f4", self.device)
+
+    def stats(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        _lib.check(self._lib.rt_learner_read_stats(self._h, C.byref(a), C.byref(b), C.byref(c),
+                                                   self._stream()))
+        return {"qloss": a.value, "td_mean": b.value, "grad_norm": c.value}
+
+    def debug(self, name, shape=None):
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(self._lib.rt_learner_debug_tensor(self._h, name.encode(), C.byref(p), C.byref(n)))
+        t = _lib.as_tensor(p.value, (n.value,), "<f4", self.device)
+        return t if shape is None else t[:int(np.prod(shape))].view(*shape)
+
+
+def batch_from_tensors(all_x, all_hx, all_cx, all_initials, returns, nsteps, target_masks, actions,
+                       importance_weights, n):
+    """Builds an rt_batch over caller-owned CUDA tensors (time-major, (S+n, B, ...) / (S, B)).
+    Returns (Batch, keepalive list)."""
+    b = _lib.Batch()
+    S, B = returns.shape
+    b.B, b.S, b.n = B, S, n
+    keep = []
+
+    def ptr(t, dtype):
+        assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), (t.dtype, dtype)
+        keep.append(t)
+        return t.data_ptr()
+    import torch
+    b.all_states[0] = ptr(all_x, torch.uint8)
+    nf = 1
+    if all_hx is not None:
+        b.all_states[1] = ptr(all_hx, torch.float32)
+        b.all_states[2] = ptr(all_cx, torch.float32)
+        b.all_states[3] = ptr(all_initials, torch.float32)
+        nf = 4
+    b.num_state_fields = nf
+    b.policy_outputs[0] = ptr(actions, torch.int64)
+    b.num_po_fields = 1
+    b.returns = ptr(returns, torch.float64)
+    b.nsteps = ptr(nsteps, torch.int64)
+    b.target_masks = ptr(target_masks, torch.float64)
+    if importance_weights is not None:
+        b.importance_weights = ptr(importance_weights, torch.float64)
+    return b, keep

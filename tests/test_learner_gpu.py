@@ -1,0 +1,152 @@
+"""CUDA learner vs the reference trainer's golden results and vs the torch fp32 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import learner_oracle as lo
+from oracle.learner_cases import CASES, batch_of, params_of, spec_of, taus_of
+from tests.util import load_golden
+
+
+def make_learner(c, **kw):
+    from rltime_b200.learner import DeviceLearner
+    return DeviceLearner(c["in_shape"], c["conv"], c["lstm"], c["fc"], c["actions"], c["nq"],
+                         c["embed"], c["dueling"], mbatch=c["B"], nstep_train=c["T"],
+                         burn_in=c["P"], nstep_target=c["n"], gamma=c["gamma"],
+                         double_q=c["double_q"], rnn_bootstrap=c["rnn_bootstrap"],
+                         vf_scale_epsilon=c["vf_eps"], clip_grad=c["clip_grad"],
+                         adam_epsilon=c["adam_eps"], lr=1e-3, **kw)
+
+
+def device_batch(raw, c):
+    from rltime_b200.learner import batch_from_tensors
+    dev = "cuda"
+    t = lambda k, dt=None: torch.from_numpy(raw[k].copy()).to(dev)
+    has = c["lstm"] > 0
+    return batch_from_tensors(
+        t("all_x"), t("all_hx") if has else None, t("all_cx") if has else None,
+        t("all_initials") if has else None, t("returns"), t("nsteps"), t("target_masks"),
+        t("actions"), t("importance_weights"), c["n"])
+
+
+def report_diff(errs, name, got, want, rtol, atol):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    if got.shape != want.shape:
+        errs.append("%s: shape %s vs %s" % (name, got.shape, want.shape))
+        return
+    bad = np.abs(got - want) > atol + rtol * np.abs(want)
+    if bad.any():
+        i = np.argmax(np.abs(got - want))
+        errs.append("%s: %d/%d off, max|d|=%.3e (got %.6g want %.6g)" % (
+            name, bad.sum(), bad.size, np.abs(got - want).max(), got.flat[i], want.flat[i]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_learner_matches_reference_golden(name):
+    c = CASES[name]
+    g = load_golden("learner_%s.npz" % name)
+    L = make_learner(c)
+    try:
+        L.load_state_dict(params_of(g, "online"), 0)
+        L.load_state_dict(params_of(g, "target"), 1)
+        # parameter layout round-trip (permuted internal layouts)
+        back = L.state_dict(0)
+        for k, v in params_of(g, "online").items():
+            np.testing.assert_array_equal(back[k].numpy(), v.numpy())
+        errs = []
+        M, Nq = c["T"] * c["B"], c["nq"]
+        for u in range(c["updates"]):
+            _, raw = batch_of(g, c, u)
+            b, keep = device_batch(raw, c)
+            taus = taus_of(g, u)
+            L.step(b, [taus["target"], taus["select"], taus["train"]])
+            st = L.stats()
+            pre = "u%d/" % u
+            # fp32 tolerance of the parity bar: TD-loss / targets within 1e-4 absolute
+            report_diff(errs, pre + "targets", L.debug("targets", (M, Nq)).cpu().numpy(),
+                        g[pre + "targets"], 1e-4, 1e-5)
+            report_diff(errs, pre + "qloss", st["qloss"], g[pre + "qloss"], 1e-4, 1e-5)
+            report_diff(errs, pre + "td_mean", st["td_mean"], g[pre + "td_mean"], 1e-4, 1e-5)
+            report_diff(errs, pre + "report", L.td_abs().cpu().numpy(), g[pre + "report"], 1e-4, 1e-5)
+            report_diff(errs, pre + "grad_norm", st["grad_norm"], g[pre + "grad_norm"], 1e-3, 1e-6)
+            grads = L.state_dict(2)
+            coef = 1.0
+            if c["clip_grad"]:
+                coef = min(1.0, c["clip_grad"] / (float(g[pre + "grad_norm"]) + 1e-6))
+            after = L.state_dict(0)
+            for k in grads:
+                # golden grads are post-clip; ours are stored pre-clip
+                report_diff(errs, pre + "grad/" + k, grads[k].numpy() * coef, g[pre + "grad/" + k],
+                            2e-3, 2e-6)
+                report_diff(errs, pre + "after/" + k, after[k].numpy(), g[pre + "after/" + k],
+                            1e-4, 2e-5)
+        assert not errs, "\n".join(errs)
+    finally:
+        L.close()
+
+
+@pytest.mark.gpu
+def test_learner_full_size_vs_oracle():
+    """Config-3 shapes (nature CNN, LSTM 512, FC 512, Nq 32, B 32, T 20): one update against
+    the torch fp32 oracle run on the host CPU."""
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    c = dict(in_shape=(4, 84, 84), conv=[(32, 8, 4), (64, 4, 2), (64, 3, 1)], lstm=512, fc=512,
+             actions=6, nq=32, embed=64, dueling=True, B=32, T=20, P=0, n=2, gamma=0.99,
+             double_q=True, rnn_bootstrap=True, vf_eps=None, clip_grad=40.0, adam_eps=1e-5)
+    spec = spec_of(c)
+    p_on, p_tg = spec.init_params(1), spec.init_params(2)
+    rs = np.random.RandomState(0)
+    S, B, n, M = c["T"], c["B"], c["n"], c["T"] * c["B"]
+    raw = {
+        "all_x": rs.randint(0, 256, (S + n, B, 4, 84, 84)).astype(np.uint8),
+        "all_hx": rs.randn(S + n, B, 512).astype(np.float32),
+        "all_cx": rs.randn(S + n, B, 512).astype(np.float32),
+        "all_initials": (rs.rand(S + n, B) < 0.02).astype(np.float32),
+        "returns": np.sign(rs.randn(S, B)), "nsteps": np.full((S, B), n, dtype=np.int64),
+        "target_masks": (rs.rand(S, B) > 0.05).astype(np.float64),
+        "actions": rs.randint(0, 6, (S, B)).astype(np.int64),
+        "importance_weights": rs.rand(S, B) * 0.5 + 0.5,
+    }
+    gen = torch.Generator().manual_seed(3)
+    taus = {k: torch.rand(M * 32, generator=gen) for k in ("target", "select", "train")}
+    allt = {k: torch.from_numpy(v.copy()) for k, v in raw.items()}
+
+    def st(lo_, hi):
+        return {"x": allt["all_x"][lo_:hi], "layer1_state": {
+            "hx": allt["all_hx"][lo_:hi], "cx": allt["all_cx"][lo_:hi],
+            "initials": allt["all_initials"][lo_:hi]}}
+    batch = {"states": st(0, S), "target_states": st(n, S + n), "returns": allt["returns"],
+             "nsteps": allt["nsteps"], "target_masks": allt["target_masks"],
+             "actions": allt["actions"], "importance_weights": allt["importance_weights"]}
+    p_ref = {k: v.clone() for k, v in p_on.items()}
+    opt = lo.Adam(p_ref, lr=1e-3, eps=c["adam_eps"])
+    res = lo.learner_update(spec, p_ref, p_tg, opt, batch, taus, c["gamma"], double_q=True,
+                            rnn_bootstrap=True, vf_eps=None, clip_grad=c["clip_grad"])
+    L = make_learner(c)
+    try:
+        L.load_state_dict(p_on, 0)
+        L.load_state_dict(p_tg, 1)
+        b, keep = device_batch(raw, c)
+        L.step(b, [taus["target"], taus["select"], taus["train"]])
+        stt = L.stats()
+        errs = []
+        report_diff(errs, "targets", L.debug("targets", (M, 32)).cpu().numpy(), res["targets"].numpy(), 0, 1e-4)
+        report_diff(errs, "qloss", stt["qloss"], float(res["loss"]), 0, 1e-4)
+        report_diff(errs, "td_mean", stt["td_mean"], float(res["td_mean"]), 0, 1e-4)
+        report_diff(errs, "report", L.td_abs().cpu().numpy(), res["report"].numpy(), 0, 1e-4)
+        report_diff(errs, "grad_norm", stt["grad_norm"], res["grad_norm"], 1e-3, 0)
+        grads = L.state_dict(2)
+        for k in grads:
+            gw = res["grads"][k].numpy()   # clipped by coef; norm < 40 here so coef == 1
+            scale = np.abs(gw).max() + 1e-12
+            report_diff(errs, "grad/" + k, grads[k].numpy() / scale, gw / scale, 0, 2e-3)
+        after = L.state_dict(0)
+        for k in after:
+            report_diff(errs, "after/" + k, after[k].numpy(), p_ref[k].numpy(), 1e-4, 2e-5)
+        print("full-size: qloss %.6f (oracle %.6f) td_mean %.6f grad_norm %.5f (oracle %.5f)" % (
+            stt["qloss"], float(res["loss"]), stt["td_mean"], stt["grad_norm"], res["grad_norm"]))
+        assert not errs, "\n".join(errs)
+    finally:
+        L.close()
