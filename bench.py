@@ -133,7 +133,8 @@ def build_device_workload(cfg, device, seed, rank):
                             mbatch=cfg["B"], nstep_train=cfg["T"], burn_in=cfg["P"],
                             nstep_target=cfg["n"], gamma=cfg["gamma"], double_q=True,
                             rnn_bootstrap=True, vf_scale_epsilon=None, clip_grad=cfg["clip_grad"],
-                            adam_epsilon=cfg["adam_eps"], lr=3e-4, seed=seed, device=device)
+                            adam_epsilon=cfg["adam_eps"], lr=3e-4, seed=seed, device=device,
+                            gemm=cfg.get("gemm", "tf32"))
     learner.load_state_dict(init_params(learner.param_info, U, seed=1), 0)
     learner.load_state_dict(init_params(learner.param_info, U, seed=2), 1)
     return hist, learner, fill_s
@@ -159,6 +160,7 @@ def run_gpu(args):
     cfg = dict(CFG)
     if args.size:
         cfg["size"] = args.size
+    cfg["gemm"] = args.gemm
     import random
     random.seed(rank)
     hist, learner, fill_s = build_device_workload(cfg, device, seed=0, rank=rank)
@@ -174,6 +176,7 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         one_update(hist, learner, B)
     barrier()
+    hist.profile_gather(True)
     launches0 = lib.rt_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -185,6 +188,8 @@ def run_gpu(args):
     ms = ev0.elapsed_time(ev1)
     launches = lib.rt_launch_count() - launches0
     stats = learner.stats()
+    gather_ms_total, gather_n = hist.gather_time()     # CUDA events around k_gather, live
+    hist.profile_gather(False)
 
     # gather kernel alone (roofline): time draws without the learner
     torch.cuda.synchronize(device)
@@ -247,21 +252,25 @@ def run_gpu(args):
         "metric": "learner updates/sec (32x20-step seq batches, 1M prioritized replay)",
         "value": world * args.steps / (ms / 1e3), "unit": "updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32 multiply / f32 accumulate" if cfg["gemm"] == "tf32" else "f32",
         "data": "synthetic",
         "config": {"workload": "atari_iqn_lstm seq-PER: N=%d T=20 n=2 B=32 Nq=32 A=6 "
                                "nature-CNN-LSTM512-FC512 dueling double-Q" % cfg["size"],
-                   "replay_per_gpu": cfg["size"], "l2": "inputs (28 GB frame store) exceed L2; "
+                   "gemm": cfg["gemm"], "replay_per_gpu": cfg["size"], "l2": "inputs (28 GB frame store) exceed L2; "
                    "every draw gathers different rows", "fill_s": round(fill_s, 1)},
         "e2e": {"value": world * args.steps / e2e_s, "unit": "updates/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
-        "roofline": {"kernel": "k_gather (sample+assemble+gather timed together)", "bound": "hbm",
-                     "achieved": gather_bytes / (draw_ms * 1e-3) / 1e9, "peak": hbm,
-                     "peak_source": which, "unit": "GB/s",
-                     "frac": gather_bytes / (draw_ms * 1e-3) / 1e9 / hbm, "traffic": None,
-                     "draw_ms": draw_ms},
+        "roofline": {"kernel": "k_gather", "bound": "hbm",
+                     "achieved": gather_bytes / (gather_ms_total / max(gather_n, 1) * 1e-3) / 1e9,
+                     "peak": hbm, "peak_source": which, "unit": "GB/s",
+                     "frac": gather_bytes / (gather_ms_total / max(gather_n, 1) * 1e-3) / 1e9 / hbm,
+                     "traffic": None, "launches_timed": int(gather_n),
+                     "us_per_launch": 1e3 * gather_ms_total / max(gather_n, 1),
+                     "algorithmic_bytes": int(gather_bytes),
+                     "draw_call_ms_host": draw_ms},
         "last_stats": stats,
     }
     if not args.no_cpu_baseline:
@@ -283,7 +292,7 @@ def run_reference(args, quiet=False):
     cfg = dict(CFG)
     cfg["size"] = args.ref_size
     cores = os.cpu_count()
-    torch.set_num_threads(cores)
+    torch.set_num_threads(min(cores, args.ref_threads) if args.ref_threads else cores)
     random.seed(0)
     np.random.seed(0)
     stream = SyntheticStream(num_envs=cfg["envs"], frame_shape=cfg["frame"], num_actions=cfg["A"],
@@ -333,6 +342,7 @@ def run_reference(args, quiet=False):
         update()
     dt = time.perf_counter() - t0
     val = steps / dt
+    cores = torch.get_num_threads()
     cb = {"value": val, "unit": "updates/s", "cores": cores, "kind": "port",
           "sample": "%d updates on a %d-transition replay (fill %.1fs untimed); torch CPU fp32, "
                     "%d threads; Python replay oracle" % (steps, cfg["size"], fill_s, cores)}
@@ -363,7 +373,11 @@ def main():
     ap.add_argument("--ref-size", type=int, default=200_000,
                     help="replay transitions filled for the CPU reference arm (bounded sample)")
     ap.add_argument("--ref-steps", type=int, default=5)
+    ap.add_argument("--ref-threads", type=int, default=32,
+                    help="torch intra-op threads for the CPU arm (0 = all cores; 128 threads are "
+                         "slower than 32 on these shapes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm", default=os.environ.get("RT_BENCH_GEMM", "tf32"), choices=["tf32", "fp32"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -126,6 +126,11 @@ int rt_replay_update_losses(rt_replay* h, int64_t m, const int64_t* pairs, const
  * (fp32, time-major T*B); performs the D2H read-back itself. */
 int rt_replay_update_losses_last(rt_replay* h, const float* td_abs_device, void* stream);
 
+/* Measurement hook: when enabled, CUDA events bracket every gather-kernel launch on its own
+ * stream; rt_replay_gather_time returns (and resets) the summed device time. */
+int rt_replay_profile(rt_replay* h, int32_t enable);
+int rt_replay_gather_time(rt_replay* h, double* total_ms, int64_t* launches);
+
 /* Unit-test hooks on the fp64 sum/min trees (data_structures/segment_tree.py). */
 int rt_replay_tree_sum(rt_replay* h, double* out, void* stream);
 int rt_replay_tree_min(rt_replay* h, double* out, void* stream);
@@ -170,7 +175,7 @@ typedef struct rt_train_desc {
   int32_t double_q;
   int32_t rnn_bootstrap;
   int32_t loss_sum;       /* loss_aggregation: 0 = mean, 1 = sum */
-  int32_t reserved;
+  int32_t gemm_mode;      /* RT_GEMM_FP32_SIMT or RT_GEMM_TF32_TCGEN05 */
   double gamma;
   double vf_scale_epsilon; /* <= 0: no value rescaling */
   double huber_kappa;
@@ -185,6 +190,9 @@ typedef struct rt_learner_io {
   int32_t field_x, field_hx, field_cx, field_initials; /* indices into rt_batch.all_states */
   int32_t po_field_actions;                            /* index into rt_batch.policy_outputs (int64) */
 } rt_learner_io;
+
+#define RT_GEMM_FP32_SIMT 0     /* fp32 CUDA-core GEMM (parity reference path) */
+#define RT_GEMM_TF32_TCGEN05 1  /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM */
 
 #define RT_BUF_ONLINE 0
 #define RT_BUF_TARGET 1
@@ -221,6 +229,11 @@ int rt_learner_td_abs(rt_learner* h, float** out_device);
 /* qloss, td_mean, grad_norm of the last step (torch/iqn.py:127-129, torch_trainer.py:187-190);
  * synchronises the stream. */
 int rt_learner_read_stats(rt_learner* h, float* loss, float* td_mean, float* grad_norm, void* stream);
+/* Test hook: C[M,N] = op(A) . op(B) on the selected GEMM path with host operands
+ * (transA: A stored [K][M]; transB: B stored [N][K]); optional per-column bias and ReLU. */
+int rt_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB,
+                 const float* A, const float* B, const float* bias, int32_t relu, float* C,
+                 int32_t device);
 /* Test hook: named intermediate activations / gradients of the last step. */
 int rt_learner_debug_tensor(rt_learner* h, const char* name, void** dev_ptr, int64_t* count);
 

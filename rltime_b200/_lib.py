@@ -47,6 +47,7 @@ class Batch(C.Structure):
 
 RT_MAX_CONV = 8
 RT_BUF_ONLINE, RT_BUF_TARGET, RT_BUF_GRAD, RT_BUF_ADAM_M, RT_BUF_ADAM_V = range(5)
+RT_GEMM_FP32_SIMT, RT_GEMM_TF32_TCGEN05 = 0, 1
 
 
 class ModelDesc(C.Structure):
@@ -63,7 +64,7 @@ class TrainDesc(C.Structure):
     _fields_ = [
         ("mbatch", C.c_int32), ("nstep_train", C.c_int32), ("burn_in", C.c_int32),
         ("nstep_target", C.c_int32), ("double_q", C.c_int32), ("rnn_bootstrap", C.c_int32),
-        ("loss_sum", C.c_int32), ("reserved", C.c_int32), ("gamma", C.c_double),
+        ("loss_sum", C.c_int32), ("gemm_mode", C.c_int32), ("gamma", C.c_double),
         ("vf_scale_epsilon", C.c_double), ("huber_kappa", C.c_double), ("clip_grad", C.c_double),
         ("adam_epsilon", C.c_double), ("lr", C.c_double), ("seed", C.c_uint64),
     ]
@@ -91,6 +92,8 @@ SIGNATURES = {
     "rt_replay_batch": (C.c_int, [_VP, C.POINTER(Batch)]),
     "rt_replay_update_losses": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP]),
     "rt_replay_update_losses_last": (C.c_int, [_VP, _VP, _VP]),
+    "rt_replay_profile": (C.c_int, [_VP, C.c_int32]),
+    "rt_replay_gather_time": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "rt_replay_tree_sum": (C.c_int, [_VP, C.POINTER(C.c_double), _VP]),
     "rt_replay_tree_min": (C.c_int, [_VP, C.POINTER(C.c_double), _VP]),
     "rt_replay_tree_leaf": (C.c_int, [_VP, C.c_int32, C.POINTER(C.c_double), _VP]),
@@ -115,6 +118,7 @@ SIGNATURES = {
     "rt_learner_read_stats": (C.c_int, [_VP, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                         C.POINTER(C.c_float), _VP]),
     "rt_learner_debug_tensor": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP), C.POINTER(C.c_int64)]),
+    "rt_gemm_test": (C.c_int, [C.c_int32] * 6 + [_VP, _VP, _VP, C.c_int32, _VP, C.c_int32]),
 }
 
 _lib = None

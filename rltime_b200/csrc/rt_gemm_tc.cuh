@@ -1,0 +1,261 @@
+// TF32 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared
+// memory -> tcgen05.mma.kind::tf32 with the fp32 accumulator in TMEM -> tcgen05.ld epilogue.
+//
+//   C[M,N] = epi( A . B ),  fp32 in memory, TF32 multiply, fp32 accumulate.
+//   A is K-major ([M][K], transA = 0) or MN-major ([K][M], transA = 1);
+//   B is K-major ([N][K], transB = 1, an nn.Linear weight) or MN-major ([K][N], transB = 0).
+// All three products of a linear layer (forward, data gradient, weight gradient) therefore
+// run on the same kernel without materialising a transpose.
+//
+// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..5 = epilogue (each owns the 32 TMEM lanes of its warp_id % 4 quarter).
+// Tile 128 x BN x 32 (one 128-byte swizzle span of fp32 along K per stage, four UMMA_K=8
+// instructions per stage), STAGES-deep mbarrier ring.  One tile per CTA; split-K over
+// gridDim.z writes raw partials that rtk::k_splitk_reduce folds deterministically.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rt_kernels.cuh"
+
+namespace rttc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;   // floats = 128 bytes
+constexpr int UMMA_K = 8;     // tf32
+constexpr int NUM_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+        "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+        "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;  // LayoutType::SWIZZLE_128B
+  return d;
+}
+
+// Extra epilogue switch on top of rtk::GemmArgs
+struct TcArgs {
+  rtk::GemmArgs g;
+  int num_kb_total;   // ceil(K / BLOCK_K)
+  int kb_per_split;
+  int round_tf32;     // round outputs to TF32 (RN) so the consumer GEMM multiplies exact values
+};
+
+template <int BN, int A_MN, int B_MN, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KiB
+  static constexpr int B_BYTES = BN * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, int A_MN, int B_MN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ TcArgs a) {
+  using L = SmemLayout<BN, A_MN, B_MN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const rtk::GemmArgs& g = a.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BN;
+  const int kb0 = blockIdx.z * a.kb_per_split;
+  int kb1 = kb0 + a.kb_per_split;
+  if (kb1 > a.num_kb_total) kb1 = a.num_kb_total;
+  const int num_kb = kb1 - kb0;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer
+      for (int i = 0; i < num_kb; ++i) {
+        int s = i % STAGES;
+        uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        int k0 = (kb0 + i) * BLOCK_K;
+        if (A_MN) {
+          // A stored [K][M]: 32-float MN atoms, each a (BLOCK_K rows x 128 B) block
+#pragma unroll
+          for (int j = 0; j < BLOCK_M / 32; ++j)
+            tma_load_2d(&tmA, &full_bar[s], sa + j * (BLOCK_K * 128), m0 + 32 * j, k0);
+        } else {
+          tma_load_2d(&tmA, &full_bar[s], sa, k0, m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+            tma_load_2d(&tmB, &full_bar[s], sb + j * (BLOCK_K * 128), n0 + 32 * j, k0);
+        } else {
+          tma_load_2d(&tmB, &full_bar[s], sb, k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer (one thread)
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)A_MN << 15) |
+                             ((uint32_t)B_MN << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BLOCK_M >> 4) << 24);
+      for (int i = 0; i < num_kb; ++i) {
+        int s = i % STAGES;
+        uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K inside the swizzle span.
+          // MN-major: atoms (BLOCK_K*128 B apart) of 8-row K groups 1024 B apart.
+          uint64_t ad = A_MN ? make_smem_desc(sa + k * 1024, BLOCK_K * 128, 1024)
+                             : make_smem_desc(sa + k * (UMMA_K * 4), 16, 1024);
+          uint64_t bd = B_MN ? make_smem_desc(sb + k * 1024, BLOCK_K * 128, 1024)
+                             : make_smem_desc(sb + k * (UMMA_K * 4), 16, 1024);
+          umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
+      }
+      umma_commit(tmem_full);         // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      if (m < g.M) {
+        int nb = n0 + c * 32;
+        if (gridDim.z > 1) {
+          float* dst = g.ws + ((size_t)blockIdx.z * g.M + m) * g.N + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < g.N) dst[j] = __uint_as_float(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            int n = nb + j;
+            if (n < g.N) {
+              float r = rtk::gemm_epilogue(g, m, n, __uint_as_float(v[j]));
+              if (a.round_tf32) {
+                uint32_t t;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
+                r = __uint_as_float(t);
+              }
+              g.C[(size_t)m * g.ldc + n] = r;
+            }
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+  }
+}
+
+}  // namespace rttc

@@ -16,12 +16,39 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "rt_common.h"
 #include "rt_kernels.cuh"
+#include "rt_gemm_tc.cuh"
 
 namespace {
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                        const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TmapKey {
+  const void* ptr;
+  uint64_t d0, d1, pitch;
+  uint32_t b0, b1;
+  bool operator<(const TmapKey& o) const {
+    return std::tie(ptr, d0, d1, pitch, b0, b1) < std::tie(o.ptr, o.d0, o.d1, o.pitch, o.b0, o.b1);
+  }
+};
+
+// Everything a GEMM launch needs besides its operands.
+struct GemmCtx {
+  float* ws = nullptr;        // split-K workspace
+  size_t ws_floats = 0;
+  int mode = 0;               // 0 = fp32 SIMT, 1 = TF32 tcgen05 where eligible
+  int round_tf32 = 0;
+  PFN_tmapEncodeTiled encode = nullptr;
+  std::map<TmapKey, CUtensorMap> tmaps;
+  long long tc_launches = 0, simt_launches = 0;
+};
 
 struct ConvL {
   int cin, hin, win, f, k, s, hout, wout, K;
@@ -39,6 +66,12 @@ struct PInfo {
 };
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#define RT_TRY(x)                   \
+  do {                              \
+    int rc__ = (x);                 \
+    if (rc__ != RT_OK) return rc__; \
+  } while (0)
 
 }  // namespace
 
@@ -80,8 +113,7 @@ struct rt_learner {
   float *dtheta = nullptr, *row_loss = nullptr, *report = nullptr, *stats = nullptr;
   float *dadv = nullptr, *dv = nullptr, *dh1 = nullptr, *dv1 = nullptr, *dxq = nullptr, *dphi = nullptr,
         *dfeatq = nullptr, *dgates = nullptr, *dh_carry = nullptr, *dc_carry = nullptr, *dfeat = nullptr;
-  float* ws = nullptr;
-  size_t ws_floats = 0;
+  GemmCtx gx;
   float* colsum_part = nullptr;
   double* sumsq_part = nullptr;
   float* tau_stage = nullptr;  // device staging for injected taus (5 segments)
@@ -144,8 +176,7 @@ size_t perm_index(const rt_learner* h, const PInfo& pi, size_t j) {
   }
 }
 
-int gemm(rt_learner* h, cudaStream_t st, rtk::GemmArgs g) {
-  if (g.M <= 0 || g.N <= 0) return RT_OK;
+int gemm_simt(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   constexpr int BM = 128, BN = 64, BK = 16;
   int tm = cdiv(g.M, BM), tn = cdiv(g.N, BN);
   long long tiles = (long long)tm * tn;
@@ -155,23 +186,132 @@ int gemm(rt_learner* h, cudaStream_t st, rtk::GemmArgs g) {
     int maxs = g.K / 512;
     if (splits > maxs) splits = maxs;
     size_t per = (size_t)g.M * g.N;
-    if ((size_t)splits * per > h->ws_floats) splits = (int)(h->ws_floats / per);
+    if ((size_t)splits * per > cx.ws_floats) splits = (int)(cx.ws_floats / per);
     if (splits < 1) splits = 1;
   }
   int kchunk = cdiv(g.K, splits);
   kchunk = cdiv(kchunk, BK) * BK;
   splits = cdiv(g.K, kchunk);
   g.kchunk = kchunk;
-  g.ws = h->ws;
+  g.ws = cx.ws;
   dim3 grid(tn, tm, splits);
   rtk::k_sgemm<BM, BN, BK, 8, 4><<<grid, 256, 0, st>>>(g);
   RT_LAUNCH_CHECK();
+  cx.simt_launches++;
   if (splits > 1) {
     size_t total = (size_t)g.M * g.N;
     rtk::k_splitk_reduce<<<cdiv(total, 256), 256, 0, st>>>(g, splits);
     RT_LAUNCH_CHECK();
   }
   return RT_OK;
+}
+
+int get_tmap(GemmCtx& cx, const float* ptr, uint64_t d0, uint64_t d1, uint64_t pitch_elems, uint32_t b0,
+             uint32_t b1, const CUtensorMap** out) {
+  TmapKey key{ptr, d0, d1, pitch_elems, b0, b1};
+  auto it = cx.tmaps.find(key);
+  if (it == cx.tmaps.end()) {
+    if (!cx.encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      RT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess)
+        return rt::fail(RT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+      cx.encode = (PFN_tmapEncodeTiled)fn;
+    }
+    CUtensorMap tm;
+    cuuint64_t gdim[2] = {d0, d1};
+    cuuint64_t gstr[1] = {pitch_elems * sizeof(float)};
+    cuuint32_t box[2] = {b0, b1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = cx.encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return rt::fail(RT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu) pitch=%llu box=(%u,%u)",
+                      (int)r, (unsigned long long)d0, (unsigned long long)d1,
+                      (unsigned long long)pitch_elems, b0, b1);
+    it = cx.tmaps.emplace(key, tm).first;
+  }
+  *out = &it->second;
+  return RT_OK;
+}
+
+template <int BN, int A_MN, int B_MN>
+int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs& a, dim3 grid, cudaStream_t st) {
+  constexpr int STAGES = BN == 128 ? 3 : 4;
+  using L = rttc::SmemLayout<BN, A_MN, B_MN, STAGES>;
+  auto kern = rttc::k_gemm_tc<BN, A_MN, B_MN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  kern<<<grid, rttc::NUM_THREADS, L::TOTAL, st>>>(*ta, *tb, a);
+  RT_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+bool tc_eligible(const rtk::GemmArgs& g) {
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  if (g.transA && !g.transB) return false;           // (MN-major A, K-major B) is never needed
+  if (g.K < 32 || g.N < 8 || g.M < 1) return false;
+  if ((g.lda & 3) || (g.ldb & 3) || !al16(g.A) || !al16(g.B)) return false;
+  if (!g.transA && g.K > g.lda) return false;
+  return true;
+}
+
+int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
+  const int BN = g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128);
+  const int A_MN = g.transA ? 1 : 0, B_MN = g.transB ? 0 : 1;
+  int tm = cdiv(g.M, rttc::BLOCK_M), tn = cdiv(g.N, BN);
+  long long tiles = (long long)tm * tn;
+  int num_kb = cdiv(g.K, rttc::BLOCK_K);
+  int splits = 1;
+  if (tiles < 148 && num_kb >= 16) {
+    splits = (int)((296 + tiles - 1) / tiles);
+    if (splits > num_kb / 4) splits = num_kb / 4;
+    size_t per = (size_t)g.M * g.N;
+    if ((size_t)splits * per > cx.ws_floats) splits = (int)(cx.ws_floats / per);
+    if (splits < 1) splits = 1;
+  }
+  int kbps = cdiv(num_kb, splits);
+  splits = cdiv(num_kb, kbps);
+  const CUtensorMap *ta = nullptr, *tb = nullptr;
+  if (A_MN) RT_TRY(get_tmap(cx, g.A, g.M, g.K, g.lda, 32, rttc::BLOCK_K, &ta));
+  else      RT_TRY(get_tmap(cx, g.A, g.K, g.M, g.lda, rttc::BLOCK_K, rttc::BLOCK_M, &ta));
+  if (B_MN) RT_TRY(get_tmap(cx, g.B, g.N, g.K, g.ldb, 32, rttc::BLOCK_K, &tb));
+  else      RT_TRY(get_tmap(cx, g.B, g.K, g.N, g.ldb, rttc::BLOCK_K, BN, &tb));
+  rttc::TcArgs a;
+  g.ws = cx.ws;
+  g.kchunk = kbps * rttc::BLOCK_K;
+  a.g = g;
+  a.num_kb_total = num_kb;
+  a.kb_per_split = kbps;
+  a.round_tf32 = cx.round_tf32;
+  dim3 grid(tn, tm, splits);
+  int rc;
+#define RT_TC_CASE(bn, am, bm) \
+  if (BN == bn && A_MN == am && B_MN == bm) rc = launch_tc<bn, am, bm>(ta, tb, a, grid, st); else
+  RT_TC_CASE(32, 0, 0) RT_TC_CASE(64, 0, 0) RT_TC_CASE(128, 0, 0)
+  RT_TC_CASE(32, 0, 1) RT_TC_CASE(64, 0, 1) RT_TC_CASE(128, 0, 1)
+  RT_TC_CASE(32, 1, 1) RT_TC_CASE(64, 1, 1) RT_TC_CASE(128, 1, 1)
+  rc = rt::fail(RT_ERR_INVALID, "no tcgen05 GEMM instantiation for BN=%d A_MN=%d B_MN=%d", BN, A_MN, B_MN);
+#undef RT_TC_CASE
+  if (rc != RT_OK) return rc;
+  cx.tc_launches++;
+  if (splits > 1) {
+    size_t total = (size_t)g.M * g.N;
+    rtk::k_splitk_reduce<<<cdiv(total, 256), 256, 0, st>>>(a.g, splits);
+    RT_LAUNCH_CHECK();
+  }
+  return RT_OK;
+}
+
+int gemm(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
+  if (g.M <= 0 || g.N <= 0) return RT_OK;
+  if (cx.mode == 1 && tc_eligible(g)) return gemm_tc(cx, st, g);
+  return gemm_simt(cx, st, g);
 }
 
 rtk::GemmArgs mk(const float* A, int lda, int transA, const float* B, int ldb, int transB, float* C,
@@ -199,12 +339,6 @@ int colsum(rt_learner* h, cudaStream_t st, const float* x, size_t rows, int N, f
   RT_LAUNCH_CHECK();
   return RT_OK;
 }
-
-#define RT_TRY(x)            \
-  do {                       \
-    int rc__ = (x);          \
-    if (rc__ != RT_OK) return rc__; \
-  } while (0)
 
 int grid1d(size_t n, int threads = 256) {
   size_t b = (n + threads - 1) / threads;
@@ -237,7 +371,7 @@ int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t*
       rtk::GemmArgs g = mk(h->col, L.K, 0, net + L.w, L.K, 1, out, L.f, (int)(rc * opix), L.f, L.K);
       g.bias = net + L.b;
       g.relu = 1;
-      RT_TRY(gemm(h, st, g));
+      RT_TRY(gemm(h->gx, st, g));
     }
   }
   return RT_OK;
@@ -250,14 +384,14 @@ int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* 
   rtk::GemmArgs g = mk(feat, h->feat, 0, net + h->o_wih, h->feat, 1, h->xg, 4 * U, rows, 4 * U, h->feat);
   g.bias = net + h->o_bih;
   g.bias2 = net + h->o_bhh;
-  RT_TRY(gemm(h, st, g));
+  RT_TRY(gemm(h->gx, st, g));
   int nb = cdiv((size_t)Beff * U, 256);
   rtk::k_lstm_init<<<nb, 256, 0, st>>>(hx, cx, initials, h->hprev, h->cprev, Beff, U);
   RT_LAUNCH_CHECK();
   for (int t = 0; t < timesteps; ++t) {
     size_t ro = (size_t)t * Beff;
     rtk::GemmArgs gh = mk(h->hprev + ro * U, U, 0, net + h->o_whh, U, 1, h->hg, 4 * U, Beff, 4 * U, U);
-    RT_TRY(gemm(h, st, gh));
+    RT_TRY(gemm(h->gx, st, gh));
     bool last = t == timesteps - 1;
     rtk::k_lstm_cell<<<nb, 256, 0, st>>>(
         h->xg + ro * 4 * U, h->hg, h->cprev + ro * U, h->gates + ro * 4 * U, h->c_all + ro * U,
@@ -298,24 +432,24 @@ int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float*
   rtk::GemmArgs g = mk(h->cf, E, 0, net + h->o_qw, E, 1, h->phi, D, (int)MQ, D, E);
   g.bias = net + h->o_qb;
   g.relu = 1;
-  RT_TRY(gemm(h, st, g));
+  RT_TRY(gemm(h->gx, st, g));
   rtk::k_quantile_mul<<<cdiv(MQ * D, 256), 256, 0, st>>>(feat, h->phi, h->xq, MQ, D, Nq);
   RT_LAUNCH_CHECK();
   g = mk(h->xq, D, 0, net + h->o_fcw, D, 1, h->h1, F, (int)MQ, F, D);
   g.bias = net + h->o_fcb;
   g.relu = 1;
-  RT_TRY(gemm(h, st, g));
+  RT_TRY(gemm(h->gx, st, g));
   g = mk(h->h1, F, 0, net + h->o_outw, F, 1, h->adv, A, (int)MQ, A, F);
   g.bias = net + h->o_outb;
-  RT_TRY(gemm(h, st, g));
+  RT_TRY(gemm(h->gx, st, g));
   if (h->dueling) {
     g = mk(h->xq, D, 0, net + h->o_vhw, D, 1, h->v1, F, (int)MQ, F, D);
     g.bias = net + h->o_vhb;
     g.relu = 1;
-    RT_TRY(gemm(h, st, g));
+    RT_TRY(gemm(h->gx, st, g));
     g = mk(h->v1, F, 0, net + h->o_vw, F, 1, h->v, 1, (int)MQ, 1, F);
     g.bias = net + h->o_vb;
-    RT_TRY(gemm(h, st, g));
+    RT_TRY(gemm(h->gx, st, g));
   }
   rtk::k_dueling<<<cdiv(MQ, 256), 256, 0, st>>>(h->adv, h->dueling ? h->v : nullptr, h->q, MQ, A);
   RT_LAUNCH_CHECK();
@@ -332,33 +466,33 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
                                                    h->dueling ? 1 : 0);
   RT_LAUNCH_CHECK();
   // out layer
-  RT_TRY(gemm(h, st, mk(h->dadv, A, 1, h->h1, F, 0, G + h->o_outw, F, A, F, (int)MQ)));
+  RT_TRY(gemm(h->gx, st, mk(h->dadv, A, 1, h->h1, F, 0, G + h->o_outw, F, A, F, (int)MQ)));
   RT_TRY(colsum(h, st, h->dadv, MQ, A, G + h->o_outb, 0));
   rtk::GemmArgs g = mk(h->dadv, A, 0, net + h->o_outw, F, 0, h->dh1, F, (int)MQ, F, A);
   g.mask = h->h1;
   g.ldmask = F;
-  RT_TRY(gemm(h, st, g));
+  RT_TRY(gemm(h->gx, st, g));
   // FC
-  RT_TRY(gemm(h, st, mk(h->dh1, F, 1, h->xq, D, 0, G + h->o_fcw, D, F, D, (int)MQ)));
+  RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 1, h->xq, D, 0, G + h->o_fcw, D, F, D, (int)MQ)));
   RT_TRY(colsum(h, st, h->dh1, MQ, F, G + h->o_fcb, 0));
-  RT_TRY(gemm(h, st, mk(h->dh1, F, 0, net + h->o_fcw, D, 0, h->dxq, D, (int)MQ, D, F)));
+  RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 0, net + h->o_fcw, D, 0, h->dxq, D, (int)MQ, D, F)));
   if (h->dueling) {
-    RT_TRY(gemm(h, st, mk(h->dv, 1, 1, h->v1, F, 0, G + h->o_vw, F, 1, F, (int)MQ)));
+    RT_TRY(gemm(h->gx, st, mk(h->dv, 1, 1, h->v1, F, 0, G + h->o_vw, F, 1, F, (int)MQ)));
     RT_TRY(colsum(h, st, h->dv, MQ, 1, G + h->o_vb, 0));
     g = mk(h->dv, 1, 0, net + h->o_vw, F, 0, h->dv1, F, (int)MQ, F, 1);
     g.mask = h->v1;
     g.ldmask = F;
-    RT_TRY(gemm(h, st, g));
-    RT_TRY(gemm(h, st, mk(h->dv1, F, 1, h->xq, D, 0, G + h->o_vhw, D, F, D, (int)MQ)));
+    RT_TRY(gemm(h->gx, st, g));
+    RT_TRY(gemm(h->gx, st, mk(h->dv1, F, 1, h->xq, D, 0, G + h->o_vhw, D, F, D, (int)MQ)));
     RT_TRY(colsum(h, st, h->dv1, MQ, F, G + h->o_vhb, 0));
     g = mk(h->dv1, F, 0, net + h->o_vhw, D, 0, h->dxq, D, (int)MQ, D, F);
     g.accumulate = 1;
-    RT_TRY(gemm(h, st, g));
+    RT_TRY(gemm(h->gx, st, g));
   }
   rtk::k_quantile_mul_bwd<<<cdiv((size_t)M * D, 256), 256, 0, st>>>(h->dxq, feat, h->phi, h->dphi,
                                                                    h->dfeatq, M, D, Nq);
   RT_LAUNCH_CHECK();
-  RT_TRY(gemm(h, st, mk(h->dphi, D, 1, h->cf, E, 0, G + h->o_qw, E, D, E, (int)MQ)));
+  RT_TRY(gemm(h->gx, st, mk(h->dphi, D, 1, h->cf, E, 0, G + h->o_qw, E, D, E, (int)MQ)));
   RT_TRY(colsum(h, st, h->dphi, MQ, D, G + h->o_qb, 0));
   return RT_OK;
 }
@@ -378,18 +512,18 @@ int lstm_backward(rt_learner* h, cudaStream_t st, const float* net, const float*
         h->dgates + ro * 4 * U, Beff, U);
     RT_LAUNCH_CHECK();
     if (t > 0) {
-      RT_TRY(gemm(h, st, mk(h->dgates + ro * 4 * U, 4 * U, 0, net + h->o_whh, U, 0, h->dh_carry, U,
+      RT_TRY(gemm(h->gx, st, mk(h->dgates + ro * 4 * U, 4 * U, 0, net + h->o_whh, U, 0, h->dh_carry, U,
                             Beff, U, 4 * U)));
       rtk::k_mask_rows<<<nb, 256, 0, st>>>(h->dh_carry, initials + ro, Beff, U);
       RT_LAUNCH_CHECK();
     }
   }
-  RT_TRY(gemm(h, st, mk(h->dgates, 4 * U, 1, h->hprev, U, 0, G + h->o_whh, U, 4 * U, U, rows)));
-  RT_TRY(gemm(h, st, mk(h->dgates, 4 * U, 1, feat, h->feat, 0, G + h->o_wih, h->feat, 4 * U, h->feat, rows)));
+  RT_TRY(gemm(h->gx, st, mk(h->dgates, 4 * U, 1, h->hprev, U, 0, G + h->o_whh, U, 4 * U, U, rows)));
+  RT_TRY(gemm(h->gx, st, mk(h->dgates, 4 * U, 1, feat, h->feat, 0, G + h->o_wih, h->feat, 4 * U, h->feat, rows)));
   RT_TRY(colsum(h, st, h->dgates, rows, 4 * U, G + h->o_bih, 0));
   RT_CUDA(cudaMemcpyAsync(G + h->o_bhh, G + h->o_bih, (size_t)4 * U * sizeof(float),
                           cudaMemcpyDeviceToDevice, st));
-  RT_TRY(gemm(h, st, mk(h->dgates, 4 * U, 0, net + h->o_wih, h->feat, 0, h->dfeat, h->feat, rows,
+  RT_TRY(gemm(h->gx, st, mk(h->dgates, 4 * U, 0, net + h->o_wih, h->feat, 0, h->dfeat, h->feat, rows,
                         h->feat, 4 * U)));
   return RT_OK;
 }
@@ -428,11 +562,11 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
       RT_LAUNCH_CHECK();
       rtk::GemmArgs g = mk(dy, L.f, 1, h->col, L.K, 0, G + L.w, L.K, L.f, L.K, (int)(rc * opix));
       g.accumulate = first ? 0 : 1;
-      RT_TRY(gemm(h, st, g));
+      RT_TRY(gemm(h->gx, st, g));
       RT_TRY(colsum(h, st, dy, (size_t)rc * opix, L.f, G + L.b, first ? 0 : 1));
       if (i > 0) {
         const ConvL& Lp = h->conv[i - 1];
-        RT_TRY(gemm(h, st, mk(dy, L.f, 0, net + L.w, L.K, 0, h->dcol, L.K, (int)(rc * opix), L.K, L.f)));
+        RT_TRY(gemm(h->gx, st, mk(dy, L.f, 0, net + L.w, L.K, 0, h->dcol, L.K, (int)(rc * opix), L.K, L.f)));
         float* dxp = h->d_c[i - 1] + (size_t)r0 * Lp.hout * Lp.wout * Lp.f;
         size_t n_in = (size_t)rc * L.hin * L.win * L.cin;
         rtk::k_col2im_nhwc<<<grid1d(n_in), 256, 0, st>>>(h->dcol, dxp, rc, L.cin, L.hin, L.win, L.k,
@@ -611,8 +745,9 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->dxq, MQ * D, "dxq"));
   RT_TRY(dalloc(h, &h->dphi, MQ * D, "dphi"));
   RT_TRY(dalloc(h, &h->dfeatq, (size_t)h->M * D, "dfeatq"));
-  h->ws_floats = (size_t)64 << 20;  // 256 MiB split-K workspace
-  RT_TRY(dalloc(h, &h->ws, h->ws_floats));
+  h->gx.ws_floats = (size_t)64 << 20;  // 256 MiB split-K workspace
+  RT_TRY(dalloc(h, &h->gx.ws, h->gx.ws_floats));
+  h->gx.mode = td->gemm_mode;
   size_t maxN = 4 * (size_t)(h->U ? h->U : 1);
   if (D > maxN) maxN = D;
   if (F > maxN) maxN = F;
@@ -856,3 +991,40 @@ int rt_learner_debug_tensor(rt_learner* h, const char* name, void** dev_ptr, int
 }
 
 }  // extern "C"
+
+extern "C" int rt_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t transA,
+                            int32_t transB, const float* A, const float* B, const float* bias,
+                            int32_t relu, float* C, int32_t device) {
+  RT_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
+  RT_CUDA(cudaSetDevice(device));
+  GemmCtx cx;
+  cx.mode = mode;
+  cx.ws_floats = (size_t)16 << 20;
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr, *dbias = nullptr;
+  size_t nA = (size_t)M * K, nB = (size_t)N * K, nC = (size_t)M * N;
+  RT_CUDA(cudaMalloc(&cx.ws, cx.ws_floats * sizeof(float)));
+  RT_CUDA(cudaMalloc(&dA, nA * sizeof(float)));
+  RT_CUDA(cudaMalloc(&dB, nB * sizeof(float)));
+  RT_CUDA(cudaMalloc(&dC, nC * sizeof(float)));
+  RT_CUDA(cudaMemcpy(dA, A, nA * sizeof(float), cudaMemcpyHostToDevice));
+  RT_CUDA(cudaMemcpy(dB, B, nB * sizeof(float), cudaMemcpyHostToDevice));
+  RT_CUDA(cudaMemset(dC, 0, nC * sizeof(float)));
+  if (bias) {
+    RT_CUDA(cudaMalloc(&dbias, (size_t)N * sizeof(float)));
+    RT_CUDA(cudaMemcpy(dbias, bias, (size_t)N * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  rtk::GemmArgs g = mk(dA, transA ? M : K, transA, dB, transB ? K : N, transB, dC, N, M, N, K);
+  g.bias = dbias;
+  g.relu = relu;
+  int rc = gemm(cx, 0, g);
+  if (rc == RT_OK) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = rt::fail(RT_ERR_CUDA, "gemm test kernel failed: %s", cudaGetErrorString(e));
+  }
+  if (rc == RT_OK && mode == 1 && cx.tc_launches == 0)
+    rc = rt::fail(RT_ERR_INVALID, "shape not eligible for the tcgen05 path");
+  if (rc == RT_OK) RT_CUDA(cudaMemcpy(C, dC, nC * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(cx.ws);
+  if (dbias) cudaFree(dbias);
+  return rc;
+}

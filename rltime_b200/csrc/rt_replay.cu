@@ -459,6 +459,10 @@ struct rt_replay {
   DevVec<double> dv_reward, dv_tree_sum, dv_tree_min;
   DevVec<uint8_t> dv_done;
   DevVec<long long> dv_p2s_at, dv_seq_base, dv_env_id;
+  // optional live timing of the gather kernel (bench.py roofline)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop)
+  size_t prof_used = 0;
   // pinned read-back for update_losses_last
   float* h_td = nullptr;
   int* h_idx = nullptr;
@@ -679,8 +683,14 @@ int assemble_and_gather(rt_replay* h, BatchSlot& bs, int B, cudaStream_t st) {
   gp.total_items = items;
   if (items > 0) {
     long long grid = items < 148LL * 16 ? items : 148LL * 16;
+    bool timed = h->profile && h->prof_used + 2 <= h->prof_ev.size();
+    if (timed) RT_CUDA(cudaEventRecord(h->prof_ev[h->prof_used], st));
     k_gather<4><<<(int)grid, RT_GATHER_THREADS, 0, st>>>(gp);
     RT_LAUNCH_CHECK();
+    if (timed) {
+      RT_CUDA(cudaEventRecord(h->prof_ev[h->prof_used + 1], st));
+      h->prof_used += 2;
+    }
   }
   return RT_OK;
 }
@@ -794,6 +804,7 @@ void rt_replay_destroy(rt_replay* h) {
   if (h->h_td) cudaFreeHost(h->h_td);
   if (h->h_idx) cudaFreeHost(h->h_idx);
   if (h->ev) cudaEventDestroy(h->ev);
+  for (auto& e : h->prof_ev) cudaEventDestroy(e);
   delete h;
 }
 
@@ -1053,6 +1064,34 @@ int rt_replay_update_losses_last(rt_replay* h, const float* td_abs_device, void*
     }
   // a sequence drawn from a since-freed leaf cannot occur: leaves are zeroed on free
   return rt_replay_update_losses(h, (int64_t)rows, pairs.data(), losses.data(), stream);
+}
+
+int rt_replay_profile(rt_replay* h, int32_t enable) {
+  RT_REQUIRE(h, "null argument");
+  RT_CUDA(cudaSetDevice(h->cfg.device));
+  if (enable && h->prof_ev.empty()) {
+    h->prof_ev.resize(2 * 512);
+    for (auto& e : h->prof_ev) RT_CUDA(cudaEventCreate(&e));
+  }
+  h->profile = enable != 0;
+  h->prof_used = 0;
+  return RT_OK;
+}
+
+int rt_replay_gather_time(rt_replay* h, double* total_ms, int64_t* launches) {
+  RT_REQUIRE(h && total_ms && launches, "null argument");
+  RT_CUDA(cudaSetDevice(h->cfg.device));
+  RT_CUDA(cudaDeviceSynchronize());
+  double t = 0;
+  for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+    float ms = 0;
+    RT_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]));
+    t += ms;
+  }
+  *total_ms = t;
+  *launches = (int64_t)(h->prof_used / 2);
+  h->prof_used = 0;
+  return RT_OK;
 }
 
 static int read_scalar(int device, const double* dptr, double* out, void* stream) {

@@ -289,6 +289,15 @@ class DeviceReplayHistoryBuffer:
             import torch
             torch.cuda.current_stream(self.device).synchronize()
 
+    def profile_gather(self, enable=True):
+        _lib.check(self._lib.rt_replay_profile(self._h, 1 if enable else 0))
+
+    def gather_time(self):
+        """(total device ms, launches) of the gather kernel since the last call."""
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(self._lib.rt_replay_gather_time(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def needed_feed_count(self, mbatch_size, num_envs):
         # replay_history.py:62-75
         if not self.train_frequency:

@@ -20,7 +20,7 @@ class DeviceLearner:
                  embedding_dim=64, dueling=True, *, mbatch, nstep_train, burn_in=0,
                  nstep_target=1, gamma=0.99, double_q=False, rnn_bootstrap=False,
                  vf_scale_epsilon=None, huber_kappa=1.0, clip_grad=None, adam_epsilon=1e-8,
-                 lr=1e-3, loss_aggregation="mean", seed=0, device=None):
+                 lr=1e-3, loss_aggregation="mean", seed=0, device=None, gemm="tf32"):
         import torch
         if not torch.cuda.is_available():
             raise _lib.RtError("rltime_b200 learner needs a CUDA device (no CPU fallback)")
@@ -51,6 +51,8 @@ class DeviceLearner:
         td.adam_epsilon = adam_epsilon
         td.lr = lr
         td.seed = seed
+        assert gemm in ("fp32", "tf32")
+        td.gemm_mode = _lib.RT_GEMM_TF32_TCGEN05 if gemm == "tf32" else _lib.RT_GEMM_FP32_SIMT
         self.B, self.T, self.P, self.n = mbatch, nstep_train, burn_in, nstep_target
         self.Nq, self.A, self.U = num_quantiles, num_actions, lstm_units
         h = C.c_void_p()

@@ -10,6 +10,7 @@ from tests.util import load_golden
 
 def make_learner(c, **kw):
     from rltime_b200.learner import DeviceLearner
+    kw.setdefault("gemm", "fp32")
     return DeviceLearner(c["in_shape"], c["conv"], c["lstm"], c["fc"], c["actions"], c["nq"],
                          c["embed"], c["dueling"], mbatch=c["B"], nstep_train=c["T"],
                          burn_in=c["P"], nstep_target=c["n"], gamma=c["gamma"],
@@ -150,3 +151,92 @@ def test_learner_full_size_vs_oracle():
         assert not errs, "\n".join(errs)
     finally:
         L.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_learner_tf32_tensor_core_path(name):
+    """Same golden cases through the tcgen05 TF32 GEMMs (where shapes are TMA-eligible).
+    TF32 multiplies carry a 2^-11 relative operand error: TD-loss / targets held to 1e-3 here,
+    the 1e-4 bar is checked at full size in test_learner_full_size_tf32."""
+    c = CASES[name]
+    g = load_golden("learner_%s.npz" % name)
+    L = make_learner(c, gemm="tf32")
+    try:
+        L.load_state_dict(params_of(g, "online"), 0)
+        L.load_state_dict(params_of(g, "target"), 1)
+        errs = []
+        M, Nq = c["T"] * c["B"], c["nq"]
+        _, raw = batch_of(g, c, 0)
+        b, keep = device_batch(raw, c)
+        taus = taus_of(g, 0)
+        L.step(b, [taus["target"], taus["select"], taus["train"]])
+        st = L.stats()
+        report_diff(errs, "targets", L.debug("targets", (M, Nq)).cpu().numpy(), g["u0/targets"], 1e-3, 1e-3)
+        report_diff(errs, "qloss", st["qloss"], g["u0/qloss"], 1e-3, 1e-3)
+        report_diff(errs, "report", L.td_abs().cpu().numpy(), g["u0/report"], 1e-3, 1e-3)
+        report_diff(errs, "grad_norm", st["grad_norm"], g["u0/grad_norm"], 2e-2, 1e-5)
+        assert not errs, "\n".join(errs)
+    finally:
+        L.close()
+
+
+def _full_size_case():
+    c = dict(in_shape=(4, 84, 84), conv=[(32, 8, 4), (64, 4, 2), (64, 3, 1)], lstm=512, fc=512,
+             actions=6, nq=32, embed=64, dueling=True, B=32, T=20, P=0, n=2, gamma=0.99,
+             double_q=True, rnn_bootstrap=True, vf_eps=None, clip_grad=40.0, adam_eps=1e-5)
+    rs = np.random.RandomState(0)
+    S, B, n = c["T"], c["B"], c["n"]
+    raw = {
+        "all_x": rs.randint(0, 256, (S + n, B, 4, 84, 84)).astype(np.uint8),
+        "all_hx": rs.randn(S + n, B, 512).astype(np.float32),
+        "all_cx": rs.randn(S + n, B, 512).astype(np.float32),
+        "all_initials": (rs.rand(S + n, B) < 0.02).astype(np.float32),
+        "returns": np.sign(rs.randn(S, B)), "nsteps": np.full((S, B), n, dtype=np.int64),
+        "target_masks": (rs.rand(S, B) > 0.05).astype(np.float64),
+        "actions": rs.randint(0, 6, (S, B)).astype(np.int64),
+        "importance_weights": rs.rand(S, B) * 0.5 + 0.5,
+    }
+    return c, raw
+
+
+@pytest.mark.gpu
+def test_learner_full_size_tf32_vs_fp32_path():
+    """Config-3 shapes: the tcgen05 TF32 path against this library's fp32 SIMT path (itself
+    pinned to the oracle above): TD-loss / per-row |td| / targets within the 1e-4 parity bar."""
+    c, raw = _full_size_case()
+    spec = spec_of(c)
+    p_on, p_tg = spec.init_params(1), spec.init_params(2)
+    gen = torch.Generator().manual_seed(3)
+    M = c["T"] * c["B"]
+    taus = [torch.rand(M * 32, generator=gen) for _ in range(3)]
+    out = {}
+    for mode in ("fp32", "tf32"):
+        L = make_learner(c, gemm=mode)
+        try:
+            L.load_state_dict(p_on, 0)
+            L.load_state_dict(p_tg, 1)
+            b, keep = device_batch(raw, c)
+            L.step(b, taus)
+            out[mode] = dict(st=L.stats(), targets=L.debug("targets", (M, 32)).cpu().numpy(),
+                             report=L.td_abs().cpu().numpy(), grads=L.state_dict(2))
+        finally:
+            L.close()
+    a, b_ = out["fp32"], out["tf32"]
+    print("qloss fp32 %.6f tf32 %.6f | td_mean %.6f %.6f | grad_norm %.5f %.5f | max|dtargets| %.2e "
+          "max|dreport| %.2e" % (a["st"]["qloss"], b_["st"]["qloss"], a["st"]["td_mean"],
+                                b_["st"]["td_mean"], a["st"]["grad_norm"], b_["st"]["grad_norm"],
+                                np.abs(a["targets"] - b_["targets"]).max(),
+                                np.abs(a["report"] - b_["report"]).max()))
+    errs = []
+    report_diff(errs, "qloss", b_["st"]["qloss"], a["st"]["qloss"], 0, 1e-4)
+    report_diff(errs, "td_mean", b_["st"]["td_mean"], a["st"]["td_mean"], 0, 1e-4)
+    report_diff(errs, "report", b_["report"], a["report"], 0, 1e-4)
+    report_diff(errs, "targets", b_["targets"], a["targets"], 0, 2e-4)
+    report_diff(errs, "grad_norm", b_["st"]["grad_norm"], a["st"]["grad_norm"], 1e-2, 0)
+    for k in a["grads"]:
+        ga, gb = a["grads"][k].numpy(), b_["grads"][k].numpy()
+        rel = np.linalg.norm(ga - gb) / (np.linalg.norm(ga) + 1e-12)
+        if rel > 5e-2:
+            errs.append("grad %s: relative L2 error %.3e" % (k, rel))
+    assert not errs, "\n".join(errs)
