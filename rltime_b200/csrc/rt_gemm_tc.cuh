@@ -89,14 +89,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
+//   layout 2 = SWIZZLE_128B          (16-byte chunks XOR row%8; K-major operands)
+//   layout 1 = SWIZZLE_128B_BASE32B  (32-byte chunks XOR row%4; the only swizzled layout the
+//              tensor core accepts for MN-major 32-bit (tf32) operands — filled by TMA with
+//              CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;  // LayoutType::SWIZZLE_128B
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -201,12 +206,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K inside the swizzle span.
-          // MN-major: atoms (BLOCK_K*128 B apart) of 8-row K groups 1024 B apart.
-          uint64_t ad = A_MN ? make_smem_desc(sa + k * 1024, BLOCK_K * 128, 1024)
-                             : make_smem_desc(sa + k * (UMMA_K * 4), 16, 1024);
-          uint64_t bd = B_MN ? make_smem_desc(sb + k * 1024, BLOCK_K * 128, 1024)
-                             : make_smem_desc(sb + k * (UMMA_K * 4), 16, 1024);
+          // K-major: 8-row groups 1024 B apart (SBO), +32 B per UMMA_K inside the swizzle span.
+          // MN-major: 32-float atoms BLOCK_K*128 B apart (LBO); inside an atom the K rows are
+          // 128 B apart in groups of 4 (SBO = 512 B); one UMMA_K = 8 rows = 1024 B.
+          uint64_t ad = A_MN ? make_smem_desc(sa + k * 1024, BLOCK_K * 128, 512, 1)
+                             : make_smem_desc(sa + k * (UMMA_K * 4), 16, 1024, 2);
+          uint64_t bd = B_MN ? make_smem_desc(sb + k * 1024, BLOCK_K * 128, 512, 1)
+                             : make_smem_desc(sb + k * (UMMA_K * 4), 16, 1024, 2);
           umma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire

@@ -129,37 +129,57 @@ __global__ void k_splitk_reduce(const __grid_constant__ GemmArgs g, int splits) 
 // ------------------------------------------------------------------------------ im2col
 // conv input NCHW uint8 frames (the replay batch), fused x.float() * (1/255)
 // (rltime/models/torch/modules/cnn.py:44-45).  col[(m,oh,ow), (c,kh,kw)].
+// VEC = 4: a thread converts four consecutive kw taps (one aligned 32-bit load, one 16-byte
+// store); requires KH % 4 == 0, S % 4 == 0, W % 4 == 0 (nature-CNN conv1: k8 s4 on 84x84).
+template <int VEC>
 __global__ void k_im2col_u8_nchw(const uint8_t* __restrict__ x, float* __restrict__ col, int rows,
                                  int C, int H, int W, int KH, int S, int OH, int OW, float scale) {
   const int K = C * KH * KH;
-  size_t total = (size_t)rows * OH * OW * K;
+  const int KV = K / VEC;
+  size_t total = (size_t)rows * OH * OW * KV;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
-    int k = (int)(idx % K);
-    size_t r = idx / K;
+    int k = (int)(idx % KV) * VEC;
+    size_t r = idx / KV;
     int ow = (int)(r % OW);
     int oh = (int)((r / OW) % OH);
     size_t m = r / ((size_t)OW * OH);
     int kw = k % KH, kh = (k / KH) % KH, c = k / (KH * KH);
-    uint8_t v = x[((m * C + c) * H + (oh * S + kh)) * W + (ow * S + kw)];
-    col[idx] = __fmul_rn((float)v, scale);
+    const uint8_t* src = x + ((m * C + c) * H + (oh * S + kh)) * W + (ow * S + kw);
+    if (VEC == 4) {
+      uint32_t v = *reinterpret_cast<const uint32_t*>(src);
+      float4 o;
+      o.x = __fmul_rn((float)(v & 0xff), scale);
+      o.y = __fmul_rn((float)((v >> 8) & 0xff), scale);
+      o.z = __fmul_rn((float)((v >> 16) & 0xff), scale);
+      o.w = __fmul_rn((float)(v >> 24), scale);
+      *reinterpret_cast<float4*>(col + r * K + k) = o;
+    } else {
+      col[r * K + k] = __fmul_rn((float)src[0], scale);
+    }
   }
 }
 
-// conv input NHWC float.  col[(m,oh,ow), (kh,kw,c)].
+// conv input NHWC float.  col[(m,oh,ow), (kh,kw,c)].  VEC = 4 moves float4 (C % 4 == 0).
+template <int VEC>
 __global__ void k_im2col_f32_nhwc(const float* __restrict__ x, float* __restrict__ col, int rows,
                                   int C, int H, int W, int KH, int S, int OH, int OW) {
   const int K = C * KH * KH;
-  size_t total = (size_t)rows * OH * OW * K;
+  const int KV = K / VEC;
+  size_t total = (size_t)rows * OH * OW * KV;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
-    int k = (int)(idx % K);
-    size_t r = idx / K;
+    int k = (int)(idx % KV) * VEC;
+    size_t r = idx / KV;
     int ow = (int)(r % OW);
     int oh = (int)((r / OW) % OH);
     size_t m = r / ((size_t)OW * OH);
     int c = k % C, kw = (k / C) % KH, kh = k / (C * KH);
-    col[idx] = x[((m * H + (oh * S + kh)) * W + (ow * S + kw)) * C + c];
+    const float* src = x + ((m * H + (oh * S + kh)) * W + (ow * S + kw)) * C + c;
+    if (VEC == 4)
+      *reinterpret_cast<float4*>(col + r * K + k) = *reinterpret_cast<const float4*>(src);
+    else
+      col[r * K + k] = src[0];
   }
 }
 
@@ -442,17 +462,26 @@ __global__ void k_loss_stats(const float* __restrict__ row_loss, const float* __
 }
 
 // -------------------------------------------------------------------- column reductions
-// out[n] = sum_m x[m, n]; two deterministic stages.
+// out[n] = sum_m x[m, n]; two deterministic stages.  Stage 1: a CTA of 32 x 8 threads owns 32
+// columns and a slab of rows; a warp reads 128 contiguous bytes per row.
 __global__ void k_colsum_partial(const float* __restrict__ x, float* __restrict__ part, size_t rows,
                                  int N, int rows_per_block) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+  __shared__ float s[8][33];
+  int n = blockIdx.x * 32 + threadIdx.x;
   size_t r0 = (size_t)blockIdx.y * rows_per_block;
   size_t r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
   float acc = 0.f;
-  for (size_t r = r0; r < r1; ++r) acc += x[r * N + n];
-  part[(size_t)blockIdx.y * N + n] = acc;
+  if (n < N)
+    for (size_t r = r0 + threadIdx.y; r < r1; r += 8) acc += x[r * N + n];
+  s[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += s[j][threadIdx.x];
+    part[(size_t)blockIdx.y * N + n] = t;
+  }
 }
 __global__ void k_colsum_final(const float* __restrict__ part, float* __restrict__ out, int parts,
                                int N, int accumulate) {

@@ -34,8 +34,10 @@ struct TmapKey {
   const void* ptr;
   uint64_t d0, d1, pitch;
   uint32_t b0, b1;
+  int mn;
   bool operator<(const TmapKey& o) const {
-    return std::tie(ptr, d0, d1, pitch, b0, b1) < std::tie(o.ptr, o.d0, o.d1, o.pitch, o.b0, o.b1);
+    return std::tie(ptr, d0, d1, pitch, b0, b1, mn) <
+           std::tie(o.ptr, o.d0, o.d1, o.pitch, o.b0, o.b1, o.mn);
   }
 };
 
@@ -207,8 +209,8 @@ int gemm_simt(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
 }
 
 int get_tmap(GemmCtx& cx, const float* ptr, uint64_t d0, uint64_t d1, uint64_t pitch_elems, uint32_t b0,
-             uint32_t b1, const CUtensorMap** out) {
-  TmapKey key{ptr, d0, d1, pitch_elems, b0, b1};
+             uint32_t b1, int mn_major, const CUtensorMap** out) {
+  TmapKey key{ptr, d0, d1, pitch_elems, b0, b1, mn_major};
   auto it = cx.tmaps.find(key);
   if (it == cx.tmaps.end()) {
     if (!cx.encode) {
@@ -225,7 +227,8 @@ int get_tmap(GemmCtx& cx, const float* ptr, uint64_t d0, uint64_t d1, uint64_t p
     cuuint32_t box[2] = {b0, b1};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = cx.encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
       return rt::fail(RT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu) pitch=%llu box=(%u,%u)",
@@ -254,10 +257,11 @@ int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs& 
 
 bool tc_eligible(const rtk::GemmArgs& g) {
   auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
-  if (g.transA && !g.transB) return false;           // (MN-major A, K-major B) is never needed
+  if (g.transA && g.transB) return false;            // (MN-major A, K-major B) is never needed
   if (g.K < 32 || g.N < 8 || g.M < 1) return false;
   if ((g.lda & 3) || (g.ldb & 3) || !al16(g.A) || !al16(g.B)) return false;
   if (!g.transA && g.K > g.lda) return false;
+  if (g.transA && g.M > g.lda) return false;
   return true;
 }
 
@@ -278,10 +282,10 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   int kbps = cdiv(num_kb, splits);
   splits = cdiv(num_kb, kbps);
   const CUtensorMap *ta = nullptr, *tb = nullptr;
-  if (A_MN) RT_TRY(get_tmap(cx, g.A, g.M, g.K, g.lda, 32, rttc::BLOCK_K, &ta));
-  else      RT_TRY(get_tmap(cx, g.A, g.K, g.M, g.lda, rttc::BLOCK_K, rttc::BLOCK_M, &ta));
-  if (B_MN) RT_TRY(get_tmap(cx, g.B, g.N, g.K, g.ldb, 32, rttc::BLOCK_K, &tb));
-  else      RT_TRY(get_tmap(cx, g.B, g.K, g.N, g.ldb, rttc::BLOCK_K, BN, &tb));
+  if (A_MN) RT_TRY(get_tmap(cx, g.A, g.M, g.K, g.lda, 32, rttc::BLOCK_K, 1, &ta));
+  else      RT_TRY(get_tmap(cx, g.A, g.K, g.M, g.lda, rttc::BLOCK_K, rttc::BLOCK_M, 0, &ta));
+  if (B_MN) RT_TRY(get_tmap(cx, g.B, g.N, g.K, g.ldb, 32, rttc::BLOCK_K, 1, &tb));
+  else      RT_TRY(get_tmap(cx, g.B, g.K, g.N, g.ldb, rttc::BLOCK_K, BN, 0, &tb));
   rttc::TcArgs a;
   g.ws = cx.ws;
   g.kchunk = kbps * rttc::BLOCK_K;
@@ -326,14 +330,16 @@ rtk::GemmArgs mk(const float* A, int lda, int transA, const float* B, int ldb, i
 
 int colsum(rt_learner* h, cudaStream_t st, const float* x, size_t rows, int N, float* out,
            int accumulate) {
-  int rpb = 1024;
-  int parts = cdiv(rows, rpb);
-  if (parts > 2048) {
-    rpb = cdiv(rows, 2048);
-    parts = cdiv(rows, rpb);
-  }
-  dim3 grid(cdiv(N, 128), parts);
-  rtk::k_colsum_partial<<<grid, 128, 0, st>>>(x, h->colsum_part, rows, N, rpb);
+  // enough row slabs to fill the GPU even when N is a single 32-column block
+  int col_blocks = cdiv(N, 32);
+  int parts = cdiv(592, col_blocks);
+  if ((size_t)parts * 64 > rows) parts = cdiv(rows, 64);
+  if (parts > 2048) parts = 2048;
+  if (parts < 1) parts = 1;
+  int rpb = cdiv(rows, parts);
+  parts = cdiv(rows, rpb);
+  dim3 grid(col_blocks, parts);
+  rtk::k_colsum_partial<<<grid, dim3(32, 8), 0, st>>>(x, h->colsum_part, rows, N, rpb);
   RT_LAUNCH_CHECK();
   rtk::k_colsum_final<<<cdiv(N, 128), 128, 0, st>>>(h->colsum_part, out, parts, N, accumulate);
   RT_LAUNCH_CHECK();
@@ -347,6 +353,32 @@ int grid1d(size_t n, int threads = 256) {
   return (int)b;
 }
 
+int launch_im2col_u8(cudaStream_t st, const uint8_t* xin, float* col, int rc, const ConvL& L, float scale) {
+  size_t n = (size_t)rc * L.hout * L.wout * L.K;
+  bool vec = (L.k % 4 == 0) && (L.s % 4 == 0) && (L.win % 4 == 0) && (((uintptr_t)xin & 3) == 0) &&
+             ((L.cin * L.hin * L.win) % 4 == 0);
+  if (vec)
+    rtk::k_im2col_u8_nchw<4><<<grid1d(n / 4), 256, 0, st>>>(xin, col, rc, L.cin, L.hin, L.win, L.k, L.s,
+                                                            L.hout, L.wout, scale);
+  else
+    rtk::k_im2col_u8_nchw<1><<<grid1d(n), 256, 0, st>>>(xin, col, rc, L.cin, L.hin, L.win, L.k, L.s,
+                                                        L.hout, L.wout, scale);
+  RT_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+int launch_im2col_f32(cudaStream_t st, const float* xin, float* col, int rc, const ConvL& L) {
+  size_t n = (size_t)rc * L.hout * L.wout * L.K;
+  if (L.cin % 4 == 0)
+    rtk::k_im2col_f32_nhwc<4><<<grid1d(n / 4), 256, 0, st>>>(xin, col, rc, L.cin, L.hin, L.win, L.k, L.s,
+                                                             L.hout, L.wout);
+  else
+    rtk::k_im2col_f32_nhwc<1><<<grid1d(n), 256, 0, st>>>(xin, col, rc, L.cin, L.hin, L.win, L.k, L.s,
+                                                         L.hout, L.wout);
+  RT_LAUNCH_CHECK();
+  return RT_OK;
+}
+
 // CNN forward for `rows` frames, chunked so the im2col buffers stay L2-resident.
 int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows) {
   const float scale = (float)(1.0 / 255.0);
@@ -358,13 +390,11 @@ int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t*
       size_t n_col = (size_t)rc * opix * L.K;
       if (i == 0) {
         const uint8_t* xin = x + (size_t)r0 * L.cin * L.hin * L.win;
-        rtk::k_im2col_u8_nchw<<<grid1d(n_col), 256, 0, st>>>(xin, h->col, rc, L.cin, L.hin, L.win,
-                                                            L.k, L.s, L.hout, L.wout, scale);
+        RT_TRY(launch_im2col_u8(st, xin, h->col, rc, L, scale));
       } else {
         const ConvL& Lp = h->conv[i - 1];
         const float* xin = h->c_out[i - 1] + (size_t)r0 * Lp.hout * Lp.wout * Lp.f;
-        rtk::k_im2col_f32_nhwc<<<grid1d(n_col), 256, 0, st>>>(xin, h->col, rc, L.cin, L.hin, L.win,
-                                                             L.k, L.s, L.hout, L.wout);
+        RT_TRY(launch_im2col_f32(st, xin, h->col, rc, L));
       }
       RT_LAUNCH_CHECK();
       float* out = h->c_out[i] + (size_t)r0 * opix * L.f;
@@ -551,13 +581,11 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
       // recompute this layer's im2col input
       if (i == 0) {
         const uint8_t* xin = x + (size_t)r0 * L.cin * L.hin * L.win;
-        rtk::k_im2col_u8_nchw<<<grid1d(n_col), 256, 0, st>>>(xin, h->col, rc, L.cin, L.hin, L.win,
-                                                            L.k, L.s, L.hout, L.wout, scale);
+        RT_TRY(launch_im2col_u8(st, xin, h->col, rc, L, scale));
       } else {
         const ConvL& Lp = h->conv[i - 1];
         const float* xin = h->c_out[i - 1] + (size_t)r0 * Lp.hout * Lp.wout * Lp.f;
-        rtk::k_im2col_f32_nhwc<<<grid1d(n_col), 256, 0, st>>>(xin, h->col, rc, L.cin, L.hin, L.win,
-                                                             L.k, L.s, L.hout, L.wout);
+        RT_TRY(launch_im2col_f32(st, xin, h->col, rc, L));
       }
       RT_LAUNCH_CHECK();
       rtk::GemmArgs g = mk(dy, L.f, 1, h->col, L.K, 0, G + L.w, L.K, L.f, L.K, (int)(rc * opix));

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt
 nproc >> gpurun_out/smi.txt
 echo "=== gemm tests"
-timeout 300 python -m pytest tests/test_gemm_gpu.py -m gpu -q -s --timeout 240 2>&1 | tail -45 | tee gpurun_out/pytest_gemm.log
+timeout 300 python -m pytest tests/test_gemm_gpu.py -m gpu -q -s --timeout 240 2>&1 | tail -80 | cut -c1-260 | tee gpurun_out/pytest_gemm.log
 if grep -q "failed\|error\|Timeout" gpurun_out/pytest_gemm.log; then export RT_BENCH_GEMM=fp32; echo "tcgen05 GEMM NOT green -> bench on fp32 path"; fi
 echo "=== pytest gpu (all, continue past failures)"
 timeout 1200 python -m pytest tests -m gpu -q --timeout 600 --deselect tests/test_gemm_gpu.py 2>&1 | tail -60 | tee gpurun_out/pytest_gpu.log
