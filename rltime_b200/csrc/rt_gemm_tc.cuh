@@ -225,30 +225,77 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int m = m0 + q * 32 + lane;
+    const bool split = gridDim.z > 1;
+    // 16-byte vector path: every pointer touched per row is 16 B aligned and the chunk is full
+    const bool vec_ok = split ? ((g.N & 3) == 0)
+                              : (((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+                                 (!g.mask || (((g.ldmask & 3) == 0) &&
+                                              ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0))) &&
+                                 (!g.bias || ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0)) &&
+                                 (!g.bias2 || ((reinterpret_cast<uintptr_t>(g.bias2) & 15) == 0)));
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      if (m < g.M) {
-        int nb = n0 + c * 32;
-        if (gridDim.z > 1) {
-          float* dst = g.ws + ((size_t)blockIdx.z * g.M + m) * g.N + nb;
+      if (m >= g.M) continue;
+      const int nb = n0 + c * 32;
+      if (nb >= g.N) continue;
+      if (vec_ok && nb + 32 <= g.N) {
+        if (split) {
+          float4* dst = reinterpret_cast<float4*>(g.ws + ((size_t)blockIdx.z * g.M + m) * g.N + nb);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < g.N) dst[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         } else {
+          float4* dst = reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + nb);
+          const float4* msk = g.mask ? reinterpret_cast<const float4*>(g.mask + (size_t)m * g.ldmask + nb) : nullptr;
+          const float4* b1 = g.bias ? reinterpret_cast<const float4*>(g.bias + nb) : nullptr;
+          const float4* b2 = g.bias2 ? reinterpret_cast<const float4*>(g.bias2 + nb) : nullptr;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            int n = nb + j;
-            if (n < g.N) {
-              float r = rtk::gemm_epilogue(g, m, n, __uint_as_float(v[j]));
-              if (a.round_tf32) {
-                uint32_t t;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
-                r = __uint_as_float(t);
-              }
-              g.C[(size_t)m * g.ldc + n] = r;
+          for (int j = 0; j < 8; ++j) {
+            float r[4] = {__uint_as_float(v[4 * j]) * g.alpha, __uint_as_float(v[4 * j + 1]) * g.alpha,
+                          __uint_as_float(v[4 * j + 2]) * g.alpha, __uint_as_float(v[4 * j + 3]) * g.alpha};
+            if (b1) { float4 t = __ldg(b1 + j); r[0] += t.x; r[1] += t.y; r[2] += t.z; r[3] += t.w; }
+            if (b2) { float4 t = __ldg(b2 + j); r[0] += t.x; r[1] += t.y; r[2] += t.z; r[3] += t.w; }
+            if (g.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) r[e] = fmaxf(r[e], 0.f);
             }
+            if (msk) {
+              float4 t = msk[j];
+              r[0] = t.x > 0.f ? r[0] : 0.f; r[1] = t.y > 0.f ? r[1] : 0.f;
+              r[2] = t.z > 0.f ? r[2] : 0.f; r[3] = t.w > 0.f ? r[3] : 0.f;
+            }
+            if (g.accumulate) { float4 t = dst[j]; r[0] += t.x; r[1] += t.y; r[2] += t.z; r[3] += t.w; }
+            if (a.round_tf32) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                uint32_t t;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r[e]));
+                r[e] = __uint_as_float(t);
+              }
+            }
+            dst[j] = make_float4(r[0], r[1], r[2], r[3]);
+          }
+        }
+      } else if (split) {
+        float* dst = g.ws + ((size_t)blockIdx.z * g.M + m) * g.N + nb;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < g.N) dst[j] = __uint_as_float(v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          int n = nb + j;
+          if (n < g.N) {
+            float r = rtk::gemm_epilogue(g, m, n, __uint_as_float(v[j]));
+            if (a.round_tf32) {
+              uint32_t t;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
+              r = __uint_as_float(t);
+            }
+            g.C[(size_t)m * g.ldc + n] = r;
           }
         }
       }

@@ -115,15 +115,23 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) k_sgemm(const __grid_co
   }
 }
 
-// Deterministic split-K reduction + epilogue.
+// Deterministic split-K reduction + epilogue: a CTA of 32 x 8 threads folds 32 outputs, the 8
+// row-lanes striding over the splits (fixed order), then a fixed 8-way tree.
 __global__ void k_splitk_reduce(const __grid_constant__ GemmArgs g, int splits) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float s[8][33];
   size_t total = (size_t)g.M * g.N;
-  if (idx >= total) return;
-  int m = (int)(idx / g.N), n = (int)(idx - (size_t)m * g.N);
+  size_t idx = (size_t)blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  for (int s = 0; s < splits; ++s) acc += g.ws[(size_t)s * total + idx];
-  g.C[(size_t)m * g.ldc + n] = gemm_epilogue(g, m, n, acc);
+  if (idx < total)
+    for (int sp = threadIdx.y; sp < splits; sp += 8) acc += g.ws[(size_t)sp * total + idx];
+  s[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && idx < total) {
+    float t = ((s[0][threadIdx.x] + s[1][threadIdx.x]) + (s[2][threadIdx.x] + s[3][threadIdx.x])) +
+              ((s[4][threadIdx.x] + s[5][threadIdx.x]) + (s[6][threadIdx.x] + s[7][threadIdx.x]));
+    int m = (int)(idx / g.N), n = (int)(idx - (size_t)m * g.N);
+    g.C[(size_t)m * g.ldc + n] = gemm_epilogue(g, m, n, t);
+  }
 }
 
 // ------------------------------------------------------------------------------ im2col
@@ -484,12 +492,152 @@ __global__ void k_colsum_partial(const float* __restrict__ x, float* __restrict_
   }
 }
 __global__ void k_colsum_final(const float* __restrict__ part, float* __restrict__ out, int parts,
-                               int N, int accumulate) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+                               int N, int accumulate, int pstride) {
+  __shared__ float s[8][33];
+  int n = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  for (int p = 0; p < parts; ++p) acc += part[(size_t)p * N + n];
-  out[n] = accumulate ? out[n] + acc : acc;
+  if (n < N)
+    for (int p = threadIdx.y; p < parts; p += 8) acc += part[(size_t)p * pstride + n];
+  s[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = ((s[0][threadIdx.x] + s[1][threadIdx.x]) + (s[2][threadIdx.x] + s[3][threadIdx.x])) +
+              ((s[4][threadIdx.x] + s[5][threadIdx.x]) + (s[6][threadIdx.x] + s[7][threadIdx.x]));
+    out[n] = accumulate ? out[n] + t : t;
+  }
+}
+
+// ------------------------------------------------------------------------- small heads
+// out layer (A actions) + dueling value layer + combine in one pass, one warp per row
+// (rltime/policies/torch/dqn.py:78-112): adv = h1 Wout^T + b, v = v1 Wv^T + bv,
+// q = v + adv - mean_a adv.  A <= 32.
+template <int MAXA>
+__global__ void k_heads_out(const float* __restrict__ h1, const float* __restrict__ v1,
+                            const float* __restrict__ Wout, const float* __restrict__ bout,
+                            const float* __restrict__ Wv, const float* __restrict__ bv,
+                            float* __restrict__ adv, float* __restrict__ vout, float* __restrict__ q,
+                            size_t rows, int F, int A) {
+  size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float acc[MAXA];
+#pragma unroll
+  for (int a = 0; a < MAXA; ++a) acc[a] = 0.f;
+  float accv = 0.f;
+  const float* hr = h1 + r * F;
+  const float* vr = v1 ? v1 + r * F : nullptr;
+  for (int f = lane; f < F; f += 32) {
+    float hv = hr[f];
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < A) acc[a] = fmaf(hv, Wout[(size_t)a * F + f], acc[a]);
+    if (vr) accv = fmaf(vr[f], Wv[f], accv);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+    accv += __shfl_xor_sync(0xffffffffu, accv, o);
+  }
+  if (lane == 0) {
+    float mean = 0.f;
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < A) {
+        acc[a] += bout[a];
+        mean += acc[a];
+      }
+    mean /= (float)A;
+    float vv = vr ? accv + bv[0] : 0.f;
+    if (vr) vout[r] = vv;
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < A) {
+        adv[r * A + a] = acc[a];
+        q[r * A + a] = vr ? (vv + acc[a] - mean) : acc[a];
+      }
+  }
+}
+
+// Data gradients of the two small layers, fused with the ReLU masks of their inputs:
+//   dh1[r,f] = (sum_a dadv[r,a] Wout[a,f]) * (h1 > 0),  dadv[r,a] = g_r (1[a==act] - dueling/A)
+//   dv1[r,f] = g_r Wv[f] * (v1 > 0)                      (dueling only)
+__global__ void k_heads_dsmall(const float* __restrict__ dtheta, const long long* __restrict__ actions,
+                               const float* __restrict__ Wout, const float* __restrict__ Wv,
+                               const float* __restrict__ h1, const float* __restrict__ v1,
+                               float* __restrict__ dh1, float* __restrict__ dv1, size_t rows, int F, int A,
+                               int Nq, int dueling) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * F) return;
+  size_t r = idx / F;
+  int f = (int)(idx - r * F);
+  float g = dtheta[r];
+  int act = (int)actions[r / Nq];
+  float w = Wout[(size_t)act * F + f];
+  if (dueling) {
+    float mean = 0.f;
+    for (int a = 0; a < A; ++a) mean += Wout[(size_t)a * F + f];
+    w -= mean / (float)A;
+  }
+  dh1[idx] = h1[idx] > 0.f ? g * w : 0.f;
+  if (dueling) dv1[idx] = v1[idx] > 0.f ? g * Wv[f] : 0.f;
+}
+
+// Weight / bias gradients of the two small layers: partial sums over a slab of rows.
+//   part[p][a][f] = sum_r dadv[r,a] h1[r,f]   (a < A)       part[p][A][f] = sum_r g_r v1[r,f]
+//   partb[p][a]   = sum_r dadv[r,a]                          partb[p][A]  = sum_r g_r
+template <int MAXA>
+__global__ void k_heads_wgrad(const float* __restrict__ dtheta, const long long* __restrict__ actions,
+                              const float* __restrict__ h1, const float* __restrict__ v1,
+                              float* __restrict__ part, float* __restrict__ partb, size_t rows, int F,
+                              int A, int Nq, int dueling, int rows_per_block) {
+  __shared__ float s[8][33];
+  int f = blockIdx.x * 32 + threadIdx.x;
+  size_t r0 = (size_t)blockIdx.y * rows_per_block, r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc[MAXA + 1], accb[MAXA + 1];
+#pragma unroll
+  for (int a = 0; a <= MAXA; ++a) acc[a] = accb[a] = 0.f;
+  const float inv = dueling ? 1.f / (float)A : 0.f;
+  if (f < F)
+    for (size_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      float g = dtheta[r];
+      int act = (int)actions[r / Nq];
+      float hv = h1[r * F + f];
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < A) {
+          float d = g * ((a == act ? 1.f : 0.f) - inv);
+          acc[a] = fmaf(d, hv, acc[a]);
+          accb[a] += d;
+        }
+      if (dueling) {
+        acc[MAXA] = fmaf(g, v1[r * F + f], acc[MAXA]);
+        accb[MAXA] += g;
+      }
+    }
+  const int nout = A + (dueling ? 1 : 0);
+  for (int o = 0; o < nout; ++o) {
+    int a = (o == A) ? MAXA : o;
+    __syncthreads();
+    s[threadIdx.y][threadIdx.x] = acc[a];
+    __syncthreads();
+    if (threadIdx.y == 0 && f < F) {
+      float t = 0.f;
+      for (int j = 0; j < 8; ++j) t += s[j][threadIdx.x];
+      part[((size_t)blockIdx.y * nout + o) * F + f] = t;
+    }
+    if (blockIdx.x == 0) {   // bias partials: identical across f, take column 0's lanes
+      __syncthreads();
+      s[threadIdx.y][threadIdx.x] = accb[a];
+      __syncthreads();
+      if (threadIdx.y == 0 && threadIdx.x == 0) {
+        float t = 0.f;
+        for (int j = 0; j < 8; ++j) t += s[j][0];
+        partb[(size_t)blockIdx.y * nout + o] = t;
+      }
+    }
+  }
 }
 
 // --------------------------------------------------------------------------- optimiser

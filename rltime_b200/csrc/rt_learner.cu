@@ -117,6 +117,8 @@ struct rt_learner {
         *dfeatq = nullptr, *dgates = nullptr, *dh_carry = nullptr, *dc_carry = nullptr, *dfeat = nullptr;
   GemmCtx gx;
   float* colsum_part = nullptr;
+  float *hw_part = nullptr, *hw_partb = nullptr;  // small-head weight-gradient partials
+  int hw_parts = 256;
   double* sumsq_part = nullptr;
   float* tau_stage = nullptr;  // device staging for injected taus (5 segments)
   unsigned long long rng_counter = 0;
@@ -202,7 +204,7 @@ int gemm_simt(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   cx.simt_launches++;
   if (splits > 1) {
     size_t total = (size_t)g.M * g.N;
-    rtk::k_splitk_reduce<<<cdiv(total, 256), 256, 0, st>>>(g, splits);
+    rtk::k_splitk_reduce<<<cdiv(total, 32), dim3(32, 8), 0, st>>>(g, splits);
     RT_LAUNCH_CHECK();
   }
   return RT_OK;
@@ -266,15 +268,19 @@ bool tc_eligible(const rtk::GemmArgs& g) {
 }
 
 int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
-  const int BN = g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128);
   const int A_MN = g.transA ? 1 : 0, B_MN = g.transB ? 0 : 1;
-  int tm = cdiv(g.M, rttc::BLOCK_M), tn = cdiv(g.N, BN);
+  int BN = g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128);
+  int tm = cdiv(g.M, rttc::BLOCK_M);
+  // few row tiles (e.g. the recurrent step, M = B): narrower N tiles put more SMs to work
+  while (BN > 32 && (long long)tm * cdiv(g.N, BN) < 74) BN >>= 1;
+  int tn = cdiv(g.N, BN);
   long long tiles = (long long)tm * tn;
   int num_kb = cdiv(g.K, rttc::BLOCK_K);
   int splits = 1;
-  if (tiles < 148 && num_kb >= 16) {
-    splits = (int)((296 + tiles - 1) / tiles);
-    if (splits > num_kb / 4) splits = num_kb / 4;
+  if (tiles < 74 && num_kb >= 64) {
+    splits = (int)((148 + tiles - 1) / tiles);
+    if (splits > num_kb / 16) splits = num_kb / 16;
+    if (splits > 32) splits = 32;
     size_t per = (size_t)g.M * g.N;
     if ((size_t)splits * per > cx.ws_floats) splits = (int)(cx.ws_floats / per);
     if (splits < 1) splits = 1;
@@ -306,7 +312,7 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   cx.tc_launches++;
   if (splits > 1) {
     size_t total = (size_t)g.M * g.N;
-    rtk::k_splitk_reduce<<<cdiv(total, 256), 256, 0, st>>>(a.g, splits);
+    rtk::k_splitk_reduce<<<cdiv(total, 32), dim3(32, 8), 0, st>>>(a.g, splits);
     RT_LAUNCH_CHECK();
   }
   return RT_OK;
@@ -341,7 +347,7 @@ int colsum(rt_learner* h, cudaStream_t st, const float* x, size_t rows, int N, f
   dim3 grid(col_blocks, parts);
   rtk::k_colsum_partial<<<grid, dim3(32, 8), 0, st>>>(x, h->colsum_part, rows, N, rpb);
   RT_LAUNCH_CHECK();
-  rtk::k_colsum_final<<<cdiv(N, 128), 128, 0, st>>>(h->colsum_part, out, parts, N, accumulate);
+  rtk::k_colsum_final<<<cdiv(N, 32), dim3(32, 8), 0, st>>>(h->colsum_part, out, parts, N, accumulate, N);
   RT_LAUNCH_CHECK();
   return RT_OK;
 }
@@ -469,20 +475,24 @@ int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float*
   g.bias = net + h->o_fcb;
   g.relu = 1;
   RT_TRY(gemm(h->gx, st, g));
-  g = mk(h->h1, F, 0, net + h->o_outw, F, 1, h->adv, A, (int)MQ, A, F);
-  g.bias = net + h->o_outb;
-  RT_TRY(gemm(h->gx, st, g));
   if (h->dueling) {
     g = mk(h->xq, D, 0, net + h->o_vhw, D, 1, h->v1, F, (int)MQ, F, D);
     g.bias = net + h->o_vhb;
     g.relu = 1;
     RT_TRY(gemm(h->gx, st, g));
-    g = mk(h->v1, F, 0, net + h->o_vw, F, 1, h->v, 1, (int)MQ, 1, F);
-    g.bias = net + h->o_vb;
-    RT_TRY(gemm(h->gx, st, g));
   }
-  rtk::k_dueling<<<cdiv(MQ, 256), 256, 0, st>>>(h->adv, h->dueling ? h->v : nullptr, h->q, MQ, A);
-  RT_LAUNCH_CHECK();
+  // out layer + value layer + dueling combine: one warp per row
+  {
+    const float* v1 = h->dueling ? h->v1 : nullptr;
+    int blocks = cdiv(MQ * 32, 256);
+    if (A <= 8)
+      rtk::k_heads_out<8><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
+                                                 net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A);
+    else
+      rtk::k_heads_out<32><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
+                                                  net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A);
+    RT_LAUNCH_CHECK();
+  }
   return RT_OK;
 }
 
@@ -491,31 +501,50 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
   int Nq = h->Nq, D = h->D, F = h->F, A = h->A, E = h->E;
   size_t MQ = (size_t)M * Nq;
   float* G = h->grad;
-  rtk::k_dueling_bwd<<<cdiv(MQ, 256), 256, 0, st>>>(h->dtheta, actions, h->dadv,
-                                                   h->dueling ? h->dv : nullptr, MQ, A, Nq,
-                                                   h->dueling ? 1 : 0);
+  const int duel = h->dueling ? 1 : 0;
+  // small layers (out, value): data gradients fused with the ReLU masks, weight gradients as
+  // slab partials folded deterministically
+  rtk::k_heads_dsmall<<<cdiv(MQ * F, 256), 256, 0, st>>>(h->dtheta, actions, net + h->o_outw,
+                                                        net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, MQ,
+                                                        F, A, Nq, duel);
   RT_LAUNCH_CHECK();
-  // out layer
-  RT_TRY(gemm(h->gx, st, mk(h->dadv, A, 1, h->h1, F, 0, G + h->o_outw, F, A, F, (int)MQ)));
-  RT_TRY(colsum(h, st, h->dadv, MQ, A, G + h->o_outb, 0));
-  rtk::GemmArgs g = mk(h->dadv, A, 0, net + h->o_outw, F, 0, h->dh1, F, (int)MQ, F, A);
-  g.mask = h->h1;
-  g.ldmask = F;
-  RT_TRY(gemm(h->gx, st, g));
+  {
+    int nout = A + duel;
+    int rpb = 128;
+    int parts = cdiv(MQ, rpb);
+    if (parts > h->hw_parts) {
+      rpb = cdiv(MQ, h->hw_parts);
+      parts = cdiv(MQ, rpb);
+    }
+    dim3 grid(cdiv(F, 32), parts);
+    if (A <= 8)
+      rtk::k_heads_wgrad<8><<<grid, dim3(32, 8), 0, st>>>(h->dtheta, actions, h->h1, h->v1, h->hw_part,
+                                                         h->hw_partb, MQ, F, A, Nq, duel, rpb);
+    else
+      rtk::k_heads_wgrad<32><<<grid, dim3(32, 8), 0, st>>>(h->dtheta, actions, h->h1, h->v1, h->hw_part,
+                                                          h->hw_partb, MQ, F, A, Nq, duel, rpb);
+    RT_LAUNCH_CHECK();
+    rtk::k_colsum_final<<<cdiv(A * F, 32), dim3(32, 8), 0, st>>>(h->hw_part, G + h->o_outw, parts, A * F,
+                                                               0, nout * F);
+    RT_LAUNCH_CHECK();
+    rtk::k_colsum_final<<<1, dim3(32, 8), 0, st>>>(h->hw_partb, G + h->o_outb, parts, A, 0, nout);
+    RT_LAUNCH_CHECK();
+    if (duel) {
+      rtk::k_colsum_final<<<cdiv(F, 32), dim3(32, 8), 0, st>>>(h->hw_part + (size_t)A * F, G + h->o_vw,
+                                                             parts, F, 0, nout * F);
+      RT_LAUNCH_CHECK();
+      rtk::k_colsum_final<<<1, dim3(32, 8), 0, st>>>(h->hw_partb + A, G + h->o_vb, parts, 1, 0, nout);
+      RT_LAUNCH_CHECK();
+    }
+  }
   // FC
   RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 1, h->xq, D, 0, G + h->o_fcw, D, F, D, (int)MQ)));
   RT_TRY(colsum(h, st, h->dh1, MQ, F, G + h->o_fcb, 0));
   RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 0, net + h->o_fcw, D, 0, h->dxq, D, (int)MQ, D, F)));
   if (h->dueling) {
-    RT_TRY(gemm(h->gx, st, mk(h->dv, 1, 1, h->v1, F, 0, G + h->o_vw, F, 1, F, (int)MQ)));
-    RT_TRY(colsum(h, st, h->dv, MQ, 1, G + h->o_vb, 0));
-    g = mk(h->dv, 1, 0, net + h->o_vw, F, 0, h->dv1, F, (int)MQ, F, 1);
-    g.mask = h->v1;
-    g.ldmask = F;
-    RT_TRY(gemm(h->gx, st, g));
     RT_TRY(gemm(h->gx, st, mk(h->dv1, F, 1, h->xq, D, 0, G + h->o_vhw, D, F, D, (int)MQ)));
     RT_TRY(colsum(h, st, h->dv1, MQ, F, G + h->o_vhb, 0));
-    g = mk(h->dv1, F, 0, net + h->o_vhw, D, 0, h->dxq, D, (int)MQ, D, F);
+    rtk::GemmArgs g = mk(h->dv1, F, 0, net + h->o_vhw, D, 0, h->dxq, D, (int)MQ, D, F);
     g.accumulate = 1;
     RT_TRY(gemm(h->gx, st, g));
   }
@@ -784,6 +813,9 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     if ((size_t)L.f > maxN) maxN = L.f;
   RT_TRY(dalloc(h, &h->colsum_part, 2048 * maxN));
   RT_TRY(dalloc(h, &h->sumsq_part, 1024));
+  RT_REQUIRE(h->A <= 32, "num_actions > 32 not supported by the fused head kernels");
+  RT_TRY(dalloc(h, &h->hw_part, (size_t)h->hw_parts * (A + 1) * F));
+  RT_TRY(dalloc(h, &h->hw_partb, (size_t)h->hw_parts * (A + 1)));
   *out = h;
   return RT_OK;
 }
