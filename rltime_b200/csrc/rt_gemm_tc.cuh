@@ -311,4 +311,191 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
 }
 
+
+// ------------------------------------------------------------------- implicit-GEMM conv
+// Forward convolution without an im2col buffer: out[(img,oh,ow), f] = relu(sum_k A[..,k] W[f,k] + b)
+// where the A tile (128 output pixels x 32 taps) is gathered straight from the input by four
+// producer warps into the 128B-swizzled K-major stage the tensor core reads:
+//   IN_U8 = 1: input uint8 NCHW frames (replay batch), k = (c, kh, kw), scaled by 1/255 on load
+//              (rltime/models/torch/modules/cnn.py:44-45) — 28 KB read per frame instead of a
+//              400 KB fp32 im2col round trip;
+//   IN_U8 = 0: input fp32 NHWC, k = (kh, kw, c), C % 32 == 0: a k-block is one 128-byte run.
+// Warps 0-3: A producers, then epilogue; warp 4: TMA producer for the filter tile; warp 5: TMEM
+// allocator + MMA issuer.
+struct ConvArgs {
+  const void* in;      // uint8 NCHW or float NHWC
+  float* out;          // [M][N] (NHWC)
+  const float* bias;
+  int rows;            // images
+  int C, H, W, KH, S, OH, OW;
+  int M, N, K;         // M = rows*OH*OW, N = filters, K = C*KH*KH (multiple of 32)
+  float scale;
+  int round_tf32;
+};
+
+template <int BN, int IN_U8, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS)
+k_conv_tc(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvArgs a) {
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
+  constexpr int B_BYTES = BN * BLOCK_K * 4;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BN;
+  const int num_kb = a.K / BLOCK_K;
+
+  if (warp == 4 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 128 + 1);   // 128 gather threads + the TMA thread
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ---------------- A gather: thread t owns 16-byte chunk j = t % 8 of rows i*16 + t/8
+    const int t = threadIdx.x;
+    const int j = t & 7;
+    long long base[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int gm = m0 + i * 16 + (t >> 3);
+      if (gm < a.M) {
+        int ow = gm % a.OW;
+        int oh = (gm / a.OW) % a.OH;
+        long long img = gm / (a.OW * a.OH);
+        base[i] = IN_U8 ? (img * a.C * a.H + (long long)oh * a.S) * a.W + (long long)ow * a.S
+                        : ((img * a.H + (long long)oh * a.S) * a.W + (long long)ow * a.S) * a.C;
+      } else {
+        base[i] = -1;
+      }
+    }
+    for (int kb = 0; kb < num_kb; ++kb) {
+      int s = kb % STAGES;
+      uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* sa = smem + s * STAGE_BYTES;
+      long long koff;
+      if (IN_U8) {
+        int k = kb * BLOCK_K + 4 * j;
+        int kw = k % a.KH, kh = (k / a.KH) % a.KH, c = k / (a.KH * a.KH);
+        koff = ((long long)c * a.H + kh) * a.W + kw;
+      } else {
+        int k = kb * BLOCK_K;
+        int c0 = k % a.C, tap = k / a.C;
+        int kw = tap % a.KH, kh = tap / a.KH;
+        koff = ((long long)kh * a.W + kw) * a.C + c0 + 4 * j;
+      }
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (base[i] < 0) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (IN_U8) {
+          uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(a.in) + base[i] + koff));
+          v[i] = make_float4(__fmul_rn((float)(u & 0xff), a.scale), __fmul_rn((float)((u >> 8) & 0xff), a.scale),
+                             __fmul_rn((float)((u >> 16) & 0xff), a.scale), __fmul_rn((float)(u >> 24), a.scale));
+        } else {
+          v[i] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(a.in) + base[i] + koff));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int r = i * 16 + (t >> 3);
+        *reinterpret_cast<float4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = v[i];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+    }
+    // ---------------- epilogue (same warps: TMEM lane quarter == warp)
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+      if (m >= a.M) continue;
+      const int nb = n0 + c * 32;
+      if (nb + 32 <= a.N && (a.N & 3) == 0) {
+        float4* dst = reinterpret_cast<float4*>(a.out + (size_t)m * a.N + nb);
+        const float4* b1 = reinterpret_cast<const float4*>(a.bias + nb);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 bb = __ldg(b1 + q);
+          float r[4] = {fmaxf(__uint_as_float(v[4 * q]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * q + 1]) + bb.y, 0.f),
+                        fmaxf(__uint_as_float(v[4 * q + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * q + 3]) + bb.w, 0.f)};
+          if (a.round_tf32) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              uint32_t tt;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tt) : "f"(r[e]));
+              r[e] = __uint_as_float(tt);
+            }
+          }
+          dst[q] = make_float4(r[0], r[1], r[2], r[3]);
+        }
+      } else {
+        for (int q = 0; q < 32; ++q)
+          if (nb + q < a.N) a.out[(size_t)m * a.N + nb + q] = fmaxf(__uint_as_float(v[q]) + a.bias[nb + q], 0.f);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (warp == 4) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        int s = kb % STAGES;
+        uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], B_BYTES);
+        tma_load_2d(&tmB, &full_bar[s], smem + s * STAGE_BYTES + A_BYTES, kb * BLOCK_K, n0);
+      }
+    }
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BLOCK_M >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        int s = kb % STAGES;
+        uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+          umma_tf32(tmem_base, make_smem_desc(sa + k * (UMMA_K * 4), 16, 1024, 2),
+                    make_smem_desc(sb + k * (UMMA_K * 4), 16, 1024, 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  }
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+  }
+}
+
 }  // namespace rttc

@@ -694,4 +694,117 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   }
 }
 
+
+// --------------------------------------------------------------------- persistent LSTM
+// Whole recurrence of lstm.py:84-116 in ONE launch: grid = U / 4 CTAs (co-resident, one per
+// SM), each CTA keeps the 16 rows of W_hh of its 4 hidden units (4 gates x 4 units x U
+// floats = 32 KiB at U = 512) in shared memory for all time-steps, stages the masked h_{t-1}
+// (B x U) through shared memory each step, and keeps every cell state c in the register of
+// the thread that owns (batch b = lane (+32 j), unit = warp).  Steps are separated by a
+// grid-wide barrier on a monotone global counter.
+namespace lstm_seq {
+constexpr int UPB = 4;        // hidden units per CTA == warps per CTA
+constexpr int HPAD = 4;       // row padding (floats) of the staged h tile: conflict-free LDS.128
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+}  // namespace lstm_seq
+
+// xg: (T*B, 4U) = x W_ih^T + b_ih + b_hh;  W_hh: (4U, U);  hx, cx: (B, U) state of step 0;
+// initials: (T*B).  Outputs as in the stepwise path: gates (T*B,4U) activated, c_all, h_all,
+// hprev / cprev (masked carry-ins, needed by BPTT), all (T*B, U).  B <= 32 * BCH.
+template <int BCH>
+__global__ void __launch_bounds__(128)
+k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, const float* __restrict__ hx,
+               const float* __restrict__ cx, const float* __restrict__ initials,
+               float* __restrict__ gates, float* __restrict__ c_all, float* __restrict__ h_all,
+               float* __restrict__ hprev, float* __restrict__ cprev, int T, int B, int U,
+               unsigned int* __restrict__ barrier) {
+  using namespace lstm_seq;
+  extern __shared__ float sm[];
+  float* Ws = sm;                          // [4 gates][UPB][U]
+  float* hs = sm + 4 * UPB * U;            // [B][U + HPAD]
+  const int HS = U + HPAD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * UPB + warp;
+  // resident weight slice
+  for (int i = threadIdx.x; i < 4 * UPB * (U / 4); i += blockDim.x) {
+    int row = i / (U / 4), k4 = i - row * (U / 4);
+    int g = row / UPB, u = row - g * UPB;
+    reinterpret_cast<float4*>(Ws)[i] =
+        reinterpret_cast<const float4*>(Whh + ((size_t)g * U + blockIdx.x * UPB + u) * U)[k4];
+  }
+  float c_reg[BCH];
+#pragma unroll
+  for (int j = 0; j < BCH; ++j) {
+    int b = lane + 32 * j;
+    c_reg[j] = b < B ? cx[(size_t)b * U + unit] : 0.f;
+  }
+  for (int t = 0; t < T; ++t) {
+    const float* hsrc = t == 0 ? hx : h_all + (size_t)(t - 1) * B * U;
+    const float* ini = initials + (size_t)t * B;
+    // stage masked h_{t-1}
+    for (int i = threadIdx.x; i < B * (U / 4); i += blockDim.x) {
+      int b = i / (U / 4), k4 = i - b * (U / 4);
+      float keep = 1.f - ini[b];
+      float4 v = __ldcg(reinterpret_cast<const float4*>(hsrc + (size_t)b * U) + k4);  // L2, never stale L1
+      v.x *= keep; v.y *= keep; v.z *= keep; v.w *= keep;
+      *reinterpret_cast<float4*>(hs + (size_t)b * HS + 4 * k4) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < BCH; ++j) {
+      int b = lane + 32 * j;
+      if (b < B) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float4* hr = reinterpret_cast<const float4*>(hs + (size_t)b * HS);
+        const float4* w0 = reinterpret_cast<const float4*>(Ws + ((size_t)0 * UPB + warp) * U);
+        const float4* w1 = reinterpret_cast<const float4*>(Ws + ((size_t)1 * UPB + warp) * U);
+        const float4* w2 = reinterpret_cast<const float4*>(Ws + ((size_t)2 * UPB + warp) * U);
+        const float4* w3 = reinterpret_cast<const float4*>(Ws + ((size_t)3 * UPB + warp) * U);
+#pragma unroll 4
+        for (int k = 0; k < U / 4; ++k) {
+          float4 h4 = hr[k];
+          float4 p = w0[k];
+          a0 = fmaf(h4.x, p.x, a0); a0 = fmaf(h4.y, p.y, a0); a0 = fmaf(h4.z, p.z, a0); a0 = fmaf(h4.w, p.w, a0);
+          p = w1[k];
+          a1 = fmaf(h4.x, p.x, a1); a1 = fmaf(h4.y, p.y, a1); a1 = fmaf(h4.z, p.z, a1); a1 = fmaf(h4.w, p.w, a1);
+          p = w2[k];
+          a2 = fmaf(h4.x, p.x, a2); a2 = fmaf(h4.y, p.y, a2); a2 = fmaf(h4.z, p.z, a2); a2 = fmaf(h4.w, p.w, a2);
+          p = w3[k];
+          a3 = fmaf(h4.x, p.x, a3); a3 = fmaf(h4.y, p.y, a3); a3 = fmaf(h4.z, p.z, a3); a3 = fmaf(h4.w, p.w, a3);
+        }
+        size_t row = (size_t)t * B + b;
+        const float* xr = xg + row * 4 * U + unit;
+        float gi = sigmoidf_(xr[0] + a0);
+        float gf = sigmoidf_(xr[U] + a1);
+        float gg = tanhf(xr[2 * U] + a2);
+        float go = sigmoidf_(xr[3 * U] + a3);
+        float keep = 1.f - ini[b];
+        float cp = c_reg[j] * keep;
+        float c = gf * cp + gi * gg;
+        float h = go * tanhf(c);
+        c_reg[j] = c;
+        float* gr = gates + row * 4 * U + unit;
+        gr[0] = gi; gr[U] = gf; gr[2 * U] = gg; gr[3 * U] = go;
+        c_all[row * U + unit] = c;
+        h_all[row * U + unit] = h;
+        cprev[row * U + unit] = cp;
+        hprev[row * U + unit] = hs[(size_t)b * HS + unit];
+      }
+    }
+    if (t + 1 < T) lstm_seq::grid_barrier(barrier, (unsigned int)(t + 1) * gridDim.x);
+  }
+}
+
 }  // namespace rtk

@@ -119,6 +119,10 @@ struct rt_learner {
   float* colsum_part = nullptr;
   float *hw_part = nullptr, *hw_partb = nullptr;  // small-head weight-gradient partials
   int hw_parts = 256;
+  unsigned int* grid_barrier = nullptr;
+  int lstm_persistent = 1;
+  int conv_implicit = 1;
+  int num_sms = 148;
   double* sumsq_part = nullptr;
   float* tau_stage = nullptr;  // device staging for injected taus (5 segments)
   unsigned long long rng_counter = 0;
@@ -385,9 +389,70 @@ int launch_im2col_f32(cudaStream_t st, const float* xin, float* col, int rc, con
   return RT_OK;
 }
 
+template <int BN, int IN_U8>
+int launch_conv_tc(const CUtensorMap* tb, const rttc::ConvArgs& a, cudaStream_t st) {
+  constexpr int STAGES = 4;
+  constexpr int SMEM = STAGES * (rttc::BLOCK_M * rttc::BLOCK_K * 4 + BN * rttc::BLOCK_K * 4) +
+                       (2 * STAGES + 1) * 8 + 16 + 1024;
+  auto kern = rttc::k_conv_tc<BN, IN_U8, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  dim3 grid(cdiv(a.N, BN), cdiv(a.M, rttc::BLOCK_M));
+  kern<<<grid, rttc::NUM_THREADS, SMEM, st>>>(*tb, a);
+  RT_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+// Implicit-GEMM forward convolution (no im2col buffer) when the layer shape allows it.
+bool conv_tc_eligible(const rt_learner* h, size_t i, const void* xin) {
+  const ConvL& L = h->conv[i];
+  if (h->gx.mode != 1 || !h->conv_implicit) return false;
+  if (L.K % 32 || L.f % 4 || L.f > 128) return false;
+  if (i == 0) return L.k % 4 == 0 && L.s % 4 == 0 && L.win % 4 == 0 && ((uintptr_t)xin & 3) == 0 &&
+                     (L.cin * L.hin * L.win) % 4 == 0;
+  return L.cin % 32 == 0 && ((uintptr_t)xin & 15) == 0;
+}
+
+int conv_forward_tc(rt_learner* h, cudaStream_t st, const float* net, size_t i, const void* xin,
+                    float* out, int rows) {
+  const ConvL& L = h->conv[i];
+  rttc::ConvArgs a;
+  a.in = xin; a.out = out; a.bias = net + L.b; a.rows = rows;
+  a.C = L.cin; a.H = L.hin; a.W = L.win; a.KH = L.k; a.S = L.s; a.OH = L.hout; a.OW = L.wout;
+  a.M = rows * L.hout * L.wout; a.N = L.f; a.K = L.K;
+  a.scale = (float)(1.0 / 255.0);
+  a.round_tf32 = h->gx.round_tf32;
+  const int BN = L.f <= 32 ? 32 : (L.f <= 64 ? 64 : 128);
+  const CUtensorMap* tb = nullptr;
+  RT_TRY(get_tmap(h->gx, net + L.w, L.K, L.f, L.K, rttc::BLOCK_K, BN, 0, &tb));
+  h->gx.tc_launches++;
+  if (i == 0) {
+    if (BN == 32) return launch_conv_tc<32, 1>(tb, a, st);
+    if (BN == 64) return launch_conv_tc<64, 1>(tb, a, st);
+    return launch_conv_tc<128, 1>(tb, a, st);
+  }
+  if (BN == 32) return launch_conv_tc<32, 0>(tb, a, st);
+  if (BN == 64) return launch_conv_tc<64, 0>(tb, a, st);
+  return launch_conv_tc<128, 0>(tb, a, st);
+}
+
 // CNN forward for `rows` frames, chunked so the im2col buffers stay L2-resident.
 int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows) {
   const float scale = (float)(1.0 / 255.0);
+  {
+    bool all = true;
+    for (size_t i = 0; i < h->conv.size(); ++i)
+      all = all && conv_tc_eligible(h, i, i == 0 ? (const void*)x : (const void*)h->c_out[i - 1]);
+    if (all) {
+      for (size_t i = 0; i < h->conv.size(); ++i)
+        RT_TRY(conv_forward_tc(h, st, net, i, i == 0 ? (const void*)x : (const void*)h->c_out[i - 1],
+                               h->c_out[i], rows));
+      return RT_OK;
+    }
+  }
   for (int r0 = 0; r0 < rows; r0 += h->chunk_rows) {
     int rc = rows - r0 < h->chunk_rows ? rows - r0 : h->chunk_rows;
     for (size_t i = 0; i < h->conv.size(); ++i) {
@@ -422,6 +487,26 @@ int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* 
   g.bias2 = net + h->o_bhh;
   RT_TRY(gemm(h->gx, st, g));
   int nb = cdiv((size_t)Beff * U, 256);
+  // whole recurrence in one persistent launch when it fits (see rtk::k_lstm_seq_fwd)
+  {
+    const int ctas = U / rtk::lstm_seq::UPB;
+    size_t smem = ((size_t)4 * rtk::lstm_seq::UPB * U + (size_t)Beff * (U + rtk::lstm_seq::HPAD)) * sizeof(float);
+    if (h->lstm_persistent && timesteps > 1 && U % 4 == 0 && Beff <= 64 && ctas <= h->num_sms &&
+        smem <= 200 * 1024) {
+      auto kern = Beff <= 32 ? rtk::k_lstm_seq_fwd<1> : rtk::k_lstm_seq_fwd<2>;
+      RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      RT_CUDA(cudaMemsetAsync(h->grid_barrier, 0, sizeof(unsigned int), st));
+      const float* whh = net + h->o_whh;
+      void* args[] = {(void*)&h->xg, (void*)&whh, (void*)&hx, (void*)&cx, (void*)&initials,
+                      (void*)&h->gates, (void*)&h->c_all, (void*)&h->h_all, (void*)&h->hprev,
+                      (void*)&h->cprev, (void*)&timesteps, (void*)&Beff, (void*)&U,
+                      (void*)&h->grid_barrier};
+      // cooperative launch: the runtime guarantees all CTAs are co-resident (grid barrier)
+      RT_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(128), args, smem, st));
+      rt::launch_counter()++;
+      return RT_OK;
+    }
+  }
   rtk::k_lstm_init<<<nb, 256, 0, st>>>(hx, cx, initials, h->hprev, h->cprev, Beff, U);
   RT_LAUNCH_CHECK();
   for (int t = 0; t < timesteps; ++t) {
@@ -814,6 +899,16 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->colsum_part, 2048 * maxN));
   RT_TRY(dalloc(h, &h->sumsq_part, 1024));
   RT_REQUIRE(h->A <= 32, "num_actions > 32 not supported by the fused head kernels");
+  RT_TRY(dalloc(h, &h->grid_barrier, 4));
+  {
+    cudaDeviceProp prop;
+    RT_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    const char* e = getenv("RT_LSTM_STEPWISE");
+    if (e && e[0] == '1') h->lstm_persistent = 0;
+    e = getenv("RT_CONV_IM2COL");
+    if (e && e[0] == '1') h->conv_implicit = 0;
+  }
   RT_TRY(dalloc(h, &h->hw_part, (size_t)h->hw_parts * (A + 1) * F));
   RT_TRY(dalloc(h, &h->hw_partb, (size_t)h->hw_parts * (A + 1)));
   *out = h;

@@ -16,3 +16,8 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k
   --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --size 65536 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log | cut -c1-400
 python scripts/summarize_launches.py gpurun_out/launches.csv | tee gpurun_out/launch_summary.txt | head -40
+echo "=== ncu full capture of the fc-size tcgen05 GEMM"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc -s 2 -c 2 -f -o gpurun_out/prof_gemm \
+  python bench.py --steps 1 --warmup 3 --size 65536 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log | cut -c1-200
+ncu -i gpurun_out/prof_gemm.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_pick.py | tee gpurun_out/prof_gemm_summary.txt

@@ -145,7 +145,7 @@ def test_learner_full_size_vs_oracle():
             report_diff(errs, "grad/" + k, grads[k].numpy() / scale, gw / scale, 0, 2e-3)
         after = L.state_dict(0)
         for k in after:
-            report_diff(errs, "after/" + k, after[k].numpy(), p_ref[k].numpy(), 1e-4, 2e-5)
+            report_diff(errs, "after/" + k, after[k].numpy(), p_ref[k].numpy(), 1e-4, 1e-4)  # Adam step ~ lr*g/(|g|+eps): sensitive where |g| ~ eps
         print("full-size: qloss %.6f (oracle %.6f) td_mean %.6f grad_norm %.5f (oracle %.5f)" % (
             stt["qloss"], float(res["loss"]), stt["td_mean"], stt["grad_norm"], res["grad_norm"]))
         assert not errs, "\n".join(errs)
