@@ -234,6 +234,11 @@ int rt_learner_read_stats(rt_learner* h, float* loss, float* td_mean, float* gra
 int rt_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB,
                  const float* A, const float* B, const float* bias, int32_t relu, float* C,
                  int32_t device);
+/* Measurement hook: average device time (CUDA events) of `iters` back-to-back launches of one
+ * GEMM shape; force_bn / force_stages (0 = heuristic) select the tcgen05 tile configuration. */
+int rt_gemm_bench(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB,
+                  int32_t force_bn, int32_t force_stages, int32_t iters, double* avg_us,
+                  int32_t device);
 /* Test hook: named intermediate activations / gradients of the last step. */
 int rt_learner_debug_tensor(rt_learner* h, const char* name, void** dev_ptr, int64_t* count);
 

@@ -388,11 +388,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvA
         base[i] = -1;
       }
     }
-    for (int kb = 0; kb < num_kb; ++kb) {
-      int s = kb % STAGES;
-      uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      uint8_t* sa = smem + s * STAGE_BYTES;
+    auto gather = [&](int kb, float4* v) {
       long long koff;
       if (IN_U8) {
         int k = kb * BLOCK_K + 4 * j;
@@ -404,7 +400,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvA
         int kw = tap % a.KH, kh = tap / a.KH;
         koff = ((long long)kh * a.W + kw) * a.C + c0 + 4 * j;
       }
-      float4 v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (base[i] < 0) {
@@ -417,13 +412,25 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvA
           v[i] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(a.in) + base[i] + koff));
         }
       }
+    };
+    // software pipeline: the loads of k-block kb+1 are in flight while kb waits for its stage
+    float4 cur[8], nxt[8];
+    gather(0, cur);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      if (kb + 1 < num_kb) gather(kb + 1, nxt);
+      int s = kb % STAGES;
+      uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* sa = smem + s * STAGE_BYTES;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         int r = i * 16 + (t >> 3);
-        *reinterpret_cast<float4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = v[i];
+        *reinterpret_cast<float4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = cur[i];
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
     }
     // ---------------- epilogue (same warps: TMEM lane quarter == warp)
     mbar_wait(tmem_full, 0);

@@ -753,13 +753,40 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
   for (int t = 0; t < T; ++t) {
     const float* hsrc = t == 0 ? hx : h_all + (size_t)(t - 1) * B * U;
     const float* ini = initials + (size_t)t * B;
-    // stage masked h_{t-1}
-    for (int i = threadIdx.x; i < B * (U / 4); i += blockDim.x) {
-      int b = i / (U / 4), k4 = i - b * (U / 4);
-      float keep = 1.f - ini[b];
-      float4 v = __ldcg(reinterpret_cast<const float4*>(hsrc + (size_t)b * U) + k4);  // L2, never stale L1
-      v.x *= keep; v.y *= keep; v.z *= keep; v.w *= keep;
-      *reinterpret_cast<float4*>(hs + (size_t)b * HS + 4 * k4) = v;
+    // prefetch this step's input-projection terms (independent of h) before anything waits
+    float xin[BCH][4];
+#pragma unroll
+    for (int j = 0; j < BCH; ++j) {
+      int b = lane + 32 * j;
+      if (b < B) {
+        const float* xr = xg + ((size_t)t * B + b) * 4 * U + unit;
+        xin[j][0] = __ldg(xr); xin[j][1] = __ldg(xr + U); xin[j][2] = __ldg(xr + 2 * U); xin[j][3] = __ldg(xr + 3 * U);
+      }
+    }
+    // stage masked h_{t-1}: 8 independent 16-byte loads in flight per thread
+    {
+      const int total = B * (U / 4);
+      for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          int i = i0 + q * blockDim.x;
+          if (i < total) {
+            int b = i / (U / 4), k4 = i - b * (U / 4);
+            v[q] = __ldcg(reinterpret_cast<const float4*>(hsrc + (size_t)b * U) + k4);  // L2: never a stale L1 line
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          int i = i0 + q * blockDim.x;
+          if (i < total) {
+            int b = i / (U / 4), k4 = i - b * (U / 4);
+            float keep = 1.f - ini[b];
+            v[q].x *= keep; v[q].y *= keep; v[q].z *= keep; v[q].w *= keep;
+            *reinterpret_cast<float4*>(hs + (size_t)b * HS + 4 * k4) = v[q];
+          }
+        }
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -785,11 +812,10 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
           a3 = fmaf(h4.x, p.x, a3); a3 = fmaf(h4.y, p.y, a3); a3 = fmaf(h4.z, p.z, a3); a3 = fmaf(h4.w, p.w, a3);
         }
         size_t row = (size_t)t * B + b;
-        const float* xr = xg + row * 4 * U + unit;
-        float gi = sigmoidf_(xr[0] + a0);
-        float gf = sigmoidf_(xr[U] + a1);
-        float gg = tanhf(xr[2 * U] + a2);
-        float go = sigmoidf_(xr[3 * U] + a3);
+        float gi = sigmoidf_(xin[j][0] + a0);
+        float gf = sigmoidf_(xin[j][1] + a1);
+        float gg = tanhf(xin[j][2] + a2);
+        float go = sigmoidf_(xin[j][3] + a3);
         float keep = 1.f - ini[b];
         float cp = c_reg[j] * keep;
         float c = gf * cp + gi * gg;

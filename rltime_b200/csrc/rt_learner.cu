@@ -50,6 +50,7 @@ struct GemmCtx {
   PFN_tmapEncodeTiled encode = nullptr;
   std::map<TmapKey, CUtensorMap> tmaps;
   long long tc_launches = 0, simt_launches = 0;
+  int force_bn = 0, force_stages = 0;   // tuning overrides (RT_TC_BN / RT_TC_STAGES, rt_gemm_bench)
 };
 
 struct ConvL {
@@ -246,9 +247,8 @@ int get_tmap(GemmCtx& cx, const float* ptr, uint64_t d0, uint64_t d1, uint64_t p
   return RT_OK;
 }
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int STAGES>
 int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs& a, dim3 grid, cudaStream_t st) {
-  constexpr int STAGES = BN == 128 ? 3 : 4;
   using L = rttc::SmemLayout<BN, A_MN, B_MN, STAGES>;
   auto kern = rttc::k_gemm_tc<BN, A_MN, B_MN, STAGES>;
   static bool configured = false;
@@ -259,6 +259,15 @@ int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs& 
   kern<<<grid, rttc::NUM_THREADS, L::TOTAL, st>>>(*ta, *tb, a);
   RT_LAUNCH_CHECK();
   return RT_OK;
+}
+
+template <int BN, int A_MN, int B_MN>
+int launch_tc_stages(int stages, const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs& a, dim3 grid,
+                     cudaStream_t st) {
+  constexpr int STAGE_BYTES = rttc::BLOCK_M * rttc::BLOCK_K * 4 + BN * rttc::BLOCK_K * 4;
+  if (stages >= 6 && 6 * STAGE_BYTES <= 200 * 1024) return launch_tc<BN, A_MN, B_MN, 6>(ta, tb, a, grid, st);
+  if (stages >= 4 && 4 * STAGE_BYTES <= 200 * 1024) return launch_tc<BN, A_MN, B_MN, 4>(ta, tb, a, grid, st);
+  return launch_tc<BN, A_MN, B_MN, 3>(ta, tb, a, grid, st);
 }
 
 bool tc_eligible(const rtk::GemmArgs& g) {
@@ -277,6 +286,9 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   int tm = cdiv(g.M, rttc::BLOCK_M);
   // few row tiles (e.g. the recurrent step, M = B): narrower N tiles put more SMs to work
   while (BN > 32 && (long long)tm * cdiv(g.N, BN) < 74) BN >>= 1;
+  int stages = BN == 128 ? 3 : 4;
+  if (cx.force_bn) BN = cx.force_bn;
+  if (cx.force_stages) stages = cx.force_stages;
   int tn = cdiv(g.N, BN);
   long long tiles = (long long)tm * tn;
   int num_kb = cdiv(g.K, rttc::BLOCK_K);
@@ -306,10 +318,10 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   dim3 grid(tn, tm, splits);
   int rc;
 #define RT_TC_CASE(bn, am, bm) \
-  if (BN == bn && A_MN == am && B_MN == bm) rc = launch_tc<bn, am, bm>(ta, tb, a, grid, st); else
-  RT_TC_CASE(32, 0, 0) RT_TC_CASE(64, 0, 0) RT_TC_CASE(128, 0, 0)
-  RT_TC_CASE(32, 0, 1) RT_TC_CASE(64, 0, 1) RT_TC_CASE(128, 0, 1)
-  RT_TC_CASE(32, 1, 1) RT_TC_CASE(64, 1, 1) RT_TC_CASE(128, 1, 1)
+  if (BN == bn && A_MN == am && B_MN == bm) rc = launch_tc_stages<bn, am, bm>(stages, ta, tb, a, grid, st); else
+  RT_TC_CASE(32, 0, 0) RT_TC_CASE(64, 0, 0) RT_TC_CASE(128, 0, 0) RT_TC_CASE(256, 0, 0)
+  RT_TC_CASE(32, 0, 1) RT_TC_CASE(64, 0, 1) RT_TC_CASE(128, 0, 1) RT_TC_CASE(256, 0, 1)
+  RT_TC_CASE(32, 1, 1) RT_TC_CASE(64, 1, 1) RT_TC_CASE(128, 1, 1) RT_TC_CASE(256, 1, 1)
   rc = rt::fail(RT_ERR_INVALID, "no tcgen05 GEMM instantiation for BN=%d A_MN=%d B_MN=%d", BN, A_MN, B_MN);
 #undef RT_TC_CASE
   if (rc != RT_OK) return rc;
@@ -890,6 +902,8 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   h->gx.ws_floats = (size_t)64 << 20;  // 256 MiB split-K workspace
   RT_TRY(dalloc(h, &h->gx.ws, h->gx.ws_floats));
   h->gx.mode = td->gemm_mode;
+  if (const char* e = getenv("RT_TC_BN")) h->gx.force_bn = atoi(e);
+  if (const char* e = getenv("RT_TC_STAGES")) h->gx.force_stages = atoi(e);
   size_t maxN = 4 * (size_t)(h->U ? h->U : 1);
   if (D > maxN) maxN = D;
   if (F > maxN) maxN = F;
@@ -1181,5 +1195,45 @@ extern "C" int rt_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, int32
   if (rc == RT_OK) RT_CUDA(cudaMemcpy(C, dC, nC * sizeof(float), cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(cx.ws);
   if (dbias) cudaFree(dbias);
+  return rc;
+}
+
+
+extern "C" int rt_gemm_bench(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t transA,
+                             int32_t transB, int32_t force_bn, int32_t force_stages, int32_t iters,
+                             double* avg_us, int32_t device) {
+  RT_REQUIRE(avg_us && M > 0 && N > 0 && K > 0 && iters > 0, "bad argument");
+  RT_CUDA(cudaSetDevice(device));
+  GemmCtx cx;
+  cx.mode = mode;
+  cx.force_bn = force_bn;
+  cx.force_stages = force_stages;
+  cx.ws_floats = (size_t)64 << 20;
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  size_t nA = (size_t)M * K, nB = (size_t)N * K, nC = (size_t)M * N;
+  RT_CUDA(cudaMalloc(&cx.ws, cx.ws_floats * sizeof(float)));
+  RT_CUDA(cudaMalloc(&dA, nA * sizeof(float)));
+  RT_CUDA(cudaMalloc(&dB, nB * sizeof(float)));
+  RT_CUDA(cudaMalloc(&dC, nC * sizeof(float)));
+  RT_CUDA(cudaMemset(dA, 0, nA * sizeof(float)));
+  RT_CUDA(cudaMemset(dB, 0, nB * sizeof(float)));
+  rtk::GemmArgs g = mk(dA, transA ? M : K, transA, dB, transB ? K : N, transB, dC, N, M, N, K);
+  cudaEvent_t e0, e1;
+  RT_CUDA(cudaEventCreate(&e0));
+  RT_CUDA(cudaEventCreate(&e1));
+  int rc = RT_OK;
+  for (int i = 0; i < 3 && rc == RT_OK; ++i) rc = gemm(cx, 0, g);
+  RT_CUDA(cudaEventRecord(e0, 0));
+  for (int i = 0; i < iters && rc == RT_OK; ++i) rc = gemm(cx, 0, g);
+  RT_CUDA(cudaEventRecord(e1, 0));
+  cudaError_t e = cudaDeviceSynchronize();
+  if (rc == RT_OK && e != cudaSuccess) rc = rt::fail(RT_ERR_CUDA, "gemm bench failed: %s", cudaGetErrorString(e));
+  float ms = 0;
+  if (rc == RT_OK) {
+    cudaEventElapsedTime(&ms, e0, e1);
+    *avg_us = 1e3 * ms / iters;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(cx.ws);
   return rc;
 }
