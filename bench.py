@@ -140,10 +140,15 @@ def build_device_workload(cfg, device, seed, rank):
     return hist, learner, fill_s
 
 
-def one_update(hist, learner, B):
+def one_update(hist, learner, B, world=1):
+    from rltime_b200 import parallel
     td = hist.get_train_data(B, 0.0)
     assert td is not None
-    learner.step(hist.last_batch)
+    if world > 1:
+        # local gradients -> NCCL sum over NVLink -> identical clip + Adam on every rank
+        parallel.data_parallel_step(learner, hist.last_batch, world)
+    else:
+        learner.step(hist.last_batch)
     hist.update_losses_device(learner.td_abs())
 
 
@@ -155,8 +160,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+        from rltime_b200 import parallel
+        parallel.init_process_group("nccl")
     cfg = dict(CFG)
     if args.size:
         cfg["size"] = args.size
@@ -173,8 +178,11 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    if world > 1:
+        from rltime_b200 import parallel
+        parallel.broadcast_params_(learner)
     for _ in range(max(args.warmup, 3)):
-        one_update(hist, learner, B)
+        one_update(hist, learner, B, world)
     barrier()
     hist.profile_gather(True)
     launches0 = lib.rt_launch_count()
@@ -182,7 +190,7 @@ def run_gpu(args):
     with ClockSampler(local) as clk:
         ev0.record()
         for _ in range(args.steps):
-            one_update(hist, learner, B)
+            one_update(hist, learner, B, world)
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
@@ -226,7 +234,7 @@ def run_gpu(args):
         hist.update_arrays(env_ids, reward, done,
                            [h_frames.numpy(), h_hx.numpy(), h_cx.numpy(), h_init.numpy()],
                            [h_act.numpy(), h_qv.numpy()])
-        one_update(hist, learner, B)
+        one_update(hist, learner, B, world)
         return learner.stats()["qloss"]
     for _ in range(3):
         e2e_update()
@@ -257,7 +265,9 @@ def run_gpu(args):
         "data": "synthetic",
         "config": {"workload": "atari_iqn_lstm seq-PER: N=%d T=20 n=2 B=32 Nq=32 A=6 "
                                "nature-CNN-LSTM512-FC512 dueling double-Q" % cfg["size"],
-                   "gemm": cfg["gemm"], "replay_per_gpu": cfg["size"], "l2": "inputs (28 GB frame store) exceed L2; "
+                   "gemm": cfg["gemm"], "replay_per_gpu": cfg["size"],
+                   "global_batch": "%d sequences x 20 steps" % (B * world),
+                   "parallelism": "dp%d: replay sharded by env, NCCL all-reduce of the flat gradient" % world, "l2": "inputs (28 GB frame store) exceed L2; "
                    "every draw gathers different rows", "fill_s": round(fill_s, 1)},
         "e2e": {"value": world * args.steps / e2e_s, "unit": "updates/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},

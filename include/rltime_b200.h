@@ -224,6 +224,14 @@ int rt_learner_set_lr(rt_learner* h, double lr);
  * forward) replacing the reference's torch.rand draws (policies/torch/iqn.py:88). */
 int rt_learner_step(rt_learner* h, const rt_batch* batch, const rt_learner_io* io,
                     const float* const* taus_host, void* stream);
+/* Data-parallel split of rt_learner_step: everything up to and including the backward pass,
+ * then (after the caller has all-reduced the flat gradient buffer, e.g. NCCL sum over NVLink)
+ * grad-norm / clip / Adam with the gradient scaled by grad_scale (= 1/world_size). */
+int rt_learner_compute_grads(rt_learner* h, const rt_batch* batch, const rt_learner_io* io,
+                             const float* const* taus_host, void* stream);
+int rt_learner_apply_grads(rt_learner* h, double grad_scale, void* stream);
+/* Flat fp32 buffers (RT_BUF_*): all tensors of one kind back to back, 256-byte aligned. */
+int rt_learner_flat_buffer(rt_learner* h, int32_t which, float** dev_ptr, int64_t* count);
 /* Device pointer to the T*B reported |td| means (torch/iqn.py:112) of the last step. */
 int rt_learner_td_abs(rt_learner* h, float** out_device);
 /* qloss, td_mean, grad_norm of the last step (torch/iqn.py:127-129, torch_trainer.py:187-190);

@@ -105,12 +105,105 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+
+// Epilogue operands shared by the GEMM and implicit-conv kernels.
+struct EpiArgs {
+  float* C;            // output rows (or split-K partial slab), row pitch ldc floats
+  int ldc;
+  int M, N;
+  float alpha;
+  const float* bias;
+  const float* bias2;
+  int relu;
+  const float* mask;
+  int ldmask;
+  int accumulate;
+  int round_tf32;
+  int raw;             // 1: store the raw accumulator (split-K partial), no epilogue ops
+};
+
+// One warp moves its 32-row x 32-column accumulator chunk (lane = row, straight out of
+// tcgen05.ld) to global memory through a padded shared-memory transpose, so that every store
+// instruction writes four complete 128-byte row segments instead of 32 scattered 16-byte
+// pieces (the scattered form capped a 42 MB output at ~1.7 TB/s).  `stage` = this warp's
+// private 32 x 36 float scratch.
+__device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const uint32_t* v, float* stage, int lane,
+                                               int row0, int nb) {
+  // lane-major -> smem (16-byte stores, conflict-free at pitch 36)
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(stage + lane * 36 + 4 * q) =
+        make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                    __uint_as_float(v[4 * q + 3]));
+  __syncwarp();
+  const int cg = lane & 7;          // 4-column group inside the chunk
+  const int n = nb + 4 * cg;
+  const bool vec = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) && (n + 4 <= e.N) &&
+                   (e.raw || ((!e.mask || (((e.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.mask) & 15) == 0))) &&
+                              (!e.bias || ((reinterpret_cast<uintptr_t>(e.bias) & 15) == 0)) &&
+                              (!e.bias2 || ((reinterpret_cast<uintptr_t>(e.bias2) & 15) == 0))));
+  float b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (!e.raw) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (n + k < e.N) {
+        if (e.bias) b[k] += __ldg(e.bias + n + k);
+        if (e.bias2) b[k] += __ldg(e.bias2 + n + k);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    const int m = row0 + r;
+    float4 t4 = *reinterpret_cast<const float4*>(stage + r * 36 + 4 * cg);
+    if (m >= e.M || n >= e.N) continue;
+    float x[4] = {t4.x, t4.y, t4.z, t4.w};
+    float* dst = e.C + (size_t)m * e.ldc + n;
+    if (!e.raw) {
+      float mk[4] = {1.f, 1.f, 1.f, 1.f}, old[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec) {
+        if (e.mask) { float4 t = *reinterpret_cast<const float4*>(e.mask + (size_t)m * e.ldmask + n); mk[0] = t.x; mk[1] = t.y; mk[2] = t.z; mk[3] = t.w; }
+        if (e.accumulate) { float4 t = *reinterpret_cast<const float4*>(dst); old[0] = t.x; old[1] = t.y; old[2] = t.z; old[3] = t.w; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (n + k < e.N) {
+            if (e.mask) mk[k] = e.mask[(size_t)m * e.ldmask + n + k];
+            if (e.accumulate) old[k] = dst[k];
+          }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float y = x[k] * e.alpha + b[k];
+        if (e.relu) y = fmaxf(y, 0.f);
+        if (e.mask) y = mk[k] > 0.f ? y : 0.f;
+        y += old[k];
+        if (e.round_tf32) {
+          uint32_t tt;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tt) : "f"(y));
+          y = __uint_as_float(tt);
+        }
+        x[k] = y;
+      }
+    }
+    if (vec) {
+      *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (n + k < e.N) dst[k] = x[k];
+    }
+  }
+  __syncwarp();
+}
+
 // Extra epilogue switch on top of rtk::GemmArgs
 struct TcArgs {
   rtk::GemmArgs g;
   int num_kb_total;   // ceil(K / BLOCK_K)
   int kb_per_split;
   int round_tf32;     // round outputs to TF32 (RN) so the consumer GEMM multiplies exact values
+  long long* dbg;     // optional clock64 phase stamps of CTA (0,0,0) (tuning aid)
 };
 
 template <int BN, int A_MN, int B_MN, int STAGES>
@@ -161,6 +254,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const bool dbg_cta = a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (dbg_cta && threadIdx.x == 0) a.dbg[0] = clock64();   // setup done
 
   if (warp == 0) {
     if (lane == 0) {
@@ -201,6 +296,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         int s = i % STAGES;
         uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
+        if (dbg_cta && i == 0) a.dbg[1] = clock64();           // first operands landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
         uint32_t sb = sa + L::A_BYTES;
@@ -218,88 +314,30 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         umma_commit(&empty_bar[s]);   // frees the smem stage once these MMAs retire
       }
       umma_commit(tmem_full);         // accumulator complete
+      if (dbg_cta) a.dbg[2] = clock64();                        // all MMAs issued
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     mbar_wait(tmem_full, 0);
+    if (dbg_cta && threadIdx.x == 64) a.dbg[3] = clock64();     // accumulator ready
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + q * 32 + lane;
+    // all MMAs have retired, so the pipeline stages are free: reuse them as transpose scratch
+    float* stage = reinterpret_cast<float*>(smem) + q * (32 * 36);
+    EpiArgs e;
     const bool split = gridDim.z > 1;
-    // 16-byte vector path: every pointer touched per row is 16 B aligned and the chunk is full
-    const bool vec_ok = split ? ((g.N & 3) == 0)
-                              : (((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
-                                 (!g.mask || (((g.ldmask & 3) == 0) &&
-                                              ((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0))) &&
-                                 (!g.bias || ((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0)) &&
-                                 (!g.bias2 || ((reinterpret_cast<uintptr_t>(g.bias2) & 15) == 0)));
+    e.C = split ? g.ws + (size_t)blockIdx.z * g.M * g.N : g.C;
+    e.ldc = split ? g.N : g.ldc;
+    e.M = g.M; e.N = g.N; e.alpha = g.alpha; e.bias = g.bias; e.bias2 = g.bias2; e.relu = g.relu;
+    e.mask = g.mask; e.ldmask = g.ldmask; e.accumulate = g.accumulate; e.round_tf32 = a.round_tf32;
+    e.raw = split ? 1 : 0;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      if (m >= g.M) continue;
-      const int nb = n0 + c * 32;
-      if (nb >= g.N) continue;
-      if (vec_ok && nb + 32 <= g.N) {
-        if (split) {
-          float4* dst = reinterpret_cast<float4*>(g.ws + ((size_t)blockIdx.z * g.M + m) * g.N + nb);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        } else {
-          float4* dst = reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + nb);
-          const float4* msk = g.mask ? reinterpret_cast<const float4*>(g.mask + (size_t)m * g.ldmask + nb) : nullptr;
-          const float4* b1 = g.bias ? reinterpret_cast<const float4*>(g.bias + nb) : nullptr;
-          const float4* b2 = g.bias2 ? reinterpret_cast<const float4*>(g.bias2 + nb) : nullptr;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float r[4] = {__uint_as_float(v[4 * j]) * g.alpha, __uint_as_float(v[4 * j + 1]) * g.alpha,
-                          __uint_as_float(v[4 * j + 2]) * g.alpha, __uint_as_float(v[4 * j + 3]) * g.alpha};
-            if (b1) { float4 t = __ldg(b1 + j); r[0] += t.x; r[1] += t.y; r[2] += t.z; r[3] += t.w; }
-            if (b2) { float4 t = __ldg(b2 + j); r[0] += t.x; r[1] += t.y; r[2] += t.z; r[3] += t.w; }
-            if (g.relu) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) r[e] = fmaxf(r[e], 0.f);
-            }
-            if (msk) {
-              float4 t = msk[j];
-              r[0] = t.x > 0.f ? r[0] : 0.f; r[1] = t.y > 0.f ? r[1] : 0.f;
-              r[2] = t.z > 0.f ? r[2] : 0.f; r[3] = t.w > 0.f ? r[3] : 0.f;
-            }
-            if (g.accumulate) { float4 t = dst[j]; r[0] += t.x; r[1] += t.y; r[2] += t.z; r[3] += t.w; }
-            if (a.round_tf32) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                uint32_t t;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r[e]));
-                r[e] = __uint_as_float(t);
-              }
-            }
-            dst[j] = make_float4(r[0], r[1], r[2], r[3]);
-          }
-        }
-      } else if (split) {
-        float* dst = g.ws + ((size_t)blockIdx.z * g.M + m) * g.N + nb;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nb + j < g.N) dst[j] = __uint_as_float(v[j]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          int n = nb + j;
-          if (n < g.N) {
-            float r = rtk::gemm_epilogue(g, m, n, __uint_as_float(v[j]));
-            if (a.round_tf32) {
-              uint32_t t;
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
-              r = __uint_as_float(t);
-            }
-            g.C[(size_t)m * g.ldc + n] = r;
-          }
-        }
-      }
+      if (n0 + c * 32 < g.N) epilogue_chunk(e, v, stage, lane, m0 + q * 32, n0 + c * 32);
     }
+    if (dbg_cta && threadIdx.x == 64) a.dbg[4] = clock64();     // epilogue done
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -435,35 +473,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvA
     // ---------------- epilogue (same warps: TMEM lane quarter == warp)
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + warp * 32 + lane;
+    float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);
+    EpiArgs e;
+    e.C = a.out; e.ldc = a.N; e.M = a.M; e.N = a.N; e.alpha = 1.f; e.bias = a.bias; e.bias2 = nullptr;
+    e.relu = 1; e.mask = nullptr; e.ldmask = 0; e.accumulate = 0; e.round_tf32 = a.round_tf32; e.raw = 0;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-      if (m >= a.M) continue;
-      const int nb = n0 + c * 32;
-      if (nb + 32 <= a.N && (a.N & 3) == 0) {
-        float4* dst = reinterpret_cast<float4*>(a.out + (size_t)m * a.N + nb);
-        const float4* b1 = reinterpret_cast<const float4*>(a.bias + nb);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 bb = __ldg(b1 + q);
-          float r[4] = {fmaxf(__uint_as_float(v[4 * q]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * q + 1]) + bb.y, 0.f),
-                        fmaxf(__uint_as_float(v[4 * q + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * q + 3]) + bb.w, 0.f)};
-          if (a.round_tf32) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              uint32_t tt;
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tt) : "f"(r[e]));
-              r[e] = __uint_as_float(tt);
-            }
-          }
-          dst[q] = make_float4(r[0], r[1], r[2], r[3]);
-        }
-      } else {
-        for (int q = 0; q < 32; ++q)
-          if (nb + q < a.N) a.out[(size_t)m * a.N + nb + q] = fmaxf(__uint_as_float(v[q]) + a.bias[nb + q], 0.f);
-      }
+      if (n0 + c * 32 < a.N) epilogue_chunk(e, v, stage, lane, m0 + warp * 32, n0 + c * 32);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else if (warp == 4) {

@@ -661,11 +661,11 @@ __global__ void k_sumsq_partial(const float* __restrict__ g, double* __restrict_
 // stage 2: norm, clip coefficient (torch.nn.utils.clip_grad_norm_: coef = min(1, c/(norm+1e-6)))
 // stats[2] = grad_norm, stats[3] = clip coefficient applied
 __global__ void k_gradnorm_final(const double* __restrict__ part, int parts, float* __restrict__ stats,
-                                 float clip) {
+                                 float clip, float grad_scale) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < parts; ++i) t += part[i];
-    float norm = (float)sqrt(t);
+    float norm = (float)sqrt(t) * grad_scale;
     stats[2] = norm;
     float coef = 1.f;
     if (clip > 0.f) {
@@ -679,8 +679,8 @@ __global__ void k_gradnorm_final(const double* __restrict__ part, int parts, flo
 // parameter / gradient / moment buffers: 16 B read + 12 B written per parameter.
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                        float* __restrict__ v, size_t n, const float* __restrict__ stats, float lr,
-                       float b1, float b2, float eps, float bc1, float bc2_sqrt) {
-  float coef = stats[3];
+                       float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+  float coef = stats[3] * grad_scale;
   float step_size = lr / bc1;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -729,7 +729,7 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
                const float* __restrict__ cx, const float* __restrict__ initials,
                float* __restrict__ gates, float* __restrict__ c_all, float* __restrict__ h_all,
                float* __restrict__ hprev, float* __restrict__ cprev, int T, int B, int U,
-               unsigned int* __restrict__ barrier) {
+               unsigned int* __restrict__ barrier, long long* __restrict__ dbg) {
   using namespace lstm_seq;
   extern __shared__ float sm[];
   float* Ws = sm;                          // [4 gates][UPB][U]
@@ -789,6 +789,7 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
       }
     }
     __syncthreads();
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4 * t + 0] = clock64();
 #pragma unroll
     for (int j = 0; j < BCH; ++j) {
       int b = lane + 32 * j;
@@ -829,7 +830,9 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
         hprev[row * U + unit] = hs[(size_t)b * HS + unit];
       }
     }
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4 * t + 1] = clock64();
     if (t + 1 < T) lstm_seq::grid_barrier(barrier, (unsigned int)(t + 1) * gridDim.x);
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4 * t + 2] = clock64();
   }
 }
 

@@ -51,6 +51,7 @@ struct GemmCtx {
   std::map<TmapKey, CUtensorMap> tmaps;
   long long tc_launches = 0, simt_launches = 0;
   int force_bn = 0, force_stages = 0;   // tuning overrides (RT_TC_BN / RT_TC_STAGES, rt_gemm_bench)
+  long long* dbg = nullptr;             // clock64 stamps of CTA 0 (rt_gemm_bench)
 };
 
 struct ConvL {
@@ -121,6 +122,7 @@ struct rt_learner {
   float *hw_part = nullptr, *hw_partb = nullptr;  // small-head weight-gradient partials
   int hw_parts = 256;
   unsigned int* grid_barrier = nullptr;
+  long long* lstm_dbg = nullptr;
   int lstm_persistent = 1;
   int conv_implicit = 1;
   int num_sms = 148;
@@ -315,6 +317,7 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   a.num_kb_total = num_kb;
   a.kb_per_split = kbps;
   a.round_tf32 = cx.round_tf32;
+  a.dbg = cx.dbg;
   dim3 grid(tn, tm, splits);
   int rc;
 #define RT_TC_CASE(bn, am, bm) \
@@ -512,7 +515,7 @@ int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* 
       void* args[] = {(void*)&h->xg, (void*)&whh, (void*)&hx, (void*)&cx, (void*)&initials,
                       (void*)&h->gates, (void*)&h->c_all, (void*)&h->h_all, (void*)&h->hprev,
                       (void*)&h->cprev, (void*)&timesteps, (void*)&Beff, (void*)&U,
-                      (void*)&h->grid_barrier};
+                      (void*)&h->grid_barrier, (void*)&h->lstm_dbg};
       // cooperative launch: the runtime guarantees all CTAs are co-resident (grid barrier)
       RT_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(128), args, smem, st));
       rt::launch_counter()++;
@@ -735,6 +738,27 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
   return RT_OK;
 }
 
+// grad-norm, clip, Adam (torch_trainer.py:177-199) on the flat buffers.  grad_scale folds the
+// 1/world_size of a data-parallel gradient mean into the same pass.
+int apply_grads(rt_learner* h, cudaStream_t st, float grad_scale) {
+
+    int parts = 512;
+    rtk::k_sumsq_partial<<<parts, 256, 0, st>>>(h->grad, h->sumsq_part, h->nparams);
+    RT_LAUNCH_CHECK();
+    rtk::k_gradnorm_final<<<1, 32, 0, st>>>(h->sumsq_part, parts, h->stats,
+                                           h->td.clip_grad > 0 ? (float)h->td.clip_grad : 0.f, grad_scale);
+    RT_LAUNCH_CHECK();
+    h->adam_t++;
+    double b1 = 0.9, b2 = 0.999;
+    float bc1 = (float)(1.0 - std::pow(b1, (double)h->adam_t));
+    float bc2s = (float)std::sqrt(1.0 - std::pow(b2, (double)h->adam_t));
+    rtk::k_adam<<<grid1d(h->nparams), 256, 0, st>>>(h->p[0], h->grad, h->adam_m, h->adam_v, h->nparams,
+                                                   h->stats, h->lr, (float)b1, (float)b2,
+                                                   (float)h->td.adam_epsilon, bc1, bc2s, grad_scale);
+    RT_LAUNCH_CHECK();
+    return RT_OK;
+}
+
 __global__ void k_uniform(float* out, size_t n, unsigned long long seed, unsigned long long ctr) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -914,6 +938,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->sumsq_part, 1024));
   RT_REQUIRE(h->A <= 32, "num_actions > 32 not supported by the fused head kernels");
   RT_TRY(dalloc(h, &h->grid_barrier, 4));
+  if (getenv("RT_DEBUG_TIMELINE")) RT_TRY(dalloc(h, &h->lstm_dbg, 4 * 256, "lstm_dbg"));
   {
     cudaDeviceProp prop;
     RT_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -1010,8 +1035,12 @@ int rt_learner_set_lr(rt_learner* h, double lr) {
   return RT_OK;
 }
 
-int rt_learner_step(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
-                    const float* const* taus_host, void* stream) {
+}  // extern "C"
+
+namespace {
+
+int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
+                      const float* const* taus_host, void* stream, bool apply) {
   RT_REQUIRE(h && b && io, "null argument");
   RT_REQUIRE(b->B == h->B && b->S == h->S && b->n == h->n,
              "batch geometry (B=%d,S=%d,n=%d) does not match the learner (B=%d,S=%d,n=%d)", b->B,
@@ -1112,23 +1141,36 @@ int rt_learner_step(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   }
   RT_TRY(cnn_backward(h, st, h->p[0], svt.x, M, dlast));
 
-  // ---- grad-norm, clip, Adam (torch_trainer.py:177-199)
-  {
-    int parts = 512;
-    rtk::k_sumsq_partial<<<parts, 256, 0, st>>>(h->grad, h->sumsq_part, h->nparams);
-    RT_LAUNCH_CHECK();
-    rtk::k_gradnorm_final<<<1, 32, 0, st>>>(h->sumsq_part, parts, h->stats,
-                                           h->td.clip_grad > 0 ? (float)h->td.clip_grad : 0.f);
-    RT_LAUNCH_CHECK();
-    h->adam_t++;
-    double b1 = 0.9, b2 = 0.999;
-    float bc1 = (float)(1.0 - std::pow(b1, (double)h->adam_t));
-    float bc2s = (float)std::sqrt(1.0 - std::pow(b2, (double)h->adam_t));
-    rtk::k_adam<<<grid1d(h->nparams), 256, 0, st>>>(h->p[0], h->grad, h->adam_m, h->adam_v, h->nparams,
-                                                   h->stats, h->lr, (float)b1, (float)b2,
-                                                   (float)h->td.adam_epsilon, bc1, bc2s);
-    RT_LAUNCH_CHECK();
-  }
+  if (!apply) return RT_OK;
+  return apply_grads(h, st, 1.0f);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_learner_step(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
+                    const float* const* taus_host, void* stream) {
+  return learner_step_impl(h, b, io, taus_host, stream, true);
+}
+
+int rt_learner_compute_grads(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
+                             const float* const* taus_host, void* stream) {
+  return learner_step_impl(h, b, io, taus_host, stream, false);
+}
+
+int rt_learner_apply_grads(rt_learner* h, double grad_scale, void* stream) {
+  RT_REQUIRE(h, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  return apply_grads(h, (cudaStream_t)stream, (float)grad_scale);
+}
+
+int rt_learner_flat_buffer(rt_learner* h, int32_t which, float** dev_ptr, int64_t* count) {
+  RT_REQUIRE(h && dev_ptr && count, "null argument");
+  float* p = which_buffer(h, which);
+  RT_REQUIRE(p, "bad buffer selector");
+  *dev_ptr = p;
+  *count = (int64_t)h->nparams;
   return RT_OK;
 }
 
@@ -1232,6 +1274,20 @@ extern "C" int rt_gemm_bench(int32_t mode, int32_t M, int32_t N, int32_t K, int3
   if (rc == RT_OK) {
     cudaEventElapsedTime(&ms, e0, e1);
     *avg_us = 1e3 * ms / iters;
+  }
+  if (rc == RT_OK && getenv("RT_DEBUG_TIMELINE") && mode == 1) {
+    long long* d = nullptr;
+    cudaMalloc(&d, 8 * sizeof(long long));
+    cudaMemset(d, 0, 8 * sizeof(long long));
+    cx.dbg = d;
+    rc = gemm(cx, 0, g);
+    long long hst[8] = {0};
+    cudaMemcpy(hst, d, sizeof(hst), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[timeline M=%d N=%d K=%d tA=%d tB=%d bn=%d st=%d] cycles since setup: first_full=%lld "
+                    "mma_issued=%lld acc_ready=%lld epilogue_done=%lld\n",
+            M, N, K, transA, transB, force_bn, force_stages, hst[1] - hst[0], hst[2] - hst[0], hst[3] - hst[0],
+            hst[4] - hst[0]);
+    cudaFree(d);
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(cx.ws);

@@ -127,19 +127,39 @@ class DeviceLearner:
     # ---- update -------------------------------------------------------------------
     def step(self, batch, taus=None, io=None):
         """batch: ctypes _lib.Batch (from a device history buffer or hand-built)."""
-        tp = None
-        keep = []
-        if taus is not None:
-            arr = (C.c_void_p * 3)()
-            for i, t in enumerate(taus):
-                a = np.ascontiguousarray(t.detach().cpu().numpy() if hasattr(t, "detach") else t,
-                                         dtype=np.float32)
-                assert a.size == self.T * self.B * self.Nq
-                keep.append(a)
-                arr[i] = a.ctypes.data
-            tp = C.cast(arr, C.c_void_p)
+        tp, keep = self._tau_ptrs(taus)
         _lib.check(self._lib.rt_learner_step(self._h, C.byref(batch), C.byref(io or self.io), tp,
                                              self._stream()))
+
+    def _tau_ptrs(self, taus):
+        if taus is None:
+            return None, []
+        keep = []
+        arr = (C.c_void_p * 3)()
+        for i, t in enumerate(taus):
+            a = np.ascontiguousarray(t.detach().cpu().numpy() if hasattr(t, "detach") else t,
+                                     dtype=np.float32)
+            assert a.size == self.T * self.B * self.Nq
+            keep.append(a)
+            arr[i] = a.ctypes.data
+        keep.append(arr)
+        return C.cast(arr, C.c_void_p), keep
+
+    def compute_grads(self, batch, taus=None, io=None):
+        """Data-parallel phase 1: everything of step() up to and including the backward pass."""
+        tp, keep = self._tau_ptrs(taus)
+        _lib.check(self._lib.rt_learner_compute_grads(self._h, C.byref(batch), C.byref(io or self.io),
+                                                      tp, self._stream()))
+
+    def apply_grads(self, grad_scale=1.0):
+        """Data-parallel phase 2: grad-norm / clip / Adam on the (all-reduced) flat gradient."""
+        _lib.check(self._lib.rt_learner_apply_grads(self._h, float(grad_scale), self._stream()))
+
+    def flat(self, which=_lib.RT_BUF_GRAD):
+        """Borrowed CUDA tensor over one flat fp32 buffer (gradient by default)."""
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(self._lib.rt_learner_flat_buffer(self._h, which, C.byref(p), C.byref(n)))
+        return _lib.as_tensor(p.value, (n.value,), "<f4", self.device)
 
     def td_abs(self):
         p = C.c_void_p()
