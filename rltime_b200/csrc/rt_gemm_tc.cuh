@@ -350,6 +350,189 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 }
 
 
+// ---------------------------------------------------------------------- persistent GEMM
+// Same math and operand handling as k_gemm_tc, restructured so that a tile's epilogue overlaps
+// the next tile's main loop: one CTA per SM loops over tiles (tile = blockIdx.x + i*gridDim.x,
+// N-tiles of one M-row adjacent so co-running CTAs share the A rows in L2), the accumulator is
+// double-buffered in TMEM (2 x BN columns) behind tmem_full / tmem_empty mbarriers, and the
+// epilogue warps drain accumulator `t & 1` while the MMA warp is already filling the other one.
+// (Measured on the one-tile-per-CTA kernel: main loop 5.7 us + epilogue 7.9 us per 128x128x512
+// tile, serialised and in lock-step across the chip.)
+template <int BN, int A_MN, int B_MN, int STAGES>
+struct SmemLayoutP {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
+  static constexpr int B_BYTES = BN * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SCRATCH_OFFSET = STAGES * STAGE_BYTES;          // 4 warps x 32 x 36 floats
+  static constexpr int BAR_OFFSET = SCRATCH_OFFSET + 4 * 32 * 36 * 4;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+template <int BN, int A_MN, int B_MN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS)
+k_gemm_tc_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ TcArgs a) {
+  using L = SmemLayoutP<BN, A_MN, B_MN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const rtk::GemmArgs& g = a.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = (g.N + BN - 1) / BN;
+  const int tiles_m = (g.M + BLOCK_M - 1) / BLOCK_M;
+  const int splits = (a.num_kb_total + a.kb_per_split - 1) / a.kb_per_split;
+  const int total_tiles = tiles_n * tiles_m * splits;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);     // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (m block, n block, k split); n fastest
+  auto decode = [&](int tile, int& mb, int& nb, int& z) {
+    nb = tile % tiles_n;
+    int r = tile / tiles_n;
+    mb = r % tiles_m;
+    z = r / tiles_m;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;   // global k-block counter: stage = it % STAGES
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mb, nb, z;
+        decode(tile, mb, nb, z);
+        const int m0 = mb * BLOCK_M, n0 = nb * BN;
+        const int kb0 = z * a.kb_per_split;
+        int kb1 = kb0 + a.kb_per_split;
+        if (kb1 > a.num_kb_total) kb1 = a.num_kb_total;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          int s = it % STAGES;
+          uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          int k0 = kb * BLOCK_K;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 32; ++j)
+              tma_load_2d(&tmA, &full_bar[s], sa + j * (BLOCK_K * 128), m0 + 32 * j, k0);
+          } else {
+            tma_load_2d(&tmA, &full_bar[s], sa, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j)
+              tma_load_2d(&tmB, &full_bar[s], sb + j * (BLOCK_K * 128), n0 + 32 * j, k0);
+          } else {
+            tma_load_2d(&tmB, &full_bar[s], sb, k0, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)A_MN << 15) |
+                             ((uint32_t)B_MN << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BLOCK_M >> 4) << 24);
+      uint32_t it = 0;
+      int lt = 0;        // local tile counter: accumulator = lt & 1
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        int mb, nb, z;
+        decode(tile, mb, nb, z);
+        const int kb0 = z * a.kb_per_split;
+        int kb1 = kb0 + a.kb_per_split;
+        if (kb1 > a.num_kb_total) kb1 = a.num_kb_total;
+        const int acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          int s = it % STAGES;
+          uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            uint64_t ad = A_MN ? make_smem_desc(sa + k * 1024, BLOCK_K * 128, 512, 1)
+                               : make_smem_desc(sa + k * (UMMA_K * 4), 16, 1024, 2);
+            uint64_t bd = B_MN ? make_smem_desc(sb + k * 1024, BLOCK_K * 128, 512, 1)
+                               : make_smem_desc(sb + k * (UMMA_K * 4), 16, 1024, 2);
+            umma_tf32(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    float* stage = reinterpret_cast<float*>(smem + L::SCRATCH_OFFSET) + q * (32 * 36);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      int mb, nb, z;
+      decode(tile, mb, nb, z);
+      const int m0 = mb * BLOCK_M, n0 = nb * BN;
+      const int acc = lt & 1;
+      EpiArgs e;
+      const bool split = splits > 1;
+      e.C = split ? g.ws + (size_t)z * g.M * g.N : g.C;
+      e.ldc = split ? g.N : g.ldc;
+      e.M = g.M; e.N = g.N; e.alpha = g.alpha; e.bias = g.bias; e.bias2 = g.bias2; e.relu = g.relu;
+      e.mask = g.mask; e.ldmask = g.ldmask; e.accumulate = g.accumulate; e.round_tf32 = a.round_tf32;
+      e.raw = split ? 1 : 0;
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        if (c == BN / 32 - 1) {
+          // every column of this accumulator is now in registers: hand it back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
+        }
+        if (n0 + c * 32 < g.N) epilogue_chunk(e, v, stage, lane, m0 + q * 32, n0 + c * 32);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------- implicit-GEMM conv
 // Forward convolution without an im2col buffer: out[(img,oh,ow), f] = relu(sum_k A[..,k] W[f,k] + b)
 // where the A tile (128 output pixels x 32 taps) is gathered straight from the input by four
@@ -509,6 +692,200 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvA
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
           umma_tf32(tmem_base, make_smem_desc(sa + k * (UMMA_K * 4), 16, 1024, 2),
                     make_smem_desc(sb + k * (UMMA_K * 4), 16, 1024, 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  }
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+  }
+}
+
+
+// --------------------------------------------------------- implicit-GEMM conv weight gradient
+// dW[f][k] = sum_p dy[p][f] * col[p][k] over a slab of output pixels p, without an im2col
+// buffer.  A = dy^T: MN-major from memory (TMA, 128B_ATOM_32B swizzle); B = col: MN-major,
+// gathered by four producer warps into the same swizzled atom layout (32 k-values x 32 pixels
+// per atom).  grid = (K / BN tiles, 1, pixel slabs); raw partials go to the split-K workspace.
+struct ConvDwArgs {
+  const void* in;      // layer input: uint8 NCHW or float NHWC
+  float* ws;           // [slabs][F][K] raw partials
+  int C, H, W, KH, S, OH, OW;
+  int P;               // output pixels = rows*OH*OW (contraction length)
+  int F, K;            // filters, taps
+  int kb_per_split;    // 32-pixel blocks per slab
+  float scale;
+};
+
+template <int BN, int IN_U8, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS)
+k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ ConvDwArgs a) {
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;          // 4 atoms of dy^T (only ceil(F/32) filled)
+  constexpr int B_BYTES = BN * BLOCK_K * 4;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int total_kb = (a.P + BLOCK_K - 1) / BLOCK_K;
+  const int kb0 = blockIdx.z * a.kb_per_split;
+  int kb1 = kb0 + a.kb_per_split;
+  if (kb1 > total_kb) kb1 = total_kb;
+  const int num_kb = kb1 - kb0;
+  const int a_atoms = (a.F + 31) / 32;
+
+  if (warp == 4 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 128 + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)(BN < 32 ? 32 : BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // rows of the A tile that no TMA box fills must still be finite (their products land in
+  // accumulator rows that are never stored, but NaN garbage is poor hygiene): zero once.
+  for (int i = threadIdx.x; i < STAGES * (A_BYTES / 16); i += blockDim.x) {
+    int s = i / (A_BYTES / 16), o = i - s * (A_BYTES / 16);
+    if (o >= a_atoms * (BLOCK_K * 128 / 16))
+      *reinterpret_cast<float4*>(smem + s * STAGE_BYTES + o * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ---------------- B gather: thread t owns 16-byte chunk j = t % 8 of pixel rows t/8 and
+    // t/8 + 16 in each of the BN/32 atoms
+    const int t = threadIdx.x;
+    const int j = t & 7;
+    constexpr int NAT = BN / 32;
+    // tap offsets of this thread's chunk in every atom are fixed for the whole kernel
+    long long koff[NAT];
+    bool kvalid[NAT];
+#pragma unroll
+    for (int at = 0; at < NAT; ++at) {
+      int k = n0 + 32 * at + 4 * j;
+      kvalid[at] = k < a.K;
+      if (IN_U8) {
+        int kw = k % a.KH, kh = (k / a.KH) % a.KH, c = k / (a.KH * a.KH);
+        koff[at] = ((long long)c * a.H + kh) * a.W + kw;
+      } else {
+        int c = k % a.C, tap = k / a.C;
+        int kw = tap % a.KH, kh = tap / a.KH;
+        koff[at] = ((long long)kh * a.W + kw) * a.C + c;
+      }
+    }
+    auto gather = [&](int kb, float4* v) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        int p = (kb0 + kb) * BLOCK_K + (t >> 3) + 16 * half;
+        long long base = -1;
+        if (p < a.P) {
+          int ow = p % a.OW;
+          int oh = (p / a.OW) % a.OH;
+          long long img = p / (a.OW * a.OH);
+          base = IN_U8 ? (img * a.C * a.H + (long long)oh * a.S) * a.W + (long long)ow * a.S
+                       : ((img * a.H + (long long)oh * a.S) * a.W + (long long)ow * a.S) * a.C;
+        }
+#pragma unroll
+        for (int at = 0; at < NAT; ++at) {
+          float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (base >= 0 && kvalid[at]) {
+            if (IN_U8) {
+              uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(a.in) + base + koff[at]));
+              r = make_float4(__fmul_rn((float)(u & 0xff), a.scale), __fmul_rn((float)((u >> 8) & 0xff), a.scale),
+                              __fmul_rn((float)((u >> 16) & 0xff), a.scale), __fmul_rn((float)(u >> 24), a.scale));
+            } else {
+              r = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(a.in) + base + koff[at]));
+            }
+          }
+          v[half * NAT + at] = r;
+        }
+      }
+    };
+    float4 cur[2 * NAT], nxt[2 * NAT];
+    if (num_kb > 0) gather(0, cur);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      if (kb + 1 < num_kb) gather(kb + 1, nxt);
+      int s = kb % STAGES;
+      uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* sb = smem + s * STAGE_BYTES + A_BYTES;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        int r = (t >> 3) + 16 * half;
+#pragma unroll
+        for (int at = 0; at < NAT; ++at)
+          // 128B_BASE32B swizzle: 32-byte chunk index XOR (row % 4), 16-byte half preserved
+          *reinterpret_cast<float4*>(sb + at * (BLOCK_K * 128) + r * 128 + ((((j >> 1) ^ (r & 3)) << 5) | ((j & 1) << 4))) =
+              cur[half * NAT + at];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+#pragma unroll
+      for (int q = 0; q < 2 * NAT; ++q) cur[q] = nxt[q];
+    }
+    // ---------------- epilogue: rows < F of the accumulator -> raw split-K partial
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* stage = reinterpret_cast<float*>(smem) + warp * (32 * 36);
+    EpiArgs e;
+    e.C = a.ws + (size_t)blockIdx.z * a.F * a.K; e.ldc = a.K; e.M = a.F; e.N = a.K; e.alpha = 1.f;
+    e.bias = nullptr; e.bias2 = nullptr; e.relu = 0; e.mask = nullptr; e.ldmask = 0; e.accumulate = 0;
+    e.round_tf32 = 0; e.raw = 1;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+      if (warp * 32 < a.F && n0 + c * 32 < a.K) epilogue_chunk(e, v, stage, lane, warp * 32, n0 + c * 32);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (warp == 4) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        int s = kb % STAGES;
+        uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], a_atoms * (BLOCK_K * 128));
+        for (int at = 0; at < a_atoms; ++at)
+          tma_load_2d(&tmA, &full_bar[s], smem + s * STAGE_BYTES + at * (BLOCK_K * 128), 32 * at,
+                      (kb0 + kb) * BLOCK_K);
+      }
+    }
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        int s = kb % STAGES;
+        uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+          umma_tf32(tmem_base, make_smem_desc(sa + k * 1024, BLOCK_K * 128, 512, 1),
+                    make_smem_desc(sb + k * 1024, BLOCK_K * 128, 512, 1), idesc, (kb > 0 || k > 0) ? 1u : 0u);
         umma_commit(&empty_bar[s]);
       }
       umma_commit(tmem_full);

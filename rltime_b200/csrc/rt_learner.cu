@@ -52,6 +52,8 @@ struct GemmCtx {
   long long tc_launches = 0, simt_launches = 0;
   int force_bn = 0, force_stages = 0;   // tuning overrides (RT_TC_BN / RT_TC_STAGES, rt_gemm_bench)
   long long* dbg = nullptr;             // clock64 stamps of CTA 0 (rt_gemm_bench)
+  int persistent = 1;                   // overlap epilogue with the next tile (k_gemm_tc_p)
+  int num_sms = 148;
 };
 
 struct ConvL {
@@ -125,6 +127,8 @@ struct rt_learner {
   long long* lstm_dbg = nullptr;
   int lstm_persistent = 1;
   int conv_implicit = 1;
+  int conv_implicit_bwd = 1;
+  float* dcol_full = nullptr;
   int num_sms = 148;
   double* sumsq_part = nullptr;
   float* tau_stage = nullptr;  // device staging for injected taus (5 segments)
@@ -263,6 +267,29 @@ int launch_tc(const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs& 
   return RT_OK;
 }
 
+template <int BN, int A_MN, int B_MN, int STAGES>
+int launch_tc_p(const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs& a, int ctas, cudaStream_t st) {
+  using L = rttc::SmemLayoutP<BN, A_MN, B_MN, STAGES>;
+  auto kern = rttc::k_gemm_tc_p<BN, A_MN, B_MN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  kern<<<ctas, rttc::NUM_THREADS, L::TOTAL, st>>>(*ta, *tb, a);
+  RT_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+// persistent variant: deepest pipeline that fits one CTA per SM next to the epilogue scratch
+template <int BN, int A_MN, int B_MN>
+int launch_tc_persistent(const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs& a, int ctas,
+                         cudaStream_t st) {
+  constexpr int STAGE_BYTES = rttc::BLOCK_M * rttc::BLOCK_K * 4 + BN * rttc::BLOCK_K * 4;
+  constexpr int STAGES = (180 * 1024) / STAGE_BYTES >= 6 ? 6 : ((180 * 1024) / STAGE_BYTES >= 5 ? 5 : (180 * 1024) / STAGE_BYTES);
+  return launch_tc_p<BN, A_MN, B_MN, STAGES>(ta, tb, a, ctas, st);
+}
+
 template <int BN, int A_MN, int B_MN>
 int launch_tc_stages(int stages, const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs& a, dim3 grid,
                      cudaStream_t st) {
@@ -320,8 +347,14 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   a.dbg = cx.dbg;
   dim3 grid(tn, tm, splits);
   int rc;
-#define RT_TC_CASE(bn, am, bm) \
-  if (BN == bn && A_MN == am && B_MN == bm) rc = launch_tc_stages<bn, am, bm>(stages, ta, tb, a, grid, st); else
+  const long long total_tiles = (long long)tn * tm * splits;
+  const bool persistent = cx.persistent && total_tiles > cx.num_sms;
+  const int ctas = (int)(total_tiles < cx.num_sms ? total_tiles : cx.num_sms);
+#define RT_TC_CASE(bn, am, bm)                                                                  \
+  if (BN == bn && A_MN == am && B_MN == bm)                                                     \
+    rc = persistent ? launch_tc_persistent<bn, am, bm>(ta, tb, a, ctas, st)                     \
+                    : launch_tc_stages<bn, am, bm>(stages, ta, tb, a, grid, st);                \
+  else
   RT_TC_CASE(32, 0, 0) RT_TC_CASE(64, 0, 0) RT_TC_CASE(128, 0, 0) RT_TC_CASE(256, 0, 0)
   RT_TC_CASE(32, 0, 1) RT_TC_CASE(64, 0, 1) RT_TC_CASE(128, 0, 1) RT_TC_CASE(256, 0, 1)
   RT_TC_CASE(32, 1, 1) RT_TC_CASE(64, 1, 1) RT_TC_CASE(128, 1, 1) RT_TC_CASE(256, 1, 1)
@@ -452,6 +485,62 @@ int conv_forward_tc(rt_learner* h, cudaStream_t st, const float* net, size_t i, 
   if (BN == 32) return launch_conv_tc<32, 0>(tb, a, st);
   if (BN == 64) return launch_conv_tc<64, 0>(tb, a, st);
   return launch_conv_tc<128, 0>(tb, a, st);
+}
+
+template <int BN, int IN_U8>
+int launch_convdw_tc(const CUtensorMap* ta, const rttc::ConvDwArgs& a, dim3 grid, cudaStream_t st) {
+  constexpr int STAGES = 4;
+  constexpr int SMEM = STAGES * (rttc::BLOCK_M * rttc::BLOCK_K * 4 + BN * rttc::BLOCK_K * 4) +
+                       (2 * STAGES + 1) * 8 + 16 + 1024;
+  auto kern = rttc::k_convdw_tc<BN, IN_U8, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  kern<<<grid, rttc::NUM_THREADS, SMEM, st>>>(*ta, a);
+  RT_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+// Implicit-GEMM weight gradient of conv layer i over all `rows` frames: dW = dy^T . col.
+int conv_dw_tc(rt_learner* h, cudaStream_t st, size_t i, const void* xin, const float* dy, int rows,
+               float* dW) {
+  const ConvL& L = h->conv[i];
+  rttc::ConvDwArgs a;
+  a.in = xin; a.ws = h->gx.ws;
+  a.C = L.cin; a.H = L.hin; a.W = L.win; a.KH = L.k; a.S = L.s; a.OH = L.hout; a.OW = L.wout;
+  a.P = rows * L.hout * L.wout; a.F = L.f; a.K = L.K;
+  a.scale = (float)(1.0 / 255.0);
+  const int BN = L.K <= 32 ? 32 : (L.K <= 64 ? 64 : 128);
+  int tiles = cdiv(L.K, BN);
+  int total_kb = cdiv(a.P, rttc::BLOCK_K);
+  int splits = cdiv(296, tiles);
+  if (splits > total_kb / 8) splits = total_kb / 8;
+  size_t per = (size_t)L.f * L.K;
+  if ((size_t)splits * per > h->gx.ws_floats) splits = (int)(h->gx.ws_floats / per);
+  if (splits < 1) splits = 1;
+  a.kb_per_split = cdiv(total_kb, splits);
+  splits = cdiv(total_kb, a.kb_per_split);
+  const CUtensorMap* ta = nullptr;
+  RT_TRY(get_tmap(h->gx, dy, L.f, a.P, L.f, 32, rttc::BLOCK_K, 1, &ta));
+  dim3 grid(tiles, 1, splits);
+  h->gx.tc_launches++;
+  if (i == 0) {
+    if (BN == 32) RT_TRY((launch_convdw_tc<32, 1>(ta, a, grid, st)));
+    else if (BN == 64) RT_TRY((launch_convdw_tc<64, 1>(ta, a, grid, st)));
+    else RT_TRY((launch_convdw_tc<128, 1>(ta, a, grid, st)));
+  } else {
+    if (BN == 32) RT_TRY((launch_convdw_tc<32, 0>(ta, a, grid, st)));
+    else if (BN == 64) RT_TRY((launch_convdw_tc<64, 0>(ta, a, grid, st)));
+    else RT_TRY((launch_convdw_tc<128, 0>(ta, a, grid, st)));
+  }
+  rtk::GemmArgs g = mk(nullptr, 0, 0, nullptr, 0, 0, dW, L.K, L.f, L.K, a.P);
+  g.ws = h->gx.ws;
+  size_t total = (size_t)L.f * L.K;
+  rtk::k_splitk_reduce<<<cdiv(total, 32), dim3(32, 8), 0, st>>>(g, splits);
+  RT_LAUNCH_CHECK();
+  return RT_OK;
 }
 
 // CNN forward for `rows` frames, chunked so the im2col buffers stay L2-resident.
@@ -699,6 +788,33 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
     rtk::k_relu_bwd_inplace<<<grid1d(n), 256, 0, st>>>(dlast, h->c_out[nl - 1], n);
     RT_LAUNCH_CHECK();
   }
+  {
+    bool all = h->conv_implicit_bwd != 0;
+    for (int i = 0; i < nl; ++i)
+      all = all && conv_tc_eligible(h, i, i == 0 ? (const void*)x : (const void*)h->c_out[i - 1]) &&
+            h->conv[i].f % 4 == 0;
+    if (all) {
+      // whole batch at once: implicit-GEMM dW (no im2col), one dcol GEMM + col2im per layer
+      for (int i = nl - 1; i >= 0; --i) {
+        const ConvL& L = h->conv[i];
+        size_t opix = (size_t)L.hout * L.wout;
+        float* dy = i == nl - 1 ? dlast : h->d_c[i];
+        const void* xin = i == 0 ? (const void*)x : (const void*)h->c_out[i - 1];
+        RT_TRY(conv_dw_tc(h, st, i, xin, dy, rows, G + L.w));
+        RT_TRY(colsum(h, st, dy, (size_t)rows * opix, L.f, G + L.b, 0));
+        if (i > 0) {
+          RT_TRY(gemm(h->gx, st, mk(dy, L.f, 0, net + L.w, L.K, 0, h->dcol_full, L.K, (int)(rows * opix), L.K, L.f)));
+          size_t n_in = (size_t)rows * L.hin * L.win * L.cin;
+          rtk::k_col2im_nhwc<<<grid1d(n_in), 256, 0, st>>>(h->dcol_full, h->d_c[i - 1], rows, L.cin, L.hin,
+                                                          L.win, L.k, L.s, L.hout, L.wout);
+          RT_LAUNCH_CHECK();
+          rtk::k_relu_bwd_inplace<<<grid1d(n_in), 256, 0, st>>>(h->d_c[i - 1], h->c_out[i - 1], n_in);
+          RT_LAUNCH_CHECK();
+        }
+      }
+      return RT_OK;
+    }
+  }
   for (int r0 = 0; r0 < rows; r0 += h->chunk_rows) {
     int rc = rows - r0 < h->chunk_rows ? rows - r0 : h->chunk_rows;
     int first = r0 == 0;
@@ -884,6 +1000,14 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   }
   RT_TRY(dalloc(h, &h->col, maxcol));
   RT_TRY(dalloc(h, &h->dcol, maxcol));
+  {
+    size_t mx = 0;
+    for (size_t i = 1; i < h->conv.size(); ++i) {
+      size_t v = (size_t)h->M * h->conv[i].hout * h->conv[i].wout * h->conv[i].K;
+      if (v > mx) mx = v;
+    }
+    RT_TRY(dalloc(h, &h->dcol_full, mx));
+  }
   if (h->U) {
     size_t U = h->U;
     RT_TRY(dalloc(h, &h->xg, rows * 4 * U, "xg"));
@@ -928,6 +1052,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   h->gx.mode = td->gemm_mode;
   if (const char* e = getenv("RT_TC_BN")) h->gx.force_bn = atoi(e);
   if (const char* e = getenv("RT_TC_STAGES")) h->gx.force_stages = atoi(e);
+  if (const char* e = getenv("RT_TC_PERSISTENT")) h->gx.persistent = atoi(e);
   size_t maxN = 4 * (size_t)(h->U ? h->U : 1);
   if (D > maxN) maxN = D;
   if (F > maxN) maxN = F;
@@ -943,10 +1068,13 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     cudaDeviceProp prop;
     RT_CUDA(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
+    h->gx.num_sms = prop.multiProcessorCount;
     const char* e = getenv("RT_LSTM_STEPWISE");
     if (e && e[0] == '1') h->lstm_persistent = 0;
     e = getenv("RT_CONV_IM2COL");
     if (e && e[0] == '1') h->conv_implicit = 0;
+    e = getenv("RT_CONV_BWD_IM2COL");
+    if (e && e[0] == '1') h->conv_implicit_bwd = 0;
   }
   RT_TRY(dalloc(h, &h->hw_part, (size_t)h->hw_parts * (A + 1) * F));
   RT_TRY(dalloc(h, &h->hw_partb, (size_t)h->hw_parts * (A + 1)));
@@ -1210,6 +1338,7 @@ extern "C" int rt_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, int32
   RT_CUDA(cudaSetDevice(device));
   GemmCtx cx;
   cx.mode = mode;
+  if (const char* e = getenv("RT_TC_PERSISTENT")) cx.persistent = atoi(e);
   cx.ws_floats = (size_t)16 << 20;
   float *dA = nullptr, *dB = nullptr, *dC = nullptr, *dbias = nullptr;
   size_t nA = (size_t)M * K, nB = (size_t)N * K, nC = (size_t)M * N;
@@ -1248,6 +1377,7 @@ extern "C" int rt_gemm_bench(int32_t mode, int32_t M, int32_t N, int32_t K, int3
   RT_CUDA(cudaSetDevice(device));
   GemmCtx cx;
   cx.mode = mode;
+  if (const char* e = getenv("RT_TC_PERSISTENT")) cx.persistent = atoi(e);
   cx.force_bn = force_bn;
   cx.force_stages = force_stages;
   cx.ws_floats = (size_t)64 << 20;

@@ -8,7 +8,6 @@ timeout 300 python -m pytest tests/test_gemm_gpu.py -m gpu -q -s --timeout 240 2
 if grep -q "failed\|error\|Timeout" gpurun_out/pytest_gemm.log; then export RT_BENCH_GEMM=fp32; echo "tcgen05 GEMM NOT green -> bench on fp32 path"; fi
 echo "=== gemm tile sweep"
 timeout 300 python scripts/gemm_sweep.py 2>&1 | tee gpurun_out/gemm_sweep.txt
-RT_DEBUG_TIMELINE=1 timeout 120 python scripts/gemm_sweep.py 2>&1 | grep timeline | grep -E "bn=128 st=3|bn=64 st=4" | tee gpurun_out/gemm_timeline.txt
 timeout 120 python scripts/timeline.py 2>&1 | tail -24 | tee gpurun_out/lstm_timeline.txt
 echo "=== pytest gpu (all, continue past failures)"
 timeout 1200 python -m pytest tests -m gpu -q --timeout 600 --deselect tests/test_gemm_gpu.py 2>&1 | tail -60 | tee gpurun_out/pytest_gpu.log

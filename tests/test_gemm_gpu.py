@@ -19,6 +19,9 @@ CASES = [
     (128, 128, 64, 1, 0, 0), (512, 512, 2048, 1, 0, 0), (2048, 3136, 640, 1, 0, 0),
     (32, 256, 51200, 1, 0, 0), (64, 576, 6272, 1, 0, 0), (512, 64, 4096, 1, 0, 0),
     (200, 96, 100, 1, 0, 0),
+    # > 148 tiles: the persistent, accumulator-double-buffered kernel (k_gemm_tc_p)
+    (20480, 512, 512, 0, 1, 1), (20480, 512, 512, 0, 0, 0), (512, 512, 20480, 1, 0, 0),
+    (20000, 500, 96, 0, 1, 1), (2048, 3136, 640, 1, 0, 0), (19000, 64, 576, 0, 1, 1),
 ]
 
 
