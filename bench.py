@@ -39,11 +39,12 @@ FRAME_BYTES = 4 * 84 * 84
 
 
 def peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s sustained, source).  TF32 tensor rate = bf16 / 2."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), "measured"
-    return 6650.0, "fallback"
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0)), "measured"
+    return 6650.0, 1400.0, "fallback"
 
 
 class ClockSampler:
@@ -199,6 +200,15 @@ def run_gpu(args):
     gather_ms_total, gather_n = hist.gather_time()     # CUDA events around k_gather, live
     hist.profile_gather(False)
 
+    # GEMM-shaped launches, live (extra profiled steps AFTER the timed region: the event pairs
+    # around ~190 launches per update perturb the step slightly, so they stay out of `value`)
+    learner.profile_gemms(True)
+    prof_steps = 5
+    for _ in range(prof_steps):
+        one_update(hist, learner, B, world)
+    gemm_ms, gemm_flops, gemm_n = learner.gemm_time()
+    learner.profile_gemms(False)
+
     # gather kernel alone (roofline): time draws without the learner
     torch.cuda.synchronize(device)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -252,7 +262,8 @@ def run_gpu(args):
     ms, e2e_s = float(vals[0]), float(vals[1])
     if rank != 0:
         return
-    hbm, which = peaks()
+    hbm, bf16_tf, which = peaks()
+    tf32_peak = bf16_tf / 2.0
     S, n = cfg["T"] + cfg["P"], cfg["n"]
     state_bytes = FRAME_BYTES + 2 * cfg["units"] * 4 + 4
     gather_bytes = 2 * (S + n) * B * state_bytes        # read once + write once
@@ -273,7 +284,16 @@ def run_gpu(args):
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
-        "roofline": {"kernel": "k_gather", "bound": "hbm",
+        "roofline": {"kernel": "tcgen05 GEMM family (k_gemm_tc_p / k_gemm_tc / k_conv_tc / k_convdw_tc): "
+                               "all GEMM-shaped launches of the update", "bound": "tensor",
+                     "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
+                     "peak": tf32_peak, "unit": "TFLOP/s",
+                     "peak_source": which + " cuBLAS bf16 sustained / 2 (TF32 multiplies at half the bf16 rate)",
+                     "frac": (gemm_flops / (gemm_ms * 1e-3) / 1e12 / tf32_peak) if gemm_ms > 0 else None,
+                     "traffic": None, "launches_timed": int(gemm_n), "profiled_steps": prof_steps,
+                     "gflop_per_update": gemm_flops / prof_steps / 1e9,
+                     "gemm_ms_per_update": gemm_ms / prof_steps},
+        "roofline_gather": {"kernel": "k_gather", "bound": "hbm",
                      "achieved": gather_bytes / (gather_ms_total / max(gather_n, 1) * 1e-3) / 1e9,
                      "peak": hbm, "peak_source": which, "unit": "GB/s",
                      "frac": gather_bytes / (gather_ms_total / max(gather_n, 1) * 1e-3) / 1e9 / hbm,

@@ -242,6 +242,11 @@ int rt_learner_read_stats(rt_learner* h, float* loss, float* td_mean, float* gra
 int rt_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB,
                  const float* A, const float* B, const float* bias, int32_t relu, float* C,
                  int32_t device);
+/* Measurement hook: when enabled, CUDA events bracket every GEMM-shaped launch (tcgen05 GEMM,
+ * implicit conv, conv weight gradient, SIMT fallback) on the launch stream;
+ * rt_learner_gemm_time returns and resets the summed device time and algorithmic flops (2MNK). */
+int rt_learner_profile(rt_learner* h, int32_t enable);
+int rt_learner_gemm_time(rt_learner* h, double* total_ms, double* total_flops, int64_t* launches);
 /* Measurement hook: average device time (CUDA events) of `iters` back-to-back launches of one
  * GEMM shape; force_bn / force_stages (0 = heuristic) select the tcgen05 tile configuration. */
 int rt_gemm_bench(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB,

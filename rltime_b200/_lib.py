@@ -122,6 +122,9 @@ SIGNATURES = {
                                         C.POINTER(C.c_float), _VP]),
     "rt_learner_debug_tensor": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP), C.POINTER(C.c_int64)]),
     "rt_gemm_test": (C.c_int, [C.c_int32] * 6 + [_VP, _VP, _VP, C.c_int32, _VP, C.c_int32]),
+    "rt_learner_profile": (C.c_int, [_VP, C.c_int32]),
+    "rt_learner_gemm_time": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_int64)]),
     "rt_gemm_bench": (C.c_int, [C.c_int32] * 9 + [C.POINTER(C.c_double), C.c_int32]),
 }
 

@@ -122,26 +122,109 @@ struct EpiArgs {
   int raw;             // 1: store the raw accumulator (split-K partial), no epilogue ops
 };
 
+// Per-warp, per-tile epilogue state: everything that does not depend on the chunk is computed
+// once (the first version re-derived pointers, predicates and parameter loads per chunk and
+// spent ~3900 cycles per 32x32 chunk in a ~400-instruction branchy sequence).
+struct EpiWarp {
+  float* dst;            // C + (row0 + lane/8) * ldc + n0 + 4 * (lane%8)
+  const float* msk;      // same position in the mask (or null)
+  size_t row_step;       // 4 * ldc floats
+  size_t mrow_step;      // 4 * ldmask floats
+  int n0;                // first column of the tile
+  int rows_left;         // M - (row0 + lane/8): row i*4 of this lane is valid iff i*4 < rows_left
+  bool fast;             // aligned, full-width tile: 16-byte path without column predicates
+};
+
+__device__ __forceinline__ EpiWarp epi_begin(const EpiArgs& e, int lane, int row0, int n0, int bn) {
+  EpiWarp w;
+  const int r = lane >> 3, cg = lane & 7;
+  w.dst = e.C + (size_t)(row0 + r) * e.ldc + n0 + 4 * cg;
+  w.msk = e.mask ? e.mask + (size_t)(row0 + r) * e.ldmask + n0 + 4 * cg : nullptr;
+  w.row_step = (size_t)4 * e.ldc;
+  w.mrow_step = (size_t)4 * e.ldmask;
+  w.n0 = n0;
+  w.rows_left = e.M - (row0 + r);
+  w.fast = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) && (n0 + bn <= e.N) &&
+           ((n0 & 3) == 0) &&
+           (e.raw || ((!e.mask || (((e.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.mask) & 15) == 0))) &&
+                      (!e.bias || ((reinterpret_cast<uintptr_t>(e.bias) & 15) == 0)) &&
+                      (!e.bias2 || ((reinterpret_cast<uintptr_t>(e.bias2) & 15) == 0))));
+  return w;
+}
+
 // One warp moves its 32-row x 32-column accumulator chunk (lane = row, straight out of
 // tcgen05.ld) to global memory through a padded shared-memory transpose, so that every store
-// instruction writes four complete 128-byte row segments instead of 32 scattered 16-byte
-// pieces (the scattered form capped a 42 MB output at ~1.7 TB/s).  `stage` = this warp's
-// private 32 x 36 float scratch.
-__device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const uint32_t* v, float* stage, int lane,
-                                               int row0, int nb) {
-  // lane-major -> smem (16-byte stores, conflict-free at pitch 36)
+// instruction writes four complete 128-byte row segments.  `stage` = this warp's private
+// 32 x 36 float scratch; chunk column offset `coff` = 32 * c.
+__device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const EpiWarp& w, const uint32_t* v, float* stage,
+                                               int lane, int row0, int nb) {
 #pragma unroll
   for (int q = 0; q < 8; ++q)
     *reinterpret_cast<float4*>(stage + lane * 36 + 4 * q) =
         make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
                     __uint_as_float(v[4 * q + 3]));
   __syncwarp();
-  const int cg = lane & 7;          // 4-column group inside the chunk
+  const int cg = lane & 7;
   const int n = nb + 4 * cg;
-  const bool vec = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) && (n + 4 <= e.N) &&
-                   (e.raw || ((!e.mask || (((e.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.mask) & 15) == 0))) &&
-                              (!e.bias || ((reinterpret_cast<uintptr_t>(e.bias) & 15) == 0)) &&
-                              (!e.bias2 || ((reinterpret_cast<uintptr_t>(e.bias2) & 15) == 0))));
+  if (w.fast) {
+    // ---- straight-line 16-byte path: loads first (LDS + optional mask / old C), then math, then stores
+    float4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const float4*>(stage + (i * 4 + (lane >> 3)) * 36 + 4 * cg);
+    const int chunk_off = nb - w.n0;                  // w.dst / w.msk already point at column n0 + 4*cg
+    float* dptr = w.dst + chunk_off;
+    if (e.raw) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i * 4 < w.rows_left) *reinterpret_cast<float4*>(dptr + i * w.row_step) = t[i];
+    } else {
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+      if (e.bias2) {
+        float4 b2 = __ldg(reinterpret_cast<const float4*>(e.bias2 + n));
+        b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+      }
+      float4 mk[8], old[8];
+      if (e.mask) {
+        const float* mp = w.msk + chunk_off;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          mk[i] = (i * 4 < w.rows_left) ? *reinterpret_cast<const float4*>(mp + i * w.mrow_step)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (e.accumulate) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          old[i] = (i * 4 < w.rows_left) ? *reinterpret_cast<const float4*>(dptr + i * w.row_step)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float x[4] = {t[i].x * e.alpha + b.x, t[i].y * e.alpha + b.y, t[i].z * e.alpha + b.z, t[i].w * e.alpha + b.w};
+        if (e.relu) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) x[k] = fmaxf(x[k], 0.f);
+        }
+        if (e.mask) {
+          x[0] = mk[i].x > 0.f ? x[0] : 0.f; x[1] = mk[i].y > 0.f ? x[1] : 0.f;
+          x[2] = mk[i].z > 0.f ? x[2] : 0.f; x[3] = mk[i].w > 0.f ? x[3] : 0.f;
+        }
+        if (e.accumulate) { x[0] += old[i].x; x[1] += old[i].y; x[2] += old[i].z; x[3] += old[i].w; }
+        if (e.round_tf32) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint32_t tt;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tt) : "f"(x[k]));
+            x[k] = __uint_as_float(tt);
+          }
+        }
+        if (i * 4 < w.rows_left) *reinterpret_cast<float4*>(dptr + i * w.row_step) = make_float4(x[0], x[1], x[2], x[3]);
+      }
+    }
+    __syncwarp();
+    return;
+  }
+  // ---- general path: column tails / unaligned operands
   float b[4] = {0.f, 0.f, 0.f, 0.f};
   if (!e.raw) {
 #pragma unroll
@@ -151,7 +234,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const uint32_t*
         if (e.bias2) b[k] += __ldg(e.bias2 + n + k);
       }
   }
-#pragma unroll
+#pragma unroll 1
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + (lane >> 3);
     const int m = row0 + r;
@@ -159,39 +242,22 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const uint32_t*
     if (m >= e.M || n >= e.N) continue;
     float x[4] = {t4.x, t4.y, t4.z, t4.w};
     float* dst = e.C + (size_t)m * e.ldc + n;
-    if (!e.raw) {
-      float mk[4] = {1.f, 1.f, 1.f, 1.f}, old[4] = {0.f, 0.f, 0.f, 0.f};
-      if (vec) {
-        if (e.mask) { float4 t = *reinterpret_cast<const float4*>(e.mask + (size_t)m * e.ldmask + n); mk[0] = t.x; mk[1] = t.y; mk[2] = t.z; mk[3] = t.w; }
-        if (e.accumulate) { float4 t = *reinterpret_cast<const float4*>(dst); old[0] = t.x; old[1] = t.y; old[2] = t.z; old[3] = t.w; }
-      } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (n + k < e.N) {
-            if (e.mask) mk[k] = e.mask[(size_t)m * e.ldmask + n + k];
-            if (e.accumulate) old[k] = dst[k];
-          }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float y = x[k] * e.alpha + b[k];
+    for (int k = 0; k < 4; ++k) {
+      if (n + k >= e.N) continue;
+      float y = x[k];
+      if (!e.raw) {
+        y = y * e.alpha + b[k];
         if (e.relu) y = fmaxf(y, 0.f);
-        if (e.mask) y = mk[k] > 0.f ? y : 0.f;
-        y += old[k];
+        if (e.mask) y = e.mask[(size_t)m * e.ldmask + n + k] > 0.f ? y : 0.f;
+        if (e.accumulate) y += dst[k];
         if (e.round_tf32) {
           uint32_t tt;
           asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tt) : "f"(y));
           y = __uint_as_float(tt);
         }
-        x[k] = y;
       }
-    }
-    if (vec) {
-      *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (n + k < e.N) dst[k] = x[k];
+      dst[k] = y;
     }
   }
   __syncwarp();
@@ -331,11 +397,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     e.M = g.M; e.N = g.N; e.alpha = g.alpha; e.bias = g.bias; e.bias2 = g.bias2; e.relu = g.relu;
     e.mask = g.mask; e.ldmask = g.ldmask; e.accumulate = g.accumulate; e.round_tf32 = a.round_tf32;
     e.raw = split ? 1 : 0;
+    const EpiWarp ew = epi_begin(e, lane, m0 + q * 32, n0, BN);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      if (n0 + c * 32 < g.N) epilogue_chunk(e, v, stage, lane, m0 + q * 32, n0 + c * 32);
+      if (n0 + c * 32 < g.N) epilogue_chunk(e, ew, v, stage, lane, m0 + q * 32, n0 + c * 32);
     }
     if (dbg_cta && threadIdx.x == 64) a.dbg[4] = clock64();     // epilogue done
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -508,6 +575,7 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       e.M = g.M; e.N = g.N; e.alpha = g.alpha; e.bias = g.bias; e.bias2 = g.bias2; e.relu = g.relu;
       e.mask = g.mask; e.ldmask = g.ldmask; e.accumulate = g.accumulate; e.round_tf32 = a.round_tf32;
       e.raw = split ? 1 : 0;
+      const EpiWarp ew = epi_begin(e, lane, m0 + q * 32, n0, BN);
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -521,7 +589,7 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (lane == 0)
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
         }
-        if (n0 + c * 32 < g.N) epilogue_chunk(e, v, stage, lane, m0 + q * 32, n0 + c * 32);
+        if (n0 + c * 32 < g.N) epilogue_chunk(e, ew, v, stage, lane, m0 + q * 32, n0 + c * 32);
       }
     }
   }
@@ -660,11 +728,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvA
     EpiArgs e;
     e.C = a.out; e.ldc = a.N; e.M = a.M; e.N = a.N; e.alpha = 1.f; e.bias = a.bias; e.bias2 = nullptr;
     e.relu = 1; e.mask = nullptr; e.ldmask = 0; e.accumulate = 0; e.round_tf32 = a.round_tf32; e.raw = 0;
+    const EpiWarp ew = epi_begin(e, lane, m0 + warp * 32, n0, BN);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-      if (n0 + c * 32 < a.N) epilogue_chunk(e, v, stage, lane, m0 + warp * 32, n0 + c * 32);
+      if (n0 + c * 32 < a.N) epilogue_chunk(e, ew, v, stage, lane, m0 + warp * 32, n0 + c * 32);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else if (warp == 4) {
@@ -852,11 +921,12 @@ k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Con
     e.C = a.ws + (size_t)blockIdx.z * a.F * a.K; e.ldc = a.K; e.M = a.F; e.N = a.K; e.alpha = 1.f;
     e.bias = nullptr; e.bias2 = nullptr; e.relu = 0; e.mask = nullptr; e.ldmask = 0; e.accumulate = 0;
     e.round_tf32 = 0; e.raw = 1;
+    const EpiWarp ew = epi_begin(e, lane, warp * 32, n0, BN);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-      if (warp * 32 < a.F && n0 + c * 32 < a.K) epilogue_chunk(e, v, stage, lane, warp * 32, n0 + c * 32);
+      if (warp * 32 < a.F && n0 + c * 32 < a.K) epilogue_chunk(e, ew, v, stage, lane, warp * 32, n0 + c * 32);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else if (warp == 4) {

@@ -196,6 +196,38 @@ __global__ void k_im2col_f32_nhwc(const float* __restrict__ x, float* __restrict
 __global__ void k_col2im_nhwc(const float* __restrict__ dcol, float* __restrict__ dx, int rows, int C,
                               int H, int W, int KH, int S, int OH, int OW) {
   const int K = C * KH * KH;
+  const int C4 = C >> 2;   // C % 4 == 0 (checked by the launcher)
+  size_t total = (size_t)rows * H * W * C4;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(idx % C4) * 4;
+    size_t r = idx / C4;
+    int iw = (int)(r % W);
+    int ih = (int)((r / W) % H);
+    size_t m = r / ((size_t)W * H);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kh = 0; kh < KH; ++kh) {
+      int t = ih - kh;
+      if (t < 0 || t % S) continue;
+      int oh = t / S;
+      if (oh >= OH) continue;
+      for (int kw = 0; kw < KH; ++kw) {
+        int u = iw - kw;
+        if (u < 0 || u % S) continue;
+        int ow = u / S;
+        if (ow >= OW) continue;
+        float4 v = *reinterpret_cast<const float4*>(dcol + ((m * OH + oh) * OW + ow) * K + (kh * KH + kw) * C + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    *reinterpret_cast<float4*>(dx + r * C + c) = acc;
+  }
+}
+
+// scalar fallback for C % 4 != 0
+__global__ void k_col2im_nhwc_s(const float* __restrict__ dcol, float* __restrict__ dx, int rows, int C,
+                                int H, int W, int KH, int S, int OH, int OW) {
+  const int K = C * KH * KH;
   size_t total = (size_t)rows * H * W * C;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -311,14 +343,17 @@ __global__ void k_cos_features(const float* __restrict__ tau, float* __restrict_
   cf[idx] = cosf(__fmul_rn(__fmul_rn((float)(i + 1), 3.14159274101257324f), t));
 }
 
-// xq[r,d] = x[r / Nq, d] * phi[r,d]      (iqn.py:84, 99-100)
+// xq[r,d] = x[r / Nq, d] * phi[r,d]      (iqn.py:84, 99-100); D % 4 == 0
 __global__ void k_quantile_mul(const float* __restrict__ x, const float* __restrict__ phi,
                                float* __restrict__ xq, size_t rowsq, int D, int Nq) {
+  const int D4 = D >> 2;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rowsq * D) return;
-  size_t r = idx / D;
-  int d = (int)(idx - r * D);
-  xq[idx] = x[(r / Nq) * D + d] * phi[idx];
+  if (idx >= rowsq * D4) return;
+  size_t r = idx / D4;
+  int d4 = (int)(idx - r * D4);
+  float4 a = reinterpret_cast<const float4*>(x + (r / Nq) * D)[d4];
+  float4 p = reinterpret_cast<const float4*>(phi + r * D)[d4];
+  reinterpret_cast<float4*>(xq + r * D)[d4] = make_float4(a.x * p.x, a.y * p.y, a.z * p.z, a.w * p.w);
 }
 
 // dphi_pre[r,d] = dxq[r,d] * x[m,d] * (phi > 0);  dx[m,d] = sum_q dxq[m*Nq+q, d] * phi[m*Nq+q, d]
@@ -526,12 +561,22 @@ __global__ void k_heads_out(const float* __restrict__ h1, const float* __restric
   float accv = 0.f;
   const float* hr = h1 + r * F;
   const float* vr = v1 ? v1 + r * F : nullptr;
-  for (int f = lane; f < F; f += 32) {
-    float hv = hr[f];
+  // F % 4 == 0: 16-byte loads, several independent rows of loads in flight per lane
+  for (int f = lane * 4; f < F; f += 128) {
+    float4 hv = *reinterpret_cast<const float4*>(hr + f);
 #pragma unroll
     for (int a = 0; a < MAXA; ++a)
-      if (a < A) acc[a] = fmaf(hv, Wout[(size_t)a * F + f], acc[a]);
-    if (vr) accv = fmaf(vr[f], Wv[f], accv);
+      if (a < A) {
+        float4 w = __ldg(reinterpret_cast<const float4*>(Wout + (size_t)a * F + f));
+        acc[a] = fmaf(hv.x, w.x, acc[a]); acc[a] = fmaf(hv.y, w.y, acc[a]);
+        acc[a] = fmaf(hv.z, w.z, acc[a]); acc[a] = fmaf(hv.w, w.w, acc[a]);
+      }
+    if (vr) {
+      float4 vv = *reinterpret_cast<const float4*>(vr + f);
+      float4 w = __ldg(reinterpret_cast<const float4*>(Wv + f));
+      accv = fmaf(vv.x, w.x, accv); accv = fmaf(vv.y, w.y, accv);
+      accv = fmaf(vv.z, w.z, accv); accv = fmaf(vv.w, w.w, accv);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -723,8 +768,10 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 // xg: (T*B, 4U) = x W_ih^T + b_ih + b_hh;  W_hh: (4U, U);  hx, cx: (B, U) state of step 0;
 // initials: (T*B).  Outputs as in the stepwise path: gates (T*B,4U) activated, c_all, h_all,
 // hprev / cprev (masked carry-ins, needed by BPTT), all (T*B, U).  B <= 32 * BCH.
+// 256 threads: all 8 warps stage h (16 independent 16-byte loads each); warp w computes unit
+// (w & 3) over K-half (w >> 2); the upper half hands its partial sums over through smem.
 template <int BCH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, const float* __restrict__ hx,
                const float* __restrict__ cx, const float* __restrict__ initials,
                float* __restrict__ gates, float* __restrict__ c_all, float* __restrict__ h_all,
@@ -735,9 +782,10 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
   float* Ws = sm;                          // [4 gates][UPB][U]
   float* hs = sm + 4 * UPB * U;            // [B][U + HPAD]
   const int HS = U + HPAD;
+  float* red = hs + (size_t)B * HS;        // [UPB][32 * BCH][4] partial sums of the upper K half
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * UPB + warp;
-  // resident weight slice
+  const int uw = warp & 3, khalf = warp >> 2;
+  const int unit = blockIdx.x * UPB + uw;
   for (int i = threadIdx.x; i < 4 * UPB * (U / 4); i += blockDim.x) {
     int row = i / (U / 4), k4 = i - row * (U / 4);
     int g = row / UPB, u = row - g * UPB;
@@ -748,28 +796,31 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
 #pragma unroll
   for (int j = 0; j < BCH; ++j) {
     int b = lane + 32 * j;
-    c_reg[j] = b < B ? cx[(size_t)b * U + unit] : 0.f;
+    c_reg[j] = (khalf == 0 && b < B) ? cx[(size_t)b * U + unit] : 0.f;
   }
+  const int KH4 = U / 8;   // float4 per K half
   for (int t = 0; t < T; ++t) {
     const float* hsrc = t == 0 ? hx : h_all + (size_t)(t - 1) * B * U;
     const float* ini = initials + (size_t)t * B;
-    // prefetch this step's input-projection terms (independent of h) before anything waits
+    // input-projection terms of this step (independent of h): issue before anything waits
     float xin[BCH][4];
+    if (khalf == 0) {
 #pragma unroll
-    for (int j = 0; j < BCH; ++j) {
-      int b = lane + 32 * j;
-      if (b < B) {
-        const float* xr = xg + ((size_t)t * B + b) * 4 * U + unit;
-        xin[j][0] = __ldg(xr); xin[j][1] = __ldg(xr + U); xin[j][2] = __ldg(xr + 2 * U); xin[j][3] = __ldg(xr + 3 * U);
+      for (int j = 0; j < BCH; ++j) {
+        int b = lane + 32 * j;
+        if (b < B) {
+          const float* xr = xg + ((size_t)t * B + b) * 4 * U + unit;
+          xin[j][0] = __ldg(xr); xin[j][1] = __ldg(xr + U); xin[j][2] = __ldg(xr + 2 * U); xin[j][3] = __ldg(xr + 3 * U);
+        }
       }
     }
-    // stage masked h_{t-1}: 8 independent 16-byte loads in flight per thread
+    // stage masked h_{t-1}
     {
       const int total = B * (U / 4);
-      for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * 8) {
-        float4 v[8];
+      for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * 16) {
+        float4 v[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 16; ++q) {
           int i = i0 + q * blockDim.x;
           if (i < total) {
             int b = i / (U / 4), k4 = i - b * (U / 4);
@@ -777,7 +828,7 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
           }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 16; ++q) {
           int i = i0 + q * blockDim.x;
           if (i < total) {
             int b = i / (U / 4), k4 = i - b * (U / 4);
@@ -790,18 +841,20 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
     }
     __syncthreads();
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4 * t + 0] = clock64();
+    float acc[BCH][4];
 #pragma unroll
     for (int j = 0; j < BCH; ++j) {
       int b = lane + 32 * j;
+      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
       if (b < B) {
+        const float4* hr = reinterpret_cast<const float4*>(hs + (size_t)b * HS) + khalf * KH4;
+        const float4* w0 = reinterpret_cast<const float4*>(Ws + ((size_t)0 * UPB + uw) * U) + khalf * KH4;
+        const float4* w1 = reinterpret_cast<const float4*>(Ws + ((size_t)1 * UPB + uw) * U) + khalf * KH4;
+        const float4* w2 = reinterpret_cast<const float4*>(Ws + ((size_t)2 * UPB + uw) * U) + khalf * KH4;
+        const float4* w3 = reinterpret_cast<const float4*>(Ws + ((size_t)3 * UPB + uw) * U) + khalf * KH4;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        const float4* hr = reinterpret_cast<const float4*>(hs + (size_t)b * HS);
-        const float4* w0 = reinterpret_cast<const float4*>(Ws + ((size_t)0 * UPB + warp) * U);
-        const float4* w1 = reinterpret_cast<const float4*>(Ws + ((size_t)1 * UPB + warp) * U);
-        const float4* w2 = reinterpret_cast<const float4*>(Ws + ((size_t)2 * UPB + warp) * U);
-        const float4* w3 = reinterpret_cast<const float4*>(Ws + ((size_t)3 * UPB + warp) * U);
 #pragma unroll 4
-        for (int k = 0; k < U / 4; ++k) {
+        for (int k = 0; k < KH4; ++k) {
           float4 h4 = hr[k];
           float4 p = w0[k];
           a0 = fmaf(h4.x, p.x, a0); a0 = fmaf(h4.y, p.y, a0); a0 = fmaf(h4.z, p.z, a0); a0 = fmaf(h4.w, p.w, a0);
@@ -812,22 +865,35 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
           p = w3[k];
           a3 = fmaf(h4.x, p.x, a3); a3 = fmaf(h4.y, p.y, a3); a3 = fmaf(h4.z, p.z, a3); a3 = fmaf(h4.w, p.w, a3);
         }
-        size_t row = (size_t)t * B + b;
-        float gi = sigmoidf_(xin[j][0] + a0);
-        float gf = sigmoidf_(xin[j][1] + a1);
-        float gg = tanhf(xin[j][2] + a2);
-        float go = sigmoidf_(xin[j][3] + a3);
-        float keep = 1.f - ini[b];
-        float cp = c_reg[j] * keep;
-        float c = gf * cp + gi * gg;
-        float h = go * tanhf(c);
-        c_reg[j] = c;
-        float* gr = gates + row * 4 * U + unit;
-        gr[0] = gi; gr[U] = gf; gr[2 * U] = gg; gr[3 * U] = go;
-        c_all[row * U + unit] = c;
-        h_all[row * U + unit] = h;
-        cprev[row * U + unit] = cp;
-        hprev[row * U + unit] = hs[(size_t)b * HS + unit];
+        acc[j][0] = a0; acc[j][1] = a1; acc[j][2] = a2; acc[j][3] = a3;
+        if (khalf == 1)
+          *reinterpret_cast<float4*>(red + ((size_t)uw * 32 * BCH + b) * 4) = make_float4(a0, a1, a2, a3);
+      }
+    }
+    __syncthreads();
+    if (khalf == 0) {
+#pragma unroll
+      for (int j = 0; j < BCH; ++j) {
+        int b = lane + 32 * j;
+        if (b < B) {
+          float4 hi = *reinterpret_cast<const float4*>(red + ((size_t)uw * 32 * BCH + b) * 4);
+          size_t row = (size_t)t * B + b;
+          float gi = sigmoidf_(xin[j][0] + (acc[j][0] + hi.x));
+          float gf = sigmoidf_(xin[j][1] + (acc[j][1] + hi.y));
+          float gg = tanhf(xin[j][2] + (acc[j][2] + hi.z));
+          float go = sigmoidf_(xin[j][3] + (acc[j][3] + hi.w));
+          float keep = 1.f - ini[b];
+          float cp = c_reg[j] * keep;
+          float c = gf * cp + gi * gg;
+          float h = go * tanhf(c);
+          c_reg[j] = c;
+          float* gr = gates + row * 4 * U + unit;
+          gr[0] = gi; gr[U] = gf; gr[2 * U] = gg; gr[3 * U] = go;
+          c_all[row * U + unit] = c;
+          h_all[row * U + unit] = h;
+          cprev[row * U + unit] = cp;
+          hprev[row * U + unit] = hs[(size_t)b * HS + unit];
+        }
       }
     }
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4 * t + 1] = clock64();

@@ -54,6 +54,11 @@ struct GemmCtx {
   long long* dbg = nullptr;             // clock64 stamps of CTA 0 (rt_gemm_bench)
   int persistent = 1;                   // overlap epilogue with the next tile (k_gemm_tc_p)
   int num_sms = 148;
+  // live timing of every GEMM-shaped launch (bench.py roofline): CUDA events on the launch stream
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
+  double prof_flops = 0;
 };
 
 struct ConvL {
@@ -370,8 +375,28 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   return RT_OK;
 }
 
+struct ProfScope {   // brackets one GEMM-shaped launch with events when profiling is on
+  GemmCtx& cx;
+  cudaStream_t st;
+  bool on;
+  ProfScope(GemmCtx& c, cudaStream_t s, double flops) : cx(c), st(s) {
+    on = cx.profile && cx.prof_used + 2 <= cx.prof_ev.size();
+    if (on) {
+      cudaEventRecord(cx.prof_ev[cx.prof_used], st);
+      cx.prof_flops += flops;
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(cx.prof_ev[cx.prof_used + 1], st);
+      cx.prof_used += 2;
+    }
+  }
+};
+
 int gemm(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   if (g.M <= 0 || g.N <= 0) return RT_OK;
+  ProfScope ps(cx, st, 2.0 * g.M * g.N * g.K);
   if (cx.mode == 1 && tc_eligible(g)) return gemm_tc(cx, st, g);
   return gemm_simt(cx, st, g);
 }
@@ -477,6 +502,7 @@ int conv_forward_tc(rt_learner* h, cudaStream_t st, const float* net, size_t i, 
   const CUtensorMap* tb = nullptr;
   RT_TRY(get_tmap(h->gx, net + L.w, L.K, L.f, L.K, rttc::BLOCK_K, BN, 0, &tb));
   h->gx.tc_launches++;
+  ProfScope ps(h->gx, st, 2.0 * a.M * a.N * a.K);
   if (i == 0) {
     if (BN == 32) return launch_conv_tc<32, 1>(tb, a, st);
     if (BN == 64) return launch_conv_tc<64, 1>(tb, a, st);
@@ -526,6 +552,7 @@ int conv_dw_tc(rt_learner* h, cudaStream_t st, size_t i, const void* xin, const 
   RT_TRY(get_tmap(h->gx, dy, L.f, a.P, L.f, 32, rttc::BLOCK_K, 1, &ta));
   dim3 grid(tiles, 1, splits);
   h->gx.tc_launches++;
+  ProfScope ps(h->gx, st, 2.0 * a.P * (double)L.f * L.K);
   if (i == 0) {
     if (BN == 32) RT_TRY((launch_convdw_tc<32, 1>(ta, a, grid, st)));
     else if (BN == 64) RT_TRY((launch_convdw_tc<64, 1>(ta, a, grid, st)));
@@ -594,8 +621,9 @@ int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* 
   // whole recurrence in one persistent launch when it fits (see rtk::k_lstm_seq_fwd)
   {
     const int ctas = U / rtk::lstm_seq::UPB;
-    size_t smem = ((size_t)4 * rtk::lstm_seq::UPB * U + (size_t)Beff * (U + rtk::lstm_seq::HPAD)) * sizeof(float);
-    if (h->lstm_persistent && timesteps > 1 && U % 4 == 0 && Beff <= 64 && ctas <= h->num_sms &&
+    size_t smem = ((size_t)4 * rtk::lstm_seq::UPB * U + (size_t)Beff * (U + rtk::lstm_seq::HPAD) +
+                   (size_t)rtk::lstm_seq::UPB * 64 * 4) * sizeof(float);
+    if (h->lstm_persistent && timesteps > 1 && U % 8 == 0 && Beff <= 64 && ctas <= h->num_sms &&
         smem <= 200 * 1024) {
       auto kern = Beff <= 32 ? rtk::k_lstm_seq_fwd<1> : rtk::k_lstm_seq_fwd<2>;
       RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -606,7 +634,7 @@ int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* 
                       (void*)&h->cprev, (void*)&timesteps, (void*)&Beff, (void*)&U,
                       (void*)&h->grid_barrier, (void*)&h->lstm_dbg};
       // cooperative launch: the runtime guarantees all CTAs are co-resident (grid barrier)
-      RT_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(128), args, smem, st));
+      RT_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(256), args, smem, st));
       rt::launch_counter()++;
       return RT_OK;
     }
@@ -658,7 +686,7 @@ int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float*
   g.bias = net + h->o_qb;
   g.relu = 1;
   RT_TRY(gemm(h->gx, st, g));
-  rtk::k_quantile_mul<<<cdiv(MQ * D, 256), 256, 0, st>>>(feat, h->phi, h->xq, MQ, D, Nq);
+  rtk::k_quantile_mul<<<cdiv(MQ * (D / 4), 256), 256, 0, st>>>(feat, h->phi, h->xq, MQ, D, Nq);
   RT_LAUNCH_CHECK();
   g = mk(h->xq, D, 0, net + h->o_fcw, D, 1, h->h1, F, (int)MQ, F, D);
   g.bias = net + h->o_fcb;
@@ -805,7 +833,7 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
         if (i > 0) {
           RT_TRY(gemm(h->gx, st, mk(dy, L.f, 0, net + L.w, L.K, 0, h->dcol_full, L.K, (int)(rows * opix), L.K, L.f)));
           size_t n_in = (size_t)rows * L.hin * L.win * L.cin;
-          rtk::k_col2im_nhwc<<<grid1d(n_in), 256, 0, st>>>(h->dcol_full, h->d_c[i - 1], rows, L.cin, L.hin,
+          rtk::k_col2im_nhwc<<<grid1d(n_in / 4), 256, 0, st>>>(h->dcol_full, h->d_c[i - 1], rows, L.cin, L.hin,
                                                           L.win, L.k, L.s, L.hout, L.wout);
           RT_LAUNCH_CHECK();
           rtk::k_relu_bwd_inplace<<<grid1d(n_in), 256, 0, st>>>(h->d_c[i - 1], h->c_out[i - 1], n_in);
@@ -842,8 +870,12 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
         RT_TRY(gemm(h->gx, st, mk(dy, L.f, 0, net + L.w, L.K, 0, h->dcol, L.K, (int)(rc * opix), L.K, L.f)));
         float* dxp = h->d_c[i - 1] + (size_t)r0 * Lp.hout * Lp.wout * Lp.f;
         size_t n_in = (size_t)rc * L.hin * L.win * L.cin;
-        rtk::k_col2im_nhwc<<<grid1d(n_in), 256, 0, st>>>(h->dcol, dxp, rc, L.cin, L.hin, L.win, L.k,
-                                                        L.s, L.hout, L.wout);
+        if (L.cin % 4 == 0)
+          rtk::k_col2im_nhwc<<<grid1d(n_in / 4), 256, 0, st>>>(h->dcol, dxp, rc, L.cin, L.hin, L.win, L.k,
+                                                              L.s, L.hout, L.wout);
+        else
+          rtk::k_col2im_nhwc_s<<<grid1d(n_in), 256, 0, st>>>(h->dcol, dxp, rc, L.cin, L.hin, L.win, L.k,
+                                                            L.s, L.hout, L.wout);
         RT_LAUNCH_CHECK();
         rtk::k_relu_bwd_inplace<<<grid1d(n_in), 256, 0, st>>>(
             dxp, h->c_out[i - 1] + (size_t)r0 * Lp.hout * Lp.wout * Lp.f, n_in);
@@ -1062,6 +1094,8 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->colsum_part, 2048 * maxN));
   RT_TRY(dalloc(h, &h->sumsq_part, 1024));
   RT_REQUIRE(h->A <= 32, "num_actions > 32 not supported by the fused head kernels");
+  RT_REQUIRE(h->F % 4 == 0 && h->D % 4 == 0, "fc_size and the quantile-layer width must be multiples of 4");
+
   RT_TRY(dalloc(h, &h->grid_barrier, 4));
   if (getenv("RT_DEBUG_TIMELINE")) RT_TRY(dalloc(h, &h->lstm_dbg, 4 * 256, "lstm_dbg"));
   {
@@ -1422,4 +1456,38 @@ extern "C" int rt_gemm_bench(int32_t mode, int32_t M, int32_t N, int32_t K, int3
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(cx.ws);
   return rc;
+}
+
+
+extern "C" int rt_learner_profile(rt_learner* h, int32_t enable) {
+  RT_REQUIRE(h, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  GemmCtx& cx = h->gx;
+  if (enable && cx.prof_ev.empty()) {
+    cx.prof_ev.resize(2 * 8192);
+    for (auto& e : cx.prof_ev) RT_CUDA(cudaEventCreate(&e));
+  }
+  cx.profile = enable != 0;
+  cx.prof_used = 0;
+  cx.prof_flops = 0;
+  return RT_OK;
+}
+
+extern "C" int rt_learner_gemm_time(rt_learner* h, double* total_ms, double* total_flops, int64_t* launches) {
+  RT_REQUIRE(h && total_ms && total_flops && launches, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  RT_CUDA(cudaDeviceSynchronize());
+  GemmCtx& cx = h->gx;
+  double t = 0;
+  for (size_t i = 0; i + 1 < cx.prof_used; i += 2) {
+    float ms = 0;
+    RT_CUDA(cudaEventElapsedTime(&ms, cx.prof_ev[i], cx.prof_ev[i + 1]));
+    t += ms;
+  }
+  *total_ms = t;
+  *total_flops = cx.prof_flops;
+  *launches = (int64_t)(cx.prof_used / 2);
+  cx.prof_used = 0;
+  cx.prof_flops = 0;
+  return RT_OK;
 }

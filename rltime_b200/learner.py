@@ -161,6 +161,15 @@ class DeviceLearner:
         _lib.check(self._lib.rt_learner_flat_buffer(self._h, which, C.byref(p), C.byref(n)))
         return _lib.as_tensor(p.value, (n.value,), "<f4", self.device)
 
+    def profile_gemms(self, enable=True):
+        _lib.check(self._lib.rt_learner_profile(self._h, 1 if enable else 0))
+
+    def gemm_time(self):
+        """(device ms, algorithmic flops, launches) of all GEMM-shaped launches since the last call."""
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        _lib.check(self._lib.rt_learner_gemm_time(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
+        return ms.value, fl.value, n.value
+
     def td_abs(self):
         p = C.c_void_p()
         _lib.check(self._lib.rt_learner_td_abs(self._h, C.byref(p)))
