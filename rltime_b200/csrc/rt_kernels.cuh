@@ -305,17 +305,19 @@ __global__ void k_lstm_cell(const float* __restrict__ xg, const float* __restric
 }
 
 // BPTT cell: dh = dout[t] + dh_carry; produces pre-activation gate grads and the carries.
+// `next_initials` = initials of step t+1: dh_carry arrives unmasked from (dgates[t+1] . W_hh) and
+// passes through step t+1's episode-reset mask here.
 __global__ void k_lstm_cell_bwd(const float* __restrict__ dout, const float* __restrict__ dh_carry,
                                 float* __restrict__ dc_carry, const float* __restrict__ gates,
                                 const float* __restrict__ c, const float* __restrict__ cprev,
-                                const float* __restrict__ initials, float* __restrict__ dgates,
-                                int B, int U) {
+                                const float* __restrict__ initials, const float* __restrict__ next_initials,
+                                float* __restrict__ dgates, int B, int U) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * U) return;
   int b = i / U, u = i - b * U;
   size_t g0 = (size_t)b * 4 * U + u;
   float gi = gates[g0], gf = gates[g0 + U], gg = gates[g0 + 2 * U], go = gates[g0 + 3 * U];
-  float dh = dout[i] + (dh_carry ? dh_carry[i] : 0.f);
+  float dh = dout[i] + (dh_carry ? dh_carry[i] * (1.f - next_initials[b]) : 0.f);
   float tc = tanhf(c[i]);
   float dc = dc_carry[i] + dh * go * (1.f - tc * tc);
   dgates[g0] = dc * gg * gi * (1.f - gi);
@@ -852,19 +854,23 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
         const float4* w1 = reinterpret_cast<const float4*>(Ws + ((size_t)1 * UPB + uw) * U) + khalf * KH4;
         const float4* w2 = reinterpret_cast<const float4*>(Ws + ((size_t)2 * UPB + uw) * U) + khalf * KH4;
         const float4* w3 = reinterpret_cast<const float4*>(Ws + ((size_t)3 * UPB + uw) * U) + khalf * KH4;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
+        // 16 independent accumulation chains (4 gates x 4 vector lanes): the dot products are
+        // latency-bound on 2 warps per scheduler otherwise
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+#pragma unroll 8
         for (int k = 0; k < KH4; ++k) {
           float4 h4 = hr[k];
           float4 p = w0[k];
-          a0 = fmaf(h4.x, p.x, a0); a0 = fmaf(h4.y, p.y, a0); a0 = fmaf(h4.z, p.z, a0); a0 = fmaf(h4.w, p.w, a0);
+          s0.x = fmaf(h4.x, p.x, s0.x); s0.y = fmaf(h4.y, p.y, s0.y); s0.z = fmaf(h4.z, p.z, s0.z); s0.w = fmaf(h4.w, p.w, s0.w);
           p = w1[k];
-          a1 = fmaf(h4.x, p.x, a1); a1 = fmaf(h4.y, p.y, a1); a1 = fmaf(h4.z, p.z, a1); a1 = fmaf(h4.w, p.w, a1);
+          s1.x = fmaf(h4.x, p.x, s1.x); s1.y = fmaf(h4.y, p.y, s1.y); s1.z = fmaf(h4.z, p.z, s1.z); s1.w = fmaf(h4.w, p.w, s1.w);
           p = w2[k];
-          a2 = fmaf(h4.x, p.x, a2); a2 = fmaf(h4.y, p.y, a2); a2 = fmaf(h4.z, p.z, a2); a2 = fmaf(h4.w, p.w, a2);
+          s2.x = fmaf(h4.x, p.x, s2.x); s2.y = fmaf(h4.y, p.y, s2.y); s2.z = fmaf(h4.z, p.z, s2.z); s2.w = fmaf(h4.w, p.w, s2.w);
           p = w3[k];
-          a3 = fmaf(h4.x, p.x, a3); a3 = fmaf(h4.y, p.y, a3); a3 = fmaf(h4.z, p.z, a3); a3 = fmaf(h4.w, p.w, a3);
+          s3.x = fmaf(h4.x, p.x, s3.x); s3.y = fmaf(h4.y, p.y, s3.y); s3.z = fmaf(h4.z, p.z, s3.z); s3.w = fmaf(h4.w, p.w, s3.w);
         }
+        float a0 = (s0.x + s0.y) + (s0.z + s0.w), a1 = (s1.x + s1.y) + (s1.z + s1.w);
+        float a2 = (s2.x + s2.y) + (s2.z + s2.w), a3 = (s3.x + s3.y) + (s3.z + s3.w);
         acc[j][0] = a0; acc[j][1] = a1; acc[j][2] = a2; acc[j][3] = a3;
         if (khalf == 1)
           *reinterpret_cast<float4*>(red + ((size_t)uw * 32 * BCH + b) * 4) = make_float4(a0, a1, a2, a3);

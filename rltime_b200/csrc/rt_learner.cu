@@ -318,8 +318,9 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   const int A_MN = g.transA ? 1 : 0, B_MN = g.transB ? 0 : 1;
   int BN = g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128);
   int tm = cdiv(g.M, rttc::BLOCK_M);
-  // few row tiles (e.g. the recurrent step, M = B): narrower N tiles put more SMs to work
-  while (BN > 32 && (long long)tm * cdiv(g.N, BN) < 74) BN >>= 1;
+  // few row tiles AND a short K loop (e.g. the recurrent step, M = B): narrower N tiles put
+  // more SMs to work; long-K products get their parallelism from split-K instead
+  while (BN > 32 && (long long)tm * cdiv(g.N, BN) < 74 && cdiv(g.K, rttc::BLOCK_K) < 64) BN >>= 1;
   int stages = BN == 128 ? 3 : 4;
   if (cx.force_bn) BN = cx.force_bn;
   if (cx.force_stages) stages = cx.force_stages;
@@ -785,14 +786,11 @@ int lstm_backward(rt_learner* h, cudaStream_t st, const float* net, const float*
     rtk::k_lstm_cell_bwd<<<nb, 256, 0, st>>>(
         h->dfeatq + ro * U, t == timesteps - 1 ? nullptr : h->dh_carry, h->dc_carry,
         h->gates + ro * 4 * U, h->c_all + ro * U, h->cprev + ro * U, initials + ro,
-        h->dgates + ro * 4 * U, Beff, U);
+        t == timesteps - 1 ? nullptr : initials + ro + Beff, h->dgates + ro * 4 * U, Beff, U);
     RT_LAUNCH_CHECK();
-    if (t > 0) {
+    if (t > 0)
       RT_TRY(gemm(h->gx, st, mk(h->dgates + ro * 4 * U, 4 * U, 0, net + h->o_whh, U, 0, h->dh_carry, U,
                             Beff, U, 4 * U)));
-      rtk::k_mask_rows<<<nb, 256, 0, st>>>(h->dh_carry, initials + ro, Beff, U);
-      RT_LAUNCH_CHECK();
-    }
   }
   RT_TRY(gemm(h->gx, st, mk(h->dgates, 4 * U, 1, h->hprev, U, 0, G + h->o_whh, U, 4 * U, U, rows)));
   RT_TRY(gemm(h->gx, st, mk(h->dgates, 4 * U, 1, feat, h->feat, 0, G + h->o_wih, h->feat, 4 * U, h->feat, rows)));
@@ -1013,7 +1011,8 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   h->M = h->T * h->B;
   h->MQ = h->M * h->Nq;
   int burn_rows = h->P * h->B;
-  h->max_rows = h->M > burn_rows ? h->M : burn_rows;
+  int shared_rows = h->M + h->n * h->B;   // online CNN shared by the selection and training passes
+  h->max_rows = shared_rows > burn_rows ? shared_rows : burn_rows;
   size_t rows = (size_t)h->max_rows;
   size_t maxcol = 0;
   for (size_t i = 0; i < h->conv.size(); ++i) {
@@ -1257,15 +1256,30 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   }
 
   // ---- bootstrap target (iqn.py:15-52): target net, then the action-selection net
+  bool shared_cnn = false;
   {
     StateView sv = view(P + n);
     int ts = rnn_boot ? T : 1;
     RT_TRY(trunk_forward(h, st, h->p[1], sv, M, ts, &feat));
     RT_TRY(heads_forward(h, st, h->p[1], feat, M, tau_seg[0]));
     RT_CUDA(cudaMemcpyAsync(h->tq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    const float* sel = h->td.double_q ? h->p[0] : h->p[1];
-    RT_TRY(trunk_forward(h, st, sel, sv, M, ts, &feat));
-    RT_TRY(heads_forward(h, st, sel, feat, M, tau_seg[1]));
+    if (!h->td.double_q) {
+      // same network, same states: only the quantile fractions differ -> reuse the whole trunk
+      RT_TRY(heads_forward(h, st, h->p[1], feat, M, tau_seg[1]));
+    } else {
+      // online net on target_states = rows [n, T+n) of the stack; the training forward below
+      // needs rows [0, T): run the online CNN ONCE over the T+n distinct rows and let both
+      // passes read their slice (saves (T-n)/(2T) of the online conv work)
+      StateView s0 = view(P);
+      RT_TRY(cnn_forward(h, st, h->p[0], s0.x, M + n * B));
+      shared_cnn = true;
+      const float* f = h->c_out.back() + (size_t)n * B * h->feat;
+      if (U) {
+        RT_TRY(lstm_forward(h, st, h->p[0], f, M, ts, sv.hx, sv.cx, sv.initials));
+        f = h->h_all;
+      }
+      RT_TRY(heads_forward(h, st, h->p[0], f, M, tau_seg[1]));
+    }
     RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
     size_t off = (size_t)P * B;
     rtk::k_iqn_target<<<cdiv(M, 128), 128, 0, st>>>(
@@ -1276,7 +1290,15 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
 
   // ---- training forward + loss (iqn.py:54-129)
   StateView svt = view(P);
-  RT_TRY(trunk_forward(h, st, h->p[0], svt, M, T, &feat));
+  if (shared_cnn) {
+    feat = h->c_out.back();
+    if (U) {
+      RT_TRY(lstm_forward(h, st, h->p[0], feat, M, T, svt.hx, svt.cx, svt.initials));
+      feat = h->h_all;
+    }
+  } else {
+    RT_TRY(trunk_forward(h, st, h->p[0], svt, M, T, &feat));
+  }
   RT_TRY(heads_forward(h, st, h->p[0], feat, M, tau_seg[2]));
   RT_CUDA(cudaMemcpyAsync(h->tau, tau_seg[2], (size_t)h->MQ * sizeof(float), cudaMemcpyDeviceToDevice, st));
   const long long* actions = (const long long*)b->policy_outputs[io->po_field_actions] + (size_t)P * B;
