@@ -776,6 +776,204 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvA
 }
 
 
+// Persistent implicit-GEMM forward convolution: same gather / math as k_conv_tc, restructured
+// like k_gemm_tc_p.  One CTA per SM loops over M tiles; EIGHT producer warps gather (4 x 16 B
+// per thread per k-block, twice the loads in flight of the one-tile kernel), the accumulator is
+// double-buffered in TMEM and four dedicated epilogue warps drain tile i while tile i+1 is
+// being gathered and multiplied.  (Measured on k_conv_tc: conv1 spends ~14 us per 128x32 tile,
+// almost all of it serialised gather latency and per-tile prologue.)
+constexpr int CONV_P_THREADS = 448;   // 8 gather + 1 TMA + 1 MMA + 4 epilogue warps
+
+template <int BN, int IN_U8, int STAGES>
+__global__ void __launch_bounds__(CONV_P_THREADS)
+k_conv_tc_p(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvArgs a) {
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
+  constexpr int B_BYTES = BN * BLOCK_K * 4;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int SCRATCH_OFFSET = STAGES * STAGE_BYTES;
+  constexpr int BAR_OFFSET = SCRATCH_OFFSET + 4 * 32 * 36 * 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = a.K / BLOCK_K;
+  const int tiles_n = (a.N + BN - 1) / BN;
+  const int tiles_m = (a.M + BLOCK_M - 1) / BLOCK_M;
+  const int total_tiles = tiles_n * tiles_m;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+
+  if (warp == 8 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 256 + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ---------------- A gather: thread t owns 16-byte chunk j = t % 8 of rows i*32 + t/8, i < 4
+    const int t = threadIdx.x;
+    const int j = t & 7;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BLOCK_M;
+      long long base[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int gm = m0 + i * 32 + (t >> 3);
+        if (gm < a.M) {
+          int ow = gm % a.OW;
+          int oh = (gm / a.OW) % a.OH;
+          long long img = gm / (a.OW * a.OH);
+          base[i] = IN_U8 ? (img * a.C * a.H + (long long)oh * a.S) * a.W + (long long)ow * a.S
+                          : ((img * a.H + (long long)oh * a.S) * a.W + (long long)ow * a.S) * a.C;
+        } else {
+          base[i] = -1;
+        }
+      }
+      auto gather = [&](int kb, float4* v) {
+        long long koff;
+        if (IN_U8) {
+          int k = kb * BLOCK_K + 4 * j;
+          int kw = k % a.KH, kh = (k / a.KH) % a.KH, c = k / (a.KH * a.KH);
+          koff = ((long long)c * a.H + kh) * a.W + kw;
+        } else {
+          int k = kb * BLOCK_K;
+          int c0 = k % a.C, tap = k / a.C;
+          int kw = tap % a.KH, kh = tap / a.KH;
+          koff = ((long long)kh * a.W + kw) * a.C + c0 + 4 * j;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (base[i] < 0) {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else if (IN_U8) {
+            uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(a.in) + base[i] + koff));
+            v[i] = make_float4(__fmul_rn((float)(u & 0xff), a.scale), __fmul_rn((float)((u >> 8) & 0xff), a.scale),
+                               __fmul_rn((float)((u >> 16) & 0xff), a.scale), __fmul_rn((float)(u >> 24), a.scale));
+          } else {
+            v[i] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(a.in) + base[i] + koff));
+          }
+        }
+      };
+      // two k-blocks of loads in flight ahead of the one being stored
+      float4 c0[4], c1[4], c2[4];
+      gather(0, c0);
+      if (num_kb > 1) gather(1, c1);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        if (kb + 2 < num_kb) gather(kb + 2, c2);
+        int s = it % STAGES;
+        uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int r = i * 32 + (t >> 3);
+          *reinterpret_cast<float4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = c0[i];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { c0[i] = c1[i]; c1[i] = c2[i]; }
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          int s = it % STAGES;
+          uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], B_BYTES);
+          tma_load_2d(&tmB, &full_bar[s], smem + s * STAGE_BYTES + A_BYTES, kb * BLOCK_K, n0);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BLOCK_M >> 4) << 24);
+      uint32_t it = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          int s = it % STAGES;
+          uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_tf32(d_tmem, make_smem_desc(sa + k * (UMMA_K * 4), 16, 1024, 2),
+                      make_smem_desc(sb + k * (UMMA_K * 4), 16, 1024, 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps 10..13: TMEM lane quarter = warp % 4
+    const int q = warp & 3;
+    float* stage = reinterpret_cast<float*>(smem + SCRATCH_OFFSET) + q * (32 * 36);
+    EpiArgs e;
+    e.C = a.out; e.ldc = a.N; e.M = a.M; e.N = a.N; e.alpha = 1.f; e.bias = a.bias; e.bias2 = nullptr;
+    e.relu = 1; e.mask = nullptr; e.ldmask = 0; e.accumulate = 0; e.round_tf32 = a.round_tf32; e.raw = 0;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
+      const int acc = lt & 1;
+      const EpiWarp ew = epi_begin(e, lane, m0 + q * 32, n0, BN);
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        if (c == BN / 32 - 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
+        }
+        if (n0 + c * 32 < a.N) epilogue_chunk(e, ew, v, stage, lane, m0 + q * 32, n0 + c * 32);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 9) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // --------------------------------------------------------- implicit-GEMM conv weight gradient
 // dW[f][k] = sum_p dy[p][f] * col[p][k] over a slab of output pixels p, without an im2col
 // buffer.  A = dy^T: MN-major from memory (TMA, 128B_ATOM_32B swizzle); B = col: MN-major,

@@ -769,54 +769,48 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 
 // xg: (T*B, 4U) = x W_ih^T + b_ih + b_hh;  W_hh: (4U, U);  hx, cx: (B, U) state of step 0;
 // initials: (T*B).  Outputs as in the stepwise path: gates (T*B,4U) activated, c_all, h_all,
-// hprev / cprev (masked carry-ins, needed by BPTT), all (T*B, U).  B <= 32 * BCH.
-// 256 threads: all 8 warps stage h (16 independent 16-byte loads each); warp w computes unit
-// (w & 3) over K-half (w >> 2); the upper half hands its partial sums over through smem.
-template <int BCH>
-__global__ void __launch_bounds__(256)
+// hprev / cprev (masked carry-ins, needed by BPTT), all (T*B, U).  B <= 32, U = 32 * KPL.
+//
+// Warp w owns hidden unit blockIdx.x*4 + w.  Its slice of W_hh (4 gate rows x U) lives in
+// REGISTERS for the whole sequence, lane l holding columns [l*KPL, (l+1)*KPL) of each row
+// (the shared-memory version was bound by 5 LDS.128 per 16 FMA).  Per step a lane forms the 4
+// partial dot products of every batch row over its K slice, then a 124-shuffle reduce-scatter
+// butterfly leaves lane b with the 4 complete gate sums of batch row b, which it finishes
+// (activations, cell update, outputs) while keeping c in a register.
+template <int KPL>
+__global__ void __launch_bounds__(128)
 k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, const float* __restrict__ hx,
                const float* __restrict__ cx, const float* __restrict__ initials,
                float* __restrict__ gates, float* __restrict__ c_all, float* __restrict__ h_all,
                float* __restrict__ hprev, float* __restrict__ cprev, int T, int B, int U,
                unsigned int* __restrict__ barrier, long long* __restrict__ dbg) {
   using namespace lstm_seq;
-  extern __shared__ float sm[];
-  float* Ws = sm;                          // [4 gates][UPB][U]
-  float* hs = sm + 4 * UPB * U;            // [B][U + HPAD]
+  extern __shared__ float hs[];            // [32][U + HPAD] masked h_{t-1} (rows >= B zero)
   const int HS = U + HPAD;
-  float* red = hs + (size_t)B * HS;        // [UPB][32 * BCH][4] partial sums of the upper K half
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int uw = warp & 3, khalf = warp >> 2;
-  const int unit = blockIdx.x * UPB + uw;
-  for (int i = threadIdx.x; i < 4 * UPB * (U / 4); i += blockDim.x) {
-    int row = i / (U / 4), k4 = i - row * (U / 4);
-    int g = row / UPB, u = row - g * UPB;
-    reinterpret_cast<float4*>(Ws)[i] =
-        reinterpret_cast<const float4*>(Whh + ((size_t)g * U + blockIdx.x * UPB + u) * U)[k4];
-  }
-  float c_reg[BCH];
+  const int unit = blockIdx.x * UPB + warp;
+  const int b = lane;                       // batch row this lane finishes
+  float w[4][KPL];
 #pragma unroll
-  for (int j = 0; j < BCH; ++j) {
-    int b = lane + 32 * j;
-    c_reg[j] = (khalf == 0 && b < B) ? cx[(size_t)b * U + unit] : 0.f;
-  }
-  const int KH4 = U / 8;   // float4 per K half
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int i = 0; i < KPL; i += 4) {
+      float4 t4 = *reinterpret_cast<const float4*>(Whh + ((size_t)g * U + unit) * U + lane * KPL + i);
+      w[g][i] = t4.x; w[g][i + 1] = t4.y; w[g][i + 2] = t4.z; w[g][i + 3] = t4.w;
+    }
+  for (int i = threadIdx.x; i < 32 * HS; i += blockDim.x) hs[i] = 0.f;
+  float c_reg = b < B ? cx[(size_t)b * U + unit] : 0.f;
+  __syncthreads();
   for (int t = 0; t < T; ++t) {
     const float* hsrc = t == 0 ? hx : h_all + (size_t)(t - 1) * B * U;
     const float* ini = initials + (size_t)t * B;
-    // input-projection terms of this step (independent of h): issue before anything waits
-    float xin[BCH][4];
-    if (khalf == 0) {
-#pragma unroll
-      for (int j = 0; j < BCH; ++j) {
-        int b = lane + 32 * j;
-        if (b < B) {
-          const float* xr = xg + ((size_t)t * B + b) * 4 * U + unit;
-          xin[j][0] = __ldg(xr); xin[j][1] = __ldg(xr + U); xin[j][2] = __ldg(xr + 2 * U); xin[j][3] = __ldg(xr + 3 * U);
-        }
-      }
+    float xin[4] = {0.f, 0.f, 0.f, 0.f};
+    if (b < B) {
+      const float* xr = xg + ((size_t)t * B + b) * 4 * U + unit;
+      xin[0] = __ldg(xr); xin[1] = __ldg(xr + U); xin[2] = __ldg(xr + 2 * U); xin[3] = __ldg(xr + 3 * U);
     }
-    // stage masked h_{t-1}
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 0] = clock64();
+    // stage masked h_{t-1}: 16 independent 16-byte loads in flight per thread
     {
       const int total = B * (U / 4);
       for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * 16) {
@@ -825,86 +819,80 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
         for (int q = 0; q < 16; ++q) {
           int i = i0 + q * blockDim.x;
           if (i < total) {
-            int b = i / (U / 4), k4 = i - b * (U / 4);
-            v[q] = __ldcg(reinterpret_cast<const float4*>(hsrc + (size_t)b * U) + k4);  // L2: never a stale L1 line
+            int bb = i / (U / 4), k4 = i - bb * (U / 4);
+            v[q] = __ldcg(reinterpret_cast<const float4*>(hsrc + (size_t)bb * U) + k4);   // L2: never a stale L1 line
           }
         }
+        if (dbg && blockIdx.x == 0 && threadIdx.x == 0 && i0 == 0) dbg[8 * t + 1] = clock64();
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           int i = i0 + q * blockDim.x;
           if (i < total) {
-            int b = i / (U / 4), k4 = i - b * (U / 4);
-            float keep = 1.f - ini[b];
+            int bb = i / (U / 4), k4 = i - bb * (U / 4);
+            float keep = 1.f - ini[bb];
             v[q].x *= keep; v[q].y *= keep; v[q].z *= keep; v[q].w *= keep;
-            *reinterpret_cast<float4*>(hs + (size_t)b * HS + 4 * k4) = v[q];
+            *reinterpret_cast<float4*>(hs + (size_t)bb * HS + 4 * k4) = v[q];
           }
         }
       }
     }
     __syncthreads();
-    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4 * t + 0] = clock64();
-    float acc[BCH][4];
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 2] = clock64();
+    // partial dot products: part[bb*4 + g] = sum_{k in this lane's slice} h[bb][k] * W[g][k]
+    float part[128];
 #pragma unroll
-    for (int j = 0; j < BCH; ++j) {
-      int b = lane + 32 * j;
-      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-      if (b < B) {
-        const float4* hr = reinterpret_cast<const float4*>(hs + (size_t)b * HS) + khalf * KH4;
-        const float4* w0 = reinterpret_cast<const float4*>(Ws + ((size_t)0 * UPB + uw) * U) + khalf * KH4;
-        const float4* w1 = reinterpret_cast<const float4*>(Ws + ((size_t)1 * UPB + uw) * U) + khalf * KH4;
-        const float4* w2 = reinterpret_cast<const float4*>(Ws + ((size_t)2 * UPB + uw) * U) + khalf * KH4;
-        const float4* w3 = reinterpret_cast<const float4*>(Ws + ((size_t)3 * UPB + uw) * U) + khalf * KH4;
-        // 16 independent accumulation chains (4 gates x 4 vector lanes): the dot products are
-        // latency-bound on 2 warps per scheduler otherwise
-        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
-#pragma unroll 8
-        for (int k = 0; k < KH4; ++k) {
-          float4 h4 = hr[k];
-          float4 p = w0[k];
-          s0.x = fmaf(h4.x, p.x, s0.x); s0.y = fmaf(h4.y, p.y, s0.y); s0.z = fmaf(h4.z, p.z, s0.z); s0.w = fmaf(h4.w, p.w, s0.w);
-          p = w1[k];
-          s1.x = fmaf(h4.x, p.x, s1.x); s1.y = fmaf(h4.y, p.y, s1.y); s1.z = fmaf(h4.z, p.z, s1.z); s1.w = fmaf(h4.w, p.w, s1.w);
-          p = w2[k];
-          s2.x = fmaf(h4.x, p.x, s2.x); s2.y = fmaf(h4.y, p.y, s2.y); s2.z = fmaf(h4.z, p.z, s2.z); s2.w = fmaf(h4.w, p.w, s2.w);
-          p = w3[k];
-          s3.x = fmaf(h4.x, p.x, s3.x); s3.y = fmaf(h4.y, p.y, s3.y); s3.z = fmaf(h4.z, p.z, s3.z); s3.w = fmaf(h4.w, p.w, s3.w);
+    for (int bb = 0; bb < 32; ++bb) {
+      float hv[KPL];
+#pragma unroll
+      for (int i = 0; i < KPL; i += 4) {
+        float4 t4 = *reinterpret_cast<const float4*>(hs + (size_t)bb * HS + lane * KPL + i);
+        hv[i] = t4.x; hv[i + 1] = t4.y; hv[i + 2] = t4.z; hv[i + 3] = t4.w;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < KPL; i += 2) {
+          a0 = fmaf(hv[i], w[g][i], a0);
+          a1 = fmaf(hv[i + 1], w[g][i + 1], a1);
         }
-        float a0 = (s0.x + s0.y) + (s0.z + s0.w), a1 = (s1.x + s1.y) + (s1.z + s1.w);
-        float a2 = (s2.x + s2.y) + (s2.z + s2.w), a3 = (s3.x + s3.y) + (s3.z + s3.w);
-        acc[j][0] = a0; acc[j][1] = a1; acc[j][2] = a2; acc[j][3] = a3;
-        if (khalf == 1)
-          *reinterpret_cast<float4*>(red + ((size_t)uw * 32 * BCH + b) * 4) = make_float4(a0, a1, a2, a3);
+        part[bb * 4 + g] = a0 + a1;
       }
     }
-    __syncthreads();
-    if (khalf == 0) {
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 3] = clock64();
+    // reduce-scatter butterfly over the 32 lanes: lane l ends with indices 4l .. 4l+3
 #pragma unroll
-      for (int j = 0; j < BCH; ++j) {
-        int b = lane + 32 * j;
-        if (b < B) {
-          float4 hi = *reinterpret_cast<const float4*>(red + ((size_t)uw * 32 * BCH + b) * 4);
-          size_t row = (size_t)t * B + b;
-          float gi = sigmoidf_(xin[j][0] + (acc[j][0] + hi.x));
-          float gf = sigmoidf_(xin[j][1] + (acc[j][1] + hi.y));
-          float gg = tanhf(xin[j][2] + (acc[j][2] + hi.z));
-          float go = sigmoidf_(xin[j][3] + (acc[j][3] + hi.w));
-          float keep = 1.f - ini[b];
-          float cp = c_reg[j] * keep;
-          float c = gf * cp + gi * gg;
-          float h = go * tanhf(c);
-          c_reg[j] = c;
-          float* gr = gates + row * 4 * U + unit;
-          gr[0] = gi; gr[U] = gf; gr[2 * U] = gg; gr[3 * U] = go;
-          c_all[row * U + unit] = c;
-          h_all[row * U + unit] = h;
-          cprev[row * U + unit] = cp;
-          hprev[row * U + unit] = hs[(size_t)b * HS + unit];
-        }
+    for (int o = 16, n = 128; o >= 1; o >>= 1, n >>= 1) {
+      const int half = n >> 1;
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        float send = up ? part[i] : part[i + half];
+        float keepv = up ? part[i + half] : part[i];
+        part[i] = keepv + __shfl_xor_sync(0xffffffffu, send, o);
       }
     }
-    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4 * t + 1] = clock64();
+    if (b < B) {
+      size_t row = (size_t)t * B + b;
+      float gi = sigmoidf_(xin[0] + part[0]);
+      float gf = sigmoidf_(xin[1] + part[1]);
+      float gg = tanhf(xin[2] + part[2]);
+      float go = sigmoidf_(xin[3] + part[3]);
+      float keep = 1.f - ini[b];
+      float cp = c_reg * keep;
+      float c = gf * cp + gi * gg;
+      float h = go * tanhf(c);
+      c_reg = c;
+      float* gr = gates + row * 4 * U + unit;
+      gr[0] = gi; gr[U] = gf; gr[2 * U] = gg; gr[3 * U] = go;
+      c_all[row * U + unit] = c;
+      h_all[row * U + unit] = h;
+      cprev[row * U + unit] = cp;
+      hprev[row * U + unit] = hs[(size_t)b * HS + unit];
+    }
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 4] = clock64();
     if (t + 1 < T) lstm_seq::grid_barrier(barrier, (unsigned int)(t + 1) * gridDim.x);
-    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[4 * t + 2] = clock64();
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 5] = clock64();
   }
 }
 

@@ -480,6 +480,22 @@ int launch_conv_tc(const CUtensorMap* tb, const rttc::ConvArgs& a, cudaStream_t 
   return RT_OK;
 }
 
+template <int BN, int IN_U8>
+int launch_conv_tc_p(const CUtensorMap* tb, const rttc::ConvArgs& a, int ctas, cudaStream_t st) {
+  constexpr int STAGE_BYTES = rttc::BLOCK_M * rttc::BLOCK_K * 4 + BN * rttc::BLOCK_K * 4;
+  constexpr int STAGES = (160 * 1024) / STAGE_BYTES >= 6 ? 6 : (160 * 1024) / STAGE_BYTES;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 4 * 32 * 36 * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+  auto kern = rttc::k_conv_tc_p<BN, IN_U8, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  kern<<<ctas, rttc::CONV_P_THREADS, SMEM, st>>>(*tb, a);
+  RT_LAUNCH_CHECK();
+  return RT_OK;
+}
+
 // Implicit-GEMM forward convolution (no im2col buffer) when the layer shape allows it.
 bool conv_tc_eligible(const rt_learner* h, size_t i, const void* xin) {
   const ConvL& L = h->conv[i];
@@ -504,6 +520,18 @@ int conv_forward_tc(rt_learner* h, cudaStream_t st, const float* net, size_t i, 
   RT_TRY(get_tmap(h->gx, net + L.w, L.K, L.f, L.K, rttc::BLOCK_K, BN, 0, &tb));
   h->gx.tc_launches++;
   ProfScope ps(h->gx, st, 2.0 * a.M * a.N * a.K);
+  const long long tiles = (long long)cdiv(a.M, rttc::BLOCK_M) * cdiv(a.N, BN);
+  if (h->gx.persistent && tiles > h->num_sms) {
+    const int ctas = h->num_sms;
+    if (i == 0) {
+      if (BN == 32) return launch_conv_tc_p<32, 1>(tb, a, ctas, st);
+      if (BN == 64) return launch_conv_tc_p<64, 1>(tb, a, ctas, st);
+      return launch_conv_tc_p<128, 1>(tb, a, ctas, st);
+    }
+    if (BN == 32) return launch_conv_tc_p<32, 0>(tb, a, ctas, st);
+    if (BN == 64) return launch_conv_tc_p<64, 0>(tb, a, ctas, st);
+    return launch_conv_tc_p<128, 0>(tb, a, ctas, st);
+  }
   if (i == 0) {
     if (BN == 32) return launch_conv_tc<32, 1>(tb, a, st);
     if (BN == 64) return launch_conv_tc<64, 1>(tb, a, st);
@@ -622,11 +650,12 @@ int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* 
   // whole recurrence in one persistent launch when it fits (see rtk::k_lstm_seq_fwd)
   {
     const int ctas = U / rtk::lstm_seq::UPB;
-    size_t smem = ((size_t)4 * rtk::lstm_seq::UPB * U + (size_t)Beff * (U + rtk::lstm_seq::HPAD) +
-                   (size_t)rtk::lstm_seq::UPB * 64 * 4) * sizeof(float);
-    if (h->lstm_persistent && timesteps > 1 && U % 8 == 0 && Beff <= 64 && ctas <= h->num_sms &&
-        smem <= 200 * 1024) {
-      auto kern = Beff <= 32 ? rtk::k_lstm_seq_fwd<1> : rtk::k_lstm_seq_fwd<2>;
+    size_t smem = (size_t)32 * (U + rtk::lstm_seq::HPAD) * sizeof(float);
+    if (h->lstm_persistent && timesteps > 1 && (U == 512 || U == 256 || U == 128) && Beff <= 32 &&
+        ctas <= h->num_sms) {
+      void (*kern)(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
+                   float*, float*, int, int, int, unsigned int*, long long*) =
+          U == 512 ? rtk::k_lstm_seq_fwd<16> : (U == 256 ? rtk::k_lstm_seq_fwd<8> : rtk::k_lstm_seq_fwd<4>);
       RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       RT_CUDA(cudaMemsetAsync(h->grid_barrier, 0, sizeof(unsigned int), st));
       const float* whh = net + h->o_whh;
@@ -635,7 +664,7 @@ int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* 
                       (void*)&h->cprev, (void*)&timesteps, (void*)&Beff, (void*)&U,
                       (void*)&h->grid_barrier, (void*)&h->lstm_dbg};
       // cooperative launch: the runtime guarantees all CTAs are co-resident (grid barrier)
-      RT_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(256), args, smem, st));
+      RT_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(128), args, smem, st));
       rt::launch_counter()++;
       return RT_OK;
     }
@@ -1096,7 +1125,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_REQUIRE(h->F % 4 == 0 && h->D % 4 == 0, "fc_size and the quantile-layer width must be multiples of 4");
 
   RT_TRY(dalloc(h, &h->grid_barrier, 4));
-  if (getenv("RT_DEBUG_TIMELINE")) RT_TRY(dalloc(h, &h->lstm_dbg, 4 * 256, "lstm_dbg"));
+  if (getenv("RT_DEBUG_TIMELINE")) RT_TRY(dalloc(h, &h->lstm_dbg, 8 * 256, "lstm_dbg"));
   {
     cudaDeviceProp prop;
     RT_CUDA(cudaGetDeviceProperties(&prop, device));

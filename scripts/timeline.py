@@ -30,11 +30,11 @@ torch.cuda.synchronize()
 import ctypes as C
 p, cnt = C.c_void_p(), C.c_int64()
 _lib.check(L._lib.rt_learner_debug_tensor(L._h, b"lstm_dbg", C.byref(p), C.byref(cnt)))
-d = _lib.as_tensor(p.value, (256, 4), "<i8", L.device).cpu().numpy()[:T]
-t0 = d[0, 0]
-print("LSTM persistent kernel, CTA 0, cycles: step | staged | computed(+writes) | barrier passed")
-prev = t0
+d = _lib.as_tensor(p.value, (256, 8), "<i8", L.device).cpu().numpy()[:T]
+print("LSTM persistent kernel, CTA 0, cycles per phase")
+prev = d[0, 0]
 for t in range(T):
-    print("%2d  stage %6d  compute %6d  barrier %6d   (step total %6d)" % (
-        t, d[t, 0] - prev, d[t, 1] - d[t, 0], d[t, 2] - d[t, 1], d[t, 2] - prev))
-    prev = d[t, 2]
+    print("%2d  xin-issue %5d | h-loads-landed %6d | staged+sync %6d | dots %6d | reduce+cell+stores %6d | "
+          "grid-barrier %6d | step %6d" % (t, d[t, 0] - prev, d[t, 1] - d[t, 0], d[t, 2] - d[t, 1],
+                                           d[t, 3] - d[t, 2], d[t, 4] - d[t, 3], d[t, 5] - d[t, 4], d[t, 5] - prev))
+    prev = d[t, 5]
