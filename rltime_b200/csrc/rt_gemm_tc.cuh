@@ -989,8 +989,10 @@ struct ConvDwArgs {
   float scale;
 };
 
+constexpr int CONVDW_THREADS = 320;   // 8 gather (first 4 also epilogue) + 1 TMA + 1 MMA warps
+
 template <int BN, int IN_U8, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS)
+__global__ void __launch_bounds__(CONVDW_THREADS)
 k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ ConvDwArgs a) {
   constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;          // 4 atoms of dy^T (only ceil(F/32) filled)
   constexpr int B_BYTES = BN * BLOCK_K * 4;
@@ -1011,16 +1013,16 @@ k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Con
   const int num_kb = kb1 - kb0;
   const int a_atoms = (a.F + 31) / 32;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 128 + 1);
+      mbar_init(&full_bar[s], 256 + 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)(BN < 32 ? 32 : BN))
                  : "memory");
@@ -1039,9 +1041,9 @@ k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Con
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ---------------- B gather: thread t owns 16-byte chunk j = t % 8 of pixel rows t/8 and
-    // t/8 + 16 in each of the BN/32 atoms
+  if (warp < 8) {
+    // ---------------- B gather (8 warps): thread t owns 16-byte chunk j = t % 8 of pixel row
+    // t/8 in each of the BN/32 atoms
     const int t = threadIdx.x;
     const int j = t & 7;
     constexpr int NAT = BN / 32;
@@ -1062,9 +1064,9 @@ k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Con
       }
     }
     auto gather = [&](int kb, float4* v) {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        int p = (kb0 + kb) * BLOCK_K + (t >> 3) + 16 * half;
+      {
+        const int half = 0;
+        int p = (kb0 + kb) * BLOCK_K + (t >> 3);
         long long base = -1;
         if (p < a.P) {
           int ow = p % a.OW;
@@ -1089,17 +1091,18 @@ k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Con
         }
       }
     };
-    float4 cur[2 * NAT], nxt[2 * NAT];
+    float4 cur[NAT], nx1[NAT], nx2[NAT];
     if (num_kb > 0) gather(0, cur);
+    if (num_kb > 1) gather(1, nx1);
     for (int kb = 0; kb < num_kb; ++kb) {
-      if (kb + 1 < num_kb) gather(kb + 1, nxt);
+      if (kb + 2 < num_kb) gather(kb + 2, nx2);
       int s = kb % STAGES;
       uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(&empty_bar[s], ph ^ 1);
       uint8_t* sb = smem + s * STAGE_BYTES + A_BYTES;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        int r = (t >> 3) + 16 * half;
+      {
+        const int half = 0;
+        int r = (t >> 3);
 #pragma unroll
         for (int at = 0; at < NAT; ++at)
           // 128B_BASE32B swizzle: 32-byte chunk index XOR (row % 4), 16-byte half preserved
@@ -1109,8 +1112,9 @@ k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Con
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
 #pragma unroll
-      for (int q = 0; q < 2 * NAT; ++q) cur[q] = nxt[q];
+      for (int q = 0; q < NAT; ++q) { cur[q] = nx1[q]; nx1[q] = nx2[q]; }
     }
+    if (warp < 4) {
     // ---------------- epilogue: rows < F of the accumulator -> raw split-K partial
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1127,7 +1131,8 @@ k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Con
       if (warp * 32 < a.F && n0 + c * 32 < a.K) epilogue_chunk(e, ew, v, stage, lane, warp * 32, n0 + c * 32);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  } else if (warp == 4) {
+    }
+  } else if (warp == 8) {
     if (lane == 0) {
       for (int kb = 0; kb < num_kb; ++kb) {
         int s = kb % STAGES;
@@ -1160,7 +1165,7 @@ k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Con
     }
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)(BN < 32 ? 32 : BN))

@@ -778,7 +778,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 // butterfly leaves lane b with the 4 complete gate sums of batch row b, which it finishes
 // (activations, cell update, outputs) while keeping c in a register.
 template <int KPL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, const float* __restrict__ hx,
                const float* __restrict__ cx, const float* __restrict__ initials,
                float* __restrict__ gates, float* __restrict__ c_all, float* __restrict__ h_all,
@@ -788,24 +788,30 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
   extern __shared__ float hs[];            // [32][U + HPAD] masked h_{t-1} (rows >= B zero)
   const int HS = U + HPAD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int unit = blockIdx.x * UPB + warp;
+  const bool worker = warp < UPB;           // warps UPB..7 only help staging h
+  const int unit = blockIdx.x * UPB + (warp & (UPB - 1));
   const int b = lane;                       // batch row this lane finishes
+  // lane l owns the 16-byte chunks {c*128 + 4l .. +3}, c < KPL/4, of every row: a warp's
+  // LDS.128 of one chunk index then reads 512 contiguous bytes (conflict-free)
   float w[4][KPL];
+  if (worker) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g)
+    for (int g = 0; g < 4; ++g)
 #pragma unroll
-    for (int i = 0; i < KPL; i += 4) {
-      float4 t4 = *reinterpret_cast<const float4*>(Whh + ((size_t)g * U + unit) * U + lane * KPL + i);
-      w[g][i] = t4.x; w[g][i + 1] = t4.y; w[g][i + 2] = t4.z; w[g][i + 3] = t4.w;
-    }
+      for (int i = 0; i < KPL; i += 4) {
+        float4 t4 = *reinterpret_cast<const float4*>(Whh + ((size_t)g * U + unit) * U + (i / 4) * 128 + lane * 4);
+        w[g][i] = t4.x; w[g][i + 1] = t4.y; w[g][i + 2] = t4.z; w[g][i + 3] = t4.w;
+      }
+  }
   for (int i = threadIdx.x; i < 32 * HS; i += blockDim.x) hs[i] = 0.f;
-  float c_reg = b < B ? cx[(size_t)b * U + unit] : 0.f;
+  float c_reg = (worker && b < B) ? cx[(size_t)b * U + unit] : 0.f;
   __syncthreads();
   for (int t = 0; t < T; ++t) {
     const float* hsrc = t == 0 ? hx : h_all + (size_t)(t - 1) * B * U;
     const float* ini = initials + (size_t)t * B;
     float xin[4] = {0.f, 0.f, 0.f, 0.f};
-    if (b < B) {
+    const float keep_b = b < B ? 1.f - ini[b] : 0.f;
+    if (worker && b < B) {
       const float* xr = xg + ((size_t)t * B + b) * 4 * U + unit;
       xin[0] = __ldg(xr); xin[1] = __ldg(xr + U); xin[2] = __ldg(xr + 2 * U); xin[3] = __ldg(xr + 3 * U);
     }
@@ -829,8 +835,7 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
           int i = i0 + q * blockDim.x;
           if (i < total) {
             int bb = i / (U / 4), k4 = i - bb * (U / 4);
-            float keep = 1.f - ini[bb];
-            v[q].x *= keep; v[q].y *= keep; v[q].z *= keep; v[q].w *= keep;
+            // unmasked copy: (h * keep) . w == keep * (h . w), the mask is applied to the sums
             *reinterpret_cast<float4*>(hs + (size_t)bb * HS + 4 * k4) = v[q];
           }
         }
@@ -838,6 +843,7 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
     }
     __syncthreads();
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 2] = clock64();
+    if (worker) {
     // partial dot products: part[bb*4 + g] = sum_{k in this lane's slice} h[bb][k] * W[g][k]
     float part[128];
 #pragma unroll
@@ -845,7 +851,7 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
       float hv[KPL];
 #pragma unroll
       for (int i = 0; i < KPL; i += 4) {
-        float4 t4 = *reinterpret_cast<const float4*>(hs + (size_t)bb * HS + lane * KPL + i);
+        float4 t4 = *reinterpret_cast<const float4*>(hs + (size_t)bb * HS + (i / 4) * 128 + lane * 4);
         hv[i] = t4.x; hv[i + 1] = t4.y; hv[i + 2] = t4.z; hv[i + 3] = t4.w;
       }
 #pragma unroll
@@ -874,11 +880,11 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
     }
     if (b < B) {
       size_t row = (size_t)t * B + b;
-      float gi = sigmoidf_(xin[0] + part[0]);
-      float gf = sigmoidf_(xin[1] + part[1]);
-      float gg = tanhf(xin[2] + part[2]);
-      float go = sigmoidf_(xin[3] + part[3]);
-      float keep = 1.f - ini[b];
+      float gi = sigmoidf_(xin[0] + keep_b * part[0]);
+      float gf = sigmoidf_(xin[1] + keep_b * part[1]);
+      float gg = tanhf(xin[2] + keep_b * part[2]);
+      float go = sigmoidf_(xin[3] + keep_b * part[3]);
+      float keep = keep_b;
       float cp = c_reg * keep;
       float c = gf * cp + gi * gg;
       float h = go * tanhf(c);
@@ -888,8 +894,9 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
       c_all[row * U + unit] = c;
       h_all[row * U + unit] = h;
       cprev[row * U + unit] = cp;
-      hprev[row * U + unit] = hs[(size_t)b * HS + unit];
+      hprev[row * U + unit] = hs[(size_t)b * HS + unit] * keep;
     }
+    }  // worker
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 4] = clock64();
     if (t + 1 < T) lstm_seq::grid_barrier(barrier, (unsigned int)(t + 1) * gridDim.x);
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 5] = clock64();

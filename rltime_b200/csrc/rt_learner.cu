@@ -133,6 +133,7 @@ struct rt_learner {
   int lstm_persistent = 1;
   int conv_implicit = 1;
   int conv_implicit_bwd = 1;
+  int conv_persistent = 0;
   float* dcol_full = nullptr;
   int num_sms = 148;
   double* sumsq_part = nullptr;
@@ -521,7 +522,9 @@ int conv_forward_tc(rt_learner* h, cudaStream_t st, const float* net, size_t i, 
   h->gx.tc_launches++;
   ProfScope ps(h->gx, st, 2.0 * a.M * a.N * a.K);
   const long long tiles = (long long)cdiv(a.M, rttc::BLOCK_M) * cdiv(a.N, BN);
-  if (h->gx.persistent && tiles > h->num_sms) {
+  // measured: for the gather-bound convolutions 2-3 one-tile CTAs per SM beat one persistent
+  // CTA (conv1 103 vs 120 us, conv2/3 34 vs 50 us), so the persistent form is opt-in
+  if (h->conv_persistent && tiles > h->num_sms) {
     const int ctas = h->num_sms;
     if (i == 0) {
       if (BN == 32) return launch_conv_tc_p<32, 1>(tb, a, ctas, st);
@@ -553,7 +556,7 @@ int launch_convdw_tc(const CUtensorMap* ta, const rttc::ConvDwArgs& a, dim3 grid
     RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  kern<<<grid, rttc::NUM_THREADS, SMEM, st>>>(*ta, a);
+  kern<<<grid, rttc::CONVDW_THREADS, SMEM, st>>>(*ta, a);
   RT_LAUNCH_CHECK();
   return RT_OK;
 }
@@ -664,7 +667,7 @@ int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* 
                       (void*)&h->cprev, (void*)&timesteps, (void*)&Beff, (void*)&U,
                       (void*)&h->grid_barrier, (void*)&h->lstm_dbg};
       // cooperative launch: the runtime guarantees all CTAs are co-resident (grid barrier)
-      RT_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(128), args, smem, st));
+      RT_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(256), args, smem, st));
       rt::launch_counter()++;
       return RT_OK;
     }
@@ -1135,6 +1138,8 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     if (e && e[0] == '1') h->lstm_persistent = 0;
     e = getenv("RT_CONV_IM2COL");
     if (e && e[0] == '1') h->conv_implicit = 0;
+    e = getenv("RT_CONV_PERSISTENT");
+    if (e && e[0] == '1') h->conv_persistent = 1;
     e = getenv("RT_CONV_BWD_IM2COL");
     if (e && e[0] == '1') h->conv_implicit_bwd = 0;
   }
