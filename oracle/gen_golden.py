@@ -23,7 +23,9 @@ def make_reference_history(p):
     from rltime.history.prioritized_replay_history import PrioritizedReplayHistoryBuffer
     from rltime.history.replay_history import ReplayHistoryBuffer
     from rltime.general.backend import StateStore
-    cls = PrioritizedReplayHistoryBuffer if p["kind"] == "per" else ReplayHistoryBuffer
+    from rltime.history.online_history import OnlineHistoryBuffer
+    cls = {"per": PrioritizedReplayHistoryBuffer, "uniform": ReplayHistoryBuffer,
+           "online": OnlineHistoryBuffer}[p["kind"]]
     h = cls(**sc.history_kwargs(p), discount_function=sc.discount_function,
             state_store=StateStore("cpu"))
     if p["kind"] == "per":

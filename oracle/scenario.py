@@ -43,6 +43,13 @@ SCENARIOS = {
     "uniform_seq": dict(kind="uniform", size=700, envs=4, T=5, P=2, n=2, B=6, iters=200,
                         frame=(2, 4, 4), units=3, actions=3, done_mode="bernoulli",
                         done_p=0.05, feed="lockstep"),
+    # online n-step buffer (rltime/history/online_history.py): fixed_target, round-robin over envs
+    "online_small": dict(kind="online", size=0, envs=4, T=5, P=0, n=5, B=4, iters=120,
+                         frame=(2, 4, 4), units=3, actions=3, done_mode="bernoulli", done_p=0.1,
+                         feed="lockstep", feed_steps=(1, 4)),
+    "online_async": dict(kind="online", size=0, envs=3, T=4, P=0, n=4, B=5, iters=150,
+                         frame=(1, 3, 3), units=0, actions=2, done_mode="bernoulli", done_p=0.15,
+                         feed="async", feed_steps=(1, 5), max_delayed_steps=9),
     "uniform_async": dict(kind="uniform", size=300, envs=3, T=1, P=0, n=3, B=7, iters=200,
                           frame=(1, 3, 3), units=0, actions=4, done_mode="bernoulli",
                           done_p=0.1, feed="async"),
@@ -58,6 +65,11 @@ def discount_function(nstep, reward, policy_output):
 
 
 def history_kwargs(p):
+    if p["kind"] == "online":
+        kw = dict(nstep_target=p["n"], nstep_train=p["T"], prefix_steps=p["P"])
+        if "max_delayed_steps" in p:
+            kw["max_delayed_steps"] = p["max_delayed_steps"]
+        return kw
     kw = dict(size=p["size"], train_frequency=None, nstep_target=p["n"],
               nstep_train=p["T"], prefix_steps=p["P"])
     if p["kind"] == "per":

@@ -44,3 +44,15 @@ def test_init_params_follow_reference_scheme():
     assert float(p["model.layers.0.layers.0.weight"].abs().max()) <= (1.0 / 36) ** 0.5
     assert float(p["model.layers.1.lstm_cell.weight_hh"].abs().max()) <= 0.5
     assert 0 < float(p["model.layers.1.lstm_cell.bias_ih"].abs().max()) <= 0.5
+
+
+@pytest.mark.parametrize("name", ["online_small", "online_async"])
+def test_online_buffer_matches_reference_golden(name):
+    """The host-side OnlineHistoryBuffer (row a11) against traces of the reference's class."""
+    from oracle import scenario as sc
+    from rltime_b200.history import OnlineHistoryBuffer
+    from tests.util import assert_trace_equal, load_golden
+    p = sc.SCENARIOS[name]
+    h = OnlineHistoryBuffer(**sc.history_kwargs(p), discount_function=sc.discount_function)
+    trace = sc.run_scenario(name, h, lambda hh: None)
+    assert_trace_equal(trace, load_golden("replay_%s.npz" % name))

@@ -8,7 +8,8 @@ from tests.util import assert_trace_equal, load_golden
 
 
 def _make(p):
-    cls = ro.PrioritizedReplayOracle if p["kind"] == "per" else ro.ReplayOracle
+    cls = {"per": ro.PrioritizedReplayOracle, "uniform": ro.ReplayOracle,
+           "online": ro.OnlineOracle}[p["kind"]]
     return cls(**sc.history_kwargs(p), discount_function=sc.discount_function)
 
 
