@@ -771,52 +771,59 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 // initials: (T*B).  Outputs as in the stepwise path: gates (T*B,4U) activated, c_all, h_all,
 // hprev / cprev (masked carry-ins, needed by BPTT), all (T*B, U).  B <= 32, U = 32 * KPL.
 //
-// Warp w owns hidden unit blockIdx.x*4 + w.  Its slice of W_hh (4 gate rows x U) lives in
-// REGISTERS for the whole sequence, lane l holding columns [l*KPL, (l+1)*KPL) of each row
-// (the shared-memory version was bound by 5 LDS.128 per 16 FMA).  Per step a lane forms the 4
-// partial dot products of every batch row over its K slice, then a 124-shuffle reduce-scatter
-// butterfly leaves lane b with the 4 complete gate sums of batch row b, which it finishes
-// (activations, cell update, outputs) while keeping c in a register.
-template <int KPL>
+// Warps w and w+4 own hidden unit blockIdx.x*4 + (w & 3), each one half of K.  Their slice
+// of W_hh (4 gate rows x U/2) lives in REGISTERS for the whole sequence (the shared-memory
+// version was bound by 5 LDS.128 per 16 FMA).  Per step a lane forms the 4 partial dot products
+// of every batch row over its K slice, a 124-shuffle reduce-scatter butterfly leaves lane b with
+// the gate sums of batch row b over that warp's K half, the upper half hands its four values
+// over through shared memory, and the lower half finishes (activations, cell update, outputs)
+// keeping c in a register.
+// h_{t-1} is exchanged through `hrep`: REP copies of the (B x U) state at distinct addresses,
+// double-buffered by step parity.  Every CTA writes its 4 units into all copies and reads the
+// whole state from copy blockIdx.x % REP — 128 CTAs pulling the same 64 KB at the same moment
+// otherwise serialise on a few L2 slices (measured: ~8 B/clk/SM).
+constexpr int LSTM_REP = 8;
+
+template <int KPL>   // K elements per lane per half: U = 2 * 32 * KPL
 __global__ void __launch_bounds__(256)
 k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, const float* __restrict__ hx,
                const float* __restrict__ cx, const float* __restrict__ initials,
                float* __restrict__ gates, float* __restrict__ c_all, float* __restrict__ h_all,
-               float* __restrict__ hprev, float* __restrict__ cprev, int T, int B, int U,
-               unsigned int* __restrict__ barrier, long long* __restrict__ dbg) {
+               float* __restrict__ hprev, float* __restrict__ cprev, float* __restrict__ hrep, int T, int B,
+               int U, unsigned int* __restrict__ barrier, long long* __restrict__ dbg) {
   using namespace lstm_seq;
-  extern __shared__ float hs[];            // [32][U + HPAD] masked h_{t-1} (rows >= B zero)
+  extern __shared__ float hs[];            // [32][U + HPAD] h_{t-1} (rows >= B zero), then [4][32][4] handover
   const int HS = U + HPAD;
+  float* red = hs + 32 * HS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool worker = warp < UPB;           // warps UPB..7 only help staging h
-  const int unit = blockIdx.x * UPB + (warp & (UPB - 1));
+  const int uw = warp & (UPB - 1), khalf = warp >> 2;
+  const int unit = blockIdx.x * UPB + uw;
   const int b = lane;                       // batch row this lane finishes
-  // lane l owns the 16-byte chunks {c*128 + 4l .. +3}, c < KPL/4, of every row: a warp's
-  // LDS.128 of one chunk index then reads 512 contiguous bytes (conflict-free)
+  const int koff = khalf * (U / 2);
+  // lane l owns the 16-byte chunks {c*128 + 4l .. +3} of its K half: conflict-free LDS.128
   float w[4][KPL];
-  if (worker) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g)
+  for (int g = 0; g < 4; ++g)
 #pragma unroll
-      for (int i = 0; i < KPL; i += 4) {
-        float4 t4 = *reinterpret_cast<const float4*>(Whh + ((size_t)g * U + unit) * U + (i / 4) * 128 + lane * 4);
-        w[g][i] = t4.x; w[g][i + 1] = t4.y; w[g][i + 2] = t4.z; w[g][i + 3] = t4.w;
-      }
-  }
+    for (int i = 0; i < KPL; i += 4) {
+      float4 t4 = *reinterpret_cast<const float4*>(Whh + ((size_t)g * U + unit) * U + koff + (i / 4) * 128 + lane * 4);
+      w[g][i] = t4.x; w[g][i + 1] = t4.y; w[g][i + 2] = t4.z; w[g][i + 3] = t4.w;
+    }
   for (int i = threadIdx.x; i < 32 * HS; i += blockDim.x) hs[i] = 0.f;
-  float c_reg = (worker && b < B) ? cx[(size_t)b * U + unit] : 0.f;
+  float c_reg = (khalf == 0 && b < B) ? cx[(size_t)b * U + unit] : 0.f;
+  const size_t rep_stride = (size_t)B * U;
   __syncthreads();
   for (int t = 0; t < T; ++t) {
-    const float* hsrc = t == 0 ? hx : h_all + (size_t)(t - 1) * B * U;
+    // step 0 reads the stored state; later steps read this CTA's replica of h_{t-1}
+    const float* hsrc = t == 0 ? hx : hrep + ((size_t)((t - 1) & 1) * LSTM_REP + (blockIdx.x % LSTM_REP)) * rep_stride;
     const float* ini = initials + (size_t)t * B;
     float xin[4] = {0.f, 0.f, 0.f, 0.f};
     const float keep_b = b < B ? 1.f - ini[b] : 0.f;
-    if (worker && b < B) {
+    if (khalf == 0 && b < B) {
       const float* xr = xg + ((size_t)t * B + b) * 4 * U + unit;
       xin[0] = __ldg(xr); xin[1] = __ldg(xr + U); xin[2] = __ldg(xr + 2 * U); xin[3] = __ldg(xr + 3 * U);
     }
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 0] = clock64();
-    // stage masked h_{t-1}: 16 independent 16-byte loads in flight per thread
     {
       const int total = B * (U / 4);
       for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * 16) {
@@ -843,7 +850,6 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
     }
     __syncthreads();
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 2] = clock64();
-    if (worker) {
     // partial dot products: part[bb*4 + g] = sum_{k in this lane's slice} h[bb][k] * W[g][k]
     float part[128];
 #pragma unroll
@@ -851,7 +857,7 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
       float hv[KPL];
 #pragma unroll
       for (int i = 0; i < KPL; i += 4) {
-        float4 t4 = *reinterpret_cast<const float4*>(hs + (size_t)bb * HS + (i / 4) * 128 + lane * 4);
+        float4 t4 = *reinterpret_cast<const float4*>(hs + (size_t)bb * HS + koff + (i / 4) * 128 + lane * 4);
         hv[i] = t4.x; hv[i + 1] = t4.y; hv[i + 2] = t4.z; hv[i + 3] = t4.w;
       }
 #pragma unroll
@@ -878,14 +884,16 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
         part[i] = keepv + __shfl_xor_sync(0xffffffffu, send, o);
       }
     }
-    if (b < B) {
+    if (khalf == 1) *reinterpret_cast<float4*>(red + (uw * 32 + lane) * 4) = make_float4(part[0], part[1], part[2], part[3]);
+    __syncthreads();
+    if (khalf == 0 && b < B) {
+      float4 hi = *reinterpret_cast<const float4*>(red + (uw * 32 + lane) * 4);
       size_t row = (size_t)t * B + b;
-      float gi = sigmoidf_(xin[0] + keep_b * part[0]);
-      float gf = sigmoidf_(xin[1] + keep_b * part[1]);
-      float gg = tanhf(xin[2] + keep_b * part[2]);
-      float go = sigmoidf_(xin[3] + keep_b * part[3]);
-      float keep = keep_b;
-      float cp = c_reg * keep;
+      float gi = sigmoidf_(xin[0] + keep_b * (part[0] + hi.x));
+      float gf = sigmoidf_(xin[1] + keep_b * (part[1] + hi.y));
+      float gg = tanhf(xin[2] + keep_b * (part[2] + hi.z));
+      float go = sigmoidf_(xin[3] + keep_b * (part[3] + hi.w));
+      float cp = c_reg * keep_b;
       float c = gf * cp + gi * gg;
       float h = go * tanhf(c);
       c_reg = c;
@@ -894,9 +902,13 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
       c_all[row * U + unit] = c;
       h_all[row * U + unit] = h;
       cprev[row * U + unit] = cp;
-      hprev[row * U + unit] = hs[(size_t)b * HS + unit] * keep;
+      hprev[row * U + unit] = hs[(size_t)b * HS + unit] * keep_b;
+      if (t + 1 < T) {
+        float* hr = hrep + (size_t)(t & 1) * LSTM_REP * rep_stride + (size_t)b * U + unit;
+#pragma unroll
+        for (int r = 0; r < LSTM_REP; ++r) hr[r * rep_stride] = h;
+      }
     }
-    }  // worker
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 4] = clock64();
     if (t + 1 < T) lstm_seq::grid_barrier(barrier, (unsigned int)(t + 1) * gridDim.x);
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 5] = clock64();

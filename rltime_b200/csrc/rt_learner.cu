@@ -130,6 +130,7 @@ struct rt_learner {
   int hw_parts = 256;
   unsigned int* grid_barrier = nullptr;
   long long* lstm_dbg = nullptr;
+  float* lstm_hrep = nullptr;   // replicated h exchange buffer of the persistent LSTM kernel
   int lstm_persistent = 1;
   int conv_implicit = 1;
   int conv_implicit_bwd = 1;
@@ -321,7 +322,7 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   int tm = cdiv(g.M, rttc::BLOCK_M);
   // few row tiles AND a short K loop (e.g. the recurrent step, M = B): narrower N tiles put
   // more SMs to work; long-K products get their parallelism from split-K instead
-  while (BN > 32 && (long long)tm * cdiv(g.N, BN) < 74 && cdiv(g.K, rttc::BLOCK_K) < 64) BN >>= 1;
+  while (BN > 32 && (long long)tm * cdiv(g.N, BN) < 74 && (cdiv(g.K, rttc::BLOCK_K) < 64 || tm == 1)) BN >>= 1;
   int stages = BN == 128 ? 3 : 4;
   if (cx.force_bn) BN = cx.force_bn;
   if (cx.force_stages) stages = cx.force_stages;
@@ -653,18 +654,18 @@ int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* 
   // whole recurrence in one persistent launch when it fits (see rtk::k_lstm_seq_fwd)
   {
     const int ctas = U / rtk::lstm_seq::UPB;
-    size_t smem = (size_t)32 * (U + rtk::lstm_seq::HPAD) * sizeof(float);
-    if (h->lstm_persistent && timesteps > 1 && (U == 512 || U == 256 || U == 128) && Beff <= 32 &&
+    size_t smem = ((size_t)32 * (U + rtk::lstm_seq::HPAD) + 4 * 32 * 4) * sizeof(float);
+    if (h->lstm_persistent && timesteps > 1 && (U == 512 || U == 256) && Beff <= 32 &&
         ctas <= h->num_sms) {
       void (*kern)(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
-                   float*, float*, int, int, int, unsigned int*, long long*) =
-          U == 512 ? rtk::k_lstm_seq_fwd<16> : (U == 256 ? rtk::k_lstm_seq_fwd<8> : rtk::k_lstm_seq_fwd<4>);
+                   float*, float*, float*, int, int, int, unsigned int*, long long*) =
+          U == 512 ? rtk::k_lstm_seq_fwd<8> : (U == 256 ? rtk::k_lstm_seq_fwd<4> : rtk::k_lstm_seq_fwd<4>);
       RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       RT_CUDA(cudaMemsetAsync(h->grid_barrier, 0, sizeof(unsigned int), st));
       const float* whh = net + h->o_whh;
       void* args[] = {(void*)&h->xg, (void*)&whh, (void*)&hx, (void*)&cx, (void*)&initials,
                       (void*)&h->gates, (void*)&h->c_all, (void*)&h->h_all, (void*)&h->hprev,
-                      (void*)&h->cprev, (void*)&timesteps, (void*)&Beff, (void*)&U,
+                      (void*)&h->cprev, (void*)&h->lstm_hrep, (void*)&timesteps, (void*)&Beff, (void*)&U,
                       (void*)&h->grid_barrier, (void*)&h->lstm_dbg};
       // cooperative launch: the runtime guarantees all CTAs are co-resident (grid barrier)
       RT_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(256), args, smem, st));
@@ -1128,6 +1129,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_REQUIRE(h->F % 4 == 0 && h->D % 4 == 0, "fc_size and the quantile-layer width must be multiples of 4");
 
   RT_TRY(dalloc(h, &h->grid_barrier, 4));
+  if (h->U) RT_TRY(dalloc(h, &h->lstm_hrep, (size_t)2 * rtk::LSTM_REP * 32 * h->U));
   if (getenv("RT_DEBUG_TIMELINE")) RT_TRY(dalloc(h, &h->lstm_dbg, 8 * 256, "lstm_dbg"));
   {
     cudaDeviceProp prop;
