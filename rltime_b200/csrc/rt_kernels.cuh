@@ -782,7 +782,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 // double-buffered by step parity.  Every CTA writes its 4 units into all copies and reads the
 // whole state from copy blockIdx.x % REP — 128 CTAs pulling the same 64 KB at the same moment
 // otherwise serialise on a few L2 slices (measured: ~8 B/clk/SM).
-constexpr int LSTM_REP = 8;
+constexpr int LSTM_REP = 1;   // replicas did not help (the 8 B/clk/SM was the LSU path, not an L2 hot spot)
 
 template <int KPL>   // K elements per lane per half: U = 2 * 32 * KPL
 __global__ void __launch_bounds__(256)
@@ -792,9 +792,15 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
                float* __restrict__ hprev, float* __restrict__ cprev, float* __restrict__ hrep, int T, int B,
                int U, unsigned int* __restrict__ barrier, long long* __restrict__ dbg) {
   using namespace lstm_seq;
-  extern __shared__ float hs[];            // [32][U + HPAD] h_{t-1} (rows >= B zero), then [4][32][4] handover
+  extern __shared__ __align__(16) float hs[];   // [32][U + HPAD] h_{t-1} (rows >= B zero), [4][32][4] handover, mbarrier
   const int HS = U + HPAD;
   float* red = hs + 32 * HS;
+  unsigned long long* tma_bar = reinterpret_cast<unsigned long long*>(red + 4 * 32 * 4);
+  const unsigned bar_addr = static_cast<unsigned>(__cvta_generic_to_shared(tma_bar));
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int uw = warp & (UPB - 1), khalf = warp >> 2;
   const int unit = blockIdx.x * UPB + uw;
@@ -824,28 +830,34 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
       xin[0] = __ldg(xr); xin[1] = __ldg(xr + U); xin[2] = __ldg(xr + 2 * U); xin[3] = __ldg(xr + 3 * U);
     }
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 0] = clock64();
+    // stage h_{t-1}: one thread issues B bulk copies (one 4U-byte row each) that the TMA engine
+    // streams from L2 into the padded rows; everybody waits on the mbarrier.  (LDG.128 through the
+    // LSU managed ~8 B/clk/SM here; the copy is unmasked: (h * keep) . w == keep * (h . w).)
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");   // other SMs' generic-proxy writes -> async proxy
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                   "r"((unsigned)(B * U * 4))
+                   : "memory");
+      for (int bb = 0; bb < B; ++bb) {
+        unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(hs + (size_t)bb * HS));
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+            "l"(hsrc + (size_t)bb * U), "r"((unsigned)(U * 4)), "r"(bar_addr)
+            : "memory");
+      }
+    }
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[8 * t + 1] = clock64();
     {
-      const int total = B * (U / 4);
-      for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * 16) {
-        float4 v[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          int i = i0 + q * blockDim.x;
-          if (i < total) {
-            int bb = i / (U / 4), k4 = i - bb * (U / 4);
-            v[q] = __ldcg(reinterpret_cast<const float4*>(hsrc + (size_t)bb * U) + k4);   // L2: never a stale L1 line
-          }
-        }
-        if (dbg && blockIdx.x == 0 && threadIdx.x == 0 && i0 == 0) dbg[8 * t + 1] = clock64();
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          int i = i0 + q * blockDim.x;
-          if (i < total) {
-            int bb = i / (U / 4), k4 = i - bb * (U / 4);
-            // unmasked copy: (h * keep) . w == keep * (h . w), the mask is applied to the sums
-            *reinterpret_cast<float4*>(hs + (size_t)bb * HS + 4 * k4) = v[q];
-          }
-        }
+      unsigned ok = 0;
+      const unsigned parity = (unsigned)(t & 1);
+      while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity)
+            : "memory");
       }
     }
     __syncthreads();

@@ -654,7 +654,7 @@ int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* 
   // whole recurrence in one persistent launch when it fits (see rtk::k_lstm_seq_fwd)
   {
     const int ctas = U / rtk::lstm_seq::UPB;
-    size_t smem = ((size_t)32 * (U + rtk::lstm_seq::HPAD) + 4 * 32 * 4) * sizeof(float);
+    size_t smem = ((size_t)32 * (U + rtk::lstm_seq::HPAD) + 4 * 32 * 4) * sizeof(float) + 16;
     if (h->lstm_persistent && timesteps > 1 && (U == 512 || U == 256) && Beff <= 32 &&
         ctas <= h->num_sms) {
       void (*kern)(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
