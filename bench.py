@@ -260,6 +260,10 @@ def run_gpu(args):
         import torch.distributed as dist
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     ms, e2e_s = float(vals[0]), float(vals[1])
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     hbm, bf16_tf, which = peaks()

@@ -833,16 +833,20 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
     // stage h_{t-1}: one thread issues B bulk copies (one 4U-byte row each) that the TMA engine
     // streams from L2 into the padded rows; everybody waits on the mbarrier.  (LDG.128 through the
     // LSU managed ~8 B/clk/SM here; the copy is unmasked: (h * keep) . w == keep * (h . w).)
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+      // lane 0 posts the expected byte count, then every lane issues the copy of one batch row
+      // (one thread issuing all 32 took ~2.7k cycles)
       asm volatile("fence.proxy.async;" ::: "memory");   // other SMs' generic-proxy writes -> async proxy
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
-                   "r"((unsigned)(B * U * 4))
-                   : "memory");
-      for (int bb = 0; bb < B; ++bb) {
-        unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(hs + (size_t)bb * HS));
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
+                     "r"((unsigned)(B * U * 4))
+                     : "memory");
+      __syncwarp();
+      if (lane < B) {
+        unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(hs + (size_t)lane * HS));
         asm volatile(
             "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-            "l"(hsrc + (size_t)bb * U), "r"((unsigned)(U * 4)), "r"(bar_addr)
+            "l"(hsrc + (size_t)lane * U), "r"((unsigned)(U * 4)), "r"(bar_addr)
             : "memory");
       }
     }
