@@ -232,6 +232,14 @@ int rt_learner_compute_grads(rt_learner* h, const rt_batch* batch, const rt_lear
 int rt_learner_apply_grads(rt_learner* h, double grad_scale, void* stream);
 /* Flat fp32 buffers (RT_BUF_*): all tensors of one kind back to back, 256-byte aligned. */
 int rt_learner_flat_buffer(rt_learner* h, int32_t which, float** dev_ptr, int64_t* count);
+/* DQNPolicy.actor_predict / IQNPolicy._actor_predict_postprocess (policies/torch/dqn.py:132-148,
+ * iqn.py:124-131) for E envs at timesteps = 1 with the ONLINE network: q-values averaged over
+ * the sampled quantiles plus the new LSTM state (LSTM.last_state, models/torch/modules/lstm.py:
+ * 118-120).  All pointers are device pointers except taus_host (E*Nq fractions or NULL).  Uses
+ * the learner's activation buffers: call between updates, on the update stream. */
+int rt_learner_act(rt_learner* h, int32_t E, const uint8_t* x, const float* hx, const float* cx,
+                   const float* initials, const float* taus_host, float* qvalues, float* h_out,
+                   float* c_out, void* stream);
 /* Device pointer to the T*B reported |td| means (torch/iqn.py:112) of the last step. */
 int rt_learner_td_abs(rt_learner* h, float** out_device);
 /* qloss, td_mean, grad_norm of the last step (torch/iqn.py:127-129, torch_trainer.py:187-190);

@@ -117,6 +117,7 @@ SIGNATURES = {
     "rt_learner_compute_grads": (C.c_int, [_VP, C.POINTER(Batch), C.POINTER(LearnerIO), _VP, _VP]),
     "rt_learner_apply_grads": (C.c_int, [_VP, C.c_double, _VP]),
     "rt_learner_flat_buffer": (C.c_int, [_VP, C.c_int32, C.POINTER(_VP), C.POINTER(C.c_int64)]),
+    "rt_learner_act": (C.c_int, [_VP, C.c_int32] + [_VP] * 8 + [_VP]),
     "rt_learner_td_abs": (C.c_int, [_VP, C.POINTER(_VP)]),
     "rt_learner_read_stats": (C.c_int, [_VP, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                         C.POINTER(C.c_float), _VP]),

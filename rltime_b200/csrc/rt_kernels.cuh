@@ -402,6 +402,16 @@ __global__ void k_dueling_bwd(const float* __restrict__ dtheta, const long long*
   if (dv) dv[r] = g;
 }
 
+// qmean[r,a] = mean_q q[r,q,a]   (IQNPolicy._actor_predict_postprocess, policies/torch/iqn.py:124-131)
+__global__ void k_quantile_mean(const float* __restrict__ q, float* __restrict__ out, int rows, int Nq, int A) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * A) return;
+  int r = i / A, a = i - r * A;
+  float s = 0.f;
+  for (int k = 0; k < Nq; ++k) s += q[((size_t)r * Nq + k) * A + a];
+  out[i] = s / (float)Nq;
+}
+
 // ------------------------------------------------------------------------------ target
 // IQN._get_bootstrap_target_value (rltime/training/torch/iqn.py:37-52) +
 // TorchTrainer.calc_target_values / _vf_unscale / _vf_scale (torch_trainer.py:46-78,144-147).

@@ -1394,6 +1394,40 @@ int rt_learner_flat_buffer(rt_learner* h, int32_t which, float** dev_ptr, int64_
   return RT_OK;
 }
 
+int rt_learner_act(rt_learner* h, int32_t E, const uint8_t* x, const float* hx, const float* cx,
+                   const float* initials, const float* taus_host, float* qvalues, float* h_out,
+                   float* c_out, void* stream) {
+  RT_REQUIRE(h && x && qvalues && E >= 1, "bad argument");
+  RT_REQUIRE(E <= h->max_rows && (size_t)E * h->Nq <= (size_t)h->MQ,
+             "acting batch of %d envs exceeds the learner's buffers (max %d)", E, h->MQ / h->Nq);
+  RT_REQUIRE(!h->U || (hx && cx && initials && h_out && c_out), "recurrent model needs hx/cx/initials");
+  RT_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  StateView sv;
+  sv.x = x;
+  sv.hx = const_cast<float*>(hx);
+  sv.cx = const_cast<float*>(cx);
+  sv.initials = initials;
+  const float* feat = nullptr;
+  RT_TRY(trunk_forward(h, st, h->p[0], sv, E, 1, &feat));
+  size_t nq = (size_t)E * h->Nq;
+  if (taus_host) {
+    RT_CUDA(cudaMemcpyAsync(h->tau_stage, taus_host, nq * sizeof(float), cudaMemcpyHostToDevice, st));
+  } else {
+    k_uniform<<<cdiv(nq, 256), 256, 0, st>>>(h->tau_stage, nq, h->td.seed ^ 0xA5A5A5A5ULL, h->rng_counter);
+    RT_LAUNCH_CHECK();
+    h->rng_counter += nq;
+  }
+  RT_TRY(heads_forward(h, st, h->p[0], feat, E, h->tau_stage));
+  rtk::k_quantile_mean<<<cdiv((size_t)E * h->A, 128), 128, 0, st>>>(h->q, qvalues, E, h->Nq, h->A);
+  RT_LAUNCH_CHECK();
+  if (h->U) {
+    RT_CUDA(cudaMemcpyAsync(h_out, h->h_all, (size_t)E * h->U * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    RT_CUDA(cudaMemcpyAsync(c_out, h->c_all, (size_t)E * h->U * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return RT_OK;
+}
+
 int rt_learner_td_abs(rt_learner* h, float** out_device) {
   RT_REQUIRE(h && out_device, "null argument");
   *out_device = h->report;

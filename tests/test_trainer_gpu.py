@@ -1,0 +1,59 @@
+"""End-to-end: IQNTrainer (reference trainer call surface) driving fake envs through the device
+history buffer, the CUDA learner and rt_learner_act acting inference."""
+import io
+
+import numpy as np
+import pytest
+
+MODEL = {"type": "sequential", "args": {"layer_configs": [
+    {"type": "cnn", "args": {"layers": [{"filters": 16, "kernel": 8, "stride": 4},
+                                         {"filters": 16, "kernel": 4, "stride": 2}]}},
+    {"type": "lstm", "args": {"num_units": 64}},
+    {"type": "fc", "args": {"fc_size": 64}}]}}
+
+
+class _Logger:
+    def __init__(self):
+        self.results, self.checkpoints = [], []
+
+    def log_result(self, name, info, step):
+        self.results.append((name, dict(info), step))
+
+    def save_checkpoint(self, data, step):
+        self.checkpoints.append((data, step))
+
+
+@pytest.mark.gpu
+def test_iqn_trainer_end_to_end_with_fake_envs():
+    import torch
+    from rltime_b200.training import IQNTrainer
+    from tests.fake_actor import FakeVecActor
+    actors = FakeVecActor(num_envs=4, num_actions=4, seed=1)
+    logger = _Logger()
+    tr = IQNTrainer(logger, actors, MODEL, {"dueling": True, "num_sampling_quantiles": 8, "embedding_dim": 16})
+    tr.train(total_steps=1200, log_freq=400, target_update_freq=300, clip_rewards=True, gamma=0.99,
+             nstep_train=4, nstep_target=2, lr=3e-4, lr_anneal=True, mbatch_size=4, warmup_steps=200,
+             burn_in_timesteps=2, rnn_bootstrap=True, double_q=True, clip_grad=40.0, adam_epsilon=1e-5,
+             history_mode={"type": "prioritized_replay",
+                           "args": {"size": 600, "train_frequency": 4, "alpha": 0.9, "beta": 0.6,
+                                    "max_envs": 4}})
+    assert tr.steps >= 1200 and tr.updates > 100
+    assert tr.log["target_syncs"] >= 3
+    st = tr.learner.stats()
+    assert np.isfinite(st["qloss"]) and np.isfinite(st["grad_norm"]) and st["grad_norm"] > 0
+    # train quota: ~train_frequency trained transitions per acted transition after warm-up
+    trained = tr.updates * 4 * 4
+    assert 0.5 < trained / (4.0 * (tr.steps - 200)) < 1.5
+    # checkpoints carry a torch-loadable state_dict with the reference's parameter names
+    assert logger.checkpoints and logger.results
+    sd = torch.load(io.BytesIO(logger.checkpoints[-1][0]["policy_state"]), map_location="cpu")
+    assert "model.layers.1.lstm_cell.weight_hh" in sd and "quantile_layer.weight" in sd and \
+        "embedding_range" in sd
+    # the weights moved away from their initialisation and stayed finite
+    from rltime_b200.init import init_params
+    p0 = init_params(tr.learner.param_info, 64, seed=0)
+    moved = max(float((sd[k] - p0[k]).abs().max()) for k in p0)
+    assert moved > 1e-4 and all(torch.isfinite(v).all() for v in sd.values())
+    # acting inference is consistent with the learner's own forward: greedy action = argmax of q
+    pred = tr.policy.actor_predict(actors.last_state, timesteps=1)
+    assert pred["qvalues"].shape == (4, 4) and (pred["actions"] == pred["qvalues"].argmax(1)).all()
