@@ -563,7 +563,7 @@ __global__ void k_heads_out(const float* __restrict__ h1, const float* __restric
                             const float* __restrict__ Wout, const float* __restrict__ bout,
                             const float* __restrict__ Wv, const float* __restrict__ bv,
                             float* __restrict__ adv, float* __restrict__ vout, float* __restrict__ q,
-                            size_t rows, int F, int A) {
+                            size_t rows, int F, int A, int ldh) {
   size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -571,8 +571,8 @@ __global__ void k_heads_out(const float* __restrict__ h1, const float* __restric
 #pragma unroll
   for (int a = 0; a < MAXA; ++a) acc[a] = 0.f;
   float accv = 0.f;
-  const float* hr = h1 + r * F;
-  const float* vr = v1 ? v1 + r * F : nullptr;
+  const float* hr = h1 + r * ldh;
+  const float* vr = v1 ? v1 + r * ldh : nullptr;
   // F % 4 == 0: 16-byte loads, several independent rows of loads in flight per lane
   for (int f = lane * 4; f < F; f += 128) {
     float4 hv = *reinterpret_cast<const float4*>(hr + f);
@@ -623,11 +623,12 @@ __global__ void k_heads_dsmall(const float* __restrict__ dtheta, const long long
                                const float* __restrict__ Wout, const float* __restrict__ Wv,
                                const float* __restrict__ h1, const float* __restrict__ v1,
                                float* __restrict__ dh1, float* __restrict__ dv1, size_t rows, int F, int A,
-                               int Nq, int dueling) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * F) return;
-  size_t r = idx / F;
-  int f = (int)(idx - r * F);
+                               int Nq, int dueling, int ldh) {
+  size_t idx0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx0 >= rows * F) return;
+  size_t r = idx0 / F;
+  int f = (int)(idx0 - r * F);
+  size_t idx = r * ldh + f;
   float g = dtheta[r];
   int act = (int)actions[r / Nq];
   float w = Wout[(size_t)act * F + f];
@@ -647,7 +648,7 @@ template <int MAXA>
 __global__ void k_heads_wgrad(const float* __restrict__ dtheta, const long long* __restrict__ actions,
                               const float* __restrict__ h1, const float* __restrict__ v1,
                               float* __restrict__ part, float* __restrict__ partb, size_t rows, int F,
-                              int A, int Nq, int dueling, int rows_per_block) {
+                              int A, int Nq, int dueling, int rows_per_block, int ldh) {
   __shared__ float s[8][33];
   int f = blockIdx.x * 32 + threadIdx.x;
   size_t r0 = (size_t)blockIdx.y * rows_per_block, r1 = r0 + rows_per_block;
@@ -660,7 +661,7 @@ __global__ void k_heads_wgrad(const float* __restrict__ dtheta, const long long*
     for (size_t r = r0 + threadIdx.y; r < r1; r += 8) {
       float g = dtheta[r];
       int act = (int)actions[r / Nq];
-      float hv = h1[r * F + f];
+      float hv = h1[r * ldh + f];
 #pragma unroll
       for (int a = 0; a < MAXA; ++a)
         if (a < A) {
@@ -669,7 +670,7 @@ __global__ void k_heads_wgrad(const float* __restrict__ dtheta, const long long*
           accb[a] += d;
         }
       if (dueling) {
-        acc[MAXA] = fmaf(g, v1[r * F + f], acc[MAXA]);
+        acc[MAXA] = fmaf(g, v1[r * ldh + f], acc[MAXA]);
         accb[MAXA] += g;
       }
     }
@@ -846,7 +847,9 @@ k_lstm_seq_fwd(const float* __restrict__ xg, const float* __restrict__ Whh, cons
     if (warp == 0) {
       // lane 0 posts the expected byte count, then every lane issues the copy of one batch row
       // (one thread issuing all 32 took ~2.7k cycles)
-      asm volatile("fence.proxy.async;" ::: "memory");   // other SMs' generic-proxy writes -> async proxy
+      // the rows were written by other SMs through the generic proxy and published by the grid
+      // barrier; order them before this SM's async-proxy (TMA) reads of global memory
+      asm volatile("fence.proxy.async.global;" ::: "memory");
       if (lane == 0)
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr),
                      "r"((unsigned)(B * U * 4))

@@ -94,6 +94,8 @@ struct rt_learner {
   int featC = 0, featHW = 0, feat = 0;  // last conv output
   int U = 0, D = 0, F = 0, A = 0, Nq = 0, E = 0;
   bool dueling = false;
+  bool fused_hidden = false;   // FC + value-hidden layers stored / executed as one [2F x D] layer
+  int ldh = 0;                 // row pitch of h1 / v1 / dh1 / dv1 (F, or 2F when fused)
   std::vector<PInfo> pinfo;
   size_t nparams = 0;
   // parameter offsets
@@ -155,13 +157,27 @@ int dalloc(rt_learner* h, T** p, size_t count, const char* name = nullptr) {
   return RT_OK;
 }
 
+size_t reserve_params(rt_learner* h, size_t count) {
+  size_t off = (h->nparams + 63) / 64 * 64;
+  h->nparams = off + count;
+  return off;
+}
+
 size_t add_param(rt_learner* h, const std::string& name, std::vector<int> shape, int perm,
-                 int conv_c = 0, int conv_k = 0) {
+                 int conv_c = 0, int conv_k = 0, long long fixed_off = -1) {
   PInfo pi;
   pi.name = name;
   pi.shape = shape;
   pi.count = 1;
   for (int d : shape) pi.count *= (size_t)d;
+  if (fixed_off >= 0) {   // placed inside a region reserved earlier (registration order is unchanged)
+    pi.off = (size_t)fixed_off;
+    pi.perm = perm;
+    pi.conv_c = conv_c;
+    pi.conv_k = conv_k;
+    h->pinfo.push_back(pi);
+    return pi.off;
+  }
   pi.off = (h->nparams + 63) / 64 * 64;  // 256-byte aligned tensors
   pi.perm = perm;
   pi.conv_c = conv_c;
@@ -323,6 +339,9 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   // few row tiles AND a short K loop (e.g. the recurrent step, M = B): narrower N tiles put
   // more SMs to work; long-K products get their parallelism from split-K instead
   while (BN > 32 && (long long)tm * cdiv(g.N, BN) < 74 && (cdiv(g.K, rttc::BLOCK_K) < 64 || tm == 1)) BN >>= 1;
+  // wide-N products with plenty of row tiles: 128x256 tiles re-read A half as often (the fc-size
+  // GEMMs move ~330 MB through L2 at 128x128 and run at the L2 rate, not the tensor rate)
+  if (BN == 128 && g.N % 256 == 0 && (long long)tm * (g.N / 256) >= cx.num_sms) BN = 256;
   int stages = BN == 128 ? 3 : 4;
   if (cx.force_bn) BN = cx.force_bn;
   if (cx.force_stages) stages = cx.force_stages;
@@ -722,15 +741,24 @@ int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float*
   RT_TRY(gemm(h->gx, st, g));
   rtk::k_quantile_mul<<<cdiv(MQ * (D / 4), 256), 256, 0, st>>>(feat, h->phi, h->xq, MQ, D, Nq);
   RT_LAUNCH_CHECK();
-  g = mk(h->xq, D, 0, net + h->o_fcw, D, 1, h->h1, F, (int)MQ, F, D);
-  g.bias = net + h->o_fcb;
-  g.relu = 1;
-  RT_TRY(gemm(h->gx, st, g));
-  if (h->dueling) {
-    g = mk(h->xq, D, 0, net + h->o_vhw, D, 1, h->v1, F, (int)MQ, F, D);
-    g.bias = net + h->o_vhb;
+  const int ldh = h->ldh;
+  if (h->fused_hidden) {
+    // [h1 | v1] = relu(xq . [Wfc ; Wvh]^T + [bfc | bvh]): one GEMM, the A operand is read once
+    g = mk(h->xq, D, 0, net + h->o_fcw, D, 1, h->h1, ldh, (int)MQ, 2 * F, D);
+    g.bias = net + h->o_fcb;
     g.relu = 1;
     RT_TRY(gemm(h->gx, st, g));
+  } else {
+    g = mk(h->xq, D, 0, net + h->o_fcw, D, 1, h->h1, F, (int)MQ, F, D);
+    g.bias = net + h->o_fcb;
+    g.relu = 1;
+    RT_TRY(gemm(h->gx, st, g));
+    if (h->dueling) {
+      g = mk(h->xq, D, 0, net + h->o_vhw, D, 1, h->v1, F, (int)MQ, F, D);
+      g.bias = net + h->o_vhb;
+      g.relu = 1;
+      RT_TRY(gemm(h->gx, st, g));
+    }
   }
   // out layer + value layer + dueling combine: one warp per row
   {
@@ -738,10 +766,10 @@ int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float*
     int blocks = cdiv(MQ * 32, 256);
     if (A <= 8)
       rtk::k_heads_out<8><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
-                                                 net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A);
+                                                 net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A, ldh);
     else
       rtk::k_heads_out<32><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
-                                                  net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A);
+                                                  net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A, ldh);
     RT_LAUNCH_CHECK();
   }
   return RT_OK;
@@ -757,7 +785,7 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
   // slab partials folded deterministically
   rtk::k_heads_dsmall<<<cdiv(MQ * F, 256), 256, 0, st>>>(h->dtheta, actions, net + h->o_outw,
                                                         net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, MQ,
-                                                        F, A, Nq, duel);
+                                                        F, A, Nq, duel, h->ldh);
   RT_LAUNCH_CHECK();
   {
     int nout = A + duel;
@@ -770,10 +798,10 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
     dim3 grid(cdiv(F, 32), parts);
     if (A <= 8)
       rtk::k_heads_wgrad<8><<<grid, dim3(32, 8), 0, st>>>(h->dtheta, actions, h->h1, h->v1, h->hw_part,
-                                                         h->hw_partb, MQ, F, A, Nq, duel, rpb);
+                                                         h->hw_partb, MQ, F, A, Nq, duel, rpb, h->ldh);
     else
       rtk::k_heads_wgrad<32><<<grid, dim3(32, 8), 0, st>>>(h->dtheta, actions, h->h1, h->v1, h->hw_part,
-                                                          h->hw_partb, MQ, F, A, Nq, duel, rpb);
+                                                          h->hw_partb, MQ, F, A, Nq, duel, rpb, h->ldh);
     RT_LAUNCH_CHECK();
     rtk::k_colsum_final<<<cdiv(A * F, 32), dim3(32, 8), 0, st>>>(h->hw_part, G + h->o_outw, parts, A * F,
                                                                0, nout * F);
@@ -788,6 +816,14 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
       RT_LAUNCH_CHECK();
     }
   }
+  if (h->fused_hidden) {
+    // [dh1 | dv1] against the stacked [Wfc ; Wvh]: weight gradient, bias gradient and data
+    // gradient of both hidden layers in one GEMM each
+    const int F2 = 2 * F;
+    RT_TRY(gemm(h->gx, st, mk(h->dh1, F2, 1, h->xq, D, 0, G + h->o_fcw, D, F2, D, (int)MQ)));
+    RT_TRY(colsum(h, st, h->dh1, MQ, F2, G + h->o_fcb, 0));
+    RT_TRY(gemm(h->gx, st, mk(h->dh1, F2, 0, net + h->o_fcw, D, 0, h->dxq, D, (int)MQ, D, F2)));
+  } else {
   // FC
   RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 1, h->xq, D, 0, G + h->o_fcw, D, F, D, (int)MQ)));
   RT_TRY(colsum(h, st, h->dh1, MQ, F, G + h->o_fcb, 0));
@@ -798,6 +834,7 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
     rtk::GemmArgs g = mk(h->dv1, F, 0, net + h->o_vhw, D, 0, h->dxq, D, (int)MQ, D, F);
     g.accumulate = 1;
     RT_TRY(gemm(h->gx, st, g));
+  }
   }
   rtk::k_quantile_mul_bwd<<<cdiv((size_t)M * D, 256), 256, 0, st>>>(h->dxq, feat, h->phi, h->dphi,
                                                                    h->dfeatq, M, D, Nq);
@@ -1016,18 +1053,28 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   }
   int featperm_cols = h->U ? PERM_NONE : PERM_FEAT_COLS;
   int featperm_rows = h->U ? PERM_NONE : PERM_FEAT_ROWS;
+  // dueling: the advantage hidden layer (model FC) and the value hidden layer read the same
+  // input, so their weights / biases are placed back to back and run as ONE [2F x D] layer
+  h->fused_hidden = h->dueling && ((size_t)h->F * h->D) % 4 == 0 && h->F % 4 == 0;
+  long long fw = -1, fb = -1;
+  if (h->fused_hidden) {
+    fw = (long long)reserve_params(h, (size_t)2 * h->F * h->D);
+    fb = (long long)reserve_params(h, (size_t)2 * h->F);
+  }
   {
     char nm[96];
     snprintf(nm, sizeof(nm), "model.layers.%d.layers.0.0.weight", fc_layer);
-    h->o_fcw = add_param(h, nm, {h->F, h->D}, featperm_cols);
+    h->o_fcw = add_param(h, nm, {h->F, h->D}, featperm_cols, 0, 0, fw);
     snprintf(nm, sizeof(nm), "model.layers.%d.layers.0.0.bias", fc_layer);
-    h->o_fcb = add_param(h, nm, {h->F}, PERM_NONE);
+    h->o_fcb = add_param(h, nm, {h->F}, PERM_NONE, 0, 0, fb);
   }
   h->o_outw = add_param(h, "out_layer.weight", {h->A, h->F}, PERM_NONE);
   h->o_outb = add_param(h, "out_layer.bias", {h->A}, PERM_NONE);
   if (h->dueling) {
-    h->o_vhw = add_param(h, "value_hidden_layer.weight", {h->F, h->D}, featperm_cols);
-    h->o_vhb = add_param(h, "value_hidden_layer.bias", {h->F}, PERM_NONE);
+    h->o_vhw = add_param(h, "value_hidden_layer.weight", {h->F, h->D}, featperm_cols, 0, 0,
+                         h->fused_hidden ? fw + (long long)h->F * h->D : -1);
+    h->o_vhb = add_param(h, "value_hidden_layer.bias", {h->F}, PERM_NONE, 0, 0,
+                         h->fused_hidden ? fb + h->F : -1);
     h->o_vw = add_param(h, "value_layer.weight", {1, h->F}, PERM_NONE);
     h->o_vb = add_param(h, "value_layer.bias", {1}, PERM_NONE);
   }
@@ -1092,8 +1139,14 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->cf, MQ * h->E, "cf"));
   RT_TRY(dalloc(h, &h->phi, MQ * D, "phi"));
   RT_TRY(dalloc(h, &h->xq, MQ * D, "xq"));
-  RT_TRY(dalloc(h, &h->h1, MQ * F, "h1"));
-  RT_TRY(dalloc(h, &h->v1, MQ * F, "v1"));
+  h->ldh = h->fused_hidden ? 2 * h->F : h->F;
+  if (h->fused_hidden) {
+    RT_TRY(dalloc(h, &h->h1, MQ * 2 * F, "h1"));
+    h->v1 = h->h1 + F;
+  } else {
+    RT_TRY(dalloc(h, &h->h1, MQ * F, "h1"));
+    RT_TRY(dalloc(h, &h->v1, MQ * F, "v1"));
+  }
   RT_TRY(dalloc(h, &h->adv, MQ * A, "adv"));
   RT_TRY(dalloc(h, &h->v, MQ, "v"));
   RT_TRY(dalloc(h, &h->q, MQ * A, "q"));
@@ -1106,8 +1159,13 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->stats, 8, "stats"));
   RT_TRY(dalloc(h, &h->dadv, MQ * A, "dadv"));
   RT_TRY(dalloc(h, &h->dv, MQ, "dv"));
-  RT_TRY(dalloc(h, &h->dh1, MQ * F, "dh1"));
-  RT_TRY(dalloc(h, &h->dv1, MQ * F, "dv1"));
+  if (h->fused_hidden) {
+    RT_TRY(dalloc(h, &h->dh1, MQ * 2 * F, "dh1"));
+    h->dv1 = h->dh1 + F;
+  } else {
+    RT_TRY(dalloc(h, &h->dh1, MQ * F, "dh1"));
+    RT_TRY(dalloc(h, &h->dv1, MQ * F, "dv1"));
+  }
   RT_TRY(dalloc(h, &h->dxq, MQ * D, "dxq"));
   RT_TRY(dalloc(h, &h->dphi, MQ * D, "dphi"));
   RT_TRY(dalloc(h, &h->dfeatq, (size_t)h->M * D, "dfeatq"));
