@@ -22,6 +22,7 @@
 #include "rt_common.h"
 #include "rt_kernels.cuh"
 #include "rt_gemm_tc.cuh"
+#include "rt_lstm_tc.cuh"
 
 namespace {
 
@@ -134,6 +135,12 @@ struct rt_learner {
   long long* lstm_dbg = nullptr;
   float* lstm_hrep = nullptr;   // replicated h exchange buffer of the persistent LSTM kernel
   int lstm_persistent = 1;
+  int lstm_tc = 1;              // tensor-core multi-sequence recurrence (TF32 mode)
+  float* lstm_xchg = nullptr;   // swizzled h exchange blocks of that kernel
+  int lstm_tcap = 0;            // time-steps the exchange buffer holds
+  int lstm_upc = 8;             // preferred hidden units per CTA of that kernel (8 or 16)
+  float *xg2 = nullptr;         // input gates of the target network's pass
+  float *h_all2 = nullptr, *h_all3 = nullptr;   // LSTM outputs of the target / selection passes
   int conv_implicit = 1;
   int conv_implicit_bwd = 1;
   int conv_persistent = 0;
@@ -661,16 +668,33 @@ int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t*
   return RT_OK;
 }
 
-// LSTM forward over `rows` = timesteps * Beff time-major rows (lstm.py:50-122).
-int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int rows,
-                 int timesteps, const float* hx, const float* cx, const float* initials) {
-  int U = h->U, Beff = rows / timesteps;
-  rtk::GemmArgs g = mk(feat, h->feat, 0, net + h->o_wih, h->feat, 1, h->xg, 4 * U, rows, 4 * U, h->feat);
+// One LSTM recurrence (lstm.py:50-122) over time-major rows t*Beff + b.
+struct SeqDesc {
+  const float* net;       // parameter buffer (online / target)
+  const float* xg;        // (timesteps*Beff, 4U) input gates incl. both biases
+  const float* hx;        // stored state of step 0
+  const float* cx;
+  const float* initials;  // (timesteps*Beff)
+  float* h_all;           // output (timesteps*Beff, U)
+  int slot;               // exchange-buffer slot: hprev rows [slot*max_rows, ...)
+  bool bptt;              // keep gates / c_all / cprev for the backward pass
+};
+
+// xg = feat . W_ih^T + b_ih + b_hh for `rows` rows
+int lstm_xgates(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int rows, float* xg) {
+  int U = h->U;
+  rtk::GemmArgs g = mk(feat, h->feat, 0, net + h->o_wih, h->feat, 1, xg, 4 * U, rows, 4 * U, h->feat);
   g.bias = net + h->o_bih;
   g.bias2 = net + h->o_bhh;
-  RT_TRY(gemm(h->gx, st, g));
+  return gemm(h->gx, st, g);
+}
+
+// fp32 recurrence of one sequence: persistent SIMT kernel when it fits, else one GEMM + cell
+// kernel per step.  gates / c_all / cprev always land in the shared BPTT buffers.
+int lstm_recur_one(rt_learner* h, cudaStream_t st, const SeqDesc& q, int timesteps, int Beff) {
+  int U = h->U;
+  float* hprev = h->hprev + (size_t)q.slot * h->max_rows * U;
   int nb = cdiv((size_t)Beff * U, 256);
-  // whole recurrence in one persistent launch when it fits (see rtk::k_lstm_seq_fwd)
   {
     const int ctas = U / rtk::lstm_seq::UPB;
     size_t smem = ((size_t)32 * (U + rtk::lstm_seq::HPAD) + 4 * 32 * 4) * sizeof(float) + 16;
@@ -678,12 +702,12 @@ int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* 
         ctas <= h->num_sms) {
       void (*kern)(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
                    float*, float*, float*, int, int, int, unsigned int*, long long*) =
-          U == 512 ? rtk::k_lstm_seq_fwd<8> : (U == 256 ? rtk::k_lstm_seq_fwd<4> : rtk::k_lstm_seq_fwd<4>);
+          U == 512 ? rtk::k_lstm_seq_fwd<8> : rtk::k_lstm_seq_fwd<4>;
       RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       RT_CUDA(cudaMemsetAsync(h->grid_barrier, 0, sizeof(unsigned int), st));
-      const float* whh = net + h->o_whh;
-      void* args[] = {(void*)&h->xg, (void*)&whh, (void*)&hx, (void*)&cx, (void*)&initials,
-                      (void*)&h->gates, (void*)&h->c_all, (void*)&h->h_all, (void*)&h->hprev,
+      const float* whh = q.net + h->o_whh;
+      void* args[] = {(void*)&q.xg, (void*)&whh, (void*)&q.hx, (void*)&q.cx, (void*)&q.initials,
+                      (void*)&h->gates, (void*)&h->c_all, (void*)&q.h_all, (void*)&hprev,
                       (void*)&h->cprev, (void*)&h->lstm_hrep, (void*)&timesteps, (void*)&Beff, (void*)&U,
                       (void*)&h->grid_barrier, (void*)&h->lstm_dbg};
       // cooperative launch: the runtime guarantees all CTAs are co-resident (grid barrier)
@@ -692,20 +716,99 @@ int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* 
       return RT_OK;
     }
   }
-  rtk::k_lstm_init<<<nb, 256, 0, st>>>(hx, cx, initials, h->hprev, h->cprev, Beff, U);
+  rtk::k_lstm_init<<<nb, 256, 0, st>>>(q.hx, q.cx, q.initials, hprev, h->cprev, Beff, U);
   RT_LAUNCH_CHECK();
   for (int t = 0; t < timesteps; ++t) {
     size_t ro = (size_t)t * Beff;
-    rtk::GemmArgs gh = mk(h->hprev + ro * U, U, 0, net + h->o_whh, U, 1, h->hg, 4 * U, Beff, 4 * U, U);
+    rtk::GemmArgs gh = mk(hprev + ro * U, U, 0, q.net + h->o_whh, U, 1, h->hg, 4 * U, Beff, 4 * U, U);
     RT_TRY(gemm(h->gx, st, gh));
     bool last = t == timesteps - 1;
     rtk::k_lstm_cell<<<nb, 256, 0, st>>>(
-        h->xg + ro * 4 * U, h->hg, h->cprev + ro * U, h->gates + ro * 4 * U, h->c_all + ro * U,
-        h->h_all + ro * U, last ? nullptr : initials + ro + Beff,
-        last ? nullptr : h->hprev + (ro + Beff) * U, last ? nullptr : h->cprev + (ro + Beff) * U, Beff, U);
+        q.xg + ro * 4 * U, h->hg, h->cprev + ro * U, h->gates + ro * 4 * U, h->c_all + ro * U,
+        q.h_all + ro * U, last ? nullptr : q.initials + ro + Beff,
+        last ? nullptr : hprev + (ro + Beff) * U, last ? nullptr : h->cprev + (ro + Beff) * U, Beff, U);
     RT_LAUNCH_CHECK();
   }
   return RT_OK;
+}
+
+template <int UPC>
+int launch_lstm_tc(rt_learner* h, cudaStream_t st, const CUtensorMap* w0, const CUtensorMap* w1,
+                   const rttc::LstmTcArgs& a, int ctas) {
+  auto kern = rttc::k_lstm_seq_tc<UPC>;
+  const int smem = rttc::LstmSmem<UPC>::total(a.U, a.arows);
+  RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  RT_CUDA(cudaMemsetAsync(h->grid_barrier, 0, 64 * sizeof(unsigned int), st));
+  void* args[] = {(void*)w0, (void*)w1, (void*)&a};
+  // cooperative launch: all CTAs co-resident (they wait on each other's step counters)
+  RT_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(rttc::LSTM_TC_THREADS), args, (size_t)smem, st));
+  rt::launch_counter()++;
+  return RT_OK;
+}
+
+// All recurrences of one phase.  TF32 path: ONE tensor-core launch runs them side by side
+// (sequences of the same network share a CTA group, see rt_lstm_tc.cuh); otherwise one after
+// the other on the fp32 path (the BPTT sequence last: it owns gates / c_all / cprev).
+int lstm_run(rt_learner* h, cudaStream_t st, const SeqDesc* seqs, int nseq, int timesteps, int Beff) {
+  const int U = h->U;
+  const float* nets[2] = {nullptr, nullptr};
+  int groups = 0;
+  bool ok = h->gx.mode == 1 && h->lstm_tc && timesteps > 1 && Beff <= 32 && U % 32 == 0 && U <= 512 &&
+            timesteps <= h->lstm_tcap;
+  rttc::LstmTcArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < nseq && ok; ++i) {
+    int g = 0;
+    while (g < groups && nets[g] != seqs[i].net) ++g;
+    if (g == groups) {
+      if (groups == 2) { ok = false; break; }
+      nets[groups++] = seqs[i].net;
+    }
+    if (a.nseq[g] == rttc::LSTM_MAX_SEQ) { ok = false; break; }
+    rttc::LstmSeq& q = a.seq[g][a.nseq[g]++];
+    q.xg = seqs[i].xg; q.hx = seqs[i].hx; q.cx = seqs[i].cx; q.initials = seqs[i].initials;
+    q.h_all = seqs[i].h_all;
+    q.gates = seqs[i].bptt ? h->gates : nullptr;
+    q.c_all = seqs[i].bptt ? h->c_all : nullptr;
+    q.cprev = seqs[i].bptt ? h->cprev : nullptr;
+    q.hprev = seqs[i].bptt ? h->hprev + (size_t)seqs[i].slot * h->max_rows * U : nullptr;
+  }
+  // narrowest CTA slice (most CTAs, shortest MMA + epilogue per step) that is co-resident and
+  // whose W slice + one step of h fit in shared memory
+  int upc = 0;
+  if (ok) {
+    a.arows = 32 * (a.nseq[0] > a.nseq[1] ? a.nseq[0] : a.nseq[1]);
+    const int cand[2] = {h->lstm_upc == 16 ? 16 : 8, 16};
+    for (int i = 0; i < 2 && !upc; ++i) {
+      const int c = cand[i];
+      const int smem = c == 8 ? rttc::LstmSmem<8>::total(U, a.arows) : rttc::LstmSmem<16>::total(U, a.arows);
+      if (U % c == 0 && groups * (U / c) <= h->num_sms && smem <= 227 * 1024) upc = c;
+    }
+    if (!upc) ok = false;
+  }
+  if (ok) {
+    a.T = timesteps; a.B = Beff; a.U = U;
+    if (const char* e = getenv("RT_LSTM_EXP")) a.exp = atoi(e);
+    a.xchg = h->lstm_xchg;
+    a.counters = h->grid_barrier;
+    a.dbg = h->lstm_dbg;
+    const CUtensorMap *w0 = nullptr, *w1 = nullptr;
+    RT_TRY(get_tmap(h->gx, nets[0] + h->o_whh, U, 4 * U, U, rttc::BLOCK_K, upc, 0, &w0));
+    RT_TRY(get_tmap(h->gx, nets[groups - 1] + h->o_whh, U, 4 * U, U, rttc::BLOCK_K, upc, 0, &w1));
+    const int ctas = groups * (U / upc);
+    if (upc == 8) return launch_lstm_tc<8>(h, st, w0, w1, a, ctas);
+    return launch_lstm_tc<16>(h, st, w0, w1, a, ctas);
+  }
+  for (int i = 0; i < nseq; ++i) RT_TRY(lstm_recur_one(h, st, seqs[i], timesteps, Beff));
+  return RT_OK;
+}
+
+// LSTM forward of one sequence set: input gates + recurrence, output in h->h_all (slot 0).
+int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int rows,
+                 int timesteps, const float* hx, const float* cx, const float* initials) {
+  RT_TRY(lstm_xgates(h, st, net, feat, rows, h->xg));
+  SeqDesc q{net, h->xg, hx, cx, initials, h->h_all, 0, true};
+  return lstm_run(h, st, &q, 1, timesteps, rows / timesteps);
 }
 
 struct StateView {  // device pointers to the (rows, ...) leaves of a batch slice
@@ -1123,7 +1226,10 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     size_t U = h->U;
     RT_TRY(dalloc(h, &h->xg, rows * 4 * U, "xg"));
     RT_TRY(dalloc(h, &h->hg, rows * 4 * U, "hg"));
-    RT_TRY(dalloc(h, &h->hprev, rows * U, "hprev"));
+    RT_TRY(dalloc(h, &h->hprev, 3 * rows * U, "hprev"));   // exchange slots: train / target / selection
+    RT_TRY(dalloc(h, &h->xg2, rows * 4 * U, "xg2"));
+    RT_TRY(dalloc(h, &h->h_all2, rows * U, "h_all2"));
+    RT_TRY(dalloc(h, &h->h_all3, rows * U, "h_all3"));
     RT_TRY(dalloc(h, &h->cprev, rows * U, "cprev"));
     RT_TRY(dalloc(h, &h->gates, rows * 4 * U, "gates"));
     RT_TRY(dalloc(h, &h->c_all, rows * U, "c_all"));
@@ -1186,8 +1292,12 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_REQUIRE(h->A <= 32, "num_actions > 32 not supported by the fused head kernels");
   RT_REQUIRE(h->F % 4 == 0 && h->D % 4 == 0, "fc_size and the quantile-layer width must be multiples of 4");
 
-  RT_TRY(dalloc(h, &h->grid_barrier, 4));
+  RT_TRY(dalloc(h, &h->grid_barrier, 64));
   if (h->U) RT_TRY(dalloc(h, &h->lstm_hrep, (size_t)2 * rtk::LSTM_REP * 32 * h->U));
+  if (h->U && h->U % 32 == 0) {
+    h->lstm_tcap = h->T > h->P ? h->T : h->P;
+    RT_TRY(dalloc(h, &h->lstm_xchg, (size_t)2 * h->lstm_tcap * (h->U / 32) * 128 * 32));
+  }
   if (getenv("RT_DEBUG_TIMELINE")) RT_TRY(dalloc(h, &h->lstm_dbg, 8 * 256, "lstm_dbg"));
   {
     cudaDeviceProp prop;
@@ -1196,6 +1306,10 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     h->gx.num_sms = prop.multiProcessorCount;
     const char* e = getenv("RT_LSTM_STEPWISE");
     if (e && e[0] == '1') h->lstm_persistent = 0;
+    e = getenv("RT_LSTM_TC");
+    if (e && e[0] == '0') h->lstm_tc = 0;
+    e = getenv("RT_LSTM_UPC");
+    if (e && atoi(e) == 16) h->lstm_upc = 16;
     e = getenv("RT_CONV_IM2COL");
     if (e && e[0] == '1') h->conv_implicit = 0;
     e = getenv("RT_CONV_PERSISTENT");
@@ -1351,7 +1465,41 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
 
   // ---- bootstrap target (iqn.py:15-52): target net, then the action-selection net
   bool shared_cnn = false;
-  {
+  StateView svt = view(P);
+  const bool merged = U > 0 && rnn_boot && T > 1;
+  if (merged) {
+    // recurrent model with rnn_bootstrap: the target, selection and training recurrences are
+    // independent, so run both CNNs + input-gate GEMMs first and then ALL recurrences in one
+    // launch (20 dependent steps instead of 60).  The online input gates are computed once
+    // over the T+n distinct rows: the selection pass reads rows [n, T+n), training rows [0, T).
+    StateView sv = view(P + n);
+    RT_TRY(cnn_forward(h, st, h->p[1], sv.x, M));
+    RT_TRY(lstm_xgates(h, st, h->p[1], h->c_out.back(), M, h->xg2));
+    SeqDesc seqs[3];
+    int ns = 0;
+    seqs[ns++] = SeqDesc{h->p[1], h->xg2, sv.hx, sv.cx, sv.initials, h->h_all2, 1, false};
+    if (h->td.double_q) {
+      RT_TRY(cnn_forward(h, st, h->p[0], svt.x, M + n * B));
+      RT_TRY(lstm_xgates(h, st, h->p[0], h->c_out.back(), M + n * B, h->xg));
+      seqs[ns++] = SeqDesc{h->p[0], h->xg + (size_t)n * B * 4 * U, sv.hx, sv.cx, sv.initials, h->h_all3, 2, false};
+    } else {
+      RT_TRY(cnn_forward(h, st, h->p[0], svt.x, M));
+      RT_TRY(lstm_xgates(h, st, h->p[0], h->c_out.back(), M, h->xg));
+    }
+    seqs[ns++] = SeqDesc{h->p[0], h->xg, svt.hx, svt.cx, svt.initials, h->h_all, 0, true};
+    RT_TRY(lstm_run(h, st, seqs, ns, T, B));
+    RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[0]));
+    RT_CUDA(cudaMemcpyAsync(h->tq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (h->td.double_q) RT_TRY(heads_forward(h, st, h->p[0], h->h_all3, M, tau_seg[1]));
+    else RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[1]));
+    RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    size_t off = (size_t)P * B;
+    rtk::k_iqn_target<<<cdiv(M, 128), 128, 0, st>>>(
+        h->tq, h->sq, b->returns + off, b->target_masks + off, (const long long*)b->nsteps + off,
+        h->targets, M, Nq, h->A, (float)h->td.gamma, h->td.vf_scale_epsilon);
+    RT_LAUNCH_CHECK();
+    feat = h->h_all;
+  } else {
     StateView sv = view(P + n);
     int ts = rnn_boot ? T : 1;
     RT_TRY(trunk_forward(h, st, h->p[1], sv, M, ts, &feat));
@@ -1380,19 +1528,19 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
         h->tq, h->sq, b->returns + off, b->target_masks + off, (const long long*)b->nsteps + off,
         h->targets, M, Nq, h->A, (float)h->td.gamma, h->td.vf_scale_epsilon);
     RT_LAUNCH_CHECK();
-  }
 
-  // ---- training forward + loss (iqn.py:54-129)
-  StateView svt = view(P);
-  if (shared_cnn) {
-    feat = h->c_out.back();
-    if (U) {
-      RT_TRY(lstm_forward(h, st, h->p[0], feat, M, T, svt.hx, svt.cx, svt.initials));
-      feat = h->h_all;
+    // ---- training forward (iqn.py:54-129)
+    if (shared_cnn) {
+      feat = h->c_out.back();
+      if (U) {
+        RT_TRY(lstm_forward(h, st, h->p[0], feat, M, T, svt.hx, svt.cx, svt.initials));
+        feat = h->h_all;
+      }
+    } else {
+      RT_TRY(trunk_forward(h, st, h->p[0], svt, M, T, &feat));
     }
-  } else {
-    RT_TRY(trunk_forward(h, st, h->p[0], svt, M, T, &feat));
   }
+  // ---- training heads + loss (iqn.py:54-129)
   RT_TRY(heads_forward(h, st, h->p[0], feat, M, tau_seg[2]));
   RT_CUDA(cudaMemcpyAsync(h->tau, tau_seg[2], (size_t)h->MQ * sizeof(float), cudaMemcpyDeviceToDevice, st));
   const long long* actions = (const long long*)b->policy_outputs[io->po_field_actions] + (size_t)P * B;

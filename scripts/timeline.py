@@ -30,11 +30,18 @@ torch.cuda.synchronize()
 import ctypes as C
 p, cnt = C.c_void_p(), C.c_int64()
 _lib.check(L._lib.rt_learner_debug_tensor(L._h, b"lstm_dbg", C.byref(p), C.byref(cnt)))
-d = _lib.as_tensor(p.value, (256, 8), "<i8", L.device).cpu().numpy()[:T]
-print("LSTM persistent kernel, CTA 0, cycles per phase")
-prev = d[0, 0]
-for t in range(T):
-    print("%2d  xin-issue %5d | h-loads-landed %6d | staged+sync %6d | dots %6d | reduce+cell+stores %6d | "
-          "grid-barrier %6d | step %6d" % (t, d[t, 0] - prev, d[t, 1] - d[t, 0], d[t, 2] - d[t, 1],
-                                           d[t, 3] - d[t, 2], d[t, 4] - d[t, 3], d[t, 5] - d[t, 4], d[t, 5] - prev))
-    prev = d[t, 5]
+dd = _lib.as_tensor(p.value, (256, 8), "<i8", L.device).cpu().numpy()
+for grp in range(2):
+    d = dd[64 * grp:64 * grp + T]
+    print("tensor-core LSTM kernel, first CTA of weight group %d (%s), cycles per phase" % (
+        grp, "target net, 1 sequence" if grp == 0 else "online net, 2 sequences"))
+    prev = d[0, 0]
+    for t in range(T):
+        # stamps: 0 producer saw every CTA's h_{t-1}, 1 last MMA issued, 2 accumulator ready, 5 accumulator
+        # in registers, 6 cell math + h stores issued, 4 h_t published, 3 remaining stores issued
+        if t in (0, 1, 2, 10, 18, 19):
+            print("%2d  publish->seen %6d | TMA+MMA issue %6d | retire %4d | tmem ld %5d | cell+h stores %5d | release %5d | other stores %5d | step %6d" % (
+                t, d[t, 0] - prev, d[t, 1] - d[t, 0], d[t, 2] - d[t, 1], d[t, 5] - d[t, 2], d[t, 6] - d[t, 5],
+                d[t, 4] - d[t, 6], d[t, 3] - d[t, 4], d[t, 4] - prev))
+        prev = d[t, 4]
+    print("whole recurrence: %d cycles" % (d[T - 1, 3] - d[0, 0]))

@@ -240,3 +240,53 @@ def test_learner_full_size_tf32_vs_fp32_path():
         if rel > 5e-2:
             errs.append("grad %s: relative L2 error %.3e" % (k, rel))
     assert not errs, "\n".join(errs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("upc", [16, 8])
+@pytest.mark.parametrize("double_q", [True, False])
+def test_lstm_tensor_core_recurrence_midsize(upc, double_q, monkeypatch):
+    """The multi-sequence tcgen05 recurrence (rt_lstm_tc.cuh) at a shape the goldens do not reach
+    (U = 64, B = 8 < 32 rows per sequence, episode resets inside the window): every saved LSTM
+    tensor of the training sequence, the targets and the per-row TD signal against this library's
+    fp32 path, for both CTA slice widths and with two / three concurrent sequences."""
+    monkeypatch.setenv("RT_LSTM_UPC", str(upc))
+    c = dict(in_shape=(4, 20, 20), conv=[(32, 8, 4), (32, 2, 1)], lstm=64, fc=32, actions=4, nq=8,
+             embed=16, dueling=True, B=8, T=6, P=0, n=2, gamma=0.99, double_q=double_q,
+             rnn_bootstrap=True, vf_eps=None, clip_grad=40.0, adam_eps=1e-5)
+    rs = np.random.RandomState(5)
+    S, B, n, U = c["T"], c["B"], c["n"], c["lstm"]
+    raw = {
+        "all_x": rs.randint(0, 256, (S + n, B) + c["in_shape"]).astype(np.uint8),
+        "all_hx": rs.randn(S + n, B, U).astype(np.float32),
+        "all_cx": rs.randn(S + n, B, U).astype(np.float32),
+        "all_initials": (rs.rand(S + n, B) < 0.2).astype(np.float32),
+        "returns": np.sign(rs.randn(S, B)), "nsteps": np.full((S, B), n, dtype=np.int64),
+        "target_masks": (rs.rand(S, B) > 0.05).astype(np.float64),
+        "actions": rs.randint(0, c["actions"], (S, B)).astype(np.int64),
+        "importance_weights": rs.rand(S, B) * 0.5 + 0.5,
+    }
+    spec = spec_of(c)
+    p_on, p_tg = spec.init_params(1), spec.init_params(2)
+    gen = torch.Generator().manual_seed(3)
+    M = c["T"] * c["B"]
+    taus = [torch.rand(M * c["nq"], generator=gen) for _ in range(3)]
+    names = {"h_all": (M, U), "gates": (M, 4 * U), "c_all": (M, U), "cprev": (M, U), "hprev": (M, U),
+             "h_all2": (M, U), "targets": (M, c["nq"])}
+    out = {}
+    for mode in ("fp32", "tf32"):
+        L = make_learner(c, gemm=mode)
+        try:
+            L.load_state_dict(p_on, 0)
+            L.load_state_dict(p_tg, 1)
+            b, keep = device_batch(raw, c)
+            L.step(b, taus)
+            out[mode] = {k: L.debug(k, shp).cpu().numpy() for k, shp in names.items()}
+            out[mode]["report"] = L.td_abs().cpu().numpy()
+            out[mode]["qloss"] = L.stats()["qloss"]
+        finally:
+            L.close()
+    errs = []
+    for k in list(names) + ["report", "qloss"]:
+        report_diff(errs, k, out["tf32"][k], out["fp32"][k], 2e-3, 2e-3)
+    assert not errs, "\n".join(errs)
