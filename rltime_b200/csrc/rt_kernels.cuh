@@ -305,19 +305,23 @@ __global__ void k_lstm_cell(const float* __restrict__ xg, const float* __restric
 }
 
 // BPTT cell: dh = dout[t] + dh_carry; produces pre-activation gate grads and the carries.
-// `next_initials` = initials of step t+1: dh_carry arrives unmasked from (dgates[t+1] . W_hh) and
-// passes through step t+1's episode-reset mask here.
-__global__ void k_lstm_cell_bwd(const float* __restrict__ dout, const float* __restrict__ dh_carry,
-                                float* __restrict__ dc_carry, const float* __restrict__ gates,
-                                const float* __restrict__ c, const float* __restrict__ cprev,
-                                const float* __restrict__ initials, const float* __restrict__ next_initials,
-                                float* __restrict__ dgates, int B, int U) {
+// dh_carry = (dgates[t+1] . W_hh) arrives as `nparts` raw split-K partials (`parts`, part_stride
+// floats apart; nparts = 1: the finished product) that are folded here in a fixed order, and
+// passes through step t+1's episode-reset mask (`next_initials`).
+__global__ void k_lstm_cell_bwd(const float* __restrict__ dout, const float* __restrict__ parts, int nparts,
+                                size_t part_stride, float* __restrict__ dc_carry,
+                                const float* __restrict__ gates, const float* __restrict__ c,
+                                const float* __restrict__ cprev, const float* __restrict__ initials,
+                                const float* __restrict__ next_initials, float* __restrict__ dgates, int B,
+                                int U) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * U) return;
   int b = i / U, u = i - b * U;
   size_t g0 = (size_t)b * 4 * U + u;
   float gi = gates[g0], gf = gates[g0 + U], gg = gates[g0 + 2 * U], go = gates[g0 + 3 * U];
-  float dh = dout[i] + (dh_carry ? dh_carry[i] * (1.f - next_initials[b]) : 0.f);
+  float carry = 0.f;
+  for (int p = 0; p < nparts; ++p) carry += parts[(size_t)p * part_stride + i];
+  float dh = dout[i] + (nparts ? carry * (1.f - next_initials[b]) : 0.f);
   float tc = tanhf(c[i]);
   float dc = dc_carry[i] + dh * go * (1.f - tc * tc);
   dgates[g0] = dc * gg * gi * (1.f - gi);

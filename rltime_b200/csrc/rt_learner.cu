@@ -54,6 +54,10 @@ struct GemmCtx {
   int force_bn = 0, force_stages = 0;   // tuning overrides (RT_TC_BN / RT_TC_STAGES, rt_gemm_bench)
   long long* dbg = nullptr;             // clock64 stamps of CTA 0 (rt_gemm_bench)
   int persistent = 1;                   // overlap epilogue with the next tile (k_gemm_tc_p)
+  // split-K partials left in `ws` for a fused consumer (BPTT cell kernel) instead of k_splitk_reduce
+  int defer_reduce = 0;
+  int last_splits = 1;                  // splits of the last GEMM (1: the result is in C)
+  int split_min_kb = 16;                // fewest k-blocks a tcgen05 split may get
   int num_sms = 148;
   // live timing of every GEMM-shaped launch (bench.py roofline): CUDA events on the launch stream
   bool profile = false;
@@ -243,7 +247,8 @@ int gemm_simt(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   rtk::k_sgemm<BM, BN, BK, 8, 4><<<grid, 256, 0, st>>>(g);
   RT_LAUNCH_CHECK();
   cx.simt_launches++;
-  if (splits > 1) {
+  cx.last_splits = splits;
+  if (splits > 1 && !cx.defer_reduce) {
     size_t total = (size_t)g.M * g.N;
     rtk::k_splitk_reduce<<<cdiv(total, 32), dim3(32, 8), 0, st>>>(g, splits);
     RT_LAUNCH_CHECK();
@@ -358,7 +363,7 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   int splits = 1;
   if (tiles < 74 && num_kb >= 64) {
     splits = (int)((148 + tiles - 1) / tiles);
-    if (splits > num_kb / 16) splits = num_kb / 16;
+    if (splits > num_kb / cx.split_min_kb) splits = num_kb / cx.split_min_kb;
     if (splits > 32) splits = 32;
     size_t per = (size_t)g.M * g.N;
     if ((size_t)splits * per > cx.ws_floats) splits = (int)(cx.ws_floats / per);
@@ -396,7 +401,8 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
 #undef RT_TC_CASE
   if (rc != RT_OK) return rc;
   cx.tc_launches++;
-  if (splits > 1) {
+  cx.last_splits = splits;
+  if (splits > 1 && !cx.defer_reduce) {
     size_t total = (size_t)g.M * g.N;
     rtk::k_splitk_reduce<<<cdiv(total, 32), dim3(32, 8), 0, st>>>(a.g, splits);
     RT_LAUNCH_CHECK();
@@ -954,16 +960,30 @@ int lstm_backward(rt_learner* h, cudaStream_t st, const float* net, const float*
   float* G = h->grad;
   int nb = cdiv((size_t)Beff * U, 256);
   RT_CUDA(cudaMemsetAsync(h->dc_carry, 0, (size_t)Beff * U * sizeof(float), st));
+  // dh_carry = dgates[t+1] . W_hh is a skinny GEMM (M = B rows, K = 4U): it runs split-K over as
+  // many CTAs as there are SMs and leaves the raw partials in the workspace; the cell kernel of
+  // step t folds them (fixed order) while it forms dh, so no reduce launch sits between the steps
+  const float* parts = nullptr;
+  int nparts = 0;
+  const size_t part_stride = (size_t)Beff * U;
   for (int t = timesteps - 1; t >= 0; --t) {
     size_t ro = (size_t)t * Beff;
     rtk::k_lstm_cell_bwd<<<nb, 256, 0, st>>>(
-        h->dfeatq + ro * U, t == timesteps - 1 ? nullptr : h->dh_carry, h->dc_carry,
+        h->dfeatq + ro * U, parts, nparts, part_stride, h->dc_carry,
         h->gates + ro * 4 * U, h->c_all + ro * U, h->cprev + ro * U, initials + ro,
         t == timesteps - 1 ? nullptr : initials + ro + Beff, h->dgates + ro * 4 * U, Beff, U);
     RT_LAUNCH_CHECK();
-    if (t > 0)
-      RT_TRY(gemm(h->gx, st, mk(h->dgates + ro * 4 * U, 4 * U, 0, net + h->o_whh, U, 0, h->dh_carry, U,
-                            Beff, U, 4 * U)));
+    if (t > 0) {
+      h->gx.defer_reduce = 1;
+      h->gx.split_min_kb = 8;
+      int rc = gemm(h->gx, st, mk(h->dgates + ro * 4 * U, 4 * U, 0, net + h->o_whh, U, 0, h->dh_carry, U,
+                                   Beff, U, 4 * U));
+      h->gx.defer_reduce = 0;
+      h->gx.split_min_kb = 16;
+      RT_TRY(rc);
+      nparts = h->gx.last_splits;
+      parts = nparts > 1 ? h->gx.ws : h->dh_carry;
+    }
   }
   RT_TRY(gemm(h->gx, st, mk(h->dgates, 4 * U, 1, h->hprev, U, 0, G + h->o_whh, U, 4 * U, U, rows)));
   RT_TRY(gemm(h->gx, st, mk(h->dgates, 4 * U, 1, feat, h->feat, 0, G + h->o_wih, h->feat, 4 * U, h->feat, rows)));
