@@ -89,6 +89,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills the chunk.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once all prior cp.async of this thread landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout).
 //   layout 2 = SWIZZLE_128B          (16-byte chunks XOR row%8; K-major operands)
 //   layout 1 = SWIZZLE_128B_BASE32B  (32-byte chunks XOR row%4; the only swizzled layout the
@@ -702,6 +711,31 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvA
         }
       }
     };
+    if (!IN_U8) {
+      // fp32 NHWC input: a chunk is a plain 16-byte copy, so the producers issue LDGSTS straight
+      // into the swizzled stage and never wait for the data themselves: every free stage is in
+      // flight at once (the register-staged version kept ONE k-block per thread in flight and a
+      // 128 x 32 tile of conv1 took ~14 us, nearly all of it load latency).  The MMA thread
+      // orders the landed generic-proxy writes before its async-proxy reads.
+      const float* in = static_cast<const float*>(a.in);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int k = kb * BLOCK_K;
+        const int c0 = k % a.C, tap = k / a.C;
+        const int kw = tap % a.KH, kh = tap / a.KH;
+        const long long koff = ((long long)kh * a.W + kw) * a.C + c0 + 4 * j;
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 16 + (t >> 3);
+          const bool ok = base[i] >= 0;
+          cp_async16(sa + r * 128 + ((j ^ (r & 7)) << 4), ok ? in + base[i] + koff : in, ok ? 16u : 0u);
+        }
+        cp_async_arrive(&full_bar[s]);
+      }
+    } else {
     // software pipeline: the loads of k-block kb+1 are in flight while kb waits for its stage
     float4 cur[8], nxt[8];
     gather(0, cur);
@@ -720,6 +754,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvA
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
 #pragma unroll
       for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+    }
     }
     // ---------------- epilogue (same warps: TMEM lane quarter == warp)
     mbar_wait(tmem_full, 0);
@@ -754,6 +789,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvA
         int s = kb % STAGES;
         uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
+        if (!IN_U8) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async writes -> MMA reads
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         uint32_t sb = sa + A_BYTES;
@@ -1091,6 +1127,33 @@ k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Con
         }
       }
     };
+    if (!IN_U8) {
+      // fp32 NHWC input: LDGSTS straight into the swizzled atoms, all free stages in flight
+      const float* in = static_cast<const float*>(a.in);
+      const int r = t >> 3;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int p = (kb0 + kb) * BLOCK_K + r;
+        long long base = -1;
+        if (p < a.P) {
+          int ow = p % a.OW;
+          int oh = (p / a.OW) % a.OH;
+          long long img = p / (a.OW * a.OH);
+          base = ((img * a.H + (long long)oh * a.S) * a.W + (long long)ow * a.S) * a.C;
+        }
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const uint32_t sb = smem_u32(smem + s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+        for (int at = 0; at < NAT; ++at) {
+          const bool ok = base >= 0 && kvalid[at];
+          // 128B_BASE32B swizzle: 32-byte chunk index XOR (row % 4), 16-byte half preserved
+          cp_async16(sb + at * (BLOCK_K * 128) + r * 128 + ((((j >> 1) ^ (r & 3)) << 5) | ((j & 1) << 4)),
+                     ok ? in + base + koff[at] : in, ok ? 16u : 0u);
+        }
+        cp_async_arrive(&full_bar[s]);
+      }
+    } else {
     float4 cur[NAT], nx1[NAT], nx2[NAT];
     if (num_kb > 0) gather(0, cur);
     if (num_kb > 1) gather(1, nx1);
@@ -1113,6 +1176,7 @@ k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Con
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
 #pragma unroll
       for (int q = 0; q < NAT; ++q) { cur[q] = nx1[q]; nx1[q] = nx2[q]; }
+    }
     }
     if (warp < 4) {
     // ---------------- epilogue: rows < F of the accumulator -> raw split-K partial
@@ -1152,6 +1216,7 @@ k_convdw_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ Con
         int s = kb % STAGES;
         uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
+        if (!IN_U8) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async writes -> MMA reads
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         uint32_t sb = sa + A_BYTES;

@@ -134,6 +134,26 @@ __global__ void k_splitk_reduce(const __grid_constant__ GemmArgs g, int splits) 
   }
 }
 
+// ------------------------------------------------------------------------ frame layout
+// uint8 NCHW frames (as acted / stored in the replay buffer) -> fp32 NHWC scaled by 1/255
+// (rltime/models/torch/modules/cnn.py:44-45).  One thread per pixel: the C channel planes are read
+// coalesced along W, the pixel's channels are written as one run (16 bytes at C = 4).
+__global__ void k_u8_nchw_to_f32_nhwc(const uint8_t* __restrict__ x, float* __restrict__ xf, size_t pixels,
+                                      int C, int HW, float scale) {
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += (size_t)gridDim.x * blockDim.x) {
+    size_t img = p / HW, hw = p - img * HW;
+    const uint8_t* src = x + img * (size_t)C * HW + hw;
+    float* dst = xf + p * C;
+    if (C == 4) {
+      *reinterpret_cast<float4*>(dst) =
+          make_float4(__fmul_rn((float)src[0], scale), __fmul_rn((float)src[HW], scale),
+                      __fmul_rn((float)src[2 * (size_t)HW], scale), __fmul_rn((float)src[3 * (size_t)HW], scale));
+    } else {
+      for (int c = 0; c < C; ++c) dst[c] = __fmul_rn((float)src[(size_t)c * HW], scale);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ im2col
 // conv input NCHW uint8 frames (the replay batch), fused x.float() * (1/255)
 // (rltime/models/torch/modules/cnn.py:44-45).  col[(m,oh,ow), (c,kh,kw)].

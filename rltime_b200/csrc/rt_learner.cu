@@ -123,6 +123,7 @@ struct rt_learner {
   std::vector<float*> c_out;   // conv outputs
   std::vector<float*> d_c;     // conv output grads
   float *col = nullptr, *dcol = nullptr;
+  float* xf = nullptr;         // frames as fp32 NHWC * (1/255): every conv layer reads NHWC runs
   float *xg = nullptr, *hg = nullptr, *hprev = nullptr, *cprev = nullptr, *gates = nullptr,
         *c_all = nullptr, *h_all = nullptr;
   float *tau = nullptr, *cf = nullptr, *phi = nullptr, *xq = nullptr, *h1 = nullptr, *v1 = nullptr,
@@ -471,16 +472,10 @@ int grid1d(size_t n, int threads = 256) {
   return (int)b;
 }
 
-int launch_im2col_u8(cudaStream_t st, const uint8_t* xin, float* col, int rc, const ConvL& L, float scale) {
-  size_t n = (size_t)rc * L.hout * L.wout * L.K;
-  bool vec = (L.k % 4 == 0) && (L.s % 4 == 0) && (L.win % 4 == 0) && (((uintptr_t)xin & 3) == 0) &&
-             ((L.cin * L.hin * L.win) % 4 == 0);
-  if (vec)
-    rtk::k_im2col_u8_nchw<4><<<grid1d(n / 4), 256, 0, st>>>(xin, col, rc, L.cin, L.hin, L.win, L.k, L.s,
-                                                            L.hout, L.wout, scale);
-  else
-    rtk::k_im2col_u8_nchw<1><<<grid1d(n), 256, 0, st>>>(xin, col, rc, L.cin, L.hin, L.win, L.k, L.s,
-                                                        L.hout, L.wout, scale);
+// uint8 NCHW frames (the replay batch) -> fp32 NHWC * (1/255) (cnn.py:44-45), once per pass
+int launch_frames_to_nhwc(cudaStream_t st, const uint8_t* x, float* xf, int rows, int C, int H, int W, float scale) {
+  size_t pixels = (size_t)rows * H * W;
+  rtk::k_u8_nchw_to_f32_nhwc<<<grid1d(pixels), 256, 0, st>>>(x, xf, pixels, C, H * W, scale);
   RT_LAUNCH_CHECK();
   return RT_OK;
 }
@@ -535,9 +530,10 @@ bool conv_tc_eligible(const rt_learner* h, size_t i, const void* xin) {
   const ConvL& L = h->conv[i];
   if (h->gx.mode != 1 || !h->conv_implicit) return false;
   if (L.K % 32 || L.f % 4 || L.f > 128) return false;
-  if (i == 0) return L.k % 4 == 0 && L.s % 4 == 0 && L.win % 4 == 0 && ((uintptr_t)xin & 3) == 0 &&
-                     (L.cin * L.hin * L.win) % 4 == 0;
-  return L.cin % 32 == 0 && ((uintptr_t)xin & 15) == 0;
+  // fp32 NHWC input: every 32-float k-block must be one contiguous run inside a patch row
+  // (kw, c): whole channel blocks (C % 32 == 0) or whole patch rows (conv1: 8 pixels x 4 channels)
+  return L.cin % 4 == 0 && (L.cin % 32 == 0 || (L.k * L.cin) % 32 == 0 && 32 % L.cin == 0) &&
+         ((uintptr_t)xin & 15) == 0;
 }
 
 int conv_forward_tc(rt_learner* h, cudaStream_t st, const float* net, size_t i, const void* xin,
@@ -559,19 +555,9 @@ int conv_forward_tc(rt_learner* h, cudaStream_t st, const float* net, size_t i, 
   // CTA (conv1 103 vs 120 us, conv2/3 34 vs 50 us), so the persistent form is opt-in
   if (h->conv_persistent && tiles > h->num_sms) {
     const int ctas = h->num_sms;
-    if (i == 0) {
-      if (BN == 32) return launch_conv_tc_p<32, 1>(tb, a, ctas, st);
-      if (BN == 64) return launch_conv_tc_p<64, 1>(tb, a, ctas, st);
-      return launch_conv_tc_p<128, 1>(tb, a, ctas, st);
-    }
     if (BN == 32) return launch_conv_tc_p<32, 0>(tb, a, ctas, st);
     if (BN == 64) return launch_conv_tc_p<64, 0>(tb, a, ctas, st);
     return launch_conv_tc_p<128, 0>(tb, a, ctas, st);
-  }
-  if (i == 0) {
-    if (BN == 32) return launch_conv_tc<32, 1>(tb, a, st);
-    if (BN == 64) return launch_conv_tc<64, 1>(tb, a, st);
-    return launch_conv_tc<128, 1>(tb, a, st);
   }
   if (BN == 32) return launch_conv_tc<32, 0>(tb, a, st);
   if (BN == 64) return launch_conv_tc<64, 0>(tb, a, st);
@@ -618,15 +604,9 @@ int conv_dw_tc(rt_learner* h, cudaStream_t st, size_t i, const void* xin, const 
   dim3 grid(tiles, 1, splits);
   h->gx.tc_launches++;
   ProfScope ps(h->gx, st, 2.0 * a.P * (double)L.f * L.K);
-  if (i == 0) {
-    if (BN == 32) RT_TRY((launch_convdw_tc<32, 1>(ta, a, grid, st)));
-    else if (BN == 64) RT_TRY((launch_convdw_tc<64, 1>(ta, a, grid, st)));
-    else RT_TRY((launch_convdw_tc<128, 1>(ta, a, grid, st)));
-  } else {
-    if (BN == 32) RT_TRY((launch_convdw_tc<32, 0>(ta, a, grid, st)));
-    else if (BN == 64) RT_TRY((launch_convdw_tc<64, 0>(ta, a, grid, st)));
-    else RT_TRY((launch_convdw_tc<128, 0>(ta, a, grid, st)));
-  }
+  if (BN == 32) RT_TRY((launch_convdw_tc<32, 0>(ta, a, grid, st)));
+  else if (BN == 64) RT_TRY((launch_convdw_tc<64, 0>(ta, a, grid, st)));
+  else RT_TRY((launch_convdw_tc<128, 0>(ta, a, grid, st)));
   rtk::GemmArgs g = mk(nullptr, 0, 0, nullptr, 0, 0, dW, L.K, L.f, L.K, a.P);
   g.ws = h->gx.ws;
   size_t total = (size_t)L.f * L.K;
@@ -635,16 +615,17 @@ int conv_dw_tc(rt_learner* h, cudaStream_t st, size_t i, const void* xin, const 
   return RT_OK;
 }
 
-// CNN forward for `rows` frames, chunked so the im2col buffers stay L2-resident.
+// CNN forward for `rows` frames: frames to fp32 NHWC once, then every layer is an implicit GEMM
+// over NHWC runs (fallback: im2col + GEMM, chunked so the im2col buffers stay L2-resident).
 int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows) {
-  const float scale = (float)(1.0 / 255.0);
+  RT_TRY(launch_frames_to_nhwc(st, x, h->xf, rows, h->md.in_c, h->md.in_h, h->md.in_w, (float)(1.0 / 255.0)));
   {
     bool all = true;
     for (size_t i = 0; i < h->conv.size(); ++i)
-      all = all && conv_tc_eligible(h, i, i == 0 ? (const void*)x : (const void*)h->c_out[i - 1]);
+      all = all && conv_tc_eligible(h, i, i == 0 ? (const void*)h->xf : (const void*)h->c_out[i - 1]);
     if (all) {
       for (size_t i = 0; i < h->conv.size(); ++i)
-        RT_TRY(conv_forward_tc(h, st, net, i, i == 0 ? (const void*)x : (const void*)h->c_out[i - 1],
+        RT_TRY(conv_forward_tc(h, st, net, i, i == 0 ? (const void*)h->xf : (const void*)h->c_out[i - 1],
                                h->c_out[i], rows));
       return RT_OK;
     }
@@ -654,16 +635,8 @@ int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t*
     for (size_t i = 0; i < h->conv.size(); ++i) {
       const ConvL& L = h->conv[i];
       size_t opix = (size_t)L.hout * L.wout;
-      size_t n_col = (size_t)rc * opix * L.K;
-      if (i == 0) {
-        const uint8_t* xin = x + (size_t)r0 * L.cin * L.hin * L.win;
-        RT_TRY(launch_im2col_u8(st, xin, h->col, rc, L, scale));
-      } else {
-        const ConvL& Lp = h->conv[i - 1];
-        const float* xin = h->c_out[i - 1] + (size_t)r0 * Lp.hout * Lp.wout * Lp.f;
-        RT_TRY(launch_im2col_f32(st, xin, h->col, rc, L));
-      }
-      RT_LAUNCH_CHECK();
+      const float* xin = (i == 0 ? h->xf : h->c_out[i - 1]) + (size_t)r0 * L.hin * L.win * L.cin;
+      RT_TRY(launch_im2col_f32(st, xin, h->col, rc, L));
       float* out = h->c_out[i] + (size_t)r0 * opix * L.f;
       rtk::GemmArgs g = mk(h->col, L.K, 0, net + L.w, L.K, 1, out, L.f, (int)(rc * opix), L.f, L.K);
       g.bias = net + L.b;
@@ -998,7 +971,7 @@ int lstm_backward(rt_learner* h, cudaStream_t st, const float* net, const float*
 // Conv stack backward; `dlast` = gradient w.r.t. the (post-ReLU) last conv output.
 int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows,
                  float* dlast) {
-  const float scale = (float)(1.0 / 255.0);
+  (void)x;   // the frames of this pass are already in h->xf (fp32 NHWC), see cnn_forward
   float* G = h->grad;
   int nl = (int)h->conv.size();
   {
@@ -1010,7 +983,7 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
   {
     bool all = h->conv_implicit_bwd != 0;
     for (int i = 0; i < nl; ++i)
-      all = all && conv_tc_eligible(h, i, i == 0 ? (const void*)x : (const void*)h->c_out[i - 1]) &&
+      all = all && conv_tc_eligible(h, i, i == 0 ? (const void*)h->xf : (const void*)h->c_out[i - 1]) &&
             h->conv[i].f % 4 == 0;
     if (all) {
       // whole batch at once: implicit-GEMM dW (no im2col), one dcol GEMM + col2im per layer
@@ -1018,7 +991,7 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
         const ConvL& L = h->conv[i];
         size_t opix = (size_t)L.hout * L.wout;
         float* dy = i == nl - 1 ? dlast : h->d_c[i];
-        const void* xin = i == 0 ? (const void*)x : (const void*)h->c_out[i - 1];
+        const void* xin = i == 0 ? (const void*)h->xf : (const void*)h->c_out[i - 1];
         RT_TRY(conv_dw_tc(h, st, i, xin, dy, rows, G + L.w));
         RT_TRY(colsum(h, st, dy, (size_t)rows * opix, L.f, G + L.b, 0));
         if (i > 0) {
@@ -1040,18 +1013,12 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
     for (int i = nl - 1; i >= 0; --i) {
       const ConvL& L = h->conv[i];
       size_t opix = (size_t)L.hout * L.wout;
-      size_t n_col = (size_t)rc * opix * L.K;
       float* dy = (i == nl - 1 ? dlast : h->d_c[i]) + (size_t)r0 * opix * L.f;
       // recompute this layer's im2col input
-      if (i == 0) {
-        const uint8_t* xin = x + (size_t)r0 * L.cin * L.hin * L.win;
-        RT_TRY(launch_im2col_u8(st, xin, h->col, rc, L, scale));
-      } else {
-        const ConvL& Lp = h->conv[i - 1];
-        const float* xin = h->c_out[i - 1] + (size_t)r0 * Lp.hout * Lp.wout * Lp.f;
+      {
+        const float* xin = (i == 0 ? h->xf : h->c_out[i - 1]) + (size_t)r0 * L.hin * L.win * L.cin;
         RT_TRY(launch_im2col_f32(st, xin, h->col, rc, L));
       }
-      RT_LAUNCH_CHECK();
       rtk::GemmArgs g = mk(dy, L.f, 1, h->col, L.K, 0, G + L.w, L.K, L.f, L.K, (int)(rc * opix));
       g.accumulate = first ? 0 : 1;
       RT_TRY(gemm(h->gx, st, g));
@@ -1156,7 +1123,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     L.K = c * L.k * L.k;
     char nm[96];
     snprintf(nm, sizeof(nm), "model.layers.0.layers.%d.weight", i);
-    L.w = add_param(h, nm, {L.f, c, L.k, L.k}, i == 0 ? PERM_NONE : PERM_CONV, c, L.k);
+    L.w = add_param(h, nm, {L.f, c, L.k, L.k}, PERM_CONV, c, L.k);
     snprintf(nm, sizeof(nm), "model.layers.0.layers.%d.bias", i);
     L.b = add_param(h, nm, {L.f}, PERM_NONE);
     h->conv.push_back(L);
@@ -1232,6 +1199,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     size_t cc = (size_t)h->chunk_rows * opix * L.K;
     if (cc > maxcol) maxcol = cc;
   }
+  RT_TRY(dalloc(h, &h->xf, rows * (size_t)md->in_c * md->in_h * md->in_w, "xf"));
   RT_TRY(dalloc(h, &h->col, maxcol));
   RT_TRY(dalloc(h, &h->dcol, maxcol));
   {
