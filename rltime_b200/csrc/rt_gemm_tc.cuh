@@ -912,6 +912,28 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Con
           }
         }
       };
+      if (!IN_U8) {
+        // fp32 NHWC: LDGSTS straight into the swizzled stage, all free stages in flight
+        const float* in = static_cast<const float*>(a.in);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int k = kb * BLOCK_K;
+          const int cc = k % a.C, tap = k / a.C;
+          const int kw = tap % a.KH, kh = tap / a.KH;
+          const long long koff = ((long long)kh * a.W + kw) * a.C + cc + 4 * j;
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = i * 32 + (t >> 3);
+            const bool ok = base[i] >= 0;
+            cp_async16(sa + r * 128 + ((j ^ (r & 7)) << 4), ok ? in + base[i] + koff : in, ok ? 16u : 0u);
+          }
+          cp_async_arrive(&full_bar[s]);
+        }
+        continue;
+      }
       // two k-blocks of loads in flight ahead of the one being stored
       float4 c0[4], c1[4], c2[4];
       gather(0, c0);
@@ -932,7 +954,7 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Con
 #pragma unroll
         for (int i = 0; i < 4; ++i) { c0[i] = c1[i]; c1[i] = c2[i]; }
       }
-    }
+        }
   } else if (warp == 8) {
     if (lane == 0) {
       uint32_t it = 0;
@@ -962,6 +984,7 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Con
           int s = it % STAGES;
           uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
+          if (!IN_U8) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async writes -> MMA reads
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           uint32_t sb = sa + A_BYTES;
@@ -999,6 +1022,204 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Con
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
         }
         if (n0 + c * 32 < a.N) epilogue_chunk(e, ew, v, stage, lane, m0 + q * 32, n0 + c * 32);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 9) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ----------------------------------------------------- implicit-GEMM conv data gradient
+// dx[img,h,w,c] = relu'(act) * sum_{kh,kw,f} dy[img,(h-kh)/S,(w-kw)/S,f] W[f,kh,kw,c] without the
+// dcol buffer / col2im scatter.  Input pixels are split into S*S parity classes (h%S, w%S): inside a
+// class only the taps kh = S*dh + h%S, kw = S*dw + w%S contribute, so each class is a dense
+// stride-1 "full" correlation of dy with (KH/S)^2 taps:
+//   A row = class pixel (img,hh,ww), k = (dh,dw,f): dy[img, hh-dh, ww-dw, f..]  (zero outside dy)
+//   B     = Wt[class][c][(dh,dw,f)]  (re-laid copy of the filters, rtk::k_conv_wT)
+// Persistent CTA as k_conv_tc_p: 8 LDGSTS producer warps (zero-fill for the border taps), TMA for
+// the filter tile, double-buffered TMEM accumulator; the epilogue applies the ReLU mask of the
+// forward activation and writes each pixel's C channels as one run.
+struct ConvDxArgs {
+  const float* dy;     // [rows][OH][OW][F]
+  const float* act;    // forward input of the layer (post-ReLU), [rows][H][W][C]: mask = act > 0
+  float* dx;           // [rows][H][W][C]
+  int rows, C, H, W, KH, S, OH, OW, F;
+  int Hc, Wc;          // class grid: ceil(H/S), ceil(W/S)
+  int KD;              // taps per dimension inside a class = KH / S
+  int Kc;              // KD*KD*F
+  int Mc;              // rows*Hc*Wc
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(CONV_P_THREADS)
+k_convdx_tc(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvDxArgs a) {
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
+  constexpr int B_BYTES = BN * BLOCK_K * 4;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = a.Kc / BLOCK_K;
+  const int tiles_m = (a.Mc + BLOCK_M - 1) / BLOCK_M;
+  const int total_tiles = a.S * a.S * tiles_m;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+
+  if (warp == 8 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 256 + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ---------------- A gather: thread t owns 16-byte chunk j = t % 8 of rows i*32 + t/8, i < 4
+    const int t = threadIdx.x;
+    const int j = t & 7;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile % tiles_m) * BLOCK_M;
+      int hh[4], ww[4];
+      long long ibase[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + i * 32 + (t >> 3);
+        if (gm < a.Mc) {
+          ww[i] = gm % a.Wc;
+          hh[i] = (gm / a.Wc) % a.Hc;
+          ibase[i] = (long long)(gm / (a.Wc * a.Hc)) * a.OH * a.OW;
+        } else {
+          ww[i] = hh[i] = -(1 << 20);   // every tap falls outside dy
+          ibase[i] = 0;
+        }
+      }
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int k = kb * BLOCK_K;
+        const int f0 = k % a.F, tapi = k / a.F;
+        const int dw = tapi % a.KD, dh = tapi / a.KD;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 32 + (t >> 3);
+          const int oh = hh[i] - dh, ow = ww[i] - dw;
+          const bool ok = oh >= 0 && oh < a.OH && ow >= 0 && ow < a.OW;
+          const float* src = ok ? a.dy + ((ibase[i] + (long long)oh * a.OW + ow) * a.F + f0 + 4 * j) : a.dy;
+          cp_async16(sa + r * 128 + ((j ^ (r & 7)) << 4), src, ok ? 16u : 0u);
+        }
+        cp_async_arrive(&full_bar[s]);
+      }
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int cls = tile / tiles_m;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          int s = it % STAGES;
+          uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], B_BYTES);
+          tma_load_2d(&tmB, &full_bar[s], smem + s * STAGE_BYTES + A_BYTES, kb * BLOCK_K, cls * a.C);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BLOCK_M >> 4) << 24);
+      uint32_t it = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          int s = it % STAGES;
+          uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async writes -> MMA reads
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_tf32(d_tmem, make_smem_desc(sa + k * (UMMA_K * 4), 16, 1024, 2),
+                      make_smem_desc(sb + k * (UMMA_K * 4), 16, 1024, 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps 10..13: TMEM lane = class pixel; mask + one run per pixel
+    const int q = warp & 3;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int cls = tile / tiles_m;
+      const int php = cls / a.S, pwp = cls % a.S;
+      const int gm = (tile % tiles_m) * BLOCK_M + q * 32 + lane;
+      long long off = -1;
+      if (gm < a.Mc) {
+        const int w = (gm % a.Wc) * a.S + pwp;
+        const int h = ((gm / a.Wc) % a.Hc) * a.S + php;
+        const long long img = gm / (a.Wc * a.Hc);
+        if (h < a.H && w < a.W) off = ((img * a.H + h) * a.W + w) * a.C;
+      }
+      const int acc = lt & 1;
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        if (c == BN / 32 - 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0)
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
+        }
+        if (off >= 0) {
+          const float4* mk = reinterpret_cast<const float4*>(a.act + off + c * 32);
+          float4* dst = reinterpret_cast<float4*>(a.dx + off + c * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 m4 = __ldg(mk + i);
+            dst[i] = make_float4(m4.x > 0.f ? __uint_as_float(v[4 * i]) : 0.f,
+                                 m4.y > 0.f ? __uint_as_float(v[4 * i + 1]) : 0.f,
+                                 m4.z > 0.f ? __uint_as_float(v[4 * i + 2]) : 0.f,
+                                 m4.w > 0.f ? __uint_as_float(v[4 * i + 3]) : 0.f);
+          }
+        }
       }
     }
   }

@@ -154,6 +154,23 @@ __global__ void k_u8_nchw_to_f32_nhwc(const uint8_t* __restrict__ x, float* __re
   }
 }
 
+// Filters [f][kh][kw][c] (internal layout) -> Wt[class (ph,pw)][c][(dh,dw,f)] with kh = S*dh + ph,
+// kw = S*dw + pw: the K-major B operand of the data-gradient implicit GEMM (rttc::k_convdx_tc).
+__global__ void k_conv_wT(const float* __restrict__ w, float* __restrict__ wt, int F, int KH, int S, int C) {
+  const int KD = KH / S;
+  const size_t total = (size_t)F * KH * KH * C;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t r = idx;
+    const int f = (int)(r % F); r /= F;
+    const int dw = (int)(r % KD); r /= KD;
+    const int dh = (int)(r % KD); r /= KD;
+    const int c = (int)(r % C); r /= C;
+    const int cls = (int)r;
+    const int kh = S * dh + cls / S, kw = S * dw + cls % S;
+    wt[idx] = w[(((size_t)f * KH + kh) * KH + kw) * C + c];
+  }
+}
+
 // ------------------------------------------------------------------------------ im2col
 // conv input NCHW uint8 frames (the replay batch), fused x.float() * (1/255)
 // (rltime/models/torch/modules/cnn.py:44-45).  col[(m,oh,ow), (c,kh,kw)].

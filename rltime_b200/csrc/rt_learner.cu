@@ -148,7 +148,9 @@ struct rt_learner {
   float *h_all2 = nullptr, *h_all3 = nullptr;   // LSTM outputs of the target / selection passes
   int conv_implicit = 1;
   int conv_implicit_bwd = 1;
-  int conv_persistent = 0;
+  int conv_persistent = 1;
+  int conv_dx_implicit = 1;
+  std::vector<float*> conv_wt;  // re-laid filters for the data-gradient implicit GEMM (per layer, null for conv1)
   float* dcol_full = nullptr;
   int num_sms = 148;
   double* sumsq_part = nullptr;
@@ -615,6 +617,55 @@ int conv_dw_tc(rt_learner* h, cudaStream_t st, size_t i, const void* xin, const 
   return RT_OK;
 }
 
+template <int BN>
+int launch_convdx_tc(const CUtensorMap* tb, const rttc::ConvDxArgs& a, int ctas, cudaStream_t st) {
+  constexpr int STAGE_BYTES = rttc::BLOCK_M * rttc::BLOCK_K * 4 + BN * rttc::BLOCK_K * 4;
+  constexpr int STAGES = (160 * 1024) / STAGE_BYTES >= 6 ? 6 : (160 * 1024) / STAGE_BYTES;
+  constexpr int SMEM = STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+  auto kern = rttc::k_convdx_tc<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  kern<<<ctas, rttc::CONV_P_THREADS, SMEM, st>>>(*tb, a);
+  RT_LAUNCH_CHECK();
+  return RT_OK;
+}
+
+bool conv_dx_tc_eligible(const rt_learner* h, int i) {
+  const ConvL& L = h->conv[i];
+  return h->gx.mode == 1 && h->conv_dx_implicit && i > 0 && L.k % L.s == 0 && L.f % 32 == 0 &&
+         (L.cin == 32 || L.cin == 64 || L.cin == 128) && h->conv_wt[i] != nullptr;
+}
+
+// Data gradient of conv layer i (i > 0), ReLU mask of the previous layer fused:
+// d_c[i-1] = relu'(c_out[i-1]) * conv_transpose(dy, W_i)
+int conv_dx_tc(rt_learner* h, cudaStream_t st, const float* net, int i, const float* dy, int rows) {
+  const ConvL& L = h->conv[i];
+  const size_t nw = (size_t)L.f * L.K;
+  rtk::k_conv_wT<<<grid1d(nw), 256, 0, st>>>(net + L.w, h->conv_wt[i], L.f, L.k, L.s, L.cin);
+  RT_LAUNCH_CHECK();
+  rttc::ConvDxArgs a;
+  a.dy = dy; a.act = h->c_out[i - 1]; a.dx = h->d_c[i - 1];
+  a.rows = rows; a.C = L.cin; a.H = L.hin; a.W = L.win; a.KH = L.k; a.S = L.s; a.OH = L.hout; a.OW = L.wout;
+  a.F = L.f;
+  a.Hc = cdiv(L.hin, L.s); a.Wc = cdiv(L.win, L.s);
+  a.KD = L.k / L.s;
+  a.Kc = a.KD * a.KD * L.f;
+  a.Mc = rows * a.Hc * a.Wc;
+  const int BN = L.cin;
+  const CUtensorMap* tb = nullptr;
+  RT_TRY(get_tmap(h->gx, h->conv_wt[i], a.Kc, (uint64_t)L.s * L.s * L.cin, a.Kc, rttc::BLOCK_K, BN, 0, &tb));
+  const long long tiles = (long long)L.s * L.s * cdiv(a.Mc, rttc::BLOCK_M);
+  const int ctas = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+  h->gx.tc_launches++;
+  ProfScope ps(h->gx, st, 2.0 * rows * L.hout * L.wout * (double)L.f * L.K);
+  if (BN == 32) return launch_convdx_tc<32>(tb, a, ctas, st);
+  if (BN == 64) return launch_convdx_tc<64>(tb, a, ctas, st);
+  return launch_convdx_tc<128>(tb, a, ctas, st);
+}
+
 // CNN forward for `rows` frames: frames to fp32 NHWC once, then every layer is an implicit GEMM
 // over NHWC runs (fallback: im2col + GEMM, chunked so the im2col buffers stay L2-resident).
 int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows) {
@@ -994,7 +1045,9 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
         const void* xin = i == 0 ? (const void*)h->xf : (const void*)h->c_out[i - 1];
         RT_TRY(conv_dw_tc(h, st, i, xin, dy, rows, G + L.w));
         RT_TRY(colsum(h, st, dy, (size_t)rows * opix, L.f, G + L.b, 0));
-        if (i > 0) {
+        if (i > 0 && conv_dx_tc_eligible(h, i)) {
+          RT_TRY(conv_dx_tc(h, st, net, i, dy, rows));
+        } else if (i > 0) {
           RT_TRY(gemm(h->gx, st, mk(dy, L.f, 0, net + L.w, L.K, 0, h->dcol_full, L.K, (int)(rows * opix), L.K, L.f)));
           size_t n_in = (size_t)rows * L.hin * L.win * L.cin;
           rtk::k_col2im_nhwc<<<grid1d(n_in / 4), 256, 0, st>>>(h->dcol_full, h->d_c[i - 1], rows, L.cin, L.hin,
@@ -1196,6 +1249,9 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     RT_TRY(dalloc(h, &dco, (size_t)h->M * opix * L.f, nm));
     h->c_out.push_back(co);
     h->d_c.push_back(dco);
+    float* wt = nullptr;
+    if (i > 0) RT_TRY(dalloc(h, &wt, (size_t)L.f * L.K));
+    h->conv_wt.push_back(wt);
     size_t cc = (size_t)h->chunk_rows * opix * L.K;
     if (cc > maxcol) maxcol = cc;
   }
@@ -1301,7 +1357,9 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     e = getenv("RT_CONV_IM2COL");
     if (e && e[0] == '1') h->conv_implicit = 0;
     e = getenv("RT_CONV_PERSISTENT");
-    if (e && e[0] == '1') h->conv_persistent = 1;
+    if (e && e[0] == '0') h->conv_persistent = 0;
+    e = getenv("RT_CONV_DX_COL2IM");
+    if (e && e[0] == '1') h->conv_dx_implicit = 0;
     e = getenv("RT_CONV_BWD_IM2COL");
     if (e && e[0] == '1') h->conv_implicit_bwd = 0;
   }
