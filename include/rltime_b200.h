@@ -160,7 +160,8 @@ typedef struct rt_model_desc {
   int32_t lstm_units;                  /* 0 = no recurrent layer */
   int32_t fc_size;
   int32_t num_actions;
-  int32_t num_quantiles;               /* num_sampling_quantiles */
+  int32_t num_quantiles;               /* num_sampling_quantiles; 0 = plain DQNPolicy (no quantile layer,
+                                        * rltime/policies/torch/dqn.py) trained by DQN._compute_grads */
   int32_t embedding_dim;
   int32_t dueling;
 } rt_model_desc;
@@ -183,6 +184,9 @@ typedef struct rt_train_desc {
   double adam_epsilon;
   double lr;               /* NB the reference's train_init ignores lr (torch_trainer.py:80-83) */
   uint64_t seed;           /* device RNG for the quantile fractions when none are injected */
+  int32_t loss_timestep_agg; /* loss_timestep_aggregation (dqn.py:116-124): 0 none, 1 mean, 2 sum */
+  int32_t loss_mse;          /* DQN loss_mode (dqn.py:96-110): 0 huber, 1 mse */
+  double clip_grad_dynamic_alpha; /* >= 0: clip to clip_grad x EMA(grad norm) (torch_trainer.py:153-175) */
 } rt_train_desc;
 
 /* Which leaves of the replay batch feed the learner. */

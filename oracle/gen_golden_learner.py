@@ -39,12 +39,31 @@ CASES = {
         in_shape=(4, 14, 14), conv=[(8, 4, 2), (4, 3, 1)], lstm=0, fc=24, actions=4, nq=8,
         embed=8, dueling=True, B=6, T=1, P=0, n=3, gamma=0.99, double_q=True,
         rnn_bootstrap=False, vf_eps=None, clip_grad=10.0, adam_eps=1.5e-4, updates=2),
+    # config-4 family (Rainbow-style DQN): CNN -> FC, dueling + double-Q + n-step + PER weights,
+    # plain DQNPolicy / DQN trainer (training/torch/dqn.py), huber loss
+    "dqn_rainbow": dict(
+        in_shape=(4, 14, 14), conv=[(8, 4, 2), (4, 3, 1)], lstm=0, fc=24, actions=4, nq=1,
+        embed=0, dueling=True, B=6, T=1, P=0, n=3, gamma=0.99, double_q=True,
+        rnn_bootstrap=False, vf_eps=None, clip_grad=10.0, adam_eps=1.5e-4, updates=2,
+        policy="dqn"),
+    # recurrent DQN: burn-in, single-Q, vf-rescale, mse loss, sum over the batch of per-sequence
+    # means over time (loss_timestep_aggregation), dynamic (EMA) gradient clipping
+    "dqn_lstm_mse": dict(
+        in_shape=(2, 16, 16), conv=[(8, 4, 2), (8, 3, 1)], lstm=16, fc=32, actions=3, nq=1,
+        embed=0, dueling=False, B=3, T=4, P=2, n=2, gamma=0.99, double_q=False,
+        rnn_bootstrap=True, vf_eps=1e-3, clip_grad=0.8, adam_eps=1e-5, updates=3,
+        policy="dqn", loss_mode="mse", loss_agg="sum", loss_ts_agg="mean", clip_dyn_alpha=0.9),
+    # IQN with mean over time then sum over the batch
+    "iqn_lstm_tsagg": dict(
+        in_shape=(1, 12, 12), conv=[(4, 4, 2)], lstm=8, fc=8, actions=2, nq=4, embed=4,
+        dueling=True, B=2, T=3, P=0, n=1, gamma=0.9, double_q=True, rnn_bootstrap=True,
+        vf_eps=None, clip_grad=None, adam_eps=1e-8, updates=1, loss_agg="sum", loss_ts_agg="mean"),
 }
 
 
 def make_spec(c):
     return ModelSpec(c["in_shape"], c["conv"], c["lstm"], c["fc"], c["actions"], c["nq"],
-                     c["embed"], c["dueling"])
+                     c["embed"], c["dueling"], policy=c.get("policy", "iqn"))
 
 
 def make_batch(c, seed):
@@ -101,6 +120,7 @@ class TauQueue:
 def run_case(name, c):
     import gym
     from rltime.training.torch.iqn import IQN
+    from rltime.training.torch.dqn import DQN
     from rltime.general.utils import deep_apply
     from rltime.general.value_log import ValueLog
 
@@ -109,20 +129,25 @@ def run_case(name, c):
     p_target = spec.init_params(seed=12)
     obs_space = gym.spaces.Box(0, 255, c["in_shape"], dtype=np.uint8)
     act_space = gym.spaces.Discrete(c["actions"])
-    policy_args = dict(dueling=c["dueling"], num_sampling_quantiles=c["nq"],
-                       embedding_dim=c["embed"], cuda=False)
-    tr = IQN(logger=None, actors=None, model_config=model_config(c), policy_args=policy_args)
+    dqn = c.get("policy", "iqn") == "dqn"
+    if dqn:
+        policy_args = dict(dueling=c["dueling"], cuda=False)
+        tr = DQN(logger=None, actors=None, model_config=model_config(c), policy_args=policy_args)
+    else:
+        policy_args = dict(dueling=c["dueling"], num_sampling_quantiles=c["nq"],
+                           embedding_dim=c["embed"], cuda=False)
+        tr = IQN(logger=None, actors=None, model_config=model_config(c), policy_args=policy_args)
 
     def make_policy(params):
         pol = tr.create_policy(model_config=model_config(c), observation_space=obs_space,
                                action_space=act_space, **policy_args)
         sd = pol.state_dict()
-        assert set(sd.keys()) == set(params.keys()) | {"embedding_range"}, \
-            (sorted(sd.keys()), sorted(params.keys()))
+        extra = set() if dqn else {"embedding_range"}
+        assert set(sd.keys()) == set(params.keys()) | extra, (sorted(sd.keys()), sorted(params.keys()))
         for k, v in params.items():
             assert sd[k].shape == v.shape, (k, sd[k].shape, v.shape)
         pol.load_state_dict({**{k: v.clone() for k, v in params.items()},
-                             "embedding_range": sd["embedding_range"]})
+                             **{k: sd[k] for k in extra}})
         return pol
     tr.policy = make_policy(p_online)
     tr.target_policy = make_policy(p_target)
@@ -130,10 +155,12 @@ def run_case(name, c):
     # dqn.py:40-47, torch_trainer.py:32-42, multi_step_trainer.py:217-219)
     tr.gamma = c["gamma"]
     tr.double_q = c["double_q"]
-    tr.loss_mode, tr.huber_kappa = "huber", 1.0
-    tr.loss_aggregation, tr.loss_timestep_aggregation = torch.mean, None
+    tr.loss_mode, tr.huber_kappa = c.get("loss_mode", "huber"), 1.0
+    tr.loss_aggregation = tr._get_aggregator(c.get("loss_agg", "mean"))
+    tr.loss_timestep_aggregation = tr._get_aggregator(c["loss_ts_agg"]) if c.get("loss_ts_agg") else None
     tr.clip_grad = c["clip_grad"]
-    tr.clip_grad_dynamic_alpha = None
+    tr.clip_grad_dynamic_alpha = c.get("clip_dyn_alpha")
+    tr._grad_norm_moving_average = None
     tr.adam_epsilon = c["adam_eps"]
     tr.vf_scale_epsilon = c["vf_eps"]
     tr.clip_rewards = False
@@ -190,6 +217,8 @@ def run_case(name, c):
         taus = tq.log
         names = (["burn_online"] + (["burn_target"] if c["rnn_bootstrap"] else []) if P else []) + \
             ["target", "select", "train"]
+        if dqn:
+            names = []
         assert len(taus) == len(names), (len(taus), names)
         for nm, t in zip(names, taus):
             out["u%d/tau/%s" % (u, nm)] = t.numpy()
@@ -197,7 +226,7 @@ def run_case(name, c):
         out["u%d/report" % u] = reported[-1]
         vals = tr.value_log.get()["train"]
         out["u%d/qloss" % u] = np.float64(vals["qloss"])
-        out["u%d/td_mean" % u] = np.float64(vals["td_mean"])
+        out["u%d/td_mean" % u] = np.float64(vals["qvalue" if dqn else "td_mean"])
         out["u%d/grad_norm" % u] = np.float64(vals["grad_norm"])
         for k, v in tr.policy.named_parameters():
             out["u%d/grad/%s" % (u, k)] = v.grad.detach().numpy().copy()   # post-clip grads
@@ -214,5 +243,7 @@ def run_case(name, c):
 
 if __name__ == "__main__":
     torch.manual_seed(0)
+    only = sys.argv[1:]
     for name, c in CASES.items():
-        run_case(name, c)
+        if not only or name in only:
+            run_case(name, c)

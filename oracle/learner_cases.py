@@ -11,7 +11,13 @@ from oracle.gen_golden_learner import CASES  # noqa: F401  (pure-data dict; no r
 
 def spec_of(c):
     return ModelSpec(c["in_shape"], c["conv"], c["lstm"], c["fc"], c["actions"], c["nq"],
-                     c["embed"], c["dueling"])
+                     c["embed"], c["dueling"], policy=c.get("policy", "iqn"))
+
+
+def update_kwargs(c):
+    """Optional trainer arguments of a case -> learner_oracle.learner_update keywords."""
+    return dict(aggregation=c.get("loss_agg", "mean"), timestep_aggregation=c.get("loss_ts_agg"),
+                loss_mode=c.get("loss_mode", "huber"))
 
 
 def params_of(g, prefix):

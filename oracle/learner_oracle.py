@@ -31,7 +31,9 @@ class ModelSpec:
     """Topology family of the hot path: CNN -> [LSTM] -> FC -> (IQN, dueling) heads."""
 
     def __init__(self, in_shape, conv, lstm_units, fc_size, num_actions, num_quantiles=32,
-                 embedding_dim=64, dueling=True):
+                 embedding_dim=64, dueling=True, policy="iqn"):
+        assert policy in ("iqn", "dqn")
+        self.policy = policy                      # "dqn": DQNPolicy, no quantile layer
         self.in_shape = tuple(in_shape)           # (C, H, W)
         self.conv = [tuple(c) for c in conv]      # (filters, kernel, stride)
         self.lstm_units = int(lstm_units)         # 0 = no recurrent layer
@@ -88,8 +90,9 @@ class ModelSpec:
             shapes["value_hidden_layer.bias"] = (self.fc_size,)
             shapes["value_layer.weight"] = (1, self.fc_size)
             shapes["value_layer.bias"] = (1,)
-        shapes["quantile_layer.weight"] = (self.quantile_dim, self.embedding_dim)
-        shapes["quantile_layer.bias"] = (self.quantile_dim,)
+        if self.policy == "iqn":
+            shapes["quantile_layer.weight"] = (self.quantile_dim, self.embedding_dim)
+            shapes["quantile_layer.bias"] = (self.quantile_dim,)
         return shapes
 
     def init_params(self, seed=0):
@@ -187,6 +190,20 @@ def predict(spec, p, states, timesteps, taus):
     return out, last
 
 
+def predict_dqn(spec, p, states, timesteps):
+    """DQNPolicy.predict (dqn.py:96-112): (q-values (M, A), last LSTM state)."""
+    x, last = trunk_forward(spec, p, states, timesteps)               # layer_inputs[-1]
+    li = spec.fc_layer_index
+    hdn = F.relu(F.linear(x, p["model.layers.%d.layers.0.0.weight" % li],
+                          p["model.layers.%d.layers.0.0.bias" % li]))
+    adv = F.linear(hdn, p["out_layer.weight"], p["out_layer.bias"])
+    if spec.dueling:                                                   # dqn.py:74-87
+        v = F.relu(F.linear(x, p["value_hidden_layer.weight"], p["value_hidden_layer.bias"]))
+        v = F.linear(v, p["value_layer.weight"], p["value_layer.bias"])
+        return v + adv - adv.mean(1, keepdim=True), last
+    return adv, last
+
+
 # ------------------------------------------------------------------------- targets
 def vf_scale(x, eps):
     if not eps:
@@ -216,11 +233,19 @@ def bootstrap_target(spec, p_online, p_target, target_states, timesteps, taus_ta
     return torch.gather(tq, dim=-1, index=act).squeeze(-1)             # (M, Nq)
 
 
+def bootstrap_target_dqn(spec, p_online, p_target, target_states, timesteps, double_q):
+    """dqn.py:52-71."""
+    tq, _ = predict_dqn(spec, p_target, target_states, timesteps)
+    sq = predict_dqn(spec, p_online, target_states, timesteps)[0] if double_q else tq
+    act = sq.argmax(dim=-1, keepdim=True)
+    return tq.gather(dim=-1, index=act).squeeze(-1)                    # (M,)
+
+
 def calc_targets(returns, boot, target_masks, nsteps, gamma, vf_eps):
     """torch_trainer.py:101-147 with make_tensor's float32 casts (models/torch/utils.py:95-121)."""
-    returns = returns.float().unsqueeze(-1)
-    masks = target_masks.float().unsqueeze(-1)
-    nsteps = nsteps.float().unsqueeze(-1)
+    returns, masks, nsteps = returns.float(), target_masks.float(), nsteps.float()
+    if boot.dim() == 2:                                               # distributional: (M, Nq)
+        returns, masks, nsteps = returns.unsqueeze(-1), masks.unsqueeze(-1), nsteps.unsqueeze(-1)
     boot = vf_unscale(boot, vf_eps)
     return vf_scale(returns + (gamma ** nsteps) * boot * masks, vf_eps)
 
@@ -249,6 +274,26 @@ def iqn_loss(spec, p, states, targets, actions, weights, timesteps, taus, kappa=
         loss = agg[timestep_aggregation](loss.view(timesteps, -1), dim=0)
     loss = agg[aggregation](loss)
     return loss, report, a.mean()
+
+
+def dqn_loss(spec, p, states, targets, actions, weights, timesteps, kappa=1.0, loss_mode="huber",
+             aggregation="mean", timestep_aggregation=None):
+    """dqn.py:126-160 (+ :83-124).  Returns (loss scalar, reported SIGNED td errors, mean chosen q)."""
+    q, _ = predict_dqn(spec, p, states, timesteps)
+    chosen = torch.gather(q, dim=-1, index=actions.long().unsqueeze(-1)).squeeze(-1)
+    td = chosen - targets
+    if loss_mode == "mse":
+        loss = td.pow(2)
+    else:
+        a = torch.abs(td)
+        loss = torch.where(a <= kappa, 0.5 * td.pow(2), kappa * (a - 0.5 * kappa))
+    if weights is not None:
+        loss = loss * weights.float()
+    agg = {"mean": torch.mean, "sum": torch.sum}
+    if timestep_aggregation:
+        loss = agg[timestep_aggregation](loss.view(timesteps, -1), dim=0)
+    loss = agg[aggregation](loss)
+    return loss, td, chosen.mean()
 
 
 # ------------------------------------------------------------------------- burn-in
@@ -306,9 +351,21 @@ class Adam:
             params[k].addcdiv_(self.m[k], denom, value=-step_size)
 
 
+class DynamicClip:
+    """torch_trainer.py:153-175: clip value = clip_grad x EMA(alpha) of the gradient norm."""
+
+    def __init__(self, clip_grad, alpha):
+        self.clip_grad, self.alpha, self.ma = clip_grad, alpha, None
+
+    def value(self, cur):
+        self.ma = cur if self.ma is None else self.ma * self.alpha + cur * (1 - self.alpha)
+        return self.ma * self.clip_grad
+
+
 def learner_update(spec, p_online, p_target, opt, batch, taus, gamma, double_q=True,
                    rnn_bootstrap=True, vf_eps=None, kappa=1.0, clip_grad=None,
-                   burn_in_timesteps=0, aggregation="mean"):
+                   burn_in_timesteps=0, aggregation="mean", timestep_aggregation=None,
+                   loss_mode="huber", dynamic_clip=None):
     """One full learner update on a (S, B, ...) time-major batch (multi_step_trainer.py:
     278-340): burn-in -> targets -> loss/grads -> clip -> Adam.  `taus` = dict with
     'burn_online', 'burn_target' (ignored values, forwards still draw), 'target', 'select',
@@ -332,18 +389,27 @@ def learner_update(spec, p_online, p_target, opt, batch, taus, gamma, double_q=T
     returns, masks, nsteps = cut(batch["returns"]), cut(batch["target_masks"]), cut(batch["nsteps"])
     actions = cut(batch["actions"])
     weights = cut(batch["importance_weights"]) if batch.get("importance_weights") is not None else None
+    dqn = spec.policy == "dqn"
     with torch.no_grad():
-        boot = bootstrap_target(spec, p_online, p_target, tstates, T if rnn_bootstrap else 1,
-                                taus["target"], taus["select"], double_q)
+        if dqn:
+            boot = bootstrap_target_dqn(spec, p_online, p_target, tstates,
+                                        T if rnn_bootstrap else 1, double_q)
+        else:
+            boot = bootstrap_target(spec, p_online, p_target, tstates, T if rnn_bootstrap else 1,
+                                    taus["target"], taus["select"], double_q)
         targets = calc_targets(returns, boot, masks, nsteps, gamma, vf_eps)
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in p_online.items()}
-    loss, report, td_mean = iqn_loss(spec, leaf, states, targets, actions, weights, T,
-                                     taus["train"], kappa, aggregation)
+    if dqn:
+        loss, report, td_mean = dqn_loss(spec, leaf, states, targets, actions, weights, T, kappa,
+                                         loss_mode, aggregation, timestep_aggregation)
+    else:
+        loss, report, td_mean = iqn_loss(spec, leaf, states, targets, actions, weights, T,
+                                         taus["train"], kappa, aggregation, timestep_aggregation)
     loss.backward()
     grads = {k: v.grad for k, v in leaf.items()}
     gn = grad_norm(grads)
     if clip_grad is not None:
-        grads = clip_grads(grads, clip_grad)
+        grads = clip_grads(grads, dynamic_clip.value(gn) if dynamic_clip is not None else clip_grad)
     with torch.no_grad():
         opt.step(p_online, grads)
     return {"loss": loss.detach(), "report": report.detach(), "td_mean": td_mean.detach(),

@@ -67,6 +67,8 @@ class TrainDesc(C.Structure):
         ("loss_sum", C.c_int32), ("gemm_mode", C.c_int32), ("gamma", C.c_double),
         ("vf_scale_epsilon", C.c_double), ("huber_kappa", C.c_double), ("clip_grad", C.c_double),
         ("adam_epsilon", C.c_double), ("lr", C.c_double), ("seed", C.c_uint64),
+        ("loss_timestep_agg", C.c_int32), ("loss_mse", C.c_int32),
+        ("clip_grad_dynamic_alpha", C.c_double),
     ]
 
 

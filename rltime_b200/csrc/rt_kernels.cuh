@@ -542,17 +542,46 @@ __global__ void k_iqn_loss(const float* __restrict__ q, const float* __restrict_
 }
 
 // stats[0] = aggregate(row_loss), stats[1] = mean(report) = td_mean (iqn.py:127-129)
-__global__ void k_loss_stats(const float* __restrict__ row_loss, const float* __restrict__ report,
-                             float* __restrict__ stats, int M, int mean_agg) {
+// DQN._compute_grads (rltime/training/torch/dqn.py:126-160): td = Q(s,a) - y, huber / mse
+// (dqn.py:96-110), importance weights; reports the SIGNED td error (dqn.py:73-81 hands it to the
+// history buffer, which takes abs) and the chosen q-value (logged as "qvalue").
+__global__ void k_dqn_loss(const float* __restrict__ q, const float* __restrict__ targets,
+                           const long long* __restrict__ actions, const double* __restrict__ weights,
+                           float* __restrict__ dtheta, float* __restrict__ row_loss,
+                           float* __restrict__ report, float* __restrict__ row_q, int M, int A, float kappa,
+                           int mse, float grad_scale) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float qa = q[(size_t)m * A + (int)actions[m]];
+  float td = qa - targets[m];
+  float w = weights ? (float)weights[m] : 1.f;
+  float a = fabsf(td), l, dl;
+  if (mse) {
+    l = td * td;
+    dl = 2.f * td;
+  } else {
+    l = (a <= kappa) ? 0.5f * td * td : kappa * (a - 0.5f * kappa);
+    dl = (a <= kappa) ? td : (td > 0.f ? kappa : -kappa);
+  }
+  row_loss[m] = l * w;
+  report[m] = td;
+  row_q[m] = qa;
+  dtheta[m] = w * grad_scale * dl;
+}
+
+// stats[0] = aggregated loss (sum x scale: the mean / sum / per-timestep combinations of
+// dqn.py:116-124 are all one scale factor), stats[1] = mean of `aux` (td_mean or qvalue)
+__global__ void k_loss_stats(const float* __restrict__ row_loss, const float* __restrict__ aux,
+                             float* __restrict__ stats, int M, float scale) {
   __shared__ double s[2][256];
   double l = 0.0, r = 0.0;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) { l += row_loss[i]; r += report[i]; }
+  for (int i = threadIdx.x; i < M; i += blockDim.x) { l += row_loss[i]; r += aux[i]; }
   s[0][threadIdx.x] = l; s[1][threadIdx.x] = r;
   __syncthreads();
   if (threadIdx.x == 0) {
     double L = 0, R = 0;
     for (int t = 0; t < blockDim.x; ++t) { L += s[0][t]; R += s[1][t]; }
-    stats[0] = (float)(mean_agg ? L / M : L);
+    stats[0] = (float)(L * scale);
     stats[1] = (float)(R / M);
   }
 }
@@ -760,7 +789,7 @@ __global__ void k_sumsq_partial(const float* __restrict__ g, double* __restrict_
 // stage 2: norm, clip coefficient (torch.nn.utils.clip_grad_norm_: coef = min(1, c/(norm+1e-6)))
 // stats[2] = grad_norm, stats[3] = clip coefficient applied
 __global__ void k_gradnorm_final(const double* __restrict__ part, int parts, float* __restrict__ stats,
-                                 float clip, float grad_scale) {
+                                 float clip, float grad_scale, float dyn_alpha) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double t = 0.0;
     for (int i = 0; i < parts; ++i) t += part[i];
@@ -768,7 +797,16 @@ __global__ void k_gradnorm_final(const double* __restrict__ part, int parts, flo
     stats[2] = norm;
     float coef = 1.f;
     if (clip > 0.f) {
-      coef = clip / (norm + 1e-6f);
+      float cv = clip;
+      if (dyn_alpha >= 0.f) {
+        // dynamic clipping (torch_trainer.py:153-175): clip to clip x EMA of the gradient norm;
+        // stats[4] = moving average, stats[5] = initialised flag
+        float ma = stats[5] > 0.5f ? stats[4] * dyn_alpha + norm * (1.f - dyn_alpha) : norm;
+        stats[4] = ma;
+        stats[5] = 1.f;
+        cv = ma * clip;
+      }
+      coef = cv / (norm + 1e-6f);
       if (coef > 1.f) coef = 1.f;
     }
     stats[3] = coef;

@@ -99,6 +99,9 @@ struct rt_learner {
   int featC = 0, featHW = 0, feat = 0;  // last conv output
   int U = 0, D = 0, F = 0, A = 0, Nq = 0, E = 0;
   bool dueling = false;
+  bool dqn = false;            // plain DQNPolicy: no quantile layer, one output per action
+  float loss_scale = 1.f;      // aggregation of the per-row losses (dqn.py:116-124) as one factor
+  float* row_q = nullptr;      // chosen q-values of the last step (DQN "qvalue" log)
   bool fused_hidden = false;   // FC + value-hidden layers stored / executed as one [2F x D] layer
   int ldh = 0;                 // row pitch of h1 / v1 / dh1 / dv1 (F, or 2F when fused)
   std::vector<PInfo> pinfo;
@@ -866,28 +869,33 @@ int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float*
                   const float* tau) {
   int Nq = h->Nq, D = h->D, F = h->F, A = h->A, E = h->E;
   size_t MQ = (size_t)M * Nq;
-  rtk::k_cos_features<<<cdiv(MQ * E, 256), 256, 0, st>>>(tau, h->cf, (int)MQ, E);
-  RT_LAUNCH_CHECK();
-  rtk::GemmArgs g = mk(h->cf, E, 0, net + h->o_qw, E, 1, h->phi, D, (int)MQ, D, E);
-  g.bias = net + h->o_qb;
-  g.relu = 1;
-  RT_TRY(gemm(h->gx, st, g));
-  rtk::k_quantile_mul<<<cdiv(MQ * (D / 4), 256), 256, 0, st>>>(feat, h->phi, h->xq, MQ, D, Nq);
-  RT_LAUNCH_CHECK();
+  rtk::GemmArgs g;
+  const float* xq = feat;     // DQN: the heads read the trunk output directly
+  if (!h->dqn) {
+    rtk::k_cos_features<<<cdiv(MQ * E, 256), 256, 0, st>>>(tau, h->cf, (int)MQ, E);
+    RT_LAUNCH_CHECK();
+    g = mk(h->cf, E, 0, net + h->o_qw, E, 1, h->phi, D, (int)MQ, D, E);
+    g.bias = net + h->o_qb;
+    g.relu = 1;
+    RT_TRY(gemm(h->gx, st, g));
+    rtk::k_quantile_mul<<<cdiv(MQ * (D / 4), 256), 256, 0, st>>>(feat, h->phi, h->xq, MQ, D, Nq);
+    RT_LAUNCH_CHECK();
+    xq = h->xq;
+  }
   const int ldh = h->ldh;
   if (h->fused_hidden) {
     // [h1 | v1] = relu(xq . [Wfc ; Wvh]^T + [bfc | bvh]): one GEMM, the A operand is read once
-    g = mk(h->xq, D, 0, net + h->o_fcw, D, 1, h->h1, ldh, (int)MQ, 2 * F, D);
+    g = mk(xq, D, 0, net + h->o_fcw, D, 1, h->h1, ldh, (int)MQ, 2 * F, D);
     g.bias = net + h->o_fcb;
     g.relu = 1;
     RT_TRY(gemm(h->gx, st, g));
   } else {
-    g = mk(h->xq, D, 0, net + h->o_fcw, D, 1, h->h1, F, (int)MQ, F, D);
+    g = mk(xq, D, 0, net + h->o_fcw, D, 1, h->h1, F, (int)MQ, F, D);
     g.bias = net + h->o_fcb;
     g.relu = 1;
     RT_TRY(gemm(h->gx, st, g));
     if (h->dueling) {
-      g = mk(h->xq, D, 0, net + h->o_vhw, D, 1, h->v1, F, (int)MQ, F, D);
+      g = mk(xq, D, 0, net + h->o_vhw, D, 1, h->v1, F, (int)MQ, F, D);
       g.bias = net + h->o_vhb;
       g.relu = 1;
       RT_TRY(gemm(h->gx, st, g));
@@ -914,6 +922,8 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
   size_t MQ = (size_t)M * Nq;
   float* G = h->grad;
   const int duel = h->dueling ? 1 : 0;
+  const float* xq = h->dqn ? feat : h->xq;
+  float* dxq = h->dqn ? h->dfeatq : h->dxq;   // DQN: the data gradient of the heads IS d(loss)/d(feat)
   // small layers (out, value): data gradients fused with the ReLU masks, weight gradients as
   // slab partials folded deterministically
   rtk::k_heads_dsmall<<<cdiv(MQ * F, 256), 256, 0, st>>>(h->dtheta, actions, net + h->o_outw,
@@ -953,22 +963,23 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
     // [dh1 | dv1] against the stacked [Wfc ; Wvh]: weight gradient, bias gradient and data
     // gradient of both hidden layers in one GEMM each
     const int F2 = 2 * F;
-    RT_TRY(gemm(h->gx, st, mk(h->dh1, F2, 1, h->xq, D, 0, G + h->o_fcw, D, F2, D, (int)MQ)));
+    RT_TRY(gemm(h->gx, st, mk(h->dh1, F2, 1, xq, D, 0, G + h->o_fcw, D, F2, D, (int)MQ)));
     RT_TRY(colsum(h, st, h->dh1, MQ, F2, G + h->o_fcb, 0));
-    RT_TRY(gemm(h->gx, st, mk(h->dh1, F2, 0, net + h->o_fcw, D, 0, h->dxq, D, (int)MQ, D, F2)));
+    RT_TRY(gemm(h->gx, st, mk(h->dh1, F2, 0, net + h->o_fcw, D, 0, dxq, D, (int)MQ, D, F2)));
   } else {
   // FC
-  RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 1, h->xq, D, 0, G + h->o_fcw, D, F, D, (int)MQ)));
+  RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 1, xq, D, 0, G + h->o_fcw, D, F, D, (int)MQ)));
   RT_TRY(colsum(h, st, h->dh1, MQ, F, G + h->o_fcb, 0));
-  RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 0, net + h->o_fcw, D, 0, h->dxq, D, (int)MQ, D, F)));
+  RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 0, net + h->o_fcw, D, 0, dxq, D, (int)MQ, D, F)));
   if (h->dueling) {
-    RT_TRY(gemm(h->gx, st, mk(h->dv1, F, 1, h->xq, D, 0, G + h->o_vhw, D, F, D, (int)MQ)));
+    RT_TRY(gemm(h->gx, st, mk(h->dv1, F, 1, xq, D, 0, G + h->o_vhw, D, F, D, (int)MQ)));
     RT_TRY(colsum(h, st, h->dv1, MQ, F, G + h->o_vhb, 0));
-    rtk::GemmArgs g = mk(h->dv1, F, 0, net + h->o_vhw, D, 0, h->dxq, D, (int)MQ, D, F);
+    rtk::GemmArgs g = mk(h->dv1, F, 0, net + h->o_vhw, D, 0, dxq, D, (int)MQ, D, F);
     g.accumulate = 1;
     RT_TRY(gemm(h->gx, st, g));
   }
   }
+  if (h->dqn) return RT_OK;
   rtk::k_quantile_mul_bwd<<<cdiv((size_t)M * D, 256), 256, 0, st>>>(h->dxq, feat, h->phi, h->dphi,
                                                                    h->dfeatq, M, D, Nq);
   RT_LAUNCH_CHECK();
@@ -1105,7 +1116,8 @@ int apply_grads(rt_learner* h, cudaStream_t st, float grad_scale) {
     rtk::k_sumsq_partial<<<parts, 256, 0, st>>>(h->grad, h->sumsq_part, h->nparams);
     RT_LAUNCH_CHECK();
     rtk::k_gradnorm_final<<<1, 32, 0, st>>>(h->sumsq_part, parts, h->stats,
-                                           h->td.clip_grad > 0 ? (float)h->td.clip_grad : 0.f, grad_scale);
+                                           h->td.clip_grad > 0 ? (float)h->td.clip_grad : 0.f, grad_scale,
+                                           (float)h->td.clip_grad_dynamic_alpha);
     RT_LAUNCH_CHECK();
     h->adam_t++;
     double b1 = 0.9, b2 = 0.999;
@@ -1149,7 +1161,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
                       rt_learner** out) {
   RT_REQUIRE(md && td && out, "null argument");
   RT_REQUIRE(md->num_conv >= 1 && md->num_conv <= RT_MAX_CONV, "num_conv out of range");
-  RT_REQUIRE(md->num_quantiles >= 1 && md->num_quantiles <= 256, "num_quantiles out of range");
+  RT_REQUIRE(md->num_quantiles >= 0 && md->num_quantiles <= 256, "num_quantiles out of range");
   RT_REQUIRE(md->num_actions >= 1 && md->num_actions <= 64, "num_actions out of range");
   RT_REQUIRE(td->mbatch >= 1 && td->nstep_train >= 1 && td->burn_in >= 0 && td->nstep_target >= 1,
              "bad batch geometry");
@@ -1158,11 +1170,20 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   h->md = *md;
   h->td = *td;
   h->device = device;
-  h->U = md->lstm_units; h->F = md->fc_size; h->A = md->num_actions; h->Nq = md->num_quantiles;
+  h->U = md->lstm_units; h->F = md->fc_size; h->A = md->num_actions;
+  h->dqn = md->num_quantiles == 0;
+  h->Nq = h->dqn ? 1 : md->num_quantiles;
   h->E = md->embedding_dim; h->dueling = md->dueling != 0;
   h->B = td->mbatch; h->T = td->nstep_train; h->P = td->burn_in; h->n = td->nstep_target;
   h->S = h->T + h->P;
   h->lr = (float)td->lr;
+  {
+    // mean / sum over the batch, optionally a different aggregation over time-steps first
+    const double Md = (double)td->nstep_train * td->mbatch;
+    if (td->loss_timestep_agg == 0) h->loss_scale = (float)(td->loss_sum ? 1.0 : 1.0 / Md);
+    else h->loss_scale = (float)((td->loss_timestep_agg == 1 ? 1.0 / td->nstep_train : 1.0) *
+                                 (td->loss_sum ? 1.0 : 1.0 / td->mbatch));
+  }
   RT_REQUIRE(!(h->P > 0 && h->U == 0), "burn-in only makes sense for recurrent models");
 
   int c = md->in_c, hh = md->in_h, ww = md->in_w;
@@ -1221,8 +1242,10 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     h->o_vw = add_param(h, "value_layer.weight", {1, h->F}, PERM_NONE);
     h->o_vb = add_param(h, "value_layer.bias", {1}, PERM_NONE);
   }
-  h->o_qw = add_param(h, "quantile_layer.weight", {h->D, h->E}, featperm_rows);
-  h->o_qb = add_param(h, "quantile_layer.bias", {h->D}, featperm_rows);
+  if (!h->dqn) {
+    h->o_qw = add_param(h, "quantile_layer.weight", {h->D, h->E}, featperm_rows);
+    h->o_qb = add_param(h, "quantile_layer.bias", {h->D}, featperm_rows);
+  }
   h->nparams = (h->nparams + 63) / 64 * 64;
 
   RT_TRY(dalloc(h, &h->p[0], h->nparams, "params_online"));
@@ -1306,6 +1329,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->dtheta, MQ, "dtheta"));
   RT_TRY(dalloc(h, &h->row_loss, (size_t)h->M, "row_loss"));
   RT_TRY(dalloc(h, &h->report, (size_t)h->M, "report"));
+  RT_TRY(dalloc(h, &h->row_q, (size_t)h->M, "row_q"));
   RT_TRY(dalloc(h, &h->stats, 8, "stats"));
   RT_TRY(dalloc(h, &h->dadv, MQ * A, "dadv"));
   RT_TRY(dalloc(h, &h->dv, MQ, "dv"));
@@ -1499,6 +1523,8 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   const float* tau_seg[3];
   for (int s = 0; s < 3; ++s) {
     float* dst = h->tau_stage + (size_t)s * h->MQ;
+    tau_seg[s] = dst;
+    if (h->dqn) continue;
     if (taus_host && taus_host[s]) {
       RT_CUDA(cudaMemcpyAsync(dst, taus_host[s], (size_t)h->MQ * sizeof(float), cudaMemcpyHostToDevice, st));
     } else {
@@ -1591,15 +1617,21 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   RT_CUDA(cudaMemcpyAsync(h->tau, tau_seg[2], (size_t)h->MQ * sizeof(float), cudaMemcpyDeviceToDevice, st));
   const long long* actions = (const long long*)b->policy_outputs[io->po_field_actions] + (size_t)P * B;
   const double* weights = b->importance_weights ? b->importance_weights + (size_t)P * B : nullptr;
-  {
+  if (h->dqn) {
+    rtk::k_dqn_loss<<<cdiv(M, 128), 128, 0, st>>>(h->q, h->targets, actions, weights, h->dtheta, h->row_loss,
+                                                 h->report, h->row_q, M, h->A, (float)h->td.huber_kappa,
+                                                 h->td.loss_mse, h->loss_scale);
+    RT_LAUNCH_CHECK();
+    rtk::k_loss_stats<<<1, 256, 0, st>>>(h->row_loss, h->row_q, h->stats, M, h->loss_scale);
+    RT_LAUNCH_CHECK();
+  } else {
     int threads = ((Nq + 31) / 32) * 32;
     size_t smem = (3 * (size_t)Nq + 2 * threads) * sizeof(float);
-    float gscale = h->td.loss_sum ? 1.f : 1.f / (float)M;
     rtk::k_iqn_loss<<<M, threads, smem, st>>>(h->q, h->targets, h->tau, actions, weights, h->dtheta,
                                              h->row_loss, h->report, Nq, h->A,
-                                             (float)h->td.huber_kappa, gscale);
+                                             (float)h->td.huber_kappa, h->loss_scale);
     RT_LAUNCH_CHECK();
-    rtk::k_loss_stats<<<1, 256, 0, st>>>(h->row_loss, h->report, h->stats, M, h->td.loss_sum ? 0 : 1);
+    rtk::k_loss_stats<<<1, 256, 0, st>>>(h->row_loss, h->report, h->stats, M, h->loss_scale);
     RT_LAUNCH_CHECK();
   }
 

@@ -20,7 +20,11 @@ class DeviceLearner:
                  embedding_dim=64, dueling=True, *, mbatch, nstep_train, burn_in=0,
                  nstep_target=1, gamma=0.99, double_q=False, rnn_bootstrap=False,
                  vf_scale_epsilon=None, huber_kappa=1.0, clip_grad=None, adam_epsilon=1e-8,
-                 lr=1e-3, loss_aggregation="mean", seed=0, device=None, gemm="tf32"):
+                 lr=1e-3, loss_aggregation="mean", seed=0, device=None, gemm="tf32", policy="iqn",
+                 loss_mode="huber", loss_timestep_aggregation=None, clip_grad_dynamic_alpha=None):
+        """policy="iqn": IQNPolicy + IQN trainer (policies/torch/iqn.py, training/torch/iqn.py);
+        policy="dqn": DQNPolicy + DQN trainer (policies/torch/dqn.py, training/torch/dqn.py:
+        Rainbow-style dueling / double-Q / n-step / PER without the quantile layer)."""
         import torch
         if not torch.cuda.is_available():
             raise _lib.RtError("rltime_b200 learner needs a CUDA device (no CPU fallback)")
@@ -35,6 +39,10 @@ class DeviceLearner:
         md.lstm_units = lstm_units
         md.fc_size = fc_size
         md.num_actions = num_actions
+        assert policy in ("iqn", "dqn")
+        self.policy = policy
+        if policy == "dqn":
+            num_quantiles = 0      # ABI: 0 quantiles = plain DQNPolicy
         md.num_quantiles = num_quantiles
         md.embedding_dim = embedding_dim
         md.dueling = 1 if dueling else 0
@@ -44,6 +52,12 @@ class DeviceLearner:
         td.rnn_bootstrap = 1 if rnn_bootstrap else 0
         assert loss_aggregation in ("mean", "sum")
         td.loss_sum = 1 if loss_aggregation == "sum" else 0
+        assert loss_timestep_aggregation in (None, "mean", "sum")
+        td.loss_timestep_agg = {None: 0, "mean": 1, "sum": 2}[loss_timestep_aggregation]
+        assert loss_mode in ("huber", "mse")
+        assert loss_mode == "huber" or policy == "dqn", "IQN uses the quantile-Huber loss"
+        td.loss_mse = 1 if loss_mode == "mse" else 0
+        td.clip_grad_dynamic_alpha = -1.0 if clip_grad_dynamic_alpha is None else float(clip_grad_dynamic_alpha)
         td.gamma = gamma
         td.vf_scale_epsilon = vf_scale_epsilon or 0.0
         td.huber_kappa = huber_kappa
@@ -54,7 +68,7 @@ class DeviceLearner:
         assert gemm in ("fp32", "tf32")
         td.gemm_mode = _lib.RT_GEMM_TF32_TCGEN05 if gemm == "tf32" else _lib.RT_GEMM_FP32_SIMT
         self.B, self.T, self.P, self.n = mbatch, nstep_train, burn_in, nstep_target
-        self.Nq, self.A, self.U = num_quantiles, num_actions, lstm_units
+        self.Nq, self.A, self.U = max(num_quantiles, 1), num_actions, lstm_units
         h = C.c_void_p()
         _lib.check(self._lib.rt_learner_create(C.byref(md), C.byref(td), self.device.index or 0,
                                                C.byref(h)))
@@ -107,8 +121,9 @@ class DeviceLearner:
         state_dict with the reference's parameter names (+ the embedding_range buffer)."""
         import torch
         sd = self.state_dict()
-        sd["embedding_range"] = torch.arange(
-            1, self.param_info[-2][1][1] + 1, dtype=torch.float32)
+        if self.policy == "iqn":
+            sd["embedding_range"] = torch.arange(
+                1, self.param_info[-2][1][1] + 1, dtype=torch.float32)
         f = io.BytesIO()
         torch.save(sd, f)
         return f.getvalue()
@@ -132,7 +147,7 @@ class DeviceLearner:
                                              self._stream()))
 
     def _tau_ptrs(self, taus):
-        if taus is None:
+        if taus is None or self.policy == "dqn":
             return None, []
         keep = []
         arr = (C.c_void_p * 3)()
@@ -179,7 +194,10 @@ class DeviceLearner:
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         _lib.check(self._lib.rt_learner_read_stats(self._h, C.byref(a), C.byref(b), C.byref(c),
                                                    self._stream()))
-        return {"qloss": a.value, "td_mean": b.value, "grad_norm": c.value}
+        # the second slot is td_mean for IQN (iqn.py:128) and the mean chosen q-value for DQN
+        # (dqn.py:159-160)
+        return {"qloss": a.value, "td_mean" if self.policy == "iqn" else "qvalue": b.value,
+                "grad_norm": c.value}
 
     def debug(self, name, shape=None):
         p, n = C.c_void_p(), C.c_int64()

@@ -16,7 +16,18 @@ def make_learner(c, **kw):
                          burn_in=c["P"], nstep_target=c["n"], gamma=c["gamma"],
                          double_q=c["double_q"], rnn_bootstrap=c["rnn_bootstrap"],
                          vf_scale_epsilon=c["vf_eps"], clip_grad=c["clip_grad"],
-                         adam_epsilon=c["adam_eps"], lr=1e-3, **kw)
+                         adam_epsilon=c["adam_eps"], lr=1e-3, policy=c.get("policy", "iqn"),
+                         loss_mode=c.get("loss_mode", "huber"),
+                         loss_aggregation=c.get("loss_agg", "mean"),
+                         loss_timestep_aggregation=c.get("loss_ts_agg"),
+                         clip_grad_dynamic_alpha=c.get("clip_dyn_alpha"), **kw)
+
+
+def step_taus(c, g, u):
+    if c.get("policy", "iqn") == "dqn":
+        return None
+    taus = taus_of(g, u)
+    return [taus["target"], taus["select"], taus["train"]]
 
 
 def device_batch(raw, c):
@@ -58,24 +69,27 @@ def test_learner_matches_reference_golden(name):
             np.testing.assert_array_equal(back[k].numpy(), v.numpy())
         errs = []
         M, Nq = c["T"] * c["B"], c["nq"]
+        dqn = c.get("policy", "iqn") == "dqn"
+        dyn = lo.DynamicClip(c["clip_grad"], c["clip_dyn_alpha"]) if c.get("clip_dyn_alpha") is not None else None
         for u in range(c["updates"]):
             _, raw = batch_of(g, c, u)
             b, keep = device_batch(raw, c)
-            taus = taus_of(g, u)
-            L.step(b, [taus["target"], taus["select"], taus["train"]])
+            L.step(b, step_taus(c, g, u))
             st = L.stats()
             pre = "u%d/" % u
             # fp32 tolerance of the parity bar: TD-loss / targets within 1e-4 absolute
-            report_diff(errs, pre + "targets", L.debug("targets", (M, Nq)).cpu().numpy(),
+            tshape = (M,) if dqn else (M, Nq)
+            report_diff(errs, pre + "targets", L.debug("targets", tshape).cpu().numpy(),
                         g[pre + "targets"], 1e-4, 1e-5)
             report_diff(errs, pre + "qloss", st["qloss"], g[pre + "qloss"], 1e-4, 1e-5)
-            report_diff(errs, pre + "td_mean", st["td_mean"], g[pre + "td_mean"], 1e-4, 1e-5)
+            report_diff(errs, pre + "td_mean", st["qvalue" if dqn else "td_mean"], g[pre + "td_mean"], 1e-4, 1e-5)
             report_diff(errs, pre + "report", L.td_abs().cpu().numpy(), g[pre + "report"], 1e-4, 1e-5)
             report_diff(errs, pre + "grad_norm", st["grad_norm"], g[pre + "grad_norm"], 1e-3, 1e-6)
             grads = L.state_dict(2)
             coef = 1.0
             if c["clip_grad"]:
-                coef = min(1.0, c["clip_grad"] / (float(g[pre + "grad_norm"]) + 1e-6))
+                cv = dyn.value(float(g[pre + "grad_norm"])) if dyn is not None else c["clip_grad"]
+                coef = min(1.0, cv / (float(g[pre + "grad_norm"]) + 1e-6))
             after = L.state_dict(0)
             for k in grads:
                 # golden grads are post-clip; ours are stored pre-clip
@@ -169,10 +183,10 @@ def test_learner_tf32_tensor_core_path(name):
         M, Nq = c["T"] * c["B"], c["nq"]
         _, raw = batch_of(g, c, 0)
         b, keep = device_batch(raw, c)
-        taus = taus_of(g, 0)
-        L.step(b, [taus["target"], taus["select"], taus["train"]])
+        L.step(b, step_taus(c, g, 0))
         st = L.stats()
-        report_diff(errs, "targets", L.debug("targets", (M, Nq)).cpu().numpy(), g["u0/targets"], 1e-3, 1e-3)
+        tshape = (M,) if c.get("policy", "iqn") == "dqn" else (M, Nq)
+        report_diff(errs, "targets", L.debug("targets", tshape).cpu().numpy(), g["u0/targets"], 1e-3, 1e-3)
         report_diff(errs, "qloss", st["qloss"], g["u0/qloss"], 1e-3, 1e-3)
         report_diff(errs, "report", L.td_abs().cpu().numpy(), g["u0/report"], 1e-3, 1e-3)
         report_diff(errs, "grad_norm", st["grad_norm"], g["u0/grad_norm"], 2e-2, 1e-5)

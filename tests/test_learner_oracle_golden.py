@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import learner_oracle as lo
-from oracle.learner_cases import CASES, batch_of, params_of, spec_of, taus_of
+from oracle.learner_cases import CASES, batch_of, params_of, spec_of, taus_of, update_kwargs
 from tests.util import load_golden
 
 
@@ -21,12 +21,13 @@ def test_learner_oracle_matches_reference(name):
     for k, v in spec.init_params(seed=11).items():
         np.testing.assert_array_equal(v.numpy(), p_online[k].numpy())
     opt = lo.Adam(p_online, lr=1e-3, eps=c["adam_eps"])   # train_init ignores lr (torch_trainer.py:80-83)
+    dyn = lo.DynamicClip(c["clip_grad"], c["clip_dyn_alpha"]) if c.get("clip_dyn_alpha") is not None else None
     for u in range(c["updates"]):
         batch, _ = batch_of(g, c, u)
         res = lo.learner_update(spec, p_online, p_target, opt, batch, taus_of(g, u), c["gamma"],
                                 double_q=c["double_q"], rnn_bootstrap=c["rnn_bootstrap"],
                                 vf_eps=c["vf_eps"], clip_grad=c["clip_grad"],
-                                burn_in_timesteps=c["P"])
+                                burn_in_timesteps=c["P"], dynamic_clip=dyn, **update_kwargs(c))
         # same library, same op order: targets / loss agree to fp32 round-off
         np.testing.assert_allclose(res["targets"].numpy(), g["u%d/targets" % u], rtol=1e-6, atol=1e-6)
         np.testing.assert_allclose(float(res["loss"]), float(g["u%d/qloss" % u]), rtol=1e-6, atol=1e-7)
