@@ -109,7 +109,9 @@ class DevicePolicy:
 
 class IQNTrainer:
     """Same call surface as the reference's `IQN` trainer: IQNTrainer(logger, actors, model_config,
-    policy_args).train(**training_args)."""
+    policy_args).train(**training_args).  `DQNTrainer` below is the non-distributional sibling
+    (training/torch/dqn.py: type "dqn", e.g. Rainbow-style dueling + double-Q + n-step + PER)."""
+    POLICY = "iqn"
 
     def __init__(self, logger, actors, model_config, policy_args=None):
         self.logger = logger
@@ -126,7 +128,7 @@ class IQNTrainer:
         obs_space, act_space = self.actors.get_spaces()
         conv, lstm_units, fc_size = parse_model_config(self.model_config)
         pa = self.policy_args
-        assert pa.get("injection_layer", -1) == -1, "only injection_layer=-1 is supported"
+        assert self.POLICY == "dqn" or pa.get("injection_layer", -1) == -1, "only injection_layer=-1 is supported"
         mbatch = t["mbatch_size"] or self.actors.get_env_count()
         nstep_target = t["nstep_target"] or t["nstep_train"]
         self.learner = DeviceLearner(
@@ -137,7 +139,9 @@ class IQNTrainer:
             rnn_bootstrap=t["rnn_bootstrap"], vf_scale_epsilon=t["vf_scale_epsilon"],
             huber_kappa=t["huber_kappa"], clip_grad=t["clip_grad"], adam_epsilon=t["adam_epsilon"],
             # the reference's train_init ignores `lr` (Adam default 1e-3) until set_lr runs
-            lr=1e-3, loss_aggregation=t["loss_aggregation"], seed=t.get("seed", 0))
+            lr=1e-3, loss_aggregation=t["loss_aggregation"], seed=t.get("seed", 0), policy=self.POLICY,
+            loss_mode=t["loss_mode"], loss_timestep_aggregation=t["loss_timestep_aggregation"],
+            clip_grad_dynamic_alpha=t["clip_grad_dynamic_alpha"])
         p0 = init_params(self.learner.param_info, lstm_units, seed=t.get("seed", 0))
         self.learner.load_state_dict(p0, _lib.RT_BUF_ONLINE)
         self.learner.load_state_dict(p0 if not t["target_update_freq"] else
@@ -164,7 +168,7 @@ class IQNTrainer:
               loss_timestep_aggregation=None, seed=0):
         assert epochs == 1 and minibatches == 1, "epochs / minibatches > 1 are PPO options"
         assert rnn_steps_train in (None, nstep_train), "rnn_steps_train != nstep_train is not supported"
-        assert clip_grad_dynamic_alpha is None and loss_timestep_aggregation is None and loss_mode == "huber"
+        assert loss_mode == "huber" or self.POLICY == "dqn", "IQN always uses the quantile-Huber loss"
         assert not async_history, "the device buffer needs no separate history process"
         t = dict(locals())
         t.pop("self")
@@ -223,3 +227,10 @@ class IQNTrainer:
                 # same checkpoint payload as PolicyTrainer._save_checkpoint (policy_trainer.py:175-185)
                 self.logger.save_checkpoint({"policy_state": self.learner.get_state(), "train_state": {}},
                                             self.steps)
+
+
+class DQNTrainer(IQNTrainer):
+    """Reference `DQN` trainer surface (training/torch/dqn.py:8-50) on the same device engine:
+    plain DQNPolicy heads (dueling optional), huber / mse TD loss, signed TD errors reported to
+    the prioritized buffer."""
+    POLICY = "dqn"

@@ -57,3 +57,35 @@ def test_iqn_trainer_end_to_end_with_fake_envs():
     # acting inference is consistent with the learner's own forward: greedy action = argmax of q
     pred = tr.policy.actor_predict(actors.last_state, timesteps=1)
     assert pred["qvalues"].shape == (4, 4) and (pred["actions"] == pred["qvalues"].argmax(1)).all()
+
+
+MODEL_FF = {"type": "sequential", "args": {"layer_configs": [
+    {"type": "cnn", "args": {"layers": [{"filters": 16, "kernel": 8, "stride": 4},
+                                         {"filters": 16, "kernel": 4, "stride": 2}]}},
+    {"type": "fc", "args": {"fc_size": 64}}]}}
+
+
+@pytest.mark.gpu
+def test_dqn_trainer_rainbow_style_end_to_end():
+    """BASELINE config 4 family: Rainbow-style DQN (dueling + double-Q + n-step 3 + prioritized
+    replay of single transitions with the min tree for global importance scaling)."""
+    import torch
+    from rltime_b200.training import DQNTrainer
+    from tests.fake_actor import FakeVecActor
+    actors = FakeVecActor(num_envs=4, num_actions=4, seed=2)
+    logger = _Logger()
+    tr = DQNTrainer(logger, actors, MODEL_FF, {"dueling": True})
+    tr.train(total_steps=1000, log_freq=500, target_update_freq=250, clip_rewards=True, gamma=0.99,
+             nstep_train=1, nstep_target=3, lr=1e-4, mbatch_size=16, warmup_steps=200, double_q=True,
+             clip_grad=10.0, adam_epsilon=1.5e-4, loss_mode="huber",
+             history_mode={"type": "prioritized_replay",
+                           "args": {"size": 500, "train_frequency": 4, "alpha": 0.5, "beta": 0.4,
+                                    "beta_anneal": True, "global_importance_scaling": True,
+                                    "max_envs": 4}})
+    assert tr.steps >= 1000 and tr.updates > 100
+    st = tr.learner.stats()
+    assert np.isfinite(st["qloss"]) and np.isfinite(st["qvalue"]) and st["grad_norm"] > 0
+    sd = torch.load(io.BytesIO(logger.checkpoints[-1][0]["policy_state"]), map_location="cpu")
+    assert "value_hidden_layer.weight" in sd and "quantile_layer.weight" not in sd
+    pred = tr.policy.actor_predict(actors.last_state, timesteps=1)
+    assert pred["qvalues"].shape == (4, 4) and (pred["actions"] == pred["qvalues"].argmax(1)).all()
