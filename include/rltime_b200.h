@@ -63,6 +63,7 @@ typedef struct rt_replay_config {
   int64_t state_field_bytes[RT_MAX_FIELDS]; /* bytes per transition per leaf */
   int32_t num_po_fields;                    /* leaves of sample["policy_output"] */
   int64_t po_field_bytes[RT_MAX_FIELDS];
+  int32_t avoid_episode_crossing;           /* uniform replay: _refine_sample_range (replay_history.py:142-171) */
 } rt_replay_config;
 
 int rt_replay_create(const rt_replay_config* cfg, rt_replay** out);
@@ -221,6 +222,12 @@ int rt_learner_get_params(rt_learner* h, int32_t which, float* const* tensors);
 int rt_learner_sync_target(rt_learner* h, void* stream);
 /* TorchTrainer.set_lr (torch_trainer.py:149-151). */
 int rt_learner_set_lr(rt_learner* h, double lr);
+/* Optimizer step counter (Adam bias correction) and learning rate, for checkpoint / resume: the
+ * reference checkpoint (policy_trainer.py:170-185) carries only the policy weights, so training
+ * cannot resume there; with RT_BUF_ADAM_M / RT_BUF_ADAM_V through rt_learner_get/load_params these
+ * complete the optimizer state. */
+int rt_learner_get_opt_state(rt_learner* h, int64_t* adam_steps, double* lr);
+int rt_learner_set_opt_state(rt_learner* h, int64_t adam_steps, double lr);
 /* One learner update on a replay batch: burn-in (multi_step_trainer.py:90-131), bootstrap
  * targets (torch/iqn.py:15-52, torch_trainer.py:101-147), training forward + quantile-Huber
  * loss + backward (torch/iqn.py:54-129), grad-norm clip + Adam (torch_trainer.py:177-199).
@@ -259,6 +266,9 @@ int rt_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t transA, 
  * rt_learner_gemm_time returns and resets the summed device time and algorithmic flops (2MNK). */
 int rt_learner_profile(rt_learner* h, int32_t enable);
 int rt_learner_gemm_time(rt_learner* h, double* total_ms, double* total_flops, int64_t* launches);
+/* Per-launch view of the same measurement (call before rt_learner_gemm_time, which resets it):
+ * algorithmic flops and device milliseconds of up to `cap` timed launches, in launch order. */
+int rt_learner_gemm_launches(rt_learner* h, int64_t cap, double* flops, double* ms, int64_t* count);
 /* Measurement hook: average device time (CUDA events) of `iters` back-to-back launches of one
  * GEMM shape; force_bn / force_stages (0 = heuristic) select the tcgen05 tile configuration. */
 int rt_gemm_bench(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB,

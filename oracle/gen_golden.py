@@ -44,7 +44,10 @@ def make_reference_history(p):
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    only = sys.argv[1:]
     for name, p in sc.SCENARIOS.items():
+        if only and name not in only:
+            continue
         h = make_reference_history(p)
         if p["kind"] == "per":
             trace = sc.run_scenario(name, h, lambda hh: hh._rec.get("idx"),

@@ -50,6 +50,10 @@ SCENARIOS = {
     "online_async": dict(kind="online", size=0, envs=3, T=4, P=0, n=4, B=5, iters=150,
                          frame=(1, 3, 3), units=0, actions=2, done_mode="bernoulli", done_p=0.15,
                          feed="async", feed_steps=(1, 5), max_delayed_steps=9),
+    # uniform replay that shifts sequences off episode boundaries (replay_history.py:142-171)
+    "uniform_avoid_crossing": dict(kind="uniform", size=600, envs=4, T=6, P=2, n=2, B=6, iters=200,
+                                   frame=(2, 4, 4), units=3, actions=3, done_mode="bernoulli",
+                                   done_p=0.08, feed="lockstep", avoid_episode_crossing=True),
     "uniform_async": dict(kind="uniform", size=300, envs=3, T=1, P=0, n=3, B=7, iters=200,
                           frame=(1, 3, 3), units=0, actions=4, done_mode="bernoulli",
                           done_p=0.1, feed="async"),
@@ -72,6 +76,8 @@ def history_kwargs(p):
         return kw
     kw = dict(size=p["size"], train_frequency=None, nstep_target=p["n"],
               nstep_train=p["T"], prefix_steps=p["P"])
+    if p["kind"] == "uniform" and p.get("avoid_episode_crossing"):
+        kw["avoid_episode_crossing"] = True
     if p["kind"] == "per":
         for k in ("alpha", "beta", "beta_anneal", "overlap", "max_weight_factor",
                   "global_importance_scaling", "eps"):

@@ -30,6 +30,7 @@ class ReplayConfig(C.Structure):
         ("max_envs", C.c_int32), ("device", C.c_int32),
         ("num_state_fields", C.c_int32), ("state_field_bytes", C.c_int64 * RT_MAX_FIELDS),
         ("num_po_fields", C.c_int32), ("po_field_bytes", C.c_int64 * RT_MAX_FIELDS),
+        ("avoid_episode_crossing", C.c_int32),
     ]
 
 
@@ -128,6 +129,9 @@ SIGNATURES = {
     "rt_learner_profile": (C.c_int, [_VP, C.c_int32]),
     "rt_learner_gemm_time": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_int64)]),
+    "rt_learner_get_opt_state": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "rt_learner_set_opt_state": (C.c_int, [_VP, C.c_int64, C.c_double]),
+    "rt_learner_gemm_launches": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP]),
     "rt_gemm_bench": (C.c_int, [C.c_int32] * 9 + [C.POINTER(C.c_double), C.c_int32]),
 }
 

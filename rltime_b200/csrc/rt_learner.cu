@@ -64,6 +64,7 @@ struct GemmCtx {
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
   double prof_flops = 0;
+  std::vector<double> prof_fl;          // flops of each timed launch
 };
 
 struct ConvL {
@@ -425,6 +426,7 @@ struct ProfScope {   // brackets one GEMM-shaped launch with events when profili
     if (on) {
       cudaEventRecord(cx.prof_ev[cx.prof_used], st);
       cx.prof_flops += flops;
+      cx.prof_fl.push_back(flops);
     }
   }
   ~ProfScope() {
@@ -1474,6 +1476,20 @@ int rt_learner_set_lr(rt_learner* h, double lr) {
   return RT_OK;
 }
 
+int rt_learner_get_opt_state(rt_learner* h, int64_t* adam_steps, double* lr) {
+  RT_REQUIRE(h && adam_steps && lr, "null argument");
+  *adam_steps = (int64_t)h->adam_t;
+  *lr = (double)h->lr;
+  return RT_OK;
+}
+
+int rt_learner_set_opt_state(rt_learner* h, int64_t adam_steps, double lr) {
+  RT_REQUIRE(h && adam_steps >= 0, "bad argument");
+  h->adam_t = (long long)adam_steps;
+  h->lr = (float)lr;
+  return RT_OK;
+}
+
 }  // extern "C"
 
 namespace {
@@ -1846,6 +1862,7 @@ extern "C" int rt_learner_profile(rt_learner* h, int32_t enable) {
   cx.profile = enable != 0;
   cx.prof_used = 0;
   cx.prof_flops = 0;
+  cx.prof_fl.clear();
   return RT_OK;
 }
 
@@ -1865,5 +1882,22 @@ extern "C" int rt_learner_gemm_time(rt_learner* h, double* total_ms, double* tot
   *launches = (int64_t)(cx.prof_used / 2);
   cx.prof_used = 0;
   cx.prof_flops = 0;
+  cx.prof_fl.clear();
+  return RT_OK;
+}
+
+extern "C" int rt_learner_gemm_launches(rt_learner* h, int64_t cap, double* flops, double* ms, int64_t* count) {
+  RT_REQUIRE(h && flops && ms && count, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  RT_CUDA(cudaDeviceSynchronize());
+  GemmCtx& cx = h->gx;
+  int64_t n = 0;
+  for (size_t i = 0; i + 1 < cx.prof_used && n < cap; i += 2, ++n) {
+    float t = 0;
+    RT_CUDA(cudaEventElapsedTime(&t, cx.prof_ev[i], cx.prof_ev[i + 1]));
+    flops[n] = cx.prof_fl[i / 2];
+    ms[n] = t;
+  }
+  *count = n;
   return RT_OK;
 }

@@ -176,6 +176,7 @@ struct AssembleParams {
   const int* col_env;
   const long long* col_start;
   const long long* col_base;
+  const long long* col_count;  // transitions the env held at the draw (null: every n-step target exists)
   const double* col_weight;
   const long long* env_ids;
   const double* reward;
@@ -206,19 +207,26 @@ __global__ void k_assemble(AssembleParams p) {
   int j = r / p.B, b = r - j * p.B;
   int e = p.col_env[b];
   long long start = p.col_start[b];
-  p.slots[r] = slot_of(p.pos2slot, p.N, e, start + j - 1);
+  // A window shifted to the very end of an env (avoid_episode_crossing, replay_history.py:167-168)
+  // has fewer than n successors: _update_nstep stops at the end of the buffer (history.py:82),
+  // so nstep < n and the target state is the last next_state that exists.
+  const long long count = p.col_count ? p.col_count[b] : (1LL << 62);
+  long long spos = start + j - 1;
+  if (spos > count - 1) spos = count - 1;
+  p.slots[r] = slot_of(p.pos2slot, p.N, e, spos);
   if (j >= p.S) return;
   long long k = start + j;  // env offset of this transition
   int own = slot_of(p.pos2slot, p.N, e, k);
   double ret = p.reward[own];
   bool mask = !p.done[own];
-  for (int q = 1; q < p.n; ++q) {
+  int ns = 1;
+  for (int q = 1; q < p.n && k + q < count; ++q, ++ns) {
     int s = slot_of(p.pos2slot, p.N, e, k + q);
     if (mask) ret = __dadd_rn(ret, __dmul_rn(p.gpow[q], p.reward[s]));
     if (p.done[s]) mask = false;
   }
   p.returns[r] = ret;
-  p.nsteps[r] = p.n;
+  p.nsteps[r] = ns;
   p.target_masks[r] = mask ? 1.0 : 0.0;
   if (p.prioritized) {
     p.weights[r] = p.col_weight[b];
@@ -334,17 +342,23 @@ struct EnvState {
   int64_t env_id = 0;
   int32_t zombie = -1; // slot of offset first-1, kept alive as the state of `first`
   std::vector<int32_t> ring;  // env offset -> slot for offsets in [first-1, count)
+  std::vector<uint8_t> dring; // env offset -> done flag (host mirror for _refine_sample_range)
   int32_t get(int64_t pos) const { return ring[pos & (int64_t)(ring.size() - 1)]; }
+  bool done_at(int64_t pos) const { return dring[pos & (int64_t)(dring.size() - 1)] != 0; }
   void put(int64_t pos, int32_t slot) {
     int64_t live = count - first + 2;
     if ((int64_t)ring.size() < live + 1) {
       size_t ncap = ring.empty() ? 64 : ring.size() * 2;
       while ((int64_t)ncap < live + 1) ncap *= 2;
       std::vector<int32_t> nr(ncap, -1);
+      std::vector<uint8_t> nd(ncap, 0);
       if (!ring.empty())
-        for (int64_t q = (first > 0 ? first - 1 : 0); q < pos; ++q)
+        for (int64_t q = (first > 0 ? first - 1 : 0); q < pos; ++q) {
           nr[q & (int64_t)(ncap - 1)] = ring[q & (int64_t)(ring.size() - 1)];
+          nd[q & (int64_t)(ncap - 1)] = dring[q & (int64_t)(dring.size() - 1)];
+        }
       ring.swap(nr);
+      dring.swap(nd);
     }
     ring[pos & (int64_t)(ring.size() - 1)] = slot;
   }
@@ -363,6 +377,7 @@ struct BatchSlot {
   int* slots = nullptr;
   int* col_env = nullptr;
   long long* col_start = nullptr;
+  long long* col_count = nullptr;
   long long* col_base = nullptr;
   double* col_weight = nullptr;
   double* uniforms = nullptr;
@@ -614,7 +629,7 @@ int ensure_batch(rt_replay* h, BatchSlot& bs, int B) {
     fr(bs.po[f]);
   }
   fr(bs.returns); fr(bs.nsteps); fr(bs.masks); fr(bs.weights); fr(bs.loss_indices);
-  fr(bs.idxes); fr(bs.slots); fr(bs.col_env); fr(bs.col_start); fr(bs.col_base);
+  fr(bs.idxes); fr(bs.slots); fr(bs.col_env); fr(bs.col_start); fr(bs.col_count); fr(bs.col_base);
   fr(bs.col_weight); fr(bs.uniforms);
   if (bs.h_uniforms) cudaFreeHost(bs.h_uniforms);
   bs.h_uniforms = nullptr;
@@ -634,6 +649,7 @@ int ensure_batch(rt_replay* h, BatchSlot& bs, int B) {
   RT_CUDA(rt::dmalloc(&bs.slots, rows_all));
   RT_CUDA(rt::dmalloc(&bs.col_env, (size_t)B));
   RT_CUDA(rt::dmalloc(&bs.col_start, (size_t)B));
+  RT_CUDA(rt::dmalloc(&bs.col_count, (size_t)B));
   RT_CUDA(rt::dmalloc(&bs.col_base, (size_t)B));
   RT_CUDA(rt::dmalloc(&bs.col_weight, (size_t)B));
   RT_CUDA(rt::dmalloc(&bs.uniforms, (size_t)B));
@@ -648,6 +664,7 @@ int assemble_and_gather(rt_replay* h, BatchSlot& bs, int B, cudaStream_t st) {
   ap.prioritized = h->per ? 1 : 0;
   ap.pos2slot = h->d_pos2slot; ap.col_env = bs.col_env; ap.col_start = bs.col_start;
   ap.col_base = bs.col_base; ap.col_weight = bs.col_weight; ap.env_ids = h->d_env_ids;
+  ap.col_count = h->per ? nullptr : bs.col_count;
   ap.reward = h->d_reward; ap.done = h->d_done; ap.gpow = h->d_gpow; ap.slots = bs.slots;
   ap.returns = bs.returns; ap.nsteps = bs.nsteps; ap.target_masks = bs.masks;
   ap.weights = bs.weights; ap.loss_indices = bs.loss_indices;
@@ -790,7 +807,7 @@ void rt_replay_destroy(rt_replay* h) {
       if (bs.po[f]) cudaFree(bs.po[f]);
     }
     void* bp[] = {bs.returns, bs.nsteps, bs.masks, bs.weights, bs.loss_indices, bs.idxes,
-                  bs.slots, bs.col_env, bs.col_start, bs.col_base, bs.col_weight, bs.uniforms};
+                  bs.slots, bs.col_env, bs.col_start, bs.col_count, bs.col_base, bs.col_weight, bs.uniforms};
     for (void* p : bp)
       if (p) cudaFree(p);
     if (bs.h_uniforms) cudaFreeHost(bs.h_uniforms);
@@ -848,6 +865,7 @@ int rt_replay_append(rt_replay* h, int64_t m, const int32_t* env, const int64_t*
     int32_t s = pop_free_slot(h);
     slots[i] = s;
     es.put(pos, s);
+    es.dring[pos & (int64_t)(es.dring.size() - 1)] = done[i] ? 1 : 0;
     h->loss[s] = 1.0;  // _max_loss, never updated by the reference (:120,141)
     h->prio[s] = -1;
     h->u_slot.push_back(s);
@@ -949,7 +967,7 @@ int rt_replay_sample_uniform(rt_replay* h, int32_t B, const int64_t* choices, vo
   RT_CUDA(cudaSetDevice(h->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
   std::vector<int> col_env(B);
-  std::vector<long long> col_start(B);
+  std::vector<long long> col_start(B), col_count(B);
   for (int b = 0; b < B; ++b) {
     int64_t c = choices[b];
     bool found = false;
@@ -958,8 +976,21 @@ int rt_replay_sample_uniform(rt_replay* h, int32_t B, const int64_t* choices, vo
       int64_t a = (es.count - es.first) - (h->S + h->n - 1);
       if (a <= 0) continue;
       if (c < a) {
+        if (h->cfg.avoid_episode_crossing) {
+          // _refine_sample_range (replay_history.py:142-171): a `done` inside the window (its last
+          // step excepted) shifts the window to the end of that episode or the start of the next
+          const int64_t amount = h->S, len = es.count - es.first;
+          for (int64_t i = 0; i < amount - 1; ++i) {
+            if (es.done_at(es.first + c + i)) {
+              if ((double)i < (double)amount / 2.0) c = std::max<int64_t>(c - (amount - i - 1), 0);
+              else c = std::min<int64_t>(c + i + 1, len - amount);
+              break;
+            }
+          }
+        }
         col_env[b] = e;
         col_start[b] = es.first + c;
+        col_count[b] = es.count;
         found = true;
         break;
       }
@@ -973,6 +1004,8 @@ int rt_replay_sample_uniform(rt_replay* h, int32_t B, const int64_t* choices, vo
   if (rc != RT_OK) return rc;
   RT_CUDA(cudaMemcpyAsync(bs.col_env, col_env.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
   RT_CUDA(cudaMemcpyAsync(bs.col_start, col_start.data(), B * sizeof(long long),
+                          cudaMemcpyHostToDevice, st));
+  RT_CUDA(cudaMemcpyAsync(bs.col_count, col_count.data(), B * sizeof(long long),
                           cudaMemcpyHostToDevice, st));
   h->last_B = B;
   return assemble_and_gather(h, bs, B, st);

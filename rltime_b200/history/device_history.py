@@ -108,10 +108,7 @@ class DeviceReplayHistoryBuffer:
         import torch
         if not torch.cuda.is_available():
             raise _lib.RtError("rltime_b200 history buffers need a CUDA device (no CPU fallback)")
-        if avoid_episode_crossing:
-            raise NotImplementedError(
-                "avoid_episode_crossing (replay_history.py:142-171) is not supported on the "
-                "device path yet")
+        self.avoid_episode_crossing = bool(avoid_episode_crossing)
         assert nstep_target == 1 or discount_function is not None or gamma is not None, \
             "History buffer must get a 'discount_function' for nstep_target>1"
         self._lib = _lib.load()
@@ -147,6 +144,7 @@ class DeviceReplayHistoryBuffer:
 
     def _extra_config(self, cfg):
         cfg.overlap = 0
+        cfg.avoid_episode_crossing = 1 if self.avoid_episode_crossing else 0
 
     def _create(self, sample):
         self._state_skel = _skeleton(sample["next_state"])

@@ -133,6 +133,24 @@ class DeviceLearner:
         sd = torch.load(io.BytesIO(state), map_location="cpu")
         self.load_state_dict(sd)
 
+    # ---- checkpoint / resume ------------------------------------------
+    def training_state(self):
+        """Everything needed to resume training bit-exactly: online / target weights, Adam
+        moments, Adam step counter and learning rate (the reference checkpoint,
+        policy_trainer.py:170-185, holds the policy weights only and cannot resume)."""
+        steps, lr = C.c_int64(), C.c_double()
+        _lib.check(self._lib.rt_learner_get_opt_state(self._h, C.byref(steps), C.byref(lr)))
+        return {"online": self.state_dict(_lib.RT_BUF_ONLINE), "target": self.state_dict(_lib.RT_BUF_TARGET),
+                "adam_m": self.state_dict(_lib.RT_BUF_ADAM_M), "adam_v": self.state_dict(_lib.RT_BUF_ADAM_V),
+                "adam_steps": steps.value, "lr": lr.value}
+
+    def load_training_state(self, st):
+        self.load_state_dict(st["online"], _lib.RT_BUF_ONLINE)
+        self.load_state_dict(st["target"], _lib.RT_BUF_TARGET)
+        self.load_state_dict(st["adam_m"], _lib.RT_BUF_ADAM_M)
+        self.load_state_dict(st["adam_v"], _lib.RT_BUF_ADAM_V)
+        _lib.check(self._lib.rt_learner_set_opt_state(self._h, int(st["adam_steps"]), float(st["lr"])))
+
     def sync_target(self):
         _lib.check(self._lib.rt_learner_sync_target(self._h, self._stream()))
 
@@ -184,6 +202,16 @@ class DeviceLearner:
         ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
         _lib.check(self._lib.rt_learner_gemm_time(self._h, C.byref(ms), C.byref(fl), C.byref(n)))
         return ms.value, fl.value, n.value
+
+    def gemm_launches(self, cap=16384):
+        """[(algorithmic flops, device ms)] of every timed GEMM-shaped launch since profiling was
+        enabled; call before gemm_time(), which resets the record."""
+        fl = np.zeros(cap, dtype=np.float64)
+        ms = np.zeros(cap, dtype=np.float64)
+        n = C.c_int64()
+        _lib.check(self._lib.rt_learner_gemm_launches(self._h, cap, fl.ctypes.data, ms.ctypes.data,
+                                                      C.byref(n)))
+        return list(zip(fl[:n.value].tolist(), ms[:n.value].tolist()))
 
     def td_abs(self):
         p = C.c_void_p()

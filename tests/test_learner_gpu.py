@@ -304,3 +304,31 @@ def test_lstm_tensor_core_recurrence_midsize(upc, double_q, monkeypatch):
     for k in list(names) + ["report", "qloss"]:
         report_diff(errs, k, out["tf32"][k], out["fp32"][k], 2e-3, 2e-3)
     assert not errs, "\n".join(errs)
+
+
+@pytest.mark.gpu
+def test_checkpoint_resume_is_bit_exact():
+    """training_state() / load_training_state(): a learner restored after two updates continues
+    exactly like the one that never stopped (weights, Adam moments, step counter, lr)."""
+    name = "iqn_lstm_clip"
+    c = CASES[name]
+    g = load_golden("learner_%s.npz" % name)
+    A, Bn = make_learner(c), make_learner(c)
+    try:
+        A.load_state_dict(params_of(g, "online"), 0)
+        A.load_state_dict(params_of(g, "target"), 1)
+        A.set_lr(3e-4)
+        batches = [device_batch(batch_of(g, c, u)[1], c) for u in range(c["updates"])]
+        for u in range(c["updates"]):
+            A.step(batches[u][0], step_taus(c, g, u))
+        Bn.load_training_state(A.training_state())
+        for L in (A, Bn):
+            L.step(batches[0][0], step_taus(c, g, 0))
+        sa, sb = A.training_state(), Bn.training_state()
+        assert sa["adam_steps"] == sb["adam_steps"] == c["updates"] + 1 and sa["lr"] == sb["lr"]
+        for part in ("online", "target", "adam_m", "adam_v"):
+            for k in sa[part]:
+                np.testing.assert_array_equal(sa[part][k].numpy(), sb[part][k].numpy(), err_msg=part + "/" + k)
+    finally:
+        A.close()
+        Bn.close()
