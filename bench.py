@@ -175,7 +175,7 @@ def one_update(hist, learner, B, world=1):
         parallel.data_parallel_step(learner, hist.last_batch, world)
     else:
         learner.step(hist.last_batch)
-    hist.update_losses_device(learner.td_abs())
+    hist.update_losses_device(learner.td_abs(), ready=learner.wait_loss)
 
 
 def run_gpu(args):
@@ -279,7 +279,7 @@ def run_gpu(args):
                            [h_frames.numpy(), h_hx.numpy(), h_cx.numpy(), h_init.numpy()],
                            [h_act.numpy(), h_qv.numpy()])
         one_update(hist, learner, B, world)
-        return learner.stats()["qloss"]
+        return learner.loss()["qloss"]       # D2H of the step's loss (final before its backward pass)
     for _ in range(3):
         e2e_update()
     barrier()

@@ -253,6 +253,14 @@ int rt_learner_act(rt_learner* h, int32_t E, const uint8_t* x, const float* hx, 
                    float* c_out, void* stream);
 /* Device pointer to the T*B reported |td| means (torch/iqn.py:112) of the last step. */
 int rt_learner_td_abs(rt_learner* h, float** out_device);
+/* The reported |td| / losses of a step are final BEFORE its backward pass (the reference reads
+ * them after backward, training/torch/dqn.py:73-81, with the same values).  wait_loss makes
+ * `stream` wait for that point of the last enqueued step, so the priority write-back
+ * (rt_replay_update_losses_last) and the next draw can run on a second stream while the backward
+ * pass and Adam still execute; read_loss does the same wait on `stream`, then reads qloss and
+ * td_mean back (pinned) and synchronises `stream` only. */
+int rt_learner_wait_loss(rt_learner* h, void* stream);
+int rt_learner_read_loss(rt_learner* h, float* loss, float* td_mean, void* stream);
 /* qloss, td_mean, grad_norm of the last step (torch/iqn.py:127-129, torch_trainer.py:187-190);
  * synchronises the stream. */
 int rt_learner_read_stats(rt_learner* h, float* loss, float* td_mean, float* grad_norm, void* stream);

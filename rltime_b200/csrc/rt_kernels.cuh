@@ -456,23 +456,40 @@ __global__ void k_quantile_mean(const float* __restrict__ q, float* __restrict__
 // ------------------------------------------------------------------------------ target
 // IQN._get_bootstrap_target_value (rltime/training/torch/iqn.py:37-52) +
 // TorchTrainer.calc_target_values / _vf_unscale / _vf_scale (torch_trainer.py:46-78,144-147).
-__global__ void k_iqn_target(const float* __restrict__ tq, const float* __restrict__ sq,
+// One warp per row m: the Nq x A selection values are staged through shared memory with
+// coalesced loads, lane a averages action a over the quantiles in index order, lane q then forms
+// target quantile q.  Block = 128 threads (4 rows); dynamic smem = 4 * Nq * A floats.
+__global__ void __launch_bounds__(128) k_iqn_target(const float* __restrict__ tq, const float* __restrict__ sq,
                              const double* __restrict__ returns, const double* __restrict__ masks,
                              const long long* __restrict__ nsteps, float* __restrict__ targets, int M,
                              int Nq, int A, float gamma, double vf_eps) {
-  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ float s_sel[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 4 + warp;
   if (m >= M) return;
+  float* ss = s_sel + (size_t)warp * Nq * A;
+  const float* src = sq + (size_t)m * Nq * A;
+  for (int i = lane; i < Nq * A; i += 32) ss[i] = src[i];
+  __syncwarp();
   int best = 0;
   float best_v = -INFINITY;
-  for (int a = 0; a < A; ++a) {
-    float s = 0.f;
-    for (int q = 0; q < Nq; ++q) s += sq[((size_t)m * Nq + q) * A + a];
-    s /= (float)Nq;
-    if (s > best_v) { best_v = s; best = a; }
+  for (int a0 = 0; a0 < A; a0 += 32) {
+    const int a = a0 + lane;
+    float sv = -INFINITY;
+    if (a < A) {
+      float t = 0.f;
+      for (int q = 0; q < Nq; ++q) t += ss[q * A + a];
+      sv = t / (float)Nq;
+    }
+    // first maximum in action order (strict >), as a sequential scan would pick it
+    for (int l = 0; l < 32 && a0 + l < A; ++l) {
+      float v = __shfl_sync(0xffffffffu, sv, l);
+      if (v > best_v) { best_v = v; best = a0 + l; }
+    }
   }
-  float ret = (float)returns[m], mask = (float)masks[m];
-  float disc = powf(gamma, (float)nsteps[m]);
-  for (int q = 0; q < Nq; ++q) {
+  const float ret = (float)returns[m], mask = (float)masks[m];
+  const float disc = powf(gamma, (float)nsteps[m]);
+  for (int q = lane; q < Nq; q += 32) {
     float boot = tq[((size_t)m * Nq + q) * A + best];
     if (vf_eps > 0.0) {
       double sx = (double)boot, a = fabs(sx), e = vf_eps;
@@ -628,61 +645,270 @@ __global__ void k_colsum_final(const float* __restrict__ part, float* __restrict
 // out layer (A actions) + dueling value layer + combine in one pass, one warp per row
 // (rltime/policies/torch/dqn.py:78-112): adv = h1 Wout^T + b, v = v1 Wv^T + bv,
 // q = v + adv - mean_a adv.  A <= 32.
-template <int MAXA>
-__global__ void k_heads_out(const float* __restrict__ h1, const float* __restrict__ v1,
+template <int MAXA, int RPW = 4>   // RPW rows per warp: each weight vector read from L1 serves RPW rows
+__global__ void __launch_bounds__(256) k_heads_out(const float* __restrict__ h1, const float* __restrict__ v1,
                             const float* __restrict__ Wout, const float* __restrict__ bout,
                             const float* __restrict__ Wv, const float* __restrict__ bv,
                             float* __restrict__ adv, float* __restrict__ vout, float* __restrict__ q,
                             size_t rows, int F, int A, int ldh) {
-  size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  size_t r0 = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW;
   int lane = threadIdx.x & 31;
-  if (r >= rows) return;
-  float acc[MAXA];
+  if (r0 >= rows) return;
+  float acc[RPW][MAXA], accv[RPW];
 #pragma unroll
-  for (int a = 0; a < MAXA; ++a) acc[a] = 0.f;
-  float accv = 0.f;
-  const float* hr = h1 + r * ldh;
-  const float* vr = v1 ? v1 + r * ldh : nullptr;
-  // F % 4 == 0: 16-byte loads, several independent rows of loads in flight per lane
+  for (int i = 0; i < RPW; ++i) {
+    accv[i] = 0.f;
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a) acc[i][a] = 0.f;
+  }
+  // rows past the end re-read the last row (results discarded): keeps the loop branch-free
+  const float* hr[RPW];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) hr[i] = h1 + (r0 + i < rows ? r0 + i : rows - 1) * ldh;
+  const ptrdiff_t voff = v1 ? v1 - h1 : 0;
+  // F % 4 == 0: 16-byte loads, RPW independent rows of loads in flight per lane
   for (int f = lane * 4; f < F; f += 128) {
-    float4 hv = *reinterpret_cast<const float4*>(hr + f);
+    float4 hv[RPW];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) hv[i] = __ldcs(reinterpret_cast<const float4*>(hr[i] + f));
 #pragma unroll
     for (int a = 0; a < MAXA; ++a)
       if (a < A) {
         float4 w = __ldg(reinterpret_cast<const float4*>(Wout + (size_t)a * F + f));
-        acc[a] = fmaf(hv.x, w.x, acc[a]); acc[a] = fmaf(hv.y, w.y, acc[a]);
-        acc[a] = fmaf(hv.z, w.z, acc[a]); acc[a] = fmaf(hv.w, w.w, acc[a]);
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+          acc[i][a] = fmaf(hv[i].x, w.x, acc[i][a]); acc[i][a] = fmaf(hv[i].y, w.y, acc[i][a]);
+          acc[i][a] = fmaf(hv[i].z, w.z, acc[i][a]); acc[i][a] = fmaf(hv[i].w, w.w, acc[i][a]);
+        }
       }
-    if (vr) {
-      float4 vv = *reinterpret_cast<const float4*>(vr + f);
+    if (v1) {
       float4 w = __ldg(reinterpret_cast<const float4*>(Wv + f));
-      accv = fmaf(vv.x, w.x, accv); accv = fmaf(vv.y, w.y, accv);
-      accv = fmaf(vv.z, w.z, accv); accv = fmaf(vv.w, w.w, accv);
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        float4 vv = __ldcs(reinterpret_cast<const float4*>(hr[i] + voff + f));
+        accv[i] = fmaf(vv.x, w.x, accv[i]); accv[i] = fmaf(vv.y, w.y, accv[i]);
+        accv[i] = fmaf(vv.z, w.z, accv[i]); accv[i] = fmaf(vv.w, w.w, accv[i]);
+      }
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-    for (int a = 0; a < MAXA; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
-    accv += __shfl_xor_sync(0xffffffffu, accv, o);
+    for (int i = 0; i < RPW; ++i) {
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a) acc[i][a] += __shfl_xor_sync(0xffffffffu, acc[i][a], o);
+      accv[i] += __shfl_xor_sync(0xffffffffu, accv[i], o);
+    }
   }
   if (lane == 0) {
-    float mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      size_t r = r0 + i;
+      if (r >= rows) break;
+      float mean = 0.f;
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < A) {
+          acc[i][a] += bout[a];
+          mean += acc[i][a];
+        }
+      mean /= (float)A;
+      float vv = v1 ? accv[i] + bv[0] : 0.f;
+      if (v1) vout[r] = vv;
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < A) {
+          adv[r * A + a] = acc[i][a];
+          q[r * A + a] = v1 ? (vv + acc[i][a] - mean) : acc[i][a];
+        }
+    }
+  }
+}
+
+// Backward of the two small layers in ONE pass over the hidden activations (rows x C virtual
+// columns, C = F out-layer inputs [+ F value-layer inputs]):
+//   data gradients with the ReLU masks of their inputs
+//     dh1[r,f] = g_r (Wout[act_r,f] - dueling * mean_a Wout[a,f]) * (h1 > 0),  dv1[r,f] = g_r Wv[f] * (v1 > 0)
+//   and, per slab of rows, the partial sums the weight / bias gradients are made of
+//     part[slab][a][c]  = sum_{r: act_r = a} g_r h1[r,c]   (c < F, a < A)
+//     part[slab][0][c]  = sum_r g_r v1[r,c-F]              (c >= F)
+//     part[slab][A][c]  = sum_r dh1|dv1[r,c]               (bias gradient of the hidden layers)
+// k_heads_bwd_final folds the slabs in a fixed order.  Grid (ceil(C/128), slabs), block (32, 8);
+// a thread owns 4 consecutive columns; warps stride the slab's rows.
+template <int MAXA>
+__global__ void __launch_bounds__(256) k_heads_bwd_fused(
+    const float* __restrict__ dtheta, const long long* __restrict__ actions,
+    const float* __restrict__ Wout, const float* __restrict__ Wv, const float* __restrict__ h1,
+    const float* __restrict__ v1, float* __restrict__ dh1, float* __restrict__ dv1,
+    float* __restrict__ part, size_t rows, int F, int A, int Nq, int dueling, int ldh,
+    int rows_per_block) {
+  __shared__ __align__(16) float s_w[MAXA][128];
+  __shared__ __align__(16) float s_red[8][128];
+  const int C = F * (dueling ? 2 : 1);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 128 + tx * 4;
+  const bool valid = c < C;
+  const bool isv = c >= F;
+  const int f = isv ? c - F : c;
+  for (int i = ty * 32 + tx; i < MAXA * 128; i += 256) {
+    int a = i >> 7, col = blockIdx.x * 128 + (i & 127);
+    float val = 0.f;
+    if (a < A && col < F) {
+      val = Wout[(size_t)a * F + col];
+      if (dueling) {
+        float mean = 0.f;
+        for (int b = 0; b < A; ++b) mean += Wout[(size_t)b * F + col];
+        val -= mean / (float)A;
+      }
+    }
+    s_w[a][i & 127] = val;
+  }
+  __syncthreads();
+  float acc[MAXA][4], cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int a = 0; a < MAXA; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
+  float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid && isv) wv = *reinterpret_cast<const float4*>(Wv + f);
+  const size_t r0 = (size_t)blockIdx.y * rows_per_block;
+  size_t r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  const float* src = isv ? v1 : h1;
+  float* dst = isv ? dv1 : dh1;
+  if (valid) {
+#pragma unroll 2
+    for (size_t r = r0 + ty; r < r1; r += 8) {
+      const float g = dtheta[r];
+      const int act = (int)actions[r / Nq];
+      const float4 x = __ldcs(reinterpret_cast<const float4*>(src + r * ldh + f));
+      float4 d;
+      if (!isv) {
+        const float4 w = *reinterpret_cast<const float4*>(&s_w[act][tx * 4]);
+        d.x = x.x > 0.f ? g * w.x : 0.f; d.y = x.y > 0.f ? g * w.y : 0.f;
+        d.z = x.z > 0.f ? g * w.z : 0.f; d.w = x.w > 0.f ? g * w.w : 0.f;
+        const float gx = g * x.x, gy = g * x.y, gz = g * x.z, gw = g * x.w;
+#pragma unroll
+        for (int a = 0; a < MAXA; ++a) {
+          const bool hit = a == act;
+          acc[a][0] += hit ? gx : 0.f; acc[a][1] += hit ? gy : 0.f;
+          acc[a][2] += hit ? gz : 0.f; acc[a][3] += hit ? gw : 0.f;
+        }
+      } else {
+        d.x = x.x > 0.f ? g * wv.x : 0.f; d.y = x.y > 0.f ? g * wv.y : 0.f;
+        d.z = x.z > 0.f ? g * wv.z : 0.f; d.w = x.w > 0.f ? g * wv.w : 0.f;
+        acc[0][0] = fmaf(g, x.x, acc[0][0]); acc[0][1] = fmaf(g, x.y, acc[0][1]);
+        acc[0][2] = fmaf(g, x.z, acc[0][2]); acc[0][3] = fmaf(g, x.w, acc[0][3]);
+      }
+      *reinterpret_cast<float4*>(dst + r * ldh + f) = d;
+      cs[0] += d.x; cs[1] += d.y; cs[2] += d.z; cs[3] += d.w;
+    }
+  }
+  // fold the 8 warps (fixed order) and emit this slab's partials
+  const int NP = A + 1;
+#pragma unroll
+  for (int o = 0; o <= MAXA; ++o) {
+    if (o > A) break;
+    float4 v4 = (o == A) ? make_float4(cs[0], cs[1], cs[2], cs[3])
+                         : make_float4(acc[o < MAXA ? o : 0][0], acc[o < MAXA ? o : 0][1],
+                                       acc[o < MAXA ? o : 0][2], acc[o < MAXA ? o : 0][3]);
+    __syncthreads();
+    *reinterpret_cast<float4*>(&s_red[ty][tx * 4]) = v4;
+    __syncthreads();
+    int col = ty * 32 + tx;      // 256 threads: the first 128 fold one column each
+    if (col < 128 && blockIdx.x * 128 + col < C) {
+      float t = ((s_red[0][col] + s_red[1][col]) + (s_red[2][col] + s_red[3][col])) +
+                ((s_red[4][col] + s_red[5][col]) + (s_red[6][col] + s_red[7][col]));
+      part[((size_t)blockIdx.y * NP + o) * C + blockIdx.x * 128 + col] = t;
+    }
+  }
+}
+
+// Folds the slab partials of k_heads_bwd_fused into the gradients of the out layer (Wout, bout),
+// the value layer (Wv, bv) and the hidden-layer biases.  Blocks [0, ceil(C/32)) own 32 columns each
+// (threads (32, 8): ty strides the slabs); the last block reduces the two bias vectors from dtheta.
+template <int MAXA>
+__global__ void __launch_bounds__(256) k_heads_bwd_final(
+    const float* __restrict__ part, int slabs, const float* __restrict__ dtheta,
+    const long long* __restrict__ actions, float* __restrict__ g_outw, float* __restrict__ g_outb,
+    float* __restrict__ g_vw, float* __restrict__ g_vb, float* __restrict__ g_fcb,
+    float* __restrict__ g_vhb, size_t rows, int F, int A, int Nq, int dueling) {
+  const int C = F * (dueling ? 2 : 1);
+  const int NP = A + 1;
+  const int col_blocks = (C + 31) / 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  __shared__ float s[8][MAXA + 1][33];
+  if ((int)blockIdx.x < col_blocks) {
+    const int c = blockIdx.x * 32 + tx;
+    float acc[MAXA + 1];
+#pragma unroll
+    for (int o = 0; o <= MAXA; ++o) acc[o] = 0.f;
+    if (c < C)
+      for (int p = ty; p < slabs; p += 8) {
+#pragma unroll
+        for (int o = 0; o <= MAXA; ++o)
+          if (o <= A) acc[o] += part[((size_t)p * NP + o) * C + c];
+      }
+#pragma unroll
+    for (int o = 0; o <= MAXA; ++o) s[ty][o][tx] = acc[o];
+    __syncthreads();
+    if (ty == 0 && c < C) {
+      float t[MAXA + 1];
+#pragma unroll
+      for (int o = 0; o <= MAXA; ++o)
+        t[o] = ((s[0][o][tx] + s[1][o][tx]) + (s[2][o][tx] + s[3][o][tx])) +
+               ((s[4][o][tx] + s[5][o][tx]) + (s[6][o][tx] + s[7][o][tx]));
+      if (c < F) {
+        float tot = 0.f;
+#pragma unroll
+        for (int a = 0; a < MAXA; ++a)
+          if (a < A) tot += t[a];
+        const float sub = dueling ? tot / (float)A : 0.f;
+#pragma unroll
+        for (int a = 0; a < MAXA; ++a)
+          if (a < A) g_outw[(size_t)a * F + c] = t[a] - sub;
+#pragma unroll
+        for (int o = 0; o <= MAXA; ++o)
+          if (o == A) g_fcb[c] = t[o];
+      } else {
+        g_vw[c - F] = t[0];
+#pragma unroll
+        for (int o = 0; o <= MAXA; ++o)
+          if (o == A) g_vhb[c - F] = t[o];
+      }
+    }
+    return;
+  }
+  // bias gradients: bout[a] = sum_{r: act = a} g_r - dueling * (sum_r g_r) / A;  bv = sum_r g_r
+  float acc[MAXA + 1];
+#pragma unroll
+  for (int o = 0; o <= MAXA; ++o) acc[o] = 0.f;
+  const int tid = ty * 32 + tx;
+  for (size_t r = tid; r < rows; r += 256) {
+    const float g = dtheta[r];
+    const int act = (int)actions[r / Nq];
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a) acc[a] += (a == act) ? g : 0.f;
+    acc[MAXA] += g;
+  }
+  // warp fold (fixed butterfly), then the 8 warps in order
+#pragma unroll
+  for (int o = 0; o <= MAXA; ++o) {
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sft);
+    if (tx == 0) s[ty][o][0] = acc[o];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float t[MAXA + 1];
+#pragma unroll
+    for (int o = 0; o <= MAXA; ++o) {
+      t[o] = 0.f;
+      for (int w = 0; w < 8; ++w) t[o] += s[w][o][0];
+    }
+    const float sub = dueling ? t[MAXA] / (float)A : 0.f;
 #pragma unroll
     for (int a = 0; a < MAXA; ++a)
-      if (a < A) {
-        acc[a] += bout[a];
-        mean += acc[a];
-      }
-    mean /= (float)A;
-    float vv = vr ? accv + bv[0] : 0.f;
-    if (vr) vout[r] = vv;
-#pragma unroll
-    for (int a = 0; a < MAXA; ++a)
-      if (a < A) {
-        adv[r * A + a] = acc[a];
-        q[r * A + a] = vr ? (vv + acc[a] - mean) : acc[a];
-      }
+      if (a < A) g_outb[a] = t[a] - sub;
+    if (dueling) g_vb[0] = t[MAXA];
   }
 }
 
@@ -770,12 +996,18 @@ __global__ void k_heads_wgrad(const float* __restrict__ dtheta, const long long*
 
 // --------------------------------------------------------------------------- optimiser
 // stage 1: per-block sum of squares of the flat gradient (deterministic)
-__global__ void k_sumsq_partial(const float* __restrict__ g, double* __restrict__ part, size_t n) {
+__global__ void __launch_bounds__(256) k_sumsq_partial(const float* __restrict__ g, double* __restrict__ part, size_t n) {
   __shared__ double s[256];
   double acc = 0.0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+  const size_t n4 = n >> 2;     // the flat buffer is 256-byte aligned
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
-    double v = g[i];
+    float4 v = g4[i];
+    acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    double v = g[(n4 << 2) + threadIdx.x];
     acc += v * v;
   }
   s[threadIdx.x] = acc;
@@ -790,9 +1022,12 @@ __global__ void k_sumsq_partial(const float* __restrict__ g, double* __restrict_
 // stats[2] = grad_norm, stats[3] = clip coefficient applied
 __global__ void k_gradnorm_final(const double* __restrict__ part, int parts, float* __restrict__ stats,
                                  float clip, float grad_scale, float dyn_alpha) {
+  // one warp: lane-strided partial sums, then a fixed butterfly
+  double t = 0.0;
+  for (int i = threadIdx.x; i < parts; i += 32) t += part[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < parts; ++i) t += part[i];
     float norm = (float)sqrt(t) * grad_scale;
     stats[2] = norm;
     float coef = 1.f;

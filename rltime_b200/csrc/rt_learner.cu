@@ -140,6 +140,8 @@ struct rt_learner {
   float* colsum_part = nullptr;
   float *hw_part = nullptr, *hw_partb = nullptr;  // small-head weight-gradient partials
   int hw_parts = 256;
+  float* hb_part = nullptr;   // slab partials of k_heads_bwd_fused: [hb_slabs][A + 1][F or 2F]
+  int hb_slabs = 256;
   unsigned int* grid_barrier = nullptr;
   long long* lstm_dbg = nullptr;
   float* lstm_hrep = nullptr;   // replicated h exchange buffer of the persistent LSTM kernel
@@ -160,6 +162,8 @@ struct rt_learner {
   double* sumsq_part = nullptr;
   float* tau_stage = nullptr;  // device staging for injected taus (5 segments)
   unsigned long long rng_counter = 0;
+  cudaEvent_t ev_loss = nullptr;   // recorded once the losses / |td| of a step are final (before the backward pass)
+  float* h_stats = nullptr;        // pinned read-back of stats[0..3]
   std::map<std::string, std::pair<void*, long long>> debug;
   std::vector<void*> allocs;
 };
@@ -903,16 +907,18 @@ int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float*
       RT_TRY(gemm(h->gx, st, g));
     }
   }
-  // out layer + value layer + dueling combine: one warp per row
+  // out layer + value layer + dueling combine: one warp per 4 rows (A <= 8) / per row
   {
     const float* v1 = h->dueling ? h->v1 : nullptr;
-    int blocks = cdiv(MQ * 32, 256);
-    if (A <= 8)
-      rtk::k_heads_out<8><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
-                                                 net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A, ldh);
-    else
-      rtk::k_heads_out<32><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
-                                                  net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A, ldh);
+    if (A <= 8) {
+      int blocks = cdiv(cdiv(MQ, 4) * 32, 256);
+      rtk::k_heads_out<8, 4><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
+                                                    net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A, ldh);
+    } else {
+      int blocks = cdiv(MQ * 32, 256);
+      rtk::k_heads_out<32, 1><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
+                                                     net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A, ldh);
+    }
     RT_LAUNCH_CHECK();
   }
   return RT_OK;
@@ -926,56 +932,49 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
   const int duel = h->dueling ? 1 : 0;
   const float* xq = h->dqn ? feat : h->xq;
   float* dxq = h->dqn ? h->dfeatq : h->dxq;   // DQN: the data gradient of the heads IS d(loss)/d(feat)
-  // small layers (out, value): data gradients fused with the ReLU masks, weight gradients as
-  // slab partials folded deterministically
-  rtk::k_heads_dsmall<<<cdiv(MQ * F, 256), 256, 0, st>>>(h->dtheta, actions, net + h->o_outw,
-                                                        net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, MQ,
-                                                        F, A, Nq, duel, h->ldh);
-  RT_LAUNCH_CHECK();
+  // small layers (out, value): data gradients (ReLU masks fused), weight / bias gradients and the
+  // hidden-layer bias gradients in one pass over [h1 | v1] + one fold launch
   {
-    int nout = A + duel;
-    int rpb = 128;
-    int parts = cdiv(MQ, rpb);
-    if (parts > h->hw_parts) {
-      rpb = cdiv(MQ, h->hw_parts);
-      parts = cdiv(MQ, rpb);
+    const int C = F * (1 + duel);
+    int rpb = 256;
+    int slabs = cdiv(MQ, rpb);
+    if (slabs > h->hb_slabs) {
+      rpb = cdiv(MQ, h->hb_slabs);
+      slabs = cdiv(MQ, rpb);
     }
-    dim3 grid(cdiv(F, 32), parts);
-    if (A <= 8)
-      rtk::k_heads_wgrad<8><<<grid, dim3(32, 8), 0, st>>>(h->dtheta, actions, h->h1, h->v1, h->hw_part,
-                                                         h->hw_partb, MQ, F, A, Nq, duel, rpb, h->ldh);
-    else
-      rtk::k_heads_wgrad<32><<<grid, dim3(32, 8), 0, st>>>(h->dtheta, actions, h->h1, h->v1, h->hw_part,
-                                                          h->hw_partb, MQ, F, A, Nq, duel, rpb, h->ldh);
-    RT_LAUNCH_CHECK();
-    rtk::k_colsum_final<<<cdiv(A * F, 32), dim3(32, 8), 0, st>>>(h->hw_part, G + h->o_outw, parts, A * F,
-                                                               0, nout * F);
-    RT_LAUNCH_CHECK();
-    rtk::k_colsum_final<<<1, dim3(32, 8), 0, st>>>(h->hw_partb, G + h->o_outb, parts, A, 0, nout);
-    RT_LAUNCH_CHECK();
-    if (duel) {
-      rtk::k_colsum_final<<<cdiv(F, 32), dim3(32, 8), 0, st>>>(h->hw_part + (size_t)A * F, G + h->o_vw,
-                                                             parts, F, 0, nout * F);
+    dim3 grid(cdiv(C, 128), slabs);
+    float* g_vhb = G + h->o_vhb;
+    if (A <= 8) {
+      rtk::k_heads_bwd_fused<8><<<grid, dim3(32, 8), 0, st>>>(
+          h->dtheta, actions, net + h->o_outw, net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, h->hb_part, MQ,
+          F, A, Nq, duel, h->ldh, rpb);
       RT_LAUNCH_CHECK();
-      rtk::k_colsum_final<<<1, dim3(32, 8), 0, st>>>(h->hw_partb + A, G + h->o_vb, parts, 1, 0, nout);
+      rtk::k_heads_bwd_final<8><<<cdiv(C, 32) + 1, dim3(32, 8), 0, st>>>(
+          h->hb_part, slabs, h->dtheta, actions, G + h->o_outw, G + h->o_outb, G + h->o_vw, G + h->o_vb,
+          G + h->o_fcb, g_vhb, MQ, F, A, Nq, duel);
+    } else {
+      rtk::k_heads_bwd_fused<32><<<grid, dim3(32, 8), 0, st>>>(
+          h->dtheta, actions, net + h->o_outw, net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, h->hb_part, MQ,
+          F, A, Nq, duel, h->ldh, rpb);
       RT_LAUNCH_CHECK();
+      rtk::k_heads_bwd_final<32><<<cdiv(C, 32) + 1, dim3(32, 8), 0, st>>>(
+          h->hb_part, slabs, h->dtheta, actions, G + h->o_outw, G + h->o_outb, G + h->o_vw, G + h->o_vb,
+          G + h->o_fcb, g_vhb, MQ, F, A, Nq, duel);
     }
+    RT_LAUNCH_CHECK();
   }
   if (h->fused_hidden) {
     // [dh1 | dv1] against the stacked [Wfc ; Wvh]: weight gradient, bias gradient and data
     // gradient of both hidden layers in one GEMM each
     const int F2 = 2 * F;
     RT_TRY(gemm(h->gx, st, mk(h->dh1, F2, 1, xq, D, 0, G + h->o_fcw, D, F2, D, (int)MQ)));
-    RT_TRY(colsum(h, st, h->dh1, MQ, F2, G + h->o_fcb, 0));
     RT_TRY(gemm(h->gx, st, mk(h->dh1, F2, 0, net + h->o_fcw, D, 0, dxq, D, (int)MQ, D, F2)));
   } else {
   // FC
   RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 1, xq, D, 0, G + h->o_fcw, D, F, D, (int)MQ)));
-  RT_TRY(colsum(h, st, h->dh1, MQ, F, G + h->o_fcb, 0));
   RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 0, net + h->o_fcw, D, 0, dxq, D, (int)MQ, D, F)));
   if (h->dueling) {
     RT_TRY(gemm(h->gx, st, mk(h->dv1, F, 1, xq, D, 0, G + h->o_vhw, D, F, D, (int)MQ)));
-    RT_TRY(colsum(h, st, h->dv1, MQ, F, G + h->o_vhb, 0));
     rtk::GemmArgs g = mk(h->dv1, F, 0, net + h->o_vhw, D, 0, dxq, D, (int)MQ, D, F);
     g.accumulate = 1;
     RT_TRY(gemm(h->gx, st, g));
@@ -1333,6 +1332,8 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->report, (size_t)h->M, "report"));
   RT_TRY(dalloc(h, &h->row_q, (size_t)h->M, "row_q"));
   RT_TRY(dalloc(h, &h->stats, 8, "stats"));
+  RT_CUDA(cudaEventCreateWithFlags(&h->ev_loss, cudaEventDisableTiming));
+  RT_CUDA(cudaMallocHost(&h->h_stats, 8 * sizeof(float)));
   RT_TRY(dalloc(h, &h->dadv, MQ * A, "dadv"));
   RT_TRY(dalloc(h, &h->dv, MQ, "dv"));
   if (h->fused_hidden) {
@@ -1391,6 +1392,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   }
   RT_TRY(dalloc(h, &h->hw_part, (size_t)h->hw_parts * (A + 1) * F));
   RT_TRY(dalloc(h, &h->hw_partb, (size_t)h->hw_parts * (A + 1)));
+  RT_TRY(dalloc(h, &h->hb_part, (size_t)h->hb_slabs * (A + 1) * 2 * F));
   *out = h;
   return RT_OK;
 }
@@ -1400,6 +1402,8 @@ void rt_learner_destroy(rt_learner* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
+  if (h->ev_loss) cudaEventDestroy(h->ev_loss);
+  if (h->h_stats) cudaFreeHost(h->h_stats);
   delete h;
 }
 
@@ -1582,7 +1586,7 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
     else RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[1]));
     RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
     size_t off = (size_t)P * B;
-    rtk::k_iqn_target<<<cdiv(M, 128), 128, 0, st>>>(
+    rtk::k_iqn_target<<<cdiv(M, 4), 128, (size_t)4 * Nq * h->A * sizeof(float), st>>>(
         h->tq, h->sq, b->returns + off, b->target_masks + off, (const long long*)b->nsteps + off,
         h->targets, M, Nq, h->A, (float)h->td.gamma, h->td.vf_scale_epsilon);
     RT_LAUNCH_CHECK();
@@ -1612,7 +1616,7 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
     }
     RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
     size_t off = (size_t)P * B;
-    rtk::k_iqn_target<<<cdiv(M, 128), 128, 0, st>>>(
+    rtk::k_iqn_target<<<cdiv(M, 4), 128, (size_t)4 * Nq * h->A * sizeof(float), st>>>(
         h->tq, h->sq, b->returns + off, b->target_masks + off, (const long long*)b->nsteps + off,
         h->targets, M, Nq, h->A, (float)h->td.gamma, h->td.vf_scale_epsilon);
     RT_LAUNCH_CHECK();
@@ -1650,6 +1654,10 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
     rtk::k_loss_stats<<<1, 256, 0, st>>>(h->row_loss, h->report, h->stats, M, h->loss_scale);
     RT_LAUNCH_CHECK();
   }
+
+  // losses, |td| and the loss statistics are final here: the priority write-back and the next
+  // draw only depend on this point, not on the backward pass (rt_learner_wait_loss)
+  RT_CUDA(cudaEventRecord(h->ev_loss, st));
 
   // ---- backward
   RT_CUDA(cudaMemsetAsync(h->grad, 0, h->nparams * sizeof(float), st));
@@ -1725,6 +1733,25 @@ int rt_learner_act(rt_learner* h, int32_t E, const uint8_t* x, const float* hx, 
     RT_CUDA(cudaMemcpyAsync(h_out, h->h_all, (size_t)E * h->U * sizeof(float), cudaMemcpyDeviceToDevice, st));
     RT_CUDA(cudaMemcpyAsync(c_out, h->c_all, (size_t)E * h->U * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
+  return RT_OK;
+}
+
+int rt_learner_wait_loss(rt_learner* h, void* stream) {
+  RT_REQUIRE(h, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  RT_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_loss, 0));
+  return RT_OK;
+}
+
+int rt_learner_read_loss(rt_learner* h, float* loss, float* td_mean, void* stream) {
+  RT_REQUIRE(h, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  RT_CUDA(cudaStreamWaitEvent(st, h->ev_loss, 0));
+  RT_CUDA(cudaMemcpyAsync(h->h_stats, h->stats, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaStreamSynchronize(st));
+  if (loss) *loss = h->h_stats[0];
+  if (td_mean) *td_mean = h->h_stats[1];
   return RT_OK;
 }
 

@@ -408,6 +408,54 @@ struct DevVec {  // grow-only device scratch
   }
 };
 
+// One host->device upload per flush: every small delta array of a flush is packed into ONE pinned
+// staging block and moved with ONE cudaMemcpyAsync (pageable sources make the runtime stage each
+// copy and stall the issuing thread ~25 us per call).  Stages rotate; a stage is reused only after
+// the event recorded behind its consumer kernels has completed.
+struct Stage {
+  uint8_t* host = nullptr;
+  uint8_t* dev = nullptr;
+  size_t cap = 0, used = 0;
+  cudaEvent_t done = nullptr;
+  cudaError_t begin(size_t bytes) {
+    cudaError_t e;
+    if (!done && (e = cudaEventCreateWithFlags(&done, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventSynchronize(done)) != cudaSuccess) return e;
+    if (bytes > cap) {
+      if (host) cudaFreeHost(host);
+      if (dev) cudaFree(dev);
+      host = dev = nullptr;
+      cap = bytes + bytes / 2 + 4096;
+      if ((e = cudaMallocHost(reinterpret_cast<void**>(&host), cap)) != cudaSuccess) return e;
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&dev), cap)) != cudaSuccess) return e;
+    }
+    used = 0;
+    return cudaSuccess;
+  }
+  static size_t padded(size_t bytes) { return (bytes + 15) & ~(size_t)15; }
+  template <typename T>
+  const T* put(const std::vector<T>& v) {   // returns the DEVICE address the block will have
+    size_t at = used;
+    if (!v.empty()) memcpy(host + at, v.data(), v.size() * sizeof(T));
+    used += padded(v.size() * sizeof(T));
+    return reinterpret_cast<const T*>(dev + at);
+  }
+  cudaError_t send(cudaStream_t s) {
+    if (!used) return cudaSuccess;
+    return cudaMemcpyAsync(dev, host, used, cudaMemcpyHostToDevice, s);
+  }
+  cudaError_t fence(cudaStream_t s) { return cudaEventRecord(done, s); }
+  void release() {
+    if (host) cudaFreeHost(host);
+    if (dev) cudaFree(dev);
+    if (done) cudaEventDestroy(done);
+    host = dev = nullptr;
+    done = nullptr;
+    cap = used = 0;
+  }
+};
+#define RT_STAGES 4
+
 }  // namespace
 
 struct rt_tree {
@@ -469,11 +517,9 @@ struct rt_replay {
   std::unordered_map<int, std::pair<double, double>> u_tree;
   std::vector<int> u_env;
   std::vector<long long> u_env_id;
-  // flattened upload buffers
-  DevVec<int> dv_slot, dv_p2s_slot, dv_seq_idx, dv_seq_env, dv_env, dv_tree_idx;
-  DevVec<double> dv_reward, dv_tree_sum, dv_tree_min;
-  DevVec<uint8_t> dv_done;
-  DevVec<long long> dv_p2s_at, dv_seq_base, dv_env_id;
+  // packed pinned upload stages (one H2D copy per flush)
+  Stage stage[RT_STAGES];
+  int stage_cur = 0;
   // optional live timing of the gather kernel (bench.py roofline)
   bool profile = false;
   std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop)
@@ -565,46 +611,67 @@ int flush_updates(rt_replay* h, cudaStream_t st) {
     seq_env.push_back(kv.second.first);
     seq_base.push_back(kv.second.second);
   }
-  int n_slot = (int)h->u_slot.size(), n_p2s = (int)h->u_p2s_at.size(),
-      n_seq = (int)seq_idx.size(), n_env = (int)h->u_env.size();
-  if (n_slot + n_p2s + n_seq + n_env > 0) {
-    RT_CUDA(h->dv_slot.upload(h->u_slot, st));
-    RT_CUDA(h->dv_reward.upload(h->u_reward, st));
-    RT_CUDA(h->dv_done.upload(h->u_done, st));
-    RT_CUDA(h->dv_p2s_at.upload(h->u_p2s_at, st));
-    RT_CUDA(h->dv_p2s_slot.upload(h->u_p2s_slot, st));
-    RT_CUDA(h->dv_seq_idx.upload(seq_idx, st));
-    RT_CUDA(h->dv_seq_env.upload(seq_env, st));
-    RT_CUDA(h->dv_seq_base.upload(seq_base, st));
-    RT_CUDA(h->dv_env.upload(h->u_env, st));
-    RT_CUDA(h->dv_env_id.upload(h->u_env_id, st));
-    int work = n_slot > n_p2s ? n_slot : n_p2s;
-    int blocks = (work + 255) / 256;
-    if (blocks < 1) blocks = 1;
-    if (blocks > 296) blocks = 296;
-    k_apply_updates<<<blocks, 256, 0, st>>>(
-        h->d_reward, h->d_done, h->dv_slot.p, h->dv_reward.p, h->dv_done.p, n_slot,
-        h->d_pos2slot, h->dv_p2s_at.p, h->dv_p2s_slot.p, n_p2s, h->d_seq_env, h->d_seq_base,
-        h->dv_seq_idx.p, h->dv_seq_env.p, h->dv_seq_base.p, n_seq, h->d_env_ids, h->dv_env.p,
-        h->dv_env_id.p, n_env);
-    RT_LAUNCH_CHECK();
+  std::vector<int> tidx;
+  std::vector<double> tsum, tmin;
+  for (auto& kv : h->u_tree) {
+    tidx.push_back(kv.first);
+    tsum.push_back(kv.second.first);
+    tmin.push_back(kv.second.second);
   }
-  if (!h->u_tree.empty()) {
-    std::vector<int> tidx;
-    std::vector<double> tsum, tmin;
-    for (auto& kv : h->u_tree) {
-      tidx.push_back(kv.first);
-      tsum.push_back(kv.second.first);
-      tmin.push_back(kv.second.second);
+  int n_slot = (int)h->u_slot.size(), n_p2s = (int)h->u_p2s_at.size(),
+      n_seq = (int)seq_idx.size(), n_env = (int)h->u_env.size(), n_tree = (int)tidx.size();
+  const bool deltas = n_slot + n_p2s + n_seq + n_env > 0;
+  if (deltas || n_tree > 0) {
+    auto pb = [](size_t count, size_t elem) { return Stage::padded(count * elem); };
+    size_t bytes = 0;
+    if (deltas)
+      bytes += pb(n_slot, 4) + pb(n_slot, 8) + pb(n_slot, 1) + pb(n_p2s, 8) + pb(n_p2s, 4) +
+               pb(n_seq, 4) + pb(n_seq, 4) + pb(n_seq, 8) + pb(n_env, 4) + pb(n_env, 8);
+    if (n_tree > 0) bytes += pb(n_tree, 4) + 2 * pb(n_tree, 8);
+    Stage& sg = h->stage[h->stage_cur];
+    h->stage_cur = (h->stage_cur + 1) % RT_STAGES;
+    RT_CUDA(sg.begin(bytes));
+    const int *d_slot = nullptr, *d_p2s_slot = nullptr, *d_seq_idx = nullptr, *d_seq_env = nullptr,
+              *d_env = nullptr, *d_tidx = nullptr;
+    const double *d_reward = nullptr, *d_tsum = nullptr, *d_tmin = nullptr;
+    const uint8_t* d_done = nullptr;
+    const long long *d_p2s_at = nullptr, *d_seq_base = nullptr, *d_env_id = nullptr;
+    if (deltas) {
+      d_slot = sg.put(h->u_slot);
+      d_reward = sg.put(h->u_reward);
+      d_done = sg.put(h->u_done);
+      d_p2s_at = sg.put(h->u_p2s_at);
+      d_p2s_slot = sg.put(h->u_p2s_slot);
+      d_seq_idx = sg.put(seq_idx);
+      d_seq_env = sg.put(seq_env);
+      d_seq_base = sg.put(seq_base);
+      d_env = sg.put(h->u_env);
+      d_env_id = sg.put(h->u_env_id);
     }
-    RT_CUDA(h->dv_tree_idx.upload(tidx, st));
-    RT_CUDA(h->dv_tree_sum.upload(tsum, st));
-    RT_CUDA(h->dv_tree_min.upload(tmin, st));
-    int m = (int)tidx.size();
-    int threads = m < 1024 ? ((m + 31) / 32) * 32 : 1024;
-    k_tree_set<<<1, threads, 0, st>>>(h->d_sum, h->d_min, h->cap, h->depth, h->dv_tree_idx.p,
-                                      h->dv_tree_sum.p, h->dv_tree_min.p, m);
-    RT_LAUNCH_CHECK();
+    if (n_tree > 0) {
+      d_tidx = sg.put(tidx);
+      d_tsum = sg.put(tsum);
+      d_tmin = sg.put(tmin);
+    }
+    RT_CUDA(sg.send(st));
+    if (deltas) {
+      int work = n_slot > n_p2s ? n_slot : n_p2s;
+      int blocks = (work + 255) / 256;
+      if (blocks < 1) blocks = 1;
+      if (blocks > 296) blocks = 296;
+      k_apply_updates<<<blocks, 256, 0, st>>>(
+          h->d_reward, h->d_done, d_slot, d_reward, d_done, n_slot, h->d_pos2slot, d_p2s_at,
+          d_p2s_slot, n_p2s, h->d_seq_env, h->d_seq_base, d_seq_idx, d_seq_env, d_seq_base, n_seq,
+          h->d_env_ids, d_env, d_env_id, n_env);
+      RT_LAUNCH_CHECK();
+    }
+    if (n_tree > 0) {
+      int threads = n_tree < 1024 ? ((n_tree + 31) / 32) * 32 : 1024;
+      k_tree_set<<<1, threads, 0, st>>>(h->d_sum, h->d_min, h->cap, h->depth, d_tidx, d_tsum, d_tmin,
+                                        n_tree);
+      RT_LAUNCH_CHECK();
+    }
+    RT_CUDA(sg.fence(st));
   }
   h->u_slot.clear();
   h->u_reward.clear();
@@ -813,11 +880,7 @@ void rt_replay_destroy(rt_replay* h) {
     if (bs.h_uniforms) cudaFreeHost(bs.h_uniforms);
     if (bs.h2d_done) cudaEventDestroy(bs.h2d_done);
   }
-  h->dv_slot.release(); h->dv_p2s_slot.release(); h->dv_seq_idx.release();
-  h->dv_seq_env.release(); h->dv_env.release(); h->dv_tree_idx.release();
-  h->dv_reward.release(); h->dv_tree_sum.release(); h->dv_tree_min.release();
-  h->dv_done.release(); h->dv_p2s_at.release(); h->dv_seq_base.release();
-  h->dv_env_id.release();
+  for (auto& sg : h->stage) sg.release();
   if (h->h_td) cudaFreeHost(h->h_td);
   if (h->h_idx) cudaFreeHost(h->h_idx);
   if (h->ev) cudaEventDestroy(h->ev);

@@ -13,6 +13,15 @@ batch gather run in librltime_b200.so (CUDA, sm_100a); this file only flattens t
 sample dicts into leaves, keeps the train-quota arithmetic and rebuilds the nested,
 time-major (S, B, ...) train-data dict out of borrowed device tensors.
 
+Streams: every replay kernel / copy runs on the buffer's OWN CUDA stream, so ingest, the
+priority write-back and the next draw + gather overlap whatever the caller's stream is doing
+(the learner's backward pass).  get_train_data makes the caller's current stream wait for the
+gather, so the returned tensors are safe to use there; a batch stays valid until the
+second-next get_train_data call (3 rotating slots, like StateStore's history,
+rltime/general/backend.py:88,149-152).  Host arrays handed to update() / update_arrays() must
+stay unmodified until the next update_losses*() / sync() (the reference keeps them by
+reference forever, history.py:159-171).
+
 There is no CPU fallback: without a CUDA device / the built library construction raises.
 """
 import ctypes as C
@@ -136,11 +145,32 @@ class DeviceReplayHistoryBuffer:
         self._po_skel = None
         self.last_sampled_idxes = None
         self.last_batch = None
+        self._own = torch.cuda.Stream(self.device)
+        self._prev_mark = None      # caller-stream event recorded when the previous draw was requested
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
+        return C.c_void_p(self._own.cuda_stream)
+
+    def sync(self):
+        """Blocks until everything this buffer enqueued (ingest copies included) has run."""
+        self._own.synchronize()
+
+    def _begin_draw(self):
+        """Slot-reuse fence: the gather of draw k overwrites the slot draw k-3 used; whatever the
+        caller had enqueued on its stream when draw k-1 was requested (the consumers of draws
+        <= k-2) must be done first.  It does not wait for the consumer of draw k-1, which is what
+        overlaps with this draw."""
         import torch
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        cur = torch.cuda.current_stream(self.device)
+        if self._prev_mark is not None:
+            self._own.wait_event(self._prev_mark)
+        self._prev_mark = torch.cuda.Event()
+        self._prev_mark.record(cur)
+        return cur
+
+    def _end_draw(self, cur):
+        cur.wait_stream(self._own)
 
     def _extra_config(self, cfg):
         cfg.overlap = 0
@@ -276,6 +306,9 @@ class DeviceReplayHistoryBuffer:
             return arr
         sp = ptrs(state_cols, self._state_leaves)
         pp = ptrs(po_cols, self._po_leaves)
+        if on_device:
+            import torch
+            self._own.wait_stream(torch.cuda.current_stream(self.device))
         _lib.check(self._lib.rt_replay_append(
             self._h, m, env.ctypes.data, env_ids.ctypes.data, reward.ctypes.data,
             done.ctypes.data, C.cast(sp, C.c_void_p), C.cast(pp, C.c_void_p),
@@ -284,8 +317,7 @@ class DeviceReplayHistoryBuffer:
             self.train_quota += self.train_frequency * m
         if on_device:
             # the copies are stream-ordered; keep the sources alive until they ran
-            import torch
-            torch.cuda.current_stream(self.device).synchronize()
+            self._own.synchronize()
 
     def profile_gather(self, enable=True):
         _lib.check(self._lib.rt_replay_profile(self._h, 1 if enable else 0))
@@ -322,8 +354,10 @@ class DeviceReplayHistoryBuffer:
             return None
         choices = np.ascontiguousarray(np.random.choice(total_available, mbatch_size),
                                        dtype=np.int64)
+        cur = self._begin_draw()
         _lib.check(self._lib.rt_replay_sample_uniform(
             self._h, mbatch_size, choices.ctypes.data, self._stream()))
+        self._end_draw(cur)
         return self._wrap_batch()
 
     def _wrap_batch(self):
@@ -429,8 +463,10 @@ class DevicePrioritizedReplayHistoryBuffer(DeviceReplayHistoryBuffer):
                              self._beta_anneal, 1.0)
         if self._h is None:
             return None
+        cur = self._begin_draw()
         rc = _lib.check(self._lib.rt_replay_sample_prioritized(
             self._h, mbatch_size, float(beta), C.cast(uniforms, C.c_void_p), self._stream()))
+        self._end_draw(cur)
         if rc == _lib.RT_NEED_MORE_DATA:
             self._last_idx_tensor = None
             return None
@@ -458,9 +494,17 @@ class DevicePrioritizedReplayHistoryBuffer(DeviceReplayHistoryBuffer):
         _lib.check(self._lib.rt_replay_update_losses(
             self._h, len(pairs), pairs.ctypes.data, losses.ctypes.data, self._stream()))
 
-    def update_losses_device(self, td_abs):
+    def update_losses_device(self, td_abs, ready=None):
         """Priority write-back for the rows trained from the last draw, |td| still on the
-        device (fp32, (T*B,) time-major)."""
+        device (fp32, (T*B,) time-major).  `ready(stream_ptr)`, when given, makes the buffer's
+        stream wait for just the point where td_abs is final (DeviceLearner.wait_loss: before the
+        backward pass), so the write-back and the next draw overlap the rest of the update;
+        otherwise the buffer's stream waits for everything enqueued on the caller's stream."""
         assert td_abs.is_cuda and td_abs.dtype.itemsize == 4 and td_abs.is_contiguous()
+        if ready is not None:
+            ready(self._stream())
+        else:
+            import torch
+            self._own.wait_stream(torch.cuda.current_stream(self.device))
         _lib.check(self._lib.rt_replay_update_losses_last(
             self._h, C.c_void_p(td_abs.data_ptr()), self._stream()))

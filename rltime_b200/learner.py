@@ -213,6 +213,22 @@ class DeviceLearner:
                                                       C.byref(n)))
         return list(zip(fl[:n.value].tolist(), ms[:n.value].tolist()))
 
+    def wait_loss(self, stream_ptr):
+        """Makes the CUDA stream `stream_ptr` wait until the |td| / losses of the last enqueued
+        step are final (they are before its backward pass)."""
+        _lib.check(self._lib.rt_learner_wait_loss(self._h, stream_ptr))
+
+    def loss(self):
+        """{'qloss', 'td_mean'} of the last step, read back as soon as the forward pass is done
+        (does not wait for the backward pass / Adam; stats() does)."""
+        import torch
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.device)
+        a, b = C.c_float(), C.c_float()
+        _lib.check(self._lib.rt_learner_read_loss(self._h, C.byref(a), C.byref(b),
+                                                  C.c_void_p(self._side.cuda_stream)))
+        return {"qloss": a.value, "td_mean" if self.policy == "iqn" else "qvalue": b.value}
+
     def td_abs(self):
         p = C.c_void_p()
         _lib.check(self._lib.rt_learner_td_abs(self._h, C.byref(p)))

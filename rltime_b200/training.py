@@ -206,7 +206,7 @@ class IQNTrainer:
                 continue
             learner.step(hist.last_batch)
             if hasattr(hist, "update_losses_device"):
-                hist.update_losses_device(learner.td_abs())
+                hist.update_losses_device(learner.td_abs(), ready=learner.wait_loss)
             self.updates += 1
             if lr_anneal not in (False, None):
                 anneal_to = 0.0 if lr_anneal is True else float(lr_anneal)

@@ -40,9 +40,13 @@ def main():
     if not rows:
         print("no device events captured")
         return
+    def short_name(n):
+        n = n.replace("(anonymous namespace)::", "").replace("void ", "")
+        return n.split("(")[0][-70:]
+    rows = [(s, e, short_name(n)) for s, e, n in rows]
     per = {}
     for s, e, n in rows:
-        short = n.split("(")[0][-70:]
+        short = n
         a = per.setdefault(short, [0, 0.0])
         a[0] += 1
         a[1] += e - s
@@ -53,7 +57,7 @@ def main():
     for s, e, n in rows[1:]:
         if s > cur_e:
             busy += cur_e - cur_s
-            gaps.append((s - cur_e, n.split("(")[0][-60:]))
+            gaps.append((s - cur_e, n[-60:]))
             cur_s, cur_e = s, e
         else:
             cur_e = max(cur_e, e)

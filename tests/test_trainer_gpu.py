@@ -89,3 +89,65 @@ def test_dqn_trainer_rainbow_style_end_to_end():
     assert "value_hidden_layer.weight" in sd and "quantile_layer.weight" not in sd
     pred = tr.policy.actor_predict(actors.last_state, timesteps=1)
     assert pred["qvalues"].shape == (4, 4) and (pred["actions"] == pred["qvalues"].argmax(1)).all()
+
+
+@pytest.mark.gpu
+def test_pipelined_update_loop_is_bit_identical_to_the_serialised_one():
+    """The priority write-back / next draw overlap the backward pass (own replay stream +
+    rt_learner_wait_loss): sampled indices, |td| and the trained weights must not change by a bit
+    against the same loop with a full device synchronisation between every call."""
+    import random
+    import torch
+    from rltime_b200.history import DevicePrioritizedReplayHistoryBuffer
+    from rltime_b200.init import init_params
+    from rltime_b200.learner import DeviceLearner
+    E, T, n, B, A, U = 8, 6, 2, 8, 4, 64
+    dev = torch.device("cuda", 0)
+
+    def run(pipelined):
+        random.seed(5)
+        rs = np.random.RandomState(3)
+        hist = DevicePrioritizedReplayHistoryBuffer(
+            size=4096, train_frequency=None, alpha=0.9, beta=0.6, nstep_target=n, nstep_train=T,
+            prefix_steps=0, gamma=0.99, max_envs=E, device=dev)
+        L = DeviceLearner((4, 84, 84), [(16, 8, 4), (16, 4, 2)], U, 64, A, 8, 16, True, mbatch=B,
+                          nstep_train=T, nstep_target=n, double_q=True, rnn_bootstrap=True,
+                          clip_grad=40.0, seed=11, device=dev)
+        L.load_state_dict(init_params(L.param_info, U, seed=1), 0)
+        L.load_state_dict(init_params(L.param_info, U, seed=2), 1)
+
+        def feed(m_steps):
+            m = m_steps * E
+            env = np.arange(m) % E
+            hist.update_arrays(env, np.sign(rs.randn(m)), (rs.rand(m) < 0.02).astype(np.uint8),
+                               [rs.randint(0, 255, (m, 4, 84, 84)).astype(np.uint8),
+                                rs.randn(m, U).astype(np.float32), rs.randn(m, U).astype(np.float32),
+                                np.zeros(m, np.float32)],
+                               [rs.randint(0, A, m).astype(np.int64), rs.randn(m, A).astype(np.float32)])
+        feed(200)
+        idx_log, td_log = [], []
+        for it in range(40):
+            if it % 3 == 0:
+                feed(2)
+            assert hist.get_train_data(B, 0.0) is not None
+            if not pipelined:
+                torch.cuda.synchronize()
+            L.step(hist.last_batch)
+            if pipelined:
+                hist.update_losses_device(L.td_abs(), ready=L.wait_loss)
+            else:
+                torch.cuda.synchronize()
+                hist.update_losses_device(L.td_abs())
+                torch.cuda.synchronize()
+            # async device-side copies on the caller's stream: no host sync inside the loop
+            idx_log.append(hist._last_idx_tensor.clone())
+            td_log.append(L.td_abs().clone())
+        torch.cuda.synchronize()
+        return ([t.cpu().tolist() for t in idx_log], torch.stack(td_log).cpu().numpy(),
+                L.flat(0).cpu().numpy().copy(), hist.tree_sum())
+
+    a, b = run(False), run(True)
+    assert a[0] == b[0]
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[2], b[2])
+    assert a[3] == b[3]
