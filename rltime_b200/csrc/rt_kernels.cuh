@@ -651,9 +651,12 @@ __global__ void __launch_bounds__(256) k_heads_out(const float* __restrict__ h1,
                             const float* __restrict__ Wv, const float* __restrict__ bv,
                             float* __restrict__ adv, float* __restrict__ vout, float* __restrict__ q,
                             size_t rows, int F, int A, int ldh) {
-  size_t r0 = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW;
   int lane = threadIdx.x & 31;
-  if (r0 >= rows) return;
+  // grid-stride over groups of RPW rows: the launch sizes the grid to the resident warps, so the
+  // last wave is as full as the others
+  const size_t warps_total = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t r0 = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW; r0 < rows;
+       r0 += warps_total * RPW) {
   float acc[RPW][MAXA], accv[RPW];
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
@@ -723,6 +726,7 @@ __global__ void __launch_bounds__(256) k_heads_out(const float* __restrict__ h1,
         }
     }
   }
+  }
 }
 
 // Backward of the two small layers in ONE pass over the hidden activations (rows x C virtual
@@ -735,13 +739,13 @@ __global__ void __launch_bounds__(256) k_heads_out(const float* __restrict__ h1,
 //     part[slab][A][c]  = sum_r dh1|dv1[r,c]               (bias gradient of the hidden layers)
 // k_heads_bwd_final folds the slabs in a fixed order.  Grid (ceil(C/128), slabs), block (32, 8);
 // a thread owns 4 consecutive columns; warps stride the slab's rows.
-template <int MAXA>
-__global__ void __launch_bounds__(256) k_heads_bwd_fused(
+template <int MAXA, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) k_heads_bwd_fused(
     const float* __restrict__ dtheta, const long long* __restrict__ actions,
     const float* __restrict__ Wout, const float* __restrict__ Wv, const float* __restrict__ h1,
     const float* __restrict__ v1, float* __restrict__ dh1, float* __restrict__ dv1,
-    float* __restrict__ part, size_t rows, int F, int A, int Nq, int dueling, int ldh,
-    int rows_per_block) {
+    float* __restrict__ part, float* __restrict__ partb, size_t rows, int F, int A, int Nq,
+    int dueling, int ldh, int rows_per_block) {
   __shared__ __align__(16) float s_w[MAXA][128];
   __shared__ __align__(16) float s_red[8][128];
   const int C = F * (dueling ? 2 : 1);
@@ -774,32 +778,58 @@ __global__ void __launch_bounds__(256) k_heads_bwd_fused(
   if (r1 > rows) r1 = rows;
   const float* src = isv ? v1 : h1;
   float* dst = isv ? dv1 : dh1;
+  // bias partials of the out / value layers (column block 0 only, one lane per warp):
+  //   accb[a] = sum_{r: act = a} g_r,  accb[MAXA] = sum_r g_r
+  // (g and act are warp-uniform per row: lane a keeps action a's sum, every lane the total)
+  float accb = 0.f, accg = 0.f;
+  const bool bias_cta = blockIdx.x == 0;
   if (valid) {
-#pragma unroll 2
-    for (size_t r = r0 + ty; r < r1; r += 8) {
-      const float g = dtheta[r];
-      const int act = (int)actions[r / Nq];
-      const float4 x = __ldcs(reinterpret_cast<const float4*>(src + r * ldh + f));
-      float4 d;
-      if (!isv) {
-        const float4 w = *reinterpret_cast<const float4*>(&s_w[act][tx * 4]);
-        d.x = x.x > 0.f ? g * w.x : 0.f; d.y = x.y > 0.f ? g * w.y : 0.f;
-        d.z = x.z > 0.f ? g * w.z : 0.f; d.w = x.w > 0.f ? g * w.w : 0.f;
-        const float gx = g * x.x, gy = g * x.y, gz = g * x.z, gw = g * x.w;
+    constexpr int RIF = 4;   // rows in flight per thread: 4 independent 16-byte loads
+    for (size_t rb = r0 + ty; rb < r1; rb += 8 * RIF) {
+      float4 xs[RIF];
+      float gs[RIF];
+      int acts[RIF];
 #pragma unroll
-        for (int a = 0; a < MAXA; ++a) {
-          const bool hit = a == act;
-          acc[a][0] += hit ? gx : 0.f; acc[a][1] += hit ? gy : 0.f;
-          acc[a][2] += hit ? gz : 0.f; acc[a][3] += hit ? gw : 0.f;
-        }
-      } else {
-        d.x = x.x > 0.f ? g * wv.x : 0.f; d.y = x.y > 0.f ? g * wv.y : 0.f;
-        d.z = x.z > 0.f ? g * wv.z : 0.f; d.w = x.w > 0.f ? g * wv.w : 0.f;
-        acc[0][0] = fmaf(g, x.x, acc[0][0]); acc[0][1] = fmaf(g, x.y, acc[0][1]);
-        acc[0][2] = fmaf(g, x.z, acc[0][2]); acc[0][3] = fmaf(g, x.w, acc[0][3]);
+      for (int i = 0; i < RIF; ++i) {
+        const size_t r = rb + (size_t)8 * i;
+        const bool in = r < r1;
+        const size_t rr = in ? r : rb;
+        xs[i] = __ldcs(reinterpret_cast<const float4*>(src + rr * ldh + f));
+        gs[i] = in ? dtheta[rr] : 0.f;
+        acts[i] = (int)actions[rr / Nq];
       }
-      *reinterpret_cast<float4*>(dst + r * ldh + f) = d;
-      cs[0] += d.x; cs[1] += d.y; cs[2] += d.z; cs[3] += d.w;
+#pragma unroll
+      for (int i = 0; i < RIF; ++i) {
+        const size_t r = rb + (size_t)8 * i;
+        if (r >= r1) break;
+        const float g = gs[i];
+        const int act = acts[i];
+        const float4 x = xs[i];
+        float4 d;
+        if (!isv) {
+          const float4 w = *reinterpret_cast<const float4*>(&s_w[act][tx * 4]);
+          d.x = x.x > 0.f ? g * w.x : 0.f; d.y = x.y > 0.f ? g * w.y : 0.f;
+          d.z = x.z > 0.f ? g * w.z : 0.f; d.w = x.w > 0.f ? g * w.w : 0.f;
+          const float gx = g * x.x, gy = g * x.y, gz = g * x.z, gw = g * x.w;
+#pragma unroll
+          for (int a = 0; a < MAXA; ++a) {
+            const bool hit = a == act;
+            acc[a][0] += hit ? gx : 0.f; acc[a][1] += hit ? gy : 0.f;
+            acc[a][2] += hit ? gz : 0.f; acc[a][3] += hit ? gw : 0.f;
+          }
+        } else {
+          d.x = x.x > 0.f ? g * wv.x : 0.f; d.y = x.y > 0.f ? g * wv.y : 0.f;
+          d.z = x.z > 0.f ? g * wv.z : 0.f; d.w = x.w > 0.f ? g * wv.w : 0.f;
+          acc[0][0] = fmaf(g, x.x, acc[0][0]); acc[0][1] = fmaf(g, x.y, acc[0][1]);
+          acc[0][2] = fmaf(g, x.z, acc[0][2]); acc[0][3] = fmaf(g, x.w, acc[0][3]);
+        }
+        __stcs(reinterpret_cast<float4*>(dst + r * ldh + f), d);
+        cs[0] += d.x; cs[1] += d.y; cs[2] += d.z; cs[3] += d.w;
+        if (bias_cta) {
+          accb += (tx == act) ? g : 0.f;
+          accg += g;
+        }
+      }
     }
   }
   // fold the 8 warps (fixed order) and emit this slab's partials
@@ -820,6 +850,18 @@ __global__ void __launch_bounds__(256) k_heads_bwd_fused(
       part[((size_t)blockIdx.y * NP + o) * C + blockIdx.x * 128 + col] = t;
     }
   }
+  if (blockIdx.x == 0) {
+    __syncthreads();
+    if (tx < MAXA) s_red[ty][tx] = accb;
+    if (tx == 0) s_red[ty][MAXA] = accg;
+    __syncthreads();
+    const int a = ty * 32 + tx;
+    if (a <= MAXA) {
+      float t = ((s_red[0][a] + s_red[1][a]) + (s_red[2][a] + s_red[3][a])) +
+                ((s_red[4][a] + s_red[5][a]) + (s_red[6][a] + s_red[7][a]));
+      partb[(size_t)blockIdx.y * (MAXA + 1) + a] = t;
+    }
+  }
 }
 
 // Folds the slab partials of k_heads_bwd_fused into the gradients of the out layer (Wout, bout),
@@ -827,10 +869,10 @@ __global__ void __launch_bounds__(256) k_heads_bwd_fused(
 // (threads (32, 8): ty strides the slabs); the last block reduces the two bias vectors from dtheta.
 template <int MAXA>
 __global__ void __launch_bounds__(256) k_heads_bwd_final(
-    const float* __restrict__ part, int slabs, const float* __restrict__ dtheta,
-    const long long* __restrict__ actions, float* __restrict__ g_outw, float* __restrict__ g_outb,
-    float* __restrict__ g_vw, float* __restrict__ g_vb, float* __restrict__ g_fcb,
-    float* __restrict__ g_vhb, size_t rows, int F, int A, int Nq, int dueling) {
+    const float* __restrict__ part, const float* __restrict__ partb, int slabs,
+    float* __restrict__ g_outw, float* __restrict__ g_outb, float* __restrict__ g_vw,
+    float* __restrict__ g_vb, float* __restrict__ g_fcb, float* __restrict__ g_vhb, int F, int A,
+    int dueling) {
   const int C = F * (dueling ? 2 : 1);
   const int NP = A + 1;
   const int col_blocks = (C + 31) / 32;
@@ -878,120 +920,17 @@ __global__ void __launch_bounds__(256) k_heads_bwd_final(
     return;
   }
   // bias gradients: bout[a] = sum_{r: act = a} g_r - dueling * (sum_r g_r) / A;  bv = sum_r g_r
-  float acc[MAXA + 1];
-#pragma unroll
-  for (int o = 0; o <= MAXA; ++o) acc[o] = 0.f;
+  // (slab partials from k_heads_bwd_fused; thread a folds column a in slab order)
   const int tid = ty * 32 + tx;
-  for (size_t r = tid; r < rows; r += 256) {
-    const float g = dtheta[r];
-    const int act = (int)actions[r / Nq];
-#pragma unroll
-    for (int a = 0; a < MAXA; ++a) acc[a] += (a == act) ? g : 0.f;
-    acc[MAXA] += g;
-  }
-  // warp fold (fixed butterfly), then the 8 warps in order
-#pragma unroll
-  for (int o = 0; o <= MAXA; ++o) {
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sft);
-    if (tx == 0) s[ty][o][0] = acc[o];
+  float* sb = &s[0][0][0];
+  if (tid <= MAXA) {
+    float t = 0.f;
+    for (int p = 0; p < slabs; ++p) t += partb[(size_t)p * (MAXA + 1) + tid];
+    sb[tid] = t;
   }
   __syncthreads();
-  if (tid == 0) {
-    float t[MAXA + 1];
-#pragma unroll
-    for (int o = 0; o <= MAXA; ++o) {
-      t[o] = 0.f;
-      for (int w = 0; w < 8; ++w) t[o] += s[w][o][0];
-    }
-    const float sub = dueling ? t[MAXA] / (float)A : 0.f;
-#pragma unroll
-    for (int a = 0; a < MAXA; ++a)
-      if (a < A) g_outb[a] = t[a] - sub;
-    if (dueling) g_vb[0] = t[MAXA];
-  }
-}
-
-// Data gradients of the two small layers, fused with the ReLU masks of their inputs:
-//   dh1[r,f] = (sum_a dadv[r,a] Wout[a,f]) * (h1 > 0),  dadv[r,a] = g_r (1[a==act] - dueling/A)
-//   dv1[r,f] = g_r Wv[f] * (v1 > 0)                      (dueling only)
-__global__ void k_heads_dsmall(const float* __restrict__ dtheta, const long long* __restrict__ actions,
-                               const float* __restrict__ Wout, const float* __restrict__ Wv,
-                               const float* __restrict__ h1, const float* __restrict__ v1,
-                               float* __restrict__ dh1, float* __restrict__ dv1, size_t rows, int F, int A,
-                               int Nq, int dueling, int ldh) {
-  size_t idx0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx0 >= rows * F) return;
-  size_t r = idx0 / F;
-  int f = (int)(idx0 - r * F);
-  size_t idx = r * ldh + f;
-  float g = dtheta[r];
-  int act = (int)actions[r / Nq];
-  float w = Wout[(size_t)act * F + f];
-  if (dueling) {
-    float mean = 0.f;
-    for (int a = 0; a < A; ++a) mean += Wout[(size_t)a * F + f];
-    w -= mean / (float)A;
-  }
-  dh1[idx] = h1[idx] > 0.f ? g * w : 0.f;
-  if (dueling) dv1[idx] = v1[idx] > 0.f ? g * Wv[f] : 0.f;
-}
-
-// Weight / bias gradients of the two small layers: partial sums over a slab of rows.
-//   part[p][a][f] = sum_r dadv[r,a] h1[r,f]   (a < A)       part[p][A][f] = sum_r g_r v1[r,f]
-//   partb[p][a]   = sum_r dadv[r,a]                          partb[p][A]  = sum_r g_r
-template <int MAXA>
-__global__ void k_heads_wgrad(const float* __restrict__ dtheta, const long long* __restrict__ actions,
-                              const float* __restrict__ h1, const float* __restrict__ v1,
-                              float* __restrict__ part, float* __restrict__ partb, size_t rows, int F,
-                              int A, int Nq, int dueling, int rows_per_block, int ldh) {
-  __shared__ float s[8][33];
-  int f = blockIdx.x * 32 + threadIdx.x;
-  size_t r0 = (size_t)blockIdx.y * rows_per_block, r1 = r0 + rows_per_block;
-  if (r1 > rows) r1 = rows;
-  float acc[MAXA + 1], accb[MAXA + 1];
-#pragma unroll
-  for (int a = 0; a <= MAXA; ++a) acc[a] = accb[a] = 0.f;
-  const float inv = dueling ? 1.f / (float)A : 0.f;
-  if (f < F)
-    for (size_t r = r0 + threadIdx.y; r < r1; r += 8) {
-      float g = dtheta[r];
-      int act = (int)actions[r / Nq];
-      float hv = h1[r * ldh + f];
-#pragma unroll
-      for (int a = 0; a < MAXA; ++a)
-        if (a < A) {
-          float d = g * ((a == act ? 1.f : 0.f) - inv);
-          acc[a] = fmaf(d, hv, acc[a]);
-          accb[a] += d;
-        }
-      if (dueling) {
-        acc[MAXA] = fmaf(g, v1[r * ldh + f], acc[MAXA]);
-        accb[MAXA] += g;
-      }
-    }
-  const int nout = A + (dueling ? 1 : 0);
-  for (int o = 0; o < nout; ++o) {
-    int a = (o == A) ? MAXA : o;
-    __syncthreads();
-    s[threadIdx.y][threadIdx.x] = acc[a];
-    __syncthreads();
-    if (threadIdx.y == 0 && f < F) {
-      float t = 0.f;
-      for (int j = 0; j < 8; ++j) t += s[j][threadIdx.x];
-      part[((size_t)blockIdx.y * nout + o) * F + f] = t;
-    }
-    if (blockIdx.x == 0) {   // bias partials: identical across f, take column 0's lanes
-      __syncthreads();
-      s[threadIdx.y][threadIdx.x] = accb[a];
-      __syncthreads();
-      if (threadIdx.y == 0 && threadIdx.x == 0) {
-        float t = 0.f;
-        for (int j = 0; j < 8; ++j) t += s[j][0];
-        partb[(size_t)blockIdx.y * nout + o] = t;
-      }
-    }
-  }
+  if (tid < A) g_outb[tid] = sb[tid] - (dueling ? sb[MAXA] / (float)A : 0.f);
+  if (tid == 0 && dueling) g_vb[0] = sb[MAXA];
 }
 
 // --------------------------------------------------------------------------- optimiser

@@ -141,6 +141,7 @@ struct rt_learner {
   float *hw_part = nullptr, *hw_partb = nullptr;  // small-head weight-gradient partials
   int hw_parts = 256;
   float* hb_part = nullptr;   // slab partials of k_heads_bwd_fused: [hb_slabs][A + 1][F or 2F]
+  float* hb_partb = nullptr;  // ... and of the out / value bias gradients: [hb_slabs][33]
   int hb_slabs = 256;
   unsigned int* grid_barrier = nullptr;
   long long* lstm_dbg = nullptr;
@@ -163,6 +164,19 @@ struct rt_learner {
   float* tau_stage = nullptr;  // device staging for injected taus (5 segments)
   unsigned long long rng_counter = 0;
   cudaEvent_t ev_loss = nullptr;   // recorded once the losses / |td| of a step are final (before the backward pass)
+  // CUDA-graph replay of the update (the ~120 launches of a step leave ~2 us of idle GPU between
+  // consecutive kernels when issued one by one).  Graphs cannot be captured on the legacy default
+  // stream, so the update runs on the learner's own stream, forked from / joined to the caller's.
+  struct StepGraphs {
+    const void* key[10] = {};
+    cudaGraphExec_t fwd = nullptr, bwd = nullptr;
+    long long n_fwd = 0, n_bwd = 0;      // launches each replay stands for (rt_launch_count)
+  };
+  std::vector<StepGraphs> graphs;
+  int graphs_enabled = 1;
+  long long steps_done = 0;
+  cudaStream_t own = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float* h_stats = nullptr;        // pinned read-back of stats[0..3]
   std::map<std::string, std::pair<void*, long long>> debug;
   std::vector<void*> allocs;
@@ -742,7 +756,11 @@ int lstm_recur_one(rt_learner* h, cudaStream_t st, const SeqDesc& q, int timeste
       void (*kern)(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
                    float*, float*, float*, int, int, int, unsigned int*, long long*) =
           U == 512 ? rtk::k_lstm_seq_fwd<8> : rtk::k_lstm_seq_fwd<4>;
-      RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      static size_t configured[2] = {0, 0};
+      if (configured[U == 512] < smem) {
+        RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[U == 512] = smem;
+      }
       RT_CUDA(cudaMemsetAsync(h->grid_barrier, 0, sizeof(unsigned int), st));
       const float* whh = q.net + h->o_whh;
       void* args[] = {(void*)&q.xg, (void*)&whh, (void*)&q.hx, (void*)&q.cx, (void*)&q.initials,
@@ -776,7 +794,11 @@ int launch_lstm_tc(rt_learner* h, cudaStream_t st, const CUtensorMap* w0, const 
                    const rttc::LstmTcArgs& a, int ctas) {
   auto kern = rttc::k_lstm_seq_tc<UPC>;
   const int smem = rttc::LstmSmem<UPC>::total(a.U, a.arows);
-  RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static int configured = 0;
+  if (configured < smem) {
+    RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
   RT_CUDA(cudaMemsetAsync(h->grid_barrier, 0, 64 * sizeof(unsigned int), st));
   void* args[] = {(void*)w0, (void*)w1, (void*)&a};
   // cooperative launch: all CTAs co-resident (they wait on each other's step counters)
@@ -907,15 +929,21 @@ int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float*
       RT_TRY(gemm(h->gx, st, g));
     }
   }
-  // out layer + value layer + dueling combine: one warp per 4 rows (A <= 8) / per row
+  // out layer + value layer + dueling combine: one warp per 2 rows (A <= 8) / per row, grid sized
+  // to the resident warps (grid-stride inside)
   {
     const float* v1 = h->dueling ? h->v1 : nullptr;
     if (A <= 8) {
-      int blocks = cdiv(cdiv(MQ, 4) * 32, 256);
-      rtk::k_heads_out<8, 4><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
+      static int occ = 0;
+      if (!occ) RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rtk::k_heads_out<8, 2>, 256, 0));
+      int blocks = cdiv(cdiv(MQ, 2) * 32, 256);
+      int resident = h->num_sms * (occ > 0 ? occ : 1);
+      if (blocks > resident) blocks = resident;
+      rtk::k_heads_out<8, 2><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
                                                     net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A, ldh);
     } else {
       int blocks = cdiv(MQ * 32, 256);
+      if (blocks > h->num_sms * 8) blocks = h->num_sms * 8;
       rtk::k_heads_out<32, 1><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
                                                      net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A, ldh);
     }
@@ -933,33 +961,49 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
   const float* xq = h->dqn ? feat : h->xq;
   float* dxq = h->dqn ? h->dfeatq : h->dxq;   // DQN: the data gradient of the heads IS d(loss)/d(feat)
   // small layers (out, value): data gradients (ReLU masks fused), weight / bias gradients and the
-  // hidden-layer bias gradients in one pass over [h1 | v1] + one fold launch
+  // hidden-layer bias gradients in one pass over [h1 | v1] + one fold launch.  The slab count makes
+  // the grid one full wave of resident CTAs.
   {
     const int C = F * (1 + duel);
-    int rpb = 256;
-    int slabs = cdiv(MQ, rpb);
-    if (slabs > h->hb_slabs) {
-      rpb = cdiv(MQ, h->hb_slabs);
-      slabs = cdiv(MQ, rpb);
+    const int col_blocks = cdiv(C, 128);
+    static int occ8 = 0, occ32 = 0, occ8b = 0, hb3 = -1;
+    if (!occ8) {
+      RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ8, rtk::k_heads_bwd_fused<8>, 256, 0));
+      RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ8b, rtk::k_heads_bwd_fused<8, 3>, 256, 0));
+      RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, rtk::k_heads_bwd_fused<32>, 256, 0));
+      const char* e = getenv("RT_HB_OCC3");
+      hb3 = e ? atoi(e) : 0;
     }
-    dim3 grid(cdiv(C, 128), slabs);
+    int occ = A <= 8 ? (hb3 ? occ8b : occ8) : occ32;
+    int slabs = (h->num_sms * (occ > 0 ? occ : 1)) / col_blocks;
+    if (slabs > h->hb_slabs) slabs = h->hb_slabs;
+    if ((size_t)slabs * 32 > MQ) slabs = cdiv(MQ, 32);
+    if (slabs < 1) slabs = 1;
+    int rpb = cdiv(MQ, slabs);
+    slabs = cdiv(MQ, rpb);
+    dim3 grid(col_blocks, slabs);
     float* g_vhb = G + h->o_vhb;
     if (A <= 8) {
-      rtk::k_heads_bwd_fused<8><<<grid, dim3(32, 8), 0, st>>>(
-          h->dtheta, actions, net + h->o_outw, net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, h->hb_part, MQ,
-          F, A, Nq, duel, h->ldh, rpb);
+      if (hb3)
+        rtk::k_heads_bwd_fused<8, 3><<<grid, dim3(32, 8), 0, st>>>(
+            h->dtheta, actions, net + h->o_outw, net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, h->hb_part,
+            h->hb_partb, MQ, F, A, Nq, duel, h->ldh, rpb);
+      else
+        rtk::k_heads_bwd_fused<8><<<grid, dim3(32, 8), 0, st>>>(
+            h->dtheta, actions, net + h->o_outw, net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, h->hb_part,
+            h->hb_partb, MQ, F, A, Nq, duel, h->ldh, rpb);
       RT_LAUNCH_CHECK();
       rtk::k_heads_bwd_final<8><<<cdiv(C, 32) + 1, dim3(32, 8), 0, st>>>(
-          h->hb_part, slabs, h->dtheta, actions, G + h->o_outw, G + h->o_outb, G + h->o_vw, G + h->o_vb,
-          G + h->o_fcb, g_vhb, MQ, F, A, Nq, duel);
+          h->hb_part, h->hb_partb, slabs, G + h->o_outw, G + h->o_outb, G + h->o_vw, G + h->o_vb,
+          G + h->o_fcb, g_vhb, F, A, duel);
     } else {
       rtk::k_heads_bwd_fused<32><<<grid, dim3(32, 8), 0, st>>>(
-          h->dtheta, actions, net + h->o_outw, net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, h->hb_part, MQ,
-          F, A, Nq, duel, h->ldh, rpb);
+          h->dtheta, actions, net + h->o_outw, net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, h->hb_part,
+          h->hb_partb, MQ, F, A, Nq, duel, h->ldh, rpb);
       RT_LAUNCH_CHECK();
       rtk::k_heads_bwd_final<32><<<cdiv(C, 32) + 1, dim3(32, 8), 0, st>>>(
-          h->hb_part, slabs, h->dtheta, actions, G + h->o_outw, G + h->o_outb, G + h->o_vw, G + h->o_vb,
-          G + h->o_fcb, g_vhb, MQ, F, A, Nq, duel);
+          h->hb_part, h->hb_partb, slabs, G + h->o_outw, G + h->o_outb, G + h->o_vw, G + h->o_vb,
+          G + h->o_fcb, g_vhb, F, A, duel);
     }
     RT_LAUNCH_CHECK();
   }
@@ -1333,6 +1377,10 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->row_q, (size_t)h->M, "row_q"));
   RT_TRY(dalloc(h, &h->stats, 8, "stats"));
   RT_CUDA(cudaEventCreateWithFlags(&h->ev_loss, cudaEventDisableTiming));
+  RT_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  RT_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  RT_CUDA(cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking));
+  if (const char* e = getenv("RT_GRAPHS")) h->graphs_enabled = atoi(e);
   RT_CUDA(cudaMallocHost(&h->h_stats, 8 * sizeof(float)));
   RT_TRY(dalloc(h, &h->dadv, MQ * A, "dadv"));
   RT_TRY(dalloc(h, &h->dv, MQ, "dv"));
@@ -1393,6 +1441,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->hw_part, (size_t)h->hw_parts * (A + 1) * F));
   RT_TRY(dalloc(h, &h->hw_partb, (size_t)h->hw_parts * (A + 1)));
   RT_TRY(dalloc(h, &h->hb_part, (size_t)h->hb_slabs * (A + 1) * 2 * F));
+  RT_TRY(dalloc(h, &h->hb_partb, (size_t)h->hb_slabs * 33));
   *out = h;
   return RT_OK;
 }
@@ -1403,6 +1452,13 @@ void rt_learner_destroy(rt_learner* h) {
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
   if (h->ev_loss) cudaEventDestroy(h->ev_loss);
+  for (auto& g : h->graphs) {
+    if (g.fwd) cudaGraphExecDestroy(g.fwd);
+    if (g.bwd) cudaGraphExecDestroy(g.bwd);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->own) cudaStreamDestroy(h->own);
   if (h->h_stats) cudaFreeHost(h->h_stats);
   delete h;
 }
@@ -1498,6 +1554,31 @@ int rt_learner_set_opt_state(rt_learner* h, int64_t adam_steps, double lr) {
 
 namespace {
 
+// Records `body`'s launches on `st` into an executable graph (nothing runs).
+template <class F>
+int capture_graph(cudaStream_t st, F&& body, cudaGraphExec_t* out, long long* launches) {
+  const long long l0 = (long long)rt::launch_counter().load();
+  RT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = body();
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(st, &g);
+  *launches = (long long)rt::launch_counter().load() - l0;
+  rt::launch_counter() -= *launches;   // nothing ran: every replay adds them instead
+  if (rc != RT_OK || e != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    if (rc != RT_OK) return rc;
+    return rt::fail(RT_ERR_CUDA, "stream capture of the update failed: %s", cudaGetErrorString(e));
+  }
+  e = cudaGraphInstantiate(out, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return rt::fail(RT_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  }
+  return RT_OK;
+}
+
 int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
                       const float* const* taus_host, void* stream, bool apply) {
   RT_REQUIRE(h && b && io, "null argument");
@@ -1505,7 +1586,15 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
              "batch geometry (B=%d,S=%d,n=%d) does not match the learner (B=%d,S=%d,n=%d)", b->B,
              b->S, b->n, h->B, h->S, h->n);
   RT_CUDA(cudaSetDevice(h->device));
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t caller = (cudaStream_t)stream;
+  // the update runs on the learner's own stream (graph capture is not possible on the legacy
+  // default stream), forked from and joined back into the caller's stream
+  const bool forked = h->graphs_enabled != 0;
+  cudaStream_t st = forked ? h->own : caller;
+  if (forked) {
+    RT_CUDA(cudaEventRecord(h->ev_fork, caller));
+    RT_CUDA(cudaStreamWaitEvent(st, h->ev_fork, 0));
+  }
   const int B = h->B, T = h->T, P = h->P, n = h->n, U = h->U, M = h->M, Nq = h->Nq;
   const size_t frame = (size_t)h->md.in_c * h->md.in_h * h->md.in_w;
   const uint8_t* all_x = (const uint8_t*)b->all_states[io->field_x];
@@ -1523,154 +1612,221 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   const float* feat = nullptr;
   const int rnn_boot = h->td.rnn_bootstrap ? 1 : 0;
 
-  // ---- burn-in (multi_step_trainer.py:90-131): only the recurrent state is needed, so the
-  // heads the reference also evaluates are skipped.  states / target_states alias one stack,
-  // and the write-back order (online first) is the reference's.
-  if (P > 0) {
-    for (int pass = 0; pass < 1 + rnn_boot; ++pass) {
-      int row0 = pass == 0 ? 0 : n;
-      StateView sv = view(row0);
-      RT_TRY(trunk_forward(h, st, h->p[pass], sv, P * B, P, &feat));
-      StateView dst = view(row0 + P);
-      size_t last = (size_t)(P - 1) * B * U;
-      k_store_state<<<cdiv((size_t)B * U, 256), 256, 0, st>>>(h->h_all + last, h->c_all + last,
-                                                             dst.initials, dst.hx, dst.cx, B, U);
-      RT_LAUNCH_CHECK();
-    }
-  }
-
-  // ---- quantile fractions: injected (parity) or drawn on the device
+  // ---- quantile fractions: injected (parity) or drawn on the device (one launch for the three
+  // segments: target / selection / training pass)
   const float* tau_seg[3];
-  for (int s = 0; s < 3; ++s) {
-    float* dst = h->tau_stage + (size_t)s * h->MQ;
-    tau_seg[s] = dst;
-    if (h->dqn) continue;
-    if (taus_host && taus_host[s]) {
-      RT_CUDA(cudaMemcpyAsync(dst, taus_host[s], (size_t)h->MQ * sizeof(float), cudaMemcpyHostToDevice, st));
-    } else {
-      k_uniform<<<cdiv(h->MQ, 256), 256, 0, st>>>(dst, (size_t)h->MQ, h->td.seed, h->rng_counter);
+  for (int s = 0; s < 3; ++s) tau_seg[s] = h->tau_stage + (size_t)s * h->MQ;
+  if (!h->dqn) {
+    bool any_host = false;
+    for (int s = 0; s < 3; ++s) any_host = any_host || (taus_host && taus_host[s]);
+    if (!any_host) {
+      k_uniform<<<cdiv((size_t)3 * h->MQ, 256), 256, 0, st>>>(h->tau_stage, (size_t)3 * h->MQ, h->td.seed,
+                                                             h->rng_counter);
       RT_LAUNCH_CHECK();
-      h->rng_counter += (unsigned long long)h->MQ;
+      h->rng_counter += (unsigned long long)3 * h->MQ;
+    } else {
+      for (int s = 0; s < 3; ++s) {
+        float* dst = h->tau_stage + (size_t)s * h->MQ;
+        if (taus_host && taus_host[s]) {
+          RT_CUDA(cudaMemcpyAsync(dst, taus_host[s], (size_t)h->MQ * sizeof(float), cudaMemcpyHostToDevice, st));
+        } else {
+          k_uniform<<<cdiv(h->MQ, 256), 256, 0, st>>>(dst, (size_t)h->MQ, h->td.seed, h->rng_counter);
+          RT_LAUNCH_CHECK();
+          h->rng_counter += (unsigned long long)h->MQ;
+        }
+      }
     }
-    tau_seg[s] = dst;
   }
 
-  // ---- bootstrap target (iqn.py:15-52): target net, then the action-selection net
-  bool shared_cnn = false;
   StateView svt = view(P);
-  const bool merged = U > 0 && rnn_boot && T > 1;
-  if (merged) {
-    // recurrent model with rnn_bootstrap: the target, selection and training recurrences are
-    // independent, so run both CNNs + input-gate GEMMs first and then ALL recurrences in one
-    // launch (20 dependent steps instead of 60).  The online input gates are computed once
-    // over the T+n distinct rows: the selection pass reads rows [n, T+n), training rows [0, T).
-    StateView sv = view(P + n);
-    RT_TRY(cnn_forward(h, st, h->p[1], sv.x, M));
-    RT_TRY(lstm_xgates(h, st, h->p[1], h->c_out.back(), M, h->xg2));
-    SeqDesc seqs[3];
-    int ns = 0;
-    seqs[ns++] = SeqDesc{h->p[1], h->xg2, sv.hx, sv.cx, sv.initials, h->h_all2, 1, false};
-    if (h->td.double_q) {
-      RT_TRY(cnn_forward(h, st, h->p[0], svt.x, M + n * B));
-      RT_TRY(lstm_xgates(h, st, h->p[0], h->c_out.back(), M + n * B, h->xg));
-      seqs[ns++] = SeqDesc{h->p[0], h->xg + (size_t)n * B * 4 * U, sv.hx, sv.cx, sv.initials, h->h_all3, 2, false};
-    } else {
-      RT_TRY(cnn_forward(h, st, h->p[0], svt.x, M));
-      RT_TRY(lstm_xgates(h, st, h->p[0], h->c_out.back(), M, h->xg));
-    }
-    seqs[ns++] = SeqDesc{h->p[0], h->xg, svt.hx, svt.cx, svt.initials, h->h_all, 0, true};
-    RT_TRY(lstm_run(h, st, seqs, ns, T, B));
-    RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[0]));
-    RT_CUDA(cudaMemcpyAsync(h->tq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (h->td.double_q) RT_TRY(heads_forward(h, st, h->p[0], h->h_all3, M, tau_seg[1]));
-    else RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[1]));
-    RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    size_t off = (size_t)P * B;
-    rtk::k_iqn_target<<<cdiv(M, 4), 128, (size_t)4 * Nq * h->A * sizeof(float), st>>>(
-        h->tq, h->sq, b->returns + off, b->target_masks + off, (const long long*)b->nsteps + off,
-        h->targets, M, Nq, h->A, (float)h->td.gamma, h->td.vf_scale_epsilon);
-    RT_LAUNCH_CHECK();
-    feat = h->h_all;
-  } else {
-    StateView sv = view(P + n);
-    int ts = rnn_boot ? T : 1;
-    RT_TRY(trunk_forward(h, st, h->p[1], sv, M, ts, &feat));
-    RT_TRY(heads_forward(h, st, h->p[1], feat, M, tau_seg[0]));
-    RT_CUDA(cudaMemcpyAsync(h->tq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (!h->td.double_q) {
-      // same network, same states: only the quantile fractions differ -> reuse the whole trunk
-      RT_TRY(heads_forward(h, st, h->p[1], feat, M, tau_seg[1]));
-    } else {
-      // online net on target_states = rows [n, T+n) of the stack; the training forward below
-      // needs rows [0, T): run the online CNN ONCE over the T+n distinct rows and let both
-      // passes read their slice (saves (T-n)/(2T) of the online conv work)
-      StateView s0 = view(P);
-      RT_TRY(cnn_forward(h, st, h->p[0], s0.x, M + n * B));
-      shared_cnn = true;
-      const float* f = h->c_out.back() + (size_t)n * B * h->feat;
-      if (U) {
-        RT_TRY(lstm_forward(h, st, h->p[0], f, M, ts, sv.hx, sv.cx, sv.initials));
-        f = h->h_all;
-      }
-      RT_TRY(heads_forward(h, st, h->p[0], f, M, tau_seg[1]));
-    }
-    RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    size_t off = (size_t)P * B;
-    rtk::k_iqn_target<<<cdiv(M, 4), 128, (size_t)4 * Nq * h->A * sizeof(float), st>>>(
-        h->tq, h->sq, b->returns + off, b->target_masks + off, (const long long*)b->nsteps + off,
-        h->targets, M, Nq, h->A, (float)h->td.gamma, h->td.vf_scale_epsilon);
-    RT_LAUNCH_CHECK();
-
-    // ---- training forward (iqn.py:54-129)
-    if (shared_cnn) {
-      feat = h->c_out.back();
-      if (U) {
-        RT_TRY(lstm_forward(h, st, h->p[0], feat, M, T, svt.hx, svt.cx, svt.initials));
-        feat = h->h_all;
-      }
-    } else {
-      RT_TRY(trunk_forward(h, st, h->p[0], svt, M, T, &feat));
-    }
-  }
-  // ---- training heads + loss (iqn.py:54-129)
-  RT_TRY(heads_forward(h, st, h->p[0], feat, M, tau_seg[2]));
-  RT_CUDA(cudaMemcpyAsync(h->tau, tau_seg[2], (size_t)h->MQ * sizeof(float), cudaMemcpyDeviceToDevice, st));
   const long long* actions = (const long long*)b->policy_outputs[io->po_field_actions] + (size_t)P * B;
   const double* weights = b->importance_weights ? b->importance_weights + (size_t)P * B : nullptr;
-  if (h->dqn) {
-    rtk::k_dqn_loss<<<cdiv(M, 128), 128, 0, st>>>(h->q, h->targets, actions, weights, h->dtheta, h->row_loss,
-                                                 h->report, h->row_q, M, h->A, (float)h->td.huber_kappa,
-                                                 h->td.loss_mse, h->loss_scale);
-    RT_LAUNCH_CHECK();
-    rtk::k_loss_stats<<<1, 256, 0, st>>>(h->row_loss, h->row_q, h->stats, M, h->loss_scale);
-    RT_LAUNCH_CHECK();
-  } else {
-    int threads = ((Nq + 31) / 32) * 32;
-    size_t smem = (3 * (size_t)Nq + 2 * threads) * sizeof(float);
-    rtk::k_iqn_loss<<<M, threads, smem, st>>>(h->q, h->targets, h->tau, actions, weights, h->dtheta,
-                                             h->row_loss, h->report, Nq, h->A,
-                                             (float)h->td.huber_kappa, h->loss_scale);
-    RT_LAUNCH_CHECK();
-    rtk::k_loss_stats<<<1, 256, 0, st>>>(h->row_loss, h->report, h->stats, M, h->loss_scale);
-    RT_LAUNCH_CHECK();
-  }
 
+  // ---- forward phase: burn-in, bootstrap targets, training forward, losses
+  auto forward_phase = [&]() -> int {
+    // ---- burn-in (multi_step_trainer.py:90-131): only the recurrent state is needed, so the
+    // heads the reference also evaluates are skipped.  states / target_states alias one stack,
+    // and the write-back order (online first) is the reference's.
+    if (P > 0) {
+      for (int pass = 0; pass < 1 + rnn_boot; ++pass) {
+        int row0 = pass == 0 ? 0 : n;
+        StateView sv = view(row0);
+        RT_TRY(trunk_forward(h, st, h->p[pass], sv, P * B, P, &feat));
+        StateView dst = view(row0 + P);
+        size_t last = (size_t)(P - 1) * B * U;
+        k_store_state<<<cdiv((size_t)B * U, 256), 256, 0, st>>>(h->h_all + last, h->c_all + last,
+                                                               dst.initials, dst.hx, dst.cx, B, U);
+        RT_LAUNCH_CHECK();
+      }
+    }
+
+    // ---- bootstrap target (iqn.py:15-52): target net, then the action-selection net
+    bool shared_cnn = false;
+    const bool merged = U > 0 && rnn_boot && T > 1;
+    if (merged) {
+      // recurrent model with rnn_bootstrap: the target, selection and training recurrences are
+      // independent, so run both CNNs + input-gate GEMMs first and then ALL recurrences in one
+      // launch (20 dependent steps instead of 60).  The online input gates are computed once
+      // over the T+n distinct rows: the selection pass reads rows [n, T+n), training rows [0, T).
+      StateView sv = view(P + n);
+      RT_TRY(cnn_forward(h, st, h->p[1], sv.x, M));
+      RT_TRY(lstm_xgates(h, st, h->p[1], h->c_out.back(), M, h->xg2));
+      SeqDesc seqs[3];
+      int ns = 0;
+      seqs[ns++] = SeqDesc{h->p[1], h->xg2, sv.hx, sv.cx, sv.initials, h->h_all2, 1, false};
+      if (h->td.double_q) {
+        RT_TRY(cnn_forward(h, st, h->p[0], svt.x, M + n * B));
+        RT_TRY(lstm_xgates(h, st, h->p[0], h->c_out.back(), M + n * B, h->xg));
+        seqs[ns++] = SeqDesc{h->p[0], h->xg + (size_t)n * B * 4 * U, sv.hx, sv.cx, sv.initials, h->h_all3, 2, false};
+      } else {
+        RT_TRY(cnn_forward(h, st, h->p[0], svt.x, M));
+        RT_TRY(lstm_xgates(h, st, h->p[0], h->c_out.back(), M, h->xg));
+      }
+      seqs[ns++] = SeqDesc{h->p[0], h->xg, svt.hx, svt.cx, svt.initials, h->h_all, 0, true};
+      RT_TRY(lstm_run(h, st, seqs, ns, T, B));
+      RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[0]));
+      RT_CUDA(cudaMemcpyAsync(h->tq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (h->td.double_q) RT_TRY(heads_forward(h, st, h->p[0], h->h_all3, M, tau_seg[1]));
+      else RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[1]));
+      RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      size_t off = (size_t)P * B;
+      rtk::k_iqn_target<<<cdiv(M, 4), 128, (size_t)4 * Nq * h->A * sizeof(float), st>>>(
+          h->tq, h->sq, b->returns + off, b->target_masks + off, (const long long*)b->nsteps + off,
+          h->targets, M, Nq, h->A, (float)h->td.gamma, h->td.vf_scale_epsilon);
+      RT_LAUNCH_CHECK();
+      feat = h->h_all;
+    } else {
+      StateView sv = view(P + n);
+      int ts = rnn_boot ? T : 1;
+      RT_TRY(trunk_forward(h, st, h->p[1], sv, M, ts, &feat));
+      RT_TRY(heads_forward(h, st, h->p[1], feat, M, tau_seg[0]));
+      RT_CUDA(cudaMemcpyAsync(h->tq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (!h->td.double_q) {
+        // same network, same states: only the quantile fractions differ -> reuse the whole trunk
+        RT_TRY(heads_forward(h, st, h->p[1], feat, M, tau_seg[1]));
+      } else {
+        // online net on target_states = rows [n, T+n) of the stack; the training forward below
+        // needs rows [0, T): run the online CNN ONCE over the T+n distinct rows and let both
+        // passes read their slice (saves (T-n)/(2T) of the online conv work)
+        StateView s0 = view(P);
+        RT_TRY(cnn_forward(h, st, h->p[0], s0.x, M + n * B));
+        shared_cnn = true;
+        const float* f = h->c_out.back() + (size_t)n * B * h->feat;
+        if (U) {
+          RT_TRY(lstm_forward(h, st, h->p[0], f, M, ts, sv.hx, sv.cx, sv.initials));
+          f = h->h_all;
+        }
+        RT_TRY(heads_forward(h, st, h->p[0], f, M, tau_seg[1]));
+      }
+      RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      size_t off = (size_t)P * B;
+      rtk::k_iqn_target<<<cdiv(M, 4), 128, (size_t)4 * Nq * h->A * sizeof(float), st>>>(
+          h->tq, h->sq, b->returns + off, b->target_masks + off, (const long long*)b->nsteps + off,
+          h->targets, M, Nq, h->A, (float)h->td.gamma, h->td.vf_scale_epsilon);
+      RT_LAUNCH_CHECK();
+
+      // ---- training forward (iqn.py:54-129)
+      if (shared_cnn) {
+        feat = h->c_out.back();
+        if (U) {
+          RT_TRY(lstm_forward(h, st, h->p[0], feat, M, T, svt.hx, svt.cx, svt.initials));
+          feat = h->h_all;
+        }
+      } else {
+        RT_TRY(trunk_forward(h, st, h->p[0], svt, M, T, &feat));
+      }
+    }
+    // ---- training heads + loss (iqn.py:54-129)
+    RT_TRY(heads_forward(h, st, h->p[0], feat, M, tau_seg[2]));
+    RT_CUDA(cudaMemcpyAsync(h->tau, tau_seg[2], (size_t)h->MQ * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (h->dqn) {
+      rtk::k_dqn_loss<<<cdiv(M, 128), 128, 0, st>>>(h->q, h->targets, actions, weights, h->dtheta, h->row_loss,
+                                                   h->report, h->row_q, M, h->A, (float)h->td.huber_kappa,
+                                                   h->td.loss_mse, h->loss_scale);
+      RT_LAUNCH_CHECK();
+      rtk::k_loss_stats<<<1, 256, 0, st>>>(h->row_loss, h->row_q, h->stats, M, h->loss_scale);
+      RT_LAUNCH_CHECK();
+    } else {
+      int threads = ((Nq + 31) / 32) * 32;
+      size_t smem = (3 * (size_t)Nq + 2 * threads) * sizeof(float);
+      rtk::k_iqn_loss<<<M, threads, smem, st>>>(h->q, h->targets, h->tau, actions, weights, h->dtheta,
+                                               h->row_loss, h->report, Nq, h->A,
+                                               (float)h->td.huber_kappa, h->loss_scale);
+      RT_LAUNCH_CHECK();
+      rtk::k_loss_stats<<<1, 256, 0, st>>>(h->row_loss, h->report, h->stats, M, h->loss_scale);
+      RT_LAUNCH_CHECK();
+    }
+
+    return RT_OK;
+  };
+  // ---- backward phase
+  auto backward_phase = [&]() -> int {
+    RT_CUDA(cudaMemsetAsync(h->grad, 0, h->nparams * sizeof(float), st));
+    RT_TRY(heads_backward(h, st, h->p[0], feat, M, actions));
+    float* dlast = h->dfeatq;
+    if (U) {
+      RT_TRY(lstm_backward(h, st, h->p[0], h->c_out.back(), M, T, svt.initials));
+      dlast = h->dfeat;
+    }
+    RT_TRY(cnn_backward(h, st, h->p[0], svt.x, M, dlast));
+
+    return RT_OK;
+  };
+
+  // ---- run: replayed from CUDA graphs once the handle is warm (every lazy allocation / kernel
+  // attribute of these shapes has happened), keyed by the batch's device pointers (the replay
+  // buffer rotates three batch slots)
+  const bool want_graph = forked && h->steps_done >= 2 && !h->gx.profile && !h->lstm_dbg;
+  rt_learner::StepGraphs* sg = nullptr;
+  if (want_graph) {
+    const void* key[10] = {all_x, all_hx, all_cx, all_init, b->returns, b->nsteps, b->target_masks,
+                           b->policy_outputs[io->po_field_actions], b->importance_weights, nullptr};
+    for (auto& g : h->graphs)
+      if (memcmp(g.key, key, sizeof(key)) == 0) sg = &g;
+    if (!sg) {
+      if (h->graphs.size() >= 8) {
+        if (h->graphs[0].fwd) cudaGraphExecDestroy(h->graphs[0].fwd);
+        if (h->graphs[0].bwd) cudaGraphExecDestroy(h->graphs[0].bwd);
+        h->graphs.erase(h->graphs.begin());
+      }
+      rt_learner::StepGraphs ng;
+      memcpy(ng.key, key, sizeof(key));
+      int rc = capture_graph(st, forward_phase, &ng.fwd, &ng.n_fwd);
+      if (rc == RT_OK) rc = capture_graph(st, backward_phase, &ng.bwd, &ng.n_bwd);
+      if (rc != RT_OK) {
+        // capture is an optimisation: fall back to issuing the launches one by one
+        if (ng.fwd) cudaGraphExecDestroy(ng.fwd);
+        if (ng.bwd) cudaGraphExecDestroy(ng.bwd);
+        h->graphs_enabled = -1;   // stay on the own stream, never try again
+        fprintf(stderr, "rltime_b200: CUDA-graph capture of the update disabled: %s\n", rt::last_error().c_str());
+      } else {
+        h->graphs.push_back(ng);
+        sg = &h->graphs.back();
+      }
+    }
+  }
+  if (sg) {
+    RT_CUDA(cudaGraphLaunch(sg->fwd, st));
+    rt::launch_counter() += sg->n_fwd;
+  } else {
+    RT_TRY(forward_phase());
+  }
   // losses, |td| and the loss statistics are final here: the priority write-back and the next
   // draw only depend on this point, not on the backward pass (rt_learner_wait_loss)
   RT_CUDA(cudaEventRecord(h->ev_loss, st));
-
-  // ---- backward
-  RT_CUDA(cudaMemsetAsync(h->grad, 0, h->nparams * sizeof(float), st));
-  RT_TRY(heads_backward(h, st, h->p[0], feat, M, actions));
-  float* dlast = h->dfeatq;
-  if (U) {
-    RT_TRY(lstm_backward(h, st, h->p[0], h->c_out.back(), M, T, svt.initials));
-    dlast = h->dfeat;
+  if (sg) {
+    RT_CUDA(cudaGraphLaunch(sg->bwd, st));
+    rt::launch_counter() += sg->n_bwd;
+  } else {
+    RT_TRY(backward_phase());
   }
-  RT_TRY(cnn_backward(h, st, h->p[0], svt.x, M, dlast));
-
-  if (!apply) return RT_OK;
-  return apply_grads(h, st, 1.0f);
+  h->steps_done++;
+  int rc_apply = apply ? apply_grads(h, st, 1.0f) : RT_OK;
+  if (forked) {
+    RT_CUDA(cudaEventRecord(h->ev_join, st));
+    RT_CUDA(cudaStreamWaitEvent(caller, h->ev_join, 0));
+  }
+  return rc_apply;
 }
 
 }  // namespace

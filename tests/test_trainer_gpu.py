@@ -94,8 +94,9 @@ def test_dqn_trainer_rainbow_style_end_to_end():
 @pytest.mark.gpu
 def test_pipelined_update_loop_is_bit_identical_to_the_serialised_one():
     """The priority write-back / next draw overlap the backward pass (own replay stream +
-    rt_learner_wait_loss): sampled indices, |td| and the trained weights must not change by a bit
-    against the same loop with a full device synchronisation between every call."""
+    rt_learner_wait_loss) and the update is replayed from CUDA graphs: sampled indices, |td| and
+    the trained weights must not change by a bit against the same loop with one-by-one launches and
+    a full device synchronisation between every call."""
     import random
     import torch
     from rltime_b200.history import DevicePrioritizedReplayHistoryBuffer
@@ -105,6 +106,10 @@ def test_pipelined_update_loop_is_bit_identical_to_the_serialised_one():
     dev = torch.device("cuda", 0)
 
     def run(pipelined):
+        import os
+        # the serialised run also issues every launch one by one; the pipelined run replays the
+        # update from CUDA graphs (read at learner construction)
+        os.environ["RT_GRAPHS"] = "1" if pipelined else "0"
         random.seed(5)
         rs = np.random.RandomState(3)
         hist = DevicePrioritizedReplayHistoryBuffer(
@@ -146,7 +151,11 @@ def test_pipelined_update_loop_is_bit_identical_to_the_serialised_one():
         return ([t.cpu().tolist() for t in idx_log], torch.stack(td_log).cpu().numpy(),
                 L.flat(0).cpu().numpy().copy(), hist.tree_sum())
 
-    a, b = run(False), run(True)
+    try:
+        a, b = run(False), run(True)
+    finally:
+        import os
+        os.environ.pop("RT_GRAPHS", None)
     assert a[0] == b[0]
     np.testing.assert_array_equal(a[1], b[1])
     np.testing.assert_array_equal(a[2], b[2])
