@@ -277,6 +277,9 @@ int rt_learner_gemm_time(rt_learner* h, double* total_ms, double* total_flops, i
 /* Per-launch view of the same measurement (call before rt_learner_gemm_time, which resets it):
  * algorithmic flops and device milliseconds of up to `cap` timed launches, in launch order. */
 int rt_learner_gemm_launches(rt_learner* h, int64_t cap, double* flops, double* ms, int64_t* count);
+/* ... and their shapes, 6 ints per launch: kind (0 GEMM, 1 conv forward, 2 conv weight gradient,
+ * 3 conv data gradient), M, N, K, transA, transB. */
+int rt_learner_gemm_shapes(rt_learner* h, int64_t cap, int32_t* shapes6, int64_t* count);
 /* Measurement hook: average device time (CUDA events) of `iters` back-to-back launches of one
  * GEMM shape; force_bn / force_stages (0 = heuristic) select the tcgen05 tile configuration. */
 int rt_gemm_bench(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t transA, int32_t transB,

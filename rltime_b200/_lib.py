@@ -134,6 +134,7 @@ SIGNATURES = {
     "rt_learner_get_opt_state": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "rt_learner_set_opt_state": (C.c_int, [_VP, C.c_int64, C.c_double]),
     "rt_learner_gemm_launches": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP]),
+    "rt_learner_gemm_shapes": (C.c_int, [_VP, C.c_int64, _VP, C.POINTER(C.c_int64)]),
     "rt_gemm_bench": (C.c_int, [C.c_int32] * 9 + [C.POINTER(C.c_double), C.c_int32]),
 }
 

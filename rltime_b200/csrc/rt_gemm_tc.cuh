@@ -142,6 +142,7 @@ struct EpiWarp {
   int n0;                // first column of the tile
   int rows_left;         // M - (row0 + lane/8): row i*4 of this lane is valid iff i*4 < rows_left
   bool fast;             // aligned, full-width tile: 16-byte path without column predicates
+  bool simple;           // fast, and only bias (+ReLU): the short instruction sequence
 };
 
 __device__ __forceinline__ EpiWarp epi_begin(const EpiArgs& e, int lane, int row0, int n0, int bn) {
@@ -158,6 +159,8 @@ __device__ __forceinline__ EpiWarp epi_begin(const EpiArgs& e, int lane, int row
            (e.raw || ((!e.mask || (((e.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.mask) & 15) == 0))) &&
                       (!e.bias || ((reinterpret_cast<uintptr_t>(e.bias) & 15) == 0)) &&
                       (!e.bias2 || ((reinterpret_cast<uintptr_t>(e.bias2) & 15) == 0))));
+  w.simple = w.fast && !e.raw && !e.mask && !e.accumulate && !e.round_tf32 && e.alpha == 1.f && !e.bias2 &&
+             w.rows_left >= 32;
   return w;
 }
 
@@ -175,6 +178,30 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const EpiWarp& 
   __syncwarp();
   const int cg = lane & 7;
   const int n = nb + 4 * cg;
+  if (w.simple) {
+    // ---- bias (+ReLU) only, all 32 rows valid: the epilogue warps are alone on their schedulers,
+    // so the chunk time is the length of this dependent instruction sequence
+    float4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const float4*>(stage + (i * 4 + (lane >> 3)) * 36 + 4 * cg);
+    float* dptr = w.dst + (nb - w.n0);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
+    if (e.relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(dptr + i * w.row_step) =
+            make_float4(fmaxf(t[i].x + b.x, 0.f), fmaxf(t[i].y + b.y, 0.f), fmaxf(t[i].z + b.z, 0.f),
+                        fmaxf(t[i].w + b.w, 0.f));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(dptr + i * w.row_step) =
+            make_float4(t[i].x + b.x, t[i].y + b.y, t[i].z + b.z, t[i].w + b.w);
+    }
+    __syncwarp();
+    return;
+  }
   if (w.fast) {
     // ---- straight-line 16-byte path: loads first (LDS + optional mask / old C), then math, then stores
     float4 t[8];

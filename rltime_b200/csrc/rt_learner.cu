@@ -65,6 +65,7 @@ struct GemmCtx {
   size_t prof_used = 0;
   double prof_flops = 0;
   std::vector<double> prof_fl;          // flops of each timed launch
+  std::vector<int> prof_shape;          // 6 ints per timed launch: kind (0 gemm, 1 conv fwd, 2 conv dW, 3 conv dX), M, N, K, transA, transB
 };
 
 struct ConvL {
@@ -378,7 +379,8 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   while (BN > 32 && (long long)tm * cdiv(g.N, BN) < 74 && (cdiv(g.K, rttc::BLOCK_K) < 64 || tm == 1)) BN >>= 1;
   // wide-N products with plenty of row tiles: 128x256 tiles re-read A half as often (the fc-size
   // GEMMs move ~330 MB through L2 at 128x128 and run at the L2 rate, not the tensor rate)
-  if (BN == 128 && g.N % 256 == 0 && (long long)tm * (g.N / 256) >= cx.num_sms) BN = 256;
+  // (not for short-K products: those are epilogue-bound and balance better over twice as many tiles)
+  if (BN == 128 && g.N % 256 == 0 && (long long)tm * (g.N / 256) >= cx.num_sms && cdiv(g.K, rttc::BLOCK_K) >= 8) BN = 256;
   int stages = BN == 128 ? 3 : 4;
   if (cx.force_bn) BN = cx.force_bn;
   if (cx.force_stages) stages = cx.force_stages;
@@ -387,7 +389,9 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   int num_kb = cdiv(g.K, rttc::BLOCK_K);
   int splits = 1;
   if (tiles < 74 && num_kb >= 64) {
-    splits = (int)((148 + tiles - 1) / tiles);
+    // as many k-slices as fit ONE wave of CTAs (rounding up left a second, nearly empty round)
+    splits = (int)(cx.num_sms / tiles);
+    if (cx.defer_reduce) splits = (int)((cx.num_sms + tiles - 1) / tiles);   // BPTT: tuned with the cell kernel's fold
     if (splits > num_kb / cx.split_min_kb) splits = num_kb / cx.split_min_kb;
     if (splits > 32) splits = 32;
     size_t per = (size_t)g.M * g.N;
@@ -439,12 +443,15 @@ struct ProfScope {   // brackets one GEMM-shaped launch with events when profili
   GemmCtx& cx;
   cudaStream_t st;
   bool on;
-  ProfScope(GemmCtx& c, cudaStream_t s, double flops) : cx(c), st(s) {
+  ProfScope(GemmCtx& c, cudaStream_t s, double flops, int kind = 0, long long M = 0, long long N = 0,
+            long long K = 0, int tA = 0, int tB = 0) : cx(c), st(s) {
     on = cx.profile && cx.prof_used + 2 <= cx.prof_ev.size();
     if (on) {
       cudaEventRecord(cx.prof_ev[cx.prof_used], st);
       cx.prof_flops += flops;
       cx.prof_fl.push_back(flops);
+      const int rec[6] = {kind, (int)M, (int)N, (int)K, tA, tB};
+      cx.prof_shape.insert(cx.prof_shape.end(), rec, rec + 6);
     }
   }
   ~ProfScope() {
@@ -457,7 +464,7 @@ struct ProfScope {   // brackets one GEMM-shaped launch with events when profili
 
 int gemm(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   if (g.M <= 0 || g.N <= 0) return RT_OK;
-  ProfScope ps(cx, st, 2.0 * g.M * g.N * g.K);
+  ProfScope ps(cx, st, 2.0 * g.M * g.N * g.K, 0, g.M, g.N, g.K, g.transA, g.transB);
   if (cx.mode == 1 && tc_eligible(g)) return gemm_tc(cx, st, g);
   return gemm_simt(cx, st, g);
 }
@@ -574,7 +581,7 @@ int conv_forward_tc(rt_learner* h, cudaStream_t st, const float* net, size_t i, 
   const CUtensorMap* tb = nullptr;
   RT_TRY(get_tmap(h->gx, net + L.w, L.K, L.f, L.K, rttc::BLOCK_K, BN, 0, &tb));
   h->gx.tc_launches++;
-  ProfScope ps(h->gx, st, 2.0 * a.M * a.N * a.K);
+  ProfScope ps(h->gx, st, 2.0 * a.M * a.N * a.K, 1, a.M, a.N, a.K);
   const long long tiles = (long long)cdiv(a.M, rttc::BLOCK_M) * cdiv(a.N, BN);
   // measured: for the gather-bound convolutions 2-3 one-tile CTAs per SM beat one persistent
   // CTA (conv1 103 vs 120 us, conv2/3 34 vs 50 us), so the persistent form is opt-in
@@ -628,7 +635,7 @@ int conv_dw_tc(rt_learner* h, cudaStream_t st, size_t i, const void* xin, const 
   RT_TRY(get_tmap(h->gx, dy, L.f, a.P, L.f, 32, rttc::BLOCK_K, 1, &ta));
   dim3 grid(tiles, 1, splits);
   h->gx.tc_launches++;
-  ProfScope ps(h->gx, st, 2.0 * a.P * (double)L.f * L.K);
+  ProfScope ps(h->gx, st, 2.0 * a.P * (double)L.f * L.K, 2, L.f, L.K, a.P);
   if (BN == 32) RT_TRY((launch_convdw_tc<32, 0>(ta, a, grid, st)));
   else if (BN == 64) RT_TRY((launch_convdw_tc<64, 0>(ta, a, grid, st)));
   else RT_TRY((launch_convdw_tc<128, 0>(ta, a, grid, st)));
@@ -683,7 +690,7 @@ int conv_dx_tc(rt_learner* h, cudaStream_t st, const float* net, int i, const fl
   const long long tiles = (long long)L.s * L.s * cdiv(a.Mc, rttc::BLOCK_M);
   const int ctas = (int)(tiles < h->num_sms ? tiles : h->num_sms);
   h->gx.tc_launches++;
-  ProfScope ps(h->gx, st, 2.0 * rows * L.hout * L.wout * (double)L.f * L.K);
+  ProfScope ps(h->gx, st, 2.0 * rows * L.hout * L.wout * (double)L.f * L.K, 3, (long long)rows * L.hin * L.win, L.cin, (long long)L.f * L.k * L.k);
   if (BN == 32) return launch_convdx_tc<32>(tb, a, ctas, st);
   if (BN == 64) return launch_convdx_tc<64>(tb, a, ctas, st);
   return launch_convdx_tc<128>(tb, a, ctas, st);
@@ -2046,6 +2053,7 @@ extern "C" int rt_learner_profile(rt_learner* h, int32_t enable) {
   cx.prof_used = 0;
   cx.prof_flops = 0;
   cx.prof_fl.clear();
+  cx.prof_shape.clear();
   return RT_OK;
 }
 
@@ -2066,6 +2074,18 @@ extern "C" int rt_learner_gemm_time(rt_learner* h, double* total_ms, double* tot
   cx.prof_used = 0;
   cx.prof_flops = 0;
   cx.prof_fl.clear();
+  cx.prof_shape.clear();
+  return RT_OK;
+}
+
+extern "C" int rt_learner_gemm_shapes(rt_learner* h, int64_t cap, int32_t* shapes6, int64_t* count) {
+  RT_REQUIRE(h && shapes6 && count, "null argument");
+  GemmCtx& cx = h->gx;
+  int64_t n = (int64_t)(cx.prof_shape.size() / 6);
+  if (n > cap) n = cap;
+  if (n > (int64_t)(cx.prof_used / 2)) n = (int64_t)(cx.prof_used / 2);
+  for (int64_t i = 0; i < n * 6; ++i) shapes6[i] = cx.prof_shape[i];
+  *count = n;
   return RT_OK;
 }
 

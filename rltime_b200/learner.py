@@ -213,6 +213,13 @@ class DeviceLearner:
                                                       C.byref(n)))
         return list(zip(fl[:n.value].tolist(), ms[:n.value].tolist()))
 
+    def gemm_shapes(self, cap=16384):
+        """[(kind, M, N, K, transA, transB)] of the timed launches, same order as gemm_launches()."""
+        sh = np.zeros((cap, 6), dtype=np.int32)
+        n = C.c_int64()
+        _lib.check(self._lib.rt_learner_gemm_shapes(self._h, cap, sh.ctypes.data, C.byref(n)))
+        return [tuple(int(v) for v in r) for r in sh[:n.value]]
+
     def wait_loss(self, stream_ptr):
         """Makes the CUDA stream `stream_ptr` wait until the |td| / losses of the last enqueued
         step are final (they are before its backward pass)."""
