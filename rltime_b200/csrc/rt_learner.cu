@@ -178,6 +178,17 @@ struct rt_learner {
   long long steps_done = 0;
   cudaStream_t own = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // Two-branch backward pass: the data-gradient chain (heads dX -> BPTT -> conv dX) is the critical
+  // path and most of it is latency-bound (20 dependent BPTT steps on a mostly idle GPU); every
+  // weight / bias gradient hangs off it as a leaf, so those run on a side stream (a parallel branch
+  // of the captured graph) with their own split-K workspace and column-sum scratch.
+  int overlap_bwd = 1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_side[8] = {};
+  int ev_side_next = 0;
+  GemmCtx gx2;
+  float* colsum_part2 = nullptr;
+  bool side_active = false;    // inside a two-branch backward pass
   float* h_stats = nullptr;        // pinned read-back of stats[0..3]
   std::map<std::string, std::pair<void*, long long>> debug;
   std::vector<void*> allocs;
@@ -480,7 +491,8 @@ rtk::GemmArgs mk(const float* A, int lda, int transA, const float* B, int ldb, i
 }
 
 int colsum(rt_learner* h, cudaStream_t st, const float* x, size_t rows, int N, float* out,
-           int accumulate) {
+           int accumulate, float* scratch = nullptr) {
+  float* part = scratch ? scratch : h->colsum_part;
   // enough row slabs to fill the GPU even when N is a single 32-column block
   int col_blocks = cdiv(N, 32);
   int parts = cdiv(592, col_blocks);
@@ -490,9 +502,9 @@ int colsum(rt_learner* h, cudaStream_t st, const float* x, size_t rows, int N, f
   int rpb = cdiv(rows, parts);
   parts = cdiv(rows, rpb);
   dim3 grid(col_blocks, parts);
-  rtk::k_colsum_partial<<<grid, dim3(32, 8), 0, st>>>(x, h->colsum_part, rows, N, rpb);
+  rtk::k_colsum_partial<<<grid, dim3(32, 8), 0, st>>>(x, part, rows, N, rpb);
   RT_LAUNCH_CHECK();
-  rtk::k_colsum_final<<<cdiv(N, 32), dim3(32, 8), 0, st>>>(h->colsum_part, out, parts, N, accumulate, N);
+  rtk::k_colsum_final<<<cdiv(N, 32), dim3(32, 8), 0, st>>>(part, out, parts, N, accumulate, N);
   RT_LAUNCH_CHECK();
   return RT_OK;
 }
@@ -613,11 +625,11 @@ int launch_convdw_tc(const CUtensorMap* ta, const rttc::ConvDwArgs& a, dim3 grid
 }
 
 // Implicit-GEMM weight gradient of conv layer i over all `rows` frames: dW = dy^T . col.
-int conv_dw_tc(rt_learner* h, cudaStream_t st, size_t i, const void* xin, const float* dy, int rows,
+int conv_dw_tc(rt_learner* h, GemmCtx& cx, cudaStream_t st, size_t i, const void* xin, const float* dy, int rows,
                float* dW) {
   const ConvL& L = h->conv[i];
   rttc::ConvDwArgs a;
-  a.in = xin; a.ws = h->gx.ws;
+  a.in = xin; a.ws = cx.ws;
   a.C = L.cin; a.H = L.hin; a.W = L.win; a.KH = L.k; a.S = L.s; a.OH = L.hout; a.OW = L.wout;
   a.P = rows * L.hout * L.wout; a.F = L.f; a.K = L.K;
   a.scale = (float)(1.0 / 255.0);
@@ -627,20 +639,20 @@ int conv_dw_tc(rt_learner* h, cudaStream_t st, size_t i, const void* xin, const 
   int splits = cdiv(296, tiles);
   if (splits > total_kb / 8) splits = total_kb / 8;
   size_t per = (size_t)L.f * L.K;
-  if ((size_t)splits * per > h->gx.ws_floats) splits = (int)(h->gx.ws_floats / per);
+  if ((size_t)splits * per > cx.ws_floats) splits = (int)(cx.ws_floats / per);
   if (splits < 1) splits = 1;
   a.kb_per_split = cdiv(total_kb, splits);
   splits = cdiv(total_kb, a.kb_per_split);
   const CUtensorMap* ta = nullptr;
-  RT_TRY(get_tmap(h->gx, dy, L.f, a.P, L.f, 32, rttc::BLOCK_K, 1, &ta));
+  RT_TRY(get_tmap(cx, dy, L.f, a.P, L.f, 32, rttc::BLOCK_K, 1, &ta));
   dim3 grid(tiles, 1, splits);
-  h->gx.tc_launches++;
-  ProfScope ps(h->gx, st, 2.0 * a.P * (double)L.f * L.K, 2, L.f, L.K, a.P);
+  cx.tc_launches++;
+  ProfScope ps(cx, st, 2.0 * a.P * (double)L.f * L.K, 2, L.f, L.K, a.P);
   if (BN == 32) RT_TRY((launch_convdw_tc<32, 0>(ta, a, grid, st)));
   else if (BN == 64) RT_TRY((launch_convdw_tc<64, 0>(ta, a, grid, st)));
   else RT_TRY((launch_convdw_tc<128, 0>(ta, a, grid, st)));
   rtk::GemmArgs g = mk(nullptr, 0, 0, nullptr, 0, 0, dW, L.K, L.f, L.K, a.P);
-  g.ws = h->gx.ws;
+  g.ws = cx.ws;
   size_t total = (size_t)L.f * L.K;
   rtk::k_splitk_reduce<<<cdiv(total, 32), dim3(32, 8), 0, st>>>(g, splits);
   RT_LAUNCH_CHECK();
@@ -959,6 +971,33 @@ int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float*
   return RT_OK;
 }
 
+// ---- two-branch backward plumbing.  side_begin() makes the side stream wait for everything
+// enqueued on `st` so far and returns the stream / GEMM context / column-sum scratch a leaf (weight
+// or bias gradient) should use; when the second branch is off these are the main ones.
+struct SideCtx {
+  cudaStream_t st;
+  GemmCtx* gx;
+  float* colsum_scratch;
+};
+int side_begin(rt_learner* h, cudaStream_t st, SideCtx* out) {
+  if (!h->side_active) {
+    *out = SideCtx{st, &h->gx, h->colsum_part};
+    return RT_OK;
+  }
+  cudaEvent_t ev = h->ev_side[h->ev_side_next];
+  h->ev_side_next = (h->ev_side_next + 1) % 7;     // [7] is the join event
+  RT_CUDA(cudaEventRecord(ev, st));
+  RT_CUDA(cudaStreamWaitEvent(h->side, ev, 0));
+  *out = SideCtx{h->side, &h->gx2, h->colsum_part2};
+  return RT_OK;
+}
+int side_join(rt_learner* h, cudaStream_t st) {
+  if (!h->side_active) return RT_OK;
+  RT_CUDA(cudaEventRecord(h->ev_side[7], h->side));
+  RT_CUDA(cudaStreamWaitEvent(st, h->ev_side[7], 0));
+  return RT_OK;
+}
+
 int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int M,
                    const long long* actions) {
   int Nq = h->Nq, D = h->D, F = h->F, A = h->A, E = h->E;
@@ -1014,29 +1053,32 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
     }
     RT_LAUNCH_CHECK();
   }
+  // weight gradients of the hidden layers: leaves on the side branch; the data gradient feeds BPTT
+  SideCtx sd;
+  RT_TRY(side_begin(h, st, &sd));
   if (h->fused_hidden) {
-    // [dh1 | dv1] against the stacked [Wfc ; Wvh]: weight gradient, bias gradient and data
-    // gradient of both hidden layers in one GEMM each
+    // [dh1 | dv1] against the stacked [Wfc ; Wvh]: weight gradient and data gradient of both hidden
+    // layers in one GEMM each (bias gradients: k_heads_bwd_final)
     const int F2 = 2 * F;
-    RT_TRY(gemm(h->gx, st, mk(h->dh1, F2, 1, xq, D, 0, G + h->o_fcw, D, F2, D, (int)MQ)));
+    RT_TRY(gemm(*sd.gx, sd.st, mk(h->dh1, F2, 1, xq, D, 0, G + h->o_fcw, D, F2, D, (int)MQ)));
     RT_TRY(gemm(h->gx, st, mk(h->dh1, F2, 0, net + h->o_fcw, D, 0, dxq, D, (int)MQ, D, F2)));
   } else {
-  // FC
-  RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 1, xq, D, 0, G + h->o_fcw, D, F, D, (int)MQ)));
-  RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 0, net + h->o_fcw, D, 0, dxq, D, (int)MQ, D, F)));
-  if (h->dueling) {
-    RT_TRY(gemm(h->gx, st, mk(h->dv1, F, 1, xq, D, 0, G + h->o_vhw, D, F, D, (int)MQ)));
-    rtk::GemmArgs g = mk(h->dv1, F, 0, net + h->o_vhw, D, 0, dxq, D, (int)MQ, D, F);
-    g.accumulate = 1;
-    RT_TRY(gemm(h->gx, st, g));
-  }
+    RT_TRY(gemm(*sd.gx, sd.st, mk(h->dh1, F, 1, xq, D, 0, G + h->o_fcw, D, F, D, (int)MQ)));
+    RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 0, net + h->o_fcw, D, 0, dxq, D, (int)MQ, D, F)));
+    if (h->dueling) {
+      RT_TRY(gemm(*sd.gx, sd.st, mk(h->dv1, F, 1, xq, D, 0, G + h->o_vhw, D, F, D, (int)MQ)));
+      rtk::GemmArgs g = mk(h->dv1, F, 0, net + h->o_vhw, D, 0, dxq, D, (int)MQ, D, F);
+      g.accumulate = 1;
+      RT_TRY(gemm(h->gx, st, g));
+    }
   }
   if (h->dqn) return RT_OK;
   rtk::k_quantile_mul_bwd<<<cdiv((size_t)M * D, 256), 256, 0, st>>>(h->dxq, feat, h->phi, h->dphi,
                                                                    h->dfeatq, M, D, Nq);
   RT_LAUNCH_CHECK();
-  RT_TRY(gemm(h->gx, st, mk(h->dphi, D, 1, h->cf, E, 0, G + h->o_qw, E, D, E, (int)MQ)));
-  RT_TRY(colsum(h, st, h->dphi, MQ, D, G + h->o_qb, 0));
+  RT_TRY(side_begin(h, st, &sd));
+  RT_TRY(gemm(*sd.gx, sd.st, mk(h->dphi, D, 1, h->cf, E, 0, G + h->o_qw, E, D, E, (int)MQ)));
+  RT_TRY(colsum(h, sd.st, h->dphi, MQ, D, G + h->o_qb, 0, sd.colsum_scratch));
   return RT_OK;
 }
 
@@ -1072,11 +1114,14 @@ int lstm_backward(rt_learner* h, cudaStream_t st, const float* net, const float*
       parts = nparts > 1 ? h->gx.ws : h->dh_carry;
     }
   }
-  RT_TRY(gemm(h->gx, st, mk(h->dgates, 4 * U, 1, h->hprev, U, 0, G + h->o_whh, U, 4 * U, U, rows)));
-  RT_TRY(gemm(h->gx, st, mk(h->dgates, 4 * U, 1, feat, h->feat, 0, G + h->o_wih, h->feat, 4 * U, h->feat, rows)));
-  RT_TRY(colsum(h, st, h->dgates, rows, 4 * U, G + h->o_bih, 0));
+  // weight / bias gradients: side branch; the feature gradient continues the critical path
+  SideCtx sd;
+  RT_TRY(side_begin(h, st, &sd));
+  RT_TRY(gemm(*sd.gx, sd.st, mk(h->dgates, 4 * U, 1, h->hprev, U, 0, G + h->o_whh, U, 4 * U, U, rows)));
+  RT_TRY(gemm(*sd.gx, sd.st, mk(h->dgates, 4 * U, 1, feat, h->feat, 0, G + h->o_wih, h->feat, 4 * U, h->feat, rows)));
+  RT_TRY(colsum(h, sd.st, h->dgates, rows, 4 * U, G + h->o_bih, 0, sd.colsum_scratch));
   RT_CUDA(cudaMemcpyAsync(G + h->o_bhh, G + h->o_bih, (size_t)4 * U * sizeof(float),
-                          cudaMemcpyDeviceToDevice, st));
+                          cudaMemcpyDeviceToDevice, sd.st));
   RT_TRY(gemm(h->gx, st, mk(h->dgates, 4 * U, 0, net + h->o_wih, h->feat, 0, h->dfeat, h->feat, rows,
                         h->feat, 4 * U)));
   return RT_OK;
@@ -1106,8 +1151,10 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
         size_t opix = (size_t)L.hout * L.wout;
         float* dy = i == nl - 1 ? dlast : h->d_c[i];
         const void* xin = i == 0 ? (const void*)h->xf : (const void*)h->c_out[i - 1];
-        RT_TRY(conv_dw_tc(h, st, i, xin, dy, rows, G + L.w));
-        RT_TRY(colsum(h, st, dy, (size_t)rows * opix, L.f, G + L.b, 0));
+        SideCtx sd;
+        RT_TRY(side_begin(h, st, &sd));
+        RT_TRY(conv_dw_tc(h, *sd.gx, sd.st, i, xin, dy, rows, G + L.w));
+        RT_TRY(colsum(h, sd.st, dy, (size_t)rows * opix, L.f, G + L.b, 0, sd.colsum_scratch));
         if (i > 0 && conv_dx_tc_eligible(h, i)) {
           RT_TRY(conv_dx_tc(h, st, net, i, dy, rows));
         } else if (i > 0) {
@@ -1388,6 +1435,9 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   RT_CUDA(cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking));
   if (const char* e = getenv("RT_GRAPHS")) h->graphs_enabled = atoi(e);
+  if (const char* e = getenv("RT_OVERLAP_BWD")) h->overlap_bwd = atoi(e);
+  RT_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  for (auto& e : h->ev_side) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   RT_CUDA(cudaMallocHost(&h->h_stats, 8 * sizeof(float)));
   RT_TRY(dalloc(h, &h->dadv, MQ * A, "dadv"));
   RT_TRY(dalloc(h, &h->dv, MQ, "dv"));
@@ -1403,6 +1453,8 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->dfeatq, (size_t)h->M * D, "dfeatq"));
   h->gx.ws_floats = (size_t)64 << 20;  // 256 MiB split-K workspace
   RT_TRY(dalloc(h, &h->gx.ws, h->gx.ws_floats));
+  h->gx2.ws_floats = (size_t)16 << 20;  // 64 MiB: split-K partials of the weight-gradient branch
+  RT_TRY(dalloc(h, &h->gx2.ws, h->gx2.ws_floats));
   h->gx.mode = td->gemm_mode;
   if (const char* e = getenv("RT_TC_BN")) h->gx.force_bn = atoi(e);
   if (const char* e = getenv("RT_TC_STAGES")) h->gx.force_stages = atoi(e);
@@ -1414,6 +1466,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   for (auto& L : h->conv)
     if ((size_t)L.f > maxN) maxN = L.f;
   RT_TRY(dalloc(h, &h->colsum_part, 2048 * maxN));
+  RT_TRY(dalloc(h, &h->colsum_part2, 2048 * maxN));
   RT_TRY(dalloc(h, &h->sumsq_part, 1024));
   RT_REQUIRE(h->A <= 32, "num_actions > 32 not supported by the fused head kernels");
   RT_REQUIRE(h->F % 4 == 0 && h->D % 4 == 0, "fc_size and the quantile-layer width must be multiples of 4");
@@ -1430,6 +1483,10 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     RT_CUDA(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
     h->gx.num_sms = prop.multiProcessorCount;
+    // the weight-gradient branch runs the same GEMM selection with its own workspace
+    h->gx2.mode = h->gx.mode; h->gx2.num_sms = h->gx.num_sms; h->gx2.persistent = h->gx.persistent;
+    h->gx2.force_bn = h->gx.force_bn; h->gx2.force_stages = h->gx.force_stages;
+    h->gx2.round_tf32 = h->gx.round_tf32;
     const char* e = getenv("RT_LSTM_STEPWISE");
     if (e && e[0] == '1') h->lstm_persistent = 0;
     e = getenv("RT_LSTM_TC");
@@ -1466,6 +1523,8 @@ void rt_learner_destroy(rt_learner* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->own) cudaStreamDestroy(h->own);
+  if (h->side) cudaStreamDestroy(h->side);
+  for (auto& e : h->ev_side) if (e) cudaEventDestroy(e);
   if (h->h_stats) cudaFreeHost(h->h_stats);
   delete h;
 }
@@ -1768,6 +1827,8 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   };
   // ---- backward phase
   auto backward_phase = [&]() -> int {
+    h->side_active = h->overlap_bwd && forked && !h->gx.profile;
+    struct Off { rt_learner* h; ~Off() { h->side_active = false; } } off{h};
     RT_CUDA(cudaMemsetAsync(h->grad, 0, h->nparams * sizeof(float), st));
     RT_TRY(heads_backward(h, st, h->p[0], feat, M, actions));
     float* dlast = h->dfeatq;
@@ -1776,8 +1837,7 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       dlast = h->dfeat;
     }
     RT_TRY(cnn_backward(h, st, h->p[0], svt.x, M, dlast));
-
-    return RT_OK;
+    return side_join(h, st);
   };
 
   // ---- run: replayed from CUDA graphs once the handle is warm (every lazy allocation / kernel
