@@ -260,6 +260,12 @@ int rt_learner_td_abs(rt_learner* h, float** out_device);
  * pass and Adam still execute; read_loss does the same wait on `stream`, then reads qloss and
  * td_mean back (pinned) and synchronises `stream` only. */
 int rt_learner_wait_loss(rt_learner* h, void* stream);
+/* Data-parallel overlap: rt_learner_compute_grads finishes the gradients of every non-convolution
+ * parameter (flat range [*first, *first + *count): LSTM, hidden, head and quantile layers, 99 % of
+ * the bytes) before it starts the convolution backward.  This makes `stream` wait for that point
+ * of the last enqueued compute_grads, so their all-reduce can run on `stream` while the
+ * convolution backward still executes.  stream == (void*)-1: only report the range. */
+int rt_learner_wait_late_grads(rt_learner* h, void* stream, int64_t* first, int64_t* count);
 int rt_learner_read_loss(rt_learner* h, float* loss, float* td_mean, void* stream);
 /* qloss, td_mean, grad_norm of the last step (torch/iqn.py:127-129, torch_trainer.py:187-190);
  * synchronises the stream. */

@@ -123,6 +123,7 @@ SIGNATURES = {
     "rt_learner_act": (C.c_int, [_VP, C.c_int32] + [_VP] * 8 + [_VP]),
     "rt_learner_td_abs": (C.c_int, [_VP, C.POINTER(_VP)]),
     "rt_learner_wait_loss": (C.c_int, [_VP, _VP]),
+    "rt_learner_wait_late_grads": (C.c_int, [_VP, _VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "rt_learner_read_loss": (C.c_int, [_VP, C.POINTER(C.c_float), C.POINTER(C.c_float), _VP]),
     "rt_learner_read_stats": (C.c_int, [_VP, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                         C.POINTER(C.c_float), _VP]),

@@ -170,14 +170,16 @@ struct rt_learner {
   // stream, so the update runs on the learner's own stream, forked from / joined to the caller's.
   struct StepGraphs {
     const void* key[10] = {};
-    cudaGraphExec_t fwd = nullptr, bwd = nullptr;
-    long long n_fwd = 0, n_bwd = 0;      // launches each replay stands for (rt_launch_count)
+    cudaGraphExec_t fwd = nullptr, bwd = nullptr, bwd2 = nullptr;
+    long long n_fwd = 0, n_bwd = 0, n_bwd2 = 0;      // launches each replay stands for (rt_launch_count)
   };
   std::vector<StepGraphs> graphs;
   int graphs_enabled = 1;
   long long steps_done = 0;
   cudaStream_t own = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_late = nullptr;    // data-parallel: gradients of every non-conv parameter are final (before the conv backward)
+  size_t conv_param_end = 0;        // flat index where the non-conv parameters start
   // Two-branch backward pass: the data-gradient chain (heads dX -> BPTT -> conv dX) is the critical
   // path and most of it is latency-bound (20 dependent BPTT steps on a mostly idle GPU); every
   // weight / bias gradient hangs off it as a leaf, so those run on a side stream (a parallel branch
@@ -710,15 +712,19 @@ int conv_dx_tc(rt_learner* h, cudaStream_t st, const float* net, int i, const fl
 
 // CNN forward for `rows` frames: frames to fp32 NHWC once, then every layer is an implicit GEMM
 // over NHWC runs (fallback: im2col + GEMM, chunked so the im2col buffers stay L2-resident).
-int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows) {
-  RT_TRY(launch_frames_to_nhwc(st, x, h->xf, rows, h->md.in_c, h->md.in_h, h->md.in_w, (float)(1.0 / 255.0)));
+// `xf_pre`: the frames of this pass already converted (a slice of h->xf written by the caller).
+int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows,
+                const float* xf_pre = nullptr) {
+  if (!xf_pre)
+    RT_TRY(launch_frames_to_nhwc(st, x, h->xf, rows, h->md.in_c, h->md.in_h, h->md.in_w, (float)(1.0 / 255.0)));
+  const float* xf = xf_pre ? xf_pre : h->xf;
   {
     bool all = true;
     for (size_t i = 0; i < h->conv.size(); ++i)
-      all = all && conv_tc_eligible(h, i, i == 0 ? (const void*)h->xf : (const void*)h->c_out[i - 1]);
+      all = all && conv_tc_eligible(h, i, i == 0 ? (const void*)xf : (const void*)h->c_out[i - 1]);
     if (all) {
       for (size_t i = 0; i < h->conv.size(); ++i)
-        RT_TRY(conv_forward_tc(h, st, net, i, i == 0 ? (const void*)h->xf : (const void*)h->c_out[i - 1],
+        RT_TRY(conv_forward_tc(h, st, net, i, i == 0 ? (const void*)xf : (const void*)h->c_out[i - 1],
                                h->c_out[i], rows));
       return RT_OK;
     }
@@ -728,7 +734,7 @@ int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t*
     for (size_t i = 0; i < h->conv.size(); ++i) {
       const ConvL& L = h->conv[i];
       size_t opix = (size_t)L.hout * L.wout;
-      const float* xin = (i == 0 ? h->xf : h->c_out[i - 1]) + (size_t)r0 * L.hin * L.win * L.cin;
+      const float* xin = (i == 0 ? xf : h->c_out[i - 1]) + (size_t)r0 * L.hin * L.win * L.cin;
       RT_TRY(launch_im2col_f32(st, xin, h->col, rc, L));
       float* out = h->c_out[i] + (size_t)r0 * opix * L.f;
       rtk::GemmArgs g = mk(h->col, L.K, 0, net + L.w, L.K, 1, out, L.f, (int)(rc * opix), L.f, L.K);
@@ -1302,6 +1308,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     h->conv.push_back(L);
     c = L.f; hh = L.hout; ww = L.wout;
   }
+  h->conv_param_end = (h->nparams + 63) / 64 * 64;
   h->featC = c; h->featHW = hh * ww; h->feat = c * hh * ww;
   int fc_layer = h->U ? 2 : 1;
   if (h->U) {
@@ -1432,6 +1439,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->stats, 8, "stats"));
   RT_CUDA(cudaEventCreateWithFlags(&h->ev_loss, cudaEventDisableTiming));
   RT_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  RT_CUDA(cudaEventCreateWithFlags(&h->ev_late, cudaEventDisableTiming));
   RT_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   RT_CUDA(cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking));
   if (const char* e = getenv("RT_GRAPHS")) h->graphs_enabled = atoi(e);
@@ -1519,7 +1527,9 @@ void rt_learner_destroy(rt_learner* h) {
   for (auto& g : h->graphs) {
     if (g.fwd) cudaGraphExecDestroy(g.fwd);
     if (g.bwd) cudaGraphExecDestroy(g.bwd);
+    if (g.bwd2) cudaGraphExecDestroy(g.bwd2);
   }
+  if (h->ev_late) cudaEventDestroy(h->ev_late);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->own) cudaStreamDestroy(h->own);
@@ -1735,13 +1745,21 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       // launch (20 dependent steps instead of 60).  The online input gates are computed once
       // over the T+n distinct rows: the selection pass reads rows [n, T+n), training rows [0, T).
       StateView sv = view(P + n);
-      RT_TRY(cnn_forward(h, st, h->p[1], sv.x, M));
+      if (h->td.double_q) {
+        // the target pass (rows [n, T+n)) and the online pass (rows [0, T+n)) read the same frames:
+        // convert them to fp32 NHWC once
+        RT_TRY(launch_frames_to_nhwc(st, svt.x, h->xf, M + n * B, h->md.in_c, h->md.in_h, h->md.in_w,
+                                     (float)(1.0 / 255.0)));
+        RT_TRY(cnn_forward(h, st, h->p[1], sv.x, M, h->xf + (size_t)n * B * frame));
+      } else {
+        RT_TRY(cnn_forward(h, st, h->p[1], sv.x, M));
+      }
       RT_TRY(lstm_xgates(h, st, h->p[1], h->c_out.back(), M, h->xg2));
       SeqDesc seqs[3];
       int ns = 0;
       seqs[ns++] = SeqDesc{h->p[1], h->xg2, sv.hx, sv.cx, sv.initials, h->h_all2, 1, false};
       if (h->td.double_q) {
-        RT_TRY(cnn_forward(h, st, h->p[0], svt.x, M + n * B));
+        RT_TRY(cnn_forward(h, st, h->p[0], svt.x, M + n * B, h->xf));
         RT_TRY(lstm_xgates(h, st, h->p[0], h->c_out.back(), M + n * B, h->xg));
         seqs[ns++] = SeqDesc{h->p[0], h->xg + (size_t)n * B * 4 * U, sv.hx, sv.cx, sv.initials, h->h_all3, 2, false};
       } else {
@@ -1826,19 +1844,24 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
     return RT_OK;
   };
   // ---- backward phase
-  auto backward_phase = [&]() -> int {
+  // part 0: the whole backward pass; 1: heads + LSTM (every non-conv gradient); 2: conv stack.
+  // Data-parallel updates (apply == false) run parts 1 and 2 with an event in between, so the
+  // all-reduce of the non-conv gradients (99 % of the bytes) overlaps the conv backward.
+  auto backward_part = [&](int part) -> int {
     h->side_active = h->overlap_bwd && forked && !h->gx.profile;
     struct Off { rt_learner* h; ~Off() { h->side_active = false; } } off{h};
-    RT_CUDA(cudaMemsetAsync(h->grad, 0, h->nparams * sizeof(float), st));
-    RT_TRY(heads_backward(h, st, h->p[0], feat, M, actions));
-    float* dlast = h->dfeatq;
-    if (U) {
-      RT_TRY(lstm_backward(h, st, h->p[0], h->c_out.back(), M, T, svt.initials));
-      dlast = h->dfeat;
+    if (part != 2) {
+      RT_CUDA(cudaMemsetAsync(h->grad, 0, h->nparams * sizeof(float), st));
+      RT_TRY(heads_backward(h, st, h->p[0], feat, M, actions));
+      if (U) RT_TRY(lstm_backward(h, st, h->p[0], h->c_out.back(), M, T, svt.initials));
     }
-    RT_TRY(cnn_backward(h, st, h->p[0], svt.x, M, dlast));
+    if (part != 1) RT_TRY(cnn_backward(h, st, h->p[0], svt.x, M, U ? h->dfeat : h->dfeatq));
     return side_join(h, st);
   };
+  auto backward_phase = [&]() -> int { return backward_part(0); };
+  auto backward_late = [&]() -> int { return backward_part(1); };
+  auto backward_conv = [&]() -> int { return backward_part(2); };
+  const bool split_bwd = !apply;
 
   // ---- run: replayed from CUDA graphs once the handle is warm (every lazy allocation / kernel
   // attribute of these shapes has happened), keyed by the batch's device pointers (the replay
@@ -1847,23 +1870,28 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   rt_learner::StepGraphs* sg = nullptr;
   if (want_graph) {
     const void* key[10] = {all_x, all_hx, all_cx, all_init, b->returns, b->nsteps, b->target_masks,
-                           b->policy_outputs[io->po_field_actions], b->importance_weights, nullptr};
+                           b->policy_outputs[io->po_field_actions], b->importance_weights,
+                           (const void*)(uintptr_t)(split_bwd ? 1 : 0)};
     for (auto& g : h->graphs)
       if (memcmp(g.key, key, sizeof(key)) == 0) sg = &g;
     if (!sg) {
       if (h->graphs.size() >= 8) {
         if (h->graphs[0].fwd) cudaGraphExecDestroy(h->graphs[0].fwd);
         if (h->graphs[0].bwd) cudaGraphExecDestroy(h->graphs[0].bwd);
+        if (h->graphs[0].bwd2) cudaGraphExecDestroy(h->graphs[0].bwd2);
         h->graphs.erase(h->graphs.begin());
       }
       rt_learner::StepGraphs ng;
       memcpy(ng.key, key, sizeof(key));
       int rc = capture_graph(st, forward_phase, &ng.fwd, &ng.n_fwd);
-      if (rc == RT_OK) rc = capture_graph(st, backward_phase, &ng.bwd, &ng.n_bwd);
+      if (rc == RT_OK && !split_bwd) rc = capture_graph(st, backward_phase, &ng.bwd, &ng.n_bwd);
+      if (rc == RT_OK && split_bwd) rc = capture_graph(st, backward_late, &ng.bwd, &ng.n_bwd);
+      if (rc == RT_OK && split_bwd) rc = capture_graph(st, backward_conv, &ng.bwd2, &ng.n_bwd2);
       if (rc != RT_OK) {
         // capture is an optimisation: fall back to issuing the launches one by one
         if (ng.fwd) cudaGraphExecDestroy(ng.fwd);
         if (ng.bwd) cudaGraphExecDestroy(ng.bwd);
+        if (ng.bwd2) cudaGraphExecDestroy(ng.bwd2);
         h->graphs_enabled = -1;   // stay on the own stream, never try again
         fprintf(stderr, "rltime_b200: CUDA-graph capture of the update disabled: %s\n", rt::last_error().c_str());
       } else {
@@ -1885,7 +1913,16 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
     RT_CUDA(cudaGraphLaunch(sg->bwd, st));
     rt::launch_counter() += sg->n_bwd;
   } else {
-    RT_TRY(backward_phase());
+    RT_TRY(split_bwd ? backward_late() : backward_phase());
+  }
+  if (split_bwd) {
+    RT_CUDA(cudaEventRecord(h->ev_late, st));
+    if (sg) {
+      RT_CUDA(cudaGraphLaunch(sg->bwd2, st));
+      rt::launch_counter() += sg->n_bwd2;
+    } else {
+      RT_TRY(backward_conv());
+    }
   }
   h->steps_done++;
   int rc_apply = apply ? apply_grads(h, st, 1.0f) : RT_OK;
@@ -1956,6 +1993,15 @@ int rt_learner_act(rt_learner* h, int32_t E, const uint8_t* x, const float* hx, 
     RT_CUDA(cudaMemcpyAsync(h_out, h->h_all, (size_t)E * h->U * sizeof(float), cudaMemcpyDeviceToDevice, st));
     RT_CUDA(cudaMemcpyAsync(c_out, h->c_all, (size_t)E * h->U * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
+  return RT_OK;
+}
+
+int rt_learner_wait_late_grads(rt_learner* h, void* stream, int64_t* first, int64_t* count) {
+  RT_REQUIRE(h, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  if (stream != (void*)-1) RT_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->ev_late, 0));
+  if (first) *first = (int64_t)h->conv_param_end;
+  if (count) *count = (int64_t)(h->nparams - h->conv_param_end);
   return RT_OK;
 }
 

@@ -220,6 +220,14 @@ class DeviceLearner:
         _lib.check(self._lib.rt_learner_gemm_shapes(self._h, cap, sh.ctypes.data, C.byref(n)))
         return [tuple(int(v) for v in r) for r in sh[:n.value]]
 
+    def wait_late_grads(self, stream_ptr=None):
+        """(first, count) of the flat gradient range that is final before the conv backward of the
+        last compute_grads(); with a stream pointer, also makes that stream wait for it."""
+        first, count = C.c_int64(), C.c_int64()
+        sp = C.c_void_p(-1) if stream_ptr is None else stream_ptr
+        _lib.check(self._lib.rt_learner_wait_late_grads(self._h, sp, C.byref(first), C.byref(count)))
+        return first.value, count.value
+
     def wait_loss(self, stream_ptr):
         """Makes the CUDA stream `stream_ptr` wait until the |td| / losses of the last enqueued
         step are final (they are before its backward pass)."""

@@ -46,11 +46,32 @@ def allreduce_sum_(flat_grad):
     return flat_grad
 
 
-def data_parallel_step(learner, batch, world_size, taus=None):
-    """compute local gradients -> all-reduce (sum) -> clip + Adam on the mean gradient."""
+_comm_streams = {}
+
+
+def data_parallel_step(learner, batch, world_size, taus=None, overlap=True):
+    """compute local gradients -> all-reduce (sum) -> clip + Adam on the mean gradient.
+
+    The gradient is reduced in two buckets: everything but the conv parameters (final before the
+    conv backward starts, rt_learner_wait_late_grads) on a communication stream while the conv
+    backward still runs, then the small conv bucket on the caller's stream."""
+    import torch
     learner.compute_grads(batch, taus)
     if world_size > 1:
-        allreduce_sum_(learner.flat())
+        g = learner.flat()
+        first, count = learner.wait_late_grads()
+        if overlap and 0 < first < g.numel():
+            import ctypes as C
+            comm = _comm_streams.get(learner.device)
+            if comm is None:
+                comm = _comm_streams[learner.device] = torch.cuda.Stream(learner.device)
+            learner.wait_late_grads(C.c_void_p(comm.cuda_stream))
+            with torch.cuda.stream(comm):
+                allreduce_sum_(g[first:first + count])
+            allreduce_sum_(g[:first])
+            torch.cuda.current_stream(learner.device).wait_stream(comm)
+        else:
+            allreduce_sum_(g)
     learner.apply_grads(1.0 / world_size)
 
 

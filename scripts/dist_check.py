@@ -42,6 +42,25 @@ for step in range(3):
     err = (L.flat() - want).abs().max().item() / (want.abs().max().item() + 1e-12)
     assert err < 1e-5, "all-reduced gradient differs from the sum of local gradients: %g" % err
     L.apply_grads(1.0 / world)
+# overlapped (two-bucket) reduction == single all-reduce, bit for bit
+L2 = DeviceLearner((4, 84, 84), [(32, 8, 4), (64, 4, 2), (64, 3, 1)], U, 128, 6, 8, 64, True, mbatch=B,
+                   nstep_train=T, nstep_target=n, double_q=True, rnn_bootstrap=True, clip_grad=40.0,
+                   device=dev)
+L2.load_training_state(L.training_state())
+for step in range(4):
+    b, keep = batch_from_tensors(
+        torch.randint(0, 255, (S + n, B, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g),
+        torch.randn(S + n, B, U, device=dev, generator=g), torch.randn(S + n, B, U, device=dev, generator=g),
+        torch.zeros(S + n, B, device=dev), torch.randn(S, B, device=dev, generator=g, dtype=torch.float64),
+        torch.full((S, B), n, device=dev, dtype=torch.int64), torch.ones(S, B, device=dev, dtype=torch.float64),
+        torch.randint(0, 6, (S, B), device=dev, generator=g), torch.ones(S, B, device=dev, dtype=torch.float64), n)
+    taus = [torch.rand(T * B * 8, generator=torch.Generator().manual_seed(1000 * step + 10 * rank + k)) for k in range(3)]
+    parallel.data_parallel_step(L, b, world, taus=taus, overlap=True)
+    parallel.data_parallel_step(L2, b, world, taus=taus, overlap=False)
+torch.cuda.synchronize()
+d12 = (L.flat(_lib.RT_BUF_ONLINE) - L2.flat(_lib.RT_BUF_ONLINE)).abs().max().item()
+# two addends commute exactly; with more ranks NCCL's reduction order depends on the message size
+assert d12 == 0.0 if world == 2 else d12 < 1e-6, "overlapped all-reduce changed the weights: %g" % d12
 w = L.flat(_lib.RT_BUF_ONLINE).clone()
 lo, hi = w.clone(), w.clone()
 dist.all_reduce(lo, op=dist.ReduceOp.MIN)
@@ -49,8 +68,8 @@ dist.all_reduce(hi, op=dist.ReduceOp.MAX)
 diff = (hi - lo).abs().max().item()
 st = L.stats()
 if rank == 0:
-    print("dist_check world=%d: replicas identical (max spread %g), grad-sum rel err %.2e, qloss %.5f grad_norm %.5f"
-          % (world, diff, err, st["qloss"], st["grad_norm"]))
+    print("dist_check world=%d: replicas identical (max spread %g), grad-sum rel err %.2e, overlapped == plain "
+          "all-reduce (max diff %g), qloss %.5f grad_norm %.5f" % (world, diff, err, d12, st["qloss"], st["grad_norm"]))
 assert diff == 0.0, "replicas diverged: %g" % diff
 dist.barrier()
 dist.destroy_process_group()
