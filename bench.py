@@ -210,7 +210,6 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         one_update(hist, learner, B, world)
     barrier()
-    hist.profile_gather(True)
     launches0 = lib.rt_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
@@ -222,8 +221,6 @@ def run_gpu(args):
     ms = ev0.elapsed_time(ev1)
     launches = lib.rt_launch_count() - launches0
     stats = learner.stats()
-    gather_ms_total, gather_n = hist.gather_time()     # CUDA events around k_gather, live
-    hist.profile_gather(False)
 
     # GEMM-shaped launches, live (extra profiled steps AFTER the timed region: the event pairs
     # around ~190 launches per update perturb the step slightly, so they stay out of `value`)
@@ -249,12 +246,19 @@ def run_gpu(args):
     reps = 50
     for _ in range(5):
         hist.get_train_data(B, 0.0)
+    torch.cuda.synchronize(device)
+    # the gather kernel timed alone (inside an update it shares the GPU with the previous update's
+    # backward pass): CUDA events around each launch on the replay stream, one draw at a time
+    hist.profile_gather(True)
     g0.record()
     for _ in range(reps):
         hist.get_train_data(B, 0.0)
+        torch.cuda.synchronize(device)
     g1.record()
     torch.cuda.synchronize(device)
     draw_ms = g0.elapsed_time(g1) / reps
+    gather_ms_total, gather_n = hist.gather_time()
+    hist.profile_gather(False)
 
     # end to end through the public API with host buffers
     E = cfg["envs"]
@@ -332,7 +336,7 @@ def run_gpu(args):
                      "traffic": None, "launches_timed": int(gemm_n), "profiled_steps": prof_steps,
                      "gflop_per_update": gemm_flops / prof_steps / 1e9,
                      "gemm_ms_per_update": gemm_ms / prof_steps},
-        "roofline_gather": {"kernel": "k_gather", "bound": "hbm",
+        "roofline_gather": {"kernel": "k_gather_bulk (cp.async.bulk global->shared->global ring), timed alone", "bound": "hbm",
                      "achieved": gather_bytes / (gather_ms_total / max(gather_n, 1) * 1e-3) / 1e9,
                      "peak": hbm, "peak_source": which, "unit": "GB/s",
                      "frac": gather_bytes / (gather_ms_total / max(gather_n, 1) * 1e-3) / 1e9 / hbm,

@@ -309,6 +309,149 @@ __global__ void __launch_bounds__(RT_GATHER_THREADS) k_gather(const __grid_const
   }
 }
 
+
+// ---- bulk-copy gather (TMA engine, no tensor map): global -> shared -> global
+// Every field whose item size is a multiple of 16 bytes (frames 28,224 B, hx / cx 2,048 B) moves
+// in chunks of <= GB_CHUNK bytes through a ring of GB_STAGES shared-memory stages: one
+// cp.async.bulk per chunk into a stage (mbarrier complete_tx), one cp.async.bulk out of it
+// (bulk_group).  Warp 0 drives the ring: its lanes resolve 32 chunk descriptors at a time in
+// parallel (row -> slot is a dependent global load), lane 0 issues the copies; GB_LOOK loads stay in
+// flight per CTA.  The other warps move the fields that are not 16-byte multiples (initials,
+// actions, q-values: a few KB in total) with plain loads and stores.  Chunks are dealt round-robin
+// to the CTAs, so with 4 chunks per frame the per-CTA load differs by one chunk at most.
+#define GB_THREADS 128
+
+__device__ __forceinline__ uint32_t gb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct BulkParams {
+  GatherField f[2 * RT_MAX_FIELDS];  // bulk-eligible fields; chunks_per_row in units of the kernel's chunk size
+  int num_fields;
+  long long total_items;
+  GatherField s[2 * RT_MAX_FIELDS];  // the other fields: one plain-copy item per (field, row)
+  int num_small;
+  long long small_items;
+};
+
+template <int GB_CHUNK, int GB_STAGES, int GB_LOOK>
+__global__ void __launch_bounds__(GB_THREADS) k_gather_bulk(const __grid_constant__ BulkParams p) {
+  extern __shared__ __align__(128) uint8_t gb_smem[];
+  __shared__ __align__(8) uint64_t bars[GB_STAGES];
+  __shared__ uint8_t* st_dst[GB_STAGES];
+  __shared__ uint32_t st_bytes[GB_STAGES];
+  __shared__ uint32_t st_armed[GB_STAGES];   // loads armed on this stage so far (phase parity of the next wait)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GB_STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gb_smem_u32(&bars[s])), "r"(1));
+      st_armed[s] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // local items of this CTA: global item = blockIdx.x + local * gridDim.x
+    const long long n = p.total_items > (long long)blockIdx.x
+                            ? (p.total_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint8_t* d_src = nullptr;   // descriptor of local item (32-block base + lane)
+    uint8_t* d_dst = nullptr;
+    uint32_t d_bytes = 0;
+    for (long long it = 0; it < n + GB_LOOK; ++it) {
+      if (it < n) {
+        if ((it & 31) == 0) {
+          const long long li = it + lane;
+          d_bytes = 0;
+          if (li < n) {
+            const long long item = blockIdx.x + li * (long long)gridDim.x;
+            int fi = 0;
+            while (fi + 1 < p.num_fields && item >= p.f[fi + 1].first_item) ++fi;
+            const GatherField& f = p.f[fi];
+            const long long local = item - f.first_item;
+            const int row = (int)(local / f.chunks_per_row);
+            const int chunk = (int)(local - (long long)row * f.chunks_per_row);
+            if (!(row >= f.row_lo && row < f.row_hi)) {
+              const long long off = (long long)chunk * GB_CHUNK;
+              long long len = f.nb - off;
+              if (len > GB_CHUNK) len = GB_CHUNK;
+              d_src = f.src + (long long)f.slots[row] * f.nb + off;
+              d_dst = f.dst + (long long)row * f.nb + off;
+              d_bytes = (uint32_t)len;
+            }
+          }
+        }
+        const int sl = (int)(it & 31);
+        const uint8_t* src = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)d_src, sl);
+        uint8_t* dst = (uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)d_dst, sl);
+        const uint32_t bytes = __shfl_sync(0xffffffffu, d_bytes, sl);
+        if (lane == 0) {
+          const int s = (int)(it % GB_STAGES);
+          // the store that last read this stage was committed GB_STAGES - GB_LOOK iterations ago:
+          // all but the newest GB_STAGES - GB_LOOK - 1 groups must have finished reading
+          if (it >= GB_STAGES)
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(GB_STAGES - GB_LOOK - 1) : "memory");
+          st_dst[s] = dst;
+          st_bytes[s] = bytes;
+          if (bytes) {
+            st_armed[s]++;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gb_smem_u32(&bars[s])),
+                         "r"(bytes)
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    gb_smem_u32(gb_smem + (size_t)s * GB_CHUNK)),
+                "l"(src), "r"(bytes), "r"(gb_smem_u32(&bars[s]))
+                : "memory");
+          }
+        }
+      }
+      const long long j = it - GB_LOOK;
+      if (lane == 0 && j >= 0 && j < n) {
+        const int s = (int)(j % GB_STAGES);
+        const uint32_t bytes = st_bytes[s];
+        if (bytes) {
+          // wait for the landed bytes: phase parity = number of earlier loads armed on this stage
+          // (skipped rows never arm it)
+          const uint32_t parity = (st_armed[s] - 1) & 1;
+          uint32_t ok = 0;
+          while (!ok) {
+            asm volatile(
+                "{\n\t.reg .pred q;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, q;\n\t}"
+                : "=r"(ok)
+                : "r"(gb_smem_u32(&bars[s])), "r"(parity)
+                : "memory");
+          }
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(st_dst[s]),
+                       "r"(gb_smem_u32(gb_smem + (size_t)s * GB_CHUNK)), "r"(bytes)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else {
+    // plain path for the small fields: one warp per (field, row) item, byte loop
+    const long long w = (long long)blockIdx.x * (GB_THREADS / 32 - 1) + (warp - 1);
+    const long long nw = (long long)gridDim.x * (GB_THREADS / 32 - 1);
+    for (long long item = w; item < p.small_items; item += nw) {
+      int fi = 0;
+      while (fi + 1 < p.num_small && item >= p.s[fi + 1].first_item) ++fi;
+      const GatherField& f = p.s[fi];
+      const int row = (int)(item - f.first_item);
+      if (row >= f.row_lo && row < f.row_hi) continue;
+      const uint8_t* src = f.src + (long long)f.slots[row] * f.nb;
+      uint8_t* dst = f.dst + (long long)row * f.nb;
+      if ((f.nb & 3) == 0) {
+        for (int i = lane; i < (int)(f.nb >> 2); i += 32)
+          reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+      } else {
+        for (int i = lane; i < (int)f.nb; i += 32) dst[i] = src[i];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------- host-side numerics
 
 // numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum_DOUBLE),
@@ -520,6 +663,9 @@ struct rt_replay {
   // packed pinned upload stages (one H2D copy per flush)
   Stage stage[RT_STAGES];
   int stage_cur = 0;
+  int gather_bulk = 1;                // bulk-copy (TMA) gather; 0 = register-staged k_gather (RT_GATHER_BULK)
+  int gather_cfg = 0, gather_cps = 3;  // ring geometry / CTAs per SM of the bulk gather (RT_GB_CFG, RT_GB_CPS)
+  int num_sms = 148;
   // optional live timing of the gather kernel (bench.py roofline)
   bool profile = false;
   std::vector<cudaEvent_t> prof_ev;   // pairs (start, stop)
@@ -766,10 +912,59 @@ int assemble_and_gather(rt_replay* h, BatchSlot& bs, int B, cudaStream_t st) {
   gp.num_fields = nf;
   gp.total_items = items;
   if (items > 0) {
-    long long grid = items < 148LL * 16 ? items : 148LL * 16;
     bool timed = h->profile && h->prof_used + 2 <= h->prof_ev.size();
     if (timed) RT_CUDA(cudaEventRecord(h->prof_ev[h->prof_used], st));
-    k_gather<4><<<(int)grid, RT_GATHER_THREADS, 0, st>>>(gp);
+    if (h->gather_bulk) {
+      // split the fields: 16-byte multiples go through the bulk-copy ring, the rest the plain path
+      static const int cfgs[4][3] = {{8192, 8, 6}, {16384, 6, 4}, {4096, 16, 12}, {32768, 4, 2}};
+      const int* cf = cfgs[h->gather_cfg & 3];
+      const int chunk_bytes = cf[0];
+      BulkParams bp;
+      memset(&bp, 0, sizeof(bp));
+      long long bi = 0, si = 0;
+      for (int f = 0; f < nf; ++f) {
+        const GatherField& g = gp.f[f];
+        if ((g.nb & 15) == 0 && g.nb >= 256) {
+          GatherField& d = bp.f[bp.num_fields++];
+          d = g;
+          d.chunks_per_row = (int)((g.nb + chunk_bytes - 1) / chunk_bytes);
+          d.first_item = bi;
+          bi += (long long)d.rows * d.chunks_per_row;
+        } else {
+          GatherField& d = bp.s[bp.num_small++];
+          d = g;
+          d.chunks_per_row = 1;
+          d.first_item = si;
+          si += d.rows;
+        }
+      }
+      bp.total_items = bi;
+      bp.small_items = si;
+      long long grid = (long long)h->num_sms * h->gather_cps;
+      long long want = bi > si ? bi : si;
+      if (want < grid) grid = want < 1 ? 1 : want;
+      const int smem = cf[0] * cf[1];
+#define RT_GB_LAUNCH(C, S, L)                                                                         \
+  {                                                                                                   \
+    static bool configured = false;                                                                   \
+    if (!configured) {                                                                                \
+      RT_CUDA(cudaFuncSetAttribute(k_gather_bulk<C, S, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   smem));                                                            \
+      configured = true;                                                                              \
+    }                                                                                                 \
+    k_gather_bulk<C, S, L><<<(int)grid, GB_THREADS, smem, st>>>(bp);                                  \
+  }
+      switch (h->gather_cfg & 3) {
+        case 0: RT_GB_LAUNCH(8192, 8, 6) break;
+        case 1: RT_GB_LAUNCH(16384, 6, 4) break;
+        case 2: RT_GB_LAUNCH(4096, 16, 12) break;
+        default: RT_GB_LAUNCH(32768, 4, 2) break;
+      }
+#undef RT_GB_LAUNCH
+    } else {
+      long long grid = items < 148LL * 16 ? items : 148LL * 16;
+      k_gather<4><<<(int)grid, RT_GATHER_THREADS, 0, st>>>(gp);
+    }
     RT_LAUNCH_CHECK();
     if (timed) {
       RT_CUDA(cudaEventRecord(h->prof_ev[h->prof_used + 1], st));
@@ -800,6 +995,14 @@ int rt_replay_create(const rt_replay_config* c, rt_replay** out) {
   RT_CUDA(cudaSetDevice(c->device));
   rt_replay* h = new rt_replay();
   h->cfg = *c;
+  {
+    cudaDeviceProp prop;
+    RT_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    h->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("RT_GATHER_BULK")) h->gather_bulk = atoi(e);
+    if (const char* e = getenv("RT_GB_CFG")) h->gather_cfg = atoi(e);
+    if (const char* e = getenv("RT_GB_CPS")) h->gather_cps = atoi(e) > 0 ? atoi(e) : 1;
+  }
   h->N = c->size;
   h->NS = c->size + c->max_envs;
   h->T = c->nstep_train; h->P = c->prefix_steps; h->n = c->nstep_target;
