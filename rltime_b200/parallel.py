@@ -56,6 +56,8 @@ def data_parallel_step(learner, batch, world_size, taus=None, overlap=True):
     conv backward starts, rt_learner_wait_late_grads) on a communication stream while the conv
     backward still runs, then the small conv bucket on the caller's stream."""
     import torch
+    if os.environ.get("RT_DP_OVERLAP") == "0":
+        overlap = False
     learner.compute_grads(batch, taus)
     if world_size > 1:
         g = learner.flat()
