@@ -25,6 +25,10 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;   // floats = 128 bytes
 constexpr int UMMA_K = 8;     // tf32
 constexpr int NUM_THREADS = 192;
+// persistent GEMM: 8 epilogue warps (two per TMEM lane quarter, alternating 32-column chunks): an
+// epilogue warp is alone on its scheduler and latency-bound, so the drain time halves
+constexpr int P_EPI_WARPS = 8;
+constexpr int NUM_THREADS_P = 64 + 32 * P_EPI_WARPS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -466,13 +470,13 @@ struct SmemLayoutP {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
   static constexpr int B_BYTES = BN * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SCRATCH_OFFSET = STAGES * STAGE_BYTES;          // 4 warps x 32 x 36 floats
-  static constexpr int BAR_OFFSET = SCRATCH_OFFSET + 4 * 32 * 36 * 4;
+  static constexpr int SCRATCH_OFFSET = STAGES * STAGE_BYTES;          // P_EPI_WARPS x 32 x 36 floats
+  static constexpr int BAR_OFFSET = SCRATCH_OFFSET + P_EPI_WARPS * 32 * 36 * 4;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
 template <int BN, int A_MN, int B_MN, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS)
+__global__ void __launch_bounds__(NUM_THREADS_P)
 k_gemm_tc_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ TcArgs a) {
   using L = SmemLayoutP<BN, A_MN, B_MN, STAGES>;
@@ -499,7 +503,7 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);     // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], P_EPI_WARPS);     // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -596,8 +600,9 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    const int q = warp & 3;
-    float* stage = reinterpret_cast<float*>(smem + L::SCRATCH_OFFSET) + q * (32 * 36);
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;       // which of the quarter's two warps: chunk parity
+    float* stage = reinterpret_cast<float*>(smem + L::SCRATCH_OFFSET) + (warp - 2) * (32 * 36);
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       int mb, nb, z;
@@ -614,11 +619,21 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const EpiWarp ew = epi_begin(e, lane, m0 + q * 32, n0, BN);
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      constexpr int CHUNKS = BN / 32;
+      constexpr int CSTEP = CHUNKS >= 2 ? 2 : 1;      // BN = 32: both warps would own the one chunk
+      const int c_first = CHUNKS >= 2 ? half : 0;
+      const int c_last = CHUNKS >= 2 ? CHUNKS - 2 + half : 0;
+      if (CHUNKS < 2 && half == 1) {
+        // nothing to drain: still hand the accumulator back
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
+        continue;
+      }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_first; c < CHUNKS; c += CSTEP) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-        if (c == BN / 32 - 1) {
+        if (c == c_last) {
           // every column of this accumulator is now in registers: hand it back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();

@@ -350,7 +350,7 @@ int launch_tc_p(const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs
     RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  kern<<<ctas, rttc::NUM_THREADS, L::TOTAL, st>>>(*ta, *tb, a);
+  kern<<<ctas, rttc::NUM_THREADS_P, L::TOTAL, st>>>(*ta, *tb, a);
   RT_LAUNCH_CHECK();
   return RT_OK;
 }
