@@ -68,7 +68,7 @@ class ClockSampler:
                 self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._th = threading.Thread(target=self._run, daemon=True)
@@ -91,29 +91,30 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def dominant_roofline(cfg, fl, ms_total, n, family_ms, prof_steps, tf32_peak, which):
+def dominant_roofline(shape, fl, ms_total, n, family_ms, prof_steps, tf32_peak, which):
     """roofline object of the single GEMM shape that takes the most device time per update."""
-    M, Nq = cfg["B"] * cfg["T"], cfg["Nq"]
-    MQ, U, F = M * Nq, cfg["units"], cfg["fc"]
-    known = {
-        2 * MQ * 2 * F * U: ("k_gemm_tc_p<256,0,0,3>: fused advantage+value hidden layer forward "
-                             "[%d x %d] = [%d x %d] . W^T" % (MQ, 2 * F, MQ, U), "%dx%dx%d" % (MQ, 2 * F, U)),
-        2 * MQ * U * 2 * F: ("hidden-layer data / weight gradient GEMM (%d x %d x %d)" % (MQ, U, 2 * F),
-                             "%dx%dx%d" % (MQ, U, 2 * F)),
-    }
-    name, key = known.get(fl, ("GEMM-shaped launch of %.3f GFLOP" % (fl / 1e9), "%d" % fl))
+    kind, M, N, K, tA, tB = shape
+    kinds = {0: "GEMM", 1: "implicit-GEMM conv forward", 2: "implicit-GEMM conv weight gradient",
+             3: "implicit-GEMM conv data gradient"}
+    key = "%dx%dx%d" % (M, N, K)
+    name = "tcgen05 TF32 %s [%d x %d] = [%d x %d] . [%d x %d] (A %s, B %s)" % (
+        kinds.get(kind, "GEMM"), M, N, M, K, K, N, "MN-major" if tA else "K-major",
+        "K-major" if tB else "MN-major")
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(key)
     achieved = fl * n / (ms_total * 1e-3) / 1e12 if ms_total > 0 else None
-    return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+    return {"kernel": name, "shape": key, "bound": "tensor", "achieved": achieved, "peak": tf32_peak,
+            "unit": "TFLOP/s",
             "peak_source": which + " cuBLAS bf16 sustained / 2 (TF32 multiplies at half the bf16 rate)",
             "frac": achieved / tf32_peak if achieved else None, "traffic": traffic,
             "algorithmic_flops_per_launch": fl, "launches_timed": int(n),
             "us_per_launch": 1e3 * ms_total / max(n, 1),
             "share_of_gemm_time": ms_total / family_ms if family_ms > 0 else None,
-            "ms_per_update": ms_total / prof_steps}
+            "ms_per_update": ms_total / prof_steps,
+            "timing": "CUDA events around each launch, launches issued one by one on a single stream "
+                      "(the timed region replays the same kernels from CUDA graphs)"}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -212,12 +213,15 @@ def run_gpu(args):
     barrier()
     launches0 = lib.rt_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        ev0.record()
-        for _ in range(args.steps):
-            one_update(hist, learner, B, world)
-        ev1.record()
-        barrier()
+    # clocks / throttle reasons are sampled from the start of the timed region to the end of the
+    # end-to-end loop (every phase in between keeps the GPU under the same load)
+    clk = ClockSampler(local)
+    clk.__enter__()
+    ev0.record()
+    for _ in range(args.steps):
+        one_update(hist, learner, B, world)
+    ev1.record()
+    barrier()
     ms = ev0.elapsed_time(ev1)
     launches = lib.rt_launch_count() - launches0
     stats = learner.stats()
@@ -229,16 +233,17 @@ def run_gpu(args):
     for _ in range(prof_steps):
         one_update(hist, learner, B, world)
     per_launch = learner.gemm_launches()
+    shapes = learner.gemm_shapes()
     gemm_ms, gemm_flops, gemm_n = learner.gemm_time()
     learner.profile_gemms(False)
-    # dominant kernel = the GEMM shape (identified by its algorithmic flops) with the largest
-    # summed device time over the profiled steps
+    # dominant kernel = the GEMM shape with the largest summed device time over the profiled steps
     groups = {}
-    for fl, t in per_launch:
-        gsum = groups.setdefault(round(fl), [0.0, 0])
+    for (fl, t), sh in zip(per_launch, shapes):
+        gsum = groups.setdefault(sh, [0.0, 0, fl])
         gsum[0] += t
         gsum[1] += 1
-    top_fl, (top_ms, top_n) = max(groups.items(), key=lambda kv: kv[1][0]) if groups else (0, (0.0, 0))
+    top_shape, (top_ms, top_n, top_fl) = max(groups.items(), key=lambda kv: kv[1][0]) if groups \
+        else ((0, 0, 0, 0, 0, 0), (0.0, 0, 0.0))
 
     # gather kernel alone (roofline): time draws without the learner
     torch.cuda.synchronize(device)
@@ -292,6 +297,7 @@ def run_gpu(args):
         e2e_update()
     barrier()
     e2e_s = time.perf_counter() - t0
+    clk.__exit__()
 
     vals = torch.tensor([ms, e2e_s], dtype=torch.float64, device=device)
     if world > 1:
@@ -320,13 +326,15 @@ def run_gpu(args):
                                "nature-CNN-LSTM512-FC512 dueling double-Q" % cfg["size"],
                    "gemm": cfg["gemm"], "replay_per_gpu": cfg["size"],
                    "global_batch": "%d sequences x 20 steps" % (B * world),
-                   "parallelism": "dp%d: replay sharded by env, NCCL all-reduce of the flat gradient" % world, "l2": "inputs (28 GB frame store) exceed L2; "
+                   "parallelism": "dp%d: replay sharded by env, NCCL all-reduce of the flat gradient" % world, "schedule": "update replayed from CUDA graphs; replay on its own stream (priority write-back, next "
+                               "draw and gather overlap the backward pass); weight gradients on a second graph branch",
+                   "l2": "inputs (28 GB frame store) exceed L2; "
                    "every draw gathers different rows", "fill_s": round(fill_s, 1)},
         "e2e": {"value": world * args.steps / e2e_s, "unit": "updates/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
-        "roofline": dominant_roofline(cfg, top_fl, top_ms, top_n, gemm_ms, prof_steps, tf32_peak, which),
+        "roofline": dominant_roofline(top_shape, top_fl, top_ms, top_n, gemm_ms, prof_steps, tf32_peak, which),
         "roofline_gemm_family": {"kernel": "tcgen05 GEMM family (k_gemm_tc_p / k_gemm_tc / k_conv_tc_p / k_convdw_tc / "
                                "k_convdx_tc): all GEMM-shaped launches of the update", "bound": "tensor",
                      "achieved": gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,

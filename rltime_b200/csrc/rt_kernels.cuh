@@ -739,8 +739,8 @@ __global__ void __launch_bounds__(256) k_heads_out(const float* __restrict__ h1,
 //     part[slab][A][c]  = sum_r dh1|dv1[r,c]               (bias gradient of the hidden layers)
 // k_heads_bwd_final folds the slabs in a fixed order.  Grid (ceil(C/128), slabs), block (32, 8);
 // a thread owns 4 consecutive columns; warps stride the slab's rows.
-template <int MAXA, int MINB = 1>
-__global__ void __launch_bounds__(256, MINB) k_heads_bwd_fused(
+template <int MAXA>
+__global__ void __launch_bounds__(256) k_heads_bwd_fused(
     const float* __restrict__ dtheta, const long long* __restrict__ actions,
     const float* __restrict__ Wout, const float* __restrict__ Wv, const float* __restrict__ h1,
     const float* __restrict__ v1, float* __restrict__ dh1, float* __restrict__ dv1,

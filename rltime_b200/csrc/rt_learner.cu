@@ -1018,15 +1018,12 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
   {
     const int C = F * (1 + duel);
     const int col_blocks = cdiv(C, 128);
-    static int occ8 = 0, occ32 = 0, occ8b = 0, hb3 = -1;
+    static int occ8 = 0, occ32 = 0;
     if (!occ8) {
       RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ8, rtk::k_heads_bwd_fused<8>, 256, 0));
-      RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ8b, rtk::k_heads_bwd_fused<8, 3>, 256, 0));
       RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, rtk::k_heads_bwd_fused<32>, 256, 0));
-      const char* e = getenv("RT_HB_OCC3");
-      hb3 = e ? atoi(e) : 0;
     }
-    int occ = A <= 8 ? (hb3 ? occ8b : occ8) : occ32;
+    int occ = A <= 8 ? occ8 : occ32;
     int slabs = (h->num_sms * (occ > 0 ? occ : 1)) / col_blocks;
     if (slabs > h->hb_slabs) slabs = h->hb_slabs;
     if ((size_t)slabs * 32 > MQ) slabs = cdiv(MQ, 32);
@@ -1036,14 +1033,9 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
     dim3 grid(col_blocks, slabs);
     float* g_vhb = G + h->o_vhb;
     if (A <= 8) {
-      if (hb3)
-        rtk::k_heads_bwd_fused<8, 3><<<grid, dim3(32, 8), 0, st>>>(
-            h->dtheta, actions, net + h->o_outw, net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, h->hb_part,
-            h->hb_partb, MQ, F, A, Nq, duel, h->ldh, rpb);
-      else
-        rtk::k_heads_bwd_fused<8><<<grid, dim3(32, 8), 0, st>>>(
-            h->dtheta, actions, net + h->o_outw, net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, h->hb_part,
-            h->hb_partb, MQ, F, A, Nq, duel, h->ldh, rpb);
+      rtk::k_heads_bwd_fused<8><<<grid, dim3(32, 8), 0, st>>>(
+          h->dtheta, actions, net + h->o_outw, net + h->o_vw, h->h1, h->v1, h->dh1, h->dv1, h->hb_part,
+          h->hb_partb, MQ, F, A, Nq, duel, h->ldh, rpb);
       RT_LAUNCH_CHECK();
       rtk::k_heads_bwd_final<8><<<cdiv(C, 32) + 1, dim3(32, 8), 0, st>>>(
           h->hb_part, h->hb_partb, slabs, G + h->o_outw, G + h->o_outb, G + h->o_vw, G + h->o_vb,

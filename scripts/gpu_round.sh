@@ -1,26 +1,43 @@
 #!/bin/bash
-# One GPU-box round: parity tests, bench, launch list.  Usage: gpurun -- bash scripts/gpu_round.sh
+# One GPU-box round: parity tests, bench, launch list, ncu captures.  Usage: gpurun -- bash scripts/gpu_round.sh
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt
 nproc >> gpurun_out/smi.txt
 echo "=== gemm tests"
 timeout 300 python -m pytest tests/test_gemm_gpu.py -m gpu -q -s --timeout 240 2>&1 | tail -80 | cut -c1-260 | tee gpurun_out/pytest_gemm.log
 if grep -q "failed\|error\|Timeout" gpurun_out/pytest_gemm.log; then export RT_BENCH_GEMM=fp32; echo "tcgen05 GEMM NOT green -> bench on fp32 path"; fi
-echo "=== gemm tile sweep"
-timeout 300 python scripts/gemm_sweep.py 2>&1 | tee gpurun_out/gemm_sweep.txt
-timeout 120 python scripts/timeline.py 2>&1 | tail -24 | tee gpurun_out/lstm_timeline.txt
 echo "=== pytest gpu (all, continue past failures)"
 timeout 1200 python -m pytest tests -m gpu -q --timeout 600 --deselect tests/test_gemm_gpu.py 2>&1 | tail -60 | tee gpurun_out/pytest_gpu.log
+echo "=== smoke"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke.log
+echo "=== gemm tile sweep / lstm timeline / kernel trace / gemm profile"
+timeout 300 python scripts/gemm_sweep.py 2>&1 | tee gpurun_out/gemm_sweep.txt | tail -3
+timeout 120 python scripts/timeline.py 2>&1 | tail -24 > gpurun_out/lstm_timeline.txt
+timeout 300 python scripts/kernel_trace.py --size 65536 --steps 5 > gpurun_out/kernel_trace.txt 2>&1
+grep "updates " gpurun_out/kernel_trace.txt | cut -c1-200
+timeout 300 python scripts/gemm_profile.py > gpurun_out/gemm_profile.txt 2>&1; tail -1 gpurun_out/gemm_profile.txt
 echo "=== bench"
-timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
+timeout 900 python bench.py --steps 30 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
+echo "=== bench --impl reference"
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+tail -2 gpurun_out/bench_reference.err; cut -c1-600 gpurun_out/bench_reference.json
 echo "=== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 3000 --csv \
   --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --size 65536 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-tail -2 gpurun_out/ncu_bench.log | cut -c1-400
-python scripts/summarize_launches.py gpurun_out/launches.csv | tee gpurun_out/launch_summary.txt | head -40
-echo "=== ncu full capture of the fc-size tcgen05 GEMM"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc -s 2 -c 2 -f -o gpurun_out/prof_gemm \
+if [ $(wc -l < gpurun_out/launches.csv) -lt 500 ]; then
+  echo "few kernels seen through the graphs: launch list with RT_GRAPHS=0"
+  RT_GRAPHS=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 3000 --csv \
+    --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --size 65536 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+fi
+tail -2 gpurun_out/ncu_bench.log | cut -c1-300
+python scripts/summarize_launches.py gpurun_out/launches.csv | tee gpurun_out/launch_summary.txt | head -30
+echo "=== ncu full capture of the persistent tcgen05 GEMM (quantile + hidden-layer forward)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc_p -s 8 -c 2 -f -o gpurun_out/prof_gemm \
   python bench.py --steps 1 --warmup 3 --size 65536 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log | cut -c1-200
-ncu -i gpurun_out/prof_gemm.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_pick.py | tee gpurun_out/prof_gemm_summary.txt
+ncu -i gpurun_out/prof_gemm.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_pick.py | tee gpurun_out/prof_gemm_summary.txt | grep -i "kernel name\|duration\|dram__bytes\|tensor"
+echo "=== ncu full capture of the gather"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gather -s 3 -c 1 -f -o gpurun_out/prof_gather \
+  python bench.py --steps 1 --warmup 3 --size 65536 --no-cpu-baseline > gpurun_out/ncu_full_gather.log 2>&1
+ncu -i gpurun_out/prof_gather.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_pick.py | tee gpurun_out/prof_gather_summary.txt | grep -i "kernel name\|duration\|dram__bytes\|dram_throughput"

@@ -148,6 +148,11 @@ def test_pipelined_update_loop_is_bit_identical_to_the_serialised_one():
             idx_log.append(hist._last_idx_tensor.clone())
             td_log.append(L.td_abs().clone())
         torch.cuda.synchronize()
+        # the early loss read-back (after the forward pass) sees the same values as stats()
+        early, full = L.loss(), L.stats()
+        assert early["qloss"] == full["qloss"] and early["td_mean"] == full["td_mean"]
+        first, count = L.wait_late_grads()
+        assert 0 < first and first + count == L.flat().numel()
         return ([t.cpu().tolist() for t in idx_log], torch.stack(td_log).cpu().numpy(),
                 L.flat(0).cpu().numpy().copy(), hist.tree_sum())
 
