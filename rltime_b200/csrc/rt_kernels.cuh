@@ -645,7 +645,10 @@ __global__ void k_colsum_final(const float* __restrict__ part, float* __restrict
 // out layer (A actions) + dueling value layer + combine in one pass, one warp per row
 // (rltime/policies/torch/dqn.py:78-112): adv = h1 Wout^T + b, v = v1 Wv^T + bv,
 // q = v + adv - mean_a adv.  A <= 32.
-template <int MAXA, int RPW = 4>   // RPW rows per warp: each weight vector read from L1 serves RPW rows
+// FI > 0: F == 128 * FI known at compile time, so the column loop unrolls fully and every data load
+// of a row group is in flight before the first FMA (the generic loop waits one memory latency per
+// 128 columns).
+template <int MAXA, int RPW = 4, int FI = 0>   // RPW rows per warp: each weight vector read from L1 serves RPW rows
 __global__ void __launch_bounds__(256) k_heads_out(const float* __restrict__ h1, const float* __restrict__ v1,
                             const float* __restrict__ Wout, const float* __restrict__ bout,
                             const float* __restrict__ Wv, const float* __restrict__ bv,
@@ -669,11 +672,7 @@ __global__ void __launch_bounds__(256) k_heads_out(const float* __restrict__ h1,
 #pragma unroll
   for (int i = 0; i < RPW; ++i) hr[i] = h1 + (r0 + i < rows ? r0 + i : rows - 1) * ldh;
   const ptrdiff_t voff = v1 ? v1 - h1 : 0;
-  // F % 4 == 0: 16-byte loads, RPW independent rows of loads in flight per lane
-  for (int f = lane * 4; f < F; f += 128) {
-    float4 hv[RPW];
-#pragma unroll
-    for (int i = 0; i < RPW; ++i) hv[i] = __ldcs(reinterpret_cast<const float4*>(hr[i] + f));
+  auto fma_cols = [&](int f, const float4 (&hv)[RPW], const float4 (&vv)[RPW]) {
 #pragma unroll
     for (int a = 0; a < MAXA; ++a)
       if (a < A) {
@@ -688,10 +687,33 @@ __global__ void __launch_bounds__(256) k_heads_out(const float* __restrict__ h1,
       float4 w = __ldg(reinterpret_cast<const float4*>(Wv + f));
 #pragma unroll
       for (int i = 0; i < RPW; ++i) {
-        float4 vv = __ldcs(reinterpret_cast<const float4*>(hr[i] + voff + f));
-        accv[i] = fmaf(vv.x, w.x, accv[i]); accv[i] = fmaf(vv.y, w.y, accv[i]);
-        accv[i] = fmaf(vv.z, w.z, accv[i]); accv[i] = fmaf(vv.w, w.w, accv[i]);
+        accv[i] = fmaf(vv[i].x, w.x, accv[i]); accv[i] = fmaf(vv[i].y, w.y, accv[i]);
+        accv[i] = fmaf(vv[i].z, w.z, accv[i]); accv[i] = fmaf(vv[i].w, w.w, accv[i]);
       }
+    }
+  };
+  if (FI > 0) {
+    float4 hv[FI > 0 ? FI : 1][RPW], vv[FI > 0 ? FI : 1][RPW];
+#pragma unroll
+    for (int j = 0; j < FI; ++j)
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        hv[j][i] = __ldcs(reinterpret_cast<const float4*>(hr[i] + lane * 4 + 128 * j));
+        vv[j][i] = v1 ? __ldcs(reinterpret_cast<const float4*>(hr[i] + voff + lane * 4 + 128 * j))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int j = 0; j < FI; ++j) fma_cols(lane * 4 + 128 * j, hv[j], vv[j]);
+  } else {
+    // F % 4 == 0: 16-byte loads, RPW independent rows of loads in flight per lane
+    for (int f = lane * 4; f < F; f += 128) {
+      float4 hv[RPW], vv[RPW];
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        hv[i] = __ldcs(reinterpret_cast<const float4*>(hr[i] + f));
+        vv[i] = v1 ? __ldcs(reinterpret_cast<const float4*>(hr[i] + voff + f)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      fma_cols(f, hv, vv);
     }
   }
 #pragma unroll

@@ -958,7 +958,15 @@ int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float*
   // to the resident warps (grid-stride inside)
   {
     const float* v1 = h->dueling ? h->v1 : nullptr;
-    if (A <= 8) {
+    if (A <= 8 && F == 512) {
+      static int occ = 0;
+      if (!occ) RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rtk::k_heads_out<8, 2, 4>, 256, 0));
+      int blocks = cdiv(cdiv(MQ, 2) * 32, 256);
+      int resident = h->num_sms * (occ > 0 ? occ : 1);
+      if (blocks > resident) blocks = resident;
+      rtk::k_heads_out<8, 2, 4><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
+                                                       net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A, ldh);
+    } else if (A <= 8) {
       static int occ = 0;
       if (!occ) RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rtk::k_heads_out<8, 2>, 256, 0));
       int blocks = cdiv(cdiv(MQ, 2) * 32, 256);
@@ -1051,30 +1059,38 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
     }
     RT_LAUNCH_CHECK();
   }
-  // weight gradients of the hidden layers: leaves on the side branch; the data gradient feeds BPTT
-  SideCtx sd;
-  RT_TRY(side_begin(h, st, &sd));
+  // data gradient first (it feeds BPTT); the weight gradients of the hidden and quantile layers are
+  // leaves and start on the side branch only once the data-gradient GEMM is done -- two L2-bound
+  // 21 GFLOP GEMMs side by side each took twice as long -- so they overlap the latency-bound BPTT
   if (h->fused_hidden) {
-    // [dh1 | dv1] against the stacked [Wfc ; Wvh]: weight gradient and data gradient of both hidden
-    // layers in one GEMM each (bias gradients: k_heads_bwd_final)
+    // [dh1 | dv1] against the stacked [Wfc ; Wvh]: data gradient of both hidden layers in one GEMM
+    // (bias gradients: k_heads_bwd_final)
     const int F2 = 2 * F;
-    RT_TRY(gemm(*sd.gx, sd.st, mk(h->dh1, F2, 1, xq, D, 0, G + h->o_fcw, D, F2, D, (int)MQ)));
     RT_TRY(gemm(h->gx, st, mk(h->dh1, F2, 0, net + h->o_fcw, D, 0, dxq, D, (int)MQ, D, F2)));
   } else {
-    RT_TRY(gemm(*sd.gx, sd.st, mk(h->dh1, F, 1, xq, D, 0, G + h->o_fcw, D, F, D, (int)MQ)));
     RT_TRY(gemm(h->gx, st, mk(h->dh1, F, 0, net + h->o_fcw, D, 0, dxq, D, (int)MQ, D, F)));
     if (h->dueling) {
-      RT_TRY(gemm(*sd.gx, sd.st, mk(h->dv1, F, 1, xq, D, 0, G + h->o_vhw, D, F, D, (int)MQ)));
       rtk::GemmArgs g = mk(h->dv1, F, 0, net + h->o_vhw, D, 0, dxq, D, (int)MQ, D, F);
       g.accumulate = 1;
       RT_TRY(gemm(h->gx, st, g));
     }
   }
-  if (h->dqn) return RT_OK;
-  rtk::k_quantile_mul_bwd<<<cdiv((size_t)M * D, 256), 256, 0, st>>>(h->dxq, feat, h->phi, h->dphi,
-                                                                   h->dfeatq, M, D, Nq);
-  RT_LAUNCH_CHECK();
+  if (!h->dqn) {
+    rtk::k_quantile_mul_bwd<<<cdiv((size_t)M * D, 256), 256, 0, st>>>(h->dxq, feat, h->phi, h->dphi,
+                                                                     h->dfeatq, M, D, Nq);
+    RT_LAUNCH_CHECK();
+  }
+  SideCtx sd;
   RT_TRY(side_begin(h, st, &sd));
+  if (h->fused_hidden) {
+    const int F2 = 2 * F;
+    RT_TRY(gemm(*sd.gx, sd.st, mk(h->dh1, F2, 1, xq, D, 0, G + h->o_fcw, D, F2, D, (int)MQ)));
+  } else {
+    RT_TRY(gemm(*sd.gx, sd.st, mk(h->dh1, F, 1, xq, D, 0, G + h->o_fcw, D, F, D, (int)MQ)));
+    if (h->dueling)
+      RT_TRY(gemm(*sd.gx, sd.st, mk(h->dv1, F, 1, xq, D, 0, G + h->o_vhw, D, F, D, (int)MQ)));
+  }
+  if (h->dqn) return RT_OK;
   RT_TRY(gemm(*sd.gx, sd.st, mk(h->dphi, D, 1, h->cf, E, 0, G + h->o_qw, E, D, E, (int)MQ)));
   RT_TRY(colsum(h, sd.st, h->dphi, MQ, D, G + h->o_qb, 0, sd.colsum_scratch));
   return RT_OK;
@@ -1433,10 +1449,15 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   RT_CUDA(cudaEventCreateWithFlags(&h->ev_late, cudaEventDisableTiming));
   RT_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-  RT_CUDA(cudaStreamCreateWithFlags(&h->own, cudaStreamNonBlocking));
+  {
+    // the critical chain outranks the weight-gradient branch when both have CTAs ready
+    int prio_lo = 0, prio_hi = 0;
+    RT_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    RT_CUDA(cudaStreamCreateWithPriority(&h->own, cudaStreamNonBlocking, prio_hi));
+    RT_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_lo));
+  }
   if (const char* e = getenv("RT_GRAPHS")) h->graphs_enabled = atoi(e);
   if (const char* e = getenv("RT_OVERLAP_BWD")) h->overlap_bwd = atoi(e);
-  RT_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   for (auto& e : h->ev_side) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   RT_CUDA(cudaMallocHost(&h->h_stats, 8 * sizeof(float)));
   RT_TRY(dalloc(h, &h->dadv, MQ * A, "dadv"));
