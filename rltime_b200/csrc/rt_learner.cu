@@ -190,7 +190,13 @@ struct rt_learner {
   int ev_side_next = 0;
   GemmCtx gx2;
   float* colsum_part2 = nullptr;
-  bool side_active = false;    // inside a two-branch backward pass
+  bool side_active = false;    // inside a two-branch phase
+  // second activation set: lets the TARGET network's passes (CNN + input gates, heads) run on the
+  // side branch of the forward graph next to the online network's
+  std::vector<float*> c_out2;
+  float *cf2 = nullptr, *phi2 = nullptr, *xq2 = nullptr, *h1b = nullptr, *v1b = nullptr, *adv2 = nullptr,
+        *vb2 = nullptr;
+  int overlap_fwd = 1;
   float* h_stats = nullptr;        // pinned read-back of stats[0..3]
   std::map<std::string, std::pair<void*, long long>> debug;
   std::vector<void*> allocs;
@@ -582,7 +588,7 @@ bool conv_tc_eligible(const rt_learner* h, size_t i, const void* xin) {
          ((uintptr_t)xin & 15) == 0;
 }
 
-int conv_forward_tc(rt_learner* h, cudaStream_t st, const float* net, size_t i, const void* xin,
+int conv_forward_tc(rt_learner* h, GemmCtx& cx, cudaStream_t st, const float* net, size_t i, const void* xin,
                     float* out, int rows) {
   const ConvL& L = h->conv[i];
   rttc::ConvArgs a;
@@ -590,12 +596,12 @@ int conv_forward_tc(rt_learner* h, cudaStream_t st, const float* net, size_t i, 
   a.C = L.cin; a.H = L.hin; a.W = L.win; a.KH = L.k; a.S = L.s; a.OH = L.hout; a.OW = L.wout;
   a.M = rows * L.hout * L.wout; a.N = L.f; a.K = L.K;
   a.scale = (float)(1.0 / 255.0);
-  a.round_tf32 = h->gx.round_tf32;
+  a.round_tf32 = cx.round_tf32;
   const int BN = L.f <= 32 ? 32 : (L.f <= 64 ? 64 : 128);
   const CUtensorMap* tb = nullptr;
-  RT_TRY(get_tmap(h->gx, net + L.w, L.K, L.f, L.K, rttc::BLOCK_K, BN, 0, &tb));
-  h->gx.tc_launches++;
-  ProfScope ps(h->gx, st, 2.0 * a.M * a.N * a.K, 1, a.M, a.N, a.K);
+  RT_TRY(get_tmap(cx, net + L.w, L.K, L.f, L.K, rttc::BLOCK_K, BN, 0, &tb));
+  cx.tc_launches++;
+  ProfScope ps(cx, st, 2.0 * a.M * a.N * a.K, 1, a.M, a.N, a.K);
   const long long tiles = (long long)cdiv(a.M, rttc::BLOCK_M) * cdiv(a.N, BN);
   // measured: for the gather-bound convolutions 2-3 one-tile CTAs per SM beat one persistent
   // CTA (conv1 103 vs 120 us, conv2/3 34 vs 50 us), so the persistent form is opt-in
@@ -713,8 +719,16 @@ int conv_dx_tc(rt_learner* h, cudaStream_t st, const float* net, int i, const fl
 // CNN forward for `rows` frames: frames to fp32 NHWC once, then every layer is an implicit GEMM
 // over NHWC runs (fallback: im2col + GEMM, chunked so the im2col buffers stay L2-resident).
 // `xf_pre`: the frames of this pass already converted (a slice of h->xf written by the caller).
+// `second`: write the conv outputs to the second activation set with the side branch's GEMM context
+// (only the implicit-GEMM path; callers check cnn_all_implicit first).
+bool cnn_all_implicit(const rt_learner* h) {
+  bool all = true;
+  for (size_t i = 0; i < h->conv.size(); ++i)
+    all = all && conv_tc_eligible(h, i, i == 0 ? (const void*)h->xf : (const void*)h->c_out[i - 1]);
+  return all;
+}
 int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows,
-                const float* xf_pre = nullptr) {
+                const float* xf_pre = nullptr, bool second = false) {
   if (!xf_pre)
     RT_TRY(launch_frames_to_nhwc(st, x, h->xf, rows, h->md.in_c, h->md.in_h, h->md.in_w, (float)(1.0 / 255.0)));
   const float* xf = xf_pre ? xf_pre : h->xf;
@@ -723,12 +737,14 @@ int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t*
     for (size_t i = 0; i < h->conv.size(); ++i)
       all = all && conv_tc_eligible(h, i, i == 0 ? (const void*)xf : (const void*)h->c_out[i - 1]);
     if (all) {
+      std::vector<float*>& out = second ? h->c_out2 : h->c_out;
+      GemmCtx& cx = second ? h->gx2 : h->gx;
       for (size_t i = 0; i < h->conv.size(); ++i)
-        RT_TRY(conv_forward_tc(h, st, net, i, i == 0 ? (const void*)xf : (const void*)h->c_out[i - 1],
-                               h->c_out[i], rows));
+        RT_TRY(conv_forward_tc(h, cx, st, net, i, i == 0 ? (const void*)xf : (const void*)out[i - 1], out[i], rows));
       return RT_OK;
     }
   }
+  RT_REQUIRE(!second, "second activation set needs the implicit-GEMM conv path");
   for (int r0 = 0; r0 < rows; r0 += h->chunk_rows) {
     int rc = rows - r0 < h->chunk_rows ? rows - r0 : h->chunk_rows;
     for (size_t i = 0; i < h->conv.size(); ++i) {
@@ -759,12 +775,13 @@ struct SeqDesc {
 };
 
 // xg = feat . W_ih^T + b_ih + b_hh for `rows` rows
-int lstm_xgates(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int rows, float* xg) {
+int lstm_xgates(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int rows, float* xg,
+                GemmCtx* cx = nullptr) {
   int U = h->U;
   rtk::GemmArgs g = mk(feat, h->feat, 0, net + h->o_wih, h->feat, 1, xg, 4 * U, rows, 4 * U, h->feat);
   g.bias = net + h->o_bih;
   g.bias2 = net + h->o_bhh;
-  return gemm(h->gx, st, g);
+  return gemm(cx ? *cx : h->gx, st, g);
 }
 
 // fp32 recurrence of one sequence: persistent SIMT kernel when it fits, else one GEMM + cell
@@ -918,67 +935,81 @@ int trunk_forward(rt_learner* h, cudaStream_t st, const float* net, const StateV
 }
 
 // IQN quantile layer + FC + out (+ dueling) on M rows (iqn.py:67-122, dqn.py:74-112).
+// Scratch / outputs of one heads pass.  The training pass must use the primary set (its backward
+// reads cf, phi, xq, h1, v1); q_out is where the (rows, A) action values land.
+struct HeadSet {
+  float *cf, *phi, *xq, *h1, *v1, *adv, *v, *q_out;
+  GemmCtx* gx;
+};
+HeadSet primary_set(rt_learner* h, float* q_out) {
+  return HeadSet{h->cf, h->phi, h->xq, h->h1, h->v1, h->adv, h->v, q_out, &h->gx};
+}
+HeadSet second_set(rt_learner* h, float* q_out) {
+  return HeadSet{h->cf2, h->phi2, h->xq2, h->h1b, h->v1b, h->adv2, h->vb2, q_out, &h->gx2};
+}
+
 int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int M,
-                  const float* tau) {
+                  const float* tau, const HeadSet* set = nullptr) {
+  const HeadSet hs = set ? *set : primary_set(h, h->q);
   int Nq = h->Nq, D = h->D, F = h->F, A = h->A, E = h->E;
   size_t MQ = (size_t)M * Nq;
   rtk::GemmArgs g;
   const float* xq = feat;     // DQN: the heads read the trunk output directly
   if (!h->dqn) {
-    rtk::k_cos_features<<<cdiv(MQ * E, 256), 256, 0, st>>>(tau, h->cf, (int)MQ, E);
+    rtk::k_cos_features<<<cdiv(MQ * E, 256), 256, 0, st>>>(tau, hs.cf, (int)MQ, E);
     RT_LAUNCH_CHECK();
-    g = mk(h->cf, E, 0, net + h->o_qw, E, 1, h->phi, D, (int)MQ, D, E);
+    g = mk(hs.cf, E, 0, net + h->o_qw, E, 1, hs.phi, D, (int)MQ, D, E);
     g.bias = net + h->o_qb;
     g.relu = 1;
-    RT_TRY(gemm(h->gx, st, g));
-    rtk::k_quantile_mul<<<cdiv(MQ * (D / 4), 256), 256, 0, st>>>(feat, h->phi, h->xq, MQ, D, Nq);
+    RT_TRY(gemm(*hs.gx, st, g));
+    rtk::k_quantile_mul<<<cdiv(MQ * (D / 4), 256), 256, 0, st>>>(feat, hs.phi, hs.xq, MQ, D, Nq);
     RT_LAUNCH_CHECK();
-    xq = h->xq;
+    xq = hs.xq;
   }
   const int ldh = h->ldh;
   if (h->fused_hidden) {
     // [h1 | v1] = relu(xq . [Wfc ; Wvh]^T + [bfc | bvh]): one GEMM, the A operand is read once
-    g = mk(xq, D, 0, net + h->o_fcw, D, 1, h->h1, ldh, (int)MQ, 2 * F, D);
+    g = mk(xq, D, 0, net + h->o_fcw, D, 1, hs.h1, ldh, (int)MQ, 2 * F, D);
     g.bias = net + h->o_fcb;
     g.relu = 1;
-    RT_TRY(gemm(h->gx, st, g));
+    RT_TRY(gemm(*hs.gx, st, g));
   } else {
-    g = mk(xq, D, 0, net + h->o_fcw, D, 1, h->h1, F, (int)MQ, F, D);
+    g = mk(xq, D, 0, net + h->o_fcw, D, 1, hs.h1, F, (int)MQ, F, D);
     g.bias = net + h->o_fcb;
     g.relu = 1;
-    RT_TRY(gemm(h->gx, st, g));
+    RT_TRY(gemm(*hs.gx, st, g));
     if (h->dueling) {
-      g = mk(xq, D, 0, net + h->o_vhw, D, 1, h->v1, F, (int)MQ, F, D);
+      g = mk(xq, D, 0, net + h->o_vhw, D, 1, hs.v1, F, (int)MQ, F, D);
       g.bias = net + h->o_vhb;
       g.relu = 1;
-      RT_TRY(gemm(h->gx, st, g));
+      RT_TRY(gemm(*hs.gx, st, g));
     }
   }
   // out layer + value layer + dueling combine: one warp per 2 rows (A <= 8) / per row, grid sized
   // to the resident warps (grid-stride inside)
   {
-    const float* v1 = h->dueling ? h->v1 : nullptr;
+    const float* v1 = h->dueling ? hs.v1 : nullptr;
     if (A <= 8 && F == 512) {
       static int occ = 0;
       if (!occ) RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rtk::k_heads_out<8, 2, 4>, 256, 0));
       int blocks = cdiv(cdiv(MQ, 2) * 32, 256);
       int resident = h->num_sms * (occ > 0 ? occ : 1);
       if (blocks > resident) blocks = resident;
-      rtk::k_heads_out<8, 2, 4><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
-                                                       net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A, ldh);
+      rtk::k_heads_out<8, 2, 4><<<blocks, 256, 0, st>>>(hs.h1, v1, net + h->o_outw, net + h->o_outb,
+                                                       net + h->o_vw, net + h->o_vb, hs.adv, hs.v, hs.q_out, MQ, F, A, ldh);
     } else if (A <= 8) {
       static int occ = 0;
       if (!occ) RT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rtk::k_heads_out<8, 2>, 256, 0));
       int blocks = cdiv(cdiv(MQ, 2) * 32, 256);
       int resident = h->num_sms * (occ > 0 ? occ : 1);
       if (blocks > resident) blocks = resident;
-      rtk::k_heads_out<8, 2><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
-                                                    net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A, ldh);
+      rtk::k_heads_out<8, 2><<<blocks, 256, 0, st>>>(hs.h1, v1, net + h->o_outw, net + h->o_outb,
+                                                    net + h->o_vw, net + h->o_vb, hs.adv, hs.v, hs.q_out, MQ, F, A, ldh);
     } else {
       int blocks = cdiv(MQ * 32, 256);
       if (blocks > h->num_sms * 8) blocks = h->num_sms * 8;
-      rtk::k_heads_out<32, 1><<<blocks, 256, 0, st>>>(h->h1, v1, net + h->o_outw, net + h->o_outb,
-                                                     net + h->o_vw, net + h->o_vb, h->adv, h->v, h->q, MQ, F, A, ldh);
+      rtk::k_heads_out<32, 1><<<blocks, 256, 0, st>>>(hs.h1, v1, net + h->o_outw, net + h->o_outb,
+                                                     net + h->o_vw, net + h->o_vb, hs.adv, hs.v, hs.q_out, MQ, F, A, ldh);
     }
     RT_LAUNCH_CHECK();
   }
@@ -1386,6 +1417,9 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     RT_TRY(dalloc(h, &dco, (size_t)h->M * opix * L.f, nm));
     h->c_out.push_back(co);
     h->d_c.push_back(dco);
+    float* co2 = nullptr;
+    RT_TRY(dalloc(h, &co2, (size_t)h->M * opix * L.f));   // target pass: M rows
+    h->c_out2.push_back(co2);
     float* wt = nullptr;
     if (i > 0) RT_TRY(dalloc(h, &wt, (size_t)L.f * L.K));
     h->conv_wt.push_back(wt);
@@ -1436,6 +1470,19 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   }
   RT_TRY(dalloc(h, &h->adv, MQ * A, "adv"));
   RT_TRY(dalloc(h, &h->v, MQ, "v"));
+  // second heads set (target pass on the side branch of the forward graph)
+  RT_TRY(dalloc(h, &h->cf2, MQ * h->E));
+  RT_TRY(dalloc(h, &h->phi2, MQ * D));
+  RT_TRY(dalloc(h, &h->xq2, MQ * D));
+  if (h->fused_hidden) {
+    RT_TRY(dalloc(h, &h->h1b, MQ * 2 * F));
+    h->v1b = h->h1b + F;
+  } else {
+    RT_TRY(dalloc(h, &h->h1b, MQ * F));
+    RT_TRY(dalloc(h, &h->v1b, MQ * F));
+  }
+  RT_TRY(dalloc(h, &h->adv2, MQ * A));
+  RT_TRY(dalloc(h, &h->vb2, MQ));
   RT_TRY(dalloc(h, &h->q, MQ * A, "q"));
   RT_TRY(dalloc(h, &h->tq, MQ * A, "tq"));
   RT_TRY(dalloc(h, &h->sq, MQ * A, "sq"));
@@ -1458,6 +1505,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   }
   if (const char* e = getenv("RT_GRAPHS")) h->graphs_enabled = atoi(e);
   if (const char* e = getenv("RT_OVERLAP_BWD")) h->overlap_bwd = atoi(e);
+  if (const char* e = getenv("RT_OVERLAP_FWD")) h->overlap_fwd = atoi(e);
   for (auto& e : h->ev_side) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   RT_CUDA(cudaMallocHost(&h->h_stats, 8 * sizeof(float)));
   RT_TRY(dalloc(h, &h->dadv, MQ * A, "dadv"));
@@ -1733,6 +1781,9 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
 
   // ---- forward phase: burn-in, bootstrap targets, training forward, losses
   auto forward_phase = [&]() -> int {
+    h->side_active = forked && !h->gx.profile;
+    struct Off { rt_learner* h; ~Off() { h->side_active = false; } } off{h};
+    bool train_heads_done = false;
     // ---- burn-in (multi_step_trainer.py:90-131): only the recurrent state is needed, so the
     // heads the reference also evaluates are skipped.  states / target_states alias one stack,
     // and the write-back order (online first) is the reference's.
@@ -1758,16 +1809,28 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       // launch (20 dependent steps instead of 60).  The online input gates are computed once
       // over the T+n distinct rows: the selection pass reads rows [n, T+n), training rows [0, T).
       StateView sv = view(P + n);
+      // Two branches: the TARGET network's work (CNN + input gates before the recurrences, its heads
+      // pass after them) runs on the side branch with the second activation set while the main
+      // branch does the online network's; they meet at the one LSTM launch and at the target kernel.
+      const bool fork_fwd = h->side_active && h->overlap_fwd && h->td.double_q && cnn_all_implicit(h);
       if (h->td.double_q) {
         // the target pass (rows [n, T+n)) and the online pass (rows [0, T+n)) read the same frames:
         // convert them to fp32 NHWC once
         RT_TRY(launch_frames_to_nhwc(st, svt.x, h->xf, M + n * B, h->md.in_c, h->md.in_h, h->md.in_w,
                                      (float)(1.0 / 255.0)));
-        RT_TRY(cnn_forward(h, st, h->p[1], sv.x, M, h->xf + (size_t)n * B * frame));
+        if (fork_fwd) {
+          SideCtx sd;
+          RT_TRY(side_begin(h, st, &sd));
+          RT_TRY(cnn_forward(h, sd.st, h->p[1], sv.x, M, h->xf + (size_t)n * B * frame, true));
+          RT_TRY(lstm_xgates(h, sd.st, h->p[1], h->c_out2.back(), M, h->xg2, sd.gx));
+        } else {
+          RT_TRY(cnn_forward(h, st, h->p[1], sv.x, M, h->xf + (size_t)n * B * frame));
+          RT_TRY(lstm_xgates(h, st, h->p[1], h->c_out.back(), M, h->xg2));
+        }
       } else {
         RT_TRY(cnn_forward(h, st, h->p[1], sv.x, M));
+        RT_TRY(lstm_xgates(h, st, h->p[1], h->c_out.back(), M, h->xg2));
       }
-      RT_TRY(lstm_xgates(h, st, h->p[1], h->c_out.back(), M, h->xg2));
       SeqDesc seqs[3];
       int ns = 0;
       seqs[ns++] = SeqDesc{h->p[1], h->xg2, sv.hx, sv.cx, sv.initials, h->h_all2, 1, false};
@@ -1780,12 +1843,27 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
         RT_TRY(lstm_xgates(h, st, h->p[0], h->c_out.back(), M, h->xg));
       }
       seqs[ns++] = SeqDesc{h->p[0], h->xg, svt.hx, svt.cx, svt.initials, h->h_all, 0, true};
+      if (fork_fwd) RT_TRY(side_join(h, st));
       RT_TRY(lstm_run(h, st, seqs, ns, T, B));
-      RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[0]));
-      RT_CUDA(cudaMemcpyAsync(h->tq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      if (h->td.double_q) RT_TRY(heads_forward(h, st, h->p[0], h->h_all3, M, tau_seg[1]));
-      else RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[1]));
-      RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (fork_fwd) {
+        // target heads on the side branch (second set, q straight into tq); selection and training
+        // heads on the main branch; the bootstrap target needs all three
+        SideCtx sd;
+        RT_TRY(side_begin(h, st, &sd));
+        const HeadSet hs2 = second_set(h, h->tq);
+        RT_TRY(heads_forward(h, sd.st, h->p[1], h->h_all2, M, tau_seg[0], &hs2));
+        const HeadSet hs_sel = primary_set(h, h->sq);
+        RT_TRY(heads_forward(h, st, h->p[0], h->h_all3, M, tau_seg[1], &hs_sel));
+        RT_TRY(heads_forward(h, st, h->p[0], h->h_all, M, tau_seg[2]));
+        RT_TRY(side_join(h, st));
+        train_heads_done = true;
+      } else {
+        RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[0]));
+        RT_CUDA(cudaMemcpyAsync(h->tq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (h->td.double_q) RT_TRY(heads_forward(h, st, h->p[0], h->h_all3, M, tau_seg[1]));
+        else RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[1]));
+        RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      }
       size_t off = (size_t)P * B;
       rtk::k_iqn_target<<<cdiv(M, 4), 128, (size_t)4 * Nq * h->A * sizeof(float), st>>>(
           h->tq, h->sq, b->returns + off, b->target_masks + off, (const long long*)b->nsteps + off,
@@ -1834,7 +1912,7 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       }
     }
     // ---- training heads + loss (iqn.py:54-129)
-    RT_TRY(heads_forward(h, st, h->p[0], feat, M, tau_seg[2]));
+    if (!train_heads_done) RT_TRY(heads_forward(h, st, h->p[0], feat, M, tau_seg[2]));
     RT_CUDA(cudaMemcpyAsync(h->tau, tau_seg[2], (size_t)h->MQ * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (h->dqn) {
       rtk::k_dqn_loss<<<cdiv(M, 128), 128, 0, st>>>(h->q, h->targets, actions, weights, h->dtheta, h->row_loss,
