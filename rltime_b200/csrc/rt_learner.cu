@@ -197,6 +197,12 @@ struct rt_learner {
   float *cf2 = nullptr, *phi2 = nullptr, *xq2 = nullptr, *h1b = nullptr, *v1b = nullptr, *adv2 = nullptr,
         *vb2 = nullptr;
   int overlap_fwd = 1;
+  // third branch (forward only): the selection heads pass, with a third activation set
+  cudaStream_t side_b = nullptr;
+  cudaEvent_t ev_side_b[2] = {};     // [0] fork, [1] join
+  GemmCtx gx3;
+  float *cf3 = nullptr, *phi3 = nullptr, *xq3 = nullptr, *h1c = nullptr, *v1c = nullptr, *adv3 = nullptr,
+        *vb3 = nullptr;
   float* h_stats = nullptr;        // pinned read-back of stats[0..3]
   std::map<std::string, std::pair<void*, long long>> debug;
   std::vector<void*> allocs;
@@ -947,6 +953,9 @@ HeadSet primary_set(rt_learner* h, float* q_out) {
 HeadSet second_set(rt_learner* h, float* q_out) {
   return HeadSet{h->cf2, h->phi2, h->xq2, h->h1b, h->v1b, h->adv2, h->vb2, q_out, &h->gx2};
 }
+HeadSet third_set(rt_learner* h, float* q_out) {
+  return HeadSet{h->cf3, h->phi3, h->xq3, h->h1c, h->v1c, h->adv3, h->vb3, q_out, &h->gx3};
+}
 
 int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int M,
                   const float* tau, const HeadSet* set = nullptr) {
@@ -1483,6 +1492,19 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   }
   RT_TRY(dalloc(h, &h->adv2, MQ * A));
   RT_TRY(dalloc(h, &h->vb2, MQ));
+  // third heads set (selection pass)
+  RT_TRY(dalloc(h, &h->cf3, MQ * h->E));
+  RT_TRY(dalloc(h, &h->phi3, MQ * D));
+  RT_TRY(dalloc(h, &h->xq3, MQ * D));
+  if (h->fused_hidden) {
+    RT_TRY(dalloc(h, &h->h1c, MQ * 2 * F));
+    h->v1c = h->h1c + F;
+  } else {
+    RT_TRY(dalloc(h, &h->h1c, MQ * F));
+    RT_TRY(dalloc(h, &h->v1c, MQ * F));
+  }
+  RT_TRY(dalloc(h, &h->adv3, MQ * A));
+  RT_TRY(dalloc(h, &h->vb3, MQ));
   RT_TRY(dalloc(h, &h->q, MQ * A, "q"));
   RT_TRY(dalloc(h, &h->tq, MQ * A, "tq"));
   RT_TRY(dalloc(h, &h->sq, MQ * A, "sq"));
@@ -1502,6 +1524,8 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     RT_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     RT_CUDA(cudaStreamCreateWithPriority(&h->own, cudaStreamNonBlocking, prio_hi));
     RT_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_lo));
+    RT_CUDA(cudaStreamCreateWithPriority(&h->side_b, cudaStreamNonBlocking, prio_lo));
+    for (auto& e : h->ev_side_b) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   if (const char* e = getenv("RT_GRAPHS")) h->graphs_enabled = atoi(e);
   if (const char* e = getenv("RT_OVERLAP_BWD")) h->overlap_bwd = atoi(e);
@@ -1524,6 +1548,8 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->gx.ws, h->gx.ws_floats));
   h->gx2.ws_floats = (size_t)16 << 20;  // 64 MiB: split-K partials of the weight-gradient branch
   RT_TRY(dalloc(h, &h->gx2.ws, h->gx2.ws_floats));
+  h->gx3.ws_floats = (size_t)1 << 20;   // heads forward GEMMs never split
+  RT_TRY(dalloc(h, &h->gx3.ws, h->gx3.ws_floats));
   h->gx.mode = td->gemm_mode;
   if (const char* e = getenv("RT_TC_BN")) h->gx.force_bn = atoi(e);
   if (const char* e = getenv("RT_TC_STAGES")) h->gx.force_stages = atoi(e);
@@ -1556,6 +1582,9 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     h->gx2.mode = h->gx.mode; h->gx2.num_sms = h->gx.num_sms; h->gx2.persistent = h->gx.persistent;
     h->gx2.force_bn = h->gx.force_bn; h->gx2.force_stages = h->gx.force_stages;
     h->gx2.round_tf32 = h->gx.round_tf32;
+    h->gx3.mode = h->gx.mode; h->gx3.num_sms = h->gx.num_sms; h->gx3.persistent = h->gx.persistent;
+    h->gx3.force_bn = h->gx.force_bn; h->gx3.force_stages = h->gx.force_stages;
+    h->gx3.round_tf32 = h->gx.round_tf32;
     const char* e = getenv("RT_LSTM_STEPWISE");
     if (e && e[0] == '1') h->lstm_persistent = 0;
     e = getenv("RT_LSTM_TC");
@@ -1595,6 +1624,8 @@ void rt_learner_destroy(rt_learner* h) {
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->own) cudaStreamDestroy(h->own);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->side_b) cudaStreamDestroy(h->side_b);
+  for (auto& e : h->ev_side_b) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_side) if (e) cudaEventDestroy(e);
   if (h->h_stats) cudaFreeHost(h->h_stats);
   delete h;
@@ -1852,9 +1883,14 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
         RT_TRY(side_begin(h, st, &sd));
         const HeadSet hs2 = second_set(h, h->tq);
         RT_TRY(heads_forward(h, sd.st, h->p[1], h->h_all2, M, tau_seg[0], &hs2));
-        const HeadSet hs_sel = primary_set(h, h->sq);
-        RT_TRY(heads_forward(h, st, h->p[0], h->h_all3, M, tau_seg[1], &hs_sel));
+        // ... and the selection pass on a third branch with its own set
+        RT_CUDA(cudaEventRecord(h->ev_side_b[0], st));
+        RT_CUDA(cudaStreamWaitEvent(h->side_b, h->ev_side_b[0], 0));
+        const HeadSet hs_sel = third_set(h, h->sq);
+        RT_TRY(heads_forward(h, h->side_b, h->p[0], h->h_all3, M, tau_seg[1], &hs_sel));
         RT_TRY(heads_forward(h, st, h->p[0], h->h_all, M, tau_seg[2]));
+        RT_CUDA(cudaEventRecord(h->ev_side_b[1], h->side_b));
+        RT_CUDA(cudaStreamWaitEvent(st, h->ev_side_b[1], 0));
         RT_TRY(side_join(h, st));
         train_heads_done = true;
       } else {
