@@ -7,7 +7,7 @@ echo "=== gemm tests"
 timeout 300 python -m pytest tests/test_gemm_gpu.py -m gpu -q -s --timeout 240 2>&1 | tail -80 | cut -c1-260 | tee gpurun_out/pytest_gemm.log
 if grep -q "failed\|error\|Timeout" gpurun_out/pytest_gemm.log; then export RT_BENCH_GEMM=fp32; echo "tcgen05 GEMM NOT green -> bench on fp32 path"; fi
 echo "=== pytest gpu (all, continue past failures)"
-timeout 1200 python -m pytest tests -m gpu -q --timeout 600 --deselect tests/test_gemm_gpu.py 2>&1 | tail -60 | tee gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -60 | tee gpurun_out/pytest_gpu.log
 echo "=== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke.log
 echo "=== gemm tile sweep / lstm timeline / kernel trace / gemm profile"
