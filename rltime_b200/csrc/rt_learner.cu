@@ -157,6 +157,7 @@ struct rt_learner {
   int conv_implicit = 1;
   int conv_implicit_bwd = 1;
   int conv_persistent = 1;
+  int conv_shallow = 1;         // shallow conv rings (2 CTAs/SM) inside the multi-branch phases (RT_CONV_SHALLOW; 2: backward too)
   int conv_dx_implicit = 1;
   std::vector<float*> conv_wt;  // re-laid filters for the data-gradient implicit GEMM (per layer, null for conv1)
   float* dcol_full = nullptr;
@@ -567,10 +568,13 @@ int launch_conv_tc(const CUtensorMap* tb, const rttc::ConvArgs& a, cudaStream_t 
   return RT_OK;
 }
 
-template <int BN, int IN_U8>
+// SHALLOW: a ring small enough (<= ~92 KB with the epilogue scratch) for two of these CTAs per SM, so
+// the target and online networks' convolutions of the two-branch forward pass share every SM
+template <int BN, int IN_U8, bool SHALLOW = false>
 int launch_conv_tc_p(const CUtensorMap* tb, const rttc::ConvArgs& a, int ctas, cudaStream_t st) {
   constexpr int STAGE_BYTES = rttc::BLOCK_M * rttc::BLOCK_K * 4 + BN * rttc::BLOCK_K * 4;
-  constexpr int STAGES = (160 * 1024) / STAGE_BYTES >= 6 ? 6 : (160 * 1024) / STAGE_BYTES;
+  constexpr int DEEP = (160 * 1024) / STAGE_BYTES >= 6 ? 6 : (160 * 1024) / STAGE_BYTES;
+  constexpr int STAGES = SHALLOW ? ((72 * 1024) / STAGE_BYTES >= 4 ? 4 : (72 * 1024) / STAGE_BYTES) : DEEP;
   constexpr int SMEM = STAGES * STAGE_BYTES + 4 * 32 * 36 * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
   auto kern = rttc::k_conv_tc_p<BN, IN_U8, STAGES>;
   static bool configured = false;
@@ -613,6 +617,9 @@ int conv_forward_tc(rt_learner* h, GemmCtx& cx, cudaStream_t st, const float* ne
   // CTA (conv1 103 vs 120 us, conv2/3 34 vs 50 us), so the persistent form is opt-in
   if (h->conv_persistent && tiles > h->num_sms) {
     const int ctas = h->num_sms;
+    const bool shallow = h->conv_shallow && h->side_active;
+    if (shallow && BN == 32) return launch_conv_tc_p<32, 0, true>(tb, a, ctas, st);
+    if (shallow && BN == 64) return launch_conv_tc_p<64, 0, true>(tb, a, ctas, st);
     if (BN == 32) return launch_conv_tc_p<32, 0>(tb, a, ctas, st);
     if (BN == 64) return launch_conv_tc_p<64, 0>(tb, a, ctas, st);
     return launch_conv_tc_p<128, 0>(tb, a, ctas, st);
@@ -622,9 +629,8 @@ int conv_forward_tc(rt_learner* h, GemmCtx& cx, cudaStream_t st, const float* ne
   return launch_conv_tc<128, 0>(tb, a, st);
 }
 
-template <int BN, int IN_U8>
+template <int BN, int IN_U8, int STAGES = 4>
 int launch_convdw_tc(const CUtensorMap* ta, const rttc::ConvDwArgs& a, dim3 grid, cudaStream_t st) {
-  constexpr int STAGES = 4;
   constexpr int SMEM = STAGES * (rttc::BLOCK_M * rttc::BLOCK_K * 4 + BN * rttc::BLOCK_K * 4) +
                        (2 * STAGES + 1) * 8 + 16 + 1024;
   auto kern = rttc::k_convdw_tc<BN, IN_U8, STAGES>;
@@ -662,8 +668,10 @@ int conv_dw_tc(rt_learner* h, GemmCtx& cx, cudaStream_t st, size_t i, const void
   dim3 grid(tiles, 1, splits);
   cx.tc_launches++;
   ProfScope ps(cx, st, 2.0 * a.P * (double)L.f * L.K, 2, L.f, L.K, a.P);
+  const bool shallow = h->conv_shallow >= 2 && h->side_active;
   if (BN == 32) RT_TRY((launch_convdw_tc<32, 0>(ta, a, grid, st)));
   else if (BN == 64) RT_TRY((launch_convdw_tc<64, 0>(ta, a, grid, st)));
+  else if (shallow) RT_TRY((launch_convdw_tc<128, 0, 3>(ta, a, grid, st)));
   else RT_TRY((launch_convdw_tc<128, 0>(ta, a, grid, st)));
   rtk::GemmArgs g = mk(nullptr, 0, 0, nullptr, 0, 0, dW, L.K, L.f, L.K, a.P);
   g.ws = cx.ws;
@@ -673,10 +681,11 @@ int conv_dw_tc(rt_learner* h, GemmCtx& cx, cudaStream_t st, size_t i, const void
   return RT_OK;
 }
 
-template <int BN>
+template <int BN, bool SHALLOW = false>
 int launch_convdx_tc(const CUtensorMap* tb, const rttc::ConvDxArgs& a, int ctas, cudaStream_t st) {
   constexpr int STAGE_BYTES = rttc::BLOCK_M * rttc::BLOCK_K * 4 + BN * rttc::BLOCK_K * 4;
-  constexpr int STAGES = (160 * 1024) / STAGE_BYTES >= 6 ? 6 : (160 * 1024) / STAGE_BYTES;
+  constexpr int DEEP = (160 * 1024) / STAGE_BYTES >= 6 ? 6 : (160 * 1024) / STAGE_BYTES;
+  constexpr int STAGES = SHALLOW ? ((80 * 1024) / STAGE_BYTES >= 4 ? 4 : (80 * 1024) / STAGE_BYTES) : DEEP;
   constexpr int SMEM = STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
   auto kern = rttc::k_convdx_tc<BN, STAGES>;
   static bool configured = false;
@@ -717,6 +726,9 @@ int conv_dx_tc(rt_learner* h, cudaStream_t st, const float* net, int i, const fl
   const int ctas = (int)(tiles < h->num_sms ? tiles : h->num_sms);
   h->gx.tc_launches++;
   ProfScope ps(h->gx, st, 2.0 * rows * L.hout * L.wout * (double)L.f * L.K, 3, (long long)rows * L.hin * L.win, L.cin, (long long)L.f * L.k * L.k);
+  const bool shallow = h->conv_shallow >= 2 && h->side_active;
+  if (shallow && BN == 32) return launch_convdx_tc<32, true>(tb, a, ctas, st);
+  if (shallow && BN == 64) return launch_convdx_tc<64, true>(tb, a, ctas, st);
   if (BN == 32) return launch_convdx_tc<32>(tb, a, ctas, st);
   if (BN == 64) return launch_convdx_tc<64>(tb, a, ctas, st);
   return launch_convdx_tc<128>(tb, a, ctas, st);
@@ -1530,6 +1542,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   if (const char* e = getenv("RT_GRAPHS")) h->graphs_enabled = atoi(e);
   if (const char* e = getenv("RT_OVERLAP_BWD")) h->overlap_bwd = atoi(e);
   if (const char* e = getenv("RT_OVERLAP_FWD")) h->overlap_fwd = atoi(e);
+  if (const char* e = getenv("RT_CONV_SHALLOW")) h->conv_shallow = atoi(e);
   for (auto& e : h->ev_side) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   RT_CUDA(cudaMallocHost(&h->h_stats, 8 * sizeof(float)));
   RT_TRY(dalloc(h, &h->dadv, MQ * A, "dadv"));

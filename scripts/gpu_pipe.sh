@@ -1,11 +1,8 @@
 #!/bin/bash
-# Quick GPU check: learner/trainer parity tests, warm kernel timeline, bench A/B.
+# Quick GPU A/B.
 mkdir -p gpurun_out
-timeout -k 10 900 python -m pytest tests/test_learner_gpu.py tests/test_trainer_gpu.py -m gpu -q -x --timeout 300 2>&1 | tail -15 | cut -c1-300 | tee gpurun_out/pytest_pipe.log
-timeout -k 10 300 python scripts/kernel_trace.py --size 65536 --steps 5 > gpurun_out/kernel_trace.txt 2>&1
-grep "updates \|disabled" gpurun_out/kernel_trace.txt | cut -c1-230
-for v in 1; do
-RT_OVERLAP_FWD=1 RT_DUMMY=$v timeout -k 10 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_f$v.json 2> gpurun_out/bench_f$v.err
-tail -3 gpurun_out/bench_f$v.err; cut -c1-200 gpurun_out/bench_f$v.json; echo; grep -o '"e2e": {[^}]*}' gpurun_out/bench_f$v.json
+for v in 1 2; do
+RT_CONV_SHALLOW=$v timeout -k 10 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/bench_s$v.json 2> gpurun_out/bench_s$v.err
+tail -3 gpurun_out/bench_s$v.err; echo "shallow=$v"; grep -o '"ms_per_step": [0-9.]*' gpurun_out/bench_s$v.json
 done
-cp gpurun_out/bench_f1.json gpurun_out/bench.json
+RT_CONV_SHALLOW=2 timeout -k 10 600 python -m pytest tests/test_trainer_gpu.py tests/test_learner_gpu.py -m gpu -q -x 2>&1 | tail -2
