@@ -171,40 +171,6 @@ __global__ void k_conv_wT(const float* __restrict__ w, float* __restrict__ wt, i
   }
 }
 
-// ------------------------------------------------------------------------------ im2col
-// conv input NCHW uint8 frames (the replay batch), fused x.float() * (1/255)
-// (rltime/models/torch/modules/cnn.py:44-45).  col[(m,oh,ow), (c,kh,kw)].
-// VEC = 4: a thread converts four consecutive kw taps (one aligned 32-bit load, one 16-byte
-// store); requires KH % 4 == 0, S % 4 == 0, W % 4 == 0 (nature-CNN conv1: k8 s4 on 84x84).
-template <int VEC>
-__global__ void k_im2col_u8_nchw(const uint8_t* __restrict__ x, float* __restrict__ col, int rows,
-                                 int C, int H, int W, int KH, int S, int OH, int OW, float scale) {
-  const int K = C * KH * KH;
-  const int KV = K / VEC;
-  size_t total = (size_t)rows * OH * OW * KV;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    int k = (int)(idx % KV) * VEC;
-    size_t r = idx / KV;
-    int ow = (int)(r % OW);
-    int oh = (int)((r / OW) % OH);
-    size_t m = r / ((size_t)OW * OH);
-    int kw = k % KH, kh = (k / KH) % KH, c = k / (KH * KH);
-    const uint8_t* src = x + ((m * C + c) * H + (oh * S + kh)) * W + (ow * S + kw);
-    if (VEC == 4) {
-      uint32_t v = *reinterpret_cast<const uint32_t*>(src);
-      float4 o;
-      o.x = __fmul_rn((float)(v & 0xff), scale);
-      o.y = __fmul_rn((float)((v >> 8) & 0xff), scale);
-      o.z = __fmul_rn((float)((v >> 16) & 0xff), scale);
-      o.w = __fmul_rn((float)(v >> 24), scale);
-      *reinterpret_cast<float4*>(col + r * K + k) = o;
-    } else {
-      col[r * K + k] = __fmul_rn((float)src[0], scale);
-    }
-  }
-}
-
 // conv input NHWC float.  col[(m,oh,ow), (kh,kw,c)].  VEC = 4 moves float4 (C % 4 == 0).
 template <int VEC>
 __global__ void k_im2col_f32_nhwc(const float* __restrict__ x, float* __restrict__ col, int rows,
@@ -369,13 +335,6 @@ __global__ void k_lstm_cell_bwd(const float* __restrict__ dout, const float* __r
   dc_carry[i] = dc * gf * (1.f - initials[b]);
 }
 
-// dh_carry = (dgates[t] . W_hh) * (1 - initials[t])
-__global__ void k_mask_rows(float* __restrict__ x, const float* __restrict__ initials, int B, int U) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * U) return;
-  x[i] *= (1.f - initials[i / U]);
-}
-
 // ------------------------------------------------------------------------------- IQN
 // cos(pi * i * tau), i = 1..E   (rltime/policies/torch/iqn.py:91-93)
 __global__ void k_cos_features(const float* __restrict__ tau, float* __restrict__ cf, int rows, int E) {
@@ -414,33 +373,6 @@ __global__ void k_quantile_mul_bwd(const float* __restrict__ dxq, const float* _
     dphi[r] = (p > 0.f) ? g * xv : 0.f;
   }
   dx[idx] = acc;
-}
-
-// q[r,a] = v[r] + adv[r,a] - mean_a adv[r,:]     (rltime/policies/torch/dqn.py:86-87)
-__global__ void k_dueling(const float* __restrict__ adv, const float* __restrict__ v,
-                          float* __restrict__ q, size_t rows, int A) {
-  size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  float s = 0.f;
-  for (int a = 0; a < A; ++a) s += adv[r * A + a];
-  float mean = s / (float)A;
-  float vv = v ? v[r] : 0.f;
-  for (int a = 0; a < A; ++a) q[r * A + a] = v ? (vv + adv[r * A + a] - mean) : adv[r * A + a];
-}
-
-// dq (nonzero only at the acted action) -> dadv, dv
-__global__ void k_dueling_bwd(const float* __restrict__ dtheta, const long long* __restrict__ actions,
-                              float* __restrict__ dadv, float* __restrict__ dv, size_t rows, int A,
-                              int Nq, int dueling) {
-  size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  int act = (int)actions[r / Nq];
-  float g = dtheta[r];
-  for (int a = 0; a < A; ++a) {
-    float d = (a == act) ? g : 0.f;
-    dadv[r * A + a] = dueling ? d - g / (float)A : d;
-  }
-  if (dv) dv[r] = g;
 }
 
 // qmean[r,a] = mean_q q[r,q,a]   (IQNPolicy._actor_predict_postprocess, policies/torch/iqn.py:124-131)

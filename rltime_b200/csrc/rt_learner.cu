@@ -135,12 +135,10 @@ struct rt_learner {
         *adv = nullptr, *v = nullptr, *q = nullptr;
   float *tq = nullptr, *sq = nullptr, *targets = nullptr;
   float *dtheta = nullptr, *row_loss = nullptr, *report = nullptr, *stats = nullptr;
-  float *dadv = nullptr, *dv = nullptr, *dh1 = nullptr, *dv1 = nullptr, *dxq = nullptr, *dphi = nullptr,
+  float *dh1 = nullptr, *dv1 = nullptr, *dxq = nullptr, *dphi = nullptr,
         *dfeatq = nullptr, *dgates = nullptr, *dh_carry = nullptr, *dc_carry = nullptr, *dfeat = nullptr;
   GemmCtx gx;
   float* colsum_part = nullptr;
-  float *hw_part = nullptr, *hw_partb = nullptr;  // small-head weight-gradient partials
-  int hw_parts = 256;
   float* hb_part = nullptr;   // slab partials of k_heads_bwd_fused: [hb_slabs][A + 1][F or 2F]
   float* hb_partb = nullptr;  // ... and of the out / value bias gradients: [hb_slabs][33]
   int hb_slabs = 256;
@@ -1545,8 +1543,6 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   if (const char* e = getenv("RT_CONV_SHALLOW")) h->conv_shallow = atoi(e);
   for (auto& e : h->ev_side) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   RT_CUDA(cudaMallocHost(&h->h_stats, 8 * sizeof(float)));
-  RT_TRY(dalloc(h, &h->dadv, MQ * A, "dadv"));
-  RT_TRY(dalloc(h, &h->dv, MQ, "dv"));
   if (h->fused_hidden) {
     RT_TRY(dalloc(h, &h->dh1, MQ * 2 * F, "dh1"));
     h->dv1 = h->dh1 + F;
@@ -1613,8 +1609,6 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     e = getenv("RT_CONV_BWD_IM2COL");
     if (e && e[0] == '1') h->conv_implicit_bwd = 0;
   }
-  RT_TRY(dalloc(h, &h->hw_part, (size_t)h->hw_parts * (A + 1) * F));
-  RT_TRY(dalloc(h, &h->hw_partb, (size_t)h->hw_parts * (A + 1)));
   RT_TRY(dalloc(h, &h->hb_part, (size_t)h->hb_slabs * (A + 1) * 2 * F));
   RT_TRY(dalloc(h, &h->hb_partb, (size_t)h->hb_slabs * 33));
   *out = h;
