@@ -48,15 +48,52 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region: NVML in-process (a sample
+    every few milliseconds), nvidia-smi as the fallback (one sample per ~100 ms call)."""
+
+    # nvmlClocksThrottleReason* / nvmlClocksEventReason* bit masks
+    _MASKS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+              ("sw_power_cap", 0x4))
 
     def __init__(self, index=0):
         self.index = index
         self.rows = []
         self._stop = threading.Event()
         self._th = None
+        self.source = "nvidia-smi"
+
+    def _nvml(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            return pynvml, h, mx
+        except Exception:
+            return None
 
     def _run(self):
+        nv = self._nvml()
+        if nv is not None:
+            pynvml, h, mx = nv
+            self.source = "nvml"
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+            while not self._stop.is_set():
+                try:
+                    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    try:
+                        bits = int(get_reasons(h)) if get_reasons else 0
+                    except Exception:
+                        bits = 0
+                    self.rows.append([str(sm), str(mx)] +
+                                     ["Active" if bits & m else "Not Active" for _, m in self._MASKS])
+                except Exception:
+                    break
+                self._stop.wait(0.004)
+            if self.rows:
+                return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -88,7 +125,7 @@ class ClockSampler:
                    if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
                 "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
 def dominant_roofline(shape, fl, ms_total, n, family_ms, prof_steps, tf32_peak, which):

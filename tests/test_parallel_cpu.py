@@ -88,3 +88,50 @@ def test_shard_helpers():
     parts = [parallel.shard_samples(samples, r, 3) for r in range(3)]
     assert sorted(s["env_id"] for p in parts for s in p) == list(range(7))
     assert [s["env_id"] for s in parts[1]] == [1, 4]
+
+
+class _FakeLearner:
+    """Host-side stand-in with the DeviceLearner surface data_parallel_step drives."""
+
+    def __init__(self, rank, n=96, first=32):
+        self.device = torch.device("cpu")
+        self.g = torch.zeros(n)
+        self.rank, self.first, self.applied = rank, first, []
+
+    def compute_grads(self, batch, taus=None):
+        self.g.copy_(torch.arange(self.g.numel(), dtype=torch.float32) * (self.rank + 1) + batch)
+
+    def flat(self):
+        return self.g
+
+    def wait_late_grads(self, stream_ptr=None):
+        return self.first, self.g.numel() - self.first
+
+    def apply_grads(self, scale):
+        self.applied.append((scale, self.g.clone()))
+
+
+def _dp_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from rltime_b200 import parallel
+    parallel.init_process_group("gloo")
+    L = _FakeLearner(rank)
+    # CPU tensors: the single all-reduce path (the two-bucket path needs CUDA streams and is
+    # checked on GPUs by scripts/dist_check.py)
+    parallel.data_parallel_step(L, 0.5, world, overlap=False)
+    if rank == 0:
+        torch.save(L.applied, out)
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_data_parallel_step(tmp_path):
+    out = str(tmp_path / "a.pt")
+    mp.spawn(_dp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    (scale, g), = torch.load(out)
+    assert scale == 0.5
+    want = torch.arange(96, dtype=torch.float32) * 3 + 1.0      # ranks contribute x1 and x2, batch term twice
+    np.testing.assert_array_equal(g.numpy(), want.numpy())
