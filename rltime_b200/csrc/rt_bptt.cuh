@@ -1,0 +1,152 @@
+// Persistent BPTT recurrence (EXPERIMENTAL, off by default: RT_BPTT_PERSISTENT=1).
+//
+// Replaces the 2 x (T-1) launches of the stepwise path (k_lstm_cell_bwd + split-K GEMM per step)
+// with ONE cooperative launch.  Per step t = T-1 .. 0:
+//     dh_t     = dout_t + (dgates_{t+1} . W_hh) * (1 - initial_{t+1})
+//     dgates_t = cell backward(dh_t, dc carry, gates_t, c_t, cprev_t)          (lstm.py:100 backward)
+// The recurrent product [B x 4U] . [4U x U] is split 2-D over KS x NS CTAs:
+//     K-slice i  = the 4 gate rows of the units [64 i, 64 i + 64)   (256 rows of W_hh)
+//     N-slice j  = the units [32 j, 32 j + 32)                       (32 columns of W_hh)
+// CTA (i, j) keeps its 256 x 32 block of W_hh in REGISTERS for the whole sequence as the B
+// fragments of 32 mma.sync.m16n8k8 (TF32, fp32 accumulate) per warp: warp w owns the 16 x 8 output
+// tile (batch rows 16 (w & 1).., columns 8 (w >> 1)..) over all 256 k.  Each step it
+//   (cell)  finishes dh for its (B x 32/KS) share of N-slice j from the KS partials of the previous
+//           product (fixed order), runs the cell backward keeping dc in a register, writes dgates_t;
+//   (sync)  grid barrier;
+//   (gemm)  stages dgates_t[:, K-slice i] (32 KB) in shared memory, multiplies, writes its
+//           partial [B x 32] to part[i];
+//   (sync)  grid barrier.
+// Exchange per step per CTA: 32 KB in + 4 KB out (+ 4 KB of partial reads), all L2-resident.
+// B == 32, U in {256, 512}; grid = (U/64) * (U/32) CTAs, all co-resident (cooperative launch).
+#pragma once
+#include <cstdint>
+
+namespace rtbptt {
+
+constexpr int THREADS = 256;
+constexpr int KROWS = 256;             // gate rows per K-slice (4 gates x 64 units)
+constexpr int DG_PITCH = KROWS + 4;    // padded row pitch of the staged dgates tile: conflict-free fragment loads
+
+struct Args {
+  const float* dout;       // (T*B, U)   d(loss)/d(h_t)
+  const float* gates;      // (T*B, 4U)  activated gates, column = gate * U + unit
+  const float* c_all;      // (T*B, U)
+  const float* cprev;      // (T*B, U)   masked carry-in cell state
+  const float* initials;   // (T*B)
+  const float* whh;        // (4U, U) row-major
+  float* dgates;           // (T*B, 4U)  out
+  float* part;             // (KS, B, U) scratch: partial products of the current step
+  unsigned int* counter;   // grid barrier, zeroed before the launch
+  int T, B, U;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(THREADS, 2) k_lstm_bptt_p(const Args a) {
+  extern __shared__ __align__(16) float dg_s[];   // [32][DG_PITCH]
+  const int U = a.U, B = a.B, T = a.T;
+  const int KS = U / 64, NS = U / 32;
+  const int i = blockIdx.x % KS;          // K-slice
+  const int j = blockIdx.x / KS;          // N-slice
+  (void)NS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int U4 = 4 * U;
+
+  // ---- resident W block as mma B fragments: k-step s covers slice rows kk = 8 s .. 8 s + 7
+  const int mi = warp & 1, ni = warp >> 1;
+  const int ncol = 32 * j + 8 * ni + (lane >> 2);           // this lane's output column (unit)
+  uint32_t wb[32][2];
+#pragma unroll
+  for (int s = 0; s < 32; ++s) {
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int kk = 8 * s + (lane & 3) + 4 * h2;           // row inside the slice
+      const int krow = (kk >> 6) * U + 64 * i + (kk & 63);  // gate * U + unit
+      wb[s][h2] = __float_as_uint(a.whh[(size_t)krow * U + ncol]);
+    }
+  }
+
+  // ---- cell ownership: (B x 32/KS) elements of N-slice j
+  const int upc = 32 / KS;                                   // units per CTA in the cell phase
+  const bool cell = tid < 32 * upc;
+  const int cb = tid & 31;                                   // batch row
+  const int cu = 32 * j + upc * i + (tid >> 5);              // unit
+  float dc_carry = 0.f;
+  unsigned int bar = 0;
+
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t ro = (size_t)t * B;
+    // ---------------- cell backward of step t
+    if (cell) {
+      const size_t e = (ro + cb) * U + cu;
+      const size_t g0 = (ro + cb) * U4 + cu;
+      const float gi = a.gates[g0], gf = a.gates[g0 + U], gg = a.gates[g0 + 2 * U], go = a.gates[g0 + 3 * U];
+      float dh = a.dout[e];
+      if (t < T - 1) {
+        float carry = 0.f;
+        for (int p = 0; p < KS; ++p) carry += __ldcg(a.part + ((size_t)p * B + cb) * U + cu);
+        dh += carry * (1.f - a.initials[ro + B + cb]);
+      }
+      const float tc = tanhf(a.c_all[e]);
+      const float dc = dc_carry + dh * go * (1.f - tc * tc);
+      a.dgates[g0] = dc * gg * gi * (1.f - gi);
+      a.dgates[g0 + U] = dc * a.cprev[e] * gf * (1.f - gf);
+      a.dgates[g0 + 2 * U] = dc * gi * (1.f - gg * gg);
+      a.dgates[g0 + 3 * U] = dh * tc * go * (1.f - go);
+      dc_carry = dc * gf * (1.f - a.initials[ro + cb]);
+    }
+    if (t == 0) break;
+    bar += gridDim.x;
+    grid_barrier(a.counter, bar);                            // dgates_t complete and visible
+
+    // ---------------- partial product: dgates_t[:, K-slice i] . W block
+    for (int v = tid; v < 32 * (KROWS / 4); v += THREADS) {
+      const int b = v / (KROWS / 4), kk = (v % (KROWS / 4)) * 4;
+      const float4 x = __ldcg(reinterpret_cast<const float4*>(
+          a.dgates + (ro + b) * U4 + (size_t)(kk >> 6) * U + 64 * i + (kk & 63)));
+      *reinterpret_cast<float4*>(dg_s + b * DG_PITCH + kk) = x;
+    }
+    __syncthreads();
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* arow0 = dg_s + (16 * mi + (lane >> 2)) * DG_PITCH + (lane & 3);
+    const float* arow1 = arow0 + 8 * DG_PITCH;
+#pragma unroll
+    for (int s = 0; s < 32; ++s) {
+      uint32_t af[4];
+      af[0] = __float_as_uint(arow0[8 * s]);
+      af[1] = __float_as_uint(arow1[8 * s]);
+      af[2] = __float_as_uint(arow0[8 * s + 4]);
+      af[3] = __float_as_uint(arow1[8 * s + 4]);
+      mma_tf32(d, af, wb[s][0], wb[s][1]);
+    }
+    {
+      const int b0 = 16 * mi + (lane >> 2);
+      const int n0 = 32 * j + 8 * ni + 2 * (lane & 3);
+      float* p0 = a.part + ((size_t)i * B + b0) * U + n0;
+      *reinterpret_cast<float2*>(p0) = make_float2(d[0], d[1]);
+      *reinterpret_cast<float2*>(p0 + (size_t)8 * U) = make_float2(d[2], d[3]);
+    }
+    bar += gridDim.x;
+    grid_barrier(a.counter, bar);                            // every partial of this step visible
+  }
+}
+
+}  // namespace rtbptt

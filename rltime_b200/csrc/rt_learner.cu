@@ -23,6 +23,7 @@
 #include "rt_kernels.cuh"
 #include "rt_gemm_tc.cuh"
 #include "rt_lstm_tc.cuh"
+#include "rt_bptt.cuh"
 
 namespace {
 
@@ -155,6 +156,7 @@ struct rt_learner {
   int conv_implicit = 1;
   int conv_implicit_bwd = 1;
   int conv_persistent = 1;
+  int bptt_persistent = 0;      // EXPERIMENTAL one-launch BPTT recurrence (RT_BPTT_PERSISTENT=1), not validated on hardware yet
   int conv_shallow = 1;         // shallow conv rings (2 CTAs/SM) inside the multi-branch phases (RT_CONV_SHALLOW; 2: backward too)
   int conv_dx_implicit = 1;
   std::vector<float*> conv_wt;  // re-laid filters for the data-gradient implicit GEMM (per layer, null for conv1)
@@ -1152,6 +1154,22 @@ int lstm_backward(rt_learner* h, cudaStream_t st, const float* net, const float*
   int U = h->U, Beff = rows / timesteps;
   float* G = h->grad;
   int nb = cdiv((size_t)Beff * U, 256);
+  const int bptt_ctas = (U / 64) * (U / 32);
+  const bool bptt_one_launch = h->bptt_persistent && h->gx.mode == 1 && Beff == 32 && (U == 512 || U == 256) &&
+                               bptt_ctas <= h->num_sms && (size_t)(U / 64) * Beff * U <= h->gx.ws_floats;
+  if (bptt_one_launch) {
+    // EXPERIMENTAL (rt_bptt.cuh, RT_BPTT_PERSISTENT=1): the whole recurrence in one cooperative launch
+    rtbptt::Args ba;
+    ba.dout = h->dfeatq; ba.gates = h->gates; ba.c_all = h->c_all; ba.cprev = h->cprev;
+    ba.initials = initials; ba.whh = net + h->o_whh; ba.dgates = h->dgates; ba.part = h->gx.ws;
+    ba.counter = h->grid_barrier; ba.T = timesteps; ba.B = Beff; ba.U = U;
+    RT_CUDA(cudaMemsetAsync(h->grid_barrier, 0, sizeof(unsigned int), st));
+    void* args[] = {(void*)&ba};
+    const size_t smem = (size_t)32 * rtbptt::DG_PITCH * sizeof(float);
+    RT_CUDA(cudaLaunchCooperativeKernel((void*)rtbptt::k_lstm_bptt_p, dim3(bptt_ctas), dim3(rtbptt::THREADS), args,
+                                        smem, st));
+    rt::launch_counter()++;
+  }
   RT_CUDA(cudaMemsetAsync(h->dc_carry, 0, (size_t)Beff * U * sizeof(float), st));
   // dh_carry = dgates[t+1] . W_hh is a skinny GEMM (M = B rows, K = 4U): it runs split-K over as
   // many CTAs as there are SMs and leaves the raw partials in the workspace; the cell kernel of
@@ -1159,7 +1177,7 @@ int lstm_backward(rt_learner* h, cudaStream_t st, const float* net, const float*
   const float* parts = nullptr;
   int nparts = 0;
   const size_t part_stride = (size_t)Beff * U;
-  for (int t = timesteps - 1; t >= 0; --t) {
+  for (int t = bptt_one_launch ? -1 : timesteps - 1; t >= 0; --t) {
     size_t ro = (size_t)t * Beff;
     rtk::k_lstm_cell_bwd<<<nb, 256, 0, st>>>(
         h->dfeatq + ro * U, parts, nparts, part_stride, h->dc_carry,
@@ -1541,6 +1559,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   if (const char* e = getenv("RT_OVERLAP_BWD")) h->overlap_bwd = atoi(e);
   if (const char* e = getenv("RT_OVERLAP_FWD")) h->overlap_fwd = atoi(e);
   if (const char* e = getenv("RT_CONV_SHALLOW")) h->conv_shallow = atoi(e);
+  if (const char* e = getenv("RT_BPTT_PERSISTENT")) h->bptt_persistent = atoi(e);
   for (auto& e : h->ev_side) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   RT_CUDA(cudaMallocHost(&h->h_stats, 8 * sizeof(float)));
   if (h->fused_hidden) {
