@@ -18,7 +18,7 @@ class SyntheticStream:
     def __init__(self, num_envs=32, frame_shape=(4, 84, 84), num_actions=6,
                  lstm_units=512, seed=1, done_mode="periodic", done_period=500,
                  done_p=0.01, pool=256, recurrent=True, env_id_base=0,
-                 clip_rewards=False):
+                 clip_rewards=False, pooled_state=False):
         self.num_envs = int(num_envs)
         self.frame_shape = tuple(frame_shape)
         self.num_actions = int(num_actions)
@@ -29,12 +29,17 @@ class SyntheticStream:
         self.done_p = float(done_p)
         self.env_id_base = env_id_base
         self.clip_rewards = clip_rewards
+        # pooled_state: hx / cx rows are views into a 256-row pool (a 1M-transition host-side
+        # reference then holds 1M references instead of 4 GB of LSTM states)
+        self.pooled_state = bool(pooled_state)
         rs = np.random.RandomState(seed)
         # Pooled frames: frame(g) = pool[g & (pool-1)] keeps a 1M-transition CPU
         # reference within RAM while the device gather cost is unchanged.
         assert pool & (pool - 1) == 0
         self.pool = rs.randint(0, 255, (pool,) + self.frame_shape).astype(np.uint8)
         self._rs = rs
+        self._state_pool = (np.random.RandomState(seed + 1000).randn(pool, self.lstm_units).astype(np.float32)
+                            if self.pooled_state and self.recurrent else None)
         self._step = 0          # vector steps taken
         self._count = 0         # transitions generated
         self._prev_done = np.ones(self.num_envs, dtype=bool)
@@ -63,9 +68,13 @@ class SyntheticStream:
             "env": envs.astype(np.int64) + self.env_id_base, "frame_idx": frame_idx,
             "reward": reward, "done": done, "action": action, "qvalues": qvalues,
         }
-        if self.recurrent:
+        if self.recurrent and self.pooled_state:
+            out["hx_idx"] = frame_idx
+            out["cx_idx"] = (frame_idx + 7) & (len(self.pool) - 1)
+        elif self.recurrent:
             out["hx"] = rs.randn(m, self.lstm_units).astype(np.float32)
             out["cx"] = rs.randn(m, self.lstm_units).astype(np.float32)
+        if self.recurrent:
             out["initials"] = self._prev_done[envs].astype(np.float32)
         self._prev_done[envs] = done
         self._count += m
@@ -86,8 +95,11 @@ class SyntheticStream:
         for i in range(len(a["env"])):
             state = {"x": self.pool[a["frame_idx"][i]], "layer0_state": {}}
             if self.recurrent:
-                state["layer1_state"] = {"hx": a["hx"][i], "cx": a["cx"][i],
-                                         "initials": a["initials"][i]}
+                if "hx_idx" in a:     # pooled: basic indexing = views of the pool rows
+                    hx, cx = self._state_pool[a["hx_idx"][i]], self._state_pool[a["cx_idx"][i]]
+                else:
+                    hx, cx = a["hx"][i], a["cx"][i]
+                state["layer1_state"] = {"hx": hx, "cx": cx, "initials": a["initials"][i]}
                 state["layer2_state"] = {}
             else:
                 state["layer1_state"] = {}
