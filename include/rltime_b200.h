@@ -197,7 +197,11 @@ typedef struct rt_learner_io {
 } rt_learner_io;
 
 #define RT_GEMM_FP32_SIMT 0     /* fp32 CUDA-core GEMM (parity reference path) */
-#define RT_GEMM_TF32_TCGEN05 1  /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM */
+#define RT_GEMM_TF32_TCGEN05 1  /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM; fp32 operands as they are in
+                                 * memory: the tensor core drops their low 13 mantissa bits (truncation) */
+#define RT_GEMM_TF32_RN 2       /* same kernels, but every forward operand is rounded to the NEAREST TF32 value by
+                                 * its producer (activations in the producing kernel's epilogue, weights in a shadow
+                                 * copy refreshed by the Adam pass): unbiased products, no extra pass over memory */
 
 #define RT_BUF_ONLINE 0
 #define RT_BUF_TARGET 1
@@ -220,6 +224,9 @@ int rt_learner_load_params(rt_learner* h, int32_t which, const float* const* ten
 int rt_learner_get_params(rt_learner* h, int32_t which, float* const* tensors);
 /* PolicyTrainer.sync_target -> TorchPolicy.copy_from (policy_trainer.py:68-70). */
 int rt_learner_sync_target(rt_learner* h, void* stream);
+/* Call after writing the online / target flat buffers (rt_learner_flat_buffer) directly, e.g. after a
+ * broadcast of the initial weights: refreshes the TF32 shadow copies of RT_GEMM_TF32_RN (no-op otherwise). */
+int rt_learner_params_changed(rt_learner* h, void* stream);
 /* TorchTrainer.set_lr (torch_trainer.py:149-151). */
 int rt_learner_set_lr(rt_learner* h, double lr);
 /* Optimizer step counter (Adam bias correction) and learning rate, for checkpoint / resume: the

@@ -48,7 +48,7 @@ class Batch(C.Structure):
 
 RT_MAX_CONV = 8
 RT_BUF_ONLINE, RT_BUF_TARGET, RT_BUF_GRAD, RT_BUF_ADAM_M, RT_BUF_ADAM_V = range(5)
-RT_GEMM_FP32_SIMT, RT_GEMM_TF32_TCGEN05 = 0, 1
+RT_GEMM_FP32_SIMT, RT_GEMM_TF32_TCGEN05, RT_GEMM_TF32_RN = 0, 1, 2
 
 
 class ModelDesc(C.Structure):
@@ -116,6 +116,7 @@ SIGNATURES = {
     "rt_learner_get_params": (C.c_int, [_VP, C.c_int32, _VP]),
     "rt_learner_sync_target": (C.c_int, [_VP, _VP]),
     "rt_learner_set_lr": (C.c_int, [_VP, C.c_double]),
+    "rt_learner_params_changed": (C.c_int, [_VP, _VP]),
     "rt_learner_step": (C.c_int, [_VP, C.POINTER(Batch), C.POINTER(LearnerIO), _VP, _VP]),
     "rt_learner_compute_grads": (C.c_int, [_VP, C.POINTER(Batch), C.POINTER(LearnerIO), _VP, _VP]),
     "rt_learner_apply_grads": (C.c_int, [_VP, C.c_double, _VP]),

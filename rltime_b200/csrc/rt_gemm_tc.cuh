@@ -163,7 +163,7 @@ __device__ __forceinline__ EpiWarp epi_begin(const EpiArgs& e, int lane, int row
            (e.raw || ((!e.mask || (((e.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.mask) & 15) == 0))) &&
                       (!e.bias || ((reinterpret_cast<uintptr_t>(e.bias) & 15) == 0)) &&
                       (!e.bias2 || ((reinterpret_cast<uintptr_t>(e.bias2) & 15) == 0))));
-  w.simple = w.fast && !e.raw && !e.mask && !e.accumulate && !e.round_tf32 && e.alpha == 1.f && !e.bias2 &&
+  w.simple = w.fast && !e.raw && !e.mask && !e.accumulate && e.alpha == 1.f && !e.bias2 &&
              w.rows_left >= 32;
   return w;
 }
@@ -191,7 +191,20 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const EpiWarp& 
     float* dptr = w.dst + (nb - w.n0);
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e.bias) b = __ldg(reinterpret_cast<const float4*>(e.bias + n));
-    if (e.relu) {
+    if (e.relu && e.round_tf32) {
+      // output feeds the next tensor-core product: store the nearest TF32 value (rtk::rna_tf32)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(dptr + i * w.row_step) =
+            make_float4(rtk::rna_tf32(fmaxf(t[i].x + b.x, 0.f)), rtk::rna_tf32(fmaxf(t[i].y + b.y, 0.f)),
+                        rtk::rna_tf32(fmaxf(t[i].z + b.z, 0.f)), rtk::rna_tf32(fmaxf(t[i].w + b.w, 0.f)));
+    } else if (e.round_tf32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(dptr + i * w.row_step) =
+            make_float4(rtk::rna_tf32(t[i].x + b.x), rtk::rna_tf32(t[i].y + b.y), rtk::rna_tf32(t[i].z + b.z),
+                        rtk::rna_tf32(t[i].w + b.w));
+    } else if (e.relu) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         *reinterpret_cast<float4*>(dptr + i * w.row_step) =

@@ -11,6 +11,16 @@
 
 namespace rtk {
 
+// fp32 -> nearest TF32 value (ties away), still an fp32 bit pattern.  tcgen05.mma.kind::tf32 reads
+// only the upper 19 bits of its operands, i.e. TRUNCATES them (a systematic shrink of every product
+// by ~3.5e-4 per operand); operands rounded here at their producer make the multiply an unbiased
+// round-to-nearest TF32 product instead (RT_GEMM_TF32_RN).
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+  return __uint_as_float(t);
+}
+
 // ------------------------------------------------------------------------------- GEMM
 // C[M,N] = epi( alpha * sum_k Aop[m,k] * Bop[k,n] )
 //   Aop[m,k] = transA ? A[k*lda+m] : A[m*lda+k]
@@ -139,17 +149,21 @@ __global__ void k_splitk_reduce(const __grid_constant__ GemmArgs g, int splits) 
 // (rltime/models/torch/modules/cnn.py:44-45).  One thread per pixel: the C channel planes are read
 // coalesced along W, the pixel's channels are written as one run (16 bytes at C = 4).
 __global__ void k_u8_nchw_to_f32_nhwc(const uint8_t* __restrict__ x, float* __restrict__ xf, size_t pixels,
-                                      int C, int HW, float scale) {
+                                      int C, int HW, float scale, int rn) {
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += (size_t)gridDim.x * blockDim.x) {
     size_t img = p / HW, hw = p - img * HW;
     const uint8_t* src = x + img * (size_t)C * HW + hw;
     float* dst = xf + p * C;
     if (C == 4) {
-      *reinterpret_cast<float4*>(dst) =
-          make_float4(__fmul_rn((float)src[0], scale), __fmul_rn((float)src[HW], scale),
-                      __fmul_rn((float)src[2 * (size_t)HW], scale), __fmul_rn((float)src[3 * (size_t)HW], scale));
+      float4 v = make_float4(__fmul_rn((float)src[0], scale), __fmul_rn((float)src[HW], scale),
+                             __fmul_rn((float)src[2 * (size_t)HW], scale), __fmul_rn((float)src[3 * (size_t)HW], scale));
+      if (rn) v = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+      *reinterpret_cast<float4*>(dst) = v;
     } else {
-      for (int c = 0; c < C; ++c) dst[c] = __fmul_rn((float)src[(size_t)c * HW], scale);
+      for (int c = 0; c < C; ++c) {
+        float v = __fmul_rn((float)src[(size_t)c * HW], scale);
+        dst[c] = rn ? rna_tf32(v) : v;
+      }
     }
   }
 }
@@ -337,17 +351,18 @@ __global__ void k_lstm_cell_bwd(const float* __restrict__ dout, const float* __r
 
 // ------------------------------------------------------------------------------- IQN
 // cos(pi * i * tau), i = 1..E   (rltime/policies/torch/iqn.py:91-93)
-__global__ void k_cos_features(const float* __restrict__ tau, float* __restrict__ cf, int rows, int E) {
+__global__ void k_cos_features(const float* __restrict__ tau, float* __restrict__ cf, int rows, int E, int rn) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)rows * E) return;
   int i = (int)(idx % E);
   float t = tau[idx / E];
-  cf[idx] = cosf(__fmul_rn(__fmul_rn((float)(i + 1), 3.14159274101257324f), t));
+  float v = cosf(__fmul_rn(__fmul_rn((float)(i + 1), 3.14159274101257324f), t));
+  cf[idx] = rn ? rna_tf32(v) : v;
 }
 
 // xq[r,d] = x[r / Nq, d] * phi[r,d]      (iqn.py:84, 99-100); D % 4 == 0
 __global__ void k_quantile_mul(const float* __restrict__ x, const float* __restrict__ phi,
-                               float* __restrict__ xq, size_t rowsq, int D, int Nq) {
+                               float* __restrict__ xq, size_t rowsq, int D, int Nq, int rn) {
   const int D4 = D >> 2;
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rowsq * D4) return;
@@ -355,7 +370,9 @@ __global__ void k_quantile_mul(const float* __restrict__ x, const float* __restr
   int d4 = (int)(idx - r * D4);
   float4 a = reinterpret_cast<const float4*>(x + (r / Nq) * D)[d4];
   float4 p = reinterpret_cast<const float4*>(phi + r * D)[d4];
-  reinterpret_cast<float4*>(xq + r * D)[d4] = make_float4(a.x * p.x, a.y * p.y, a.z * p.z, a.w * p.w);
+  float4 v = make_float4(a.x * p.x, a.y * p.y, a.z * p.z, a.w * p.w);
+  if (rn) v = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+  reinterpret_cast<float4*>(xq + r * D)[d4] = v;
 }
 
 // dphi_pre[r,d] = dxq[r,d] * x[m,d] * (phi > 0);  dx[m,d] = sum_q dxq[m*Nq+q, d] * phi[m*Nq+q, d]
@@ -942,20 +959,57 @@ __global__ void k_gradnorm_final(const double* __restrict__ part, int parts, flo
 }
 // torch.optim.Adam single-tensor math (torch_trainer.py:82-83,199): one pass over the flat
 // parameter / gradient / moment buffers: 16 B read + 12 B written per parameter.
-__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                       float* __restrict__ v, size_t n, const float* __restrict__ stats, float lr,
-                       float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
-  float coef = stats[3] * grad_scale;
-  float step_size = lr / bc1;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+// The flat buffers are 256-byte aligned and padded to 64 floats, so the pass runs on float4s.
+// `shadow` (optional): the copy of the parameters the tensor-core kernels read: tensors flagged in
+// `wflag` (one byte per 64-float block: 1 = operand of a GEMM-shaped kernel) rounded to the nearest
+// TF32 value, everything else (biases, the SIMT head layers) verbatim.
+__device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, float coef, float step_size,
+                                          float b1, float b2, float eps, float bc2_sqrt) {
+  float gi = g * coef;
+  float mi = m + (gi - m) * (1.f - b1);       // exp_avg.lerp_(grad, 1 - beta1)
+  float vi = v * b2 + (1.f - b2) * gi * gi;
+  float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p = p - step_size * (mi / denom);
+  m = mi;
+  v = vi;
+  return p;
+}
+__global__ void __launch_bounds__(256)
+k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+       float* __restrict__ v, size_t n, const float* __restrict__ stats, float lr,
+       float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale,
+       float* __restrict__ shadow, const uint8_t* __restrict__ wflag) {
+  const float coef = stats[3] * grad_scale;
+  const float step_size = lr / bc1;
+  const size_t n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (size_t)gridDim.x * blockDim.x) {
-    float gi = g[i] * coef;
-    float mi = m[i] + (gi - m[i]) * (1.f - b1);       // exp_avg.lerp_(grad, 1 - beta1)
-    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
-    float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - step_size * (mi / denom);
-    m[i] = mi;
-    v[i] = vi;
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = g4[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, coef, step_size, b1, b2, eps, bc2_sqrt);
+    adam_one(pp.y, gg.y, mm.y, vv.y, coef, step_size, b1, b2, eps, bc2_sqrt);
+    adam_one(pp.z, gg.z, mm.z, vv.z, coef, step_size, b1, b2, eps, bc2_sqrt);
+    adam_one(pp.w, gg.w, mm.w, vv.w, coef, step_size, b1, b2, eps, bc2_sqrt);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    if (shadow) {
+      if (wflag[i >> 4]) pp = make_float4(rna_tf32(pp.x), rna_tf32(pp.y), rna_tf32(pp.z), rna_tf32(pp.w));
+      reinterpret_cast<float4*>(shadow)[i] = pp;
+    }
+  }
+}
+// shadow = wflag ? rna_tf32(p) : p over the whole flat buffer (parameter load / target sync)
+__global__ void k_shadow_params(const float* __restrict__ p, float* __restrict__ shadow,
+                                const uint8_t* __restrict__ wflag, size_t n) {
+  const size_t n4 = n >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<const float4*>(p)[i];
+    if (wflag[i >> 4]) pp = make_float4(rna_tf32(pp.x), rna_tf32(pp.y), rna_tf32(pp.z), rna_tf32(pp.w));
+    reinterpret_cast<float4*>(shadow)[i] = pp;
   }
 }
 

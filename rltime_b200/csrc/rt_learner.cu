@@ -82,6 +82,7 @@ struct PInfo {
   size_t off, count;
   int perm;
   int conv_c = 0, conv_k = 0;  // PERM_CONV geometry
+  bool gemm_w = false;         // weight operand of a GEMM-shaped (tensor-core) kernel: TF32-rounded in the shadow copy
 };
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -113,6 +114,12 @@ struct rt_learner {
   size_t o_wih = 0, o_whh = 0, o_bih = 0, o_bhh = 0, o_fcw = 0, o_fcb = 0, o_outw = 0, o_outb = 0,
          o_vhw = 0, o_vhb = 0, o_vw = 0, o_vb = 0, o_qw = 0, o_qb = 0;
   float* p[2] = {nullptr, nullptr};  // 0 online, 1 target
+  // RT_GEMM_TF32_RN: what the kernels read.  pr[i] == p[i] unless rn, in which case it is a shadow of
+  // p[i] with every GEMM weight rounded to the nearest TF32 value (biases / SIMT head layers verbatim),
+  // refreshed by the Adam pass, parameter loads and target syncs.
+  float* pr[2] = {nullptr, nullptr};
+  int rn = 0;
+  uint8_t* wflag = nullptr;          // one byte per 64-float block of the flat buffer: 1 = GEMM weight
   float* grad = nullptr;
   float* adam_m = nullptr;
   float* adam_v = nullptr;
@@ -532,9 +539,10 @@ int grid1d(size_t n, int threads = 256) {
 }
 
 // uint8 NCHW frames (the replay batch) -> fp32 NHWC * (1/255) (cnn.py:44-45), once per pass
-int launch_frames_to_nhwc(cudaStream_t st, const uint8_t* x, float* xf, int rows, int C, int H, int W, float scale) {
+int launch_frames_to_nhwc(cudaStream_t st, const uint8_t* x, float* xf, int rows, int C, int H, int W, float scale,
+                          int rn) {
   size_t pixels = (size_t)rows * H * W;
-  rtk::k_u8_nchw_to_f32_nhwc<<<grid1d(pixels), 256, 0, st>>>(x, xf, pixels, C, H * W, scale);
+  rtk::k_u8_nchw_to_f32_nhwc<<<grid1d(pixels), 256, 0, st>>>(x, xf, pixels, C, H * W, scale, rn);
   RT_LAUNCH_CHECK();
   return RT_OK;
 }
@@ -606,7 +614,7 @@ int conv_forward_tc(rt_learner* h, GemmCtx& cx, cudaStream_t st, const float* ne
   a.C = L.cin; a.H = L.hin; a.W = L.win; a.KH = L.k; a.S = L.s; a.OH = L.hout; a.OW = L.wout;
   a.M = rows * L.hout * L.wout; a.N = L.f; a.K = L.K;
   a.scale = (float)(1.0 / 255.0);
-  a.round_tf32 = cx.round_tf32;
+  a.round_tf32 = cx.round_tf32 || h->rn;   // the output is the A operand of the next layer's product
   const int BN = L.f <= 32 ? 32 : (L.f <= 64 ? 64 : 128);
   const CUtensorMap* tb = nullptr;
   RT_TRY(get_tmap(cx, net + L.w, L.K, L.f, L.K, rttc::BLOCK_K, BN, 0, &tb));
@@ -748,7 +756,7 @@ bool cnn_all_implicit(const rt_learner* h) {
 int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows,
                 const float* xf_pre = nullptr, bool second = false) {
   if (!xf_pre)
-    RT_TRY(launch_frames_to_nhwc(st, x, h->xf, rows, h->md.in_c, h->md.in_h, h->md.in_w, (float)(1.0 / 255.0)));
+    RT_TRY(launch_frames_to_nhwc(st, x, h->xf, rows, h->md.in_c, h->md.in_h, h->md.in_w, (float)(1.0 / 255.0), h->rn));
   const float* xf = xf_pre ? xf_pre : h->xf;
   {
     bool all = true;
@@ -910,6 +918,7 @@ int lstm_run(rt_learner* h, cudaStream_t st, const SeqDesc* seqs, int nseq, int 
   if (ok) {
     a.T = timesteps; a.B = Beff; a.U = U;
     if (const char* e = getenv("RT_LSTM_EXP")) a.exp = atoi(e);
+    a.rn = h->rn;
     a.xchg = h->lstm_xchg;
     a.counters = h->grid_barrier;
     a.dbg = h->lstm_dbg;
@@ -977,13 +986,13 @@ int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float*
   rtk::GemmArgs g;
   const float* xq = feat;     // DQN: the heads read the trunk output directly
   if (!h->dqn) {
-    rtk::k_cos_features<<<cdiv(MQ * E, 256), 256, 0, st>>>(tau, hs.cf, (int)MQ, E);
+    rtk::k_cos_features<<<cdiv(MQ * E, 256), 256, 0, st>>>(tau, hs.cf, (int)MQ, E, h->rn);
     RT_LAUNCH_CHECK();
     g = mk(hs.cf, E, 0, net + h->o_qw, E, 1, hs.phi, D, (int)MQ, D, E);
     g.bias = net + h->o_qb;
     g.relu = 1;
     RT_TRY(gemm(*hs.gx, st, g));
-    rtk::k_quantile_mul<<<cdiv(MQ * (D / 4), 256), 256, 0, st>>>(feat, hs.phi, hs.xq, MQ, D, Nq);
+    rtk::k_quantile_mul<<<cdiv(MQ * (D / 4), 256), 256, 0, st>>>(feat, hs.phi, hs.xq, MQ, D, Nq, h->rn);
     RT_LAUNCH_CHECK();
     xq = hs.xq;
   }
@@ -1304,9 +1313,10 @@ int apply_grads(rt_learner* h, cudaStream_t st, float grad_scale) {
     double b1 = 0.9, b2 = 0.999;
     float bc1 = (float)(1.0 - std::pow(b1, (double)h->adam_t));
     float bc2s = (float)std::sqrt(1.0 - std::pow(b2, (double)h->adam_t));
-    rtk::k_adam<<<grid1d(h->nparams), 256, 0, st>>>(h->p[0], h->grad, h->adam_m, h->adam_v, h->nparams,
-                                                   h->stats, h->lr, (float)b1, (float)b2,
-                                                   (float)h->td.adam_epsilon, bc1, bc2s, grad_scale);
+    rtk::k_adam<<<grid1d(h->nparams / 4), 256, 0, st>>>(h->p[0], h->grad, h->adam_m, h->adam_v, h->nparams,
+                                                       h->stats, h->lr, (float)b1, (float)b2,
+                                                       (float)h->td.adam_epsilon, bc1, bc2s, grad_scale,
+                                                       h->rn ? h->pr[0] : nullptr, h->wflag);
     RT_LAUNCH_CHECK();
     return RT_OK;
 }
@@ -1379,6 +1389,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     char nm[96];
     snprintf(nm, sizeof(nm), "model.layers.0.layers.%d.weight", i);
     L.w = add_param(h, nm, {L.f, c, L.k, L.k}, PERM_CONV, c, L.k);
+    h->pinfo.back().gemm_w = true;
     snprintf(nm, sizeof(nm), "model.layers.0.layers.%d.bias", i);
     L.b = add_param(h, nm, {L.f}, PERM_NONE);
     h->conv.push_back(L);
@@ -1390,7 +1401,9 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   if (h->U) {
     int U = h->U;
     h->o_wih = add_param(h, "model.layers.1.lstm_cell.weight_ih", {4 * U, h->feat}, PERM_FEAT_COLS);
+    h->pinfo.back().gemm_w = true;
     h->o_whh = add_param(h, "model.layers.1.lstm_cell.weight_hh", {4 * U, U}, PERM_NONE);
+    h->pinfo.back().gemm_w = true;
     h->o_bih = add_param(h, "model.layers.1.lstm_cell.bias_ih", {4 * U}, PERM_NONE);
     h->o_bhh = add_param(h, "model.layers.1.lstm_cell.bias_hh", {4 * U}, PERM_NONE);
     h->D = U;
@@ -1411,6 +1424,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     char nm[96];
     snprintf(nm, sizeof(nm), "model.layers.%d.layers.0.0.weight", fc_layer);
     h->o_fcw = add_param(h, nm, {h->F, h->D}, featperm_cols, 0, 0, fw);
+    h->pinfo.back().gemm_w = true;
     snprintf(nm, sizeof(nm), "model.layers.%d.layers.0.0.bias", fc_layer);
     h->o_fcb = add_param(h, nm, {h->F}, PERM_NONE, 0, 0, fb);
   }
@@ -1419,6 +1433,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   if (h->dueling) {
     h->o_vhw = add_param(h, "value_hidden_layer.weight", {h->F, h->D}, featperm_cols, 0, 0,
                          h->fused_hidden ? fw + (long long)h->F * h->D : -1);
+    h->pinfo.back().gemm_w = true;
     h->o_vhb = add_param(h, "value_hidden_layer.bias", {h->F}, PERM_NONE, 0, 0,
                          h->fused_hidden ? fb + h->F : -1);
     h->o_vw = add_param(h, "value_layer.weight", {1, h->F}, PERM_NONE);
@@ -1426,12 +1441,27 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   }
   if (!h->dqn) {
     h->o_qw = add_param(h, "quantile_layer.weight", {h->D, h->E}, featperm_rows);
+    h->pinfo.back().gemm_w = true;
     h->o_qb = add_param(h, "quantile_layer.bias", {h->D}, featperm_rows);
   }
   h->nparams = (h->nparams + 63) / 64 * 64;
 
   RT_TRY(dalloc(h, &h->p[0], h->nparams, "params_online"));
   RT_TRY(dalloc(h, &h->p[1], h->nparams, "params_target"));
+  RT_REQUIRE(td->gemm_mode >= RT_GEMM_FP32_SIMT && td->gemm_mode <= RT_GEMM_TF32_RN, "bad gemm_mode %d", td->gemm_mode);
+  h->rn = td->gemm_mode == RT_GEMM_TF32_RN;
+  h->pr[0] = h->p[0];
+  h->pr[1] = h->p[1];
+  if (h->rn) {
+    RT_TRY(dalloc(h, &h->pr[0], h->nparams, "params_online_tf32"));
+    RT_TRY(dalloc(h, &h->pr[1], h->nparams, "params_target_tf32"));
+    std::vector<uint8_t> flags(h->nparams / 64, 0);
+    for (const PInfo& pi : h->pinfo)
+      if (pi.gemm_w)
+        for (size_t b = pi.off / 64; b <= (pi.off + pi.count - 1) / 64; ++b) flags[b] = 1;
+    RT_TRY(dalloc(h, &h->wflag, flags.size()));
+    RT_CUDA(cudaMemcpy(h->wflag, flags.data(), flags.size(), cudaMemcpyHostToDevice));
+  }
   RT_TRY(dalloc(h, &h->grad, h->nparams, "grad"));
   RT_TRY(dalloc(h, &h->adam_m, h->nparams, "adam_m"));
   RT_TRY(dalloc(h, &h->adam_v, h->nparams, "adam_v"));
@@ -1578,7 +1608,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_TRY(dalloc(h, &h->gx2.ws, h->gx2.ws_floats));
   h->gx3.ws_floats = (size_t)1 << 20;   // heads forward GEMMs never split
   RT_TRY(dalloc(h, &h->gx3.ws, h->gx3.ws_floats));
-  h->gx.mode = td->gemm_mode;
+  h->gx.mode = td->gemm_mode == RT_GEMM_FP32_SIMT ? 0 : 1;
   if (const char* e = getenv("RT_TC_BN")) h->gx.force_bn = atoi(e);
   if (const char* e = getenv("RT_TC_STAGES")) h->gx.force_stages = atoi(e);
   if (const char* e = getenv("RT_TC_PERSISTENT")) h->gx.persistent = atoi(e);
@@ -1697,6 +1727,11 @@ int rt_learner_load_params(rt_learner* h, int32_t which, const float* const* ten
     for (size_t j = 0; j < pi.count; ++j) flat[pi.off + perm_index(h, pi, j)] = tensors[i][j];
   }
   RT_CUDA(cudaMemcpy(dst, flat.data(), h->nparams * sizeof(float), cudaMemcpyHostToDevice));
+  if (h->rn && (which == RT_BUF_ONLINE || which == RT_BUF_TARGET)) {
+    rtk::k_shadow_params<<<grid1d(h->nparams / 4), 256, 0, 0>>>(h->p[which], h->pr[which], h->wflag, h->nparams);
+    RT_LAUNCH_CHECK();
+    RT_CUDA(cudaDeviceSynchronize());
+  }
   return RT_OK;
 }
 
@@ -1721,6 +1756,21 @@ int rt_learner_sync_target(rt_learner* h, void* stream) {
   // TorchPolicy.copy_from with factor 1.0 (torch_policy.py:61-68): one flat copy
   RT_CUDA(cudaMemcpyAsync(h->p[1], h->p[0], h->nparams * sizeof(float), cudaMemcpyDeviceToDevice,
                           (cudaStream_t)stream));
+  if (h->rn)
+    RT_CUDA(cudaMemcpyAsync(h->pr[1], h->pr[0], h->nparams * sizeof(float), cudaMemcpyDeviceToDevice,
+                            (cudaStream_t)stream));
+  return RT_OK;
+}
+
+int rt_learner_params_changed(rt_learner* h, void* stream) {
+  RT_REQUIRE(h, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  if (!h->rn) return RT_OK;
+  for (int w = 0; w < 2; ++w) {
+    rtk::k_shadow_params<<<grid1d(h->nparams / 4), 256, 0, (cudaStream_t)stream>>>(h->p[w], h->pr[w], h->wflag,
+                                                                                 h->nparams);
+    RT_LAUNCH_CHECK();
+  }
   return RT_OK;
 }
 
@@ -1848,7 +1898,7 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       for (int pass = 0; pass < 1 + rnn_boot; ++pass) {
         int row0 = pass == 0 ? 0 : n;
         StateView sv = view(row0);
-        RT_TRY(trunk_forward(h, st, h->p[pass], sv, P * B, P, &feat));
+        RT_TRY(trunk_forward(h, st, h->pr[pass], sv, P * B, P, &feat));
         StateView dst = view(row0 + P);
         size_t last = (size_t)(P - 1) * B * U;
         k_store_state<<<cdiv((size_t)B * U, 256), 256, 0, st>>>(h->h_all + last, h->c_all + last,
@@ -1874,32 +1924,32 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
         // the target pass (rows [n, T+n)) and the online pass (rows [0, T+n)) read the same frames:
         // convert them to fp32 NHWC once
         RT_TRY(launch_frames_to_nhwc(st, svt.x, h->xf, M + n * B, h->md.in_c, h->md.in_h, h->md.in_w,
-                                     (float)(1.0 / 255.0)));
+                                     (float)(1.0 / 255.0), h->rn));
         if (fork_fwd) {
           SideCtx sd;
           RT_TRY(side_begin(h, st, &sd));
-          RT_TRY(cnn_forward(h, sd.st, h->p[1], sv.x, M, h->xf + (size_t)n * B * frame, true));
-          RT_TRY(lstm_xgates(h, sd.st, h->p[1], h->c_out2.back(), M, h->xg2, sd.gx));
+          RT_TRY(cnn_forward(h, sd.st, h->pr[1], sv.x, M, h->xf + (size_t)n * B * frame, true));
+          RT_TRY(lstm_xgates(h, sd.st, h->pr[1], h->c_out2.back(), M, h->xg2, sd.gx));
         } else {
-          RT_TRY(cnn_forward(h, st, h->p[1], sv.x, M, h->xf + (size_t)n * B * frame));
-          RT_TRY(lstm_xgates(h, st, h->p[1], h->c_out.back(), M, h->xg2));
+          RT_TRY(cnn_forward(h, st, h->pr[1], sv.x, M, h->xf + (size_t)n * B * frame));
+          RT_TRY(lstm_xgates(h, st, h->pr[1], h->c_out.back(), M, h->xg2));
         }
       } else {
-        RT_TRY(cnn_forward(h, st, h->p[1], sv.x, M));
-        RT_TRY(lstm_xgates(h, st, h->p[1], h->c_out.back(), M, h->xg2));
+        RT_TRY(cnn_forward(h, st, h->pr[1], sv.x, M));
+        RT_TRY(lstm_xgates(h, st, h->pr[1], h->c_out.back(), M, h->xg2));
       }
       SeqDesc seqs[3];
       int ns = 0;
-      seqs[ns++] = SeqDesc{h->p[1], h->xg2, sv.hx, sv.cx, sv.initials, h->h_all2, 1, false};
+      seqs[ns++] = SeqDesc{h->pr[1], h->xg2, sv.hx, sv.cx, sv.initials, h->h_all2, 1, false};
       if (h->td.double_q) {
-        RT_TRY(cnn_forward(h, st, h->p[0], svt.x, M + n * B, h->xf));
-        RT_TRY(lstm_xgates(h, st, h->p[0], h->c_out.back(), M + n * B, h->xg));
-        seqs[ns++] = SeqDesc{h->p[0], h->xg + (size_t)n * B * 4 * U, sv.hx, sv.cx, sv.initials, h->h_all3, 2, false};
+        RT_TRY(cnn_forward(h, st, h->pr[0], svt.x, M + n * B, h->xf));
+        RT_TRY(lstm_xgates(h, st, h->pr[0], h->c_out.back(), M + n * B, h->xg));
+        seqs[ns++] = SeqDesc{h->pr[0], h->xg + (size_t)n * B * 4 * U, sv.hx, sv.cx, sv.initials, h->h_all3, 2, false};
       } else {
-        RT_TRY(cnn_forward(h, st, h->p[0], svt.x, M));
-        RT_TRY(lstm_xgates(h, st, h->p[0], h->c_out.back(), M, h->xg));
+        RT_TRY(cnn_forward(h, st, h->pr[0], svt.x, M));
+        RT_TRY(lstm_xgates(h, st, h->pr[0], h->c_out.back(), M, h->xg));
       }
-      seqs[ns++] = SeqDesc{h->p[0], h->xg, svt.hx, svt.cx, svt.initials, h->h_all, 0, true};
+      seqs[ns++] = SeqDesc{h->pr[0], h->xg, svt.hx, svt.cx, svt.initials, h->h_all, 0, true};
       if (fork_fwd) RT_TRY(side_join(h, st));
       RT_TRY(lstm_run(h, st, seqs, ns, T, B));
       if (fork_fwd) {
@@ -1908,22 +1958,22 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
         SideCtx sd;
         RT_TRY(side_begin(h, st, &sd));
         const HeadSet hs2 = second_set(h, h->tq);
-        RT_TRY(heads_forward(h, sd.st, h->p[1], h->h_all2, M, tau_seg[0], &hs2));
+        RT_TRY(heads_forward(h, sd.st, h->pr[1], h->h_all2, M, tau_seg[0], &hs2));
         // ... and the selection pass on a third branch with its own set
         RT_CUDA(cudaEventRecord(h->ev_side_b[0], st));
         RT_CUDA(cudaStreamWaitEvent(h->side_b, h->ev_side_b[0], 0));
         const HeadSet hs_sel = third_set(h, h->sq);
-        RT_TRY(heads_forward(h, h->side_b, h->p[0], h->h_all3, M, tau_seg[1], &hs_sel));
-        RT_TRY(heads_forward(h, st, h->p[0], h->h_all, M, tau_seg[2]));
+        RT_TRY(heads_forward(h, h->side_b, h->pr[0], h->h_all3, M, tau_seg[1], &hs_sel));
+        RT_TRY(heads_forward(h, st, h->pr[0], h->h_all, M, tau_seg[2]));
         RT_CUDA(cudaEventRecord(h->ev_side_b[1], h->side_b));
         RT_CUDA(cudaStreamWaitEvent(st, h->ev_side_b[1], 0));
         RT_TRY(side_join(h, st));
         train_heads_done = true;
       } else {
-        RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[0]));
+        RT_TRY(heads_forward(h, st, h->pr[1], h->h_all2, M, tau_seg[0]));
         RT_CUDA(cudaMemcpyAsync(h->tq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        if (h->td.double_q) RT_TRY(heads_forward(h, st, h->p[0], h->h_all3, M, tau_seg[1]));
-        else RT_TRY(heads_forward(h, st, h->p[1], h->h_all2, M, tau_seg[1]));
+        if (h->td.double_q) RT_TRY(heads_forward(h, st, h->pr[0], h->h_all3, M, tau_seg[1]));
+        else RT_TRY(heads_forward(h, st, h->pr[1], h->h_all2, M, tau_seg[1]));
         RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
       }
       size_t off = (size_t)P * B;
@@ -1935,25 +1985,25 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
     } else {
       StateView sv = view(P + n);
       int ts = rnn_boot ? T : 1;
-      RT_TRY(trunk_forward(h, st, h->p[1], sv, M, ts, &feat));
-      RT_TRY(heads_forward(h, st, h->p[1], feat, M, tau_seg[0]));
+      RT_TRY(trunk_forward(h, st, h->pr[1], sv, M, ts, &feat));
+      RT_TRY(heads_forward(h, st, h->pr[1], feat, M, tau_seg[0]));
       RT_CUDA(cudaMemcpyAsync(h->tq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
       if (!h->td.double_q) {
         // same network, same states: only the quantile fractions differ -> reuse the whole trunk
-        RT_TRY(heads_forward(h, st, h->p[1], feat, M, tau_seg[1]));
+        RT_TRY(heads_forward(h, st, h->pr[1], feat, M, tau_seg[1]));
       } else {
         // online net on target_states = rows [n, T+n) of the stack; the training forward below
         // needs rows [0, T): run the online CNN ONCE over the T+n distinct rows and let both
         // passes read their slice (saves (T-n)/(2T) of the online conv work)
         StateView s0 = view(P);
-        RT_TRY(cnn_forward(h, st, h->p[0], s0.x, M + n * B));
+        RT_TRY(cnn_forward(h, st, h->pr[0], s0.x, M + n * B));
         shared_cnn = true;
         const float* f = h->c_out.back() + (size_t)n * B * h->feat;
         if (U) {
-          RT_TRY(lstm_forward(h, st, h->p[0], f, M, ts, sv.hx, sv.cx, sv.initials));
+          RT_TRY(lstm_forward(h, st, h->pr[0], f, M, ts, sv.hx, sv.cx, sv.initials));
           f = h->h_all;
         }
-        RT_TRY(heads_forward(h, st, h->p[0], f, M, tau_seg[1]));
+        RT_TRY(heads_forward(h, st, h->pr[0], f, M, tau_seg[1]));
       }
       RT_CUDA(cudaMemcpyAsync(h->sq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
       size_t off = (size_t)P * B;
@@ -1966,15 +2016,15 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       if (shared_cnn) {
         feat = h->c_out.back();
         if (U) {
-          RT_TRY(lstm_forward(h, st, h->p[0], feat, M, T, svt.hx, svt.cx, svt.initials));
+          RT_TRY(lstm_forward(h, st, h->pr[0], feat, M, T, svt.hx, svt.cx, svt.initials));
           feat = h->h_all;
         }
       } else {
-        RT_TRY(trunk_forward(h, st, h->p[0], svt, M, T, &feat));
+        RT_TRY(trunk_forward(h, st, h->pr[0], svt, M, T, &feat));
       }
     }
     // ---- training heads + loss (iqn.py:54-129)
-    if (!train_heads_done) RT_TRY(heads_forward(h, st, h->p[0], feat, M, tau_seg[2]));
+    if (!train_heads_done) RT_TRY(heads_forward(h, st, h->pr[0], feat, M, tau_seg[2]));
     RT_CUDA(cudaMemcpyAsync(h->tau, tau_seg[2], (size_t)h->MQ * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (h->dqn) {
       rtk::k_dqn_loss<<<cdiv(M, 128), 128, 0, st>>>(h->q, h->targets, actions, weights, h->dtheta, h->row_loss,
@@ -2005,10 +2055,10 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
     struct Off { rt_learner* h; ~Off() { h->side_active = false; } } off{h};
     if (part != 2) {
       RT_CUDA(cudaMemsetAsync(h->grad, 0, h->nparams * sizeof(float), st));
-      RT_TRY(heads_backward(h, st, h->p[0], feat, M, actions));
-      if (U) RT_TRY(lstm_backward(h, st, h->p[0], h->c_out.back(), M, T, svt.initials));
+      RT_TRY(heads_backward(h, st, h->pr[0], feat, M, actions));
+      if (U) RT_TRY(lstm_backward(h, st, h->pr[0], h->c_out.back(), M, T, svt.initials));
     }
-    if (part != 1) RT_TRY(cnn_backward(h, st, h->p[0], svt.x, M, U ? h->dfeat : h->dfeatq));
+    if (part != 1) RT_TRY(cnn_backward(h, st, h->pr[0], svt.x, M, U ? h->dfeat : h->dfeatq));
     return side_join(h, st);
   };
   auto backward_phase = [&]() -> int { return backward_part(0); };
@@ -2130,7 +2180,7 @@ int rt_learner_act(rt_learner* h, int32_t E, const uint8_t* x, const float* hx, 
   sv.cx = const_cast<float*>(cx);
   sv.initials = initials;
   const float* feat = nullptr;
-  RT_TRY(trunk_forward(h, st, h->p[0], sv, E, 1, &feat));
+  RT_TRY(trunk_forward(h, st, h->pr[0], sv, E, 1, &feat));
   size_t nq = (size_t)E * h->Nq;
   if (taus_host) {
     RT_CUDA(cudaMemcpyAsync(h->tau_stage, taus_host, nq * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -2139,7 +2189,7 @@ int rt_learner_act(rt_learner* h, int32_t E, const uint8_t* x, const float* hx, 
     RT_LAUNCH_CHECK();
     h->rng_counter += nq;
   }
-  RT_TRY(heads_forward(h, st, h->p[0], feat, E, h->tau_stage));
+  RT_TRY(heads_forward(h, st, h->pr[0], feat, E, h->tau_stage));
   rtk::k_quantile_mean<<<cdiv((size_t)E * h->A, 128), 128, 0, st>>>(h->q, qvalues, E, h->Nq, h->A);
   RT_LAUNCH_CHECK();
   if (h->U) {

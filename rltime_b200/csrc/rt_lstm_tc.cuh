@@ -52,6 +52,7 @@ struct LstmTcArgs {
   int nseq[2];
   int T, B, U;
   int exp;                 // tuning experiments: 1 = skip the MMAs, 2 = skip the per-step loads
+  int rn;                  // round every h that becomes an MMA operand to the nearest TF32 value
   int arows;               // 32 * max sequences per group: rows per k-block of the A operand
   float* xchg;             // exchange buffer: [2 groups][T][U/32][arows][32] floats, swizzled
   unsigned int* counters;  // one per group, 32 words apart, zeroed before the launch
@@ -213,6 +214,7 @@ k_lstm_seq_tc(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ 
             float4 h4 = *reinterpret_cast<const float4*>(sq.hx + (size_t)b * U + u0 + j);
             float4 c4 = *reinterpret_cast<const float4*>(sq.cx + (size_t)b * U + u0 + j);
             h4 = make_float4(h4.x * keep0, h4.y * keep0, h4.z * keep0, h4.w * keep0);
+            if (a.rn) h4 = make_float4(rtk::rna_tf32(h4.x), rtk::rna_tf32(h4.y), rtk::rna_tf32(h4.z), rtk::rna_tf32(h4.w));
             *reinterpret_cast<float4*>(xg_ + xchg_off(a.arows, r, u0 + j)) = h4;
             if (sq.hprev) *reinterpret_cast<float4*>(sq.hprev + (size_t)b * U + u0 + j) = h4;
             c[j] = c4.x; c[j + 1] = c4.y; c[j + 2] = c4.z; c[j + 3] = c4.w;
@@ -275,6 +277,7 @@ k_lstm_seq_tc(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ 
             c[j] = cn;
             cpv[j] = cp;
             hv[j] = go * fast_tanh(cn);
+            if (a.rn) hv[j] = rtk::rna_tf32(hv[j]);   // h_t feeds the next step's MMA and the heads GEMMs
             xin[j] = gi; xin[UPC + j] = gf; xin[2 * UPC + j] = gg; xin[3 * UPC + j] = go;
           }
           // exchange block of step t+1 first: it is on the critical path of every CTA

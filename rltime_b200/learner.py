@@ -65,8 +65,13 @@ class DeviceLearner:
         td.adam_epsilon = adam_epsilon
         td.lr = lr
         td.seed = seed
-        assert gemm in ("fp32", "tf32")
-        td.gemm_mode = _lib.RT_GEMM_TF32_TCGEN05 if gemm == "tf32" else _lib.RT_GEMM_FP32_SIMT
+        # "tf32": tcgen05 TF32 products on operands rounded to nearest at their producers (default);
+        # "tf32_trunc": the same kernels on raw fp32 operands (the tensor core truncates them);
+        # "fp32": CUDA-core fp32 GEMMs (in-library parity reference)
+        modes = {"fp32": _lib.RT_GEMM_FP32_SIMT, "tf32_trunc": _lib.RT_GEMM_TF32_TCGEN05,
+                 "tf32": _lib.RT_GEMM_TF32_RN}
+        assert gemm in modes, gemm
+        td.gemm_mode = modes[gemm]
         self.B, self.T, self.P, self.n = mbatch, nstep_train, burn_in, nstep_target
         self.Nq, self.A, self.U = max(num_quantiles, 1), num_actions, lstm_units
         h = C.c_void_p()
@@ -150,6 +155,10 @@ class DeviceLearner:
         self.load_state_dict(st["adam_m"], _lib.RT_BUF_ADAM_M)
         self.load_state_dict(st["adam_v"], _lib.RT_BUF_ADAM_V)
         _lib.check(self._lib.rt_learner_set_opt_state(self._h, int(st["adam_steps"]), float(st["lr"])))
+
+    def params_changed(self):
+        """After writing flat(RT_BUF_ONLINE / RT_BUF_TARGET) directly (e.g. a broadcast)."""
+        _lib.check(self._lib.rt_learner_params_changed(self._h, self._stream()))
 
     def sync_target(self):
         _lib.check(self._lib.rt_learner_sync_target(self._h, self._stream()))

@@ -84,3 +84,4 @@ def broadcast_params_(learner, src=0):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         for which in (_lib.RT_BUF_ONLINE, _lib.RT_BUF_TARGET):
             dist.broadcast(learner.flat(which), src=src)
+        learner.params_changed()
