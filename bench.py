@@ -224,15 +224,12 @@ def build_history(cfg, device, seed, rank):
 def build_learner(cfg, device, gemm, seed=0):
     from rltime_b200.learner import DeviceLearner
     from rltime_b200.init import init_params
-    from rltime_b200 import _lib
     U, A = cfg["units"], cfg["A"]
     learner = DeviceLearner(cfg["frame"], cfg["conv"], U, cfg["fc"], A, cfg["Nq"], 64, True,
                             mbatch=cfg["B"], nstep_train=cfg["T"], burn_in=cfg["P"],
                             nstep_target=cfg["n"], gamma=cfg["gamma"], double_q=True,
                             rnn_bootstrap=bool(U), vf_scale_epsilon=None, clip_grad=cfg["clip_grad"],
                             adam_epsilon=cfg["adam_eps"], lr=3e-4, seed=seed, device=device, gemm=gemm)
-    if not U:
-        learner.io = _lib.LearnerIO(0, -1, -1, -1, 0)
     learner.load_state_dict(init_params(learner.param_info, U, seed=1), 0)
     learner.load_state_dict(init_params(learner.param_info, U, seed=2), 1)
     return learner

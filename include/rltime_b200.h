@@ -115,6 +115,11 @@ typedef struct rt_batch {
   int64_t* loss_indices;           /* S*B*2 (PER): (env_id, env_offset) or (-1,-1) */
   int32_t* idxes;                  /* B (PER): drawn prioritization indices */
   int32_t* slots;                  /* (S+n)*B storage slots behind all_states (debug/fusion) */
+  /* Optional: separately stacked target states, S*B items per leaf (history.py:268-270, the layout of
+   * batches whose n-step varies per row, e.g. OnlineHistoryBuffer with fixed_target).  When
+   * target_states[0] is non-null the learner reads the bootstrap states from here and all_states only has
+   * to hold the S*B training rows. */
+  void* target_states[RT_MAX_FIELDS];
 } rt_batch;
 
 int rt_replay_batch(rt_replay* h, rt_batch* out);
@@ -154,9 +159,11 @@ typedef struct rt_learner rt_learner;
  * json model description consumed by SequentialModel (rltime/models/torch/sequential.py:15-66,
  * configs/models/nature_cnn_lstm512_fc512.json) and the IQNPolicy / DQNPolicy constructor
  * arguments (rltime/policies/torch/iqn.py:12-13, dqn.py:15-16). */
+#define RT_MAX_PRE_FC 8
 typedef struct rt_model_desc {
-  int32_t in_c, in_h, in_w;            /* observation (C, H, W), uint8, channel first */
-  int32_t num_conv;
+  int32_t in_c, in_h, in_w;            /* observation (C, H, W), uint8, channel first; num_conv == 0: a float32
+                                        * vector of in_c * in_h * in_w values (configs/models/mlp_2x64.json) */
+  int32_t num_conv;                    /* 0 = no CNN module */
   int32_t conv_filters[RT_MAX_CONV], conv_kernel[RT_MAX_CONV], conv_stride[RT_MAX_CONV];
   int32_t lstm_units;                  /* 0 = no recurrent layer */
   int32_t fc_size;
@@ -165,6 +172,17 @@ typedef struct rt_model_desc {
                                         * rltime/policies/torch/dqn.py) trained by DQN._compute_grads */
   int32_t embedding_dim;
   int32_t dueling;
+  /* Tuple observation (models/torch/torch_model.py:33-56): width of the extra 1-D feature vector that
+   * SequentialModel._combine_extra_inputs concatenates to the input of the LSTM layer
+   * (models/torch/sequential.py:146-165,193-195; env_wrappers/common.py:221-233).  0 = plain Box. */
+  int32_t extra_dim;
+  /* Linear + ReLU layers (models/torch/modules/fc.py:7-36, every layer of every FC module that is not the
+   * last module) between the CNN / the raw observation and the LSTM / the last FC module, in forward order:
+   * output width, index of the module in SequentialModel.layers, index of the layer inside its module. */
+  int32_t num_pre_fc;
+  int32_t pre_fc_size[RT_MAX_PRE_FC];
+  int32_t pre_fc_module[RT_MAX_PRE_FC];
+  int32_t pre_fc_sub[RT_MAX_PRE_FC];
 } rt_model_desc;
 
 /* Training arguments: union of IQN/DQN._train, TorchTrainer._train and MultiStepTrainer._train
@@ -188,12 +206,18 @@ typedef struct rt_train_desc {
   int32_t loss_timestep_agg; /* loss_timestep_aggregation (dqn.py:116-124): 0 none, 1 mean, 2 sum */
   int32_t loss_mse;          /* DQN loss_mode (dqn.py:96-110): 0 huber, 1 mse */
   double clip_grad_dynamic_alpha; /* >= 0: clip to clip_grad x EMA(grad norm) (torch_trainer.py:153-175) */
+  /* rnn_steps_train (multi_step_trainer.py:192-216,239,305): the LSTM views the T*B time-major rows of a
+   * pass as (rnn_steps_train, T*B / rnn_steps_train) -- exactly the reference's x.view(timesteps, -1, ...)
+   * (models/torch/modules/lstm.py:60-79) -- taking the stored state of its first T*B/rnn_steps_train rows.
+   * 0 = nstep_train.  Must divide nstep_train. */
+  int32_t rnn_steps_train;
 } rt_train_desc;
 
 /* Which leaves of the replay batch feed the learner. */
 typedef struct rt_learner_io {
   int32_t field_x, field_hx, field_cx, field_initials; /* indices into rt_batch.all_states */
   int32_t po_field_actions;                            /* index into rt_batch.policy_outputs (int64) */
+  int32_t field_extra;                                 /* extra feature vector (float32), read when extra_dim > 0 */
 } rt_learner_io;
 
 #define RT_GEMM_FP32_SIMT 0     /* fp32 CUDA-core GEMM (parity reference path) */
@@ -235,6 +259,11 @@ int rt_learner_set_lr(rt_learner* h, double lr);
  * complete the optimizer state. */
 int rt_learner_get_opt_state(rt_learner* h, int64_t* adam_steps, double* lr);
 int rt_learner_set_opt_state(rt_learner* h, int64_t adam_steps, double lr);
+/* The rest of the state a bit-exact resume needs: the counter of the device RNG that draws the IQN quantile
+ * fractions (policies/torch/iqn.py:88 draws them with torch.rand) and the moving average of the dynamic
+ * gradient clip (torch_trainer.py:153-175). */
+int rt_learner_get_aux_state(rt_learner* h, uint64_t* rng_counter, float* clip_ema, int32_t* clip_ema_init);
+int rt_learner_set_aux_state(rt_learner* h, uint64_t rng_counter, float clip_ema, int32_t clip_ema_init);
 /* One learner update on a replay batch: burn-in (multi_step_trainer.py:90-131), bootstrap
  * targets (torch/iqn.py:15-52, torch_trainer.py:101-147), training forward + quantile-Huber
  * loss + backward (torch/iqn.py:54-129), grad-norm clip + Adam (torch_trainer.py:177-199).
@@ -253,11 +282,12 @@ int rt_learner_flat_buffer(rt_learner* h, int32_t which, float** dev_ptr, int64_
 /* DQNPolicy.actor_predict / IQNPolicy._actor_predict_postprocess (policies/torch/dqn.py:132-148,
  * iqn.py:124-131) for E envs at timesteps = 1 with the ONLINE network: q-values averaged over
  * the sampled quantiles plus the new LSTM state (LSTM.last_state, models/torch/modules/lstm.py:
- * 118-120).  All pointers are device pointers except taus_host (E*Nq fractions or NULL).  Uses
+ * 118-120).  All pointers are device pointers except taus_host (E*Nq fractions or NULL); x is uint8
+ * frames (float32 vectors when num_conv == 0), extra the E x extra_dim extra features or NULL.  Uses
  * the learner's activation buffers: call between updates, on the update stream. */
-int rt_learner_act(rt_learner* h, int32_t E, const uint8_t* x, const float* hx, const float* cx,
-                   const float* initials, const float* taus_host, float* qvalues, float* h_out,
-                   float* c_out, void* stream);
+int rt_learner_act(rt_learner* h, int32_t E, const void* x, const float* extra, const float* hx,
+                   const float* cx, const float* initials, const float* taus_host, float* qvalues,
+                   float* h_out, float* c_out, void* stream);
 /* Device pointer to the T*B reported |td| means (torch/iqn.py:112) of the last step. */
 int rt_learner_td_abs(rt_learner* h, float** out_device);
 /* The reported |td| / losses of a step are final BEFORE its backward pass (the reference reads

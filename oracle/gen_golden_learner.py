@@ -53,6 +53,28 @@ CASES = {
         embed=0, dueling=False, B=3, T=4, P=2, n=2, gamma=0.99, double_q=False,
         rnn_bootstrap=True, vf_eps=1e-3, clip_grad=0.8, adam_eps=1e-5, updates=3,
         policy="dqn", loss_mode="mse", loss_agg="sum", loss_ts_agg="mean", clip_dyn_alpha=0.9),
+    # the shipped atari_iqn_lstm wrapper stack: tuple observation (frame, extra features = one-hot last action,
+    # reward, timestep: env_wrappers/common.py:221-233) with the extra vector concatenated at the LSTM input
+    "iqn_lstm_extra": dict(
+        in_shape=(1, 16, 16), conv=[(8, 4, 2), (8, 3, 1)], lstm=16, fc=32, actions=3, nq=4,
+        embed=8, dueling=True, B=3, T=4, P=2, n=2, gamma=0.99, double_q=True,
+        rnn_bootstrap=True, vf_eps=None, clip_grad=40.0, adam_eps=1e-5, updates=2, extra=5),
+    # config-1 family: MLP (configs/models/mlp_2x64.json shrunk) on a 1-D float observation, DQN
+    "dqn_mlp": dict(
+        in_shape=(4,), conv=[], pre_fc=[[16]], lstm=0, fc=16, actions=2, nq=1, embed=0,
+        dueling=False, B=8, T=1, P=0, n=3, gamma=0.99, double_q=True, rnn_bootstrap=False,
+        vf_eps=None, clip_grad=None, adam_eps=1e-8, updates=2, policy="dqn"),
+    # CNN -> FC (fc_count 2) -> LSTM -> FC (configs/models/nature_cnn_fc512_lstm512_fc512.json family), IQN
+    "iqn_cnn_fc_lstm_fc": dict(
+        in_shape=(2, 16, 16), conv=[(8, 4, 2), (8, 3, 1)], pre_fc=[[12, 12], [20]], lstm=16, fc=24, actions=3,
+        nq=4, embed=8, dueling=True, B=3, T=4, P=0, n=2, gamma=0.99, double_q=True,
+        rnn_bootstrap=True, vf_eps=1e-3, clip_grad=40.0, adam_eps=1e-5, updates=2),
+    # rnn_steps_train < nstep_train: the LSTM views the T*B rows as (rnn_steps, T*B/rnn_steps)
+    # (multi_step_trainer.py:192-216,239,305; lstm.py:60-79)
+    "iqn_lstm_rnnsteps": dict(
+        in_shape=(2, 16, 16), conv=[(8, 4, 2), (8, 3, 1)], lstm=16, fc=32, actions=3, nq=4,
+        embed=8, dueling=True, B=3, T=6, P=0, n=2, gamma=0.99, double_q=True,
+        rnn_bootstrap=True, vf_eps=None, clip_grad=40.0, adam_eps=1e-5, updates=2, rnn_steps=2),
     # IQN with mean over time then sum over the batch
     "iqn_lstm_tsagg": dict(
         in_shape=(1, 12, 12), conv=[(4, 4, 2)], lstm=8, fc=8, actions=2, nq=4, embed=4,
@@ -63,7 +85,8 @@ CASES = {
 
 def make_spec(c):
     return ModelSpec(c["in_shape"], c["conv"], c["lstm"], c["fc"], c["actions"], c["nq"],
-                     c["embed"], c["dueling"], policy=c.get("policy", "iqn"))
+                     c["embed"], c["dueling"], policy=c.get("policy", "iqn"),
+                     pre_fc=c.get("pre_fc", ()), extra_dim=c.get("extra", 0))
 
 
 def make_batch(c, seed):
@@ -72,7 +95,8 @@ def make_batch(c, seed):
     S, B, n = c["T"] + c["P"], c["B"], c["n"]
     U = max(c["lstm"], 1)
     b = {
-        "all_x": rs.randint(0, 256, (S + n, B) + tuple(c["in_shape"])).astype(np.uint8),
+        "all_x": rs.randint(0, 256, (S + n, B) + tuple(c["in_shape"])).astype(np.uint8) if c["conv"]
+        else rs.randn(S + n, B, *c["in_shape"]).astype(np.float32),
         "returns": rs.randn(S, B),
         "nsteps": np.full((S, B), n, dtype=np.int64),
         "target_masks": (rs.rand(S, B) > 0.2).astype(np.float64),
@@ -83,12 +107,20 @@ def make_batch(c, seed):
         b["all_hx"] = rs.randn(S + n, B, U).astype(np.float32)
         b["all_cx"] = rs.randn(S + n, B, U).astype(np.float32)
         b["all_initials"] = (rs.rand(S + n, B) < 0.15).astype(np.float32)
+    if c.get("extra"):
+        b["all_extra"] = rs.randn(S + n, B, c["extra"]).astype(np.float32)
     return b
 
 
 def model_config(c):
-    layers = [{"type": "cnn", "args": {"layers": [
-        {"filters": f, "kernel": k, "stride": s} for f, k, s in c["conv"]]}}]
+    layers = []
+    if c["conv"]:
+        layers.append({"type": "cnn", "args": {"layers": [
+            {"filters": f, "kernel": k, "stride": s} for f, k, s in c["conv"]]}})
+    for sizes in c.get("pre_fc", ()):
+        # an FC module has ONE fc_size for all its fc_count layers (fc.py:18-24)
+        assert len(set(sizes)) == 1
+        layers.append({"type": "fc", "args": {"fc_size": sizes[0], "fc_count": len(sizes)}})
     if c["lstm"]:
         layers.append({"type": "lstm", "args": {"num_units": c["lstm"]}})
     layers.append({"type": "fc", "args": {"fc_size": c["fc"]}})
@@ -127,7 +159,12 @@ def run_case(name, c):
     spec = make_spec(c)
     p_online = spec.init_params(seed=11)
     p_target = spec.init_params(seed=12)
-    obs_space = gym.spaces.Box(0, 255, c["in_shape"], dtype=np.uint8)
+    if c["conv"]:
+        obs_space = gym.spaces.Box(0, 255, c["in_shape"], dtype=np.uint8)
+    else:
+        obs_space = gym.spaces.Box(-10, 10, c["in_shape"], dtype=np.float32)
+    if c.get("extra"):
+        obs_space = gym.spaces.Tuple((obs_space, gym.spaces.Box(-10, 10, (c["extra"],), dtype=np.float32)))
     act_space = gym.spaces.Discrete(c["actions"])
     dqn = c.get("policy", "iqn") == "dqn"
     if dqn:
@@ -184,15 +221,15 @@ def run_case(name, c):
             out["u%d/batch/%s" % (u, k)] = v
         # the replay buffer hands states/target_states as views of one stacked tensor
         # (history.py:254-265 + general/backend.py:143-147)
-        all_states = {"x": torch.from_numpy(b["all_x"].copy()), "layer0_state": {}}
+        x0 = torch.from_numpy(b["all_x"].copy())
+        all_states = {"x": (x0, torch.from_numpy(b["all_extra"].copy())) if c.get("extra") else x0}
+        for li in range(spec.fc_layer_index + 1):
+            all_states["layer%d_state" % li] = {}
         if c["lstm"]:
-            all_states["layer1_state"] = {
+            all_states["layer%d_state" % spec.lstm_index] = {
                 "hx": torch.from_numpy(b["all_hx"].copy()),
                 "cx": torch.from_numpy(b["all_cx"].copy()),
                 "initials": torch.from_numpy(b["all_initials"].copy())}
-            all_states["layer2_state"] = {}
-        else:
-            all_states["layer1_state"] = {}
         train_data = {
             "states": deep_apply(all_states, lambda x: x[:S]),
             "target_states": deep_apply(all_states, lambda x: x[n:]),
@@ -210,10 +247,10 @@ def run_case(name, c):
                 train_data, lambda x: x.reshape((x.shape[0] * x.shape[1],) + x.shape[2:]))
             targets = tr.calc_target_values(
                 train_data["returns"], train_data["target_states"], train_data["target_masks"],
-                nsteps=train_data["nsteps"], timesteps=1 if not c["rnn_bootstrap"] else T)
+                nsteps=train_data["nsteps"], timesteps=1 if not c["rnn_bootstrap"] else c.get("rnn_steps", T))
             params_before = {k: v.detach().clone() for k, v in tr.policy.state_dict().items()}
             tr.train_batch(train_data["states"], targets, train_data["policy_outputs"],
-                           train_data["extra_data"], T)
+                           train_data["extra_data"], c.get("rnn_steps", T))
         taus = tq.log
         names = (["burn_online"] + (["burn_target"] if c["rnn_bootstrap"] else []) if P else []) + \
             ["target", "select", "train"]

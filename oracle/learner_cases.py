@@ -11,13 +11,14 @@ from oracle.gen_golden_learner import CASES  # noqa: F401  (pure-data dict; no r
 
 def spec_of(c):
     return ModelSpec(c["in_shape"], c["conv"], c["lstm"], c["fc"], c["actions"], c["nq"],
-                     c["embed"], c["dueling"], policy=c.get("policy", "iqn"))
+                     c["embed"], c["dueling"], policy=c.get("policy", "iqn"),
+                     pre_fc=c.get("pre_fc", ()), extra_dim=c.get("extra", 0))
 
 
 def update_kwargs(c):
     """Optional trainer arguments of a case -> learner_oracle.learner_update keywords."""
     return dict(aggregation=c.get("loss_agg", "mean"), timestep_aggregation=c.get("loss_ts_agg"),
-                loss_mode=c.get("loss_mode", "huber"))
+                loss_mode=c.get("loss_mode", "huber"), rnn_steps_train=c.get("rnn_steps"))
 
 
 def params_of(g, prefix):
@@ -34,11 +35,14 @@ def batch_of(g, c, u):
     # (multi_step_trainer.py:117-126), which matters when prefix_steps == nstep_target.
     allt = {k: torch.from_numpy(b[k].copy()) for k in b if k.startswith("all_")}
 
+    spec = spec_of(c)
+
     def st(lo, hi):
-        s = {"x": allt["all_x"][lo:hi]}
+        s = {"x": (allt["all_x"][lo:hi], allt["all_extra"][lo:hi]) if c.get("extra") else allt["all_x"][lo:hi]}
         if c["lstm"]:
-            s["layer1_state"] = {"hx": allt["all_hx"][lo:hi], "cx": allt["all_cx"][lo:hi],
-                                 "initials": allt["all_initials"][lo:hi]}
+            s["layer%d_state" % spec.lstm_index] = {
+                "hx": allt["all_hx"][lo:hi], "cx": allt["all_cx"][lo:hi],
+                "initials": allt["all_initials"][lo:hi]}
         return s
     return {
         "states": st(0, S), "target_states": st(n, S + n),

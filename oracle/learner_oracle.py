@@ -31,11 +31,19 @@ class ModelSpec:
     """Topology family of the hot path: CNN -> [LSTM] -> FC -> (IQN, dueling) heads."""
 
     def __init__(self, in_shape, conv, lstm_units, fc_size, num_actions, num_quantiles=32,
-                 embedding_dim=64, dueling=True, policy="iqn"):
+                 embedding_dim=64, dueling=True, policy="iqn", pre_fc=(), extra_dim=0):
+        """pre_fc: FC modules between the CNN (or the raw 1-D observation when conv is empty) and
+        the LSTM / last FC module, one list of layer sizes per module (fc.py: fc_count layers of
+        fc_size); extra_dim: width of the extra 1-D feature vector of a tuple observation,
+        concatenated at the LSTM input (sequential.py:146-165, extra_input_layer = first recurrent
+        layer)."""
         assert policy in ("iqn", "dqn")
         self.policy = policy                      # "dqn": DQNPolicy, no quantile layer
-        self.in_shape = tuple(in_shape)           # (C, H, W)
+        self.in_shape = tuple(in_shape)           # (C, H, W), or (D,) without a CNN
         self.conv = [tuple(c) for c in conv]      # (filters, kernel, stride)
+        self.pre_fc = [list(m) for m in pre_fc]
+        self.extra_dim = int(extra_dim)
+        assert not self.extra_dim or lstm_units, "extra features are fed to the LSTM layer"
         self.lstm_units = int(lstm_units)         # 0 = no recurrent layer
         self.fc_size = int(fc_size)
         self.num_actions = int(num_actions)
@@ -45,6 +53,8 @@ class ModelSpec:
 
     @property
     def conv_out(self):
+        if not self.conv:
+            return self.in_shape
         c, h, w = self.in_shape
         for f, k, s in self.conv:
             h = (h - k) // s + 1
@@ -53,13 +63,29 @@ class ModelSpec:
         return c, h, w
 
     @property
+    def conv_feat(self):
+        n = 1
+        for d in self.conv_out:
+            n *= d
+        return n
+
+    @property
     def feat(self):
-        c, h, w = self.conv_out
-        return c * h * w
+        """Width of the trunk features that reach the LSTM / the last FC module."""
+        return self.pre_fc[-1][-1] if self.pre_fc else self.conv_feat
+
+    # module indices inside SequentialModel.layers
+    @property
+    def pre_fc_index(self):
+        return 1 if self.conv else 0
+
+    @property
+    def lstm_index(self):
+        return self.pre_fc_index + len(self.pre_fc)
 
     @property
     def fc_layer_index(self):
-        return 2 if self.lstm_units else 1
+        return self.lstm_index + (1 if self.lstm_units else 0)
 
     @property
     def quantile_dim(self):
@@ -74,12 +100,19 @@ class ModelSpec:
             shapes["model.layers.0.layers.%d.weight" % i] = (f, cin, k, k)
             shapes["model.layers.0.layers.%d.bias" % i] = (f,)
             cin = f
+        d = self.conv_feat
+        for m, sizes in enumerate(self.pre_fc):
+            for j, sz in enumerate(sizes):
+                shapes["model.layers.%d.layers.%d.0.weight" % (self.pre_fc_index + m, j)] = (sz, d)
+                shapes["model.layers.%d.layers.%d.0.bias" % (self.pre_fc_index + m, j)] = (sz,)
+                d = sz
         if self.lstm_units:
             u = self.lstm_units
-            shapes["model.layers.1.lstm_cell.weight_ih"] = (4 * u, self.feat)
-            shapes["model.layers.1.lstm_cell.weight_hh"] = (4 * u, u)
-            shapes["model.layers.1.lstm_cell.bias_ih"] = (4 * u,)
-            shapes["model.layers.1.lstm_cell.bias_hh"] = (4 * u,)
+            ln = "model.layers.%d.lstm_cell." % self.lstm_index
+            shapes[ln + "weight_ih"] = (4 * u, self.feat + self.extra_dim)
+            shapes[ln + "weight_hh"] = (4 * u, u)
+            shapes[ln + "bias_ih"] = (4 * u,)
+            shapes[ln + "bias_hh"] = (4 * u,)
         li = self.fc_layer_index
         shapes["model.layers.%d.layers.0.0.weight" % li] = (self.fc_size, self.quantile_dim)
         shapes["model.layers.%d.layers.0.0.bias" % li] = (self.fc_size,)
@@ -118,12 +151,30 @@ class ModelSpec:
 
 # ------------------------------------------------------------------------- forward
 def cnn_forward(spec, p, x_u8):
+    if not spec.conv:
+        return x_u8.float().reshape(x_u8.shape[0], -1)     # fc.py:30 flattens whatever arrives
     x = x_u8.float() * (1.0 / 255.0)                       # cnn.py:44-45
     for i, (f, k, s) in enumerate(spec.conv):
         x = F.conv2d(x, p["model.layers.0.layers.%d.weight" % i],
                      p["model.layers.0.layers.%d.bias" % i], stride=s)
         x = F.relu(x)
     return x.reshape(x.shape[0], -1)
+
+
+def pre_fc_forward(spec, p, x):
+    """FC modules in front of the LSTM / last FC module (fc.py:29-36: linear + ReLU per layer)."""
+    for m, sizes in enumerate(spec.pre_fc):
+        for j in range(len(sizes)):
+            n = "model.layers.%d.layers.%d.0." % (spec.pre_fc_index + m, j)
+            x = F.relu(F.linear(x, p[n + "weight"], p[n + "bias"]))
+    return x
+
+
+def split_obs(x):
+    """TorchModel._get_inputs (torch_model.py:58-65): (main observation, extra features or None)."""
+    if isinstance(x, (tuple, list)):
+        return x[0], torch.cat([e.float() for e in x[1:]], dim=-1)
+    return x, None
 
 
 def lstm_forward(spec, p, x, hx, cx, initials, timesteps):
@@ -135,8 +186,9 @@ def lstm_forward(spec, p, x, hx, cx, initials, timesteps):
     c = cx.view(timesteps, B, U)[0]
     xs = x.view(timesteps, B, -1)
     ini = initials.view(timesteps, B)
-    w_ih, w_hh = p["model.layers.1.lstm_cell.weight_ih"], p["model.layers.1.lstm_cell.weight_hh"]
-    b_ih, b_hh = p["model.layers.1.lstm_cell.bias_ih"], p["model.layers.1.lstm_cell.bias_hh"]
+    ln = "model.layers.%d.lstm_cell." % spec.lstm_index
+    w_ih, w_hh = p[ln + "weight_ih"], p[ln + "weight_hh"]
+    b_ih, b_hh = p[ln + "bias_ih"], p[ln + "bias_hh"]
     outs = []
     for t in range(timesteps):
         keep = (1 - ini[t]).unsqueeze(-1)
@@ -163,10 +215,13 @@ def quantile_layer(spec, p, x, taus):
 
 def trunk_forward(spec, p, states, timesteps):
     """CNN (+LSTM) part shared by predict and burn-in.  Returns (features (M, D), last (h, c))."""
-    x = cnn_forward(spec, p, states["x"])
+    main, extra = split_obs(states["x"])
+    x = pre_fc_forward(spec, p, cnn_forward(spec, p, main))
     last = None
     if spec.lstm_units:
-        ls = states["layer1_state"]
+        if extra is not None:                              # sequential.py:146-165,193-195
+            x = torch.cat([x, extra.reshape(extra.shape[0], -1)], dim=-1)
+        ls = states["layer%d_state" % spec.lstm_index]
         x, last = lstm_forward(spec, p, x, ls["hx"], ls["cx"], ls["initials"], timesteps)
     return x, last
 
@@ -223,13 +278,18 @@ def vf_unscale(sx, eps):
 
 
 def bootstrap_target(spec, p_online, p_target, target_states, timesteps, taus_target,
-                     taus_select, double_q):
+                     taus_select, double_q, margin_out=None):
     """iqn.py:15-52."""
     tq, _ = predict(spec, p_target, target_states, timesteps, taus_target)
     sel_p = p_online if double_q else p_target
     sq, _ = predict(spec, sel_p, target_states, timesteps, taus_select)
     act = sq.mean(1).argmax(dim=-1, keepdim=True)                      # (M, 1)
     act = act.unsqueeze(1).repeat([1, spec.num_quantiles, 1])
+    if margin_out is not None and sq.shape[-1] > 1:
+        # test aid: gap between the best and second-best selection value per row (a row whose gap is
+        # below the arithmetic noise has no well-defined argmax to compare against)
+        top2 = sq.mean(1).topk(2, dim=-1).values
+        margin_out.append(top2[:, 0] - top2[:, 1])
     return torch.gather(tq, dim=-1, index=act).squeeze(-1)             # (M, Nq)
 
 
@@ -302,9 +362,12 @@ def burn_in(spec, p, states, burn_in_timesteps):
     LSTM state of step P with the produced one (masked by that step's initials, lstm.py:150-152).
     Mutates states['layer1_state']['hx'/'cx'][P] and returns nothing; callers slice [P:]."""
     P = burn_in_timesteps
-    sub = {"x": states["x"][:P].reshape((-1,) + states["x"].shape[2:])}
-    ls = states["layer1_state"]
-    sub["layer1_state"] = {k: v[:P].reshape((-1,) + v.shape[2:]) for k, v in ls.items()}
+    flat = lambda v: v[:P].reshape((-1,) + v.shape[2:])
+    x = states["x"]
+    sub = {"x": tuple(flat(v) for v in x) if isinstance(x, (tuple, list)) else flat(x)}
+    key = "layer%d_state" % spec.lstm_index
+    ls = states[key]
+    sub[key] = {k: flat(v) for k, v in ls.items()}
     _, (h, c) = trunk_forward(spec, p, sub, P)
     keep = (1 - ls["initials"][P]).unsqueeze(-1)
     ls["hx"][P] = h * keep
@@ -365,7 +428,7 @@ class DynamicClip:
 def learner_update(spec, p_online, p_target, opt, batch, taus, gamma, double_q=True,
                    rnn_bootstrap=True, vf_eps=None, kappa=1.0, clip_grad=None,
                    burn_in_timesteps=0, aggregation="mean", timestep_aggregation=None,
-                   loss_mode="huber", dynamic_clip=None):
+                   loss_mode="huber", dynamic_clip=None, rnn_steps_train=None):
     """One full learner update on a (S, B, ...) time-major batch (multi_step_trainer.py:
     278-340): burn-in -> targets -> loss/grads -> clip -> Adam.  `taus` = dict with
     'burn_online', 'burn_target' (ignored values, forwards still draw), 'target', 'select',
@@ -375,6 +438,7 @@ def learner_update(spec, p_online, p_target, opt, batch, taus, gamma, double_q=T
     P = burn_in_timesteps
     S, B = batch["returns"].shape
     T = S - P
+    R = rnn_steps_train or T      # LSTM sequence length of the target / training passes
     if P:
         with torch.no_grad():
             burn_in(spec, p_online, batch["states"], P)
@@ -384,26 +448,29 @@ def learner_update(spec, p_online, p_target, opt, batch, taus, gamma, double_q=T
     def cut(tree):
         if isinstance(tree, dict):
             return {k: cut(v) for k, v in tree.items()}
+        if isinstance(tree, (tuple, list)):
+            return tuple(cut(v) for v in tree)
         return tree[P:].reshape((-1,) + tree.shape[2:])
     states, tstates = cut(batch["states"]), cut(batch["target_states"])
     returns, masks, nsteps = cut(batch["returns"]), cut(batch["target_masks"]), cut(batch["nsteps"])
     actions = cut(batch["actions"])
     weights = cut(batch["importance_weights"]) if batch.get("importance_weights") is not None else None
     dqn = spec.policy == "dqn"
+    margins = []
     with torch.no_grad():
         if dqn:
             boot = bootstrap_target_dqn(spec, p_online, p_target, tstates,
-                                        T if rnn_bootstrap else 1, double_q)
+                                        R if rnn_bootstrap else 1, double_q)
         else:
-            boot = bootstrap_target(spec, p_online, p_target, tstates, T if rnn_bootstrap else 1,
-                                    taus["target"], taus["select"], double_q)
+            boot = bootstrap_target(spec, p_online, p_target, tstates, R if rnn_bootstrap else 1,
+                                    taus["target"], taus["select"], double_q, margin_out=margins)
         targets = calc_targets(returns, boot, masks, nsteps, gamma, vf_eps)
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in p_online.items()}
     if dqn:
-        loss, report, td_mean = dqn_loss(spec, leaf, states, targets, actions, weights, T, kappa,
+        loss, report, td_mean = dqn_loss(spec, leaf, states, targets, actions, weights, R, kappa,
                                          loss_mode, aggregation, timestep_aggregation)
     else:
-        loss, report, td_mean = iqn_loss(spec, leaf, states, targets, actions, weights, T,
+        loss, report, td_mean = iqn_loss(spec, leaf, states, targets, actions, weights, R,
                                          taus["train"], kappa, aggregation, timestep_aggregation)
     loss.backward()
     grads = {k: v.grad for k, v in leaf.items()}
@@ -413,4 +480,5 @@ def learner_update(spec, p_online, p_target, opt, batch, taus, gamma, double_q=T
     with torch.no_grad():
         opt.step(p_online, grads)
     return {"loss": loss.detach(), "report": report.detach(), "td_mean": td_mean.detach(),
-            "grad_norm": gn, "targets": targets, "grads": grads}
+            "grad_norm": gn, "targets": targets, "grads": grads,
+            "select_margin": margins[0] if margins else None}

@@ -54,6 +54,14 @@ SCENARIOS = {
     "uniform_avoid_crossing": dict(kind="uniform", size=600, envs=4, T=6, P=2, n=2, B=6, iters=200,
                                    frame=(2, 4, 4), units=3, actions=3, done_mode="bernoulli",
                                    done_p=0.08, feed="lockstep", avoid_episode_crossing=True),
+    # ONE env holding the whole (small) buffer: the evicted predecessor of the oldest transition still backs
+    # its state, i.e. N + 1 live positions of one env (eviction wrap-around every 90 transitions)
+    "uniform_single_env": dict(kind="uniform", size=90, envs=1, T=4, P=1, n=2, B=5, iters=160,
+                               frame=(1, 3, 3), units=2, actions=3, done_mode="bernoulli", done_p=0.07,
+                               feed="lockstep", feed_steps=(1, 9)),
+    "per_single_env": dict(kind="per", size=120, envs=1, T=4, P=2, n=2, B=4, iters=160, alpha=0.7, beta=0.5,
+                           frame=(1, 3, 3), units=2, actions=3, done_mode="bernoulli", done_p=0.07,
+                           feed="lockstep", feed_steps=(1, 9)),
     "uniform_async": dict(kind="uniform", size=300, envs=3, T=1, P=0, n=3, B=7, iters=200,
                           frame=(1, 3, 3), units=0, actions=4, done_mode="bernoulli",
                           done_p=0.1, feed="async"),

@@ -43,10 +43,12 @@ class Batch(C.Structure):
         ("returns", C.c_void_p), ("nsteps", C.c_void_p), ("target_masks", C.c_void_p),
         ("importance_weights", C.c_void_p), ("loss_indices", C.c_void_p),
         ("idxes", C.c_void_p), ("slots", C.c_void_p),
+        ("target_states", C.c_void_p * RT_MAX_FIELDS),
     ]
 
 
 RT_MAX_CONV = 8
+RT_MAX_PRE_FC = 8
 RT_BUF_ONLINE, RT_BUF_TARGET, RT_BUF_GRAD, RT_BUF_ADAM_M, RT_BUF_ADAM_V = range(5)
 RT_GEMM_FP32_SIMT, RT_GEMM_TF32_TCGEN05, RT_GEMM_TF32_RN = 0, 1, 2
 
@@ -58,6 +60,9 @@ class ModelDesc(C.Structure):
         ("conv_stride", C.c_int32 * RT_MAX_CONV), ("lstm_units", C.c_int32),
         ("fc_size", C.c_int32), ("num_actions", C.c_int32), ("num_quantiles", C.c_int32),
         ("embedding_dim", C.c_int32), ("dueling", C.c_int32),
+        ("extra_dim", C.c_int32), ("num_pre_fc", C.c_int32),
+        ("pre_fc_size", C.c_int32 * RT_MAX_PRE_FC), ("pre_fc_module", C.c_int32 * RT_MAX_PRE_FC),
+        ("pre_fc_sub", C.c_int32 * RT_MAX_PRE_FC),
     ]
 
 
@@ -69,13 +74,14 @@ class TrainDesc(C.Structure):
         ("vf_scale_epsilon", C.c_double), ("huber_kappa", C.c_double), ("clip_grad", C.c_double),
         ("adam_epsilon", C.c_double), ("lr", C.c_double), ("seed", C.c_uint64),
         ("loss_timestep_agg", C.c_int32), ("loss_mse", C.c_int32),
-        ("clip_grad_dynamic_alpha", C.c_double),
+        ("clip_grad_dynamic_alpha", C.c_double), ("rnn_steps_train", C.c_int32),
     ]
 
 
 class LearnerIO(C.Structure):
     _fields_ = [("field_x", C.c_int32), ("field_hx", C.c_int32), ("field_cx", C.c_int32),
-                ("field_initials", C.c_int32), ("po_field_actions", C.c_int32)]
+                ("field_initials", C.c_int32), ("po_field_actions", C.c_int32),
+                ("field_extra", C.c_int32)]
 
 
 # name -> (restype, argtypes); also the list the CPU test checks against the header
@@ -121,7 +127,7 @@ SIGNATURES = {
     "rt_learner_compute_grads": (C.c_int, [_VP, C.POINTER(Batch), C.POINTER(LearnerIO), _VP, _VP]),
     "rt_learner_apply_grads": (C.c_int, [_VP, C.c_double, _VP]),
     "rt_learner_flat_buffer": (C.c_int, [_VP, C.c_int32, C.POINTER(_VP), C.POINTER(C.c_int64)]),
-    "rt_learner_act": (C.c_int, [_VP, C.c_int32] + [_VP] * 8 + [_VP]),
+    "rt_learner_act": (C.c_int, [_VP, C.c_int32] + [_VP] * 9 + [_VP]),
     "rt_learner_td_abs": (C.c_int, [_VP, C.POINTER(_VP)]),
     "rt_learner_wait_loss": (C.c_int, [_VP, _VP]),
     "rt_learner_wait_late_grads": (C.c_int, [_VP, _VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -135,6 +141,8 @@ SIGNATURES = {
                                        C.POINTER(C.c_int64)]),
     "rt_learner_get_opt_state": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "rt_learner_set_opt_state": (C.c_int, [_VP, C.c_int64, C.c_double]),
+    "rt_learner_get_aux_state": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "rt_learner_set_aux_state": (C.c_int, [_VP, C.c_uint64, C.c_float, C.c_int32]),
     "rt_learner_gemm_launches": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP]),
     "rt_learner_gemm_shapes": (C.c_int, [_VP, C.c_int64, _VP, C.POINTER(C.c_int64)]),
     "rt_gemm_bench": (C.c_int, [C.c_int32] * 9 + [C.POINTER(C.c_double), C.c_int32]),

@@ -43,6 +43,7 @@ struct GemmArgs {
   int accumulate;
   float* ws;      // split-K workspace [splits][M][N] (raw partial sums)
   int kchunk;     // K range per z-slice
+  int round_out;  // store the nearest TF32 value (the output is an operand of a tensor-core product)
 };
 
 __device__ __forceinline__ float gemm_epilogue(const GemmArgs& g, int m, int n, float acc) {
@@ -52,6 +53,7 @@ __device__ __forceinline__ float gemm_epilogue(const GemmArgs& g, int m, int n, 
   if (g.relu) v = fmaxf(v, 0.f);
   if (g.mask) v = (g.mask[(size_t)m * g.ldmask + n] > 0.f) ? v : 0.f;
   if (g.accumulate) v += g.C[(size_t)m * g.ldc + n];
+  if (g.round_out) v = rna_tf32(v);
   return v;
 }
 

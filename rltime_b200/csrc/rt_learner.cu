@@ -74,7 +74,12 @@ struct ConvL {
   size_t w, b;  // offsets in the flat parameter buffer
 };
 
-enum PermKind { PERM_NONE = 0, PERM_CONV = 1, PERM_FEAT_COLS = 2, PERM_FEAT_ROWS = 3 };
+enum PermKind { PERM_NONE = 0, PERM_CONV = 1, PERM_FEAT_COLS = 2, PERM_FEAT_ROWS = 3, PERM_WIH_EXTRA = 4 };
+
+struct PreL {   // linear + ReLU layer in front of the LSTM / the last FC module
+  int in, out;
+  size_t w, b;
+};
 
 struct PInfo {
   std::string name;
@@ -100,7 +105,14 @@ struct rt_learner {
   rt_train_desc td;
   int device = 0;
   std::vector<ConvL> conv;
-  int featC = 0, featHW = 0, feat = 0;  // last conv output
+  int featC = 0, featHW = 0, cfeat = 0;  // last conv output (no CNN: the raw float observation, featHW = 1)
+  int feat = 0;                          // trunk features that reach the LSTM / the last FC module
+  std::vector<PreL> pre;                 // FC layers between the two
+  std::vector<float*> pre_out, pre_out2, d_pre;   // activations (primary / second set), gradients
+  float* d_cfeat = nullptr;              // gradient w.r.t. the conv output when FC layers follow it
+  bool wih_perm = false;                 // W_ih columns follow the conv feature permutation
+  int X = 0;                             // extra 1-D features of a tuple observation, fed to the LSTM
+  size_t o_wihx = 0;                     // [4U][X] block of W_ih (stored behind the [4U][feat] block)
   int U = 0, D = 0, F = 0, A = 0, Nq = 0, E = 0;
   bool dueling = false;
   bool dqn = false;            // plain DQNPolicy: no quantile layer, one output per action
@@ -128,6 +140,7 @@ struct rt_learner {
 
   // geometry
   int B = 0, T = 0, P = 0, n = 0, S = 0;
+  int R = 0;          // rnn_steps_train: LSTM sequence length of the target / training passes (divides T)
   int max_rows = 0;   // trunk rows per pass
   int M = 0, MQ = 0;  // head rows (T*B) and quantile-expanded rows
   int chunk_rows = 128;
@@ -177,7 +190,7 @@ struct rt_learner {
   // consecutive kernels when issued one by one).  Graphs cannot be captured on the legacy default
   // stream, so the update runs on the learner's own stream, forked from / joined to the caller's.
   struct StepGraphs {
-    const void* key[10] = {};
+    const void* key[12] = {};
     cudaGraphExec_t fwd = nullptr, bwd = nullptr, bwd2 = nullptr;
     long long n_fwd = 0, n_bwd = 0, n_bwd2 = 0;      // launches each replay stands for (rt_launch_count)
   };
@@ -268,13 +281,21 @@ size_t perm_index(const rt_learner* h, const PInfo& pi, size_t j) {
       return f * per_f + ((size_t)kh * K + kw) * C + c;
     }
     case PERM_FEAT_COLS: {  // [rows][c*HW + hw] -> [rows][hw*C + c]
-      size_t cols = (size_t)h->feat;
+      size_t cols = (size_t)h->cfeat;
       size_t row = j / cols, col = j % cols;
       int c = (int)(col / h->featHW), hw = (int)(col % h->featHW);
       return row * cols + (size_t)hw * h->featC + c;
     }
+    case PERM_WIH_EXTRA: {  // [4U][feat + X] -> [4U][feat] block (feature columns permuted) + [4U][X] block
+      size_t cols = (size_t)h->feat + h->X;
+      size_t row = j / cols, col = j % cols;
+      if (col >= (size_t)h->feat) return (size_t)4 * h->U * h->feat + row * h->X + (col - h->feat);
+      if (!h->wih_perm) return row * h->feat + col;
+      int c = (int)(col / h->featHW), hw = (int)(col % h->featHW);
+      return row * h->feat + (size_t)hw * h->featC + c;
+    }
     case PERM_FEAT_ROWS: {  // [c*HW + hw][inner] -> [hw*C + c][inner]
-      size_t inner = pi.count / (size_t)h->feat;
+      size_t inner = pi.count / (size_t)h->cfeat;
       size_t row = j / inner, in = j % inner;
       int c = (int)(row / h->featHW), hw = (int)(row % h->featHW);
       return ((size_t)hw * h->featC + c) * inner + in;
@@ -444,7 +465,7 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   a.g = g;
   a.num_kb_total = num_kb;
   a.kb_per_split = kbps;
-  a.round_tf32 = cx.round_tf32;
+  a.round_tf32 = cx.round_tf32 || g.round_out;
   a.dbg = cx.dbg;
   dim3 grid(tn, tm, splits);
   int rc;
@@ -788,6 +809,31 @@ int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t*
   return RT_OK;
 }
 
+// Feature extractor of one pass: CNN (if any) + the FC layers in front of the LSTM / last FC module
+// (fc.py:29-36: linear + ReLU).  *out = (rows, h->feat) features.  Without a CNN the observation rows
+// are float32 vectors and feed the first FC layer (or the LSTM / heads) directly.
+int feature_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows,
+                    const float** out, const float* xf_pre = nullptr, bool second = false) {
+  const float* f = reinterpret_cast<const float*>(x);
+  if (!h->conv.empty()) {
+    RT_TRY(cnn_forward(h, st, net, x, rows, xf_pre, second));
+    f = (second ? h->c_out2 : h->c_out).back();
+  }
+  GemmCtx& cx = second ? h->gx2 : h->gx;
+  for (size_t k = 0; k < h->pre.size(); ++k) {
+    const PreL& L = h->pre[k];
+    float* o = (second ? h->pre_out2 : h->pre_out)[k];
+    rtk::GemmArgs g = mk(f, L.in, 0, net + L.w, L.in, 1, o, L.out, rows, L.out, L.in);
+    g.bias = net + L.b;
+    g.relu = 1;
+    g.round_out = h->rn;
+    RT_TRY(gemm(cx, st, g));
+    f = o;
+  }
+  *out = f;
+  return RT_OK;
+}
+
 // One LSTM recurrence (lstm.py:50-122) over time-major rows t*Beff + b.
 struct SeqDesc {
   const float* net;       // parameter buffer (online / target)
@@ -800,14 +846,22 @@ struct SeqDesc {
   bool bptt;              // keep gates / c_all / cprev for the backward pass
 };
 
-// xg = feat . W_ih^T + b_ih + b_hh for `rows` rows
+// xg = [feat | extra] . W_ih^T + b_ih + b_hh for `rows` rows (the extra features of a tuple observation
+// are concatenated at the LSTM input, sequential.py:146-165: a second skinny product into the same sums)
 int lstm_xgates(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int rows, float* xg,
-                GemmCtx* cx = nullptr) {
+                const float* extra, GemmCtx* cx = nullptr) {
   int U = h->U;
   rtk::GemmArgs g = mk(feat, h->feat, 0, net + h->o_wih, h->feat, 1, xg, 4 * U, rows, 4 * U, h->feat);
   g.bias = net + h->o_bih;
   g.bias2 = net + h->o_bhh;
-  return gemm(cx ? *cx : h->gx, st, g);
+  RT_TRY(gemm(cx ? *cx : h->gx, st, g));
+  if (h->X) {
+    RT_REQUIRE(extra, "the model takes %d extra features but the batch has none (rt_learner_io.field_extra)", h->X);
+    rtk::GemmArgs g2 = mk(extra, h->X, 0, net + h->o_wihx, h->X, 1, xg, 4 * U, rows, 4 * U, h->X);
+    g2.accumulate = 1;
+    RT_TRY(gemm_simt(cx ? *cx : h->gx, st, g2));
+  }
+  return RT_OK;
 }
 
 // fp32 recurrence of one sequence: persistent SIMT kernel when it fits, else one GEMM + cell
@@ -935,26 +989,27 @@ int lstm_run(rt_learner* h, cudaStream_t st, const SeqDesc* seqs, int nseq, int 
 
 // LSTM forward of one sequence set: input gates + recurrence, output in h->h_all (slot 0).
 int lstm_forward(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int rows,
-                 int timesteps, const float* hx, const float* cx, const float* initials) {
-  RT_TRY(lstm_xgates(h, st, net, feat, rows, h->xg));
+                 int timesteps, const float* hx, const float* cx, const float* initials, const float* extra) {
+  RT_TRY(lstm_xgates(h, st, net, feat, rows, h->xg, extra));
   SeqDesc q{net, h->xg, hx, cx, initials, h->h_all, 0, true};
   return lstm_run(h, st, &q, 1, timesteps, rows / timesteps);
 }
 
 struct StateView {  // device pointers to the (rows, ...) leaves of a batch slice
-  const uint8_t* x;
+  const uint8_t* x;       // uint8 frames; float32 vectors when the model has no CNN
   float* hx;
   float* cx;
   const float* initials;
+  const float* extra;     // (rows, X) extra features of a tuple observation, or null
 };
 
 // CNN (+LSTM); returns the feature pointer [rows, D-or-feat] that feeds the heads.
 int trunk_forward(rt_learner* h, cudaStream_t st, const float* net, const StateView& sv, int rows,
                   int timesteps, const float** feat_out) {
-  RT_TRY(cnn_forward(h, st, net, sv.x, rows));
-  const float* feat = h->c_out.back();
+  const float* feat = nullptr;
+  RT_TRY(feature_forward(h, st, net, sv.x, rows, &feat));
   if (h->U) {
-    RT_TRY(lstm_forward(h, st, net, feat, rows, timesteps, sv.hx, sv.cx, sv.initials));
+    RT_TRY(lstm_forward(h, st, net, feat, rows, timesteps, sv.hx, sv.cx, sv.initials, sv.extra));
     feat = h->h_all;
   }
   *feat_out = feat;
@@ -1159,7 +1214,7 @@ int heads_backward(rt_learner* h, cudaStream_t st, const float* net, const float
 
 // BPTT through the LSTM given dfeatq = d(loss)/d(h_all); produces dfeat (CNN features).
 int lstm_backward(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int rows,
-                  int timesteps, const float* initials) {
+                  int timesteps, const float* initials, const float* extra) {
   int U = h->U, Beff = rows / timesteps;
   float* G = h->grad;
   int nb = cdiv((size_t)Beff * U, 256);
@@ -1210,6 +1265,8 @@ int lstm_backward(rt_learner* h, cudaStream_t st, const float* net, const float*
   RT_TRY(side_begin(h, st, &sd));
   RT_TRY(gemm(*sd.gx, sd.st, mk(h->dgates, 4 * U, 1, h->hprev, U, 0, G + h->o_whh, U, 4 * U, U, rows)));
   RT_TRY(gemm(*sd.gx, sd.st, mk(h->dgates, 4 * U, 1, feat, h->feat, 0, G + h->o_wih, h->feat, 4 * U, h->feat, rows)));
+  if (h->X)
+    RT_TRY(gemm_simt(*sd.gx, sd.st, mk(h->dgates, 4 * U, 1, extra, h->X, 0, G + h->o_wihx, h->X, 4 * U, h->X, rows)));
   RT_TRY(colsum(h, sd.st, h->dgates, rows, 4 * U, G + h->o_bih, 0, sd.colsum_scratch));
   RT_CUDA(cudaMemcpyAsync(G + h->o_bhh, G + h->o_bih, (size_t)4 * U * sizeof(float),
                           cudaMemcpyDeviceToDevice, sd.st));
@@ -1298,6 +1355,43 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
   return RT_OK;
 }
 
+// Backward of the feature extractor: `dlast` = gradient w.r.t. the (post-ReLU) trunk features of the
+// training pass, `x` = that pass's observation rows.  FC layers first (weight / bias gradients on the side
+// branch, the data gradient with the previous layer's ReLU mask fused in the GEMM epilogue), then the CNN.
+int features_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows, float* dlast) {
+  float* G = h->grad;
+  const int np = (int)h->pre.size();
+  if (np) {
+    {
+      size_t n = (size_t)rows * h->pre[np - 1].out;
+      rtk::k_relu_bwd_inplace<<<grid1d(n), 256, 0, st>>>(dlast, h->pre_out[np - 1], n);
+      RT_LAUNCH_CHECK();
+    }
+    for (int k = np - 1; k >= 0; --k) {
+      const PreL& L = h->pre[k];
+      const float* in = k > 0 ? h->pre_out[k - 1]
+                              : (h->conv.empty() ? reinterpret_cast<const float*>(x) : h->c_out.back());
+      float* dz = k == np - 1 ? dlast : h->d_pre[k];
+      SideCtx sd;
+      RT_TRY(side_begin(h, st, &sd));
+      RT_TRY(gemm(*sd.gx, sd.st, mk(dz, L.out, 1, in, L.in, 0, G + L.w, L.in, L.out, L.in, rows)));
+      RT_TRY(colsum(h, sd.st, dz, rows, L.out, G + L.b, 0, sd.colsum_scratch));
+      if (k > 0) {
+        rtk::GemmArgs g = mk(dz, L.out, 0, net + L.w, L.in, 0, h->d_pre[k - 1], L.in, rows, L.in, L.out);
+        g.mask = h->pre_out[k - 1];
+        g.ldmask = L.in;
+        RT_TRY(gemm(h->gx, st, g));
+      } else if (!h->conv.empty()) {
+        // the ReLU mask of the last conv layer is applied by cnn_backward
+        RT_TRY(gemm(h->gx, st, mk(dz, L.out, 0, net + L.w, L.in, 0, h->d_cfeat, L.in, rows, L.in, L.out)));
+      }
+    }
+    dlast = h->d_cfeat;
+  }
+  if (!h->conv.empty()) RT_TRY(cnn_backward(h, st, net, x, rows, dlast));
+  return RT_OK;
+}
+
 // grad-norm, clip, Adam (torch_trainer.py:177-199) on the flat buffers.  grad_scale folds the
 // 1/world_size of a data-parallel gradient mean into the same pass.
 int apply_grads(rt_learner* h, cudaStream_t st, float grad_scale) {
@@ -1351,7 +1445,10 @@ extern "C" {
 int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t device,
                       rt_learner** out) {
   RT_REQUIRE(md && td && out, "null argument");
-  RT_REQUIRE(md->num_conv >= 1 && md->num_conv <= RT_MAX_CONV, "num_conv out of range");
+  RT_REQUIRE(md->num_conv >= 0 && md->num_conv <= RT_MAX_CONV, "num_conv out of range");
+  RT_REQUIRE(md->num_pre_fc >= 0 && md->num_pre_fc <= RT_MAX_PRE_FC, "num_pre_fc out of range");
+  RT_REQUIRE(md->extra_dim >= 0 && (md->extra_dim == 0 || md->lstm_units > 0),
+             "extra features are fed to the LSTM layer: extra_dim needs lstm_units > 0");
   RT_REQUIRE(md->num_quantiles >= 0 && md->num_quantiles <= 256, "num_quantiles out of range");
   RT_REQUIRE(md->num_actions >= 1 && md->num_actions <= 64, "num_actions out of range");
   RT_REQUIRE(td->mbatch >= 1 && td->nstep_train >= 1 && td->burn_in >= 0 && td->nstep_target >= 1,
@@ -1367,13 +1464,17 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   h->E = md->embedding_dim; h->dueling = md->dueling != 0;
   h->B = td->mbatch; h->T = td->nstep_train; h->P = td->burn_in; h->n = td->nstep_target;
   h->S = h->T + h->P;
+  h->R = td->rnn_steps_train > 0 ? td->rnn_steps_train : h->T;
+  RT_REQUIRE(h->T % h->R == 0, "nstep_train (%d) must be divisible by rnn_steps_train (%d)", h->T, h->R);
   h->lr = (float)td->lr;
   {
-    // mean / sum over the batch, optionally a different aggregation over time-steps first
+    // mean / sum over the batch, optionally a different aggregation over time-steps first.  The
+    // reference views the losses as (timesteps, -1) with timesteps = rnn_steps_train (dqn.py:120-130)
     const double Md = (double)td->nstep_train * td->mbatch;
+    const double Rd = (double)h->R, Bd = Md / Rd;
     if (td->loss_timestep_agg == 0) h->loss_scale = (float)(td->loss_sum ? 1.0 : 1.0 / Md);
-    else h->loss_scale = (float)((td->loss_timestep_agg == 1 ? 1.0 / td->nstep_train : 1.0) *
-                                 (td->loss_sum ? 1.0 : 1.0 / td->mbatch));
+    else h->loss_scale = (float)((td->loss_timestep_agg == 1 ? 1.0 / Rd : 1.0) *
+                                 (td->loss_sum ? 1.0 : 1.0 / Bd));
   }
   RT_REQUIRE(!(h->P > 0 && h->U == 0), "burn-in only makes sense for recurrent models");
 
@@ -1395,23 +1496,63 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     h->conv.push_back(L);
     c = L.f; hh = L.hout; ww = L.wout;
   }
+  if (md->num_conv == 0) {   // raw float observation: no layout permutation (featHW = 1)
+    h->featC = c * hh * ww; h->featHW = 1;
+  } else {
+    h->featC = c; h->featHW = hh * ww;
+  }
+  h->cfeat = c * hh * ww;
+  h->X = md->extra_dim;
+  // FC layers in front of the LSTM / last FC module (fc.py:18-24), reference registration order
+  int next_module = md->num_conv ? 1 : 0;
+  {
+    int d = h->cfeat;
+    for (int k = 0; k < md->num_pre_fc; ++k) {
+      RT_REQUIRE(md->pre_fc_size[k] > 0 && md->pre_fc_module[k] >= next_module - (k ? 1 : 0), "bad FC layer %d", k);
+      PreL L;
+      L.in = d; L.out = md->pre_fc_size[k];
+      char nm[96];
+      snprintf(nm, sizeof(nm), "model.layers.%d.layers.%d.0.weight", md->pre_fc_module[k], md->pre_fc_sub[k]);
+      L.w = add_param(h, nm, {L.out, L.in}, k == 0 ? PERM_FEAT_COLS : PERM_NONE);
+      h->pinfo.back().gemm_w = true;
+      snprintf(nm, sizeof(nm), "model.layers.%d.layers.%d.0.bias", md->pre_fc_module[k], md->pre_fc_sub[k]);
+      L.b = add_param(h, nm, {L.out}, PERM_NONE);
+      h->pre.push_back(L);
+      d = L.out;
+      next_module = md->pre_fc_module[k] + 1;
+    }
+    h->feat = d;
+  }
+  // the gradients of everything registered so far (CNN + these FC layers) are final only at the very end of
+  // the backward pass: the data-parallel "late" bucket starts here
   h->conv_param_end = (h->nparams + 63) / 64 * 64;
-  h->featC = c; h->featHW = hh * ww; h->feat = c * hh * ww;
-  int fc_layer = h->U ? 2 : 1;
+  const bool trunk_perm = h->pre.empty();   // the consumer of the trunk features sees the conv layout
+  int fc_layer = next_module + (h->U ? 1 : 0);
   if (h->U) {
     int U = h->U;
-    h->o_wih = add_param(h, "model.layers.1.lstm_cell.weight_ih", {4 * U, h->feat}, PERM_FEAT_COLS);
+    char nm[96];
+    snprintf(nm, sizeof(nm), "model.layers.%d.lstm_cell.weight_ih", next_module);
+    h->wih_perm = trunk_perm;
+    if (h->X) {
+      h->o_wih = add_param(h, nm, {4 * U, h->feat + h->X}, PERM_WIH_EXTRA);
+      h->o_wihx = h->o_wih + (size_t)4 * U * h->feat;
+    } else {
+      h->o_wih = add_param(h, nm, {4 * U, h->feat}, trunk_perm ? PERM_FEAT_COLS : PERM_NONE);
+    }
     h->pinfo.back().gemm_w = true;
-    h->o_whh = add_param(h, "model.layers.1.lstm_cell.weight_hh", {4 * U, U}, PERM_NONE);
+    snprintf(nm, sizeof(nm), "model.layers.%d.lstm_cell.weight_hh", next_module);
+    h->o_whh = add_param(h, nm, {4 * U, U}, PERM_NONE);
     h->pinfo.back().gemm_w = true;
-    h->o_bih = add_param(h, "model.layers.1.lstm_cell.bias_ih", {4 * U}, PERM_NONE);
-    h->o_bhh = add_param(h, "model.layers.1.lstm_cell.bias_hh", {4 * U}, PERM_NONE);
+    snprintf(nm, sizeof(nm), "model.layers.%d.lstm_cell.bias_ih", next_module);
+    h->o_bih = add_param(h, nm, {4 * U}, PERM_NONE);
+    snprintf(nm, sizeof(nm), "model.layers.%d.lstm_cell.bias_hh", next_module);
+    h->o_bhh = add_param(h, nm, {4 * U}, PERM_NONE);
     h->D = U;
   } else {
     h->D = h->feat;
   }
-  int featperm_cols = h->U ? PERM_NONE : PERM_FEAT_COLS;
-  int featperm_rows = h->U ? PERM_NONE : PERM_FEAT_ROWS;
+  int featperm_cols = (h->U || !trunk_perm) ? PERM_NONE : PERM_FEAT_COLS;
+  int featperm_rows = (h->U || !trunk_perm) ? PERM_NONE : PERM_FEAT_ROWS;
   // dueling: the advantage hidden layer (model FC) and the value hidden layer read the same
   // input, so their weights / biases are placed back to back and run as ONE [2F x D] layer
   h->fused_hidden = h->dueling && ((size_t)h->F * h->D) % 4 == 0 && h->F % 4 == 0;
@@ -1493,7 +1634,19 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     size_t cc = (size_t)h->chunk_rows * opix * L.K;
     if (cc > maxcol) maxcol = cc;
   }
-  RT_TRY(dalloc(h, &h->xf, rows * (size_t)md->in_c * md->in_h * md->in_w, "xf"));
+  RT_TRY(dalloc(h, &h->xf, h->conv.empty() ? 1 : rows * (size_t)md->in_c * md->in_h * md->in_w, "xf"));
+  for (size_t k = 0; k < h->pre.size(); ++k) {
+    float *a = nullptr, *b2 = nullptr, *d = nullptr;
+    char nm[32];
+    snprintf(nm, sizeof(nm), "pre%d", (int)k);
+    RT_TRY(dalloc(h, &a, rows * h->pre[k].out, nm));
+    RT_TRY(dalloc(h, &b2, (size_t)h->M * h->pre[k].out));
+    RT_TRY(dalloc(h, &d, (size_t)h->M * h->pre[k].out));
+    h->pre_out.push_back(a);
+    h->pre_out2.push_back(b2);
+    h->d_pre.push_back(d);
+  }
+  if (!h->pre.empty() && !h->conv.empty()) RT_TRY(dalloc(h, &h->d_cfeat, (size_t)h->M * h->cfeat, "d_cfeat"));
   RT_TRY(dalloc(h, &h->col, maxcol));
   RT_TRY(dalloc(h, &h->dcol, maxcol));
   {
@@ -1618,6 +1771,8 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   if (A > maxN) maxN = A;
   for (auto& L : h->conv)
     if ((size_t)L.f > maxN) maxN = L.f;
+  for (auto& L : h->pre)
+    if ((size_t)L.out > maxN) maxN = L.out;
   RT_TRY(dalloc(h, &h->colsum_part, 2048 * maxN));
   RT_TRY(dalloc(h, &h->colsum_part2, 2048 * maxN));
   RT_TRY(dalloc(h, &h->sumsq_part, 1024));
@@ -1794,6 +1949,28 @@ int rt_learner_set_opt_state(rt_learner* h, int64_t adam_steps, double lr) {
   return RT_OK;
 }
 
+int rt_learner_get_aux_state(rt_learner* h, uint64_t* rng_counter, float* clip_ema, int32_t* clip_ema_init) {
+  RT_REQUIRE(h && rng_counter && clip_ema && clip_ema_init, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  RT_CUDA(cudaDeviceSynchronize());
+  float s[2];
+  RT_CUDA(cudaMemcpy(s, h->stats + 4, sizeof(s), cudaMemcpyDeviceToHost));
+  *rng_counter = h->rng_counter;
+  *clip_ema = s[0];
+  *clip_ema_init = s[1] > 0.5f ? 1 : 0;
+  return RT_OK;
+}
+
+int rt_learner_set_aux_state(rt_learner* h, uint64_t rng_counter, float clip_ema, int32_t clip_ema_init) {
+  RT_REQUIRE(h, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  RT_CUDA(cudaDeviceSynchronize());
+  const float s[2] = {clip_ema, clip_ema_init ? 1.f : 0.f};
+  RT_CUDA(cudaMemcpy(h->stats + 4, s, sizeof(s), cudaMemcpyHostToDevice));
+  h->rng_counter = rng_counter;
+  return RT_OK;
+}
+
 }  // extern "C"
 
 namespace {
@@ -1839,21 +2016,42 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
     RT_CUDA(cudaEventRecord(h->ev_fork, caller));
     RT_CUDA(cudaStreamWaitEvent(st, h->ev_fork, 0));
   }
-  const int B = h->B, T = h->T, P = h->P, n = h->n, U = h->U, M = h->M, Nq = h->Nq;
+  const int B = h->B, P = h->P, n = h->n, U = h->U, M = h->M, Nq = h->Nq;
   const size_t frame = (size_t)h->md.in_c * h->md.in_h * h->md.in_w;
   const uint8_t* all_x = (const uint8_t*)b->all_states[io->field_x];
   float* all_hx = U ? (float*)b->all_states[io->field_hx] : nullptr;
   float* all_cx = U ? (float*)b->all_states[io->field_cx] : nullptr;
   const float* all_init = U ? (const float*)b->all_states[io->field_initials] : nullptr;
+  const int X = h->X;
+  RT_REQUIRE(!X || (io->field_extra >= 0 && io->field_extra < RT_MAX_FIELDS && b->all_states[io->field_extra]),
+             "the model takes %d extra features: rt_learner_io.field_extra must name that batch leaf", X);
+  const float* all_extra = X ? (const float*)b->all_states[io->field_extra] : nullptr;
+  // bytes per observation row: uint8 frames, or float32 vectors without a CNN
+  const size_t xrow = frame * (h->conv.empty() ? sizeof(float) : 1);
+  // separately stacked target states (online history: per-row n-step): no row sharing between the passes
+  const bool sep_targets = b->target_states[io->field_x] != nullptr;
+  auto tview = [&](int row0) {
+    StateView sv;
+    sv.x = (const uint8_t*)b->target_states[io->field_x] + (size_t)row0 * B * xrow;
+    sv.extra = X ? (const float*)b->target_states[io->field_extra] + (size_t)row0 * B * X : nullptr;
+    sv.hx = U ? (float*)b->target_states[io->field_hx] + (size_t)row0 * B * U : nullptr;
+    sv.cx = U ? (float*)b->target_states[io->field_cx] + (size_t)row0 * B * U : nullptr;
+    sv.initials = U ? (const float*)b->target_states[io->field_initials] + (size_t)row0 * B : nullptr;
+    return sv;
+  };
   auto view = [&](int row0) {
     StateView sv;
-    sv.x = all_x + (size_t)row0 * B * frame;
+    sv.x = all_x + (size_t)row0 * B * xrow;
+    sv.extra = X ? all_extra + (size_t)row0 * B * X : nullptr;
     sv.hx = U ? all_hx + (size_t)row0 * B * U : nullptr;
     sv.cx = U ? all_cx + (size_t)row0 * B * U : nullptr;
     sv.initials = U ? all_init + (size_t)row0 * B : nullptr;
     return sv;
   };
   const float* feat = nullptr;
+  // (M, h->feat) trunk features of the training pass: deterministic buffer addresses, so the value set
+  // while the forward phase is issued / captured is also right when the phases replay from graphs
+  const float* train_feat = nullptr;
   const int rnn_boot = h->td.rnn_bootstrap ? 1 : 0;
 
   // ---- quantile fractions: injected (parity) or drawn on the device (one launch for the three
@@ -1895,6 +2093,7 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
     // heads the reference also evaluates are skipped.  states / target_states alias one stack,
     // and the write-back order (online first) is the reference's.
     if (P > 0) {
+      RT_REQUIRE(!sep_targets, "burn-in needs the overlapped state stack (replay history buffers)");
       for (int pass = 0; pass < 1 + rnn_boot; ++pass) {
         int row0 = pass == 0 ? 0 : n;
         StateView sv = view(row0);
@@ -1909,7 +2108,8 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
 
     // ---- bootstrap target (iqn.py:15-52): target net, then the action-selection net
     bool shared_cnn = false;
-    const bool merged = U > 0 && rnn_boot && T > 1;
+    const int R = h->R, BR = M / h->R;     // LSTM view of a pass: R steps of BR rows (R = T, BR = B by default)
+    const bool merged = U > 0 && rnn_boot && R > 1 && !sep_targets;
     if (merged) {
       // recurrent model with rnn_bootstrap: the target, selection and training recurrences are
       // independent, so run both CNNs + input-gate GEMMs first and then ALL recurrences in one
@@ -1920,38 +2120,43 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       // pass after them) runs on the side branch with the second activation set while the main
       // branch does the online network's; they meet at the one LSTM launch and at the target kernel.
       const bool fork_fwd = h->side_active && h->overlap_fwd && h->td.double_q && cnn_all_implicit(h);
+      const bool has_cnn = !h->conv.empty();
+      const float* f = nullptr;
       if (h->td.double_q) {
         // the target pass (rows [n, T+n)) and the online pass (rows [0, T+n)) read the same frames:
         // convert them to fp32 NHWC once
-        RT_TRY(launch_frames_to_nhwc(st, svt.x, h->xf, M + n * B, h->md.in_c, h->md.in_h, h->md.in_w,
-                                     (float)(1.0 / 255.0), h->rn));
+        if (has_cnn)
+          RT_TRY(launch_frames_to_nhwc(st, svt.x, h->xf, M + n * B, h->md.in_c, h->md.in_h, h->md.in_w,
+                                       (float)(1.0 / 255.0), h->rn));
+        const float* xf_t = has_cnn ? h->xf + (size_t)n * B * frame : nullptr;
         if (fork_fwd) {
           SideCtx sd;
           RT_TRY(side_begin(h, st, &sd));
-          RT_TRY(cnn_forward(h, sd.st, h->pr[1], sv.x, M, h->xf + (size_t)n * B * frame, true));
-          RT_TRY(lstm_xgates(h, sd.st, h->pr[1], h->c_out2.back(), M, h->xg2, sd.gx));
+          RT_TRY(feature_forward(h, sd.st, h->pr[1], sv.x, M, &f, xf_t, true));
+          RT_TRY(lstm_xgates(h, sd.st, h->pr[1], f, M, h->xg2, sv.extra, sd.gx));
         } else {
-          RT_TRY(cnn_forward(h, st, h->pr[1], sv.x, M, h->xf + (size_t)n * B * frame));
-          RT_TRY(lstm_xgates(h, st, h->pr[1], h->c_out.back(), M, h->xg2));
+          RT_TRY(feature_forward(h, st, h->pr[1], sv.x, M, &f, xf_t));
+          RT_TRY(lstm_xgates(h, st, h->pr[1], f, M, h->xg2, sv.extra));
         }
       } else {
-        RT_TRY(cnn_forward(h, st, h->pr[1], sv.x, M));
-        RT_TRY(lstm_xgates(h, st, h->pr[1], h->c_out.back(), M, h->xg2));
+        RT_TRY(feature_forward(h, st, h->pr[1], sv.x, M, &f));
+        RT_TRY(lstm_xgates(h, st, h->pr[1], f, M, h->xg2, sv.extra));
       }
       SeqDesc seqs[3];
       int ns = 0;
       seqs[ns++] = SeqDesc{h->pr[1], h->xg2, sv.hx, sv.cx, sv.initials, h->h_all2, 1, false};
       if (h->td.double_q) {
-        RT_TRY(cnn_forward(h, st, h->pr[0], svt.x, M + n * B, h->xf));
-        RT_TRY(lstm_xgates(h, st, h->pr[0], h->c_out.back(), M + n * B, h->xg));
+        RT_TRY(feature_forward(h, st, h->pr[0], svt.x, M + n * B, &f, has_cnn ? h->xf : nullptr));
+        RT_TRY(lstm_xgates(h, st, h->pr[0], f, M + n * B, h->xg, svt.extra));
         seqs[ns++] = SeqDesc{h->pr[0], h->xg + (size_t)n * B * 4 * U, sv.hx, sv.cx, sv.initials, h->h_all3, 2, false};
       } else {
-        RT_TRY(cnn_forward(h, st, h->pr[0], svt.x, M));
-        RT_TRY(lstm_xgates(h, st, h->pr[0], h->c_out.back(), M, h->xg));
+        RT_TRY(feature_forward(h, st, h->pr[0], svt.x, M, &f));
+        RT_TRY(lstm_xgates(h, st, h->pr[0], f, M, h->xg, svt.extra));
       }
+      train_feat = f;
       seqs[ns++] = SeqDesc{h->pr[0], h->xg, svt.hx, svt.cx, svt.initials, h->h_all, 0, true};
       if (fork_fwd) RT_TRY(side_join(h, st));
-      RT_TRY(lstm_run(h, st, seqs, ns, T, B));
+      RT_TRY(lstm_run(h, st, seqs, ns, R, BR));
       if (fork_fwd) {
         // target heads on the side branch (second set, q straight into tq); selection and training
         // heads on the main branch; the bootstrap target needs all three
@@ -1983,24 +2188,29 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       RT_LAUNCH_CHECK();
       feat = h->h_all;
     } else {
-      StateView sv = view(P + n);
-      int ts = rnn_boot ? T : 1;
+      StateView sv = sep_targets ? tview(P) : view(P + n);
+      int ts = rnn_boot ? R : 1;
       RT_TRY(trunk_forward(h, st, h->pr[1], sv, M, ts, &feat));
       RT_TRY(heads_forward(h, st, h->pr[1], feat, M, tau_seg[0]));
       RT_CUDA(cudaMemcpyAsync(h->tq, h->q, (size_t)h->MQ * h->A * sizeof(float), cudaMemcpyDeviceToDevice, st));
       if (!h->td.double_q) {
         // same network, same states: only the quantile fractions differ -> reuse the whole trunk
         RT_TRY(heads_forward(h, st, h->pr[1], feat, M, tau_seg[1]));
+      } else if (sep_targets) {
+        // separately stacked target states: the online network's selection pass is a pass of its own
+        const float* f = nullptr;
+        RT_TRY(trunk_forward(h, st, h->pr[0], sv, M, ts, &f));
+        RT_TRY(heads_forward(h, st, h->pr[0], f, M, tau_seg[1]));
       } else {
         // online net on target_states = rows [n, T+n) of the stack; the training forward below
         // needs rows [0, T): run the online CNN ONCE over the T+n distinct rows and let both
         // passes read their slice (saves (T-n)/(2T) of the online conv work)
         StateView s0 = view(P);
-        RT_TRY(cnn_forward(h, st, h->pr[0], s0.x, M + n * B));
+        RT_TRY(feature_forward(h, st, h->pr[0], s0.x, M + n * B, &train_feat));
         shared_cnn = true;
-        const float* f = h->c_out.back() + (size_t)n * B * h->feat;
+        const float* f = train_feat + (size_t)n * B * h->feat;
         if (U) {
-          RT_TRY(lstm_forward(h, st, h->pr[0], f, M, ts, sv.hx, sv.cx, sv.initials));
+          RT_TRY(lstm_forward(h, st, h->pr[0], f, M, ts, sv.hx, sv.cx, sv.initials, sv.extra));
           f = h->h_all;
         }
         RT_TRY(heads_forward(h, st, h->pr[0], f, M, tau_seg[1]));
@@ -2014,13 +2224,16 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
 
       // ---- training forward (iqn.py:54-129)
       if (shared_cnn) {
-        feat = h->c_out.back();
+        feat = train_feat;
         if (U) {
-          RT_TRY(lstm_forward(h, st, h->pr[0], feat, M, T, svt.hx, svt.cx, svt.initials));
+          RT_TRY(lstm_forward(h, st, h->pr[0], feat, M, R, svt.hx, svt.cx, svt.initials, svt.extra));
           feat = h->h_all;
         }
       } else {
-        RT_TRY(trunk_forward(h, st, h->pr[0], svt, M, T, &feat));
+        RT_TRY(trunk_forward(h, st, h->pr[0], svt, M, R, &feat));
+        // trunk features of the training pass (the LSTM's input): what the backward pass reads
+        train_feat = h->pre.empty() ? (h->conv.empty() ? reinterpret_cast<const float*>(svt.x) : h->c_out.back())
+                                    : h->pre_out.back();
       }
     }
     // ---- training heads + loss (iqn.py:54-129)
@@ -2056,9 +2269,9 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
     if (part != 2) {
       RT_CUDA(cudaMemsetAsync(h->grad, 0, h->nparams * sizeof(float), st));
       RT_TRY(heads_backward(h, st, h->pr[0], feat, M, actions));
-      if (U) RT_TRY(lstm_backward(h, st, h->pr[0], h->c_out.back(), M, T, svt.initials));
+      if (U) RT_TRY(lstm_backward(h, st, h->pr[0], train_feat, M, h->R, svt.initials, svt.extra));
     }
-    if (part != 1) RT_TRY(cnn_backward(h, st, h->pr[0], svt.x, M, U ? h->dfeat : h->dfeatq));
+    if (part != 1) RT_TRY(features_backward(h, st, h->pr[0], svt.x, M, U ? h->dfeat : h->dfeatq));
     return side_join(h, st);
   };
   auto backward_phase = [&]() -> int { return backward_part(0); };
@@ -2072,9 +2285,9 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   const bool want_graph = forked && h->steps_done >= 2 && !h->gx.profile && !h->lstm_dbg;
   rt_learner::StepGraphs* sg = nullptr;
   if (want_graph) {
-    const void* key[10] = {all_x, all_hx, all_cx, all_init, b->returns, b->nsteps, b->target_masks,
+    const void* key[12] = {all_x, all_hx, all_cx, all_init, b->returns, b->nsteps, b->target_masks,
                            b->policy_outputs[io->po_field_actions], b->importance_weights,
-                           (const void*)(uintptr_t)(split_bwd ? 1 : 0)};
+                           (const void*)(uintptr_t)(split_bwd ? 1 : 0), all_extra, b->target_states[io->field_x]};
     for (auto& g : h->graphs)
       if (memcmp(g.key, key, sizeof(key)) == 0) sg = &g;
     if (!sg) {
@@ -2165,17 +2378,19 @@ int rt_learner_flat_buffer(rt_learner* h, int32_t which, float** dev_ptr, int64_
   return RT_OK;
 }
 
-int rt_learner_act(rt_learner* h, int32_t E, const uint8_t* x, const float* hx, const float* cx,
-                   const float* initials, const float* taus_host, float* qvalues, float* h_out,
-                   float* c_out, void* stream) {
+int rt_learner_act(rt_learner* h, int32_t E, const void* x, const float* extra, const float* hx,
+                   const float* cx, const float* initials, const float* taus_host, float* qvalues,
+                   float* h_out, float* c_out, void* stream) {
   RT_REQUIRE(h && x && qvalues && E >= 1, "bad argument");
   RT_REQUIRE(E <= h->max_rows && (size_t)E * h->Nq <= (size_t)h->MQ,
              "acting batch of %d envs exceeds the learner's buffers (max %d)", E, h->MQ / h->Nq);
   RT_REQUIRE(!h->U || (hx && cx && initials && h_out && c_out), "recurrent model needs hx/cx/initials");
+  RT_REQUIRE(!h->X || extra, "the model takes %d extra features per observation", h->X);
   RT_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   StateView sv;
-  sv.x = x;
+  sv.x = static_cast<const uint8_t*>(x);
+  sv.extra = extra;
   sv.hx = const_cast<float*>(hx);
   sv.cx = const_cast<float*>(cx);
   sv.initials = initials;

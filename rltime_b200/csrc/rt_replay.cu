@@ -7,7 +7,7 @@
 //   state field f : uint8 [NS][bytes_f]     next_state leaves (frames 28,224 B, hx, cx, ...)
 //   po field f    : uint8 [NS][bytes_f]     policy_output leaves (actions, qvalues)
 //   reward f64[NS], done u8[NS]
-//   pos2slot      : int32 [max_envs][N]     (env, env offset mod N) -> slot
+//   pos2slot      : int32 [max_envs][N+1]   (env, env offset mod (N+1)) -> slot
 //   sum/min tree  : f64 [2*cap]             root at 1, leaves at cap+idx (segment_tree.py)
 //   seq_env/base  : prioritization idx -> (dense env, base env offset)
 //
@@ -873,7 +873,7 @@ int ensure_batch(rt_replay* h, BatchSlot& bs, int B) {
 // Assemble + gather for the columns already written to bs.col_*.
 int assemble_and_gather(rt_replay* h, BatchSlot& bs, int B, cudaStream_t st) {
   AssembleParams ap;
-  ap.B = B; ap.S = h->S; ap.n = h->n; ap.P = h->P; ap.T = h->T; ap.N = h->N;
+  ap.B = B; ap.S = h->S; ap.n = h->n; ap.P = h->P; ap.T = h->T; ap.N = h->N + 1;   // pos2slot ring length
   ap.prioritized = h->per ? 1 : 0;
   ap.pos2slot = h->d_pos2slot; ap.col_env = bs.col_env; ap.col_start = bs.col_start;
   ap.col_base = bs.col_base; ap.col_weight = bs.col_weight; ap.env_ids = h->d_env_ids;
@@ -1039,7 +1039,9 @@ int rt_replay_create(const rt_replay_config* c, rt_replay** out) {
   }
   RT_CUDA(rt::dmalloc(&h->d_reward, (size_t)h->NS));
   RT_CUDA(rt::dmalloc(&h->d_done, (size_t)h->NS));
-  RT_CUDA(rt::dmalloc(&h->d_pos2slot, (size_t)c->max_envs * h->N));
+  // N + 1 entries per env: an env that alone holds all N transitions still needs the entry of the evicted
+  // "zombie" at offset first-1 (it backs the state of `first`), i.e. N + 1 live positions
+  RT_CUDA(rt::dmalloc(&h->d_pos2slot, (size_t)c->max_envs * (h->N + 1)));
   RT_CUDA(rt::dmalloc(&h->d_env_ids, (size_t)c->max_envs));
   RT_CUDA(rt::dmalloc(&h->d_gpow, (size_t)h->n));
   RT_CUDA(cudaMemcpy(h->d_gpow, h->gpow.data(), h->n * sizeof(double), cudaMemcpyHostToDevice));
@@ -1137,7 +1139,7 @@ int rt_replay_append(rt_replay* h, int64_t m, const int32_t* env, const int64_t*
     h->u_slot.push_back(s);
     h->u_reward.push_back(reward[i]);
     h->u_done.push_back(done[i] ? 1 : 0);
-    h->u_p2s_at.push_back((long long)e * h->N + (pos % h->N));
+    h->u_p2s_at.push_back((long long)e * (h->N + 1) + (pos % (h->N + 1)));
     h->u_p2s_slot.push_back(s);
     if (h->per) {
       // activation of a new overlapped sequence (:152-172)
@@ -1343,25 +1345,32 @@ int rt_replay_update_losses_last(rt_replay* h, const float* td_abs_device, void*
     if (h->h_td) cudaFreeHost(h->h_td);
     if (h->h_idx) cudaFreeHost(h->h_idx);
     RT_CUDA(cudaMallocHost(&h->h_td, rows * sizeof(float)));
-    RT_CUDA(cudaMallocHost(&h->h_idx, 1024 * sizeof(int)));
+    RT_CUDA(cudaMallocHost(&h->h_idx, 3 * 1024 * sizeof(long long)));
     h->h_td_cap = rows;
   }
+  RT_REQUIRE(B <= 1024, "batch of %d sequences exceeds the write-back staging", B);
   BatchSlot& bs = h->batch[h->cur];
+  // (env, base offset) of every drawn sequence AS RECORDED BY THE DRAW (k_per_draw writes col_env /
+  // col_base into the batch slot): the reference writes back through the loss_indices captured at draw
+  // time (prioritized_replay_history.py:335-338) and skips rows evicted since (:254-257).  Resolving
+  // the drawn prioritization indices through seq_env / seq_base now instead would go wrong when an
+  // append between the draw and this call freed or re-assigned one of them.
+  long long* h_base = reinterpret_cast<long long*>(h->h_idx);
+  int* h_env = reinterpret_cast<int*>(h_base + 1024);
   RT_CUDA(cudaMemcpyAsync(h->h_td, td_abs_device, rows * sizeof(float), cudaMemcpyDeviceToHost, st));
-  RT_CUDA(cudaMemcpyAsync(h->h_idx, bs.idxes, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaMemcpyAsync(h_base, bs.col_base, B * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  RT_CUDA(cudaMemcpyAsync(h_env, bs.col_env, B * sizeof(int), cudaMemcpyDeviceToHost, st));
   RT_CUDA(cudaEventRecord(h->ev, st));
   RT_CUDA(cudaEventSynchronize(h->ev));
   std::vector<int64_t> pairs(rows * 2);
   std::vector<double> losses(rows);
   for (int t = 0; t < h->T; ++t)
     for (int b = 0; b < B; ++b) {
-      int idx = h->h_idx[b];
       size_t r = (size_t)t * B + b;
-      pairs[2 * r] = h->seq_env[idx];
-      pairs[2 * r + 1] = h->seq_base[idx] + t;
+      pairs[2 * r] = h_env[b];
+      pairs[2 * r + 1] = h_base[b] + t;
       losses[r] = (double)h->h_td[r];
     }
-  // a sequence drawn from a since-freed leaf cannot occur: leaves are zeroed on free
   return rt_replay_update_losses(h, (int64_t)rows, pairs.data(), losses.data(), stream);
 }
 

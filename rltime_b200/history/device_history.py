@@ -420,6 +420,12 @@ class DevicePrioritizedReplayHistoryBuffer(DeviceReplayHistoryBuffer):
     def __init__(self, alpha=0.6, beta=0.4, beta_anneal=False, eps=1e-6, overlap=None,
                  max_weight_factor=0.9, global_importance_scaling=False, **kwargs):
         super().__init__(**kwargs)
+        if self.avoid_episode_crossing:
+            # the reference shifts prioritized sequences too (prioritized_replay_history.py:317-318);
+            # the device draw has no refine step yet, and silently ignoring the flag would change what
+            # is trained on
+            raise NotImplementedError(
+                "avoid_episode_crossing=True is supported by the uniform device replay buffer only")
         self._alpha, self._beta, self._beta_anneal, self._eps = alpha, beta, beta_anneal, eps
         self._max_weight_factor = max_weight_factor
         self._global_importance_scaling = global_importance_scaling

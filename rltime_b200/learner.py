@@ -21,10 +21,15 @@ class DeviceLearner:
                  nstep_target=1, gamma=0.99, double_q=False, rnn_bootstrap=False,
                  vf_scale_epsilon=None, huber_kappa=1.0, clip_grad=None, adam_epsilon=1e-8,
                  lr=1e-3, loss_aggregation="mean", seed=0, device=None, gemm="tf32", policy="iqn",
-                 loss_mode="huber", loss_timestep_aggregation=None, clip_grad_dynamic_alpha=None):
+                 loss_mode="huber", loss_timestep_aggregation=None, clip_grad_dynamic_alpha=None,
+                 pre_fc=(), extra_dim=0, rnn_steps_train=None):
         """policy="iqn": IQNPolicy + IQN trainer (policies/torch/iqn.py, training/torch/iqn.py);
         policy="dqn": DQNPolicy + DQN trainer (policies/torch/dqn.py, training/torch/dqn.py:
-        Rainbow-style dueling / double-Q / n-step / PER without the quantile layer)."""
+        Rainbow-style dueling / double-Q / n-step / PER without the quantile layer).
+        in_shape: (C, H, W) uint8 frames, or (D,) float32 vectors with conv == [] (MLP models);
+        pre_fc: FC modules (models/torch/modules/fc.py) between the CNN / observation and the LSTM /
+        last FC module, one list of layer widths per module; extra_dim: width of the extra feature
+        vector of a tuple observation, fed to the LSTM (models/torch/sequential.py:146-165)."""
         import torch
         if not torch.cuda.is_available():
             raise _lib.RtError("rltime_b200 learner needs a CUDA device (no CPU fallback)")
@@ -32,8 +37,27 @@ class DeviceLearner:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
             else torch.device(device)
         md = _lib.ModelDesc()
+        in_shape = tuple(int(d) for d in in_shape)
+        if len(conv) == 0:
+            assert len(in_shape) >= 1, "MLP models take a float32 vector observation"
+            in_shape = (int(np.prod(in_shape)), 1, 1)
         md.in_c, md.in_h, md.in_w = in_shape
+        self.obs_dtype = np.uint8 if len(conv) else np.float32
         md.num_conv = len(conv)
+        md.extra_dim = int(extra_dim)
+        self.X = int(extra_dim)
+        module = 1 if len(conv) else 0
+        k = 0
+        for sizes in pre_fc:
+            for j, sz in enumerate(sizes):
+                assert k < _lib.RT_MAX_PRE_FC, "too many FC layers in front of the LSTM / last FC module"
+                md.pre_fc_size[k], md.pre_fc_module[k], md.pre_fc_sub[k] = int(sz), module, j
+                k += 1
+            module += 1
+        md.num_pre_fc = k
+        # indices of the LSTM / last FC module in SequentialModel.layers ('layer{i}_state' keys)
+        self.lstm_module = module
+        self.fc_module = module + (1 if lstm_units else 0)
         for i, (f, k, s) in enumerate(conv):
             md.conv_filters[i], md.conv_kernel[i], md.conv_stride[i] = f, k, s
         md.lstm_units = lstm_units
@@ -58,6 +82,9 @@ class DeviceLearner:
         assert loss_mode == "huber" or policy == "dqn", "IQN uses the quantile-Huber loss"
         td.loss_mse = 1 if loss_mode == "mse" else 0
         td.clip_grad_dynamic_alpha = -1.0 if clip_grad_dynamic_alpha is None else float(clip_grad_dynamic_alpha)
+        td.rnn_steps_train = int(rnn_steps_train or 0)
+        assert not td.rnn_steps_train or nstep_train % td.rnn_steps_train == 0, \
+            "nstep_train must be divisible by rnn_steps_train"
         td.gamma = gamma
         td.vf_scale_epsilon = vf_scale_epsilon or 0.0
         td.huber_kappa = huber_kappa
@@ -85,7 +112,10 @@ class DeviceLearner:
             nd = C.c_int32()
             _lib.check(self._lib.rt_learner_param_info(self._h, i, name, 128, shape, C.byref(nd)))
             self.param_info.append((name.value.decode(), tuple(shape[:nd.value])))
-        self.io = _lib.LearnerIO(0, 1, 2, 3, 0)
+        # leaf order of a flattened next_state: x (, extra), hx, cx, initials
+        e = 1 if self.X else 0
+        self.io = _lib.LearnerIO(0, 1 + e, 2 + e, 3 + e, 0, 1 if self.X else -1) if lstm_units else \
+            _lib.LearnerIO(0, -1, -1, -1, 0, -1)
 
     def close(self):
         if getattr(self, "_h", None) is not None:
@@ -128,7 +158,7 @@ class DeviceLearner:
         sd = self.state_dict()
         if self.policy == "iqn":
             sd["embedding_range"] = torch.arange(
-                1, self.param_info[-2][1][1] + 1, dtype=torch.float32)
+                1, dict(self.param_info)["quantile_layer.weight"][1] + 1, dtype=torch.float32)
         f = io.BytesIO()
         torch.save(sd, f)
         return f.getvalue()
@@ -141,20 +171,34 @@ class DeviceLearner:
     # ---- checkpoint / resume ------------------------------------------
     def training_state(self):
         """Everything needed to resume training bit-exactly: online / target weights, Adam
-        moments, Adam step counter and learning rate (the reference checkpoint,
+        moments, Adam step counter, learning rate, the counter of the device RNG behind the IQN
+        quantile fractions and the dynamic grad-clip moving average (the reference checkpoint,
         policy_trainer.py:170-185, holds the policy weights only and cannot resume)."""
+        st = self.optimizer_state()
+        st.update({"online": self.state_dict(_lib.RT_BUF_ONLINE), "target": self.state_dict(_lib.RT_BUF_TARGET)})
+        return st
+
+    def optimizer_state(self):
+        """training_state() without the two weight sets (what a trainer checkpoint stores next to
+        policy_state)."""
         steps, lr = C.c_int64(), C.c_double()
         _lib.check(self._lib.rt_learner_get_opt_state(self._h, C.byref(steps), C.byref(lr)))
-        return {"online": self.state_dict(_lib.RT_BUF_ONLINE), "target": self.state_dict(_lib.RT_BUF_TARGET),
-                "adam_m": self.state_dict(_lib.RT_BUF_ADAM_M), "adam_v": self.state_dict(_lib.RT_BUF_ADAM_V),
-                "adam_steps": steps.value, "lr": lr.value}
+        rng, ema, ema_init = C.c_uint64(), C.c_float(), C.c_int32()
+        _lib.check(self._lib.rt_learner_get_aux_state(self._h, C.byref(rng), C.byref(ema), C.byref(ema_init)))
+        return {"adam_m": self.state_dict(_lib.RT_BUF_ADAM_M), "adam_v": self.state_dict(_lib.RT_BUF_ADAM_V),
+                "adam_steps": steps.value, "lr": lr.value, "rng_counter": rng.value,
+                "clip_ema": ema.value, "clip_ema_init": ema_init.value}
 
     def load_training_state(self, st):
-        self.load_state_dict(st["online"], _lib.RT_BUF_ONLINE)
-        self.load_state_dict(st["target"], _lib.RT_BUF_TARGET)
+        if "online" in st:
+            self.load_state_dict(st["online"], _lib.RT_BUF_ONLINE)
+            self.load_state_dict(st["target"], _lib.RT_BUF_TARGET)
         self.load_state_dict(st["adam_m"], _lib.RT_BUF_ADAM_M)
         self.load_state_dict(st["adam_v"], _lib.RT_BUF_ADAM_V)
         _lib.check(self._lib.rt_learner_set_opt_state(self._h, int(st["adam_steps"]), float(st["lr"])))
+        _lib.check(self._lib.rt_learner_set_aux_state(
+            self._h, int(st.get("rng_counter", 0)), float(st.get("clip_ema", 0.0)),
+            int(st.get("clip_ema_init", 0))))
 
     def params_changed(self):
         """After writing flat(RT_BUF_ONLINE / RT_BUF_TARGET) directly (e.g. a broadcast)."""
@@ -275,8 +319,11 @@ class DeviceLearner:
 
 
 def batch_from_tensors(all_x, all_hx, all_cx, all_initials, returns, nsteps, target_masks, actions,
-                       importance_weights, n):
+                       importance_weights, n, all_extra=None, targets=None):
     """Builds an rt_batch over caller-owned CUDA tensors (time-major, (S+n, B, ...) / (S, B)).
+    Leaf order = DeviceLearner.io: x (, extra), hx, cx, initials.  `targets`: optional dict of
+    separately stacked target states {"x", "extra", "hx", "cx", "initials"} of (S, B, ...) each
+    (batches whose n-step varies per row); the all_* tensors then only hold the S training rows.
     Returns (Batch, keepalive list)."""
     b = _lib.Batch()
     S, B = returns.shape
@@ -288,13 +335,22 @@ def batch_from_tensors(all_x, all_hx, all_cx, all_initials, returns, nsteps, tar
         keep.append(t)
         return t.data_ptr()
     import torch
-    b.all_states[0] = ptr(all_x, torch.uint8)
+    b.all_states[0] = ptr(all_x, all_x.dtype)
+    assert all_x.dtype in (torch.uint8, torch.float32)
     nf = 1
+    if all_extra is not None:
+        b.all_states[nf] = ptr(all_extra, torch.float32)
+        nf += 1
     if all_hx is not None:
-        b.all_states[1] = ptr(all_hx, torch.float32)
-        b.all_states[2] = ptr(all_cx, torch.float32)
-        b.all_states[3] = ptr(all_initials, torch.float32)
-        nf = 4
+        b.all_states[nf] = ptr(all_hx, torch.float32)
+        b.all_states[nf + 1] = ptr(all_cx, torch.float32)
+        b.all_states[nf + 2] = ptr(all_initials, torch.float32)
+        nf += 3
+    if targets is not None:
+        order = ["x"] + (["extra"] if all_extra is not None else []) + \
+            (["hx", "cx", "initials"] if all_hx is not None else [])
+        for i, k in enumerate(order):
+            b.target_states[i] = ptr(targets[k], all_x.dtype if k == "x" else torch.float32)
     b.num_state_fields = nf
     b.policy_outputs[0] = ptr(actions, torch.int64)
     b.num_po_fields = 1

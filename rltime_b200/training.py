@@ -1,4 +1,4 @@
-"""Trainer-side mirror: an IQN trainer with the reference's constructor / train() surface whose
+"""Trainer-side mirror: IQN / DQN trainers with the reference's constructor / train() surface whose
 learner, history buffer and acting-time inference all run in librltime_b200.so.
 
 Mirrors (paths in the reference tree):
@@ -22,33 +22,84 @@ import numpy as np
 from . import _lib
 from .history import get_types as _history_types
 from .init import init_params
-from .learner import DeviceLearner
+from .learner import DeviceLearner, batch_from_tensors
+
+
+def _layer_kind(layer):
+    t = layer.get("type")
+    if isinstance(t, str):
+        return t
+    return {"CNN": "cnn", "FC": "fc", "LSTM": "lstm"}.get(getattr(t, "__name__", ""), str(t))
 
 
 def parse_model_config(model_config):
-    """{'type': 'sequential', 'args': {'layer_configs': [cnn, (lstm), fc]}} (configs/models/*.json)
-    -> (conv list, lstm_units, fc_size)."""
-    assert model_config.get("type") in ("sequential", None) or not isinstance(model_config.get("type"), str), \
-        "only the sequential model family is supported"
-    layers = model_config["args"]["layer_configs"]
-    kinds = [l["type"] for l in layers]
-    assert kinds in (["cnn", "lstm", "fc"], ["cnn", "fc"]), \
-        "supported topologies: cnn -> [lstm] -> fc (got %s)" % kinds
-    conv = [(int(l["filters"]), int(l["kernel"]), int(l["stride"])) for l in layers[0]["args"]["layers"]]
-    lstm_units = int(layers[1]["args"]["num_units"]) if "lstm" in kinds else 0
-    fc_args = layers[-1].get("args", {})
-    assert fc_args.get("fc_count", 1) == 1 and not fc_args.get("batch_norm", False) and \
-        fc_args.get("activation", "relu") == "relu", "only a single ReLU FC layer is supported"
-    return conv, lstm_units, int(fc_args["fc_size"])
+    """{'type': 'sequential', 'args': {'layer_configs': [...]}} (configs/models/*.json,
+    models/torch/sequential.py:15-66) -> dict(conv, pre_fc, lstm_units, fc_size).
+
+    Supported module sequences: [cnn] -> fc* -> [lstm] -> fc, i.e. nature_cnn_fc512,
+    nature_cnn_lstm512_fc512, nature_cnn_fc512_lstm512_fc512 and mlp_2x64 of the reference's
+    configs/models.  Every FC module but the last may use fc_count > 1 (fc.py:18-24)."""
+    t = model_config.get("type")
+    assert t in ("sequential", None) or not isinstance(t, str), "only the sequential model family is supported"
+    args = model_config.get("args", {})
+    assert args.get("extra_input_layer") is None, \
+        "extra_input_layer: only the default (the LSTM layer, sequential.py:67-79) is supported"
+    layers = args["layer_configs"]
+    kinds = [_layer_kind(l) for l in layers]
+    assert kinds and kinds[-1] == "fc", \
+        "the last module must be an FC module (IQN injected before an LSTM is not supported), got %s" % kinds
+    conv, pre_fc, lstm_units = [], [], 0
+    i = 0
+    if kinds[0] == "cnn":
+        conv = [(int(l["filters"]), int(l["kernel"]), int(l["stride"])) for l in layers[0]["args"]["layers"]]
+        i = 1
+
+    def fc_args(layer):
+        a = layer.get("args", {})
+        assert not a.get("batch_norm", False) and a.get("activation", "relu") == "relu", \
+            "FC modules: only ReLU without batch-norm is supported"
+        return int(a["fc_size"]), int(a.get("fc_count", 1))
+    while i < len(layers) - 1 and kinds[i] == "fc":
+        size, count = fc_args(layers[i])
+        pre_fc.append([size] * count)
+        i += 1
+    if i < len(layers) - 1:
+        assert kinds[i] == "lstm" and i == len(layers) - 2, \
+            "supported topologies: [cnn] -> fc* -> [lstm] -> fc (got %s)" % kinds
+        lstm_units = int(layers[i]["args"]["num_units"])
+    size, count = fc_args(layers[-1])
+    assert count == 1, "fc_count > 1 is supported in every FC module but the last one"
+    return {"conv": conv, "pre_fc": pre_fc, "lstm_units": lstm_units, "fc_size": size}
+
+
+def parse_observation_space(space):
+    """Box -> (shape, 0); Tuple(main Box, 1-D extra Boxes...) -> (main shape, total extra width)
+    (models/torch/torch_model.py:28-56)."""
+    if hasattr(space, "spaces"):
+        main = space.spaces[0]
+        extra = 0
+        for s in space.spaces[1:]:
+            assert len(s.shape) == 1, "extra observation spaces must be 1-D"
+            extra += int(s.shape[0])
+        return tuple(main.shape), extra
+    return tuple(space.shape), 0
 
 
 class DevicePolicy:
-    """Actor-facing policy backed by the learner's online network (rt_learner_act)."""
+    """Actor-facing policy backed by the learner's online network (rt_learner_act).
+
+    The recurrent state stays on the device between calls: actor_predict reads the previous call's
+    h / c there and the episode-start mask is applied by the LSTM kernel, so a vector step costs one
+    H2D of the observations (pinned staging) and one D2H of [q-values | h | c] -- the copy of h, c is
+    needed because the reference's acting schema stores them with every transition
+    (acting/acting_interface.py:83-90, lstm.py:157-161)."""
 
     def __init__(self, learner, num_actions):
         self.learner = learner
         self.num_actions = num_actions
-        self._last = None        # (h, c) device tensors of the previous act call
+        self._dev_state = None    # (h, c) device tensors produced by the last actor_predict
+        self._host_state = None   # their host copies (what make_input_state hands out)
+        self._stage = {}
 
     def is_recurrent(self):
         return self.learner.U > 0
@@ -60,51 +111,118 @@ class DevicePolicy:
         self.learner.load_state(state)
 
     def make_input_state(self, inp, initials):
-        """SequentialModel.make_input_state + LSTM.get_state: last recurrent state masked by
-        the episode-start flags."""
+        """SequentialModel.make_input_state + LSTM.get_state (sequential.py:128-144, lstm.py:131-161):
+        {'x': obs, 'layer{i}_state': ...} with the last recurrent state masked by the episode starts."""
         initials = np.asarray(initials).astype("float32")
-        state = {"x": inp, "layer0_state": {}}
+        L = self.learner
+        state = {"x": inp}
+        li = L.lstm_module if L.U else -1
+        for i in range(L.fc_module + 1):
+            state["layer%d_state" % i] = {}
         if self.is_recurrent():
-            E, U = len(initials), self.learner.U
-            if self._last is None:
+            E, U = len(initials), L.U
+            if self._host_state is None:
                 assert np.all(initials), "first call must be all-initial states"
                 hx = np.zeros((E, U), np.float32)
                 cx = np.zeros((E, U), np.float32)
             else:
-                hx, cx = (t.cpu().numpy() for t in self._last)
+                hx, cx = self._host_state
             mask = (1 - initials)[:, None]
-            state["layer1_state"] = {"hx": hx * mask, "cx": cx * mask, "initials": initials}
-            state["layer2_state"] = {}
-        else:
-            state["layer1_state"] = {}
+            self._handed_hx = hx * mask      # identity tag: actor_predict recognises its own state
+            state["layer%d_state" % li] = {"hx": self._handed_hx, "cx": cx * mask, "initials": initials}
         return state
 
-    def actor_predict(self, state, timesteps=1, for_eval=False):
+    def _pinned(self, key, shape, dtype):
+        import torch
+        t = self._stage.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = self._stage[key] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+        return t
+
+    def actor_predict(self, state, timesteps=1, for_eval=False, taus=None):
+        """DQNPolicy.actor_predict (policies/torch/dqn.py:132-148) for one time-step."""
         import torch
         assert timesteps == 1, "acting runs one time-step at a time"
         L = self.learner
         dev = L.device
-        x = torch.as_tensor(np.ascontiguousarray(state["x"]), device=dev)
-        assert x.dtype == torch.uint8, "observations must be uint8 frames"
-        E = x.shape[0]
-        q = torch.empty(E, self.num_actions, dtype=torch.float32, device=dev)
+        obs = state["x"]
+        extra = None
+        if isinstance(obs, (tuple, list)):
+            extra = np.concatenate([np.asarray(e, dtype=np.float32).reshape(len(e), -1) for e in obs[1:]], axis=1)
+            obs = obs[0]
+        obs = np.ascontiguousarray(obs, dtype=L.obs_dtype)
+        E = obs.shape[0]
+        hx_in = self._pinned("x", obs.shape, torch.from_numpy(obs[:0]).dtype)
+        hx_in.numpy()[...] = obs
+        x = hx_in.to(dev, non_blocking=True)
         null = C.c_void_p()
+        q = torch.empty(E, self.num_actions, dtype=torch.float32, device=dev)
+        ex_p = null
+        if L.X:
+            assert extra is not None and extra.shape[1] == L.X, "tuple observation with %d extra features expected" % L.X
+            ex = torch.from_numpy(np.ascontiguousarray(extra)).to(dev)
+            ex_p = C.c_void_p(ex.data_ptr())
         if L.U:
-            ls = state["layer1_state"]
-            hx = torch.as_tensor(np.ascontiguousarray(ls["hx"], dtype=np.float32), device=dev)
-            cx = torch.as_tensor(np.ascontiguousarray(ls["cx"], dtype=np.float32), device=dev)
-            ini = torch.as_tensor(np.ascontiguousarray(ls["initials"], dtype=np.float32), device=dev)
-            h_out, c_out = torch.empty_like(hx), torch.empty_like(cx)
-            ptrs = [C.c_void_p(t.data_ptr()) for t in (x, hx, cx, ini)]
+            ls = state["layer%d_state" % L.lstm_module]
+            ini = torch.from_numpy(np.ascontiguousarray(ls["initials"], dtype=np.float32)).to(dev)
+            if self._dev_state is not None and self._dev_state[0].shape[0] == E and \
+                    ls["hx"] is getattr(self, "_handed_hx", None):
+                # the state this policy produced itself is still on the device; the LSTM kernel applies
+                # the episode-start mask (same values as the host-side masking of make_input_state)
+                hx, cx = self._dev_state
+            else:
+                hx = torch.from_numpy(np.ascontiguousarray(ls["hx"], dtype=np.float32)).to(dev)
+                cx = torch.from_numpy(np.ascontiguousarray(ls["cx"], dtype=np.float32)).to(dev)
+            h_out, c_out = torch.empty(E, L.U, device=dev), torch.empty(E, L.U, device=dev)
+            ptrs = [C.c_void_p(x.data_ptr()), ex_p] + [C.c_void_p(t.data_ptr()) for t in (hx, cx, ini)]
             outs = [C.c_void_p(t.data_ptr()) for t in (q, h_out, c_out)]
         else:
-            ptrs = [C.c_void_p(x.data_ptr()), null, null, null]
+            ptrs = [C.c_void_p(x.data_ptr()), ex_p, null, null, null]
             outs = [C.c_void_p(q.data_ptr()), null, null]
-        _lib.check(L._lib.rt_learner_act(L._h, E, *ptrs, null, *outs, L._stream()))
+        tp = null
+        if taus is not None:
+            taus = np.ascontiguousarray(taus, dtype=np.float32)
+            tp = C.c_void_p(taus.ctypes.data)
+        _lib.check(L._lib.rt_learner_act(L._h, E, *ptrs, tp, *outs, L._stream()))
         if L.U:
-            self._last = (h_out, c_out)
-        qv = q.cpu().numpy()
+            self._dev_state = (h_out, c_out)
+            host = self._pinned("hc", (2, E, L.U), torch.float32)
+            host[0].copy_(h_out, non_blocking=True)
+            host[1].copy_(c_out, non_blocking=True)
+        qh = self._pinned("q", (E, self.num_actions), torch.float32)
+        qh.copy_(q, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        if L.U:
+            hc = host.numpy().copy()
+            self._host_state = (hc[0], hc[1])
+        qv = qh.numpy().copy()
         return {"actions": np.argmax(qv, axis=1), "qvalues": qv}
+
+
+class _ValueLog:
+    """The slice of rltime.general.value_log.ValueLog this trainer needs: grouped keys aggregated by
+    mean / sum / max since the last get()."""
+
+    def __init__(self):
+        self.data = {}
+
+    def log(self, key, val, agg="mean", group=None, keep=False):
+        self.data.setdefault((group, key), [agg, [], keep])[1].append(float(val))
+
+    def get(self):
+        out = {}
+        for (group, key), (agg, vals, keep) in list(self.data.items()):
+            if not vals:
+                continue
+            v = {"mean": np.mean, "sum": np.sum, "max": np.max}[agg](vals)
+            dst = out
+            if group:
+                for g in group.split("->"):
+                    dst = dst.setdefault(g, {})
+            dst[key] = float(v)
+            if not keep:
+                self.data[(group, key)][1] = []
+        return out
 
 
 class IQNTrainer:
@@ -122,17 +240,38 @@ class IQNTrainer:
         self.updates = 0
         self.log = {}
         self.policy = None
+        self.value_log = _ValueLog()
+        self._timer = None
+        # test / reproducibility hooks: (online, target) state_dicts to start from instead of a fresh
+        # initialisation, and a callable update_index -> [tau_target, tau_select, tau_train] replacing the
+        # device RNG (the reference draws the fractions with torch.rand, policies/torch/iqn.py:88)
+        self.initial_state_dicts = None
+        self.tau_source = None
+
+    # -- PolicyTrainer._start_timer / _end_timer (policy_trainer.py:228-244) ----------------------
+    def _start_timer(self, name):
+        self._timer = (name, time.time())
+
+    def _end_timer(self):
+        name, t0 = self._timer
+        ms = (time.time() - t0) * 1000.0
+        self.value_log.log(name, ms, agg="mean", group="timings_mean_ms")
+        self.value_log.log(name, ms, agg="sum", group="timings_total_ms")
 
     # -- PolicyTrainer.init_policies -------------------------------------------------------
     def _build(self, t):
         obs_space, act_space = self.actors.get_spaces()
-        conv, lstm_units, fc_size = parse_model_config(self.model_config)
+        m = parse_model_config(self.model_config)
+        in_shape, extra_dim = parse_observation_space(obs_space)
         pa = self.policy_args
         assert self.POLICY == "dqn" or pa.get("injection_layer", -1) == -1, "only injection_layer=-1 is supported"
+        assert not pa.get("dueling_value_layer_hidden_size"), "dueling_value_layer_hidden_size: only the default"
         mbatch = t["mbatch_size"] or self.actors.get_env_count()
         nstep_target = t["nstep_target"] or t["nstep_train"]
+        rnn_steps = t["rnn_steps_train"] or t["nstep_train"]
+        assert t["nstep_train"] % rnn_steps == 0, "nstep_train must be divisible by rnn_steps_train"
         self.learner = DeviceLearner(
-            tuple(obs_space.shape), conv, lstm_units, fc_size, int(act_space.n),
+            in_shape, m["conv"], m["lstm_units"], m["fc_size"], int(act_space.n),
             pa.get("num_sampling_quantiles", 32), pa.get("embedding_dim", 64), pa.get("dueling", False),
             mbatch=mbatch, nstep_train=t["nstep_train"], burn_in=t["burn_in_timesteps"],
             nstep_target=nstep_target, gamma=t["gamma"], double_q=t["double_q"],
@@ -141,12 +280,17 @@ class IQNTrainer:
             # the reference's train_init ignores `lr` (Adam default 1e-3) until set_lr runs
             lr=1e-3, loss_aggregation=t["loss_aggregation"], seed=t.get("seed", 0), policy=self.POLICY,
             loss_mode=t["loss_mode"], loss_timestep_aggregation=t["loss_timestep_aggregation"],
-            clip_grad_dynamic_alpha=t["clip_grad_dynamic_alpha"])
-        p0 = init_params(self.learner.param_info, lstm_units, seed=t.get("seed", 0))
+            clip_grad_dynamic_alpha=t["clip_grad_dynamic_alpha"], pre_fc=m["pre_fc"], extra_dim=extra_dim,
+            rnn_steps_train=rnn_steps, gemm=pa.get("gemm", "tf32"))
+        lstm_units = m["lstm_units"]
+        if self.initial_state_dicts is not None:
+            p0, p1 = self.initial_state_dicts
+        else:
+            p0 = init_params(self.learner.param_info, lstm_units, seed=t.get("seed", 0))
+            p1 = p0 if not t["target_update_freq"] else \
+                init_params(self.learner.param_info, lstm_units, seed=t.get("seed", 0) + 1)
         self.learner.load_state_dict(p0, _lib.RT_BUF_ONLINE)
-        self.learner.load_state_dict(p0 if not t["target_update_freq"] else
-                                     init_params(self.learner.param_info, lstm_units, seed=t.get("seed", 0) + 1),
-                                     _lib.RT_BUF_TARGET)
+        self.learner.load_state_dict(p1, _lib.RT_BUF_TARGET)
         self.policy = DevicePolicy(self.learner, int(act_space.n))
         self.actors.set_actor_policy(self.policy)
         hist_cls = t["history_mode"].get("type", "replay")
@@ -156,7 +300,41 @@ class IQNTrainer:
         self.history_buffer = hist_cls(
             **t["history_mode"].get("args", {}), nstep_target=nstep_target, nstep_train=t["nstep_train"],
             prefix_steps=t["burn_in_timesteps"], discount_function=lambda n, r, po: (g ** n) * r)
-        return mbatch
+        self._assert_nsteps = t["rnn_bootstrap"]
+        return mbatch, nstep_target
+
+    # -- device batch of a host-side (online) history buffer ------------------------------------
+    def _host_batch(self, td, nstep_target):
+        """Builds the learner's batch view from a (T, B, ...) train-data dict of host arrays / tensors
+        with separately stacked target states (history.py:268-270; OnlineHistoryBuffer)."""
+        import torch
+        dev = self.learner.device
+
+        def dev_t(x, dtype=None):
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+            t = t.to(dev)
+            return t.contiguous() if dtype is None else t.to(dtype).contiguous()
+        L = self.learner
+
+        def leaves(states):
+            x = states["x"]
+            out = {}
+            if isinstance(x, (tuple, list)):
+                out["extra"] = torch.cat([dev_t(e, torch.float32).reshape(e.shape[0], e.shape[1], -1) for e in x[1:]], -1)
+                x = x[0]
+            out["x"] = dev_t(x, torch.uint8 if L.obs_dtype == np.uint8 else torch.float32)
+            if L.U:
+                ls = states["layer%d_state" % L.lstm_module]
+                out.update({k: dev_t(ls[k], torch.float32) for k in ("hx", "cx", "initials")})
+            return out
+        s, tg = leaves(td["states"]), leaves(td["target_states"])
+        b, keep = batch_from_tensors(
+            s["x"], s.get("hx"), s.get("cx"), s.get("initials"), dev_t(td["returns"], torch.float64),
+            dev_t(td["nsteps"], torch.int64), dev_t(td["target_masks"], torch.float64),
+            dev_t(td["policy_outputs"]["actions"], torch.int64), None, nstep_target,
+            all_extra=s.get("extra"), targets=tg)
+        self._host_keep = keep + list(tg.values())
+        return b
 
     def train(self, total_steps, log_freq=10000, target_update_freq=0, clip_rewards=False,
               early_stop_steps=None, episode_history_windows=(10, 100), *, gamma, nstep_train, lr,
@@ -167,17 +345,23 @@ class IQNTrainer:
               double_q=False, loss_mode="huber", huber_kappa=1.0, loss_aggregation="mean",
               loss_timestep_aggregation=None, seed=0):
         assert epochs == 1 and minibatches == 1, "epochs / minibatches > 1 are PPO options"
-        assert rnn_steps_train in (None, nstep_train), "rnn_steps_train != nstep_train is not supported"
         assert loss_mode == "huber" or self.POLICY == "dqn", "IQN always uses the quantile-Huber loss"
-        assert not async_history, "the device buffer needs no separate history process"
+        # async_history (multi_step_trainer.py:143-150, history/parallel_history.py:118-130) asks for the
+        # batch of update k+1 to be produced while update k trains.  The device buffers do exactly that
+        # inside the library (the replay stream's draw + gather overlap the backward pass) with the
+        # reference's synchronous priority order, so the flag is accepted and needs no second process.
+        self.async_history = bool(async_history)
         t = dict(locals())
         t.pop("self")
-        mbatch = self._build(t)
+        mbatch, n_target = self._build(t)
         learner, hist = self.learner, self.history_buffer
         env_count = self.actors.get_env_count()
         self.actors.update_state(progress=0.0)
         base_lr = lr
-        t_start = time.time()
+        t_start = self._ts_start = time.time()
+        self._ts_steps = self._ts_trained = 0
+        actors_last_update_steps = 0
+        rnn_steps = rnn_steps_train or nstep_train
         while True:
             progress = self.steps / total_steps
             if progress >= 1.0 or (early_stop_steps is not None and self.steps >= early_stop_steps):
@@ -187,46 +371,98 @@ class IQNTrainer:
             if n is not None:
                 if warming_up:
                     n = max(n, env_count)
+                self._start_timer("sample_actors")
                 samples = self.actors.get_samples(n)
                 if samples:
+                    for s in samples:
+                        if s["done"]:
+                            self.value_log.log("episodes", 1, agg="sum", group="this_interval")
                     if clip_rewards:
                         for s in samples:
                             s["reward"] = np.sign(s["reward"])
                     before = self.steps
                     self.steps += len(samples)
+                    self._ts_steps += len(samples)
                     if target_update_freq > 0 and \
                             self.steps // target_update_freq != before // target_update_freq:
                         learner.sync_target()
                         self.log["target_syncs"] = self.log.get("target_syncs", 0) + 1
                     if self.steps // log_freq != before // log_freq:
                         self._log_checkpoint(t_start)
+                    self._end_timer()
+                    self._start_timer("history_update")
                     hist.update(samples)
+                    self._end_timer()
+            self._start_timer("get_train_data")
             td = hist.get_train_data(mbatch, train_progress=progress)
-            if td is None or warming_up:
+            if td is None:
                 continue
-            learner.step(hist.last_batch)
+            self._end_timer()
+            if warming_up:
+                continue
+            self._start_timer("train")
+            batch = getattr(hist, "last_batch", None)
+            if batch is None or not hasattr(hist, "update_losses_device"):
+                batch = self._host_batch(td, n_target)      # host-side buffer (online history)
+            elif self._assert_nsteps:
+                pass    # replay buffers guarantee the fixed n-step (multi_step_trainer.py:299-303)
+            learner.step(batch, None if self.tau_source is None else self.tau_source(self.updates))
             if hasattr(hist, "update_losses_device"):
                 hist.update_losses_device(learner.td_abs(), ready=learner.wait_loss)
+            if not target_update_freq:
+                # no separate target policy: the reference bootstraps from the online policy object itself
+                # (policy_trainer.py:56-58), i.e. always from the current weights
+                learner.sync_target()
             self.updates += 1
+            self._ts_trained += mbatch * nstep_train
+            self.value_log.log("batch_size", mbatch * nstep_train, group="train")
+            self.value_log.log("steps_trained", mbatch * nstep_train, agg="sum", group="this_interval")
             if lr_anneal not in (False, None):
                 anneal_to = 0.0 if lr_anneal is True else float(lr_anneal)
-                learner.set_lr(base_lr - progress * (base_lr - anneal_to))
-            if not actor_update_frequency_steps or self.updates % 16 == 0:
+                lr = base_lr - progress * (base_lr - anneal_to)
+                learner.set_lr(lr)
+            self.value_log.log("lr", lr, group="train")
+            # multi_step_trainer.py:363-373
+            if not actor_update_frequency_steps or \
+                    self.steps - actors_last_update_steps >= actor_update_frequency_steps:
                 self.actors.update_state(progress=progress)
+                actors_last_update_steps = self.steps
+            self._end_timer()
         self._log_checkpoint(t_start)
+        if hasattr(hist, "close") and async_history:
+            hist.close()
         logging.getLogger().info("Training finished")
 
     def _log_checkpoint(self, t_start):
+        """PolicyTrainer._log_checkpoint (policy_trainer.py:187-226): same group / key names."""
+        now = time.time()
         st = self.learner.stats() if self.updates else {}
-        self.log.update({"steps": self.steps, "updates": self.updates,
-                         "seconds": time.time() - t_start, **{"train." + k: v for k, v in st.items()}})
+        for k, v in st.items():
+            self.value_log.log(k, v, group="train")
+        dt = now - self._ts_start + 1e-5
+        vl = self.value_log
+        vl.log("steps_acted_per_second", int(self._ts_steps / dt), group="this_interval")
+        vl.log("steps_trained_per_second", int(self._ts_trained / dt), group="this_interval")
+        vl.log("train_ratio", self._ts_trained / max(self._ts_steps, 1), group="this_interval")
+        vl.log("seconds", now - self._ts_start, group="this_interval")
+        vl.log("seconds", now - t_start, group="total")
+        vl.log("steps_acted", self._ts_steps, group="this_interval")
+        vl.log("steps_acted", self.steps, group="total")
+        info = vl.get()
+        self.log.update({"steps": self.steps, "updates": self.updates, "seconds": now - t_start,
+                         **{"train." + k: v for k, v in st.items()}})
+        info.update({k: v for k, v in self.log.items() if k not in info})
+        self.last_log = info
         if self.logger is not None:
             if hasattr(self.logger, "log_result"):
-                self.logger.log_result("train", dict(self.log), self.steps)
+                self.logger.log_result("train", info, self.steps)
             if hasattr(self.logger, "save_checkpoint"):
-                # same checkpoint payload as PolicyTrainer._save_checkpoint (policy_trainer.py:175-185)
-                self.logger.save_checkpoint({"policy_state": self.learner.get_state(), "train_state": {}},
-                                            self.steps)
+                # same payload as PolicyTrainer._save_checkpoint (policy_trainer.py:175-185); train_state
+                # additionally carries what a resume needs (the reference stores {} and cannot resume)
+                self.logger.save_checkpoint({"policy_state": self.learner.get_state(),
+                                             "train_state": self.learner.optimizer_state()}, self.steps)
+        self._ts_start = now
+        self._ts_steps = self._ts_trained = 0
 
 
 class DQNTrainer(IQNTrainer):

@@ -24,10 +24,14 @@ if __name__ == "__main__":
             print("%-22s %-10s " % (name, mode) + " | ".join(
                 "u%d t %.1e q %.1e m %.1e r %.1e" % (u, e["targets"], e["qloss"], e["td_mean"], e["report"])
                 for u, e in enumerate(rows)))
-    print("== full size, %d consecutive updates vs the torch fp32 oracle" % updates)
-    res = full_size_drift(MODES, updates, log=print)
-    for mode, rows in res.items():
-        print("SUMMARY %-10s max|d| qloss %.2e td_mean %.2e report %.2e targets %.2e (oracle |targets| max %.3f)" % (
-            mode, max(e["qloss"] for e in rows), max(e["td_mean"] for e in rows),
-            max(e["report"] for e in rows), max(e["targets"] for e in rows),
-            max(e["ref_targets_absmax"] for e in rows)))
+    for tf in (True, False):
+        print("== full size, %d consecutive updates vs the torch fp32 oracle, %s" % (
+            updates, "weights reset to the oracle's before every update (teacher-forced)" if tf else "free-running"))
+        res = full_size_drift(MODES, updates, log=print, teacher_forced=tf)
+        for mode, rows in res.items():
+            print("SUMMARY %s %-10s max|d| qloss %.2e td_mean %.2e report %.2e targets %.2e (oracle |targets| max %.3f) "
+                  "near-tie rows %d flipped rows %d" % (
+                      "teacher-forced" if tf else "free-running", mode, max(e["qloss"] for e in rows),
+                      max(e["td_mean"] for e in rows), max(e["report"] for e in rows),
+                      max(e["targets"] for e in rows), max(e["ref_targets_absmax"] for e in rows),
+                      sum(e["tie_rows"] for e in rows), sum(e["flipped_rows"] for e in rows)))

@@ -45,8 +45,11 @@ def test_struct_layouts_match_header(lib):
 #include <stdio.h>
 #include <stddef.h>
 #include "rltime_b200.h"
-int main(){ printf("%zu %zu %zu %zu %zu\n", sizeof(rt_replay_config), offsetof(rt_replay_config, gamma),
-  offsetof(rt_replay_config, state_field_bytes), sizeof(rt_batch), offsetof(rt_batch, returns)); return 0; }
+int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(rt_replay_config), offsetof(rt_replay_config, gamma),
+  offsetof(rt_replay_config, state_field_bytes), sizeof(rt_batch), offsetof(rt_batch, returns),
+  offsetof(rt_batch, target_states), sizeof(rt_model_desc), offsetof(rt_model_desc, extra_dim),
+  offsetof(rt_model_desc, pre_fc_sub), sizeof(rt_train_desc), offsetof(rt_train_desc, rnn_steps_train),
+  sizeof(rt_learner_io)); return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "t.c")
@@ -56,7 +59,9 @@ int main(){ printf("%zu %zu %zu %zu %zu\n", sizeof(rt_replay_config), offsetof(r
         out = subprocess.check_output([exe]).decode().split()
     got = [ctypes.sizeof(lib.ReplayConfig), lib.ReplayConfig.gamma.offset,
            lib.ReplayConfig.state_field_bytes.offset, ctypes.sizeof(lib.Batch),
-           lib.Batch.returns.offset]
+           lib.Batch.returns.offset, lib.Batch.target_states.offset, ctypes.sizeof(lib.ModelDesc),
+           lib.ModelDesc.extra_dim.offset, lib.ModelDesc.pre_fc_sub.offset, ctypes.sizeof(lib.TrainDesc),
+           lib.TrainDesc.rnn_steps_train.offset, ctypes.sizeof(lib.LearnerIO)]
     assert [int(x) for x in out] == got
 
 

@@ -91,6 +91,115 @@ def test_dqn_trainer_rainbow_style_end_to_end():
     assert pred["qvalues"].shape == (4, 4) and (pred["actions"] == pred["qvalues"].argmax(1)).all()
 
 
+MODEL_MLP = {"type": "sequential", "args": {"layer_configs": [
+    {"type": "fc", "args": {"fc_size": 64}}, {"type": "fc", "args": {"fc_size": 64}}]}}
+
+
+@pytest.mark.gpu
+def test_dqn_trainer_mlp_with_online_history():
+    """BASELINE config 1 family: DQN on a 1-D float observation with the reference's mlp_2x64 model
+    (configs/models/mlp_2x64.json) and the ONLINE n-step history buffer (a host-side structure: the
+    trainer uploads its separately stacked states / target states, per-row n-steps)."""
+    from rltime_b200.training import DQNTrainer
+    from tests.fake_actor import FakeVecActor
+    actors = FakeVecActor(num_envs=2, frame_shape=(4,), num_actions=2, seed=4, vector_obs=True)
+    logger = _Logger()
+    tr = DQNTrainer(logger, actors, MODEL_MLP, {"dueling": False})
+    tr.train(total_steps=600, log_freq=200, target_update_freq=100, gamma=0.99, nstep_train=5, lr=1e-3,
+             mbatch_size=2, double_q=True, history_mode={"type": "online"})
+    assert tr.steps >= 600 and tr.updates >= 50
+    st = tr.learner.stats()
+    assert np.isfinite(st["qloss"]) and st["grad_norm"] > 0
+    names = [n for n, _ in tr.learner.param_info]
+    assert names[:4] == ["model.layers.0.layers.0.0.weight", "model.layers.0.layers.0.0.bias",
+                         "model.layers.1.layers.0.0.weight", "model.layers.1.layers.0.0.bias"]
+    pred = tr.policy.actor_predict(actors.last_state, timesteps=1)
+    assert pred["qvalues"].shape == (2, 2)
+    # the reference's log groups (policy_trainer.py:187-244)
+    info = logger.results[-1][1]
+    for grp in ("timings_mean_ms", "timings_total_ms", "this_interval", "train"):
+        assert grp in info, grp
+    assert {"get_train_data", "train", "sample_actors", "history_update"} <= set(info["timings_mean_ms"])
+    assert {"steps_trained", "steps_acted", "train_ratio", "seconds"} <= set(info["this_interval"])
+
+
+MODEL_LSTM1 = {"type": "sequential", "args": {"layer_configs": [
+    {"type": "cnn", "args": {"layers": [{"filters": 16, "kernel": 8, "stride": 4},
+                                         {"filters": 16, "kernel": 4, "stride": 2}]}},
+    {"type": "lstm", "args": {"num_units": 64}},
+    {"type": "fc", "args": {"fc_size": 64}}]}}
+
+
+@pytest.mark.gpu
+def test_iqn_trainer_tuple_observation_rnn_steps_async_flag():
+    """The shipped configs/atari_iqn_lstm.json wrapper stack: single-frame observations plus the
+    extra feature vector of ExtraFeaturesEnvWrapper, fed to the LSTM; rnn_steps_train < nstep_train;
+    async_history=True is accepted (the device buffer prefetches inside the library)."""
+    import torch
+    from rltime_b200.training import IQNTrainer
+    from tests.fake_actor import FakeVecActor
+    actors = FakeVecActor(num_envs=4, frame_shape=(1, 84, 84), num_actions=4, seed=5, extra_dim=6)
+    logger = _Logger()
+    tr = IQNTrainer(logger, actors, MODEL_LSTM1, {"dueling": True, "num_sampling_quantiles": 8, "embedding_dim": 16})
+    tr.train(total_steps=900, log_freq=300, target_update_freq=300, clip_rewards=True, gamma=0.99,
+             nstep_train=8, nstep_target=2, rnn_steps_train=4, lr=3e-4, mbatch_size=4, warmup_steps=200,
+             rnn_bootstrap=True, double_q=True, clip_grad=40.0, adam_epsilon=1e-5, async_history=True,
+             actor_update_frequency_steps=64,
+             history_mode={"type": "prioritized_replay",
+                           "args": {"size": 600, "train_frequency": 4, "alpha": 0.9, "beta": 0.6, "max_envs": 4}})
+    assert tr.steps >= 900 and tr.updates > 30
+    st = tr.learner.stats()
+    assert np.isfinite(st["qloss"]) and st["grad_norm"] > 0
+    sd = torch.load(io.BytesIO(logger.checkpoints[-1][0]["policy_state"]), map_location="cpu")
+    assert tuple(sd["model.layers.1.lstm_cell.weight_ih"].shape) == (4 * 64, 16 * 9 * 9 + 6)
+    assert "adam_steps" in logger.checkpoints[-1][0]["train_state"]
+    # actor refresh cadence follows actor_update_frequency_steps (multi_step_trainer.py:363-373)
+    assert 3 <= actors.updates <= 2 + (tr.steps - 200) // 64 + 1
+
+
+@pytest.mark.gpu
+def test_acting_inference_matches_oracle():
+    """rt_learner_act through DevicePolicy.actor_predict against the oracle's IQNPolicy
+    forward at timesteps = 1 with injected quantile fractions: q-values within 1e-4, identical greedy
+    actions, the carried LSTM state within 1e-5 -- over three consecutive vector steps with an episode
+    reset in between (the state stays on the device between the calls)."""
+    import torch
+    from oracle import learner_oracle as lo
+    from rltime_b200.learner import DeviceLearner
+    from rltime_b200.training import DevicePolicy
+    E, U, A, Nq = 6, 32, 5, 8
+    conv = [(16, 8, 4), (16, 4, 2)]
+    spec = lo.ModelSpec((4, 84, 84), conv, U, 48, A, Nq, 16, True)
+    p = spec.init_params(3)
+    L = DeviceLearner((4, 84, 84), conv, U, 48, A, Nq, 16, True, mbatch=E, nstep_train=2, nstep_target=1,
+                      double_q=True, rnn_bootstrap=True, gemm="fp32")
+    try:
+        L.load_state_dict(p, 0)
+        L.load_state_dict(p, 1)
+        pol = DevicePolicy(L, A)
+        rs = np.random.RandomState(0)
+        h = torch.zeros(E, U)
+        c = torch.zeros(E, U)
+        initials = np.ones(E, dtype=bool)
+        for step in range(3):
+            obs = rs.randint(0, 256, (E, 4, 84, 84)).astype(np.uint8)
+            state = pol.make_input_state(obs, initials)
+            taus = torch.rand(E * Nq, generator=torch.Generator().manual_seed(step))
+            got = pol.actor_predict(state, taus=taus.numpy())
+            ini = torch.from_numpy(initials.astype(np.float32))
+            st = {"x": torch.from_numpy(obs), "layer1_state": {"hx": h, "cx": c, "initials": ini}}
+            with torch.no_grad():
+                q, (h, c) = lo.predict(spec, p, st, 1, taus)
+            want = q.mean(1).numpy()
+            np.testing.assert_allclose(got["qvalues"], want, rtol=0, atol=1e-4)
+            assert (got["actions"] == want.argmax(1)).all()
+            np.testing.assert_allclose(pol._host_state[0], h.numpy(), rtol=0, atol=1e-5)
+            np.testing.assert_allclose(pol._host_state[1], c.numpy(), rtol=0, atol=1e-5)
+            initials = rs.rand(E) < 0.3
+    finally:
+        L.close()
+
+
 @pytest.mark.gpu
 def test_pipelined_update_loop_is_bit_identical_to_the_serialised_one():
     """The priority write-back / next draw overlap the backward pass (own replay stream +
