@@ -1,9 +1,9 @@
-// Persistent BPTT recurrence (EXPERIMENTAL, off by default: RT_BPTT_PERSISTENT=1).
+// One-launch BPTT recurrence (rltime/models/torch/modules/lstm.py:84-116 backward).
 //
 // Replaces the 2 x (T-1) launches of the stepwise path (k_lstm_cell_bwd + split-K GEMM per step)
 // with ONE cooperative launch.  Per step t = T-1 .. 0:
 //     dh_t     = dout_t + (dgates_{t+1} . W_hh) * (1 - initial_{t+1})
-//     dgates_t = cell backward(dh_t, dc carry, gates_t, c_t, cprev_t)          (lstm.py:100 backward)
+//     dgates_t = cell backward(dh_t, dc carry, gates_t, c_t, cprev_t)
 // The recurrent product [B x 4U] . [4U x U] is split 2-D over KS x NS CTAs:
 //     K-slice i  = the 4 gate rows of the units [64 i, 64 i + 64)   (256 rows of W_hh)
 //     N-slice j  = the units [32 j, 32 j + 32)                       (32 columns of W_hh)
@@ -12,11 +12,14 @@
 // tile (batch rows 16 (w & 1).., columns 8 (w >> 1)..) over all 256 k.  Each step it
 //   (cell)  finishes dh for its (B x 32/KS) share of N-slice j from the KS partials of the previous
 //           product (fixed order), runs the cell backward keeping dc in a register, writes dgates_t;
-//   (sync)  grid barrier;
 //   (gemm)  stages dgates_t[:, K-slice i] (32 KB) in shared memory, multiplies, writes its
-//           partial [B x 32] to part[i];
-//   (sync)  grid barrier.
-// Exchange per step per CTA: 32 KB in + 4 KB out (+ 4 KB of partial reads), all L2-resident.
+//           partial [B x 32] to part[i].
+// Synchronisation is by producer group, not by grid: the dgates of K-slice i are written by the 2 KS
+// CTAs (*, 2i) and (*, 2i+1) -> counter cell_done[i]; the partials of N-slice j by the 8 CTAs (*, j) ->
+// counter part_done[j] (release / acquire on global counters 128 B apart, monotone over the steps).
+// Everything a cell needs that does not depend on the recurrence (gates, c, c_prev, dout, masks) is
+// loaded BEFORE it waits for the partials.  Partial buffers alternate by step parity, so a CTA two
+// phases ahead never overwrites partials a slower CTA still reads.
 // B == 32, U in {256, 512}; grid = (U/64) * (U/32) CTAs, all co-resident (cooperative launch).
 #pragma once
 #include <cstdint>
@@ -26,6 +29,7 @@ namespace rtbptt {
 constexpr int THREADS = 256;
 constexpr int KROWS = 256;             // gate rows per K-slice (4 gates x 64 units)
 constexpr int DG_PITCH = KROWS + 4;    // padded row pitch of the staged dgates tile: conflict-free fragment loads
+constexpr int CTR_STRIDE = 32;         // counters 128 B apart
 
 struct Args {
   const float* dout;       // (T*B, U)   d(loss)/d(h_t)
@@ -35,19 +39,21 @@ struct Args {
   const float* initials;   // (T*B)
   const float* whh;        // (4U, U) row-major
   float* dgates;           // (T*B, 4U)  out
-  float* part;             // (KS, B, U) scratch: partial products of the current step
-  unsigned int* counter;   // grid barrier, zeroed before the launch
+  float* part;             // (2, KS, B, U) scratch: partial products, alternating by step parity
+  unsigned int* counter;   // [(KS + NS) * CTR_STRIDE] zeroed before the launch: cell_done[KS], part_done[NS]
   int T, B, U;
 };
 
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+__device__ __forceinline__ void signal(unsigned int* ctr) {
+  // every thread's prior global stores -> visible before the increment (CTA barrier + cumulative release)
   __syncthreads();
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+}
+__device__ __forceinline__ void wait_for(const unsigned int* ctr, unsigned int target) {
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
     unsigned int v;
     do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     } while (v < target);
   }
   __syncthreads();
@@ -60,15 +66,17 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+template <int KS>   // K-slices = U / 64 (8 at U = 512, 4 at U = 256)
 __global__ void __launch_bounds__(THREADS, 2) k_lstm_bptt_p(const Args a) {
   extern __shared__ __align__(16) float dg_s[];   // [32][DG_PITCH]
   const int U = a.U, B = a.B, T = a.T;
-  const int KS = U / 64, NS = U / 32;
   const int i = blockIdx.x % KS;          // K-slice
   const int j = blockIdx.x / KS;          // N-slice
-  (void)NS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int U4 = 4 * U;
+  unsigned int* cell_done = a.counter;                          // [KS]
+  unsigned int* part_done = a.counter + KS * CTR_STRIDE;        // [NS]
+  const size_t part_words = (size_t)KS * B * U;
 
   // ---- resident W block as mma B fragments: k-step s covers slice rows kk = 8 s .. 8 s + 7
   const int mi = warp & 1, ni = warp >> 1;
@@ -84,38 +92,55 @@ __global__ void __launch_bounds__(THREADS, 2) k_lstm_bptt_p(const Args a) {
     }
   }
 
-  // ---- cell ownership: (B x 32/KS) elements of N-slice j
-  const int upc = 32 / KS;                                   // units per CTA in the cell phase
-  const bool cell = tid < 32 * upc;
-  const int cb = tid & 31;                                   // batch row
-  const int cu = 32 * j + upc * i + (tid >> 5);              // unit
+  // ---- cell ownership: (B x 32/KS) elements of N-slice j; consecutive threads = consecutive units
+  constexpr int UPC = 32 / KS;                               // units per CTA in the cell phase
+  const bool cell = tid < 32 * UPC;
+  const int cb = tid / UPC;                                  // batch row
+  const int cu = 32 * j + UPC * i + (tid % UPC);             // unit
   float dc_carry = 0.f;
-  unsigned int bar = 0;
 
   for (int t = T - 1; t >= 0; --t) {
     const size_t ro = (size_t)t * B;
+    const int step = T - 1 - t;                              // 0, 1, ...
     // ---------------- cell backward of step t
+    float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, dh = 0.f, cv = 0.f, cpv = 0.f, keep_n = 0.f, keep = 0.f;
+    size_t g0 = 0;
     if (cell) {
+      // everything that does not depend on the recurrence: issued before the wait
       const size_t e = (ro + cb) * U + cu;
-      const size_t g0 = (ro + cb) * U4 + cu;
-      const float gi = a.gates[g0], gf = a.gates[g0 + U], gg = a.gates[g0 + 2 * U], go = a.gates[g0 + 3 * U];
-      float dh = a.dout[e];
-      if (t < T - 1) {
+      g0 = (ro + cb) * U4 + cu;
+      gi = __ldg(a.gates + g0); gf = __ldg(a.gates + g0 + U); gg = __ldg(a.gates + g0 + 2 * U); go = __ldg(a.gates + g0 + 3 * U);
+      dh = __ldg(a.dout + e);
+      cv = __ldg(a.c_all + e);
+      cpv = __ldg(a.cprev + e);
+      keep = 1.f - __ldg(a.initials + ro + cb);
+      if (t < T - 1) keep_n = 1.f - __ldg(a.initials + ro + B + cb);
+    }
+    if (t < T - 1) {
+      wait_for(part_done + j * CTR_STRIDE, (unsigned int)(KS * step));      // partials of step t+1 complete
+      if (cell) {
+        const float* pp = a.part + (size_t)((step - 1) & 1) * part_words + (size_t)cb * U + cu;
+        float pv[KS];
+#pragma unroll
+        for (int p = 0; p < KS; ++p) pv[p] = __ldcg(pp + (size_t)p * B * U);
         float carry = 0.f;
-        for (int p = 0; p < KS; ++p) carry += __ldcg(a.part + ((size_t)p * B + cb) * U + cu);
-        dh += carry * (1.f - a.initials[ro + B + cb]);
+#pragma unroll
+        for (int p = 0; p < KS; ++p) carry += pv[p];
+        dh += carry * keep_n;
       }
-      const float tc = tanhf(a.c_all[e]);
+    }
+    if (cell) {
+      const float tc = tanhf(cv);
       const float dc = dc_carry + dh * go * (1.f - tc * tc);
       a.dgates[g0] = dc * gg * gi * (1.f - gi);
-      a.dgates[g0 + U] = dc * a.cprev[e] * gf * (1.f - gf);
+      a.dgates[g0 + U] = dc * cpv * gf * (1.f - gf);
       a.dgates[g0 + 2 * U] = dc * gi * (1.f - gg * gg);
       a.dgates[g0 + 3 * U] = dh * tc * go * (1.f - go);
-      dc_carry = dc * gf * (1.f - a.initials[ro + cb]);
+      dc_carry = dc * gf * keep;
     }
     if (t == 0) break;
-    bar += gridDim.x;
-    grid_barrier(a.counter, bar);                            // dgates_t complete and visible
+    signal(cell_done + (j >> 1) * CTR_STRIDE);                               // my share of K-slice j/2 is written
+    wait_for(cell_done + i * CTR_STRIDE, (unsigned int)(2 * KS * (step + 1)));   // dgates_t[:, K-slice i] complete
 
     // ---------------- partial product: dgates_t[:, K-slice i] . W block
     for (int v = tid; v < 32 * (KROWS / 4); v += THREADS) {
@@ -140,12 +165,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_lstm_bptt_p(const Args a) {
     {
       const int b0 = 16 * mi + (lane >> 2);
       const int n0 = 32 * j + 8 * ni + 2 * (lane & 3);
-      float* p0 = a.part + ((size_t)i * B + b0) * U + n0;
+      float* p0 = a.part + (size_t)(step & 1) * part_words + ((size_t)i * B + b0) * U + n0;
       *reinterpret_cast<float2*>(p0) = make_float2(d[0], d[1]);
       *reinterpret_cast<float2*>(p0 + (size_t)8 * U) = make_float2(d[2], d[3]);
     }
-    bar += gridDim.x;
-    grid_barrier(a.counter, bar);                            // every partial of this step visible
+    signal(part_done + j * CTR_STRIDE);                                      // my partial of N-slice j is written
   }
 }
 

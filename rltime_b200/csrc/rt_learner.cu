@@ -164,6 +164,7 @@ struct rt_learner {
   float* hb_partb = nullptr;  // ... and of the out / value bias gradients: [hb_slabs][33]
   int hb_slabs = 256;
   unsigned int* grid_barrier = nullptr;
+  unsigned int* bptt_counters = nullptr;   // producer-group counters of the one-launch BPTT kernel
   long long* lstm_dbg = nullptr;
   float* lstm_hrep = nullptr;   // replicated h exchange buffer of the persistent LSTM kernel
   int lstm_persistent = 1;
@@ -176,7 +177,7 @@ struct rt_learner {
   int conv_implicit = 1;
   int conv_implicit_bwd = 1;
   int conv_persistent = 1;
-  int bptt_persistent = 0;      // EXPERIMENTAL one-launch BPTT recurrence (RT_BPTT_PERSISTENT=1), not validated on hardware yet
+  int bptt_persistent = 0;      // one-launch BPTT recurrence (rt_bptt.cuh); RT_BPTT_PERSISTENT overrides
   int conv_shallow = 1;         // shallow conv rings (2 CTAs/SM) inside the multi-branch phases (RT_CONV_SHALLOW; 2: backward too)
   int conv_dx_implicit = 1;
   std::vector<float*> conv_wt;  // re-laid filters for the data-gradient implicit GEMM (per layer, null for conv1)
@@ -1220,18 +1221,20 @@ int lstm_backward(rt_learner* h, cudaStream_t st, const float* net, const float*
   int nb = cdiv((size_t)Beff * U, 256);
   const int bptt_ctas = (U / 64) * (U / 32);
   const bool bptt_one_launch = h->bptt_persistent && h->gx.mode == 1 && Beff == 32 && (U == 512 || U == 256) &&
-                               bptt_ctas <= h->num_sms && (size_t)(U / 64) * Beff * U <= h->gx.ws_floats;
+                               timesteps > 1 && bptt_ctas <= h->num_sms &&
+                               (size_t)2 * (U / 64) * Beff * U <= h->gx.ws_floats;
   if (bptt_one_launch) {
-    // EXPERIMENTAL (rt_bptt.cuh, RT_BPTT_PERSISTENT=1): the whole recurrence in one cooperative launch
+    // rt_bptt.cuh: the whole recurrence in one cooperative launch (RT_BPTT_PERSISTENT=0: stepwise path)
     rtbptt::Args ba;
     ba.dout = h->dfeatq; ba.gates = h->gates; ba.c_all = h->c_all; ba.cprev = h->cprev;
     ba.initials = initials; ba.whh = net + h->o_whh; ba.dgates = h->dgates; ba.part = h->gx.ws;
-    ba.counter = h->grid_barrier; ba.T = timesteps; ba.B = Beff; ba.U = U;
-    RT_CUDA(cudaMemsetAsync(h->grid_barrier, 0, sizeof(unsigned int), st));
+    ba.counter = h->bptt_counters; ba.T = timesteps; ba.B = Beff; ba.U = U;
+    const int KS = U / 64, NS = U / 32;
+    RT_CUDA(cudaMemsetAsync(h->bptt_counters, 0, (size_t)(KS + NS) * rtbptt::CTR_STRIDE * sizeof(unsigned int), st));
     void* args[] = {(void*)&ba};
     const size_t smem = (size_t)32 * rtbptt::DG_PITCH * sizeof(float);
-    RT_CUDA(cudaLaunchCooperativeKernel((void*)rtbptt::k_lstm_bptt_p, dim3(bptt_ctas), dim3(rtbptt::THREADS), args,
-                                        smem, st));
+    void* kern = KS == 8 ? (void*)rtbptt::k_lstm_bptt_p<8> : (void*)rtbptt::k_lstm_bptt_p<4>;
+    RT_CUDA(cudaLaunchCooperativeKernel(kern, dim3(bptt_ctas), dim3(rtbptt::THREADS), args, smem, st));
     rt::launch_counter()++;
   }
   RT_CUDA(cudaMemsetAsync(h->dc_carry, 0, (size_t)Beff * U * sizeof(float), st));
@@ -1780,6 +1783,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   RT_REQUIRE(h->F % 4 == 0 && h->D % 4 == 0, "fc_size and the quantile-layer width must be multiples of 4");
 
   RT_TRY(dalloc(h, &h->grid_barrier, 64));
+  RT_TRY(dalloc(h, &h->bptt_counters, (size_t)(8 + 16) * rtbptt::CTR_STRIDE));
   if (h->U) RT_TRY(dalloc(h, &h->lstm_hrep, (size_t)2 * rtk::LSTM_REP * 32 * h->U));
   if (h->U && h->U % 32 == 0) {
     h->lstm_tcap = h->T > h->P ? h->T : h->P;
