@@ -243,7 +243,7 @@ def build_device_workload(cfg, device, seed, rank):
 
 def one_update(hist, learner, B, world=1):
     from rltime_b200 import parallel
-    td = hist.get_train_data(B, 0.0)
+    td = hist.draw(B, 0.0)          # what IQNTrainer.train calls: get_train_data minus the dict of views
     assert td is not None
     if world > 1:
         # local gradients -> NCCL sum over NVLink -> identical clip + Adam on every rank
@@ -352,6 +352,8 @@ def run_gpu(args):
 
     if world > 1:
         from rltime_b200 import parallel
+        if os.environ.get("RT_DP_LIB", "1") != "0":
+            parallel.init_library_comm(learner)      # rt_comm_init: the gradient exchange runs inside the library
         parallel.broadcast_params_(learner)
     for _ in range(warmup):
         one_update(hist, learner, B, world)

@@ -120,6 +120,11 @@ typedef struct rt_batch {
    * target_states[0] is non-null the learner reads the bootstrap states from here and all_states only has
    * to hold the S*B training rows. */
   void* target_states[RT_MAX_FIELDS];
+  /* PER: [1] the weight the importance weights of this batch were divided by (the batch maximum, or the
+   * min-tree value with global_importance_scaling; prioritized_replay_history.py:347-354).  A sharded replay
+   * rescales importance_weights by weight_max / max-over-ranks(weight_max) so every shard normalises by
+   * the same global maximum (rt_comm_allreduce_max_f64). */
+  double* weight_max;
 } rt_batch;
 
 int rt_replay_batch(rt_replay* h, rt_batch* out);
@@ -277,6 +282,24 @@ int rt_learner_step(rt_learner* h, const rt_batch* batch, const rt_learner_io* i
 int rt_learner_compute_grads(rt_learner* h, const rt_batch* batch, const rt_learner_io* io,
                              const float* const* taus_host, void* stream);
 int rt_learner_apply_grads(rt_learner* h, double grad_scale, void* stream);
+/* ---- data parallelism inside the library (SURVEY.md 8b export list: rt_comm_init).  The reference has no
+ * multi-GPU path; these make the one exchange step of the sharded design (8e) host-language neutral: the
+ * host only has to carry the 128-byte NCCL id from rank 0 to the other ranks (file, socket, MPI, a
+ * torch.distributed broadcast ...).  NCCL is dlopen'ed at run time (libnccl.so.2). */
+#define RT_COMM_ID_BYTES 128
+int rt_comm_unique_id(uint8_t* id128);                    /* rank 0: ncclGetUniqueId */
+int rt_comm_init(rt_learner* h, const uint8_t* id128, int32_t rank, int32_t world);
+int rt_comm_destroy(rt_learner* h);
+/* Every rank starts from rank `root`'s online / target weights. */
+int rt_comm_broadcast_params(rt_learner* h, int32_t root, void* stream);
+/* In-place max over the ranks of `count` device doubles (global importance-weight normalisation of the
+ * sharded prioritized replay, prioritized_replay_history.py:347-354). */
+int rt_comm_allreduce_max_f64(rt_learner* h, double* dev_values, int32_t count, void* stream);
+/* rt_learner_step across the communicator: local gradients, NCCL sum (the non-convolution bucket overlaps
+ * the convolution backward on an internal communication stream), identical clip + Adam with the gradient
+ * mean on every rank. */
+int rt_learner_step_dp(rt_learner* h, const rt_batch* batch, const rt_learner_io* io,
+                       const float* const* taus_host, void* stream);
 /* Flat fp32 buffers (RT_BUF_*): all tensors of one kind back to back, 256-byte aligned. */
 int rt_learner_flat_buffer(rt_learner* h, int32_t which, float** dev_ptr, int64_t* count);
 /* DQNPolicy.actor_predict / IQNPolicy._actor_predict_postprocess (policies/torch/dqn.py:132-148,

@@ -458,6 +458,7 @@ class PrioritizedReplayOracle(ReplayOracle):
             max_weight = (p_min * total_items) ** (-beta)
         else:
             max_weight = np.max(td["extra_data"]["importance_weights"])
+        self.last_weight_max = float(max_weight)      # test aid: what this batch was normalised by
         td["extra_data"]["importance_weights"] /= max_weight
         return td
 

@@ -43,7 +43,7 @@ class Batch(C.Structure):
         ("returns", C.c_void_p), ("nsteps", C.c_void_p), ("target_masks", C.c_void_p),
         ("importance_weights", C.c_void_p), ("loss_indices", C.c_void_p),
         ("idxes", C.c_void_p), ("slots", C.c_void_p),
-        ("target_states", C.c_void_p * RT_MAX_FIELDS),
+        ("target_states", C.c_void_p * RT_MAX_FIELDS), ("weight_max", C.c_void_p),
     ]
 
 
@@ -126,6 +126,12 @@ SIGNATURES = {
     "rt_learner_step": (C.c_int, [_VP, C.POINTER(Batch), C.POINTER(LearnerIO), _VP, _VP]),
     "rt_learner_compute_grads": (C.c_int, [_VP, C.POINTER(Batch), C.POINTER(LearnerIO), _VP, _VP]),
     "rt_learner_apply_grads": (C.c_int, [_VP, C.c_double, _VP]),
+    "rt_comm_unique_id": (C.c_int, [_VP]),
+    "rt_comm_init": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32]),
+    "rt_comm_destroy": (C.c_int, [_VP]),
+    "rt_comm_broadcast_params": (C.c_int, [_VP, C.c_int32, _VP]),
+    "rt_comm_allreduce_max_f64": (C.c_int, [_VP, _VP, C.c_int32, _VP]),
+    "rt_learner_step_dp": (C.c_int, [_VP, C.POINTER(Batch), C.POINTER(LearnerIO), _VP, _VP]),
     "rt_learner_flat_buffer": (C.c_int, [_VP, C.c_int32, C.POINTER(_VP), C.POINTER(C.c_int64)]),
     "rt_learner_act": (C.c_int, [_VP, C.c_int32] + [_VP] * 9 + [_VP]),
     "rt_learner_td_abs": (C.c_int, [_VP, C.POINTER(_VP)]),

@@ -684,6 +684,14 @@ struct ConvArgs {
   int M, N, K;         // M = rows*OH*OW, N = filters, K = C*KH*KH (multiple of 32)
   float scale;
   int round_tf32;
+  // Two networks in one product (k_conv_tc_p, BN = 64 = 2 x 32 filters): the filter tile is [W_a ; W_b], the
+  // 32-column accumulator chunk 0 goes to `out` (+bias) for every row, chunk 1 to `out2` (+bias2) for the
+  // rows >= row_shift2 only, stored at row - row_shift2 (the second network reads a suffix of the same
+  // frames).  row_shift2 must be a multiple of the 128-row tile.
+  float* out2;
+  const float* bias2;
+  int split2;
+  int row_shift2;
 };
 
 template <int BN, int IN_U8, int STAGES>
@@ -1059,11 +1067,18 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Con
     EpiArgs e;
     e.C = a.out; e.ldc = a.N; e.M = a.M; e.N = a.N; e.alpha = 1.f; e.bias = a.bias; e.bias2 = nullptr;
     e.relu = 1; e.mask = nullptr; e.ldmask = 0; e.accumulate = 0; e.round_tf32 = a.round_tf32; e.raw = 0;
+    EpiArgs e2 = e;           // second network of a split product: its own output rows / bias
+    if (BN == 64 && a.split2) {
+      e.ldc = 32; e.N = 32;
+      e2.C = a.out2; e2.ldc = 32; e2.N = 32; e2.M = a.M - a.row_shift2; e2.bias = a.bias2;
+    }
     int lt = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
       const int acc = lt & 1;
-      const EpiWarp ew = epi_begin(e, lane, m0 + q * 32, n0, BN);
+      const bool split = BN == 64 && a.split2;
+      const EpiWarp ew = epi_begin(e, lane, m0 + q * 32, n0, split ? 32 : BN);
+      const EpiWarp ew2 = epi_begin(e2, lane, m0 - a.row_shift2 + q * 32, 0, 32);
       mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -1076,7 +1091,11 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Con
           if (lane == 0)
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
         }
-        if (n0 + c * 32 < a.N) epilogue_chunk(e, ew, v, stage, lane, m0 + q * 32, n0 + c * 32);
+        if (split && c == 1) {
+          if (m0 >= a.row_shift2) epilogue_chunk(e2, ew2, v, stage, lane, m0 - a.row_shift2 + q * 32, 0);
+        } else if (n0 + c * 32 < a.N) {
+          epilogue_chunk(e, ew, v, stage, lane, m0 + q * 32, n0 + c * 32);
+        }
       }
     }
   }

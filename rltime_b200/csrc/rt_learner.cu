@@ -12,6 +12,9 @@
 // gradient and Adam-moment buffers, so clip + Adam + target sync are single passes.  Internal
 // weight layouts are permuted once at load time (conv filters to (f,kh,kw,c), CNN-feature
 // columns to (h,w,c)) so that activations can stay NHWC and every layer is a K-major GEMM.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -177,9 +180,11 @@ struct rt_learner {
   int conv_implicit = 1;
   int conv_implicit_bwd = 1;
   int conv_persistent = 1;
-  int bptt_persistent = 0;      // one-launch BPTT recurrence (rt_bptt.cuh); RT_BPTT_PERSISTENT overrides
+  int bptt_persistent = 1;      // one-launch BPTT recurrence (rt_bptt.cuh); RT_BPTT_PERSISTENT=0: stepwise path
   int conv_shallow = 1;         // shallow conv rings (2 CTAs/SM) inside the multi-branch phases (RT_CONV_SHALLOW; 2: backward too)
   int conv_dx_implicit = 1;
+  int conv1_pair = 1;           // conv1 of the online + target networks as one N = 64 product (RT_CONV1_PAIR=0: separate)
+  float* wcat = nullptr;        // [2 x f][K] staging of the two conv1 filter banks
   std::vector<float*> conv_wt;  // re-laid filters for the data-gradient implicit GEMM (per layer, null for conv1)
   float* dcol_full = nullptr;
   int num_sms = 148;
@@ -228,6 +233,11 @@ struct rt_learner {
   float* h_stats = nullptr;        // pinned read-back of stats[0..3]
   std::map<std::string, std::pair<void*, long long>> debug;
   std::vector<void*> allocs;
+  // data parallelism inside the library (rt_comm_*): NCCL communicator + communication stream
+  ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_comm = nullptr;
 };
 
 namespace {
@@ -637,6 +647,7 @@ int conv_forward_tc(rt_learner* h, GemmCtx& cx, cudaStream_t st, const float* ne
   a.M = rows * L.hout * L.wout; a.N = L.f; a.K = L.K;
   a.scale = (float)(1.0 / 255.0);
   a.round_tf32 = cx.round_tf32 || h->rn;   // the output is the A operand of the next layer's product
+  a.out2 = nullptr; a.bias2 = nullptr; a.split2 = 0; a.row_shift2 = 0;
   const int BN = L.f <= 32 ? 32 : (L.f <= 64 ? 64 : 128);
   const CUtensorMap* tb = nullptr;
   RT_TRY(get_tmap(cx, net + L.w, L.K, L.f, L.K, rttc::BLOCK_K, BN, 0, &tb));
@@ -657,6 +668,38 @@ int conv_forward_tc(rt_learner* h, GemmCtx& cx, cudaStream_t st, const float* ne
   if (BN == 32) return launch_conv_tc<32, 0>(tb, a, st);
   if (BN == 64) return launch_conv_tc<64, 0>(tb, a, st);
   return launch_conv_tc<128, 0>(tb, a, st);
+}
+
+// conv1 of the online AND the target network in ONE implicit GEMM (N = 2 x 32 filters) over the shared
+// fp32 frames: the online network needs rows [0, rows), the target network the suffix [shift_rows, rows)
+// (target_states = states shifted by n steps).  The 4x-overlapping patch gather -- the L2 traffic that
+// bounds this layer -- is done once instead of twice.
+bool conv1_pair_eligible(const rt_learner* h, int shift_rows) {
+  if (h->conv.empty() || !h->conv1_pair || !h->wcat) return false;
+  const ConvL& L = h->conv[0];
+  const long long shift = (long long)shift_rows * L.hout * L.wout;
+  return L.f == 32 && conv_tc_eligible(h, 0, h->xf) && shift % rttc::BLOCK_M == 0 && h->conv_persistent;
+}
+int conv1_pair_forward(rt_learner* h, cudaStream_t st, const float* net_a, const float* net_b, const float* xf,
+                       int rows, int shift_rows) {
+  const ConvL& L = h->conv[0];
+  const size_t nw = (size_t)L.f * L.K;
+  RT_CUDA(cudaMemcpyAsync(h->wcat, net_a + L.w, nw * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RT_CUDA(cudaMemcpyAsync(h->wcat + nw, net_b + L.w, nw * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  rttc::ConvArgs a;
+  a.in = xf; a.out = h->c_out[0]; a.bias = net_a + L.b; a.rows = rows;
+  a.C = L.cin; a.H = L.hin; a.W = L.win; a.KH = L.k; a.S = L.s; a.OH = L.hout; a.OW = L.wout;
+  a.M = rows * L.hout * L.wout; a.N = 2 * L.f; a.K = L.K;
+  a.scale = (float)(1.0 / 255.0);
+  a.round_tf32 = h->rn;
+  a.out2 = h->c_out2[0]; a.bias2 = net_b + L.b; a.split2 = 1; a.row_shift2 = shift_rows * L.hout * L.wout;
+  const CUtensorMap* tb = nullptr;
+  RT_TRY(get_tmap(h->gx, h->wcat, L.K, 2 * L.f, L.K, rttc::BLOCK_K, 64, 0, &tb));
+  h->gx.tc_launches++;
+  ProfScope ps(h->gx, st, 2.0 * a.M * a.N * a.K, 1, a.M, a.N, a.K);
+  const long long tiles = cdiv(a.M, rttc::BLOCK_M);
+  const int ctas = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+  return launch_conv_tc_p<64, 0>(tb, a, ctas, st);
 }
 
 template <int BN, int IN_U8, int STAGES = 4>
@@ -776,7 +819,7 @@ bool cnn_all_implicit(const rt_learner* h) {
   return all;
 }
 int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows,
-                const float* xf_pre = nullptr, bool second = false) {
+                const float* xf_pre = nullptr, bool second = false, int first_layer = 0) {
   if (!xf_pre)
     RT_TRY(launch_frames_to_nhwc(st, x, h->xf, rows, h->md.in_c, h->md.in_h, h->md.in_w, (float)(1.0 / 255.0), h->rn));
   const float* xf = xf_pre ? xf_pre : h->xf;
@@ -787,12 +830,12 @@ int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t*
     if (all) {
       std::vector<float*>& out = second ? h->c_out2 : h->c_out;
       GemmCtx& cx = second ? h->gx2 : h->gx;
-      for (size_t i = 0; i < h->conv.size(); ++i)
+      for (size_t i = first_layer; i < h->conv.size(); ++i)
         RT_TRY(conv_forward_tc(h, cx, st, net, i, i == 0 ? (const void*)xf : (const void*)out[i - 1], out[i], rows));
       return RT_OK;
     }
   }
-  RT_REQUIRE(!second, "second activation set needs the implicit-GEMM conv path");
+  RT_REQUIRE(!second && first_layer == 0, "second activation set needs the implicit-GEMM conv path");
   for (int r0 = 0; r0 < rows; r0 += h->chunk_rows) {
     int rc = rows - r0 < h->chunk_rows ? rows - r0 : h->chunk_rows;
     for (size_t i = 0; i < h->conv.size(); ++i) {
@@ -814,10 +857,10 @@ int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t*
 // (fc.py:29-36: linear + ReLU).  *out = (rows, h->feat) features.  Without a CNN the observation rows
 // are float32 vectors and feed the first FC layer (or the LSTM / heads) directly.
 int feature_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows,
-                    const float** out, const float* xf_pre = nullptr, bool second = false) {
+                    const float** out, const float* xf_pre = nullptr, bool second = false, int first_conv = 0) {
   const float* f = reinterpret_cast<const float*>(x);
   if (!h->conv.empty()) {
-    RT_TRY(cnn_forward(h, st, net, x, rows, xf_pre, second));
+    RT_TRY(cnn_forward(h, st, net, x, rows, xf_pre, second, first_conv));
     f = (second ? h->c_out2 : h->c_out).back();
   }
   GemmCtx& cx = second ? h->gx2 : h->gx;
@@ -1650,6 +1693,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     h->d_pre.push_back(d);
   }
   if (!h->pre.empty() && !h->conv.empty()) RT_TRY(dalloc(h, &h->d_cfeat, (size_t)h->M * h->cfeat, "d_cfeat"));
+  if (!h->conv.empty()) RT_TRY(dalloc(h, &h->wcat, (size_t)2 * h->conv[0].f * h->conv[0].K));
   RT_TRY(dalloc(h, &h->col, maxcol));
   RT_TRY(dalloc(h, &h->dcol, maxcol));
   {
@@ -1814,6 +1858,8 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     if (e && e[0] == '0') h->conv_persistent = 0;
     e = getenv("RT_CONV_DX_COL2IM");
     if (e && e[0] == '1') h->conv_dx_implicit = 0;
+    e = getenv("RT_CONV1_PAIR");
+    if (e && e[0] == '0') h->conv1_pair = 0;
     e = getenv("RT_CONV_BWD_IM2COL");
     if (e && e[0] == '1') h->conv_implicit_bwd = 0;
   }
@@ -1843,6 +1889,7 @@ void rt_learner_destroy(rt_learner* h) {
   for (auto& e : h->ev_side_b) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_side) if (e) cudaEventDestroy(e);
   if (h->h_stats) cudaFreeHost(h->h_stats);
+  if (h->comm) rt_comm_destroy(h);
   delete h;
 }
 
@@ -2126,6 +2173,7 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       const bool fork_fwd = h->side_active && h->overlap_fwd && h->td.double_q && cnn_all_implicit(h);
       const bool has_cnn = !h->conv.empty();
       const float* f = nullptr;
+      bool pair1 = false;
       if (h->td.double_q) {
         // the target pass (rows [n, T+n)) and the online pass (rows [0, T+n)) read the same frames:
         // convert them to fp32 NHWC once
@@ -2134,9 +2182,12 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
                                        (float)(1.0 / 255.0), h->rn));
         const float* xf_t = has_cnn ? h->xf + (size_t)n * B * frame : nullptr;
         if (fork_fwd) {
+          // conv1 of both networks as one product over the shared frames, then the branches split
+          pair1 = has_cnn && conv1_pair_eligible(h, n * B);
+          if (pair1) RT_TRY(conv1_pair_forward(h, st, h->pr[0], h->pr[1], h->xf, M + n * B, n * B));
           SideCtx sd;
           RT_TRY(side_begin(h, st, &sd));
-          RT_TRY(feature_forward(h, sd.st, h->pr[1], sv.x, M, &f, xf_t, true));
+          RT_TRY(feature_forward(h, sd.st, h->pr[1], sv.x, M, &f, xf_t, true, pair1 ? 1 : 0));
           RT_TRY(lstm_xgates(h, sd.st, h->pr[1], f, M, h->xg2, sv.extra, sd.gx));
         } else {
           RT_TRY(feature_forward(h, st, h->pr[1], sv.x, M, &f, xf_t));
@@ -2150,7 +2201,7 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       int ns = 0;
       seqs[ns++] = SeqDesc{h->pr[1], h->xg2, sv.hx, sv.cx, sv.initials, h->h_all2, 1, false};
       if (h->td.double_q) {
-        RT_TRY(feature_forward(h, st, h->pr[0], svt.x, M + n * B, &f, has_cnn ? h->xf : nullptr));
+        RT_TRY(feature_forward(h, st, h->pr[0], svt.x, M + n * B, &f, has_cnn ? h->xf : nullptr, false, pair1 ? 1 : 0));
         RT_TRY(lstm_xgates(h, st, h->pr[0], f, M + n * B, h->xg, svt.extra));
         seqs[ns++] = SeqDesc{h->pr[0], h->xg + (size_t)n * B * 4 * U, sv.hx, sv.cx, sv.initials, h->h_all3, 2, false};
       } else {
@@ -2474,6 +2525,155 @@ int rt_learner_debug_tensor(rt_learner* h, const char* name, void** dev_ptr, int
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ data parallelism (NCCL)
+// NCCL is bound at run time (dlopen of libnccl.so.2: inside a PyTorch process that is the copy torch
+// already loaded), so the library itself has no link-time dependency on it.
+namespace {
+struct Nccl {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+int nccl_api(Nccl** out) {
+  static Nccl api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+      if (api.lib) break;
+    }
+    if (api.lib) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+      api.CommInitRankConfig = (decltype(api.CommInitRankConfig))dlsym(api.lib, "ncclCommInitRankConfig");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+      api.Broadcast = (decltype(api.Broadcast))dlsym(api.lib, "ncclBroadcast");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+    }
+  }
+  if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.Broadcast || !api.CommDestroy)
+    return rt::fail(RT_ERR_NCCL, "libnccl.so.2 could not be loaded (%s)", api.lib ? "missing symbols" : dlerror());
+  *out = &api;
+  return RT_OK;
+}
+#define RT_NCCL(api, call)                                                                         \
+  do {                                                                                             \
+    ncclResult_t r__ = (call);                                                                     \
+    if (r__ != ncclSuccess)                                                                        \
+      return rt::fail(RT_ERR_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call,                   \
+                      (api)->GetErrorString ? (api)->GetErrorString(r__) : "nccl error");          \
+  } while (0)
+}  // namespace
+
+extern "C" int rt_comm_unique_id(uint8_t* id128) {
+  RT_REQUIRE(id128, "null argument");
+  Nccl* api = nullptr;
+  RT_TRY(nccl_api(&api));
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == RT_COMM_ID_BYTES, "ncclUniqueId size");
+  RT_NCCL(api, api->GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return RT_OK;
+}
+
+extern "C" int rt_comm_init(rt_learner* h, const uint8_t* id128, int32_t rank, int32_t world) {
+  RT_REQUIRE(h && id128 && world >= 1 && rank >= 0 && rank < world, "bad argument");
+  RT_REQUIRE(!h->comm, "communicator already initialised");
+  RT_CUDA(cudaSetDevice(h->device));
+  Nccl* api = nullptr;
+  RT_TRY(nccl_api(&api));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  // few CTAs: the all-reduce of the late-gradient bucket runs next to the persistent conv-backward CTAs,
+  // which want every SM; NVLS / NVLink 5 moves 32 MB with a handful of CTAs (RT_NCCL_MAX_CTAS overrides)
+  int max_ctas = 16;
+  if (const char* e = getenv("RT_NCCL_MAX_CTAS")) max_ctas = atoi(e);
+  if (api->CommInitRankConfig && max_ctas > 0) {
+    ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+    cfg.maxCTAs = max_ctas;
+    RT_NCCL(api, api->CommInitRankConfig(&h->comm, world, id, rank, &cfg));
+  } else {
+    RT_NCCL(api, api->CommInitRank(&h->comm, world, id, rank));
+  }
+  h->comm_rank = rank;
+  h->comm_world = world;
+  int lo = 0, hi = 0;
+  RT_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  RT_CUDA(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, lo));
+  RT_CUDA(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+  return RT_OK;
+}
+
+extern "C" int rt_comm_destroy(rt_learner* h) {
+  RT_REQUIRE(h, "null argument");
+  if (!h->comm) return RT_OK;
+  Nccl* api = nullptr;
+  RT_TRY(nccl_api(&api));
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  api->CommDestroy(h->comm);
+  h->comm = nullptr;
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+  h->comm_stream = nullptr;
+  h->ev_comm = nullptr;
+  h->comm_world = 1;
+  return RT_OK;
+}
+
+extern "C" int rt_comm_broadcast_params(rt_learner* h, int32_t root, void* stream) {
+  RT_REQUIRE(h && h->comm, "rt_comm_init first");
+  RT_CUDA(cudaSetDevice(h->device));
+  Nccl* api = nullptr;
+  RT_TRY(nccl_api(&api));
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int w = 0; w < 2; ++w)
+    RT_NCCL(api, api->Broadcast(h->p[w], h->p[w], h->nparams, ncclFloat, root, h->comm, st));
+  return rt_learner_params_changed(h, stream);
+}
+
+extern "C" int rt_comm_allreduce_max_f64(rt_learner* h, double* dev_values, int32_t count, void* stream) {
+  RT_REQUIRE(h && h->comm && dev_values && count > 0, "bad argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  Nccl* api = nullptr;
+  RT_TRY(nccl_api(&api));
+  RT_NCCL(api, api->AllReduce(dev_values, dev_values, (size_t)count, ncclDouble, ncclMax, h->comm, (cudaStream_t)stream));
+  return RT_OK;
+}
+
+// One data-parallel update entirely inside the library: local gradients -> NCCL sum over NVLink in two
+// buckets (every non-conv gradient on the communication stream while the conv backward still runs, the
+// small conv bucket afterwards) -> identical clip + Adam on every rank with grad_scale = 1 / world.
+extern "C" int rt_learner_step_dp(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
+                                  const float* const* taus_host, void* stream) {
+  RT_REQUIRE(h && h->comm, "rt_comm_init first");
+  Nccl* api = nullptr;
+  RT_TRY(nccl_api(&api));
+  RT_TRY(learner_step_impl(h, b, io, taus_host, stream, false));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t first = h->conv_param_end, count = h->nparams - h->conv_param_end;
+  if (h->comm_world > 1) {
+    if (first > 0 && count > 0) {
+      RT_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_late, 0));
+      RT_NCCL(api, api->AllReduce(h->grad + first, h->grad + first, count, ncclFloat, ncclSum, h->comm, h->comm_stream));
+      RT_CUDA(cudaEventRecord(h->ev_comm, h->comm_stream));
+      RT_NCCL(api, api->AllReduce(h->grad, h->grad, first, ncclFloat, ncclSum, h->comm, st));
+      RT_CUDA(cudaStreamWaitEvent(st, h->ev_comm, 0));
+    } else {
+      RT_NCCL(api, api->AllReduce(h->grad, h->grad, h->nparams, ncclFloat, ncclSum, h->comm, st));
+    }
+  }
+  return apply_grads(h, st, 1.0f / (float)h->comm_world);
+}
 
 extern "C" int rt_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t transA,
                             int32_t transB, const float* A, const float* B, const float* bias,

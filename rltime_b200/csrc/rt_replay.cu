@@ -132,6 +132,7 @@ struct DrawParams {
   long long* col_start;   // base - P : env offset of row t = 0
   long long* col_base;
   double* col_weight;     // normalised importance weight per column
+  double* weight_max;     // [1] the weight the batch was normalised by (sharded replay: rescale to the global max)
 };
 
 // _sample_proportional + per-sequence importance weight (prioritized_replay_history.py:
@@ -166,6 +167,7 @@ __global__ void k_per_draw(DrawParams p) {
     for (int j = 0; j < p.B; ++j) max_w = fmax(max_w, s_w[j]);
   }
   if (i < p.B) p.col_weight[i] = __ddiv_rn(w, max_w);
+  if (i == 0) p.weight_max[0] = max_w;
 }
 
 struct AssembleParams {
@@ -523,6 +525,7 @@ struct BatchSlot {
   long long* col_count = nullptr;
   long long* col_base = nullptr;
   double* col_weight = nullptr;
+  double* weight_max = nullptr;
   double* uniforms = nullptr;
   double* h_uniforms = nullptr;   // pinned staging (pageable H2D would serialise the stream)
   cudaEvent_t h2d_done = nullptr;
@@ -843,7 +846,7 @@ int ensure_batch(rt_replay* h, BatchSlot& bs, int B) {
   }
   fr(bs.returns); fr(bs.nsteps); fr(bs.masks); fr(bs.weights); fr(bs.loss_indices);
   fr(bs.idxes); fr(bs.slots); fr(bs.col_env); fr(bs.col_start); fr(bs.col_count); fr(bs.col_base);
-  fr(bs.col_weight); fr(bs.uniforms);
+  fr(bs.col_weight); fr(bs.weight_max); fr(bs.uniforms);
   if (bs.h_uniforms) cudaFreeHost(bs.h_uniforms);
   bs.h_uniforms = nullptr;
   RT_CUDA(cudaMallocHost(&bs.h_uniforms, (size_t)B * sizeof(double)));
@@ -865,6 +868,7 @@ int ensure_batch(rt_replay* h, BatchSlot& bs, int B) {
   RT_CUDA(rt::dmalloc(&bs.col_count, (size_t)B));
   RT_CUDA(rt::dmalloc(&bs.col_base, (size_t)B));
   RT_CUDA(rt::dmalloc(&bs.col_weight, (size_t)B));
+  RT_CUDA(rt::dmalloc(&bs.weight_max, (size_t)1));
   RT_CUDA(rt::dmalloc(&bs.uniforms, (size_t)B));
   bs.B = B;
   return RT_OK;
@@ -1221,7 +1225,7 @@ int rt_replay_sample_prioritized(rt_replay* h, int32_t B, double beta, const dou
   dp.global_scaling = h->cfg.global_importance_scaling ? 1 : 0;
   dp.uniforms = bs.uniforms; dp.seq_env = h->d_seq_env; dp.seq_base = h->d_seq_base;
   dp.idxes = bs.idxes; dp.col_env = bs.col_env; dp.col_start = bs.col_start;
-  dp.col_base = bs.col_base; dp.col_weight = bs.col_weight;
+  dp.col_base = bs.col_base; dp.col_weight = bs.col_weight; dp.weight_max = bs.weight_max;
   int threads = ((B + 31) / 32) * 32;
   k_per_draw<<<1, threads, threads * sizeof(double), st>>>(dp);
   RT_LAUNCH_CHECK();
@@ -1300,6 +1304,7 @@ int rt_replay_batch(rt_replay* h, rt_batch* out) {
   out->loss_indices = h->per ? (int64_t*)bs.loss_indices : nullptr;
   out->idxes = h->per ? bs.idxes : nullptr;
   out->slots = bs.slots;
+  out->weight_max = h->per ? bs.weight_max : nullptr;
   return RT_OK;
 }
 

@@ -147,6 +147,8 @@ class DeviceReplayHistoryBuffer:
         self.last_batch = None
         self._own = torch.cuda.Stream(self.device)
         self._prev_mark = None      # caller-stream event recorded when the previous draw was requested
+        self._views = {}            # (ptr, shape, typestr) -> borrowed tensor view (the batch slots rotate
+                                    # over three fixed device buffers, so every view is built once)
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -210,8 +212,16 @@ class DeviceReplayHistoryBuffer:
 
     def close(self):
         if self._h is not None:
+            self._views = {}
             self._lib.rt_replay_destroy(self._h)
             self._h = None
+
+    def _view(self, ptr, shape, typestr):
+        key = (ptr, shape, typestr)
+        t = self._views.get(key)
+        if t is None:
+            t = self._views[key] = _lib.as_tensor(ptr, shape, typestr, self.device)
+        return t
 
     def __del__(self):
         try:
@@ -344,6 +354,16 @@ class DeviceReplayHistoryBuffer:
             assert self.train_quota > -100 * mbatch_size * self.nstep_train
         return self._get_train_data(mbatch_size, train_progress)
 
+    def draw(self, mbatch_size, train_progress=None):
+        """get_train_data for a consumer that reads the raw device batch (self.last_batch, the input of
+        DeviceLearner.step) and does not need the nested dict of tensor views: same quota / RNG / draw,
+        returns True or None."""
+        self._raw_only = True
+        try:
+            return self.get_train_data(mbatch_size, train_progress)
+        finally:
+            self._raw_only = False
+
     def _get_train_data(self, mbatch_size, train_progress):
         # replay_history.py:93-140
         if self._h is None:
@@ -364,19 +384,23 @@ class DeviceReplayHistoryBuffer:
         b = _lib.Batch()
         _lib.check(self._lib.rt_replay_batch(self._h, C.byref(b)))
         self.last_batch = b      # raw device view of the draw (input of DeviceLearner.step)
+        if getattr(self, "_raw_only", False):
+            if b.importance_weights:
+                self._last_idx_tensor = self._view(b.idxes, (b.B,), "<i4")
+            return True
         B, S, n = b.B, b.S, b.n
         dev = self.device
         states, targets = [], []
         for f, l in enumerate(self._state_leaves):
-            full = _lib.as_tensor(b.all_states[f], (S + n, B) + l.shape, l.typestr, dev)
+            full = self._view(b.all_states[f], (S + n, B) + l.shape, l.typestr)
             states.append(full[:S])
             targets.append(full[n:])
-        pos = [_lib.as_tensor(b.policy_outputs[f], (S, B) + l.shape, l.typestr, dev)
+        pos = [self._view(b.policy_outputs[f], (S, B) + l.shape, l.typestr)
                for f, l in enumerate(self._po_leaves)]
         td = {
-            "returns": _lib.as_tensor(b.returns, (S, B), "<f8", dev),
-            "nsteps": _lib.as_tensor(b.nsteps, (S, B), "<i8", dev),
-            "target_masks": _lib.as_tensor(b.target_masks, (S, B), "<f8", dev),
+            "returns": self._view(b.returns, (S, B), "<f8"),
+            "nsteps": self._view(b.nsteps, (S, B), "<i8"),
+            "target_masks": self._view(b.target_masks, (S, B), "<f8"),
             "policy_outputs": _rebuild(self._po_skel, pos),
             "states": _rebuild(self._state_skel, states),
             "target_states": _rebuild(self._state_skel, targets),
@@ -384,10 +408,10 @@ class DeviceReplayHistoryBuffer:
         }
         if b.importance_weights:
             td["extra_data"] = {
-                "importance_weights": _lib.as_tensor(b.importance_weights, (S, B), "<f8", dev),
-                "loss_indices": _lib.as_tensor(b.loss_indices, (S, B, 2), "<i8", dev),
+                "importance_weights": self._view(b.importance_weights, (S, B), "<f8"),
+                "loss_indices": self._view(b.loss_indices, (S, B, 2), "<i8"),
             }
-            self._last_idx_tensor = _lib.as_tensor(b.idxes, (B,), "<i4", dev)
+            self._last_idx_tensor = self._view(b.idxes, (B,), "<i4")
         if self.output == "numpy":
             # the reference hands numpy for everything except the state tensors
             # (history.py:235-241 vs general/backend.py:136-153)
@@ -439,6 +463,11 @@ class DevicePrioritizedReplayHistoryBuffer(DeviceReplayHistoryBuffer):
         self._overlap = overlap
         self._gap = self.nstep_train - overlap
         self._last_idx_tensor = None
+        # sharded replay: callable(device f64[1] tensor) that replaces its value by the maximum
+        # over all shards in place (e.g. torch.distributed.all_reduce(MAX) or rt_comm_allreduce_max_f64), on
+        # the CURRENT stream.  The importance weights of a draw are then normalised by the global maximum
+        # weight instead of this shard's (prioritized_replay_history.py:347-354 on the union of the shards).
+        self.global_weight_max = None
 
     def _extra_config(self, cfg):
         cfg.overlap = self._overlap
@@ -472,11 +501,24 @@ class DevicePrioritizedReplayHistoryBuffer(DeviceReplayHistoryBuffer):
         cur = self._begin_draw()
         rc = _lib.check(self._lib.rt_replay_sample_prioritized(
             self._h, mbatch_size, float(beta), C.cast(uniforms, C.c_void_p), self._stream()))
+        if rc != _lib.RT_NEED_MORE_DATA and self.global_weight_max is not None:
+            self._rescale_to_global_max()
         self._end_draw(cur)
         if rc == _lib.RT_NEED_MORE_DATA:
             self._last_idx_tensor = None
             return None
         return self._wrap_batch()
+
+    def _rescale_to_global_max(self):
+        import torch
+        b = _lib.Batch()
+        _lib.check(self._lib.rt_replay_batch(self._h, C.byref(b)))
+        with torch.cuda.stream(self._own):
+            local = _lib.as_tensor(b.weight_max, (1,), "<f8", self.device)
+            g = local.clone()
+            self.global_weight_max(g)
+            w = _lib.as_tensor(b.importance_weights, (b.S * b.B,), "<f8", self.device)
+            w.mul_(local / g)
 
     def update_losses(self, indices, losses):
         """prioritized_replay_history.py:243-279.  indices: (M, 2) rows of

@@ -231,6 +231,29 @@ class DeviceLearner:
         keep.append(arr)
         return C.cast(arr, C.c_void_p), keep
 
+    # ---- data parallelism inside the library (rt_comm_*) ---------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id (rank 0 creates it, every rank passes the same bytes to comm_init)."""
+        buf = (C.c_uint8 * 128)()
+        _lib.check(_lib.load().rt_comm_unique_id(C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _lib.check(self._lib.rt_comm_init(self._h, C.cast(buf, C.c_void_p), int(rank), int(world)))
+        self.world = int(world)
+
+    def comm_broadcast_params(self, root=0):
+        _lib.check(self._lib.rt_comm_broadcast_params(self._h, int(root), self._stream()))
+
+    def step_dp(self, batch, taus=None, io=None):
+        """One data-parallel update: local gradients, in-library NCCL sum (overlapping the conv backward),
+        identical clip + Adam on the gradient mean."""
+        tp, keep = self._tau_ptrs(taus)
+        _lib.check(self._lib.rt_learner_step_dp(self._h, C.byref(batch), C.byref(io or self.io), tp,
+                                                self._stream()))
+
     def compute_grads(self, batch, taus=None, io=None):
         """Data-parallel phase 1: everything of step() up to and including the backward pass."""
         tp, keep = self._tau_ptrs(taus)

@@ -49,6 +49,22 @@ def allreduce_sum_(flat_grad):
 _comm_streams = {}
 
 
+def init_library_comm(learner):
+    """Creates the learner's own NCCL communicator (rt_comm_init): rank 0 draws the 128-byte id, the
+    process group carries it to the other ranks -- the only thing the host language has to do."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if rank == 0:
+        ident = torch.tensor(list(learner.comm_unique_id()), dtype=torch.uint8)
+    else:
+        ident = torch.zeros(128, dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        ident = ident.to(learner.device)
+    dist.broadcast(ident, src=0)
+    learner.comm_init(bytes(ident.cpu().tolist()), rank, world)
+
+
 def data_parallel_step(learner, batch, world_size, taus=None, overlap=True):
     """compute local gradients -> all-reduce (sum) -> clip + Adam on the mean gradient.
 
@@ -56,6 +72,9 @@ def data_parallel_step(learner, batch, world_size, taus=None, overlap=True):
     conv backward starts, rt_learner_wait_late_grads) on a communication stream while the conv
     backward still runs, then the small conv bucket on the caller's stream."""
     import torch
+    if getattr(learner, "world", 1) == world_size and world_size > 1 and os.environ.get("RT_DP_LIB", "1") != "0":
+        learner.step_dp(batch, taus)      # the whole exchange inside the library (rt_learner_step_dp)
+        return
     if os.environ.get("RT_DP_OVERLAP") == "0":
         overlap = False
     learner.compute_grads(batch, taus)
@@ -82,6 +101,9 @@ def broadcast_params_(learner, src=0):
     import torch.distributed as dist
     from . import _lib
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if getattr(learner, "world", 1) == dist.get_world_size():
+            learner.comm_broadcast_params(src)
+            return
         for which in (_lib.RT_BUF_ONLINE, _lib.RT_BUF_TARGET):
             dist.broadcast(learner.flat(which), src=src)
         learner.params_changed()

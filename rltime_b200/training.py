@@ -394,7 +394,9 @@ class IQNTrainer:
                     hist.update(samples)
                     self._end_timer()
             self._start_timer("get_train_data")
-            td = hist.get_train_data(mbatch, train_progress=progress)
+            # device buffers: draw() = get_train_data without building the nested dict of tensor views
+            # (the learner reads the raw device batch)
+            td = (hist.draw if hasattr(hist, "draw") else hist.get_train_data)(mbatch, train_progress=progress)
             if td is None:
                 continue
             self._end_timer()

@@ -47,6 +47,13 @@ L2 = DeviceLearner((4, 84, 84), [(32, 8, 4), (64, 4, 2), (64, 3, 1)], U, 128, 6,
                    nstep_train=T, nstep_target=n, double_q=True, rnn_bootstrap=True, clip_grad=40.0,
                    device=dev)
 L2.load_training_state(L.training_state())
+# third replica: the whole exchange inside the library (rt_comm_init + rt_learner_step_dp, own NCCL communicator)
+L3 = DeviceLearner((4, 84, 84), [(32, 8, 4), (64, 4, 2), (64, 3, 1)], U, 128, 6, 8, 64, True, mbatch=B,
+                   nstep_train=T, nstep_target=n, double_q=True, rnn_bootstrap=True, clip_grad=40.0,
+                   device=dev)
+L3.load_training_state(L.training_state())
+parallel.init_library_comm(L3)
+os.environ["RT_DP_LIB"] = "1"
 for step in range(4):
     b, keep = batch_from_tensors(
         torch.randint(0, 255, (S + n, B, 4, 84, 84), dtype=torch.uint8, device=dev, generator=g),
@@ -57,8 +64,11 @@ for step in range(4):
     taus = [torch.rand(T * B * 8, generator=torch.Generator().manual_seed(1000 * step + 10 * rank + k)) for k in range(3)]
     parallel.data_parallel_step(L, b, world, taus=taus, overlap=True)
     parallel.data_parallel_step(L2, b, world, taus=taus, overlap=False)
+    parallel.data_parallel_step(L3, b, world, taus=taus)          # -> L3.step_dp
 torch.cuda.synchronize()
 d12 = (L.flat(_lib.RT_BUF_ONLINE) - L2.flat(_lib.RT_BUF_ONLINE)).abs().max().item()
+d13 = (L.flat(_lib.RT_BUF_ONLINE) - L3.flat(_lib.RT_BUF_ONLINE)).abs().max().item()
+assert d13 == 0.0 if world == 2 else d13 < 1e-6, "in-library data-parallel step changed the weights: %g" % d13
 # two addends commute exactly; with more ranks NCCL's reduction order depends on the message size
 assert d12 == 0.0 if world == 2 else d12 < 1e-6, "overlapped all-reduce changed the weights: %g" % d12
 w = L.flat(_lib.RT_BUF_ONLINE).clone()
@@ -69,7 +79,8 @@ diff = (hi - lo).abs().max().item()
 st = L.stats()
 if rank == 0:
     print("dist_check world=%d: replicas identical (max spread %g), grad-sum rel err %.2e, overlapped == plain "
-          "all-reduce (max diff %g), qloss %.5f grad_norm %.5f" % (world, diff, err, d12, st["qloss"], st["grad_norm"]))
+          "all-reduce (max diff %g), rt_learner_step_dp == torch.distributed path (max diff %g), qloss %.5f "
+          "grad_norm %.5f" % (world, diff, err, d12, d13, st["qloss"], st["grad_norm"]))
 assert diff == 0.0, "replicas diverged: %g" % diff
 dist.barrier()
 dist.destroy_process_group()

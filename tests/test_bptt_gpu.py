@@ -1,14 +1,11 @@
-"""Checks for code paths that are compiled but NOT enabled by default because they have not been
-validated on hardware yet.  Skipped unless RT_TEST_EXPERIMENTAL=1 (the default GPU suite must
-never depend on them)."""
+"""The one-launch BPTT recurrence (rt_bptt.cuh, the default since round 2) against the stepwise
+recurrence it replaced (RT_BPTT_PERSISTENT=0), at the full config-3 LSTM width."""
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("RT_TEST_EXPERIMENTAL") != "1",
-                                 reason="experimental paths: set RT_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _grads(env):
