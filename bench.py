@@ -245,6 +245,7 @@ def one_update(hist, learner, B, world=1):
     from rltime_b200 import parallel
     td = hist.draw(B, 0.0)          # what IQNTrainer.train calls: get_train_data minus the dict of views
     assert td is not None
+    learner.prefetch(hist.last_batch, hist._stream())     # frame conversion behind the gather, on the replay stream
     if world > 1:
         # local gradients -> NCCL sum over NVLink -> identical clip + Adam on every rank
         parallel.data_parallel_step(learner, hist.last_batch, world)

@@ -282,6 +282,11 @@ int rt_learner_step(rt_learner* h, const rt_batch* batch, const rt_learner_io* i
 int rt_learner_compute_grads(rt_learner* h, const rt_batch* batch, const rt_learner_io* io,
                              const float* const* taus_host, void* stream);
 int rt_learner_apply_grads(rt_learner* h, double grad_scale, void* stream);
+/* Optional overlap hook: converts the uint8 frames of `batch` (cnn.py:44-45: float, x 1/255) on `stream` --
+ * typically the replay buffer's stream, right behind the gather of the draw -- into a frame buffer private to
+ * that batch slot, so the next rt_learner_step / compute_grads on this batch starts at the first convolution.
+ * A no-op for model / training configurations whose passes do not share one frame conversion. */
+int rt_learner_prefetch(rt_learner* h, const rt_batch* batch, const rt_learner_io* io, void* stream);
 /* ---- data parallelism inside the library (SURVEY.md 8b export list: rt_comm_init).  The reference has no
  * multi-GPU path; these make the one exchange step of the sharded design (8e) host-language neutral: the
  * host only has to carry the 128-byte NCCL id from rank 0 to the other ranks (file, socket, MPI, a

@@ -126,6 +126,7 @@ SIGNATURES = {
     "rt_learner_step": (C.c_int, [_VP, C.POINTER(Batch), C.POINTER(LearnerIO), _VP, _VP]),
     "rt_learner_compute_grads": (C.c_int, [_VP, C.POINTER(Batch), C.POINTER(LearnerIO), _VP, _VP]),
     "rt_learner_apply_grads": (C.c_int, [_VP, C.c_double, _VP]),
+    "rt_learner_prefetch": (C.c_int, [_VP, C.POINTER(Batch), C.POINTER(LearnerIO), _VP]),
     "rt_comm_unique_id": (C.c_int, [_VP]),
     "rt_comm_init": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32]),
     "rt_comm_destroy": (C.c_int, [_VP]),

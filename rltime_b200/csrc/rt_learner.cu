@@ -153,6 +153,14 @@ struct rt_learner {
   std::vector<float*> d_c;     // conv output grads
   float *col = nullptr, *dcol = nullptr;
   float* xf = nullptr;         // frames as fp32 NHWC * (1/255): every conv layer reads NHWC runs
+  // one fp32-frame buffer per replay batch slot (keyed by the batch's frame pointer), so that the uint8 ->
+  // fp32 NHWC conversion of draw k+1 can run on the replay stream while update k still reads its own
+  // (rt_learner_prefetch); xf0 = the default buffer (hand-built batches, burn-in, acting)
+  float* xf0 = nullptr;
+  size_t xf_floats = 0;
+  std::map<const void*, float*> xf_slots;
+  const void* prefetched_x = nullptr;
+  cudaEvent_t ev_prefetch = nullptr;
   float *xg = nullptr, *hg = nullptr, *hprev = nullptr, *cprev = nullptr, *gates = nullptr,
         *c_all = nullptr, *h_all = nullptr;
   float *tau = nullptr, *cf = nullptr, *phi = nullptr, *xq = nullptr, *h1 = nullptr, *v1 = nullptr,
@@ -172,6 +180,7 @@ struct rt_learner {
   float* lstm_hrep = nullptr;   // replicated h exchange buffer of the persistent LSTM kernel
   int lstm_persistent = 1;
   int lstm_tc = 1;              // tensor-core multi-sequence recurrence (TF32 mode)
+  int lstm_mma = 0;             // ... its mma.sync variant with register-resident W_hh (RT_LSTM_MMA=1)
   float* lstm_xchg = nullptr;   // swizzled h exchange blocks of that kernel
   int lstm_tcap = 0;            // time-steps the exchange buffer holds
   int lstm_upc = 8;             // preferred hidden units per CTA of that kernel (8 or 16)
@@ -973,6 +982,23 @@ int launch_lstm_tc(rt_learner* h, cudaStream_t st, const CUtensorMap* w0, const 
   return RT_OK;
 }
 
+template <int MT>
+int launch_lstm_mma(rt_learner* h, cudaStream_t st, const rttc::LstmTcArgs& a, const float* whh0, const float* whh1,
+                    int ctas) {
+  auto kern = rttc::k_lstm_seq_mma<MT>;
+  const int smem = rttc::LstmMmaSmem::total(a.U, 16 * MT);
+  static int configured = 0;
+  if (configured < smem) {
+    RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  RT_CUDA(cudaMemsetAsync(h->grid_barrier, 0, 64 * sizeof(unsigned int), st));
+  void* args[] = {(void*)&a, (void*)&whh0, (void*)&whh1};
+  RT_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(ctas), dim3(rttc::LSTM_MMA_THREADS), args, (size_t)smem, st));
+  rt::launch_counter()++;
+  return RT_OK;
+}
+
 // All recurrences of one phase.  TF32 path: ONE tensor-core launch runs them side by side
 // (sequences of the same network share a CTA group, see rt_lstm_tc.cuh); otherwise one after
 // the other on the fp32 path (the BPTT sequence last: it owns gates / c_all / cprev).
@@ -1020,6 +1046,17 @@ int lstm_run(rt_learner* h, cudaStream_t st, const SeqDesc* seqs, int nseq, int 
     a.xchg = h->lstm_xchg;
     a.counters = h->grid_barrier;
     a.dbg = h->lstm_dbg;
+    // mma.sync variant (register-resident W_hh slice, rt_lstm_tc.cuh): U = 512, at most two sequences per
+    // weight group, 8 units per CTA
+    const int maxseq = a.nseq[0] > a.nseq[1] ? a.nseq[0] : a.nseq[1];
+    if (h->lstm_mma && U == 512 && maxseq <= 2 && groups * (U / 8) <= h->num_sms &&
+        rttc::LstmMmaSmem::total(U, 32 * maxseq) <= 227 * 1024) {
+      const int ctas = groups * (U / 8);
+      const float* whh0 = nets[0] + h->o_whh;
+      const float* whh1 = nets[groups - 1] + h->o_whh;
+      if (maxseq == 1) return launch_lstm_mma<2>(h, st, a, whh0, whh1, ctas);
+      return launch_lstm_mma<4>(h, st, a, whh0, whh1, ctas);
+    }
     const CUtensorMap *w0 = nullptr, *w1 = nullptr;
     RT_TRY(get_tmap(h->gx, nets[0] + h->o_whh, U, 4 * U, U, rttc::BLOCK_K, upc, 0, &w0));
     RT_TRY(get_tmap(h->gx, nets[groups - 1] + h->o_whh, U, 4 * U, U, rttc::BLOCK_K, upc, 0, &w1));
@@ -1316,18 +1353,26 @@ int lstm_backward(rt_learner* h, cudaStream_t st, const float* net, const float*
   RT_TRY(colsum(h, sd.st, h->dgates, rows, 4 * U, G + h->o_bih, 0, sd.colsum_scratch));
   RT_CUDA(cudaMemcpyAsync(G + h->o_bhh, G + h->o_bih, (size_t)4 * U * sizeof(float),
                           cudaMemcpyDeviceToDevice, sd.st));
-  RT_TRY(gemm(h->gx, st, mk(h->dgates, 4 * U, 0, net + h->o_wih, h->feat, 0, h->dfeat, h->feat, rows,
-                        h->feat, 4 * U)));
+  {
+    // gradient w.r.t. the trunk features; those are post-ReLU outputs (last conv / FC layer), so the ReLU
+    // derivative is applied in this GEMM's epilogue instead of a separate pass over dfeat
+    rtk::GemmArgs g = mk(h->dgates, 4 * U, 0, net + h->o_wih, h->feat, 0, h->dfeat, h->feat, rows, h->feat, 4 * U);
+    if (!h->conv.empty() || !h->pre.empty()) {
+      g.mask = feat;
+      g.ldmask = h->feat;
+    }
+    RT_TRY(gemm(h->gx, st, g));
+  }
   return RT_OK;
 }
 
 // Conv stack backward; `dlast` = gradient w.r.t. the (post-ReLU) last conv output.
 int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows,
-                 float* dlast) {
+                 float* dlast, bool dlast_masked = false) {
   (void)x;   // the frames of this pass are already in h->xf (fp32 NHWC), see cnn_forward
   float* G = h->grad;
   int nl = (int)h->conv.size();
-  {
+  if (!dlast_masked) {
     const ConvL& L = h->conv[nl - 1];
     size_t n = (size_t)rows * L.hout * L.wout * L.f;
     rtk::k_relu_bwd_inplace<<<grid1d(n), 256, 0, st>>>(dlast, h->c_out[nl - 1], n);
@@ -1404,11 +1449,12 @@ int cnn_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t
 // Backward of the feature extractor: `dlast` = gradient w.r.t. the (post-ReLU) trunk features of the
 // training pass, `x` = that pass's observation rows.  FC layers first (weight / bias gradients on the side
 // branch, the data gradient with the previous layer's ReLU mask fused in the GEMM epilogue), then the CNN.
-int features_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows, float* dlast) {
+int features_backward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows, float* dlast,
+                      bool dlast_masked) {
   float* G = h->grad;
   const int np = (int)h->pre.size();
   if (np) {
-    {
+    if (!dlast_masked) {
       size_t n = (size_t)rows * h->pre[np - 1].out;
       rtk::k_relu_bwd_inplace<<<grid1d(n), 256, 0, st>>>(dlast, h->pre_out[np - 1], n);
       RT_LAUNCH_CHECK();
@@ -1433,8 +1479,9 @@ int features_backward(rt_learner* h, cudaStream_t st, const float* net, const ui
       }
     }
     dlast = h->d_cfeat;
+    dlast_masked = false;
   }
-  if (!h->conv.empty()) RT_TRY(cnn_backward(h, st, net, x, rows, dlast));
+  if (!h->conv.empty()) RT_TRY(cnn_backward(h, st, net, x, rows, dlast, dlast_masked));
   return RT_OK;
 }
 
@@ -1680,7 +1727,10 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     size_t cc = (size_t)h->chunk_rows * opix * L.K;
     if (cc > maxcol) maxcol = cc;
   }
-  RT_TRY(dalloc(h, &h->xf, h->conv.empty() ? 1 : rows * (size_t)md->in_c * md->in_h * md->in_w, "xf"));
+  h->xf_floats = h->conv.empty() ? 1 : rows * (size_t)md->in_c * md->in_h * md->in_w;
+  RT_TRY(dalloc(h, &h->xf, h->xf_floats, "xf"));
+  h->xf0 = h->xf;
+  RT_CUDA(cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming));
   for (size_t k = 0; k < h->pre.size(); ++k) {
     float *a = nullptr, *b2 = nullptr, *d = nullptr;
     char nm[32];
@@ -1850,6 +1900,8 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     if (e && e[0] == '1') h->lstm_persistent = 0;
     e = getenv("RT_LSTM_TC");
     if (e && e[0] == '0') h->lstm_tc = 0;
+    e = getenv("RT_LSTM_MMA");
+    if (e) h->lstm_mma = atoi(e);
     e = getenv("RT_LSTM_UPC");
     if (e && atoi(e) == 16) h->lstm_upc = 16;
     e = getenv("RT_CONV_IM2COL");
@@ -1889,6 +1941,7 @@ void rt_learner_destroy(rt_learner* h) {
   for (auto& e : h->ev_side_b) if (e) cudaEventDestroy(e);
   for (auto& e : h->ev_side) if (e) cudaEventDestroy(e);
   if (h->h_stats) cudaFreeHost(h->h_stats);
+  if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
   if (h->comm) rt_comm_destroy(h);
   delete h;
 }
@@ -2051,6 +2104,27 @@ int capture_graph(cudaStream_t st, F&& body, cudaGraphExec_t* out, long long* la
   return RT_OK;
 }
 
+// fp32-frame buffer of a batch (by its frame pointer); up to 3 replay slots get their own, everything else
+// shares the default buffer
+float* xf_for(rt_learner* h, const void* all_x, bool create) {
+  auto it = h->xf_slots.find(all_x);
+  if (it != h->xf_slots.end()) return it->second;
+  if (!create || h->xf_slots.size() >= RT_BATCH_SLOTS || h->conv.empty()) return h->xf0;
+  float* p = nullptr;
+  if (cudaMalloc(&p, h->xf_floats * sizeof(float)) != cudaSuccess) {
+    cudaGetLastError();
+    return h->xf0;
+  }
+  h->allocs.push_back(p);
+  h->xf_slots[all_x] = p;
+  return p;
+}
+// the shared-frames fast path of the update: recurrent model, rnn_bootstrap, double-Q (config 3)
+bool shared_frames_path(const rt_learner* h, const rt_batch* b, const rt_learner_io* io) {
+  return h->U > 0 && h->td.rnn_bootstrap && h->R > 1 && h->td.double_q && !h->conv.empty() &&
+         b->target_states[io->field_x] == nullptr;
+}
+
 int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
                       const float* const* taus_host, void* stream, bool apply) {
   RT_REQUIRE(h && b && io, "null argument");
@@ -2070,6 +2144,11 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   const int B = h->B, P = h->P, n = h->n, U = h->U, M = h->M, Nq = h->Nq;
   const size_t frame = (size_t)h->md.in_c * h->md.in_h * h->md.in_w;
   const uint8_t* all_x = (const uint8_t*)b->all_states[io->field_x];
+  // frames already converted by rt_learner_prefetch (on the replay stream, behind the gather)?
+  const bool prefetched = h->prefetched_x == (const void*)all_x && shared_frames_path(h, b, io);
+  h->xf = prefetched ? xf_for(h, all_x, false) : h->xf0;
+  if (prefetched) RT_CUDA(cudaStreamWaitEvent(st, h->ev_prefetch, 0));
+  h->prefetched_x = nullptr;
   float* all_hx = U ? (float*)b->all_states[io->field_hx] : nullptr;
   float* all_cx = U ? (float*)b->all_states[io->field_cx] : nullptr;
   const float* all_init = U ? (const float*)b->all_states[io->field_initials] : nullptr;
@@ -2177,7 +2256,7 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       if (h->td.double_q) {
         // the target pass (rows [n, T+n)) and the online pass (rows [0, T+n)) read the same frames:
         // convert them to fp32 NHWC once
-        if (has_cnn)
+        if (has_cnn && !prefetched)
           RT_TRY(launch_frames_to_nhwc(st, svt.x, h->xf, M + n * B, h->md.in_c, h->md.in_h, h->md.in_w,
                                        (float)(1.0 / 255.0), h->rn));
         const float* xf_t = has_cnn ? h->xf + (size_t)n * B * frame : nullptr;
@@ -2326,7 +2405,8 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       RT_TRY(heads_backward(h, st, h->pr[0], feat, M, actions));
       if (U) RT_TRY(lstm_backward(h, st, h->pr[0], train_feat, M, h->R, svt.initials, svt.extra));
     }
-    if (part != 1) RT_TRY(features_backward(h, st, h->pr[0], svt.x, M, U ? h->dfeat : h->dfeatq));
+    // with an LSTM the ReLU derivative of the trunk's last layer is already applied to dfeat (lstm_backward)
+    if (part != 1) RT_TRY(features_backward(h, st, h->pr[0], svt.x, M, U ? h->dfeat : h->dfeatq, U > 0));
     return side_join(h, st);
   };
   auto backward_phase = [&]() -> int { return backward_part(0); };
@@ -2342,7 +2422,8 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   if (want_graph) {
     const void* key[12] = {all_x, all_hx, all_cx, all_init, b->returns, b->nsteps, b->target_masks,
                            b->policy_outputs[io->po_field_actions], b->importance_weights,
-                           (const void*)(uintptr_t)(split_bwd ? 1 : 0), all_extra, b->target_states[io->field_x]};
+                           (const void*)(uintptr_t)((split_bwd ? 1 : 0) | (prefetched ? 2 : 0)), all_extra,
+                           b->target_states[io->field_x]};
     for (auto& g : h->graphs)
       if (memcmp(g.key, key, sizeof(key)) == 0) sg = &g;
     if (!sg) {
@@ -2396,6 +2477,7 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
     }
   }
   h->steps_done++;
+  h->xf = h->xf0;     // everything of this update is enqueued: acting / hand-built batches use the default buffer
   int rc_apply = apply ? apply_grads(h, st, 1.0f) : RT_OK;
   if (forked) {
     RT_CUDA(cudaEventRecord(h->ev_join, st));
@@ -2416,6 +2498,22 @@ int rt_learner_step(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
 int rt_learner_compute_grads(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
                              const float* const* taus_host, void* stream) {
   return learner_step_impl(h, b, io, taus_host, stream, false);
+}
+
+int rt_learner_prefetch(rt_learner* h, const rt_batch* b, const rt_learner_io* io, void* stream) {
+  RT_REQUIRE(h && b && io, "null argument");
+  RT_CUDA(cudaSetDevice(h->device));
+  if (!shared_frames_path(h, b, io) || b->B != h->B || b->S != h->S || b->n != h->n) return RT_OK;
+  const uint8_t* all_x = (const uint8_t*)b->all_states[io->field_x];
+  float* xf = xf_for(h, all_x, true);
+  if (xf == h->xf0) return RT_OK;     // no private buffer for this batch: the update converts the frames itself
+  const size_t frame = (size_t)h->md.in_c * h->md.in_h * h->md.in_w;
+  cudaStream_t st = (cudaStream_t)stream;
+  RT_TRY(launch_frames_to_nhwc(st, all_x + (size_t)h->P * h->B * frame, xf, h->M + h->n * h->B, h->md.in_c,
+                               h->md.in_h, h->md.in_w, (float)(1.0 / 255.0), h->rn));
+  RT_CUDA(cudaEventRecord(h->ev_prefetch, st));
+  h->prefetched_x = all_x;
+  return RT_OK;
 }
 
 int rt_learner_apply_grads(rt_learner* h, double grad_scale, void* stream) {

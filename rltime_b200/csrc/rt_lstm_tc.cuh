@@ -338,4 +338,237 @@ k_lstm_seq_tc(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Same recurrence, recurrent product on mma.sync (m16n8k8 TF32, fp32 accumulate) instead of tcgen05.
+// Why: with M = 32..64 batch rows per CTA the tcgen05 version is bound by instruction issue, not by
+// math -- 64 dependent 128 x 32 x 8 MMAs per step at the ~115-cycle SS-mode floor = ~7400 cycles per
+// step, 3/4 of the 128 accumulator rows unused.  Here the [4*UPC x U] slice of W_hh lives in the
+// REGISTERS of eight compute warps as mma B fragments (warp w owns k in [64 w, 64 w + 64)), the staged
+// h_{t-1} tile (same pre-swizzled exchange blocks, same bulk copies) supplies the A fragments with
+// conflict-free LDS, and the eight K-partials are folded through shared memory in a fixed order by the
+// thread that then runs the cell for those outputs:
+//   producer warp (1)  : waits for the step counter, bulk-loads the h_{t-1} blocks          [as above]
+//   compute warps (8)  : 16*MT x 32 x 64 partial product each -> smem; thread (row r, unit pair p) folds
+//                        its 2 units x 4 gates, updates c / h, writes the exchange block of t+1
+// UPC = 8 (N = 32: n-tile == gate), up to two sequences per weight group (MT = 2 or 4 m-tiles).
+constexpr int LSTM_MMA_COMPUTE_WARPS = 8;
+constexpr int LSTM_MMA_THREADS = 32 * (1 + LSTM_MMA_COMPUTE_WARPS);
+constexpr int LSTM_FIN_PITCH = 36;     // padded row pitch (floats) of the partial tiles
+
+struct LstmMmaSmem {
+  static int total(int U, int arows) {
+    return (U / BLOCK_K) * arows * 128                                   // h tile
+           + LSTM_MMA_COMPUTE_WARPS * arows * LSTM_FIN_PITCH * 4         // K-partials
+           + (U / BLOCK_K + 2) * 8 + 16 + 1024;
+  }
+};
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int MT>   // m-tiles of 16 rows: 2 (one sequence per group) or 4 (two)
+__global__ void __launch_bounds__(LSTM_MMA_THREADS, 1)
+k_lstm_seq_mma(const __grid_constant__ LstmTcArgs a, const float* __restrict__ whh0, const float* __restrict__ whh1) {
+  constexpr int UPC = 8;
+  constexpr int AROWS = 16 * MT;
+  constexpr int NCW = LSTM_MMA_COMPUTE_WARPS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int U = a.U, T = a.T, B = a.B;
+  const int KB = U / BLOCK_K;
+  float* asm_ = reinterpret_cast<float*>(smem);                               // [KB][AROWS][32] swizzled
+  float* part = asm_ + (size_t)KB * AROWS * 32;                               // [8][AROWS][36]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(part + (size_t)NCW * AROWS * LSTM_FIN_PITCH);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cpg = U / UPC;                              // CTAs per group
+  const int grp = blockIdx.x / cpg;
+  const int u0 = (blockIdx.x - grp * cpg) * UPC;
+  const int nseq = a.nseq[grp];
+  unsigned int* counter = a.counters + grp * 32;
+  const unsigned int per_step = (unsigned int)(cpg * NCW);      // one publication per compute warp
+  const size_t step_floats = (size_t)KB * a.arows * 32;
+  float* const xg_ = a.xchg + (size_t)grp * T * step_floats;   // this group's exchange blocks
+  const int ablk = a.arows * 128;                       // bytes of one k-block of the exchange layout
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < KB; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- producer: the h_{t-1} block of every step (AROWS rows of every k-block)
+      const uint32_t cp_bytes = (uint32_t)(AROWS * 128);
+      for (int t = 0; t < T; ++t) {
+        const unsigned int want = (unsigned int)(t + 1) * per_step;
+        unsigned int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < want);
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(xg_ + (size_t)t * step_floats);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_expect_tx(&full_bar[kb], cp_bytes);
+          bulk_load(reinterpret_cast<uint8_t*>(asm_) + (size_t)kb * cp_bytes, src + (size_t)kb * ablk, cp_bytes,
+                    &full_bar[kb]);
+        }
+      }
+    }
+    return;
+  }
+  // ---------------- compute warps: k in [64 w, 64 w + 64)
+  const int w = warp - 1;
+  const int g = lane >> 2, tq = lane & 3;
+  const float* whh = grp == 0 ? whh0 : whh1;
+  // resident B fragments: k-step s (8 per warp), n-tile nt == gate nt: W[gate nt, unit u0 + g][k]
+  uint32_t wb[8][4][2];
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float* wr = whh + (size_t)(nt * U + u0 + g) * U + 64 * w + 8 * s + tq;
+      wb[s][nt][0] = __float_as_uint(__ldg(wr));
+      wb[s][nt][1] = __float_as_uint(__ldg(wr + 4));
+    }
+  // cell ownership: thread ti of the 256 -> row r = ti / 4 (+ 64 for the second half when AROWS > 64 never
+  // happens: AROWS <= 64), unit pair p = ti % 4 (units u0 + 2p, u0 + 2p + 1)
+  const int ti = w * 32 + lane;
+  const int r = ti >> 2, p2 = (ti & 3) * 2;
+  const int q = r >> 5, b = r & 31;
+  const bool act = r < AROWS && q < nseq && b < B;
+  const LstmSeq sq = a.seq[grp][q < LSTM_MAX_SEQ ? q : 0];
+  float c0 = 0.f, c1 = 0.f;
+  {
+    // publication 1: step-0 block = stored h * keep_0 (lstm.py:67-70, 95-98)
+    if (act) {
+      const float keep0 = 1.f - sq.initials[b];
+      float2 h2 = *reinterpret_cast<const float2*>(sq.hx + (size_t)b * U + u0 + p2);
+      const float2 cc = *reinterpret_cast<const float2*>(sq.cx + (size_t)b * U + u0 + p2);
+      h2 = make_float2(h2.x * keep0, h2.y * keep0);
+      if (a.rn) h2 = make_float2(rtk::rna_tf32(h2.x), rtk::rna_tf32(h2.y));
+      *reinterpret_cast<float2*>(xg_ + xchg_off(a.arows, r, u0 + p2)) = h2;
+      if (sq.hprev) *reinterpret_cast<float2*>(sq.hprev + (size_t)b * U + u0 + p2) = h2;
+      c0 = cc.x; c1 = cc.y;
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+  }
+  for (int t = 0; t < T; ++t) {
+    const size_t row = (size_t)t * B + b;
+    // this step's input gates and masks: issued before waiting for the operands
+    float2 xin[4];
+    float keep = 0.f, keep_next = 0.f;
+    if (act) {
+      const float* xr = sq.xg + row * 4 * U + u0 + p2;
+#pragma unroll
+      for (int gt = 0; gt < 4; ++gt) xin[gt] = __ldg(reinterpret_cast<const float2*>(xr + (size_t)gt * U));
+      keep = 1.f - sq.initials[row];
+      if (t + 1 < T) keep_next = 1.f - sq.initials[row + B];
+    } else {
+#pragma unroll
+      for (int gt = 0; gt < 4; ++gt) xin[gt] = make_float2(0.f, 0.f);
+    }
+    float acc[MT][4][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+#pragma unroll
+    for (int kbl = 0; kbl < 2; ++kbl) {
+      const int kb = 2 * w + kbl;
+      mbar_wait(&full_bar[kb], (uint32_t)(t & 1));
+      const float* ablock = asm_ + (size_t)kb * AROWS * 32;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {          // k-step inside the k-block: k = 8 s4 + tq (+4)
+        const int s = 4 * kbl + s4;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int r0 = 16 * mt + g, r1 = r0 + 8;
+          uint32_t af[4];
+          // 128B swizzle of the exchange layout: 16-byte chunk c of row r sits at chunk c ^ (r & 7)
+          af[0] = __float_as_uint(ablock[r0 * 32 + (((2 * s4) ^ (r0 & 7)) << 2) + tq]);
+          af[1] = __float_as_uint(ablock[r1 * 32 + (((2 * s4) ^ (r1 & 7)) << 2) + tq]);
+          af[2] = __float_as_uint(ablock[r0 * 32 + (((2 * s4 + 1) ^ (r0 & 7)) << 2) + tq]);
+          af[3] = __float_as_uint(ablock[r1 * 32 + (((2 * s4 + 1) ^ (r1 & 7)) << 2) + tq]);
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32_16x8x8(acc[mt][nt], af, wb[s][nt][0], wb[s][nt][1]);
+        }
+      }
+    }
+    // every compute warp is done folding the previous step's partials before they are overwritten
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * NCW) : "memory");
+    {
+      float* pw = part + (size_t)w * AROWS * LSTM_FIN_PITCH;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int r0 = 16 * mt + g, cc = 8 * nt + 2 * tq;
+          *reinterpret_cast<float2*>(pw + r0 * LSTM_FIN_PITCH + cc) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+          *reinterpret_cast<float2*>(pw + (r0 + 8) * LSTM_FIN_PITCH + cc) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+        }
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(32 * NCW) : "memory");
+    if (r < AROWS) {
+      // fold the 8 K-partials of (row r, gate gt, units p2, p2+1) in warp order, add the input gates
+#pragma unroll
+      for (int gt = 0; gt < 4; ++gt) {
+        float2 sum = *reinterpret_cast<const float2*>(part + r * LSTM_FIN_PITCH + 8 * gt + p2);
+#pragma unroll
+        for (int ww = 1; ww < NCW; ++ww) {
+          const float2 v = *reinterpret_cast<const float2*>(part + ((size_t)ww * AROWS + r) * LSTM_FIN_PITCH + 8 * gt + p2);
+          sum.x += v.x; sum.y += v.y;
+        }
+        xin[gt].x += sum.x; xin[gt].y += sum.y;
+      }
+    }
+    float h0 = 0.f, h1 = 0.f, cp0 = 0.f, cp1 = 0.f;
+    if (act) {
+      const float gi0 = fast_sigmoid(xin[0].x), gi1 = fast_sigmoid(xin[0].y);
+      const float gf0 = fast_sigmoid(xin[1].x), gf1 = fast_sigmoid(xin[1].y);
+      const float gg0 = fast_tanh(xin[2].x), gg1 = fast_tanh(xin[2].y);
+      const float go0 = fast_sigmoid(xin[3].x), go1 = fast_sigmoid(xin[3].y);
+      cp0 = c0 * keep; cp1 = c1 * keep;
+      c0 = gf0 * cp0 + gi0 * gg0;
+      c1 = gf1 * cp1 + gi1 * gg1;
+      h0 = go0 * fast_tanh(c0);
+      h1 = go1 * fast_tanh(c1);
+      if (a.rn) { h0 = rtk::rna_tf32(h0); h1 = rtk::rna_tf32(h1); }
+      xin[0] = make_float2(gi0, gi1); xin[1] = make_float2(gf0, gf1);
+      xin[2] = make_float2(gg0, gg1); xin[3] = make_float2(go0, go1);
+      // exchange block of step t+1 first: it is on the critical path of every CTA
+      if (t + 1 < T)
+        *reinterpret_cast<float2*>(xg_ + (size_t)(t + 1) * step_floats + xchg_off(a.arows, r, u0 + p2)) =
+            make_float2(h0 * keep_next, h1 * keep_next);
+    }
+    if (t + 1 < T) {
+      __syncwarp();
+      if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+    }
+    // everything else is off the critical path
+    if (act) {
+      *reinterpret_cast<float2*>(sq.h_all + row * U + u0 + p2) = make_float2(h0, h1);
+      if (sq.gates) {
+        float* gr = sq.gates + row * 4 * U + u0 + p2;
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt) *reinterpret_cast<float2*>(gr + (size_t)gt * U) = xin[gt];
+        *reinterpret_cast<float2*>(sq.c_all + row * U + u0 + p2) = make_float2(c0, c1);
+        *reinterpret_cast<float2*>(sq.cprev + row * U + u0 + p2) = make_float2(cp0, cp1);
+        if (t + 1 < T)
+          *reinterpret_cast<float2*>(sq.hprev + (row + B) * U + u0 + p2) = make_float2(h0 * keep_next, h1 * keep_next);
+      }
+    }
+  }
+}
+
 }  // namespace rttc

@@ -217,6 +217,11 @@ class DeviceLearner:
         _lib.check(self._lib.rt_learner_step(self._h, C.byref(batch), C.byref(io or self.io), tp,
                                              self._stream()))
 
+    def prefetch(self, batch, stream_ptr, io=None):
+        """Frame conversion of `batch` on another stream (the replay buffer's), off the update's critical
+        path; the next step() on this batch picks it up (rt_learner_prefetch)."""
+        _lib.check(self._lib.rt_learner_prefetch(self._h, C.byref(batch), C.byref(io or self.io), stream_ptr))
+
     def _tau_ptrs(self, taus):
         if taus is None or self.policy == "dqn":
             return None, []

@@ -408,6 +408,8 @@ class IQNTrainer:
                 batch = self._host_batch(td, n_target)      # host-side buffer (online history)
             elif self._assert_nsteps:
                 pass    # replay buffers guarantee the fixed n-step (multi_step_trainer.py:299-303)
+            if hasattr(hist, "update_losses_device"):
+                learner.prefetch(batch, hist._stream())      # frame conversion on the replay stream
             learner.step(batch, None if self.tau_source is None else self.tau_source(self.updates))
             if hasattr(hist, "update_losses_device"):
                 hist.update_losses_device(learner.td_abs(), ready=learner.wait_loss)
