@@ -61,7 +61,8 @@ def static_config(world, size, gemm="tf32"):
     """The `config` object: identical in the GPU arm and the reference arm."""
     return {"workload": "atari_iqn_lstm seq-PER: N=%d T=20 n=2 B=32 Nq=32 A=6 nature-CNN-LSTM512-FC512 dueling "
                         "double-Q rnn_bootstrap, weighted PER alpha .9 beta .6 overlap 10, train_frequency 4" % size,
-            "replay_per_gpu": size, "global_batch": "%d sequences x 20 steps" % (32 * world),
+            "replay_total": size, "replay_per_gpu": size // world,
+            "global_batch": "%d sequences x 20 steps" % (32 * world),
             "parallelism": "dp%d" % world,
             "l2": "inputs (28 GB frame store) exceed L2; every draw gathers different rows"}
 
@@ -336,6 +337,13 @@ def run_gpu(args):
     cfg = dict(CFG)
     if args.size:
         cfg["size"] = args.size
+    total_size = cfg["size"]
+    if world > 1:
+        # the 1M-transition replay is SHARDED by env across the GPUs (BASELINE config 4): every rank owns the
+        # transitions of its 32 / world envs in a buffer of 1M / world
+        assert cfg["envs"] % world == 0
+        cfg["size"] = cfg["size"] // world
+        cfg["envs"] = cfg["envs"] // world
     cfg["gemm"] = args.gemm
     import random
     random.seed(rank)
@@ -513,11 +521,12 @@ def run_gpu(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": dtype_of[cfg["gemm"]],
         "data": "synthetic",
-        "config": static_config(world, cfg["size"]),
+        "config": static_config(world, total_size),
         "arm": {"gemm": cfg["gemm"], "fill_s": round(fill_s, 1),
                 "schedule": "update replayed from CUDA graphs; replay on its own stream (priority write-back, next "
                             "draw and gather overlap the backward pass); weight gradients on a second graph branch",
-                "parallelism": "dp%d: replay sharded by env, NCCL all-reduce of the flat gradient" % world,
+                "parallelism": "dp%d: replay sharded by env (%d envs, %d transitions per GPU), in-library NCCL "
+                               "all-reduce of the flat gradient (rt_learner_step_dp)" % (world, cfg["envs"], cfg["size"]),
                 "updates_per_s_counts": "32-sequence batch-equivalents: world x optimizer steps/s"},
         "optimizer_steps_per_s": args.steps / (ms / 1e3),
         "value_long": {"value": world * long_steps / (ms_long / 1e3), "steps": long_steps,

@@ -180,7 +180,7 @@ struct rt_learner {
   float* lstm_hrep = nullptr;   // replicated h exchange buffer of the persistent LSTM kernel
   int lstm_persistent = 1;
   int lstm_tc = 1;              // tensor-core multi-sequence recurrence (TF32 mode)
-  int lstm_mma = 0;             // ... its mma.sync variant with register-resident W_hh (RT_LSTM_MMA=1)
+  int lstm_mma = 1;             // ... its mma.sync variant with register-resident W_hh (RT_LSTM_MMA=0: tcgen05 kernel)
   float* lstm_xchg = nullptr;   // swizzled h exchange blocks of that kernel
   int lstm_tcap = 0;            // time-steps the exchange buffer holds
   int lstm_upc = 8;             // preferred hidden units per CTA of that kernel (8 or 16)

@@ -401,12 +401,20 @@ k_lstm_seq_mma(const __grid_constant__ LstmTcArgs a, const float* __restrict__ w
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  // rows of the tile no copy ever fills (a group with fewer sequences than the other) feed accumulator rows
+  // nobody reads; zero them once so they stay finite
+  for (int i = threadIdx.x; i < KB * AROWS * 8; i += blockDim.x) {
+    const int rr = (i >> 3) % AROWS;
+    if (rr >= nseq * 32) reinterpret_cast<float4*>(asm_)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   __syncthreads();
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- producer: the h_{t-1} block of every step (AROWS rows of every k-block)
-      const uint32_t cp_bytes = (uint32_t)(AROWS * 128);
+      // ---------------- producer: the h_{t-1} block of every step: the rows of THIS group's sequences of
+      // every k-block (the exchange traffic -- every CTA pulls its group's whole h -- is what bounds a step:
+      // 128 CTAs x 128 KB = 16 MB through L2 if both groups loaded two sequences' worth)
+      const uint32_t cp_bytes = (uint32_t)(nseq * 32 * 128);
       for (int t = 0; t < T; ++t) {
         const unsigned int want = (unsigned int)(t + 1) * per_step;
         unsigned int v;
@@ -417,7 +425,7 @@ k_lstm_seq_mma(const __grid_constant__ LstmTcArgs a, const float* __restrict__ w
         const uint8_t* src = reinterpret_cast<const uint8_t*>(xg_ + (size_t)t * step_floats);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_expect_tx(&full_bar[kb], cp_bytes);
-          bulk_load(reinterpret_cast<uint8_t*>(asm_) + (size_t)kb * cp_bytes, src + (size_t)kb * ablk, cp_bytes,
+          bulk_load(reinterpret_cast<uint8_t*>(asm_) + (size_t)kb * (AROWS * 128), src + (size_t)kb * ablk, cp_bytes,
                     &full_bar[kb]);
         }
       }
@@ -493,6 +501,7 @@ k_lstm_seq_mma(const __grid_constant__ LstmTcArgs a, const float* __restrict__ w
         const int s = 4 * kbl + s4;
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
+          if (mt >= 2 * nseq) continue;             // m-tiles of sequences this group does not have
           const int r0 = 16 * mt + g, r1 = r0 + 8;
           uint32_t af[4];
           // 128B swizzle of the exchange layout: 16-byte chunk c of row r sits at chunk c ^ (r & 7)

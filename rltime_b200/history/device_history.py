@@ -139,6 +139,8 @@ class DeviceReplayHistoryBuffer:
         self.output = output
         self._h = None
         self._env_index = {}        # caller's env id -> dense index
+        self._env_code = {}         # caller's env id -> integer code stored with the transitions
+        self._code_index = {}       # that code -> dense index (update_losses gets the codes back)
         self._state_leaves = None
         self._po_leaves = None
         self._state_skel = None
@@ -236,6 +238,11 @@ class DeviceReplayHistoryBuffer:
             if e >= self.max_envs:
                 raise _lib.RtError("more than max_envs=%d distinct env ids" % self.max_envs)
             self._env_index[env_id] = e
+            # integer code echoed in loss_indices: the id itself when it is an integer, else a code
+            # outside the usual id range (remote actors use e.g. (actor, env) tuples or strings)
+            code = int(env_id) if isinstance(env_id, (int, np.integer)) else (1 << 40) + e
+            self._env_code[env_id] = code
+            self._code_index[code] = e
         return e
 
     # ------------------------------------------------------------------ History API
@@ -261,7 +268,7 @@ class DeviceReplayHistoryBuffer:
         po_cols = [np.empty((m,) + l.shape, dtype=l.dtype) for l in self._po_leaves]
         for i, s in enumerate(samples):
             env[i] = self._dense_env(s["env_id"])
-            env_ids[i] = int(s["env_id"])
+            env_ids[i] = self._env_code[s["env_id"]]
             reward[i] = float(s["reward"])
             done[i] = 1 if s["done"] else 0
             for col, (_, v) in zip(state_cols, _flatten(s["next_state"])):
@@ -534,7 +541,7 @@ class DevicePrioritizedReplayHistoryBuffer(DeviceReplayHistoryBuffer):
         assert len(indices) == len(losses)
         pairs = np.empty((len(indices), 2), dtype=np.int64)
         try:
-            pairs[:, 0] = [self._env_index[int(e)] for e in indices[:, 0]]
+            pairs[:, 0] = [self._code_index[int(e)] for e in indices[:, 0]]
         except KeyError as ex:
             raise KeyError("update_losses: unknown env id %s (prefix rows (-1,-1) must not be "
                            "sent back)" % ex)

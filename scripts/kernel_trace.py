@@ -19,6 +19,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=65536)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--timeline", action="store_true",
+                    help="also print every kernel of the last profiled update in start order: offset, duration, stream")
     args = ap.parse_args()
     cfg = dict(bench.CFG)
     cfg["size"] = args.size
@@ -36,6 +38,21 @@ def main():
             bench.one_update(hist, learner, cfg["B"])
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    if args.timeline:
+        def sn(n):
+            n = n.replace("(anonymous namespace)::", "").replace("void ", "")
+            return n.split("(")[0][-60:]
+        tl = sorted(((e.time_range.start, e.time_range.end, sn(e.name), getattr(e, "device_resource_id", -1))
+                     for e in evs), key=lambda r: r[0])
+        # the last update starts at the last k_uniform (quantile fractions: first kernel of a learner step)
+        starts = [i for i, r in enumerate(tl) if r[2].endswith("k_uniform")]
+        if starts:
+            i0 = starts[-1]
+            # include the replay kernels of this update's draw that ran just before
+            t0 = tl[i0][0]
+            print("timeline of the last update (us from its first learner kernel; stream = CUPTI stream id)")
+            for s_, e_, n_, st_ in tl[max(i0 - 12, 0):]:
+                print("  %9.1f %8.1f  s%-4s %s" % (s_ - t0, e_ - s_, st_, n_))
     rows = sorted(((e.time_range.start, e.time_range.end, e.name) for e in evs), key=lambda r: r[0])
     if not rows:
         print("no device events captured")

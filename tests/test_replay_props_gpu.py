@@ -99,3 +99,49 @@ def test_full_frame_replay_properties():
         torch.cuda.synchronize()
     finally:
         hist.close()
+
+
+@pytest.mark.gpu
+def test_non_integer_env_ids_round_trip():
+    """Remote actor pools hand out env ids that are not integers (acting/actor_pool.py builds (actor, env)
+    style ids): the buffer maps them to dense indices, echoes an integer code in loss_indices and accepts
+    that code back in update_losses; every other field is identical to the same run with integer ids."""
+    import random
+    from oracle import scenario as sc
+    from rltime_b200.history import DevicePrioritizedReplayHistoryBuffer
+    from rltime_b200.synthetic import SyntheticStream
+    kw = dict(size=300, train_frequency=None, alpha=0.8, beta=0.5, nstep_target=2, nstep_train=4, prefix_steps=1)
+    outs = []
+    for named in (False, True):
+        h = DevicePrioritizedReplayHistoryBuffer(**kw, discount_function=sc.discount_function, max_envs=3)
+        stream = SyntheticStream(num_envs=3, frame_shape=(1, 4, 4), num_actions=3, lstm_units=2, seed=2,
+                                 done_mode="bernoulli", done_p=0.05, pool=64)
+        random.seed(3)
+        rs = np.random.RandomState(4)
+        trace = []
+        try:
+            for it in range(60):
+                samples = stream.next_samples()
+                if named:
+                    for s in samples:
+                        s["env_id"] = ("actor%d" % (s["env_id"] % 2), s["env_id"])
+                h.update(samples)
+                td = h.get_train_data(4, 0.1)
+                if td is None:
+                    continue
+                flat = sc.flatten_train_data(td)
+                li = flat["extra_data/loss_indices"][1:].reshape(-1, 2)
+                h.update_losses(li, np.abs(rs.randn(len(li))))
+                flat["idx"] = np.asarray(h.last_sampled_idxes)
+                trace.append(flat)
+        finally:
+            h.close()
+        outs.append(trace)
+    assert len(outs[0]) == len(outs[1]) > 20
+    for a, b in zip(*outs):
+        for k in a:
+            if k == "extra_data/loss_indices":
+                np.testing.assert_array_equal(a[k][..., 1], b[k][..., 1])      # env offsets
+                assert ((b[k][1:, :, 0] >= (1 << 40)) | (b[k][1:, :, 0] == -1)).all()
+            else:
+                np.testing.assert_array_equal(a[k], b[k], err_msg=k)
