@@ -221,6 +221,7 @@ struct rt_learner {
   // weight / bias gradient hangs off it as a leaf, so those run on a side stream (a parallel branch
   // of the captured graph) with their own split-K workspace and column-sum scratch.
   int overlap_bwd = 1;
+  int dp_split = 0;                 // data-parallel backward as two graphs with an event in between (RT_DP_SPLIT=1)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_side[8] = {};
   int ev_side_next = 0;
@@ -1837,6 +1838,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   }
   if (const char* e = getenv("RT_GRAPHS")) h->graphs_enabled = atoi(e);
   if (const char* e = getenv("RT_OVERLAP_BWD")) h->overlap_bwd = atoi(e);
+  if (const char* e = getenv("RT_DP_SPLIT")) h->dp_split = atoi(e);
   if (const char* e = getenv("RT_OVERLAP_FWD")) h->overlap_fwd = atoi(e);
   if (const char* e = getenv("RT_CONV_SHALLOW")) h->conv_shallow = atoi(e);
   if (const char* e = getenv("RT_BPTT_PERSISTENT")) h->bptt_persistent = atoi(e);
@@ -2397,6 +2399,11 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   // part 0: the whole backward pass; 1: heads + LSTM (every non-conv gradient); 2: conv stack.
   // Data-parallel updates (apply == false) run parts 1 and 2 with an event in between, so the
   // all-reduce of the non-conv gradients (99 % of the bytes) overlaps the conv backward.
+  // Data-parallel updates (apply == false) additionally publish the point where the gradients of every
+  // non-conv parameter (99 % of the bytes) are final: an EXTERNAL event-record node on the weight-gradient
+  // branch right behind its last such leaf, inside the one backward graph -- the caller's all-reduce of that
+  // bucket then overlaps the conv backward without cutting the schedule in two (rt_learner_wait_late_grads).
+  const bool dp_event = !apply && h->dp_split == 0;
   auto backward_part = [&](int part) -> int {
     h->side_active = h->overlap_bwd && forked && !h->gx.profile;
     struct Off { rt_learner* h; ~Off() { h->side_active = false; } } off{h};
@@ -2404,6 +2411,13 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       RT_CUDA(cudaMemsetAsync(h->grad, 0, h->nparams * sizeof(float), st));
       RT_TRY(heads_backward(h, st, h->pr[0], feat, M, actions));
       if (U) RT_TRY(lstm_backward(h, st, h->pr[0], train_feat, M, h->R, svt.initials, svt.extra));
+      if (part == 0 && dp_event) {
+        cudaStream_t es = h->side_active ? h->side : st;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        RT_CUDA(cudaStreamIsCapturing(es, &cs));
+        RT_CUDA(cudaEventRecordWithFlags(h->ev_late, es, cs == cudaStreamCaptureStatusActive
+                                                              ? cudaEventRecordExternal : cudaEventRecordDefault));
+      }
     }
     // with an LSTM the ReLU derivative of the trunk's last layer is already applied to dfeat (lstm_backward)
     if (part != 1) RT_TRY(features_backward(h, st, h->pr[0], svt.x, M, U ? h->dfeat : h->dfeatq, U > 0));
@@ -2412,7 +2426,7 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   auto backward_phase = [&]() -> int { return backward_part(0); };
   auto backward_late = [&]() -> int { return backward_part(1); };
   auto backward_conv = [&]() -> int { return backward_part(2); };
-  const bool split_bwd = !apply;
+  const bool split_bwd = !apply && h->dp_split != 0;    // RT_DP_SPLIT=1: the older two-graph schedule
 
   // ---- run: replayed from CUDA graphs once the handle is warm (every lazy allocation / kernel
   // attribute of these shapes has happened), keyed by the batch's device pointers (the replay
@@ -2422,7 +2436,8 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   if (want_graph) {
     const void* key[12] = {all_x, all_hx, all_cx, all_init, b->returns, b->nsteps, b->target_masks,
                            b->policy_outputs[io->po_field_actions], b->importance_weights,
-                           (const void*)(uintptr_t)((split_bwd ? 1 : 0) | (prefetched ? 2 : 0)), all_extra,
+                           (const void*)(uintptr_t)((split_bwd ? 1 : 0) | (prefetched ? 2 : 0) | (dp_event ? 4 : 0)),
+                           all_extra,
                            b->target_states[io->field_x]};
     for (auto& g : h->graphs)
       if (memcmp(g.key, key, sizeof(key)) == 0) sg = &g;
