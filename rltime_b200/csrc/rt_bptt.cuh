@@ -28,7 +28,12 @@ namespace rtbptt {
 
 constexpr int THREADS = 256;
 constexpr int KROWS = 256;             // gate rows per K-slice (4 gates x 64 units)
-constexpr int DG_PITCH = KROWS + 4;    // padded row pitch of the staged dgates tile: conflict-free fragment loads
+// The dgates tile is staged in two halves of 128 k (2 gates x 64 units): 16.9 KB of shared memory instead of
+// 33.3 KB, so that a CTA of this latency-bound kernel fits on an SM NEXT TO two CTAs of the weight-gradient
+// GEMMs of the side branch (2 x 97 KB) -- otherwise the cooperative launch waits for that branch's first
+// GEMM to drain (measured: 75 us on the critical path).
+constexpr int KHALF = KROWS / 2;
+constexpr int DG_PITCH = KHALF + 4;    // padded row pitch of the staged half tile: conflict-free fragment loads
 constexpr int CTR_STRIDE = 32;         // counters 128 B apart
 
 struct Args {
@@ -142,25 +147,40 @@ __global__ void __launch_bounds__(THREADS, 2) k_lstm_bptt_p(const Args a) {
     signal(cell_done + (j >> 1) * CTR_STRIDE);                               // my share of K-slice j/2 is written
     wait_for(cell_done + i * CTR_STRIDE, (unsigned int)(2 * KS * (step + 1)));   // dgates_t[:, K-slice i] complete
 
-    // ---------------- partial product: dgates_t[:, K-slice i] . W block
-    for (int v = tid; v < 32 * (KROWS / 4); v += THREADS) {
-      const int b = v / (KROWS / 4), kk = (v % (KROWS / 4)) * 4;
-      const float4 x = __ldcg(reinterpret_cast<const float4*>(
-          a.dgates + (ro + b) * U4 + (size_t)(kk >> 6) * U + 64 * i + (kk & 63)));
-      *reinterpret_cast<float4*>(dg_s + b * DG_PITCH + kk) = x;
-    }
-    __syncthreads();
+    // ---------------- partial product: dgates_t[:, K-slice i] . W block, in two halves of 128 k
     float d[4] = {0.f, 0.f, 0.f, 0.f};
     const float* arow0 = dg_s + (16 * mi + (lane >> 2)) * DG_PITCH + (lane & 3);
     const float* arow1 = arow0 + 8 * DG_PITCH;
+    // both halves' loads are issued up front (registers), the second half is stored once the first is consumed
+    float4 stage[2][(32 * (KHALF / 4)) / THREADS];
 #pragma unroll
-    for (int s = 0; s < 32; ++s) {
-      uint32_t af[4];
-      af[0] = __float_as_uint(arow0[8 * s]);
-      af[1] = __float_as_uint(arow1[8 * s]);
-      af[2] = __float_as_uint(arow0[8 * s + 4]);
-      af[3] = __float_as_uint(arow1[8 * s + 4]);
-      mma_tf32(d, af, wb[s][0], wb[s][1]);
+    for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+      for (int it = 0; it < (32 * (KHALF / 4)) / THREADS; ++it) {
+        const int v = tid + it * THREADS;
+        const int b = v / (KHALF / 4), kk = hf * KHALF + (v % (KHALF / 4)) * 4;
+        stage[hf][it] = __ldcg(reinterpret_cast<const float4*>(
+            a.dgates + (ro + b) * U4 + (size_t)(kk >> 6) * U + 64 * i + (kk & 63)));
+      }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      if (hf) __syncthreads();                 // every warp is done reading the first half
+#pragma unroll
+      for (int it = 0; it < (32 * (KHALF / 4)) / THREADS; ++it) {
+        const int v = tid + it * THREADS;
+        const int b = v / (KHALF / 4), kk = (v % (KHALF / 4)) * 4;
+        *reinterpret_cast<float4*>(dg_s + b * DG_PITCH + kk) = stage[hf][it];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < 16; ++s) {
+        uint32_t af[4];
+        af[0] = __float_as_uint(arow0[8 * s]);
+        af[1] = __float_as_uint(arow1[8 * s]);
+        af[2] = __float_as_uint(arow0[8 * s + 4]);
+        af[3] = __float_as_uint(arow1[8 * s + 4]);
+        mma_tf32(d, af, wb[16 * hf + s][0], wb[16 * hf + s][1]);
+      }
     }
     {
       const int b0 = 16 * mi + (lane >> 2);

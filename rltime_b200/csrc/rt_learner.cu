@@ -237,6 +237,8 @@ struct rt_learner {
   // third branch (forward only): the selection heads pass, with a third activation set
   cudaStream_t side_b = nullptr;
   cudaEvent_t ev_side_b[2] = {};     // [0] fork, [1] join
+  cudaEvent_t ev_phi = nullptr;      // early quantile embeddings of the training pass are done
+  int phi_early = 1;                 // RT_PHI_EARLY=0: embeddings inside the heads passes, after the recurrence
   GemmCtx gx3;
   float *cf3 = nullptr, *phi3 = nullptr, *xq3 = nullptr, *h1c = nullptr, *v1c = nullptr, *adv3 = nullptr,
         *vb3 = nullptr;
@@ -1115,20 +1117,25 @@ HeadSet third_set(rt_learner* h, float* q_out) {
   return HeadSet{h->cf3, h->phi3, h->xq3, h->h1c, h->v1c, h->adv3, h->vb3, q_out, &h->gx3};
 }
 
+// phase 0: the whole pass; 1: only the quantile embedding phi = relu(cos(pi i tau) Wq + bq), which does not depend
+// on the trunk (it can run next to the LSTM recurrence); 2: everything after it
 int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float* feat, int M,
-                  const float* tau, const HeadSet* set = nullptr) {
+                  const float* tau, const HeadSet* set = nullptr, int phase = 0) {
   const HeadSet hs = set ? *set : primary_set(h, h->q);
   int Nq = h->Nq, D = h->D, F = h->F, A = h->A, E = h->E;
   size_t MQ = (size_t)M * Nq;
   rtk::GemmArgs g;
   const float* xq = feat;     // DQN: the heads read the trunk output directly
-  if (!h->dqn) {
+  if (!h->dqn && phase != 2) {
     rtk::k_cos_features<<<cdiv(MQ * E, 256), 256, 0, st>>>(tau, hs.cf, (int)MQ, E, h->rn);
     RT_LAUNCH_CHECK();
     g = mk(hs.cf, E, 0, net + h->o_qw, E, 1, hs.phi, D, (int)MQ, D, E);
     g.bias = net + h->o_qb;
     g.relu = 1;
     RT_TRY(gemm(*hs.gx, st, g));
+  }
+  if (phase == 1) return RT_OK;
+  if (!h->dqn) {
     rtk::k_quantile_mul<<<cdiv(MQ * (D / 4), 256), 256, 0, st>>>(feat, hs.phi, hs.xq, MQ, D, Nq, h->rn);
     RT_LAUNCH_CHECK();
     xq = hs.xq;
@@ -1835,6 +1842,8 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     RT_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, prio_lo));
     RT_CUDA(cudaStreamCreateWithPriority(&h->side_b, cudaStreamNonBlocking, prio_lo));
     for (auto& e : h->ev_side_b) RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    RT_CUDA(cudaEventCreateWithFlags(&h->ev_phi, cudaEventDisableTiming));
+    if (const char* e = getenv("RT_PHI_EARLY")) h->phi_early = atoi(e);
   }
   if (const char* e = getenv("RT_GRAPHS")) h->graphs_enabled = atoi(e);
   if (const char* e = getenv("RT_OVERLAP_BWD")) h->overlap_bwd = atoi(e);
@@ -1941,6 +1950,7 @@ void rt_learner_destroy(rt_learner* h) {
   if (h->side) cudaStreamDestroy(h->side);
   if (h->side_b) cudaStreamDestroy(h->side_b);
   for (auto& e : h->ev_side_b) if (e) cudaEventDestroy(e);
+  if (h->ev_phi) cudaEventDestroy(h->ev_phi);
   for (auto& e : h->ev_side) if (e) cudaEventDestroy(e);
   if (h->h_stats) cudaFreeHost(h->h_stats);
   if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
@@ -2292,20 +2302,35 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
       train_feat = f;
       seqs[ns++] = SeqDesc{h->pr[0], h->xg, svt.hx, svt.cx, svt.initials, h->h_all, 0, true};
       if (fork_fwd) RT_TRY(side_join(h, st));
+      // The quantile embeddings of the three heads passes do not depend on the trunk: they run on the side
+      // branches NEXT TO the recurrence (whose 128 latency-bound CTAs leave the rest of the GPU idle)
+      const bool phi_early = fork_fwd && !h->dqn && h->phi_early;
+      const HeadSet hs2 = second_set(h, h->tq);
+      const HeadSet hs_sel = third_set(h, h->sq);
+      if (phi_early) {
+        SideCtx sd;
+        RT_TRY(side_begin(h, st, &sd));
+        RT_TRY(heads_forward(h, sd.st, h->pr[1], nullptr, M, tau_seg[0], &hs2, 1));
+        RT_CUDA(cudaEventRecord(h->ev_side_b[0], st));
+        RT_CUDA(cudaStreamWaitEvent(h->side_b, h->ev_side_b[0], 0));
+        RT_TRY(heads_forward(h, h->side_b, h->pr[0], nullptr, M, tau_seg[1], &hs_sel, 1));
+        RT_TRY(heads_forward(h, h->side_b, h->pr[0], nullptr, M, tau_seg[2], nullptr, 1));
+        RT_CUDA(cudaEventRecord(h->ev_phi, h->side_b));
+      }
       RT_TRY(lstm_run(h, st, seqs, ns, R, BR));
+      const int hp = phi_early ? 2 : 0;
+      if (phi_early) RT_CUDA(cudaStreamWaitEvent(st, h->ev_phi, 0));
       if (fork_fwd) {
         // target heads on the side branch (second set, q straight into tq); selection and training
         // heads on the main branch; the bootstrap target needs all three
         SideCtx sd;
         RT_TRY(side_begin(h, st, &sd));
-        const HeadSet hs2 = second_set(h, h->tq);
-        RT_TRY(heads_forward(h, sd.st, h->pr[1], h->h_all2, M, tau_seg[0], &hs2));
+        RT_TRY(heads_forward(h, sd.st, h->pr[1], h->h_all2, M, tau_seg[0], &hs2, hp));
         // ... and the selection pass on a third branch with its own set
         RT_CUDA(cudaEventRecord(h->ev_side_b[0], st));
         RT_CUDA(cudaStreamWaitEvent(h->side_b, h->ev_side_b[0], 0));
-        const HeadSet hs_sel = third_set(h, h->sq);
-        RT_TRY(heads_forward(h, h->side_b, h->pr[0], h->h_all3, M, tau_seg[1], &hs_sel));
-        RT_TRY(heads_forward(h, st, h->pr[0], h->h_all, M, tau_seg[2]));
+        RT_TRY(heads_forward(h, h->side_b, h->pr[0], h->h_all3, M, tau_seg[1], &hs_sel, hp));
+        RT_TRY(heads_forward(h, st, h->pr[0], h->h_all, M, tau_seg[2], nullptr, hp));
         RT_CUDA(cudaEventRecord(h->ev_side_b[1], h->side_b));
         RT_CUDA(cudaStreamWaitEvent(st, h->ev_side_b[1], 0));
         RT_TRY(side_join(h, st));
