@@ -94,6 +94,7 @@ struct PInfo {
 };
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+int grid1d(size_t n, int threads = 256);
 
 #define RT_TRY(x)                   \
   do {                              \
@@ -353,7 +354,7 @@ int gemm_simt(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   cx.last_splits = splits;
   if (splits > 1 && !cx.defer_reduce) {
     size_t total = (size_t)g.M * g.N;
-    rtk::k_splitk_reduce<<<cdiv(total, 32), dim3(32, 8), 0, st>>>(g, splits);
+    rtk::k_splitk_reduce<<<grid1d(total / 4 + 1), 256, 0, st>>>(g, splits);
     RT_LAUNCH_CHECK();
   }
   return RT_OK;
@@ -510,7 +511,7 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   cx.last_splits = splits;
   if (splits > 1 && !cx.defer_reduce) {
     size_t total = (size_t)g.M * g.N;
-    rtk::k_splitk_reduce<<<cdiv(total, 32), dim3(32, 8), 0, st>>>(a.g, splits);
+    rtk::k_splitk_reduce<<<grid1d(total / 4 + 1), 256, 0, st>>>(a.g, splits);
     RT_LAUNCH_CHECK();
   }
   return RT_OK;
@@ -575,7 +576,7 @@ int colsum(rt_learner* h, cudaStream_t st, const float* x, size_t rows, int N, f
   return RT_OK;
 }
 
-int grid1d(size_t n, int threads = 256) {
+int grid1d(size_t n, int threads) {
   size_t b = (n + threads - 1) / threads;
   if (b > 148 * 32) b = 148 * 32;
   if (b < 1) b = 1;
@@ -761,7 +762,7 @@ int conv_dw_tc(rt_learner* h, GemmCtx& cx, cudaStream_t st, size_t i, const void
   rtk::GemmArgs g = mk(nullptr, 0, 0, nullptr, 0, 0, dW, L.K, L.f, L.K, a.P);
   g.ws = cx.ws;
   size_t total = (size_t)L.f * L.K;
-  rtk::k_splitk_reduce<<<cdiv(total, 32), dim3(32, 8), 0, st>>>(g, splits);
+  rtk::k_splitk_reduce<<<grid1d(total / 4 + 1), 256, 0, st>>>(g, splits);
   RT_LAUNCH_CHECK();
   return RT_OK;
 }
