@@ -127,11 +127,29 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) k_sgemm(const __grid_co
   }
 }
 
-// Deterministic split-K reduction + epilogue.  The partials are [splits][M][N] with N % 4 == 0 on the
-// vector path: a thread owns four consecutive outputs and folds the splits in index order (fixed order =
-// bit-reproducible) with 16-byte loads, `splits` independent loads in flight.  (The first version gave every
-// 32 outputs a 256-thread CTA: 16k tiny CTAs for the hidden-layer weight gradient, 44 us next to the BPTT
-// kernel for 10 MB of traffic.)
+// Split-K reduction for SMALL outputs with MANY splits (conv weight gradients: 8k..37k outputs, up to 148
+// splits): a CTA of 32 x 8 threads folds 32 outputs, the 8 row-lanes striding over the splits (fixed order),
+// then a fixed 8-way tree.
+__global__ void k_splitk_reduce_small(const __grid_constant__ GemmArgs g, int splits) {
+  __shared__ float s[8][33];
+  size_t total = (size_t)g.M * g.N;
+  size_t idx = (size_t)blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (idx < total)
+    for (int sp = threadIdx.y; sp < splits; sp += 8) acc += g.ws[(size_t)sp * total + idx];
+  s[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && idx < total) {
+    float t = ((s[0][threadIdx.x] + s[1][threadIdx.x]) + (s[2][threadIdx.x] + s[3][threadIdx.x])) +
+              ((s[4][threadIdx.x] + s[5][threadIdx.x]) + (s[6][threadIdx.x] + s[7][threadIdx.x]));
+    int m = (int)(idx / g.N), n = (int)(idx - (size_t)m * g.N);
+    g.C[(size_t)m * g.ldc + n] = gemm_epilogue(g, m, n, t);
+  }
+}
+
+// ... and for LARGE outputs with few splits (hidden-layer weight gradient: 512k outputs, 4 splits): a thread
+// owns four consecutive outputs and folds the splits in index order with 16-byte loads (the CTA-per-32-outputs
+// form above is 16k tiny CTAs here: 44 us next to the BPTT kernel for 10 MB of traffic; this one 5.5 us).
 __global__ void __launch_bounds__(256) k_splitk_reduce(const __grid_constant__ GemmArgs g, int splits) {
   const size_t total = (size_t)g.M * g.N;
   if ((g.N & 3) == 0) {
@@ -580,19 +598,8 @@ __global__ void k_colsum_partial(const float* __restrict__ x, float* __restrict_
   size_t r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
   float acc = 0.f;
-  if (n < N) {
-    // four independent row streams per thread: the loop is load-latency-bound with one
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    size_t r = r0 + threadIdx.y;
-    for (; r + 24 < r1; r += 32) {
-      a0 += x[r * N + n];
-      a1 += x[(r + 8) * N + n];
-      a2 += x[(r + 16) * N + n];
-      a3 += x[(r + 24) * N + n];
-    }
-    for (; r < r1; r += 8) a0 += x[r * N + n];
-    acc = (a0 + a1) + (a2 + a3);
-  }
+  if (n < N)
+    for (size_t r = r0 + threadIdx.y; r < r1; r += 8) acc += x[r * N + n];
   s[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {

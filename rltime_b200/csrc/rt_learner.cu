@@ -95,6 +95,14 @@ struct PInfo {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 int grid1d(size_t n, int threads = 256);
+// fixed-order fold of split-K partials: vector form for large outputs, CTA-per-32-outputs form for small ones
+inline void launch_splitk_reduce(cudaStream_t st, const rtk::GemmArgs& g, int splits) {
+  const size_t total = (size_t)g.M * g.N;
+  if (total >= ((size_t)1 << 18) && (g.N & 3) == 0)
+    launch_splitk_reduce(st, g, splits);
+  else
+    rtk::k_splitk_reduce_small<<<(unsigned)((total + 31) / 32), dim3(32, 8), 0, st>>>(g, splits);
+}
 
 #define RT_TRY(x)                   \
   do {                              \
@@ -354,7 +362,7 @@ int gemm_simt(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   cx.last_splits = splits;
   if (splits > 1 && !cx.defer_reduce) {
     size_t total = (size_t)g.M * g.N;
-    rtk::k_splitk_reduce<<<grid1d(total / 4 + 1), 256, 0, st>>>(g, splits);
+    launch_splitk_reduce(st, g, splits);
     RT_LAUNCH_CHECK();
   }
   return RT_OK;
@@ -511,7 +519,7 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   cx.last_splits = splits;
   if (splits > 1 && !cx.defer_reduce) {
     size_t total = (size_t)g.M * g.N;
-    rtk::k_splitk_reduce<<<grid1d(total / 4 + 1), 256, 0, st>>>(a.g, splits);
+    launch_splitk_reduce(st, a.g, splits);
     RT_LAUNCH_CHECK();
   }
   return RT_OK;
@@ -762,7 +770,7 @@ int conv_dw_tc(rt_learner* h, GemmCtx& cx, cudaStream_t st, size_t i, const void
   rtk::GemmArgs g = mk(nullptr, 0, 0, nullptr, 0, 0, dW, L.K, L.f, L.K, a.P);
   g.ws = cx.ws;
   size_t total = (size_t)L.f * L.K;
-  rtk::k_splitk_reduce<<<grid1d(total / 4 + 1), 256, 0, st>>>(g, splits);
+  launch_splitk_reduce(st, g, splits);
   RT_LAUNCH_CHECK();
   return RT_OK;
 }
