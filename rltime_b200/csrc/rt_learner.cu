@@ -99,7 +99,7 @@ int grid1d(size_t n, int threads = 256);
 inline void launch_splitk_reduce(cudaStream_t st, const rtk::GemmArgs& g, int splits) {
   const size_t total = (size_t)g.M * g.N;
   if (total >= ((size_t)1 << 18) && (g.N & 3) == 0)
-    launch_splitk_reduce(st, g, splits);
+    rtk::k_splitk_reduce<<<grid1d(total / 4 + 1), 256, 0, st>>>(g, splits);
   else
     rtk::k_splitk_reduce_small<<<(unsigned)((total + 31) / 32), dim3(32, 8), 0, st>>>(g, splits);
 }
