@@ -489,3 +489,113 @@ def test_checkpoint_resume_is_bit_exact():
     finally:
         A.close()
         Bn.close()
+
+
+def _one_update_vs_oracle(c, seed, mode="tf32"):
+    """One update of case `c` (full-size shapes) on seeded random data: CUDA path vs the torch oracle."""
+    spec = spec_of(c)
+    rs = np.random.RandomState(seed)
+    S, B, n, T, P = c["T"] + c["P"], c["B"], c["n"], c["T"], c["P"]
+    M, Nq, U = T * B, c["nq"], c["lstm"]
+    raw = {
+        "all_x": rs.randint(0, 256, (S + n, B) + tuple(c["in_shape"])).astype(np.uint8),
+        "returns": np.sign(rs.randn(S, B)) * (rs.rand(S, B) < 0.3), "nsteps": np.full((S, B), n, dtype=np.int64),
+        "target_masks": (rs.rand(S, B) > 0.05).astype(np.float64),
+        "actions": rs.randint(0, c["actions"], (S, B)).astype(np.int64),
+        "importance_weights": rs.rand(S, B) * 0.5 + 0.5,
+    }
+    if U:
+        raw["all_hx"] = (0.3 * rs.randn(S + n, B, U)).astype(np.float32)
+        raw["all_cx"] = (0.3 * rs.randn(S + n, B, U)).astype(np.float32)
+        raw["all_initials"] = (rs.rand(S + n, B) < 0.03).astype(np.float32)
+    allt = {k: torch.from_numpy(v.copy()) for k, v in raw.items()}
+
+    def st(lo_, hi):
+        s = {"x": allt["all_x"][lo_:hi]}
+        if U:
+            s["layer1_state"] = {"hx": allt["all_hx"][lo_:hi], "cx": allt["all_cx"][lo_:hi],
+                                 "initials": allt["all_initials"][lo_:hi]}
+        return s
+    batch = {"states": st(0, S), "target_states": st(n, S + n), "returns": allt["returns"],
+             "nsteps": allt["nsteps"], "target_masks": allt["target_masks"],
+             "actions": allt["actions"], "importance_weights": allt["importance_weights"]}
+    gen = torch.Generator().manual_seed(seed + 1)
+    taus = [torch.rand(M * Nq, generator=gen) for _ in range(3)]
+    p_on, p_tg = spec.init_params(1), spec.init_params(2)
+    p_ref = {k: v.clone() for k, v in p_on.items()}
+    opt = lo.Adam(p_ref, lr=1e-3, eps=c["adam_eps"])
+    res = lo.learner_update(spec, p_ref, p_tg, opt, batch, {"target": taus[0], "select": taus[1], "train": taus[2]},
+                            c["gamma"], double_q=c["double_q"], rnn_bootstrap=c["rnn_bootstrap"],
+                            vf_eps=c["vf_eps"], clip_grad=c["clip_grad"], burn_in_timesteps=P)
+    L = make_learner(c, gemm=mode)
+    try:
+        L.load_state_dict(p_on, 0)
+        L.load_state_dict(p_tg, 1)
+        b, keep = device_batch(raw, c)
+        L.step(b, taus)
+        stt = L.stats()
+        ok = res["select_margin"].numpy() >= 2e-4
+        errs = []
+        dt = np.abs(L.debug("targets", (M, Nq)).cpu().numpy() - res["targets"].numpy())
+        dr = np.abs(L.td_abs().cpu().numpy() - res["report"].numpy())
+        for name, v in (("targets", float(dt[ok].max())), ("report", float(dr[ok].max())),
+                        ("qloss", abs(stt["qloss"] - float(res["loss"]))),
+                        ("td_mean", abs(stt["td_mean"] - float(res["td_mean"])))):
+            if not v <= 1e-4:
+                errs.append("%s: |d| = %.3e > 1e-4" % (name, v))
+        if abs(stt["grad_norm"] - res["grad_norm"]) > 2e-2 * res["grad_norm"]:
+            errs.append("grad_norm %.5f vs %.5f" % (stt["grad_norm"], res["grad_norm"]))
+        print("qloss %.6f (oracle %.6f) max|d targets| %.2e max|d report| %.2e near-tie rows %d" % (
+            stt["qloss"], float(res["loss"]), dt[ok].max(), dr[ok].max(), int((~ok).sum())))
+        assert not errs, "\n".join(errs)
+    finally:
+        L.close()
+
+
+@pytest.mark.gpu
+def test_learner_full_size_burn_in_vs_oracle():
+    """BASELINE config 3 at real size: nature CNN, LSTM 512, Nq 32, B 32, T 20 with a burn-in prefix and
+    n = 5 (S + n = 33 time-steps of 84x84x4 frames), vf-rescale on: TF32 path vs the torch oracle."""
+    c = dict(in_shape=(4, 84, 84), conv=[(32, 8, 4), (64, 4, 2), (64, 3, 1)], lstm=512, fc=512,
+             actions=6, nq=32, embed=64, dueling=True, B=32, T=20, P=8, n=5, gamma=0.997,
+             double_q=True, rnn_bootstrap=True, vf_eps=1e-3, clip_grad=40.0, adam_eps=1e-5)
+    _one_update_vs_oracle(c, seed=21)
+
+
+@pytest.mark.gpu
+def test_learner_full_size_config2_cnn_iqn_vs_oracle():
+    """BASELINE config 2 at real size: IQN on the 3136-wide CNN output (nature_cnn_fc512, no LSTM), T = 1,
+    n = 3, B = 32, Nq = 32: TF32 path vs the torch oracle."""
+    c = dict(in_shape=(4, 84, 84), conv=[(32, 8, 4), (64, 4, 2), (64, 3, 1)], lstm=0, fc=512,
+             actions=6, nq=32, embed=64, dueling=True, B=32, T=1, P=0, n=3, gamma=0.99,
+             double_q=True, rnn_bootstrap=False, vf_eps=None, clip_grad=10.0, adam_eps=1.5e-4)
+    _one_update_vs_oracle(c, seed=22)
+
+
+@pytest.mark.gpu
+def test_checkpoint_resume_covers_device_rng_and_dynamic_clip():
+    """A resumed learner continues bit-exactly also when the quantile fractions come from the device RNG
+    (no injected tau) and the gradient clip follows its moving average (rng counter + EMA are part of
+    training_state())."""
+    name = "iqn_lstm_clip"
+    c = dict(CASES[name], clip_dyn_alpha=0.9)
+    g = load_golden("learner_%s.npz" % name)
+    A, Bn = make_learner(c), make_learner(c)
+    try:
+        A.load_state_dict(params_of(g, "online"), 0)
+        A.load_state_dict(params_of(g, "target"), 1)
+        batches = [device_batch(batch_of(g, c, u)[1], c) for u in range(c["updates"])]
+        for u in range(c["updates"]):
+            A.step(batches[u][0])
+        Bn.load_training_state(A.training_state())
+        for L in (A, Bn):
+            L.step(batches[0][0])
+            L.step(batches[1][0])
+        sa, sb = A.training_state(), Bn.training_state()
+        assert sa["rng_counter"] == sb["rng_counter"] > 0 and sa["clip_ema"] == sb["clip_ema"] > 0
+        for part in ("online", "adam_m", "adam_v"):
+            for k in sa[part]:
+                np.testing.assert_array_equal(sa[part][k].numpy(), sb[part][k].numpy(), err_msg=part + "/" + k)
+    finally:
+        A.close()
+        Bn.close()
