@@ -642,10 +642,6 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
         continue;
       }
-      // fused dueling heads: partial dot products of this lane's row with the out / value layer rows
-      float pa[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pa[i] = 0.f;
 #pragma unroll 1
       for (int c = c_first; c < CHUNKS; c += CSTEP) {
         uint32_t v[32];
@@ -657,43 +653,7 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (lane == 0)
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[acc])) : "memory");
         }
-        const int ncol = n0 + c * 32;
-        if (g.hd_part && ncol < g.N) {
-          // lane = row of the tile; x = relu(acc + bias) exactly as the stored activation
-          const bool adv_half = ncol < g.hd_F;
-          const float* wrow = adv_half ? g.hd_wout + ncol : g.hd_wv + (ncol - g.hd_F);
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + ncol) + i4);
-            const float x0 = fmaxf(__uint_as_float(v[4 * i4]) + b4.x, 0.f);
-            const float x1 = fmaxf(__uint_as_float(v[4 * i4 + 1]) + b4.y, 0.f);
-            const float x2 = fmaxf(__uint_as_float(v[4 * i4 + 2]) + b4.z, 0.f);
-            const float x3 = fmaxf(__uint_as_float(v[4 * i4 + 3]) + b4.w, 0.f);
-            if (adv_half) {
-#pragma unroll
-              for (int aa = 0; aa < 8; ++aa)
-                if (aa < g.hd_A) {
-                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + (size_t)aa * g.hd_F) + i4);
-                  pa[aa] = fmaf(x0, w4.x, pa[aa]); pa[aa] = fmaf(x1, w4.y, pa[aa]);
-                  pa[aa] = fmaf(x2, w4.z, pa[aa]); pa[aa] = fmaf(x3, w4.w, pa[aa]);
-                }
-            } else {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow) + i4);
-              pa[0] = fmaf(x0, w4.x, pa[0]); pa[0] = fmaf(x1, w4.y, pa[0]);
-              pa[0] = fmaf(x2, w4.z, pa[0]); pa[0] = fmaf(x3, w4.w, pa[0]);
-            }
-          }
-        }
-        if (ncol < g.N && !(g.hd_part && g.hd_skip_store)) epilogue_chunk(e, ew, v, stage, lane, m0 + q * 32, ncol);
-      }
-      if (g.hd_part) {
-        const int row = m0 + q * 32 + lane;
-        if (row < g.M) {
-          const int slots = 2 * tiles_n;
-          float4* dstp = reinterpret_cast<float4*>(g.hd_part + ((size_t)row * slots + (2 * nb + half)) * 8);
-          dstp[0] = make_float4(pa[0], pa[1], pa[2], pa[3]);
-          dstp[1] = make_float4(pa[4], pa[5], pa[6], pa[7]);
-        }
+        if (n0 + c * 32 < g.N) epilogue_chunk(e, ew, v, stage, lane, m0 + q * 32, n0 + c * 32);
       }
     }
   }

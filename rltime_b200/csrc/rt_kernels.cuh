@@ -44,15 +44,6 @@ struct GemmArgs {
   float* ws;      // split-K workspace [splits][M][N] (raw partial sums)
   int kchunk;     // K range per z-slice
   int round_out;  // store the nearest TF32 value (the output is an operand of a tensor-core product)
-  // Fused dueling heads (persistent tcgen05 kernel only): C = relu(A.B + bias) is the hidden activation
-  // [h1 | v1] (hd_F columns each); while a 32-column chunk of a row is in registers the epilogue also forms its
-  // partial dot products with the out-layer rows (h1 half: hd_A actions) or the value-layer row (v1 half) and
-  // writes them to hd_part[row][slot][8] (slot = 2 * n-tile + epilogue-warp half).  k_heads_combine folds
-  // the slots in order.  hd_skip_store: do not write C at all (passes whose hidden activations nobody reads).
-  const float* hd_wout;
-  const float* hd_wv;
-  float* hd_part;
-  int hd_A, hd_F, hd_skip_store;
 };
 
 __device__ __forceinline__ float gemm_epilogue(const GemmArgs& g, int m, int n, float acc) {
@@ -742,41 +733,6 @@ __global__ void __launch_bounds__(256) k_heads_out(const float* __restrict__ h1,
     }
   }
   }
-}
-
-// Fold of the fused-heads partials (GemmArgs::hd_part): adv[a] = sum over the h1-half slots + b_out[a],
-// v = sum over the v1-half slots + b_v, q = v + adv - mean(adv)   (dqn.py:74-87).  One thread per row.
-__global__ void k_heads_combine(const float* __restrict__ part, int slots, int adv_slots,
-                                const float* __restrict__ bout, const float* __restrict__ bv,
-                                float* __restrict__ adv, float* __restrict__ vout, float* __restrict__ q,
-                                size_t rows, int A) {
-  const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  const float4* p = reinterpret_cast<const float4*>(part + r * slots * 8);
-  float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int s = 0; s < adv_slots; ++s) {
-    const float4 lo = p[2 * s], hi = p[2 * s + 1];
-    a8[0] += lo.x; a8[1] += lo.y; a8[2] += lo.z; a8[3] += lo.w;
-    a8[4] += hi.x; a8[5] += hi.y; a8[6] += hi.z; a8[7] += hi.w;
-  }
-  float v = 0.f;
-  for (int s = adv_slots; s < slots; ++s) v += p[2 * s].x;
-  v += bv[0];
-  float mean = 0.f;
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-    if (a < A) {
-      a8[a] += bout[a];
-      mean += a8[a];
-    }
-  mean /= (float)A;
-  vout[r] = v;
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-    if (a < A) {
-      adv[r * A + a] = a8[a];
-      q[r * A + a] = v + a8[a] - mean;
-    }
 }
 
 // Backward of the two small layers in ONE pass over the hidden activations (rows x C virtual

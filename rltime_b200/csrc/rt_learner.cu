@@ -175,8 +175,6 @@ struct rt_learner {
   float *tau = nullptr, *cf = nullptr, *phi = nullptr, *xq = nullptr, *h1 = nullptr, *v1 = nullptr,
         *adv = nullptr, *v = nullptr, *q = nullptr;
   float *tq = nullptr, *sq = nullptr, *targets = nullptr;
-  float* hpart[3] = {nullptr, nullptr, nullptr};   // fused-heads partial dot products per head set: [MQ][slots][8]
-  int heads_fused = 1;                             // RT_HEADS_FUSED=0: separate k_heads_out pass
   float *dtheta = nullptr, *row_loss = nullptr, *report = nullptr, *stats = nullptr;
   float *dh1 = nullptr, *dv1 = nullptr, *dxq = nullptr, *dphi = nullptr,
         *dfeatq = nullptr, *dgates = nullptr, *dh_carry = nullptr, *dc_carry = nullptr, *dfeat = nullptr;
@@ -504,9 +502,6 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   int rc;
   const long long total_tiles = (long long)tn * tm * splits;
   const bool persistent = cx.persistent && total_tiles > cx.num_sms;
-  if (g.hd_part)
-    RT_REQUIRE(BN == 256 && persistent && !A_MN && !B_MN && splits == 1 && g.hd_F % 256 == 0 && g.N == 2 * g.hd_F,
-               "fused heads need the persistent 128x256 tcgen05 configuration");
   const int ctas = (int)(total_tiles < cx.num_sms ? total_tiles : cx.num_sms);
 #define RT_TC_CASE(bn, am, bm)                                                                  \
   if (BN == bn && A_MN == am && B_MN == bm)                                                     \
@@ -772,7 +767,6 @@ int conv_dw_tc(rt_learner* h, GemmCtx& cx, cudaStream_t st, size_t i, const void
   else RT_TRY((launch_convdw_tc<128, 0>(ta, a, grid, st)));
   rtk::GemmArgs g = mk(nullptr, 0, 0, nullptr, 0, 0, dW, L.K, L.f, L.K, a.P);
   g.ws = cx.ws;
-
   launch_splitk_reduce(st, g, splits);
   RT_LAUNCH_CHECK();
   return RT_OK;
@@ -1118,25 +1112,15 @@ int trunk_forward(rt_learner* h, cudaStream_t st, const float* net, const StateV
 struct HeadSet {
   float *cf, *phi, *xq, *h1, *v1, *adv, *v, *q_out;
   GemmCtx* gx;
-  float* hpart;      // fused-heads partials (rt_learner::hpart)
-  bool keep_hidden;  // the hidden activations are read later (training pass: its backward)
 };
 HeadSet primary_set(rt_learner* h, float* q_out) {
-  return HeadSet{h->cf, h->phi, h->xq, h->h1, h->v1, h->adv, h->v, q_out, &h->gx, h->hpart[0], true};
+  return HeadSet{h->cf, h->phi, h->xq, h->h1, h->v1, h->adv, h->v, q_out, &h->gx};
 }
 HeadSet second_set(rt_learner* h, float* q_out) {
-  return HeadSet{h->cf2, h->phi2, h->xq2, h->h1b, h->v1b, h->adv2, h->vb2, q_out, &h->gx2, h->hpart[1], false};
+  return HeadSet{h->cf2, h->phi2, h->xq2, h->h1b, h->v1b, h->adv2, h->vb2, q_out, &h->gx2};
 }
 HeadSet third_set(rt_learner* h, float* q_out) {
-  return HeadSet{h->cf3, h->phi3, h->xq3, h->h1c, h->v1c, h->adv3, h->vb3, q_out, &h->gx3, h->hpart[2], false};
-}
-// The out / value layers + dueling combine ride in the epilogue of the fused hidden-layer GEMM when that GEMM
-// takes the persistent 128x256 tcgen05 configuration (same conditions as gemm_tc's tile choice).
-bool heads_fusable(const rt_learner* h, const HeadSet& hs, size_t MQ) {
-  const GemmCtx& cx = *hs.gx;
-  return h->heads_fused && cx.mode == 1 && h->fused_hidden && hs.hpart && h->F % 256 == 0 && h->A <= 8 &&
-         !cx.force_bn && cx.persistent && !cx.profile && h->D % 4 == 0 && cdiv(h->D, rttc::BLOCK_K) >= 8 &&
-         (long long)cdiv(MQ, rttc::BLOCK_M) * (2 * h->F / 256) > cx.num_sms;
+  return HeadSet{h->cf3, h->phi3, h->xq3, h->h1c, h->v1c, h->adv3, h->vb3, q_out, &h->gx3};
 }
 
 // phase 0: the whole pass; 1: only the quantile embedding phi = relu(cos(pi i tau) Wq + bq), which does not depend
@@ -1163,22 +1147,6 @@ int heads_forward(rt_learner* h, cudaStream_t st, const float* net, const float*
     xq = hs.xq;
   }
   const int ldh = h->ldh;
-  if (h->fused_hidden && heads_fusable(h, hs, MQ)) {
-    // hidden layer + out / value layers + dueling combine: the GEMM epilogue forms the per-row partial dot
-    // products with the out / value rows, k_heads_combine folds them; passes whose hidden activations nobody
-    // reads (target / selection) never write the 84 MB of [h1 | v1]
-    g = mk(xq, D, 0, net + h->o_fcw, D, 1, hs.h1, ldh, (int)MQ, 2 * F, D);
-    g.bias = net + h->o_fcb;
-    g.relu = 1;
-    g.hd_wout = net + h->o_outw; g.hd_wv = net + h->o_vw; g.hd_part = hs.hpart;
-    g.hd_A = A; g.hd_F = F; g.hd_skip_store = hs.keep_hidden ? 0 : 1;
-    RT_TRY(gemm(*hs.gx, st, g));
-    const int slots = 2 * (2 * F / 256);
-    rtk::k_heads_combine<<<cdiv(MQ, 128), 128, 0, st>>>(hs.hpart, slots, slots / 2, net + h->o_outb, net + h->o_vb,
-                                                       hs.adv, hs.v, hs.q_out, MQ, A);
-    RT_LAUNCH_CHECK();
-    return RT_OK;
-  }
   if (h->fused_hidden) {
     // [h1 | v1] = relu(xq . [Wfc ; Wvh]^T + [bfc | bvh]): one GEMM, the A operand is read once
     g = mk(xq, D, 0, net + h->o_fcw, D, 1, hs.h1, ldh, (int)MQ, 2 * F, D);
@@ -1859,9 +1827,6 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   }
   RT_TRY(dalloc(h, &h->adv3, MQ * A));
   RT_TRY(dalloc(h, &h->vb3, MQ));
-  if (h->fused_hidden && F % 256 == 0 && A <= 8)
-    for (int i = 0; i < 3; ++i) RT_TRY(dalloc(h, &h->hpart[i], MQ * (size_t)(2 * (2 * F / 256)) * 8));
-  if (const char* e = getenv("RT_HEADS_FUSED")) h->heads_fused = atoi(e);
   RT_TRY(dalloc(h, &h->q, MQ * A, "q"));
   RT_TRY(dalloc(h, &h->tq, MQ * A, "tq"));
   RT_TRY(dalloc(h, &h->sq, MQ * A, "sq"));
