@@ -257,6 +257,7 @@ struct rt_learner {
   // data parallelism inside the library (rt_comm_*): NCCL communicator + communication stream
   ncclComm_t comm = nullptr;
   int comm_rank = 0, comm_world = 1;
+  int reserve_sms = 0;               // SMs the persistent conv-backward kernels leave to NCCL (world > 1)
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_comm = nullptr;
 };
@@ -814,7 +815,10 @@ int conv_dx_tc(rt_learner* h, cudaStream_t st, const float* net, int i, const fl
   const CUtensorMap* tb = nullptr;
   RT_TRY(get_tmap(h->gx, h->conv_wt[i], a.Kc, (uint64_t)L.s * L.s * L.cin, a.Kc, rttc::BLOCK_K, BN, 0, &tb));
   const long long tiles = (long long)L.s * L.s * cdiv(a.Mc, rttc::BLOCK_M);
-  const int ctas = (int)(tiles < h->num_sms ? tiles : h->num_sms);
+  // data-parallel: this persistent kernel runs while NCCL reduces the non-conv gradient bucket; CTAs that hold
+  // every SM for the whole kernel would keep NCCL's CTAs waiting, so it leaves them room
+  const int avail = h->num_sms - h->reserve_sms;
+  const int ctas = (int)(tiles < avail ? tiles : avail);
   h->gx.tc_launches++;
   ProfScope ps(h->gx, st, 2.0 * rows * L.hout * L.wout * (double)L.f * L.K, 3, (long long)rows * L.hin * L.win, L.cin, (long long)L.f * L.k * L.k);
   const bool shallow = h->conv_shallow >= 2 && h->side_active;
@@ -2750,6 +2754,10 @@ extern "C" int rt_comm_init(rt_learner* h, const uint8_t* id128, int32_t rank, i
   }
   h->comm_rank = rank;
   h->comm_world = world;
+  if (world > 1) {
+    h->reserve_sms = max_ctas > 0 && max_ctas < 64 ? max_ctas : 16;
+    if (const char* e = getenv("RT_DP_RESERVE_SMS")) h->reserve_sms = atoi(e);
+  }
   int lo = 0, hi = 0;
   RT_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   RT_CUDA(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, lo));
