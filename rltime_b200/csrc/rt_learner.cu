@@ -2758,9 +2758,13 @@ extern "C" int rt_comm_init(rt_learner* h, const uint8_t* id128, int32_t rank, i
     h->reserve_sms = max_ctas > 0 && max_ctas < 64 ? max_ctas : 16;
     if (const char* e = getenv("RT_DP_RESERVE_SMS")) h->reserve_sms = atoi(e);
   }
+  // highest priority: NCCL's few CTAs must all become resident to make progress, and they compete with the
+  // conv backward's CTAs for every slot that frees up (RT_DP_COMM_PRIO=0: lowest priority)
   int lo = 0, hi = 0;
   RT_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  RT_CUDA(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, lo));
+  int prio = hi;
+  if (const char* e = getenv("RT_DP_COMM_PRIO")) prio = atoi(e) ? hi : lo;
+  RT_CUDA(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, prio));
   RT_CUDA(cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
   return RT_OK;
 }
