@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt; nproc >> gpurun_out/smi.txt
 echo "=== pytest gpu"
-timeout -k 10 1200 python -m pytest tests/ -q -m gpu --timeout 300 2>&1 | tail -30 | cut -c1-300 | tee gpurun_out/pytest_gpu.log
+timeout -k 10 900 python -m pytest tests/ -q -m gpu --timeout 300 2>&1 | tail -30 | cut -c1-300 | tee gpurun_out/pytest_gpu.log
 echo "=== smoke"
 timeout 400 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/smoke.log
 echo "=== bench (full line)"
@@ -27,18 +27,20 @@ tail -2 gpurun_out/bench_reference.err; cut -c1-300 gpurun_out/bench_reference.j
 echo "=== kernel timeline"
 timeout -k 10 300 python scripts/kernel_trace.py --size 65536 --steps 5 --timeline > gpurun_out/kernel_timeline.txt 2>&1
 grep "updates " gpurun_out/kernel_timeline.txt
+echo "=== per-GEMM device times"
+timeout -k 10 200 python scripts/gemm_profile.py > gpurun_out/gemm_profile.txt 2>&1; tail -1 gpurun_out/gemm_profile.txt | cut -c1-200
 echo "=== ncu launch list"
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 3000 --csv \
-  --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --size 65536 --no-cpu-baseline --no-side-lines > gpurun_out/ncu_bench.log 2>&1
+  --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --long-steps 2 --size 65536 --no-cpu-baseline --no-side-lines > gpurun_out/ncu_bench.log 2>&1
 if [ $(wc -l < gpurun_out/launches.csv) -lt 500 ]; then
   echo "few kernels seen through the graphs: launch list with RT_GRAPHS=0"
   RT_GRAPHS=0 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 3000 --csv \
-    --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --size 65536 --no-cpu-baseline --no-side-lines > gpurun_out/ncu_bench.log 2>&1
+    --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --long-steps 2 --size 65536 --no-cpu-baseline --no-side-lines > gpurun_out/ncu_bench.log 2>&1
 fi
 python scripts/summarize_launches.py gpurun_out/launches.csv | tee gpurun_out/launch_summary.txt | head -25
 cap() {  # name regex skip count
-  timeout -k 10 420 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c $4 -f -o gpurun_out/prof_$1 \
-    python bench.py --steps 1 --warmup 3 --size 65536 --no-cpu-baseline --no-side-lines > gpurun_out/ncu_full_$1.log 2>&1
+  timeout -k 10 300 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:$2 -s $3 -c $4 -f -o gpurun_out/prof_$1 \
+    python bench.py --steps 1 --warmup 3 --long-steps 1 --size 65536 --no-cpu-baseline --no-side-lines > gpurun_out/ncu_full_$1.log 2>&1
   ncu -i gpurun_out/prof_$1.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_pick.py > gpurun_out/prof_$1_summary.txt
   grep -i "kernel name\|gpu__time_duration\|dram__bytes\|tensor_cycles\|lts__throughput\|dram_throughput" gpurun_out/prof_$1_summary.txt | cut -c1-150
 }
@@ -49,5 +51,3 @@ cap gather k_gather 3 1
 echo "=== ncu full: LSTM recurrence (mma.sync) and one-launch BPTT"
 cap lstm k_lstm_seq_mma 1 1
 cap bptt k_lstm_bptt_p 1 1
-echo "=== ncu full: paired conv1"
-cap conv1 "k_conv_tc_pILi64ELi0ELi6" 1 1
