@@ -152,9 +152,9 @@ class DevicePolicy:
             obs = obs[0]
         obs = np.ascontiguousarray(obs, dtype=L.obs_dtype)
         E = obs.shape[0]
-        hx_in = self._pinned("x", obs.shape, torch.from_numpy(obs[:0]).dtype)
-        hx_in.numpy()[...] = obs
-        x = hx_in.to(dev, non_blocking=True)
+        x_host = self._pinned("x", obs.shape, torch.from_numpy(obs[:0]).dtype)
+        x_host.numpy()[...] = obs
+        x = x_host.to(dev, non_blocking=True)    # the stream is synchronised before this call returns
         null = C.c_void_p()
         q = torch.empty(E, self.num_actions, dtype=torch.float32, device=dev)
         ex_p = null
