@@ -842,9 +842,12 @@ bool cnn_all_implicit(const rt_learner* h) {
 }
 int cnn_forward(rt_learner* h, cudaStream_t st, const float* net, const uint8_t* x, int rows,
                 const float* xf_pre = nullptr, bool second = false, int first_layer = 0) {
+  // a pass that converts its own frames (burn-in, the non-shared target / training passes, acting) uses the
+  // DEFAULT frame buffer: h->xf may be a batch slot's private buffer holding frames that rt_learner_prefetch
+  // already converted for the training window of this very update
   if (!xf_pre)
-    RT_TRY(launch_frames_to_nhwc(st, x, h->xf, rows, h->md.in_c, h->md.in_h, h->md.in_w, (float)(1.0 / 255.0), h->rn));
-  const float* xf = xf_pre ? xf_pre : h->xf;
+    RT_TRY(launch_frames_to_nhwc(st, x, h->xf0, rows, h->md.in_c, h->md.in_h, h->md.in_w, (float)(1.0 / 255.0), h->rn));
+  const float* xf = xf_pre ? xf_pre : h->xf0;
   {
     bool all = true;
     for (size_t i = 0; i < h->conv.size(); ++i)

@@ -403,13 +403,15 @@ class IQNTrainer:
             if warming_up:
                 continue
             self._start_timer("train")
-            batch = getattr(hist, "last_batch", None)
-            if batch is None or not hasattr(hist, "update_losses_device"):
-                batch = self._host_batch(td, n_target)      # host-side buffer (online history)
-            elif self._assert_nsteps:
-                pass    # replay buffers guarantee the fixed n-step (multi_step_trainer.py:299-303)
-            if hasattr(hist, "update_losses_device"):
+            device_hist = hasattr(hist, "last_batch") and hasattr(hist, "_stream")
+            if device_hist:
+                # replay buffers guarantee the fixed n-step that rnn_bootstrap needs (multi_step_trainer.py:299-303)
+                batch = hist.last_batch
                 learner.prefetch(batch, hist._stream())      # frame conversion on the replay stream
+            else:
+                assert not rnn_bootstrap or np.all(np.asarray(td["nsteps"]) == n_target), \
+                    "rnn_bootstrap is only supported with history buffers which guarantee the fixed target nstep"
+                batch = self._host_batch(td, n_target)      # host-side buffer (online history)
             learner.step(batch, None if self.tau_source is None else self.tau_source(self.updates))
             if hasattr(hist, "update_losses_device"):
                 hist.update_losses_device(learner.td_abs(), ready=learner.wait_loss)

@@ -201,6 +201,76 @@ def test_acting_inference_matches_oracle():
 
 
 @pytest.mark.gpu
+def test_iqn_trainer_uniform_device_replay():
+    """history_mode "replay" (the shipped atari_iqn_lstm.json uses the uniform buffer): the trainer takes the
+    raw device batch of the uniform device buffer, which has no priority write-back."""
+    from rltime_b200.training import IQNTrainer
+    from tests.fake_actor import FakeVecActor
+    actors = FakeVecActor(num_envs=4, num_actions=4, seed=6)
+    tr = IQNTrainer(_Logger(), actors, MODEL, {"dueling": True, "num_sampling_quantiles": 8, "embedding_dim": 16})
+    tr.train(total_steps=700, log_freq=350, target_update_freq=200, clip_rewards=True, gamma=0.99,
+             nstep_train=4, nstep_target=2, lr=3e-4, mbatch_size=4, warmup_steps=200, rnn_bootstrap=True,
+             double_q=True, clip_grad=40.0, adam_epsilon=1e-5,
+             history_mode={"type": "replay", "args": {"size": 600, "train_frequency": 4, "max_envs": 4}})
+    assert tr.steps >= 700 and tr.updates > 50
+    st = tr.learner.stats()
+    assert np.isfinite(st["qloss"]) and st["grad_norm"] > 0
+
+
+@pytest.mark.gpu
+def test_frame_prefetch_with_burn_in_is_bit_identical():
+    """rt_learner_prefetch converts the training window's frames into the batch slot's private buffer on the
+    replay stream; the burn-in passes of the same update convert THEIR frames into the default buffer.  With and
+    without the prefetch the trained weights and the |td| signal must not differ by a bit."""
+    import random
+    import torch
+    from rltime_b200.history import DevicePrioritizedReplayHistoryBuffer
+    from rltime_b200.init import init_params
+    from rltime_b200.learner import DeviceLearner
+    E, T, P, n, B, A, U = 8, 6, 3, 2, 8, 4, 64
+    dev = torch.device("cuda", 0)
+
+    def run(prefetch):
+        random.seed(5)
+        rs = np.random.RandomState(3)
+        hist = DevicePrioritizedReplayHistoryBuffer(
+            size=4096, train_frequency=None, alpha=0.9, beta=0.6, nstep_target=n, nstep_train=T,
+            prefix_steps=P, gamma=0.99, max_envs=E, device=dev)
+        L = DeviceLearner((4, 84, 84), [(32, 8, 4), (64, 4, 2)], U, 64, A, 8, 16, True, mbatch=B,
+                          nstep_train=T, burn_in=P, nstep_target=n, double_q=True, rnn_bootstrap=True,
+                          clip_grad=40.0, seed=11, device=dev)
+        L.load_state_dict(init_params(L.param_info, U, seed=1), 0)
+        L.load_state_dict(init_params(L.param_info, U, seed=2), 1)
+        m = 200 * E
+        env = np.arange(m) % E
+        hist.update_arrays(env, np.sign(rs.randn(m)), (rs.rand(m) < 0.02).astype(np.uint8),
+                           [rs.randint(0, 255, (m, 4, 84, 84)).astype(np.uint8),
+                            rs.randn(m, U).astype(np.float32), rs.randn(m, U).astype(np.float32),
+                            np.zeros(m, np.float32)],
+                           [rs.randint(0, A, m).astype(np.int64), rs.randn(m, A).astype(np.float32)])
+        tds = []
+        for it in range(12):
+            assert hist.draw(B, 0.0) is not None
+            if prefetch:
+                L.prefetch(hist.last_batch, hist._stream())
+            L.step(hist.last_batch)
+            hist.update_losses_device(L.td_abs(), ready=L.wait_loss)
+            tds.append(L.td_abs().clone())
+        torch.cuda.synchronize()
+        w = {k: v.clone() for k, v in L.state_dict(0).items()}
+        tds = [t.cpu().numpy() for t in tds]
+        L.close()
+        hist.close()
+        return w, tds
+    w0, t0 = run(False)
+    w1, t1 = run(True)
+    for a, b in zip(t0, t1):
+        np.testing.assert_array_equal(a, b)
+    for k in w0:
+        np.testing.assert_array_equal(w0[k].numpy(), w1[k].numpy(), err_msg=k)
+
+
+@pytest.mark.gpu
 def test_pipelined_update_loop_is_bit_identical_to_the_serialised_one():
     """The priority write-back / next draw overlap the backward pass (own replay stream +
     rt_learner_wait_loss) and the update is replayed from CUDA graphs: sampled indices, |td| and
