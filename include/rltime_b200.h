@@ -79,6 +79,17 @@ int rt_replay_append(rt_replay* h, int64_t m, const int32_t* env, const int64_t*
                      const void* const* state_fields, const void* const* po_fields,
                      int32_t fields_on_device, void* stream);
 
+/* Train quota of the replay buffers (replay_history.py:62-75,173-184), for hosts that do not keep it themselves:
+ * every appended transition adds train_frequency to the quota, every get_train_data takes mbatch * nstep_train.
+ *   rt_replay_needed_feed  -> -1: the reference's None (train first, do not act); 0: take whatever is ready
+ *                              (no train_frequency); > 0: samples wanted (at least num_envs)
+ *   rt_replay_consume_quota: call once per get_train_data, BEFORE the draw (the reference subtracts even when it then
+ *                              returns None); RT_ERR_STATE when the +-100 x mbatch x nstep_train sanity bound breaks. */
+int rt_replay_set_train_frequency(rt_replay* h, double train_frequency);
+int64_t rt_replay_needed_feed(const rt_replay* h, int32_t mbatch, int32_t num_envs);
+int rt_replay_consume_quota(rt_replay* h, int32_t mbatch);
+double rt_replay_train_quota(const rt_replay* h);
+
 /* Bookkeeping queries (len(linear_history); active sequences = len(_index_data) -
  * len(_free_indexes), prioritized_replay_history.py:291; uniform `total_available`,
  * replay_history.py:98-107). */

@@ -93,6 +93,10 @@ SIGNATURES = {
     "rt_replay_create": (C.c_int, [C.POINTER(ReplayConfig), C.POINTER(_VP)]),
     "rt_replay_destroy": (None, [_VP]),
     "rt_replay_append": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
+    "rt_replay_set_train_frequency": (C.c_int, [_VP, C.c_double]),
+    "rt_replay_needed_feed": (C.c_int64, [_VP, C.c_int32, C.c_int32]),
+    "rt_replay_consume_quota": (C.c_int, [_VP, C.c_int32]),
+    "rt_replay_train_quota": (C.c_double, [_VP]),
     "rt_replay_len": (C.c_int64, [_VP]),
     "rt_replay_active_sequences": (C.c_int64, [_VP]),
     "rt_replay_uniform_available": (C.c_int64, [_VP]),

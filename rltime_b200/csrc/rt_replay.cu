@@ -615,6 +615,7 @@ struct rt_tree {
 
 struct rt_replay {
   rt_replay_config cfg;
+  double train_frequency = 0.0, train_quota = 0.0;   // replay_history.py:62-75,173-184 (0 = no quota)
   int64_t N = 0, NS = 0;
   int T = 0, P = 0, n = 0, S = 0, gap = 1;
   bool per = false;
@@ -1106,6 +1107,7 @@ int rt_replay_append(rt_replay* h, int64_t m, const int32_t* env, const int64_t*
              (long long)m, (long long)h->N);
   RT_CUDA(cudaSetDevice(h->cfg.device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->train_frequency > 0) h->train_quota += h->train_frequency * (double)m;   // replay_history.py:91
   std::vector<int32_t> slots((size_t)m);
   for (int64_t i = 0; i < m; ++i) {
     int e = env[i];
@@ -1182,6 +1184,33 @@ int rt_replay_append(rt_replay* h, int64_t m, const int32_t* env, const int64_t*
   }
   return flush_updates(h, st);
 }
+
+int rt_replay_set_train_frequency(rt_replay* h, double train_frequency) {
+  RT_REQUIRE(h, "null argument");
+  h->train_frequency = train_frequency > 0 ? train_frequency : 0.0;
+  return RT_OK;
+}
+
+int64_t rt_replay_needed_feed(const rt_replay* h, int32_t mbatch, int32_t num_envs) {
+  (void)mbatch;
+  if (!h || h->train_frequency <= 0) return 0;            // take whatever is ready
+  if (h->train_quota > 0) return -1;                       // None: do not act, train first
+  int64_t want = (int64_t)(-h->train_quota / h->train_frequency);
+  return want > num_envs ? want : num_envs;
+}
+
+int rt_replay_consume_quota(rt_replay* h, int32_t mbatch) {
+  RT_REQUIRE(h && mbatch >= 1, "bad argument");
+  if (h->train_frequency <= 0) return RT_OK;
+  const double step = (double)mbatch * h->T;
+  h->train_quota -= step;
+  if (!(h->train_quota < 100.0 * step && h->train_quota > -100.0 * step))
+    return rt::fail(RT_ERR_STATE, "train quota %.1f outside +-100 x mbatch x nstep_train (replay_history.py:179-181)",
+                    h->train_quota);
+  return RT_OK;
+}
+
+double rt_replay_train_quota(const rt_replay* h) { return h ? h->train_quota : 0.0; }
 
 int64_t rt_replay_len(const rt_replay* h) { return h ? h->fifo_len : 0; }
 int64_t rt_replay_active_sequences(const rt_replay* h) { return h ? h->active : 0; }

@@ -123,7 +123,7 @@ class DeviceReplayHistoryBuffer:
         self._lib = _lib.load()
         self.size = int(size)
         self.train_frequency = train_frequency
-        self.train_quota = 0
+        self._pre_consumed = []
         self.nstep_target = int(nstep_target)
         self.nstep_train = int(nstep_train)
         self.prefix_steps = int(prefix_steps)
@@ -211,6 +211,12 @@ class DeviceReplayHistoryBuffer:
         h = C.c_void_p()
         _lib.check(self._lib.rt_replay_create(C.byref(cfg), C.byref(h)))
         self._h = h
+        # the train quota (replay_history.py:62-75,173-184) is kept by the library: rt_replay_append adds,
+        # rt_replay_consume_quota takes, rt_replay_needed_feed answers
+        _lib.check(self._lib.rt_replay_set_train_frequency(self._h, float(self.train_frequency or 0)))
+        for mb in self._pre_consumed:     # get_train_data calls made before the first sample arrived
+            _lib.check(self._lib.rt_replay_consume_quota(self._h, mb))
+        self._pre_consumed = []
 
     def close(self):
         if self._h is not None:
@@ -330,8 +336,6 @@ class DeviceReplayHistoryBuffer:
             self._h, m, env.ctypes.data, env_ids.ctypes.data, reward.ctypes.data,
             done.ctypes.data, C.cast(sp, C.c_void_p), C.cast(pp, C.c_void_p),
             1 if on_device else 0, self._stream()))
-        if self.train_frequency:
-            self.train_quota += self.train_frequency * m
         if on_device:
             # the copies are stream-ordered; keep the sources alive until they ran
             self._own.synchronize()
@@ -349,16 +353,23 @@ class DeviceReplayHistoryBuffer:
         # replay_history.py:62-75
         if not self.train_frequency:
             return 0
-        if self.train_quota > 0:
-            return None
-        return max(int(-self.train_quota / self.train_frequency), num_envs)
+        if self._h is None:              # nothing fed yet: quota = -(what the early get_train_data calls took)
+            taken = sum(self._pre_consumed) * self.nstep_train
+            return max(int(taken / self.train_frequency), num_envs)
+        n = self._lib.rt_replay_needed_feed(self._h, mbatch_size, num_envs)
+        return None if n < 0 else int(n)
+
+    @property
+    def train_quota(self):
+        return 0 if self._h is None else self._lib.rt_replay_train_quota(self._h)
 
     def get_train_data(self, mbatch_size, train_progress=None):
         # replay_history.py:173-184
         if self.train_frequency:
-            self.train_quota -= mbatch_size * self.nstep_train
-            assert self.train_quota < 100 * mbatch_size * self.nstep_train
-            assert self.train_quota > -100 * mbatch_size * self.nstep_train
+            if self._h is None:
+                self._pre_consumed.append(int(mbatch_size))
+            else:
+                _lib.check(self._lib.rt_replay_consume_quota(self._h, mbatch_size))
         return self._get_train_data(mbatch_size, train_progress)
 
     def draw(self, mbatch_size, train_progress=None):
