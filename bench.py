@@ -477,7 +477,7 @@ def run_gpu(args):
         pol = DevicePolicy(learner, cfg["A"])
         obs = rs.randint(0, 255, (E,) + cfg["frame"]).astype(np.uint8)
         state = pol.make_input_state(obs, np.ones(E, dtype=bool))
-        for _ in range(5):
+        for _ in range(8):      # both alternating state buffers reach their CUDA graph
             pol.actor_predict(state)
             state = pol.make_input_state(obs, np.zeros(E, dtype=bool))
         torch.cuda.synchronize(device)

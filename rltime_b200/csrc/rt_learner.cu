@@ -220,6 +220,15 @@ struct rt_learner {
   };
   std::vector<StepGraphs> graphs;
   int graphs_enabled = 1;
+  // acting step (rt_learner_act) replayed from a graph once the same buffers were seen three times in a row
+  struct ActGraph {
+    const void* key[10] = {};
+    cudaGraphExec_t g = nullptr;
+    long long n = 0;
+    int seen = 0;
+  };
+  std::vector<ActGraph> act_graphs;
+  int act_graphs_enabled = 1;       // RT_ACT_GRAPH=0: issue the ~20 launches of an acting step one by one
   long long steps_done = 0;
   cudaStream_t own = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1859,6 +1868,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
     if (const char* e = getenv("RT_PHI_EARLY")) h->phi_early = atoi(e);
   }
   if (const char* e = getenv("RT_GRAPHS")) h->graphs_enabled = atoi(e);
+  if (const char* e = getenv("RT_ACT_GRAPH")) h->act_graphs_enabled = atoi(e);
   if (const char* e = getenv("RT_OVERLAP_BWD")) h->overlap_bwd = atoi(e);
   if (const char* e = getenv("RT_DP_SPLIT")) h->dp_split = atoi(e);
   if (const char* e = getenv("RT_OVERLAP_FWD")) h->overlap_fwd = atoi(e);
@@ -1956,6 +1966,8 @@ void rt_learner_destroy(rt_learner* h) {
     if (g.bwd) cudaGraphExecDestroy(g.bwd);
     if (g.bwd2) cudaGraphExecDestroy(g.bwd2);
   }
+  for (auto& g : h->act_graphs)
+    if (g.g) cudaGraphExecDestroy(g.g);
   if (h->ev_late) cudaEventDestroy(h->ev_late);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -2469,7 +2481,7 @@ int learner_step_impl(rt_learner* h, const rt_batch* b, const rt_learner_io* io,
   // ---- run: replayed from CUDA graphs once the handle is warm (every lazy allocation / kernel
   // attribute of these shapes has happened), keyed by the batch's device pointers (the replay
   // buffer rotates three batch slots)
-  const bool want_graph = forked && h->steps_done >= 2 && !h->gx.profile && !h->lstm_dbg;
+  const bool want_graph = h->graphs_enabled > 0 && h->steps_done >= 2 && !h->gx.profile && !h->lstm_dbg;
   rt_learner::StepGraphs* sg = nullptr;
   if (want_graph) {
     const void* key[12] = {all_x, all_hx, all_cx, all_init, b->returns, b->nsteps, b->target_masks,
@@ -2600,24 +2612,61 @@ int rt_learner_act(rt_learner* h, int32_t E, const void* x, const float* extra, 
   sv.hx = const_cast<float*>(hx);
   sv.cx = const_cast<float*>(cx);
   sv.initials = initials;
-  const float* feat = nullptr;
-  RT_TRY(trunk_forward(h, st, h->pr[0], sv, E, 1, &feat));
-  size_t nq = (size_t)E * h->Nq;
-  if (taus_host) {
-    RT_CUDA(cudaMemcpyAsync(h->tau_stage, taus_host, nq * sizeof(float), cudaMemcpyHostToDevice, st));
-  } else {
-    k_uniform<<<cdiv(nq, 256), 256, 0, st>>>(h->tau_stage, nq, h->td.seed ^ 0xA5A5A5A5ULL, h->rng_counter);
+  // quantile fractions first: they are the only per-call input that is not behind a stable pointer
+  const size_t nq = (size_t)E * h->Nq;
+  if (!h->dqn) {
+    if (taus_host) {
+      RT_CUDA(cudaMemcpyAsync(h->tau_stage, taus_host, nq * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+      k_uniform<<<cdiv(nq, 256), 256, 0, st>>>(h->tau_stage, nq, h->td.seed ^ 0xA5A5A5A5ULL, h->rng_counter);
+      RT_LAUNCH_CHECK();
+      h->rng_counter += nq;
+    }
+  }
+  auto body = [&]() -> int {
+    const float* feat = nullptr;
+    RT_TRY(trunk_forward(h, st, h->pr[0], sv, E, 1, &feat));
+    RT_TRY(heads_forward(h, st, h->pr[0], feat, E, h->tau_stage));
+    rtk::k_quantile_mean<<<cdiv((size_t)E * h->A, 128), 128, 0, st>>>(h->q, qvalues, E, h->Nq, h->A);
     RT_LAUNCH_CHECK();
-    h->rng_counter += nq;
+    if (h->U) {
+      RT_CUDA(cudaMemcpyAsync(h_out, h->h_all, (size_t)E * h->U * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      RT_CUDA(cudaMemcpyAsync(c_out, h->c_all, (size_t)E * h->U * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    return RT_OK;
+  };
+  // A host that acts from persistent buffers (DevicePolicy: two alternating state buffers) gets the step
+  // replayed from a CUDA graph: the launches are ~5 us of GPU work each, issued one by one they are bound
+  // by the launch path.  Graphs cannot be captured on the legacy default stream.
+  rt_learner::ActGraph* ag = nullptr;
+  if (h->act_graphs_enabled > 0 && st != nullptr && st != cudaStreamLegacy && !h->gx.profile && !h->lstm_dbg) {
+    const void* key[10] = {(const void*)(intptr_t)E, x, extra, hx, cx, initials, qvalues, h_out, c_out, h->xf};
+    for (auto& g : h->act_graphs)
+      if (memcmp(g.key, key, sizeof(key)) == 0) ag = &g;
+    if (!ag) {
+      if (h->act_graphs.size() >= 4) {
+        if (h->act_graphs[0].g) cudaGraphExecDestroy(h->act_graphs[0].g);
+        h->act_graphs.erase(h->act_graphs.begin());
+      }
+      h->act_graphs.emplace_back();
+      ag = &h->act_graphs.back();
+      memcpy(ag->key, key, sizeof(key));
+    }
+    if (!ag->g && ++ag->seen >= 3) {
+      // every lazy allocation / kernel attribute of these shapes happened in the two calls before
+      if (capture_graph(st, body, &ag->g, &ag->n) != RT_OK) {
+        ag->g = nullptr;
+        h->act_graphs_enabled = -1;
+        fprintf(stderr, "rltime_b200: CUDA-graph capture of the acting step disabled: %s\n", rt::last_error().c_str());
+      }
+    }
   }
-  RT_TRY(heads_forward(h, st, h->pr[0], feat, E, h->tau_stage));
-  rtk::k_quantile_mean<<<cdiv((size_t)E * h->A, 128), 128, 0, st>>>(h->q, qvalues, E, h->Nq, h->A);
-  RT_LAUNCH_CHECK();
-  if (h->U) {
-    RT_CUDA(cudaMemcpyAsync(h_out, h->h_all, (size_t)E * h->U * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    RT_CUDA(cudaMemcpyAsync(c_out, h->c_all, (size_t)E * h->U * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (ag && ag->g) {
+    RT_CUDA(cudaGraphLaunch(ag->g, st));
+    rt::launch_counter() += ag->n;
+    return RT_OK;
   }
-  return RT_OK;
+  return body();
 }
 
 int rt_learner_wait_late_grads(rt_learner* h, void* stream, int64_t* first, int64_t* count) {

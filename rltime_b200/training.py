@@ -97,9 +97,9 @@ class DevicePolicy:
     def __init__(self, learner, num_actions):
         self.learner = learner
         self.num_actions = num_actions
-        self._dev_state = None    # (h, c) device tensors produced by the last actor_predict
+        self._dev_state = None    # output slot holding the (h, c) produced by the last actor_predict
         self._host_state = None   # their host copies (what make_input_state hands out)
-        self._stage = {}
+        self._buf_key = None
 
     def is_recurrent(self):
         return self.learner.U > 0
@@ -132,70 +132,86 @@ class DevicePolicy:
             state["layer%d_state" % li] = {"hx": self._handed_hx, "cx": cx * mask, "initials": initials}
         return state
 
-    def _pinned(self, key, shape, dtype):
+    def _buffers(self, E, obs_shape, obs_dtype):
+        """Persistent staging for E envs: ONE pinned input block [obs | initials | extra | taus] with its device
+        twin and two alternating device output blocks [q | h | c] (the previous call's block is this call's
+        recurrent input), so that every pointer rt_learner_act sees repeats and the step replays from a graph."""
         import torch
-        t = self._stage.get(key)
-        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-            t = self._stage[key] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
-        return t
+        key = (E, tuple(obs_shape), np.dtype(obs_dtype).str)
+        if self._buf_key == key:
+            return
+        L = self.learner
+        up = lambda n: (int(n) + 255) // 256 * 256
+        obs_bytes = int(np.prod(obs_shape)) * np.dtype(obs_dtype).itemsize
+        self._off = off = {"ini": up(obs_bytes)}
+        off["extra"] = off["ini"] + up(4 * E)
+        off["tau"] = off["extra"] + up(4 * E * L.X)
+        off["end"] = off["tau"] + up(4 * E * max(L.Nq, 1))
+        self._in_host = torch.empty(off["end"], dtype=torch.uint8).pin_memory()
+        self._in_dev = torch.empty(off["end"], dtype=torch.uint8, device=L.device)
+        host = self._in_host.numpy()
+        self._x_np = host[:obs_bytes].view(obs_dtype).reshape(obs_shape)
+        self._ini_np = host[off["ini"]:off["ini"] + 4 * E].view(np.float32)
+        self._extra_np = host[off["extra"]:off["extra"] + 4 * E * L.X].view(np.float32).reshape(E, L.X)
+        self._tau_np = host[off["tau"]:off["tau"] + 4 * E * max(L.Nq, 1)].view(np.float32)
+        A, U = self.num_actions, L.U
+        self._out_dev = [torch.zeros(E * A + 2 * E * U, dtype=torch.float32, device=L.device) for _ in range(2)]
+        self._out_host = torch.empty(E * A + 2 * E * U, dtype=torch.float32).pin_memory()
+        self._slot = 0
+        self._dev_state = None
+        self._buf_key = key
 
     def actor_predict(self, state, timesteps=1, for_eval=False, taus=None):
         """DQNPolicy.actor_predict (policies/torch/dqn.py:132-148) for one time-step."""
         import torch
         assert timesteps == 1, "acting runs one time-step at a time"
         L = self.learner
-        dev = L.device
         obs = state["x"]
         extra = None
         if isinstance(obs, (tuple, list)):
             extra = np.concatenate([np.asarray(e, dtype=np.float32).reshape(len(e), -1) for e in obs[1:]], axis=1)
             obs = obs[0]
-        obs = np.ascontiguousarray(obs, dtype=L.obs_dtype)
-        E = obs.shape[0]
-        x_host = self._pinned("x", obs.shape, torch.from_numpy(obs[:0]).dtype)
-        x_host.numpy()[...] = obs
-        x = x_host.to(dev, non_blocking=True)    # the stream is synchronised before this call returns
+        obs = np.asarray(obs)
+        E, A, U = obs.shape[0], self.num_actions, L.U
+        self._buffers(E, obs.shape, L.obs_dtype)
+        off, base = self._off, self._in_dev.data_ptr()
+        self._x_np[...] = obs
         null = C.c_void_p()
-        q = torch.empty(E, self.num_actions, dtype=torch.float32, device=dev)
         ex_p = null
         if L.X:
             assert extra is not None and extra.shape[1] == L.X, "tuple observation with %d extra features expected" % L.X
-            ex = torch.from_numpy(np.ascontiguousarray(extra)).to(dev)
-            ex_p = C.c_void_p(ex.data_ptr())
-        if L.U:
+            self._extra_np[...] = extra
+            ex_p = C.c_void_p(base + off["extra"])
+        out, prev = self._out_dev[self._slot], self._out_dev[1 - self._slot]
+        if U:
             ls = state["layer%d_state" % L.lstm_module]
-            ini = torch.from_numpy(np.ascontiguousarray(ls["initials"], dtype=np.float32)).to(dev)
-            if self._dev_state is not None and self._dev_state[0].shape[0] == E and \
-                    ls["hx"] is getattr(self, "_handed_hx", None):
-                # the state this policy produced itself is still on the device; the LSTM kernel applies
-                # the episode-start mask (same values as the host-side masking of make_input_state)
-                hx, cx = self._dev_state
-            else:
-                hx = torch.from_numpy(np.ascontiguousarray(ls["hx"], dtype=np.float32)).to(dev)
-                cx = torch.from_numpy(np.ascontiguousarray(ls["cx"], dtype=np.float32)).to(dev)
-            h_out, c_out = torch.empty(E, L.U, device=dev), torch.empty(E, L.U, device=dev)
-            ptrs = [C.c_void_p(x.data_ptr()), ex_p] + [C.c_void_p(t.data_ptr()) for t in (hx, cx, ini)]
-            outs = [C.c_void_p(t.data_ptr()) for t in (q, h_out, c_out)]
+            self._ini_np[...] = np.asarray(ls["initials"], dtype=np.float32)
+            if not (self._dev_state == 1 - self._slot and ls["hx"] is getattr(self, "_handed_hx", None)):
+                # a state this policy did not produce itself: upload it where the previous call's would be.
+                # (Its own state is still on the device; the LSTM kernel applies the episode-start mask --
+                # the same values as the host-side masking of make_input_state.)
+                hc = np.stack([np.asarray(ls["hx"], dtype=np.float32), np.asarray(ls["cx"], dtype=np.float32)])
+                prev[E * A:].copy_(torch.from_numpy(hc.reshape(-1)))
+            f4 = lambda t, o: C.c_void_p(t.data_ptr() + 4 * o)
+            ptrs = [C.c_void_p(base), ex_p, f4(prev, E * A), f4(prev, E * A + E * U), C.c_void_p(base + off["ini"])]
+            outs = [f4(out, 0), f4(out, E * A), f4(out, E * A + E * U)]
         else:
-            ptrs = [C.c_void_p(x.data_ptr()), ex_p, null, null, null]
-            outs = [C.c_void_p(q.data_ptr()), null, null]
+            ptrs = [C.c_void_p(base), ex_p, null, null, null]
+            outs = [C.c_void_p(out.data_ptr()), null, null]
         tp = null
         if taus is not None:
-            taus = np.ascontiguousarray(taus, dtype=np.float32)
-            tp = C.c_void_p(taus.ctypes.data)
+            self._tau_np[...] = np.asarray(taus, dtype=np.float32).reshape(-1)
+            tp = C.c_void_p(self._in_host.data_ptr() + off["tau"])     # pinned: the library's own copy stays async
+        self._in_dev[:off["tau"]].copy_(self._in_host[:off["tau"]], non_blocking=True)
         _lib.check(L._lib.rt_learner_act(L._h, E, *ptrs, tp, *outs, L._stream()))
-        if L.U:
-            self._dev_state = (h_out, c_out)
-            host = self._pinned("hc", (2, E, L.U), torch.float32)
-            host[0].copy_(h_out, non_blocking=True)
-            host[1].copy_(c_out, non_blocking=True)
-        qh = self._pinned("q", (E, self.num_actions), torch.float32)
-        qh.copy_(q, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        if L.U:
-            hc = host.numpy().copy()
-            self._host_state = (hc[0], hc[1])
-        qv = qh.numpy().copy()
+        self._out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(L.device).synchronize()
+        res = self._out_host.numpy().copy()
+        if U:
+            self._dev_state = self._slot
+            self._slot = 1 - self._slot
+            self._host_state = (res[E * A:E * A + E * U].reshape(E, U), res[E * A + E * U:].reshape(E, U))
+        qv = res[:E * A].reshape(E, A)
         return {"actions": np.argmax(qv, axis=1), "qvalues": qv}
 
 

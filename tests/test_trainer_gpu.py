@@ -161,8 +161,9 @@ def test_iqn_trainer_tuple_observation_rnn_steps_async_flag():
 def test_acting_inference_matches_oracle():
     """rt_learner_act through DevicePolicy.actor_predict against the oracle's IQNPolicy
     forward at timesteps = 1 with injected quantile fractions: q-values within 1e-4, identical greedy
-    actions, the carried LSTM state within 1e-5 -- over three consecutive vector steps with an episode
-    reset in between (the state stays on the device between the calls)."""
+    actions, the carried LSTM state within 1e-5 -- over eight consecutive vector steps with episode
+    resets in between (the state stays on the device between the calls; from the fifth step on the library
+    replays the step from its CUDA graph)."""
     import torch
     from oracle import learner_oracle as lo
     from rltime_b200.learner import DeviceLearner
@@ -181,7 +182,7 @@ def test_acting_inference_matches_oracle():
         h = torch.zeros(E, U)
         c = torch.zeros(E, U)
         initials = np.ones(E, dtype=bool)
-        for step in range(3):
+        for step in range(8):
             obs = rs.randint(0, 256, (E, 4, 84, 84)).astype(np.uint8)
             state = pol.make_input_state(obs, initials)
             taus = torch.rand(E * Nq, generator=torch.Generator().manual_seed(step))
