@@ -75,6 +75,12 @@ CASES = {
         in_shape=(2, 16, 16), conv=[(8, 4, 2), (8, 3, 1)], lstm=16, fc=32, actions=3, nq=4,
         embed=8, dueling=True, B=3, T=6, P=0, n=2, gamma=0.99, double_q=True,
         rnn_bootstrap=True, vf_eps=None, clip_grad=40.0, adam_eps=1e-5, updates=2, rnn_steps=2),
+    # configs/ple_flappy_bird_iqn_lstm.json family: RGB frames without stacking, taller than wide (the shipped
+    # warp is 120 x 80 x 3), plus the extra-features tuple of the atari_iqn_lstm wrapper stack
+    "iqn_lstm_rgb_rect": dict(
+        in_shape=(3, 30, 20), conv=[(8, 8, 4), (8, 3, 1), (8, 2, 1)], lstm=16, fc=32, actions=2, nq=4,
+        embed=8, dueling=True, B=3, T=4, P=1, n=2, gamma=0.99, double_q=True,
+        rnn_bootstrap=True, vf_eps=1e-3, clip_grad=40.0, adam_eps=1e-5, updates=2, extra=4),
     # IQN with mean over time then sum over the batch
     "iqn_lstm_tsagg": dict(
         in_shape=(1, 12, 12), conv=[(4, 4, 2)], lstm=8, fc=8, actions=2, nq=4, embed=4,

@@ -508,10 +508,12 @@ def _one_update_vs_oracle(c, seed, mode="tf32"):
         raw["all_hx"] = (0.3 * rs.randn(S + n, B, U)).astype(np.float32)
         raw["all_cx"] = (0.3 * rs.randn(S + n, B, U)).astype(np.float32)
         raw["all_initials"] = (rs.rand(S + n, B) < 0.03).astype(np.float32)
+    if c.get("extra"):
+        raw["all_extra"] = rs.rand(S + n, B, c["extra"]).astype(np.float32)
     allt = {k: torch.from_numpy(v.copy()) for k, v in raw.items()}
 
     def st(lo_, hi):
-        s = {"x": allt["all_x"][lo_:hi]}
+        s = {"x": (allt["all_x"][lo_:hi], allt["all_extra"][lo_:hi]) if c.get("extra") else allt["all_x"][lo_:hi]}
         if U:
             s["layer1_state"] = {"hx": allt["all_hx"][lo_:hi], "cx": allt["all_cx"][lo_:hi],
                                  "initials": allt["all_initials"][lo_:hi]}
@@ -570,6 +572,18 @@ def test_learner_full_size_config2_cnn_iqn_vs_oracle():
              actions=6, nq=32, embed=64, dueling=True, B=32, T=1, P=0, n=3, gamma=0.99,
              double_q=True, rnn_bootstrap=False, vf_eps=None, clip_grad=10.0, adam_eps=1.5e-4)
     _one_update_vs_oracle(c, seed=22)
+
+
+@pytest.mark.gpu
+def test_learner_full_size_flappy_bird_rgb_frames_vs_oracle():
+    """configs/ple_flappy_bird_iqn_lstm.json at real size: unstacked RGB frames of 120 x 80 (3 input channels:
+    conv1 takes the im2col path, its patch rows are not 16-byte runs), the extra-features tuple (one-hot last
+    action + reward + timestep = A + 2 values) at the LSTM input, nature CNN -> 4224 features -> LSTM 512 ->
+    FC 512, Nq 32, B 32, T 20, n 3: TF32 path vs the torch oracle."""
+    c = dict(in_shape=(3, 120, 80), conv=[(32, 8, 4), (64, 4, 2), (64, 3, 1)], lstm=512, fc=512,
+             actions=2, nq=32, embed=64, dueling=True, B=32, T=20, P=0, n=3, gamma=0.99,
+             double_q=True, rnn_bootstrap=True, vf_eps=1e-3, clip_grad=40.0, adam_eps=1e-5, extra=4)
+    _one_update_vs_oracle(c, seed=23)
 
 
 @pytest.mark.gpu
