@@ -665,6 +665,209 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair persistent GEMM
+// k_gemm_tc_p<256> is bound by shared-memory bandwidth, not by the tensor pipe: a 128x256x8 TF32 MMA reads
+// 12 KB of operands from shared memory in the 176 cycles it takes at peak while TMA writes the next 12 KB
+// (140 B/clk against the SM's 128 B/clk; ncu: the MMA warp never waits for data or for an accumulator, the
+// producer and the epilogue warps wait for IT, tensor pipe 52 % active).  Here two CTAs of a cluster (the two
+// SMs of a TPC) share one 256 x 256 tile: tcgen05.mma.cta_group::2 with M = 256, each CTA holds its 128 rows of
+// A and HALF of the B tile (its 128 of the 256 columns) -- 32 KB per k-block and SM instead of 48 KB -- and the
+// accumulator rows of its half in its own TMEM.  K-major A and B only (the hidden-layer products), no split-K.
+//   full[s]       leader CTA's barrier: its producer arms it for both CTAs' bytes, both CTAs' TMA complete on it
+//   empty[s]      one per CTA, released by the leader's commit (multicast to both)
+//   tmem_full[a]  one per CTA (multicast commit); tmem_empty[a]: leader's, 2 x P_EPI_WARPS arrivals (the peer's
+//                 epilogue warps arrive remotely)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_cluster_addr, void* dst, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+constexpr int PAIR_BN = 256;          // columns of the pair's tile (each CTA stages 128 of them)
+template <int STAGES>
+struct SmemLayoutPair {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;
+  static constexpr int B_BYTES = (PAIR_BN / 2) * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SCRATCH_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = SCRATCH_OFFSET + P_EPI_WARPS * 32 * 36 * 4;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS_P, 1)
+k_gemm_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TcArgs a) {
+  using L = SmemLayoutPair<STAGES>;
+  constexpr int BN = PAIR_BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const rtk::GemmArgs& g = a.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int tiles_n = g.N / BN;
+  const int tiles_m = (g.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int total_tiles = tiles_n * tiles_m;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * P_EPI_WARPS);     // one arrive per epilogue warp of both CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();      // both CTAs' barriers exist before anything arrives on them from the peer
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const int nb = tile % tiles_n, mb = tile / tiles_n;
+        const int m0 = mb * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+        const int n0 = nb * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < a.num_kb_total; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+          const int k0 = kb * BLOCK_K;
+          tma_load_2d_pair(&tmA, bar, sa, k0, m0);
+          tma_load_2d_pair(&tmB, bar, sb, k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+      uint32_t it = 0;
+      int lt = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs, ++lt) {
+        const int acc = lt & 1;
+        mbar_wait(&tmem_empty[acc], ((lt >> 1) & 1) ^ 1);   // both epilogues have drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < a.num_kb_total; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t ad = make_smem_desc(sa + k * (UMMA_K * 4), 16, 1024, 2);
+            const uint64_t bd = make_smem_desc(sb + k * (UMMA_K * 4), 16, 1024, 2);
+            umma_tf32_pair(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[s]);
+        }
+        umma_commit_pair(&tmem_full[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* stage = reinterpret_cast<float*>(smem + L::SCRATCH_OFFSET) + (warp - 2) * (32 * 36);
+    int lt = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++lt) {
+      const int nb = tile % tiles_n, mb = tile / tiles_n;
+      const int m0 = mb * (2 * BLOCK_M) + (int)rank * BLOCK_M, n0 = nb * BN;
+      const int acc = lt & 1;
+      EpiArgs e;
+      e.C = g.C; e.ldc = g.ldc;
+      e.M = g.M; e.N = g.N; e.alpha = g.alpha; e.bias = g.bias; e.bias2 = g.bias2; e.relu = g.relu;
+      e.mask = g.mask; e.ldmask = g.ldmask; e.accumulate = g.accumulate; e.round_tf32 = a.round_tf32;
+      e.raw = 0;
+      const EpiWarp ew = epi_begin(e, lane, m0 + q * 32, n0, BN);
+      mbar_wait(&tmem_full[acc], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      constexpr int CHUNKS = BN / 32;
+      const int c_last = CHUNKS - 2 + half;
+#pragma unroll 1
+      for (int c = half; c < CHUNKS; c += 2) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+        if (c == c_last) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+        }
+        if (m0 + q * 32 < g.M) epilogue_chunk(e, ew, v, stage, lane, m0 + q * 32, n0 + c * 32);
+      }
+    }
+  }
+  __syncwarp();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();      // the peer may still read this CTA's operands / signal its barriers until here
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------- implicit-GEMM conv
 // Forward convolution without an im2col buffer: out[(img,oh,ow), f] = relu(sum_k A[..,k] W[f,k] + b)
 // where the A tile (128 output pixels x 32 taps) is gathered straight from the input by four

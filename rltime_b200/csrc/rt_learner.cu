@@ -58,6 +58,7 @@ struct GemmCtx {
   int force_bn = 0, force_stages = 0;   // tuning overrides (RT_TC_BN / RT_TC_STAGES, rt_gemm_bench)
   long long* dbg = nullptr;             // clock64 stamps of CTA 0 (rt_gemm_bench)
   int persistent = 1;                   // overlap epilogue with the next tile (k_gemm_tc_p)
+  int pair = 1;                         // CTA-pair (cta_group::2) kernel for the wide K-major products (RT_TC_PAIR=0: off)
   // split-K partials left in `ws` for a fused consumer (BPTT cell kernel) instead of k_splitk_reduce
   int defer_reduce = 0;
   int last_splits = 1;                  // splits of the last GEMM (1: the result is in C)
@@ -437,6 +438,49 @@ int launch_tc_p(const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs
   return RT_OK;
 }
 
+// CTA-pair variant (rttc::k_gemm_tc_pair): clusters of 2, as many pairs as the device can co-schedule
+int launch_tc_pair(const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs& a, int ctas, long long pair_tiles,
+                   cudaStream_t st, bool* launched) {
+  constexpr int STAGES = 5;
+  using L = rttc::SmemLayoutPair<STAGES>;
+  auto kern = rttc::k_gemm_tc_pair<STAGES>;
+  static int max_pairs = 0;      // 0: not asked yet; -1: clusters of 2 with this footprint are not available
+  *launched = false;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(rttc::NUM_THREADS_P);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (!max_pairs) {
+    RT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    cfg.gridDim = dim3(2);
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess) cudaGetLastError();
+    max_pairs = (e == cudaSuccess && n > 0) ? n : -1;
+  }
+  if (max_pairs < 0) return RT_OK;
+  long long pairs = ctas / 2;
+  if (pairs > max_pairs) pairs = max_pairs;
+  if (pairs > pair_tiles) pairs = pair_tiles;
+  if (pairs < 1) return RT_OK;
+  // the same number of waves on the fewest pairs (320 tiles: 5 waves on 64 pairs instead of 74): the last
+  // wave is full, and the SMs left over run the kernels of the other branches
+  const long long waves = (pair_tiles + pairs - 1) / pairs;
+  pairs = (pair_tiles + waves - 1) / waves;
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  RT_CUDA(cudaLaunchKernelEx(&cfg, kern, *ta, *tb, a));
+  rt::launch_counter()++;
+  *launched = true;
+  return RT_OK;
+}
+
 // persistent variant: deepest pipeline that fits one CTA per SM next to the epilogue scratch
 template <int BN, int A_MN, int B_MN>
 int launch_tc_persistent(const CUtensorMap* ta, const CUtensorMap* tb, const rttc::TcArgs& a, int ctas,
@@ -513,6 +557,18 @@ int gemm_tc(GemmCtx& cx, cudaStream_t st, rtk::GemmArgs g) {
   const long long total_tiles = (long long)tn * tm * splits;
   const bool persistent = cx.persistent && total_tiles > cx.num_sms;
   const int ctas = (int)(total_tiles < cx.num_sms ? total_tiles : cx.num_sms);
+  if (cx.pair && persistent && BN == 256 && !A_MN && !B_MN && splits == 1 && g.N % 256 == 0) {
+    // the wide K-major products: two SMs per 256 x 256 tile, each staging half of B
+    const CUtensorMap* tb2 = nullptr;
+    RT_TRY(get_tmap(cx, g.B, g.K, g.N, g.ldb, rttc::BLOCK_K, rttc::PAIR_BN / 2, 0, &tb2));
+    bool launched = false;
+    RT_TRY(launch_tc_pair(ta, tb2, a, ctas, (long long)cdiv(g.M, 2 * rttc::BLOCK_M) * (g.N / 256), st, &launched));
+    if (launched) {
+      cx.tc_launches++;
+      cx.last_splits = 1;
+      return RT_OK;
+    }
+  }
 #define RT_TC_CASE(bn, am, bm)                                                                  \
   if (BN == bn && A_MN == am && B_MN == bm)                                                     \
     rc = persistent ? launch_tc_persistent<bn, am, bm>(ta, tb, a, ctas, st)                     \
@@ -1896,6 +1952,7 @@ int rt_learner_create(const rt_model_desc* md, const rt_train_desc* td, int32_t 
   if (const char* e = getenv("RT_TC_BN")) h->gx.force_bn = atoi(e);
   if (const char* e = getenv("RT_TC_STAGES")) h->gx.force_stages = atoi(e);
   if (const char* e = getenv("RT_TC_PERSISTENT")) h->gx.persistent = atoi(e);
+  if (const char* e = getenv("RT_TC_PAIR")) h->gx.pair = atoi(e);
   size_t maxN = 4 * (size_t)(h->U ? h->U : 1);
   if (D > maxN) maxN = D;
   if (F > maxN) maxN = F;
@@ -2891,6 +2948,7 @@ extern "C" int rt_gemm_test(int32_t mode, int32_t M, int32_t N, int32_t K, int32
   GemmCtx cx;
   cx.mode = mode;
   if (const char* e = getenv("RT_TC_PERSISTENT")) cx.persistent = atoi(e);
+  if (const char* e = getenv("RT_TC_PAIR")) cx.pair = atoi(e);
   cx.ws_floats = (size_t)16 << 20;
   float *dA = nullptr, *dB = nullptr, *dC = nullptr, *dbias = nullptr;
   size_t nA = (size_t)M * K, nB = (size_t)N * K, nC = (size_t)M * N;
@@ -2930,6 +2988,7 @@ extern "C" int rt_gemm_bench(int32_t mode, int32_t M, int32_t N, int32_t K, int3
   GemmCtx cx;
   cx.mode = mode;
   if (const char* e = getenv("RT_TC_PERSISTENT")) cx.persistent = atoi(e);
+  if (const char* e = getenv("RT_TC_PAIR")) cx.pair = atoi(e);
   cx.force_bn = force_bn;
   cx.force_stages = force_stages;
   cx.ws_floats = (size_t)64 << 20;

@@ -22,6 +22,9 @@ CASES = [
     # > 148 tiles: the persistent, accumulator-double-buffered kernel (k_gemm_tc_p)
     (20480, 512, 512, 0, 1, 1), (20480, 512, 512, 0, 0, 0), (512, 512, 20480, 1, 0, 0),
     (20000, 500, 96, 0, 1, 1), (2048, 3136, 640, 1, 0, 0), (19000, 64, 576, 0, 1, 1),
+    # wide K-major products with >= 148 128x256 tiles: the CTA-pair kernel (k_gemm_tc_pair, cta_group::2),
+    # full size, a ragged last row tile whose second half is empty, and an odd number of 128-row tiles
+    (20480, 1024, 512, 0, 1, 1), (19000, 512, 256, 0, 1, 1), (19328, 512, 512, 0, 1, 0),
 ]
 
 
